@@ -1,0 +1,138 @@
+/* interdiff_b200.h -- C ABI of libinterdiff_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the InterDiff sampling hot path.  The reference
+ * reaches this path through Python module APIs, not an FFI; each entry point below names the
+ * reference interface it replaces (paths relative to /root/reference/interdiff).  The Python
+ * veneer in interdiff_b200/ binds these with ctypes (see INTEGRATION.md for the stub a
+ * maintainer of the reference would add).
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every function returns 0 on
+ * success and a non-zero status otherwise, with a message in idb_last_error(); nothing throws
+ * or aborts across the boundary.  `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream); all work is enqueued on it and no call synchronises unless documented.  Tensor
+ * arguments are DEVICE pointers to contiguous float32 unless marked `host_or_dev` (those are
+ * copied with cudaMemcpyDefault).  One handle per device; a handle is not re-entrant.
+ */
+#ifndef INTERDIFF_B200_H
+#define INTERDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct idb_handle idb_handle;
+
+int idb_version(void);
+int idb_create(idb_handle** out);                 /* on the current CUDA device */
+int idb_destroy(idb_handle* h);
+const char* idb_last_error(const idb_handle* h);
+long long idb_launch_count(const idb_handle* h);  /* kernels launched so far through h */
+int idb_set_gemm_backend(idb_handle* h, int backend); /* 0 = fp32 SIMT (debug/bisect), 1 = tcgen05 3xTF32 */
+
+/* ---- denoiser: MDM.forward / MDM._decode --------------------------------------------------
+ * replaces model/diffusion_smpl.py:239-246,226-237 (variant 0) and
+ * model/diffusion_skeleton.py:250-257,231-248 (variant 1), incl. TimestepEmbedder
+ * (model/layers.py:42-43), PositionalEncoding (:24-26), the 8-layer TransformerDecoder
+ * (:258-264; torch.nn.TransformerDecoderLayer for layers without `queries`,
+ * TransformerDecoderLayerQaN model/sublayers.py:311-375 otherwise). */
+typedef struct {
+    int variant;          /* 0 = SMPL (144 ch), 1 = skeleton (106 ch) */
+    int d_model;          /* 256 */
+    int n_heads;          /* 4 */
+    int d_ff;             /* 1024 (SMPL ckpt) / 256 (skeleton ckpt) */
+    int n_layers;         /* 8 */
+    int n_queries;        /* 10 */
+    int c_body;           /* 135 / 63 : channels fed to bodyEmbedding */
+    int c_obj;            /* 9 / 36   : channels fed to objEmbedding */
+    int c_extra;          /* 0 / 7    : trailing channels not embedded (skeleton 7-D pose) */
+    int n_points;         /* skeleton: object keypoints (12); SMPL: 0 */
+    int qan_mask;         /* bit i set => layer i is a QaN layer (0x7e for the shipped models) */
+    float rotary_offsets[3]; /* q_pos - k_pos for key slots (t-1, t, t+1): {1,0,-1} ('absolute'
+                                local-attention <=1.5) or {2,1,0} ('bucketed' >=1.6) */
+} idb_denoiser_config;
+
+int idb_denoiser_init(idb_handle* h, const idb_denoiser_config* cfg);
+/* Load one tensor by its reference state_dict name without the "model." prefix, e.g.
+ * "decoder.layers.3.queries"; data host_or_dev float32.  Unknown names are ignored (returns 0)
+ * so a whole checkpoint can be streamed in (strict loading is done by the Python veneer). */
+int idb_denoiser_load(idb_handle* h, const char* name, const float* data, const int64_t* shape, int ndim);
+int idb_denoiser_commit(idb_handle* h);           /* checks completeness, packs / folds weights */
+/* Bind a batch: cond = MDM._get_embeddings()[0], (Tm,B,D) seq-first as the reference passes it
+ * in model_kwargs['y']['cond']; zero_pose_obj (B,P,3) for variant 1 else NULL.  Precomputes the
+ * step-invariant cross-attention K/V of `cond` for every layer. */
+int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const float* cond, const float* zero_pose_obj, void* stream);
+/* x (B,1,C,T), timesteps (B) int64 device, out (B,1,C,T)  == MDM.forward(x, timesteps, y) */
+int idb_denoiser_forward(idb_handle* h, const float* x, const int64_t* timesteps, float* out, void* stream);
+
+/* ---- diffusion: SpacedDiffusion / GaussianDiffusion sampling ------------------------------
+ * replaces diffusion/gaussian_diffusion.py:160-197 (tables), 277-388 (p_mean_variance, START_X,
+ * FIXED_SMALL, inpainting blend :307-311), 253-275, 496-548 (p_sample), 598-736 (p_sample_loop),
+ * diffusion/respace.py:64-129 (timestep_map).  betas: the (re-spaced) float64 schedule on the
+ * host; timestep_map[n] the model timestep of step index i. */
+int idb_diffusion_init(idb_handle* h, const double* betas, const int64_t* timestep_map, int n);
+/* One p_sample at step index i: x_t -> x_{t-1}.  gt/mask (uint8, 1 = keep gt) may be NULL (no
+ * inpainting); noise is the eps drawn for this step; x0_out may be NULL. */
+int idb_p_sample(idb_handle* h, int i, const float* x_t, const float* noise, const float* gt,
+                 const uint8_t* mask, float* x_out, float* x0_out, void* stream);
+/* The two halves of p_sample around the denoised_fn hook (gaussian_diffusion.py:354-360):
+ * predict: x0 = inpaint(model(x_t, t_i));  finish: x_{t-1} = posterior(x0', x_t) + sigma*noise */
+int idb_p_sample_predict(idb_handle* h, int i, const float* x_t, const float* gt, const uint8_t* mask,
+                         float* x0_out, void* stream);
+int idb_p_sample_finish(idb_handle* h, int i, const float* x0, const float* x_t, const float* noise,
+                        float* x_out, void* stream);
+/* Whole loop: x_T = tape[0], eps of the k-th executed step = tape[k+1] (n+1 entries of the
+ * sample shape); steps i = n-1 .. 0.  correction != 0 runs the fused denoised_fn
+ * (idb_correction_apply) on the steps the reference's hook is active on (t <= 500, t % 50 == 0).
+ * Uses a CUDA graph per step when use_graph != 0. */
+int idb_p_sample_loop(idb_handle* h, const float* tape, const float* gt, const uint8_t* mask,
+                      int correction, int use_graph, float* x_out, void* stream);
+
+/* ---- SMPL-H linear blend skinning: SMPL_Layer.forward -------------------------------------
+ * replaces libsmpl/smplpytorch/pytorch/smpl_layer.py:72-175 (+ rodrigues_layer.py:13-52,
+ * tensutils.py:6-53).  Model arrays host_or_dev: v_template (V,3), shapedirs (V,3,NB),
+ * posedirs (V,3,(J-1)*9), J_regressor (J,V), weights (V,J), parents (J) int32, faces (Fc,3) int32. */
+int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const float* v_template, const float* shapedirs,
+                  const float* posedirs, const float* J_regressor, const float* weights,
+                  const int32_t* parents, const int32_t* faces);
+/* pose (F,J*3) axis-angle, betas (F,NB), trans (F,3) -> verts (F,V,3), jtr (F,J,3) (either may be NULL) */
+int idb_smplh_lbs(idb_handle* h, int F, const float* pose, const float* betas, const float* trans,
+                  float* verts, float* jtr, void* stream);
+
+/* ---- geometry helpers ---------------------------------------------------------------------
+ * vertex_normals: data/tools.py:4-39 (faces shared by all frames = body faces of idb_body_init)
+ * signed_nn:      tools.py:11-76 point2point_signed, one direction: for every query point the
+ *                 first-minimum squared-L2 nearest target (chamfer_distance ext, tools.py:45-47),
+ *                 dist = |q - t_nn| * sign(n_nn . (q - t_nn)) when target normals are given. */
+int idb_vertex_normals(idb_handle* h, int F, const float* verts, float* normals, void* stream);
+int idb_signed_nn(idb_handle* h, int F, int Pq, int Pt, const float* query, const float* target,
+                  const float* target_normals, float* signed_dist, int32_t* idx, float* vec, void* stream);
+/* rotation conversions used around the loop (pytorch3d.transforms 0.7.2 semantics):
+ * rot6d (n,6) -> axis-angle (n,3) == matrix_to_axis_angle(rotation_6d_to_matrix(.)) */
+int idb_rot6d_to_axis_angle(idb_handle* h, int n, const float* rot6d, float* aa, void* stream);
+
+/* ---- correction: ObjProjector.sample + denoised_fn ----------------------------------------
+ * replaces model/correction_smpl.py:79-138 (eval mode) and eval_smpl_short.py:84-130. */
+int idb_projector_init(idb_handle* h, int past_len, int future_len, int n_pre, int n_markers);
+int idb_projector_load(idb_handle* h, const char* name, const float* data, const int64_t* shape, int ndim);
+int idb_projector_commit(idb_handle* h);
+/* obj_angles (T,B,6), obj_trans (T,B,3), markers (T,B,P,3), contact (B,P) int32 -> out (T,B,9) */
+int idb_projector_sample(idb_handle* h, int T, int B, const float* obj_angles, const float* obj_trans,
+                         const float* markers, const int32_t* contact, float* out, void* stream);
+/* Bind the per-batch context of the hook: hand_pose (T,B,90), betas (T,B,10), obj_points (B,P,3),
+ * marker vertex ids (n_markers) int32, hand marker ids (n_hand) int32 (host_or_dev). */
+int idb_correction_bind(idb_handle* h, int B, int T, int past_len, int n_obj_points, const float* hand_pose,
+                        const float* betas, const float* obj_points, const int32_t* marker_ids,
+                        const int32_t* hand_marker_ids, int n_hand, void* stream);
+/* denoised_fn body for an ACTIVE step (the caller applies the t <= 500 && t % 50 == 0 gate):
+ * x0 (B,1,144,T) is corrected in place; gt is the inpainted motion; t is the timestep value used
+ * in the (t/1000) blend.  Optional debug outputs (may be NULL): condition (B) uint8,
+ * contact (B,P) int32, markers (T,B,P,3), o2h_signed (T*B,Pobj). */
+int idb_correction_apply(idb_handle* h, float* x0, const float* gt, int t, uint8_t* condition_out,
+                         int32_t* contact_out, float* markers_out, float* o2h_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,49 @@
+// Handle lifecycle of the C ABI (include/interdiff_b200.h).
+#include "common.cuh"
+
+void idb_denoiser_release(idb_handle* h);
+void idb_sampler_release(idb_handle* h);
+void idb_body_release(idb_handle* h);
+void idb_projector_release(idb_handle* h);
+int idb_denoiser_prepare_kernels(idb_handle* h);
+
+extern "C" int idb_version(void) { return 100; }
+
+extern "C" int idb_create(idb_handle** out) {
+    if (!out) return IDB_ERR_ARG;
+    *out = nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return IDB_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return IDB_ERR_CUDA;
+    idb_handle* h = new idb_handle();
+    h->device = dev;
+    h->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        // sm_100a-only library: refuse loudly rather than fall back
+        h->err = "interdiff_b200 needs a Blackwell (sm_100) device";
+        *out = h;
+        return IDB_ERR_CUDA;
+    }
+    int rc = idb_denoiser_prepare_kernels(h);
+    *out = h;
+    return rc;
+}
+
+extern "C" int idb_destroy(idb_handle* h) {
+    if (!h) return IDB_OK;
+    idb_sampler_release(h);
+    idb_denoiser_release(h);
+    idb_projector_release(h);
+    idb_body_release(h);
+    delete h;
+    return IDB_OK;
+}
+
+extern "C" const char* idb_last_error(const idb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" long long idb_launch_count(const idb_handle* h) { return h ? h->launches : 0; }
+extern "C" int idb_set_gemm_backend(idb_handle* h, int backend) {
+    if (!h || backend < 0 || backend > 1) return IDB_ERR_ARG;
+    h->gemm_backend = backend;
+    return IDB_OK;
+}

@@ -1,0 +1,126 @@
+// Shared internals of libinterdiff_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/interdiff_b200.h"
+
+#define IDB_OK 0
+#define IDB_ERR_CUDA 1
+#define IDB_ERR_ARG 2
+#define IDB_ERR_STATE 3
+
+struct DevTensor {
+    float* p = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel() const { size_t n = 1; for (auto s : shape) n *= (size_t)s; return n; }
+};
+
+struct StepParams {      // one row per diffusion step index i (device table)
+    long long t;         // timestep passed to the model (timestep_map[i])
+    float c1, c2;        // posterior_mean_coef1/2[i]
+    float sigma_nz;      // (i != 0) * exp(0.5 * posterior_log_variance_clipped[i])
+    float pad;
+};
+
+struct DenoiserLayer {
+    bool qan = false;
+    // standard self-attention
+    float *w_qkv = nullptr, *b_qkv = nullptr, *w_o = nullptr, *b_o = nullptr;
+    // QaN
+    float *qt = nullptr, *wk = nullptr;  // qt: [3*N][D] folded queries
+    // cross attention
+    float *w_qc = nullptr, *b_qc = nullptr, *w_kvc = nullptr, *b_kvc = nullptr, *w_oc = nullptr, *b_oc = nullptr;
+    float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+    float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr, *ln3w = nullptr, *ln3b = nullptr;
+    float* kv_mem = nullptr;  // [Tm*B][2D] cross-attention K|V of the bound memory
+};
+
+struct Denoiser {
+    idb_denoiser_config cfg{};
+    bool configured = false, committed = false;
+    std::map<std::string, DevTensor> raw;   // reference state_dict name -> device copy
+    std::vector<DenoiserLayer> layers;
+    std::vector<float*> owned;              // packed buffers to free
+    float *w_inT = nullptr, *b_in = nullptr;      // [C][D] k-major input embedding, summed bias
+    float *w_outT = nullptr, *b_out = nullptr;    // [D][Clin] k-major output heads
+    float *pe = nullptr; int pe_rows = 0;         // sinusoid table [rows][D]
+    float *te_w0T = nullptr, *te_b0 = nullptr, *te_w2T = nullptr, *te_b2 = nullptr;
+    // bound problem
+    int B = 0, T = 0, M = 0, Tm = 0;
+    float *cond = nullptr, *zero_pose = nullptr;
+    float *temb = nullptr, *h = nullptr, *h2 = nullptr, *qkv = nullptr, *att = nullptr, *ff = nullptr, *qc = nullptr;
+    long long* t_dev = nullptr;
+    std::vector<float*> bound;              // workspaces to free on rebind
+};
+
+struct Diffusion {
+    int n = 0;
+    std::vector<StepParams> host;
+    StepParams* tbl = nullptr;
+    int* counter = nullptr;   // device: current step index i
+};
+
+struct BodyModel;     // lbs.cu
+struct Projector;     // correction.cu
+struct Sampler;       // sampler.cu
+
+struct idb_handle {
+    std::string err;
+    int device = 0, sm_count = 148;
+    long long launches = 0;   // kernels launched through this handle (bench's gpu_launches)
+    int gemm_backend = 0;     // 0 = fp32 SIMT, 1 = tcgen05 3xTF32
+    Denoiser den;
+    Diffusion diff;
+    BodyModel* body = nullptr;
+    Projector* proj = nullptr;
+    Sampler* sampler = nullptr;
+};
+
+int idb_fail(idb_handle* h, int code, const char* fmt, ...);
+
+#define CUDA_TRY(h, expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return idb_fail((h), IDB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,              \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                    \
+    } while (0)
+
+#define LAUNCH_CHECK(h)                                                                     \
+    do {                                                                                    \
+        (h)->launches++;                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                \
+        if (_e != cudaSuccess)                                                              \
+            return idb_fail((h), IDB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",          \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                    \
+    } while (0)
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+// GEMM front door (gemm.cu): C[M,N] = epi(A[M,K] * W[N,K]^T)   (nn.Linear layout, all row-major)
+enum { EPI_BIAS = 1, EPI_GELU = 2, EPI_RES = 4, EPI_SILU = 8 };
+int idb_gemm(idb_handle* h, const float* A, int lda, const float* W, int ldw, const float* bias,
+             const float* res, int ldr, float* C, int ldc, int M, int N, int K, int epi, cudaStream_t st);
+
+// allocation helpers
+int idb_dev_alloc(idb_handle* h, float** p, size_t n_floats);
+int idb_upload(idb_handle* h, float** p, const float* host, size_t n_floats);

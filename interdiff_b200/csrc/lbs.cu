@@ -1,0 +1,296 @@
+// SMPL-H linear blend skinning (fp32).  Replaces reference
+// libsmpl/smplpytorch/pytorch/smpl_layer.py:72-175, rodrigues_layer.py:13-52, tensutils.py:6-53.
+//
+// Data layout in HBM (built once in idb_body_init):
+//   posedirsT  [Kp][3][V]   k-major so a warp reads 32 consecutive vertices of one basis row
+//   shapedirsT [NB][3][V]
+//   v_templT   [3][V]
+//   weightsT   [J][V]
+//   J_templ [J][3], J_shape [J][3][NB]: the joint regressor folded through the shape blend,
+//     J_rest = J_reg (v_t + S beta) = J_reg v_t + (J_reg S) beta   (exact algebra, computed in
+//     float64 on the host; the reference evaluates the left form in fp32)
+// Two kernels per call:
+//   k_lbs_pose  (one block per frame): Rodrigues (quaternion route), rest joints, kinematic chain,
+//               A_j = G_j - [0 | G_j J_j], pose_map = vec(R_1..R_{J-1} - I)
+//   k_lbs_skin  (vertex tile x frame group): v_posed = v_t + S beta + P pose_map; T = sum_j w_j A_j;
+//               verts = T [v_posed; 1] + trans.  Each block keeps FB frames of pose_map / A in
+//               shared memory and streams the bases once for all of them.
+#include "common.cuh"
+#include "body.cuh"
+
+namespace {
+
+constexpr int FB = 16;  // frames per skinning block
+
+__global__ void k_lbs_pose(const float* __restrict__ pose, const float* __restrict__ betas, const float* __restrict__ trans,
+                           const float* __restrict__ J_templ, const float* __restrict__ J_shape,
+                           const int* __restrict__ parents, float* __restrict__ Aout, float* __restrict__ pose_map,
+                           float* __restrict__ jtr, int J, int NB, int Kp) {
+    extern __shared__ float sm[];
+    float* sR = sm;            // [J][9]
+    float* sJ = sR + J * 9;    // [J][3]
+    float* sG = sJ + J * 3;    // [J][12]
+    const int f = blockIdx.x, j = threadIdx.x;
+    if (j < J) {
+        // batch_rodrigues (rodrigues_layer.py:41-52): angle = |aa + 1e-8|
+        const float ax = pose[(size_t)f * J * 3 + j * 3 + 0], ay = pose[(size_t)f * J * 3 + j * 3 + 1], az = pose[(size_t)f * J * 3 + j * 3 + 2];
+        const float bx = ax + 1e-8f, by = ay + 1e-8f, bz = az + 1e-8f;
+        const float angle = sqrtf(bx * bx + by * by + bz * bz);
+        const float nx = ax / angle, ny = ay / angle, nz = az / angle;
+        const float half = angle * 0.5f;
+        const float c = cosf(half), s = sinf(half);
+        float qw = c, qx = s * nx, qy = s * ny, qz = s * nz;
+        const float qn = sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
+        qw /= qn; qx /= qn; qy /= qn; qz /= qn;
+        const float w2 = qw * qw, x2 = qx * qx, y2 = qy * qy, z2 = qz * qz;
+        const float wx = qw * qx, wy = qw * qy, wz = qw * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz;
+        float* R = sR + j * 9;
+        R[0] = w2 + x2 - y2 - z2; R[1] = 2 * xy - 2 * wz;   R[2] = 2 * wy + 2 * xz;
+        R[3] = 2 * wz + 2 * xy;   R[4] = w2 - x2 + y2 - z2; R[5] = 2 * yz - 2 * wx;
+        R[6] = 2 * xz - 2 * wy;   R[7] = 2 * wx + 2 * yz;   R[8] = w2 - x2 - y2 + z2;
+        for (int c3 = 0; c3 < 3; c3++) {
+            float v = J_templ[j * 3 + c3];
+            for (int b = 0; b < NB; b++) v = fmaf(J_shape[(j * 3 + c3) * NB + b], betas[(size_t)f * NB + b], v);
+            sJ[j * 3 + c3] = v;
+        }
+        if (j >= 1)
+            for (int e = 0; e < 9; e++)
+                pose_map[(size_t)f * Kp + (j - 1) * 9 + e] = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+    }
+    __syncthreads();
+    if (j == 0) {
+        // kinematic chain (smpl_layer.py:119-130), sequential: parents precede children
+        for (int i = 0; i < J; i++) {
+            const float* R = sR + i * 9;
+            float* G = sG + i * 12;
+            if (i == 0) {
+                for (int r = 0; r < 3; r++) { G[r * 4 + 0] = R[r * 3]; G[r * 4 + 1] = R[r * 3 + 1]; G[r * 4 + 2] = R[r * 3 + 2]; G[r * 4 + 3] = sJ[r]; }
+            } else {
+                const int p = parents[i];
+                const float* Gp = sG + p * 12;
+                const float tx = sJ[i * 3] - sJ[p * 3], ty = sJ[i * 3 + 1] - sJ[p * 3 + 1], tz = sJ[i * 3 + 2] - sJ[p * 3 + 2];
+                for (int r = 0; r < 3; r++) {
+                    const float g0 = Gp[r * 4], g1 = Gp[r * 4 + 1], g2 = Gp[r * 4 + 2], g3 = Gp[r * 4 + 3];
+                    G[r * 4 + 0] = g0 * R[0] + g1 * R[3] + g2 * R[6];
+                    G[r * 4 + 1] = g0 * R[1] + g1 * R[4] + g2 * R[7];
+                    G[r * 4 + 2] = g0 * R[2] + g1 * R[5] + g2 * R[8];
+                    G[r * 4 + 3] = g0 * tx + g1 * ty + g2 * tz + g3;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (j < J) {
+        const float* G = sG + j * 12;
+        float* A = Aout + ((size_t)f * J + j) * 12;
+        const float jx = sJ[j * 3], jy = sJ[j * 3 + 1], jz = sJ[j * 3 + 2];
+        for (int r = 0; r < 3; r++) {
+            A[r * 4 + 0] = G[r * 4 + 0]; A[r * 4 + 1] = G[r * 4 + 1]; A[r * 4 + 2] = G[r * 4 + 2];
+            A[r * 4 + 3] = G[r * 4 + 3] - (G[r * 4] * jx + G[r * 4 + 1] * jy + G[r * 4 + 2] * jz);
+        }
+        if (jtr)
+            for (int r = 0; r < 3; r++) jtr[((size_t)f * J + j) * 3 + r] = G[r * 4 + 3] + trans[(size_t)f * 3 + r];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_lbs_skin(const float* __restrict__ posedirsT, const float* __restrict__ shapedirsT, const float* __restrict__ v_templT,
+           const float* __restrict__ weightsT, const float* __restrict__ Ain, const float* __restrict__ pose_map,
+           const float* __restrict__ betas, const float* __restrict__ trans, float* __restrict__ verts,
+           int F, int V, int J, int NB, int Kp) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_pm = sm;                  // [Kp][FB]
+    float* s_A = s_pm + Kp * FB;       // [FB][J][12]
+    float* s_b = s_A + FB * J * 12;    // [NB][FB]
+    float* s_t = s_b + NB * FB;        // [FB][3]
+    const int f0 = blockIdx.y * FB, tid = threadIdx.x;
+    const int nf = min(FB, F - f0);
+    for (int i = tid; i < Kp * FB; i += 256) {
+        const int k = i / FB, ff = i % FB;
+        s_pm[i] = ff < nf ? pose_map[(size_t)(f0 + ff) * Kp + k] : 0.f;
+    }
+    for (int i = tid; i < FB * J * 12; i += 256) s_A[i] = (i / (J * 12)) < nf ? Ain[(size_t)f0 * J * 12 + i] : 0.f;
+    for (int i = tid; i < NB * FB; i += 256) {
+        const int b = i / FB, ff = i % FB;
+        s_b[i] = ff < nf ? betas[(size_t)(f0 + ff) * NB + b] : 0.f;
+    }
+    for (int i = tid; i < FB * 3; i += 256) s_t[i] = (i / 3) < nf ? trans[(size_t)f0 * 3 + i] : 0.f;
+    __syncthreads();
+    const int v = blockIdx.x * 256 + tid;
+    if (v >= V) return;
+
+    float acc[3][FB];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float t0 = v_templT[(size_t)c * V + v];
+#pragma unroll
+        for (int ff = 0; ff < FB; ff++) acc[c][ff] = t0;
+    }
+    for (int b = 0; b < NB; b++) {
+        const float s0 = shapedirsT[((size_t)b * 3 + 0) * V + v], s1 = shapedirsT[((size_t)b * 3 + 1) * V + v],
+                    s2 = shapedirsT[((size_t)b * 3 + 2) * V + v];
+#pragma unroll
+        for (int ff = 0; ff < FB; ff++) {
+            const float bb = s_b[b * FB + ff];
+            acc[0][ff] = fmaf(s0, bb, acc[0][ff]); acc[1][ff] = fmaf(s1, bb, acc[1][ff]); acc[2][ff] = fmaf(s2, bb, acc[2][ff]);
+        }
+    }
+#pragma unroll 2
+    for (int k = 0; k < Kp; k++) {
+        const float p0 = __ldg(posedirsT + ((size_t)k * 3 + 0) * V + v), p1 = __ldg(posedirsT + ((size_t)k * 3 + 1) * V + v),
+                    p2 = __ldg(posedirsT + ((size_t)k * 3 + 2) * V + v);
+        const float4* pm4 = reinterpret_cast<const float4*>(s_pm + k * FB);
+#pragma unroll
+        for (int q = 0; q < FB / 4; q++) {
+            const float4 m = pm4[q];
+            acc[0][q * 4 + 0] = fmaf(p0, m.x, acc[0][q * 4 + 0]); acc[1][q * 4 + 0] = fmaf(p1, m.x, acc[1][q * 4 + 0]); acc[2][q * 4 + 0] = fmaf(p2, m.x, acc[2][q * 4 + 0]);
+            acc[0][q * 4 + 1] = fmaf(p0, m.y, acc[0][q * 4 + 1]); acc[1][q * 4 + 1] = fmaf(p1, m.y, acc[1][q * 4 + 1]); acc[2][q * 4 + 1] = fmaf(p2, m.y, acc[2][q * 4 + 1]);
+            acc[0][q * 4 + 2] = fmaf(p0, m.z, acc[0][q * 4 + 2]); acc[1][q * 4 + 2] = fmaf(p1, m.z, acc[1][q * 4 + 2]); acc[2][q * 4 + 2] = fmaf(p2, m.z, acc[2][q * 4 + 2]);
+            acc[0][q * 4 + 3] = fmaf(p0, m.w, acc[0][q * 4 + 3]); acc[1][q * 4 + 3] = fmaf(p1, m.w, acc[1][q * 4 + 3]); acc[2][q * 4 + 3] = fmaf(p2, m.w, acc[2][q * 4 + 3]);
+        }
+    }
+    // skinning, one frame at a time (keeps the 12-entry transform in registers)
+    for (int ff = 0; ff < nf; ff++) {
+        float Tm[12];
+#pragma unroll
+        for (int e = 0; e < 12; e++) Tm[e] = 0.f;
+        const float4* A4 = reinterpret_cast<const float4*>(s_A + (size_t)ff * J * 12);
+        for (int jn = 0; jn < J; jn++) {
+            const float w = __ldg(weightsT + (size_t)jn * V + v);
+            const float4 a0 = A4[jn * 3], a1 = A4[jn * 3 + 1], a2 = A4[jn * 3 + 2];
+            Tm[0] = fmaf(w, a0.x, Tm[0]); Tm[1] = fmaf(w, a0.y, Tm[1]); Tm[2] = fmaf(w, a0.z, Tm[2]); Tm[3] = fmaf(w, a0.w, Tm[3]);
+            Tm[4] = fmaf(w, a1.x, Tm[4]); Tm[5] = fmaf(w, a1.y, Tm[5]); Tm[6] = fmaf(w, a1.z, Tm[6]); Tm[7] = fmaf(w, a1.w, Tm[7]);
+            Tm[8] = fmaf(w, a2.x, Tm[8]); Tm[9] = fmaf(w, a2.y, Tm[9]); Tm[10] = fmaf(w, a2.z, Tm[10]); Tm[11] = fmaf(w, a2.w, Tm[11]);
+        }
+        // acc[.][ff] with a runtime ff: select through a small unrolled switch to stay in registers
+        float px = 0.f, py = 0.f, pz = 0.f;
+#pragma unroll
+        for (int q = 0; q < FB; q++)
+            if (q == ff) { px = acc[0][q]; py = acc[1][q]; pz = acc[2][q]; }
+        float* o = verts + ((size_t)(f0 + ff) * V + v) * 3;
+        o[0] = (Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3]) + s_t[ff * 3 + 0];
+        o[1] = (Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7]) + s_t[ff * 3 + 1];
+        o[2] = (Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11]) + s_t[ff * 3 + 2];
+    }
+}
+
+}  // namespace
+
+void idb_body_release(idb_handle* h) {
+    if (!h->body) return;
+    BodyModel& m = *h->body;
+    for (void* p : m.owned) cudaFree(p);
+    if (m.A) { cudaFree(m.A); cudaFree(m.pose_map); }
+    delete h->body;
+    h->body = nullptr;
+}
+
+extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const float* v_template, const float* shapedirs,
+                             const float* posedirs, const float* J_regressor, const float* weights,
+                             const int32_t* parents, const int32_t* faces) {
+    if (!h || !v_template || !shapedirs || !posedirs || !J_regressor || !weights || !parents) return IDB_ERR_ARG;
+    if (V <= 0 || J <= 1 || J > 64 || NB <= 0 || NB > 16) return idb_fail(h, IDB_ERR_ARG, "bad body model dimensions");
+    idb_body_release(h);
+    h->body = new BodyModel();
+    BodyModel& m = *h->body;
+    m.V = V; m.J = J; m.NB = NB; m.Fc = Fc; m.Kp = (J - 1) * 9;
+    const int Kp = m.Kp;
+    auto pull = [&](const void* src, size_t bytes, void* dst) { return cudaMemcpy(dst, src, bytes, cudaMemcpyDefault); };
+    std::vector<float> vt((size_t)V * 3), sd((size_t)V * 3 * NB), pd((size_t)V * 3 * Kp), jr((size_t)J * V), w((size_t)V * J);
+    std::vector<int32_t> par(J);
+    CUDA_TRY(h, pull(v_template, vt.size() * 4, vt.data())); CUDA_TRY(h, pull(shapedirs, sd.size() * 4, sd.data()));
+    CUDA_TRY(h, pull(posedirs, pd.size() * 4, pd.data())); CUDA_TRY(h, pull(J_regressor, jr.size() * 4, jr.data()));
+    CUDA_TRY(h, pull(weights, w.size() * 4, w.data())); CUDA_TRY(h, pull(parents, par.size() * 4, par.data()));
+    for (int i = 1; i < J; i++)
+        if (par[i] < 0 || par[i] >= i) return idb_fail(h, IDB_ERR_ARG, "parents must precede children (joint %d)", i);
+    std::vector<float> vtT((size_t)3 * V), sdT((size_t)NB * 3 * V), pdT((size_t)Kp * 3 * V), wT((size_t)J * V);
+    for (int v = 0; v < V; v++)
+        for (int c = 0; c < 3; c++) {
+            vtT[(size_t)c * V + v] = vt[(size_t)v * 3 + c];
+            for (int b = 0; b < NB; b++) sdT[((size_t)b * 3 + c) * V + v] = sd[((size_t)v * 3 + c) * NB + b];
+            for (int k = 0; k < Kp; k++) pdT[((size_t)k * 3 + c) * V + v] = pd[((size_t)v * 3 + c) * Kp + k];
+        }
+    for (int v = 0; v < V; v++) for (int j = 0; j < J; j++) wT[(size_t)j * V + v] = w[(size_t)v * J + j];
+    std::vector<float> Jt((size_t)J * 3), Js((size_t)J * 3 * NB);
+    for (int j = 0; j < J; j++)
+        for (int c = 0; c < 3; c++) {
+            double a = 0;
+            for (int v = 0; v < V; v++) a += (double)jr[(size_t)j * V + v] * vt[(size_t)v * 3 + c];
+            Jt[j * 3 + c] = (float)a;
+            for (int b = 0; b < NB; b++) {
+                double s = 0;
+                for (int v = 0; v < V; v++) s += (double)jr[(size_t)j * V + v] * sd[((size_t)v * 3 + c) * NB + b];
+                Js[((size_t)j * 3 + c) * NB + b] = (float)s;
+            }
+        }
+    auto up = [&](const void* src, size_t bytes, void** dst) {
+        cudaError_t e = cudaMalloc(dst, bytes ? bytes : 4);
+        if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) m.owned.push_back(*dst);
+        return e;
+    };
+    CUDA_TRY(h, up(vtT.data(), vtT.size() * 4, (void**)&m.v_templT)); CUDA_TRY(h, up(sdT.data(), sdT.size() * 4, (void**)&m.shapedirsT));
+    CUDA_TRY(h, up(pdT.data(), pdT.size() * 4, (void**)&m.posedirsT)); CUDA_TRY(h, up(wT.data(), wT.size() * 4, (void**)&m.weightsT));
+    CUDA_TRY(h, up(Jt.data(), Jt.size() * 4, (void**)&m.J_templ)); CUDA_TRY(h, up(Js.data(), Js.size() * 4, (void**)&m.J_shape));
+    CUDA_TRY(h, up(par.data(), par.size() * 4, (void**)&m.parents));
+    if (faces && Fc > 0) {
+        std::vector<int32_t> fc((size_t)Fc * 3);
+        CUDA_TRY(h, pull(faces, fc.size() * 4, fc.data()));
+        // vertex -> incident (face, corner) list in the reference's accumulation order
+        // (data/tools.py:26-34: all corner-1 adds, then corner-2, then corner-0; index_add_ is
+        // sequential in face order on CPU)
+        std::vector<int32_t> off(V + 1, 0), ent;
+        const int order[3] = {1, 2, 0};
+        for (int pass = 0; pass < 3; pass++)
+            for (int f = 0; f < Fc; f++) {
+                int vv = fc[(size_t)f * 3 + order[pass]];
+                if (vv < 0 || vv >= V) return idb_fail(h, IDB_ERR_ARG, "face index out of range");
+                off[vv + 1]++;
+            }
+        for (int v = 0; v < V; v++) off[v + 1] += off[v];
+        ent.resize((size_t)Fc * 3);
+        std::vector<int32_t> cur(off.begin(), off.end() - 1);
+        for (int pass = 0; pass < 3; pass++)
+            for (int f = 0; f < Fc; f++) {
+                int vv = fc[(size_t)f * 3 + order[pass]];
+                ent[cur[vv]++] = f * 4 + order[pass];
+            }
+        CUDA_TRY(h, up(fc.data(), fc.size() * 4, (void**)&m.faces));
+        CUDA_TRY(h, up(off.data(), off.size() * 4, (void**)&m.vf_off));
+        CUDA_TRY(h, up(ent.data(), ent.size() * 4, (void**)&m.vf_ent));
+    }
+    const int smem_skin = (int)sizeof(float) * (Kp * FB + FB * J * 12 + NB * FB + FB * 3);
+    CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_skin));
+    return IDB_OK;
+}
+
+int idb_body_workspace(idb_handle* h, int F) {
+    BodyModel& m = *h->body;
+    if (F <= m.capF) return IDB_OK;
+    if (m.A) { cudaFree(m.A); cudaFree(m.pose_map); }
+    CUDA_TRY(h, cudaMalloc((void**)&m.A, sizeof(float) * (size_t)F * m.J * 12));
+    CUDA_TRY(h, cudaMalloc((void**)&m.pose_map, sizeof(float) * (size_t)F * m.Kp));
+    m.capF = F;
+    return IDB_OK;
+}
+
+extern "C" int idb_smplh_lbs(idb_handle* h, int F, const float* pose, const float* betas, const float* trans,
+                             float* verts, float* jtr, void* stream) {
+    if (!h || !pose || !betas || !trans || F <= 0) return IDB_ERR_ARG;
+    if (!h->body) return idb_fail(h, IDB_ERR_STATE, "idb_body_init first");
+    BodyModel& m = *h->body;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = idb_body_workspace(h, F);
+    if (rc) return rc;
+    const size_t smem_pose = sizeof(float) * (size_t)m.J * (9 + 3 + 12);
+    k_lbs_pose<<<F, 64, smem_pose, st>>>(pose, betas, trans, m.J_templ, m.J_shape, m.parents, m.A, m.pose_map, jtr, m.J, m.NB, m.Kp);
+    LAUNCH_CHECK(h);
+    if (verts) {
+        const size_t smem_skin = sizeof(float) * ((size_t)m.Kp * FB + (size_t)FB * m.J * 12 + (size_t)m.NB * FB + FB * 3);
+        dim3 grid((m.V + 255) / 256, (F + FB - 1) / FB);
+        k_lbs_skin<<<grid, 256, smem_skin, st>>>(m.posedirsT, m.shapedirsT, m.v_templT, m.weightsT, m.A, m.pose_map, betas, trans,
+                                                  verts, F, m.V, m.J, m.NB, m.Kp);
+        LAUNCH_CHECK(h);
+    }
+    return IDB_OK;
+}

@@ -1,0 +1,246 @@
+// Diffusion process: ancestral DDPM sampling (START_X, FIXED_SMALL) around the denoiser.
+// Replaces reference diffusion/gaussian_diffusion.py:160-197 (coefficient tables, float64 on the
+// host exactly like the reference, then .float()), :253-275, :277-388, :496-548, :598-736 and
+// diffusion/respace.py:64-129.
+//
+// Every per-step scalar lives in a device table indexed by a device-side step counter, so one
+// captured CUDA graph of a step can be replayed for every timestep without host patching.
+#include "common.cuh"
+
+int idb_denoiser_run(idb_handle* h, const float* x, const long long* t_dev, const float* gt, const unsigned char* mask,
+                     float* out, cudaStream_t st);
+int idb_denoiser_fill_t(idb_handle* h, cudaStream_t st);
+int idb_correction_apply_dev(idb_handle* h, float* x0, const float* gt, int t, cudaStream_t st);
+
+struct Sampler {
+    float *x_a = nullptr, *x_b = nullptr, *x0 = nullptr;
+    size_t numel = 0;
+    cudaGraphExec_t step_graph = nullptr;     // predict + finish for a plain step
+    cudaGraphExec_t predict_graph = nullptr;  // predict only (correction steps)
+    const float* g_gt = nullptr; const unsigned char* g_mask = nullptr; const float* g_tape = nullptr;
+    int gB = 0, gT = 0;
+    int launches_per_step = 0, launches_per_predict = 0;
+};
+
+namespace {
+
+__global__ void k_set_counter(int* counter, int v) { *counter = v; }
+__global__ void k_dec_counter(int* counter) { *counter -= 1; }
+
+// x_{t-1} = c1[i] x0 + c2[i] x_t + 1[i != 0] exp(0.5 logvar[i]) eps   (gaussian_diffusion.py:253-275,537-547)
+// noise pointer: explicit, or tape + (n_steps - i) * numel when tape_mode (eps of the k-th step is tape[k+1]).
+__global__ void k_posterior(const float* __restrict__ x0, const float* xt, const float* __restrict__ noise,
+                            const StepParams* __restrict__ tbl, const int* __restrict__ counter, int n_steps,
+                            int tape_mode, float* out, size_t numel) {
+    const int i = *counter;
+    const StepParams p = tbl[i];
+    const float* nz = tape_mode ? noise + (size_t)(n_steps - i) * numel : noise;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel; e += (size_t)gridDim.x * blockDim.x) {
+        const float mean = p.c1 * x0[e] + p.c2 * xt[e];
+        out[e] = mean + p.sigma_nz * nz[e];
+    }
+}
+
+}  // namespace
+
+extern "C" int idb_diffusion_init(idb_handle* h, const double* betas, const int64_t* timestep_map, int n) {
+    if (!h || !betas || n <= 0) return IDB_ERR_ARG;
+    Diffusion& df = h->diff;
+    // float64 tables exactly as GaussianDiffusion.__init__ (gaussian_diffusion.py:160-197)
+    std::vector<double> ac(n), ac_prev(n), post_var(n), logvar(n), c1(n), c2(n);
+    double prod = 1.0;
+    for (int i = 0; i < n; i++) {
+        if (!(betas[i] > 0 && betas[i] <= 1)) return idb_fail(h, IDB_ERR_ARG, "betas must be in (0,1]");
+        prod *= (1.0 - betas[i]);
+        ac[i] = prod;
+        ac_prev[i] = i == 0 ? 1.0 : ac[i - 1];
+    }
+    for (int i = 0; i < n; i++) {
+        post_var[i] = betas[i] * (1.0 - ac_prev[i]) / (1.0 - ac[i]);
+        c1[i] = betas[i] * std::sqrt(ac_prev[i]) / (1.0 - ac[i]);
+        c2[i] = (1.0 - ac_prev[i]) * std::sqrt(1.0 - betas[i]) / (1.0 - ac[i]);
+    }
+    for (int i = 0; i < n; i++) logvar[i] = std::log(i == 0 ? post_var[n > 1 ? 1 : 0] : post_var[i]);
+    df.host.resize(n);
+    for (int i = 0; i < n; i++) {
+        StepParams& p = df.host[i];
+        p.t = timestep_map ? (long long)timestep_map[i] : i;
+        p.c1 = (float)c1[i];
+        p.c2 = (float)c2[i];
+        // reference: th.exp(0.5 * float32(logvar)) evaluated in float32
+        const float lv = (float)logvar[i];
+        p.sigma_nz = i == 0 ? 0.0f : expf(0.5f * lv);
+        p.pad = 0.f;
+    }
+    if (df.tbl) cudaFree(df.tbl);
+    if (!df.counter) CUDA_TRY(h, cudaMalloc((void**)&df.counter, sizeof(int)));
+    CUDA_TRY(h, cudaMalloc((void**)&df.tbl, sizeof(StepParams) * n));
+    CUDA_TRY(h, cudaMemcpy(df.tbl, df.host.data(), sizeof(StepParams) * n, cudaMemcpyHostToDevice));
+    df.n = n;
+    if (h->sampler) {
+        if (h->sampler->step_graph) cudaGraphExecDestroy(h->sampler->step_graph);
+        if (h->sampler->predict_graph) cudaGraphExecDestroy(h->sampler->predict_graph);
+        h->sampler->step_graph = h->sampler->predict_graph = nullptr;
+    }
+    return IDB_OK;
+}
+
+static int sampler_ready(idb_handle* h, size_t numel) {
+    if (!h->diff.n) return idb_fail(h, IDB_ERR_STATE, "idb_diffusion_init first");
+    if (!h->den.B) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_bind first");
+    if (!h->sampler) h->sampler = new Sampler();
+    Sampler& s = *h->sampler;
+    if (s.numel != numel) {
+        if (s.x_a) { cudaFree(s.x_a); cudaFree(s.x_b); cudaFree(s.x0); }
+        CUDA_TRY(h, cudaMalloc((void**)&s.x_a, numel * sizeof(float)));
+        CUDA_TRY(h, cudaMalloc((void**)&s.x_b, numel * sizeof(float)));
+        CUDA_TRY(h, cudaMalloc((void**)&s.x0, numel * sizeof(float)));
+        s.numel = numel;
+        if (s.step_graph) { cudaGraphExecDestroy(s.step_graph); s.step_graph = nullptr; }
+        if (s.predict_graph) { cudaGraphExecDestroy(s.predict_graph); s.predict_graph = nullptr; }
+    }
+    return IDB_OK;
+}
+
+static size_t sample_numel(idb_handle* h) {
+    const idb_denoiser_config& c = h->den.cfg;
+    return (size_t)h->den.B * (c.c_body + c.c_obj + c.c_extra) * h->den.T;
+}
+
+// predict with the device counter already set
+static int predict_dev(idb_handle* h, const float* x_t, const float* gt, const unsigned char* mask, float* x0, cudaStream_t st) {
+    int rc = idb_denoiser_fill_t(h, st);
+    if (rc) return rc;
+    return idb_denoiser_run(h, x_t, h->den.t_dev, gt, mask, x0, st);
+}
+
+static int finish_dev(idb_handle* h, const float* x0, const float* x_t, const float* noise, int tape_mode, float* out, cudaStream_t st) {
+    const size_t n = sample_numel(h);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_posterior<<<blocks, 256, 0, st>>>(x0, x_t, noise, h->diff.tbl, h->diff.counter, h->diff.n, tape_mode, out, n);
+    LAUNCH_CHECK(h);
+    return IDB_OK;
+}
+
+extern "C" int idb_p_sample_predict(idb_handle* h, int i, const float* x_t, const float* gt, const uint8_t* mask, float* x0_out, void* stream) {
+    if (!h || !x_t || !x0_out) return IDB_ERR_ARG;
+    if (i < 0 || i >= h->diff.n) return idb_fail(h, IDB_ERR_ARG, "step index out of range");
+    if ((gt == nullptr) != (mask == nullptr)) return idb_fail(h, IDB_ERR_ARG, "gt and mask must be given together");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_set_counter<<<1, 1, 0, st>>>(h->diff.counter, i);
+    LAUNCH_CHECK(h);
+    return predict_dev(h, x_t, gt, mask, x0_out, st);
+}
+
+extern "C" int idb_p_sample_finish(idb_handle* h, int i, const float* x0, const float* x_t, const float* noise, float* x_out, void* stream) {
+    if (!h || !x0 || !x_t || !noise || !x_out) return IDB_ERR_ARG;
+    if (i < 0 || i >= h->diff.n) return idb_fail(h, IDB_ERR_ARG, "step index out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_set_counter<<<1, 1, 0, st>>>(h->diff.counter, i);
+    LAUNCH_CHECK(h);
+    return finish_dev(h, x0, x_t, noise, 0, x_out, st);
+}
+
+extern "C" int idb_p_sample(idb_handle* h, int i, const float* x_t, const float* noise, const float* gt, const uint8_t* mask,
+                            float* x_out, float* x0_out, void* stream) {
+    if (!h || !x_t || !noise || !x_out) return IDB_ERR_ARG;
+    int rc = sampler_ready(h, sample_numel(h));
+    if (rc) return rc;
+    float* x0 = x0_out ? x0_out : h->sampler->x0;
+    if ((rc = idb_p_sample_predict(h, i, x_t, gt, mask, x0, stream))) return rc;
+    return finish_dev(h, x0, x_t, noise, 0, x_out, (cudaStream_t)stream);
+}
+
+extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* gt, const uint8_t* mask, int correction,
+                                 int use_graph, float* x_out, void* stream) {
+    if (!h || !tape || !x_out) return IDB_ERR_ARG;
+    if ((gt == nullptr) != (mask == nullptr)) return idb_fail(h, IDB_ERR_ARG, "gt and mask must be given together");
+    const size_t numel = sample_numel(h);
+    int rc = sampler_ready(h, numel);
+    if (rc) return rc;
+    Sampler& s = *h->sampler;
+    Diffusion& df = h->diff;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = df.n;
+    // The per-step graphs read x from s.x_a and write s.x_b, then the roles swap: capture two
+    // parities instead (a -> b, b -> a) by capturing ONE graph that does a full a -> b -> a pair?
+    // Simpler and just as cheap: the graph always reads x_a and writes x_a (x0 is a separate
+    // buffer, and the posterior is elementwise, so in-place is safe).
+    CUDA_TRY(h, cudaMemcpyAsync(s.x_a, tape, numel * sizeof(float), cudaMemcpyDefault, st));
+    k_set_counter<<<1, 1, 0, st>>>(df.counter, n - 1);
+    LAUNCH_CHECK(h);
+
+    const bool graph_ok = use_graph != 0;
+    if (graph_ok && (!s.step_graph || s.g_gt != gt || s.g_mask != mask || s.g_tape != tape || s.gB != h->den.B || s.gT != h->den.T)) {
+        if (s.step_graph) { cudaGraphExecDestroy(s.step_graph); s.step_graph = nullptr; }
+        if (s.predict_graph) { cudaGraphExecDestroy(s.predict_graph); s.predict_graph = nullptr; }
+        cudaStream_t cs;
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t g;
+        // full plain step
+        long long saved = h->launches;
+        CUDA_TRY(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        rc = predict_dev(h, s.x_a, gt, mask, s.x0, cs);
+        if (!rc) rc = finish_dev(h, s.x0, s.x_a, tape, 1, s.x_a, cs);
+        if (!rc) { k_dec_counter<<<1, 1, 0, cs>>>(df.counter); h->launches++; }
+        cudaError_t ce = cudaStreamEndCapture(cs, &g);
+        if (rc || ce != cudaSuccess) { cudaStreamDestroy(cs); return rc ? rc : idb_fail(h, IDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)); }
+        s.launches_per_step = (int)(h->launches - saved);
+        CUDA_TRY(h, cudaGraphInstantiate(&s.step_graph, g, 0));
+        cudaGraphDestroy(g);
+        // predict only
+        CUDA_TRY(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        rc = predict_dev(h, s.x_a, gt, mask, s.x0, cs);
+        ce = cudaStreamEndCapture(cs, &g);
+        if (rc || ce != cudaSuccess) { cudaStreamDestroy(cs); return rc ? rc : idb_fail(h, IDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)); }
+        s.launches_per_predict = s.launches_per_step - 2;
+        CUDA_TRY(h, cudaGraphInstantiate(&s.predict_graph, g, 0));
+        cudaGraphDestroy(g);
+        cudaStreamDestroy(cs);
+        h->launches = saved;
+        s.g_gt = gt; s.g_mask = mask; s.g_tape = tape; s.gB = h->den.B; s.gT = h->den.T;
+    }
+
+    for (int i = n - 1; i >= 0; i--) {
+        const long long t = df.host[i].t;  // denoised_fn receives the UN-mapped t (gaussian_diffusion.py:356): i
+        const bool corr = correction && i <= 500 && (i % 50 == 0);
+        (void)t;
+        if (!corr) {
+            if (graph_ok) {
+                CUDA_TRY(h, cudaGraphLaunch(s.step_graph, st));
+                h->launches += s.launches_per_step;
+            } else {
+                if ((rc = predict_dev(h, s.x_a, gt, mask, s.x0, st))) return rc;
+                if ((rc = finish_dev(h, s.x0, s.x_a, tape, 1, s.x_a, st))) return rc;
+                k_dec_counter<<<1, 1, 0, st>>>(df.counter);
+                LAUNCH_CHECK(h);
+            }
+        } else {
+            if (graph_ok) {
+                CUDA_TRY(h, cudaGraphLaunch(s.predict_graph, st));
+                h->launches += s.launches_per_predict;
+            } else if ((rc = predict_dev(h, s.x_a, gt, mask, s.x0, st))) return rc;
+            if ((rc = idb_correction_apply_dev(h, s.x0, gt, i, st))) return rc;
+            if ((rc = finish_dev(h, s.x0, s.x_a, tape, 1, s.x_a, st))) return rc;
+            k_dec_counter<<<1, 1, 0, st>>>(df.counter);
+            LAUNCH_CHECK(h);
+        }
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(x_out, s.x_a, numel * sizeof(float), cudaMemcpyDefault, st));
+    return IDB_OK;
+}
+
+void idb_sampler_release(idb_handle* h) {
+    if (h->sampler) {
+        Sampler& s = *h->sampler;
+        if (s.step_graph) cudaGraphExecDestroy(s.step_graph);
+        if (s.predict_graph) cudaGraphExecDestroy(s.predict_graph);
+        if (s.x_a) { cudaFree(s.x_a); cudaFree(s.x_b); cudaFree(s.x0); }
+        delete h->sampler;
+        h->sampler = nullptr;
+    }
+    if (h->diff.tbl) cudaFree(h->diff.tbl);
+    if (h->diff.counter) cudaFree(h->diff.counter);
+    h->diff = Diffusion();
+}

@@ -1,0 +1,286 @@
+"""Thin host wrapper over the C ABI: one Engine = one idb_handle on one GPU.
+
+PyTorch is used for device memory and streams only (tensor.data_ptr() in, tensor out); all
+arithmetic on the hot path runs in libinterdiff_b200.so.  Nothing here falls back to torch ops.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ROTARY_OFFSETS = {"absolute": (1.0, 0.0, -1.0), "bucketed": (2.0, 1.0, 0.0)}
+
+# reference data/utils.py:232-238, 252-253 (constants of the correction hook)
+MARKERSET_SSM67_SMPLH = [3470, 3171, 3327, 857, 1812, 628, 182, 3116, 3040, 239,
+                         1666, 1725, 0, 2174, 1568, 1368, 3387, 2112, 1053, 1058,
+                         3336, 3346, 1323, 2108, 3122, 3314, 1252, 1082, 1861, 1454,
+                         850, 2224, 3233, 1769, 6728, 4343, 5273, 4116, 3694, 6399,
+                         6540, 6488, 3749, 5135, 5194, 3512, 5635, 5210, 4360, 4841,
+                         6786, 5573, 4538, 4544, 6736, 6747, 4804, 5568, 6544, 6682,
+                         5322, 4927, 5686, 4598, 6633, 3506, 3508]
+HAND_MARKERS = [10, 11, 14, 31, 13, 17, 23, 28, 27] + [60, 43, 44, 47, 62, 46, 51, 57]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _shape_arr(shape):
+    return (C.c_int64 * max(len(shape), 1))(*[int(s) for s in shape])
+
+
+class Engine:
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise EngineError("interdiff_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.lib = _lib.lib()
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.idb_create(C.byref(self._h))
+        if rc:
+            msg = self.lib.idb_last_error(self._h).decode() if self._h else "idb_create failed"
+            raise EngineError(msg)
+        self._keep = []       # tensors the library may still read asynchronously
+        self.variant = None
+        self.C = None
+        self.n_steps = 0
+
+    def close(self):
+        if self._h:
+            torch.cuda.synchronize(self.device)
+            self.lib.idb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _chk(self, rc):
+        if rc:
+            raise EngineError("%s (status %d)" % (self.lib.idb_last_error(self._h).decode(), rc))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, t):
+        if isinstance(t, np.ndarray):
+            t = torch.from_numpy(t)
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+
+    @property
+    def launch_count(self):
+        return int(self.lib.idb_launch_count(self._h))
+
+    def set_gemm_backend(self, backend):
+        self._chk(self.lib.idb_set_gemm_backend(self._h, {"simt": 0, "tcgen05": 1}.get(backend, backend)))
+
+    # ------------------------------------------------------------------ denoiser
+    def load_denoiser(self, state_dict, variant="smpl", rotary="absolute", n_heads=4, n_queries=10):
+        """state_dict: reference names without the 'model.' prefix (tensors or arrays)."""
+        sd = {k: v for k, v in state_dict.items()}
+        D = int(sd["bodyEmbedding.weight"].shape[0])
+        layers = sorted({int(k.split(".")[2]) for k in sd if k.startswith("decoder.layers.")})
+        qan_mask = 0
+        for l in layers:
+            if "decoder.layers.%d.queries" % l in sd:
+                qan_mask |= 1 << l
+        cfg = _lib.DenoiserConfig()
+        cfg.variant = 0 if variant == "smpl" else 1
+        cfg.d_model, cfg.n_heads, cfg.n_layers, cfg.n_queries = D, n_heads, len(layers), n_queries
+        cfg.d_ff = int(sd["decoder.layers.0.linear1.weight"].shape[0])
+        cfg.c_body = int(sd["bodyEmbedding.weight"].shape[1])
+        cfg.c_obj = int(sd["objEmbedding.weight"].shape[1])
+        cfg.c_extra = 0 if variant == "smpl" else 7
+        cfg.n_points = 0 if variant == "smpl" else cfg.c_obj // 3
+        cfg.qan_mask = qan_mask
+        for i, o in enumerate(ROTARY_OFFSETS[rotary]):
+            cfg.rotary_offsets[i] = o
+        self._chk(self.lib.idb_denoiser_init(self._h, C.byref(cfg)))
+        for name, w in sd.items():
+            if not torch.is_tensor(w):
+                w = torch.as_tensor(np.asarray(w))
+            if not w.dtype.is_floating_point:
+                continue
+            w = w.detach().to(dtype=torch.float32).contiguous()
+            self._chk(self.lib.idb_denoiser_load(self._h, name.encode(), C.c_void_p(w.data_ptr()),
+                                                 _shape_arr(w.shape), w.dim()))
+        self._chk(self.lib.idb_denoiser_commit(self._h))
+        self.variant = variant
+        self.C = cfg.c_body + cfg.c_obj + cfg.c_extra
+        self.D = D
+
+    def bind(self, cond, T, zero_pose_obj=None):
+        """cond (Tm,B,D) as in model_kwargs['y']['cond']."""
+        cond = self._f32(cond)
+        Tm, B, _ = cond.shape
+        zp = self._f32(zero_pose_obj) if zero_pose_obj is not None else None
+        self._chk(self.lib.idb_denoiser_bind(self._h, B, T, Tm, self._ptr(cond), self._ptr(zp), self._stream()))
+        self._keep = [cond, zp]
+        self.B, self.T = B, T
+
+    def forward(self, x, timesteps):
+        x = self._f32(x)
+        t = timesteps.to(device=self.device, dtype=torch.int64).contiguous()
+        out = torch.empty_like(x)
+        self._chk(self.lib.idb_denoiser_forward(self._h, self._ptr(x), self._ptr(t), self._ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ diffusion
+    def init_diffusion(self, betas, timestep_map=None):
+        betas = np.ascontiguousarray(betas, dtype=np.float64)
+        n = len(betas)
+        tm = None
+        if timestep_map is not None:
+            tm = (C.c_int64 * n)(*[int(v) for v in timestep_map])
+        self._chk(self.lib.idb_diffusion_init(self._h, betas.ctypes.data_as(C.POINTER(C.c_double)), tm, n))
+        self.n_steps = n
+
+    @staticmethod
+    def _mask_u8(mask, device):
+        if mask is None:
+            return None
+        return mask.to(device=device).to(torch.uint8).contiguous()
+
+    def p_sample(self, i, x_t, noise, gt=None, mask=None):
+        x_t, noise = self._f32(x_t), self._f32(noise)
+        gt = self._f32(gt) if gt is not None else None
+        m = self._mask_u8(mask, self.device)
+        out, x0 = torch.empty_like(x_t), torch.empty_like(x_t)
+        self._chk(self.lib.idb_p_sample(self._h, int(i), self._ptr(x_t), self._ptr(noise), self._ptr(gt), self._ptr(m),
+                                        self._ptr(out), self._ptr(x0), self._stream()))
+        return out, x0
+
+    def p_sample_predict(self, i, x_t, gt=None, mask=None):
+        x_t = self._f32(x_t)
+        gt = self._f32(gt) if gt is not None else None
+        m = self._mask_u8(mask, self.device)
+        x0 = torch.empty_like(x_t)
+        self._chk(self.lib.idb_p_sample_predict(self._h, int(i), self._ptr(x_t), self._ptr(gt), self._ptr(m), self._ptr(x0), self._stream()))
+        return x0
+
+    def p_sample_finish(self, i, x0, x_t, noise):
+        x0, x_t, noise = self._f32(x0), self._f32(x_t), self._f32(noise)
+        out = torch.empty_like(x_t)
+        self._chk(self.lib.idb_p_sample_finish(self._h, int(i), self._ptr(x0), self._ptr(x_t), self._ptr(noise), self._ptr(out), self._stream()))
+        return out
+
+    def p_sample_loop(self, tape, gt=None, mask=None, correction=False, use_graph=True, out=None):
+        """tape: (n_steps+1, B,1,C,T) device tensor; tape[0] = x_T."""
+        assert tape.is_cuda and tape.dtype == torch.float32 and tape.is_contiguous()
+        assert tape.shape[0] == self.n_steps + 1
+        gt = self._f32(gt) if gt is not None else None
+        m = self._mask_u8(mask, self.device)
+        if out is None:
+            out = torch.empty_like(tape[0])
+        self._chk(self.lib.idb_p_sample_loop(self._h, self._ptr(tape), self._ptr(gt), self._ptr(m), int(bool(correction)),
+                                             int(bool(use_graph)), self._ptr(out), self._stream()))
+        self._keep_loop = [tape, gt, m]
+        return out
+
+    # ------------------------------------------------------------------ body model / geometry
+    def load_body(self, smplh):
+        f = lambda k: np.ascontiguousarray(np.asarray(smplh[k]), dtype=np.float32)
+        vt, sd, pd, jr, w = f("v_template"), f("shapedirs"), f("posedirs"), f("J_regressor"), f("weights")
+        parents = np.ascontiguousarray(np.asarray(smplh["parents"]), dtype=np.int32)
+        faces = np.ascontiguousarray(np.asarray(smplh["faces"]), dtype=np.int32)
+        V, J, NB = vt.shape[0], jr.shape[0], sd.shape[2]
+        assert pd.shape == (V, 3, (J - 1) * 9) and w.shape == (V, J)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        self._chk(self.lib.idb_body_init(self._h, V, J, NB, faces.shape[0], p(vt), p(sd), p(pd), p(jr), p(w), p(parents), p(faces)))
+        self.V, self.J = V, J
+
+    def lbs(self, pose, betas, trans, want_verts=True, want_jtr=True):
+        pose, betas, trans = self._f32(pose), self._f32(betas), self._f32(trans)
+        F = pose.shape[0]
+        verts = torch.empty(F, self.V, 3, device=self.device) if want_verts else None
+        jtr = torch.empty(F, self.J, 3, device=self.device) if want_jtr else None
+        self._chk(self.lib.idb_smplh_lbs(self._h, F, self._ptr(pose), self._ptr(betas), self._ptr(trans),
+                                         self._ptr(verts), self._ptr(jtr), self._stream()))
+        return verts, jtr
+
+    def vertex_normals(self, verts):
+        verts = self._f32(verts)
+        out = torch.empty_like(verts)
+        self._chk(self.lib.idb_vertex_normals(self._h, verts.shape[0], self._ptr(verts), self._ptr(out), self._stream()))
+        return out
+
+    def signed_nn(self, query, target, target_normals=None):
+        query, target = self._f32(query), self._f32(target)
+        tn = self._f32(target_normals) if target_normals is not None else None
+        F, Pq, _ = query.shape
+        Pt = target.shape[1]
+        d = torch.empty(F, Pq, device=self.device)
+        idx = torch.empty(F, Pq, device=self.device, dtype=torch.int32)
+        vec = torch.empty(F, Pq, 3, device=self.device)
+        self._chk(self.lib.idb_signed_nn(self._h, F, Pq, Pt, self._ptr(query), self._ptr(target), self._ptr(tn),
+                                         self._ptr(d), self._ptr(idx), self._ptr(vec), self._stream()))
+        return d, idx, vec
+
+    def rot6d_to_axis_angle(self, d6):
+        d6 = self._f32(d6)
+        out = torch.empty(d6.shape[:-1] + (3,), device=self.device)
+        self._chk(self.lib.idb_rot6d_to_axis_angle(self._h, d6.numel() // 6, self._ptr(d6), self._ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ correction
+    def load_projector(self, state_dict, past_len, future_len, n_pre=10, n_markers=67):
+        self._chk(self.lib.idb_projector_init(self._h, past_len, future_len, n_pre, n_markers))
+        for name, w in state_dict.items():
+            if not torch.is_tensor(w):
+                w = torch.as_tensor(np.asarray(w))
+            if not w.dtype.is_floating_point:
+                continue
+            w = w.detach().to(dtype=torch.float32).contiguous()
+            self._chk(self.lib.idb_projector_load(self._h, name.encode(), C.c_void_p(w.data_ptr()), _shape_arr(w.shape), w.dim()))
+        self._chk(self.lib.idb_projector_commit(self._h))
+        self.past_len, self.future_len = past_len, future_len
+
+    def bind_correction(self, hand_pose, betas, obj_points, past_len=None, marker_ids=None, hand_marker_ids=None):
+        hand_pose, betas, obj_points = self._f32(hand_pose), self._f32(betas), self._f32(obj_points)
+        T, B, _ = hand_pose.shape
+        mk = np.asarray(marker_ids if marker_ids is not None else MARKERSET_SSM67_SMPLH, dtype=np.int32)
+        hm = np.asarray(hand_marker_ids if hand_marker_ids is not None else HAND_MARKERS, dtype=np.int32)
+        self._chk(self.lib.idb_correction_bind(self._h, B, T, past_len if past_len is not None else self.past_len,
+                                               obj_points.shape[1], self._ptr(hand_pose), self._ptr(betas), self._ptr(obj_points),
+                                               C.c_void_p(mk.ctypes.data), C.c_void_p(hm.ctypes.data), len(hm), self._stream()))
+        torch.cuda.synchronize(self.device)
+        self.n_markers = len(mk)
+        self.n_obj = obj_points.shape[1]
+
+    def projector_sample(self, obj_angles, obj_trans, markers, contact):
+        a, t, m = self._f32(obj_angles), self._f32(obj_trans), self._f32(markers)
+        c = contact.to(device=self.device, dtype=torch.int32).contiguous()
+        T, B, _ = a.shape
+        out = torch.empty(T, B, 9, device=self.device)
+        self._chk(self.lib.idb_projector_sample(self._h, T, B, self._ptr(a), self._ptr(t), self._ptr(m), self._ptr(c), self._ptr(out), self._stream()))
+        return out
+
+    def correction_apply(self, x0, gt, t, debug=False):
+        """In-place denoised_fn body on x0 (B,1,144,T) for an active step; returns x0 (and the
+        decision tensors when debug=True)."""
+        assert x0.is_cuda and x0.is_contiguous() and x0.dtype == torch.float32
+        gt = self._f32(gt)
+        B, _, _, T = x0.shape
+        dbg = {}
+        cond = contact = markers = o2h = None
+        if debug:
+            cond = torch.empty(B, dtype=torch.uint8, device=self.device)
+            contact = torch.empty(B, self.n_markers, dtype=torch.int32, device=self.device)
+            markers = torch.empty(T, B, self.n_markers, 3, device=self.device)
+            o2h = torch.empty(T * B, self.n_obj, device=self.device)
+        self._chk(self.lib.idb_correction_apply(self._h, self._ptr(x0), self._ptr(gt), int(t), self._ptr(cond), self._ptr(contact),
+                                                self._ptr(markers), self._ptr(o2h), self._stream()))
+        if debug:
+            dbg = dict(condition=cond.bool(), contact=contact, markers=markers, o2h_signed=o2h)
+            return x0, dbg
+        return x0

@@ -1,0 +1,47 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+import torch
+
+from interdiff_b200 import synthetic as S
+from interdiff_b200 import weights as W
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+def mdm_weights(variant="smpl", source="auto", seed=233):
+    """{name: torch tensor} of the hot-path tensors.  source: 'ref' (exported checkpoint weights,
+    skips if absent), 'random' (seeded init), 'auto' (ref if present else random)."""
+    F = 1024 if variant == "smpl" else 256
+    shapes = W.mdm_hot_shapes(variant, F=F)
+    sd = None
+    if source in ("ref", "auto"):
+        sd = W.load_ref_weights("diffusion_" + variant)
+        if sd is None and source == "ref":
+            import pytest
+            pytest.skip("exported reference weights not present (oracle/export_ref_weights.py)")
+    if sd is None:
+        sd = W.random_state_dict({k: v for k, v in shapes.items() if not k.endswith(".pe")}, seed)
+    pe = S.sinusoid_table(5000, 256).reshape(5000, 1, 256)
+    sd = dict(sd)
+    sd["PositionalEmbedding.pe"] = pe
+    sd["embedTimeStep.sequence_pos_encoder.pe"] = pe
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+
+
+def projector_weights(source="auto", seed=233):
+    sd = None
+    if source in ("ref", "auto"):
+        sd = W.load_ref_weights("correction_smpl")
+        if sd is None and source == "ref":
+            import pytest
+            pytest.skip("exported reference weights not present")
+    if sd is None:
+        sd = W.random_state_dict(W.projector_shapes(), seed)
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+
+
+def smplh_torch(smplh_np):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in smplh_np.items()}

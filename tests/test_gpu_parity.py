@@ -1,0 +1,195 @@
+"""GPU parity: the CUDA path (through the C ABI) against oracle.restate on the same seeded
+inputs.  Tolerances are max-norm relative, max|a-b| / max|b| (SURVEY 8d "Parity check"); the
+north-star bound is 1e-3, the bounds asserted here are the tighter ones an fp32-grade
+implementation should meet."""
+import numpy as np
+import pytest
+import torch
+
+from interdiff_b200 import synthetic as S
+from oracle import restate as R
+from tests.helpers import mdm_weights, projector_weights, rel, smplh_torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from interdiff_b200.engine import Engine
+    e = Engine("cuda:0")
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("source", ["random", "ref"])
+@pytest.mark.parametrize("rotary", ["absolute", "bucketed"])
+def test_denoiser_forward_smpl(eng, source, rotary):
+    sd = mdm_weights("smpl", source)
+    eng.load_denoiser(sd, "smpl", rotary=rotary)
+    B, T = 5, 30
+    b = S.make_smpl_batch(B=B, T=T)
+    eng.bind(b["cond"], T)
+    x = torch.from_numpy(S.noise_tape(b["gt"].shape, 0)[0])
+    t = torch.tensor([999, 500, 37, 1, 0])
+    got = eng.forward(x.cuda(), t.cuda()).cpu()
+    with torch.no_grad():
+        ref = R.mdm_smpl_forward(sd, x, t, torch.from_numpy(b["cond"]), rotary=rotary, faithful=True)
+    assert rel(got, ref) < 2e-4
+
+
+def test_denoiser_forward_T35(eng):
+    """default reference window (past 10 + future 25), T > 32 exercises the strided loops"""
+    sd = mdm_weights("smpl", "auto")
+    eng.load_denoiser(sd, "smpl")
+    B, T = 3, 35
+    b = S.make_smpl_batch(B=B, T=T)
+    eng.bind(b["cond"], T)
+    x = torch.from_numpy(S.noise_tape(b["gt"].shape, 0)[0])
+    t = torch.tensor([800, 20, 3])
+    got = eng.forward(x.cuda(), t.cuda()).cpu()
+    with torch.no_grad():
+        ref = R.mdm_smpl_forward(sd, x, t, torch.from_numpy(b["cond"]), faithful=False)
+    assert rel(got, ref) < 2e-4
+
+
+@pytest.mark.parametrize("source", ["random", "ref"])
+def test_denoiser_forward_skeleton(eng, source):
+    """BASELINE config 1: skeleton diffusion, B=2, T=15."""
+    sd = mdm_weights("skeleton", source)
+    eng.load_denoiser(sd, "skeleton")
+    b = S.make_skeleton_batch(B=2, T=15)
+    eng.bind(b["cond"], 15, zero_pose_obj=b["zero_pose_obj"])
+    x = torch.from_numpy(S.noise_tape(b["gt"].shape, 0)[0])
+    t = torch.tensor([999, 4])
+    got = eng.forward(x.cuda(), t.cuda()).cpu()
+    with torch.no_grad():
+        ref = R.mdm_skeleton_forward(sd, x, t, torch.from_numpy(b["zero_pose_obj"]), torch.from_numpy(b["cond"]))
+    assert rel(got, ref) < 2e-4
+
+
+def _loop_setup(eng, B, T, steps, source="auto"):
+    sd = mdm_weights("smpl", source)
+    eng.load_denoiser(sd, "smpl")
+    b = S.make_smpl_batch(B=B, T=T)
+    eng.bind(b["cond"], T)
+    betas = R.named_beta_schedule("cosine", steps)
+    eng.init_diffusion(betas)
+    tape = torch.from_numpy(S.noise_tape(b["gt"].shape, steps))
+    return sd, b, R.diffusion_tables(betas), tape
+
+
+def test_p_sample_teacher_forced(eng):
+    """Every step of a 1000-step schedule is checked from the ORACLE's x_t (no chaotic
+    amplification: see DESIGN.md 'Conditioning'), at a spread of timesteps."""
+    steps = 1000
+    sd, b, tables, tape = _loop_setup(eng, 4, 30, steps)
+    gt, mask, cond = torch.from_numpy(b["gt"]), torch.from_numpy(b["mask"]), torch.from_numpy(b["cond"])
+    model_fn = lambda x, t: R.mdm_smpl_forward(sd, x, t, cond, faithful=False)
+    x = tape[0].clone()
+    worst = 0.0
+    for k, i in enumerate([999, 998, 750, 500, 250, 50, 2, 1, 0]):
+        noise = tape[k + 1]
+        with torch.no_grad():
+            ref, ref0 = R.p_sample_step(model_fn, tables, x, i, noise, gt, mask)
+        got, got0 = eng.p_sample(i, x.cuda(), noise.cuda(), gt.cuda(), mask.cuda())
+        worst = max(worst, rel(got, ref), rel(got0, ref0))
+        x = ref
+    assert worst < 2e-4, worst
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_p_sample_loop_short(eng, use_graph):
+    """Full loop on an 8-step schedule, graph replay and plain launches."""
+    steps = 8
+    sd, b, tables, tape = _loop_setup(eng, 4, 30, steps)
+    gt, mask, cond = torch.from_numpy(b["gt"]), torch.from_numpy(b["mask"]), torch.from_numpy(b["cond"])
+    with torch.no_grad():
+        ref = R.p_sample_loop(lambda x, t: R.mdm_smpl_forward(sd, x, t, cond, faithful=False), tables, tape, gt, mask)
+    got = eng.p_sample_loop(tape.cuda(), gt.cuda(), mask.cuda(), correction=False, use_graph=use_graph).cpu()
+    assert rel(got, ref) < 1e-3
+    # inpainting property: the past frames of the final sample equal the ground truth exactly
+    assert torch.equal(got[..., :10], gt[..., :10])
+
+
+def test_smplh_lbs(eng, smplh_np):
+    eng.load_body(smplh_np)
+    smplh = smplh_torch(smplh_np)
+    g = torch.Generator().manual_seed(1)
+    Fn = 37  # not a multiple of the 16-frame skinning group
+    pose = 0.4 * torch.randn(Fn, 156, generator=g)
+    pose[0, 3:6] = 0
+    pose[1] = 0
+    betas = torch.randn(Fn, 10, generator=g)
+    trans = torch.randn(Fn, 3, generator=g)
+    verts, jtr = eng.lbs(pose, betas, trans)
+    with torch.no_grad():
+        v_ref, j_ref = R.smplh_lbs(smplh, pose, betas, trans)
+    assert rel(verts, v_ref) < 1e-5 and rel(jtr, j_ref) < 1e-5
+    # property: a pure translation moves every vertex by exactly that offset (to rounding)
+    v2, _ = eng.lbs(pose, betas, trans + 1.0)
+    assert rel(v2 - 1.0, verts) < 1e-5
+
+
+def test_geometry(eng, smplh_np):
+    eng.load_body(smplh_np)
+    g = torch.Generator().manual_seed(2)
+    verts = torch.from_numpy(smplh_np["v_template"])[None].repeat(3, 1, 1) + 0.01 * torch.randn(3, 6890, 3, generator=g)
+    n = eng.vertex_normals(verts).cpu()
+    n_ref = R.vertex_normals(verts, torch.from_numpy(smplh_np["faces"]))
+    assert rel(n, n_ref) < 1e-5
+    y = verts[:, ::13][:, :500] * 1.05 + 0.01 * torch.randn(3, 500, 3, generator=g)
+    d, idx, vec = eng.signed_nn(y, verts, n_ref)
+    ref = R.point2point_signed(verts, y, n_ref)
+    assert torch.equal(idx.cpu().long(), ref[2])          # nearest indices: bit exact
+    assert torch.equal(d.cpu().sign(), ref[0].sign())      # inside / outside decisions
+    assert rel(d, ref[0]) < 1e-6 and rel(vec, ref[4]) < 1e-6
+    d6 = torch.randn(1000, 6, generator=g)
+    aa = eng.rot6d_to_axis_angle(d6).cpu()
+    from oracle import transforms as tf
+    assert rel(aa, tf.matrix_to_axis_angle(tf.rotation_6d_to_matrix(d6))) < 1e-5
+
+
+@pytest.mark.parametrize("source", ["random", "ref"])
+def test_projector(eng, smplh_np, source):
+    psd = projector_weights(source)
+    eng.load_body(smplh_np)
+    eng.load_projector(psd, 10, 20)
+    g = torch.Generator().manual_seed(3)
+    T, B = 30, 6
+    ang, tr = torch.randn(T, B, 6, generator=g), torch.randn(T, B, 3, generator=g)
+    hv = torch.randn(T, B, 67, 3, generator=g)
+    contact = (torch.rand(B, 67, generator=g) < 0.05).long() * torch.randint(1, 5, (B, 67), generator=g)
+    contact[1] = 0
+    b = S.make_smpl_batch(B=B, T=T)
+    eng.bind_correction(b["hand_pose"], b["betas"], b["obj_points"], past_len=10)
+    got = eng.projector_sample(ang, tr, hv, contact).cpu()
+    with torch.no_grad():
+        ref = R.obj_projector_sample(psd, ang, tr, hv, contact, 10, 20)
+    assert rel(got, ref) < 1e-4
+
+
+def test_correction_hook(eng, smplh_np):
+    """denoised_fn body: decisions (condition / contact) must agree exactly, continuous outputs
+    within tolerance (SURVEY section 7 'discrete decisions')."""
+    psd = projector_weights("auto")
+    eng.load_body(smplh_np)
+    eng.load_projector(psd, 10, 20)
+    T, B = 30, 3
+    b = S.make_smpl_batch(B=B, T=T)
+    eng.bind_correction(b["hand_pose"], b["betas"], b["obj_points"], past_len=10)
+    gt = torch.from_numpy(b["gt"])
+    g = torch.Generator().manual_seed(4)
+    x = gt + 0.02 * torch.randn(gt.shape, generator=g)
+    ctx = dict(past_len=10, future_len=20, smpl_dim=132, gt=gt, hand_pose=torch.from_numpy(b["hand_pose"]),
+               betas=torch.from_numpy(b["betas"]), obj_points=torch.from_numpy(b["obj_points"]),
+               smplh=smplh_torch(smplh_np), projector=psd)
+    with torch.no_grad():
+        obs = R.correction_observables(x, ctx)
+        ref = R.make_denoised_fn(ctx)(x.clone(), torch.full((B,), 450), None)
+    xg = x.clone().cuda()
+    got, dbg = eng.correction_apply(xg, gt.cuda(), 450, debug=True)
+    assert rel(dbg["markers"], obs["markers"]) < 1e-5
+    assert rel(dbg["o2h_signed"], obs["o2h_signed"]) < 1e-4
+    assert torch.equal(dbg["condition"].cpu(), obs["condition"])
+    assert torch.equal(dbg["contact"].cpu().long(), obs["contact"])
+    assert rel(got, ref) < 1e-4

@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench.py -- HOI denoising-steps/sec on synthetic BEHAVE-shape sequences (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+One bench "step" = one full sampling call of the workload (BASELINE config 2: SMPL diffusion,
+100 DDPM steps, B=64, T=30, inpainted past of 10 frames, no correction) on every rank; the
+metric counts the DENOISING steps executed:  value = N_ranks * K * 100 / max-over-ranks time,
+i.e. denoising steps of a (B=64, T=30) batch per second, whole job ("scaling": "weak": every rank
+samples its own batch of 64 sequences; the path has no data-path collective).
+
+  value : inputs (noise tape, gt, mask, cond) already resident in HBM, device time (CUDA events)
+  e2e   : the same loop through the public Python API with HOST (pinned) buffers: H2D of x_T, gt,
+          mask, cond and D2H of the sample inside the timed region; per-step noise is drawn on the
+          device like the reference does (th.randn_like).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="smpl_diffusion_100step", B=64, T=30, past_len=10, diffusion_steps=100, C=144)
+METRIC = "HOI denoising-steps/sec (B=64,T=30)"
+UNIT = "denoising steps/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_rate(n_denoise_steps, threads=None, seed=233):
+    """The reference's CPU algorithm for the path (oracle port, faithful QaN structure incl. the
+    10x replicated LocalAttention input) on the workload's B=64, T=30 batch: times
+    `n_denoise_steps` p_sample steps after one untimed step.  Returns (steps/s, seconds, cores)."""
+    import torch
+    from interdiff_b200 import synthetic as S
+    from oracle import restate as R
+    from tests.helpers import mdm_weights
+    cores = threads or os.cpu_count()
+    torch.set_num_threads(cores)
+    w = WORKLOAD
+    sd = mdm_weights("smpl", "auto")
+    b = S.make_smpl_batch(B=w["B"], T=w["T"], past_len=w["past_len"], seed=seed)
+    tables = R.diffusion_tables(R.named_beta_schedule("cosine", w["diffusion_steps"]))
+    gt, mask, cond = torch.from_numpy(b["gt"]), torch.from_numpy(b["mask"]), torch.from_numpy(b["cond"])
+    tape = torch.from_numpy(S.noise_tape(b["gt"].shape, n_denoise_steps + 1, seed))
+    fn = lambda x, t: R.mdm_smpl_forward(sd, x, t, cond, faithful=True)
+    x = tape[0]
+    with torch.no_grad():
+        x, _ = R.p_sample_step(fn, tables, x, w["diffusion_steps"] - 1, tape[1], gt, mask)  # warm-up
+        t0 = time.perf_counter()
+        for k in range(n_denoise_steps):
+            x, _ = R.p_sample_step(fn, tables, x, w["diffusion_steps"] - 2 - k, tape[2 + k], gt, mask)
+        dt = time.perf_counter() - t0
+    return n_denoise_steps / dt, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per = 3  # denoising steps per bench "step" (bounded sample of the 100-step workload)
+    total = max(1, args.steps) * per
+    rate, secs, cores = cpu_reference_rate(total)
+    line = dict(impl="reference", metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000.0 * secs / max(1, args.steps), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload="SMPL diffusion, 100 DDPM steps, B=64, T=30 (configs[1]); each bench step = %d denoising steps" % per,
+                            weights="reference checkpoint" if _have_ref_weights() else "seeded random init"),
+                cpu_baseline=dict(value=rate, unit=UNIT, cores=cores, kind="port",
+                                  sample="%d p_sample steps of the B=64,T=30 batch, oracle.restate faithful port, torch CPU fp32" % total),
+                e2e=dict(value=rate, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def _have_ref_weights():
+    from interdiff_b200 import weights as W
+    return os.path.exists(W.ref_weights_path("diffusion_smpl"))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from interdiff_b200 import synthetic as S
+    from interdiff_b200.engine import Engine
+    from oracle import restate as R  # beta schedule helper + cpu_baseline leg only
+    from tests.helpers import mdm_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOAD
+    n = w["diffusion_steps"]
+    eng = Engine(dev)
+    if args.backend:
+        eng.set_gemm_backend(args.backend)
+    sd = mdm_weights("smpl", "auto")
+    eng.load_denoiser(sd, "smpl")
+    b = S.make_smpl_batch(B=w["B"], T=w["T"], past_len=w["past_len"], seed=233 + rank)  # each rank its own 64 sequences
+    eng.init_diffusion(R.named_beta_schedule("cosine", n))
+    shape = b["gt"].shape
+    # ---- device-resident leg
+    gt_d, mask_d, cond_d = torch.from_numpy(b["gt"]).to(dev), torch.from_numpy(b["mask"]).to(dev), torch.from_numpy(b["cond"]).to(dev)
+    eng.bind(cond_d, w["T"])
+    tape_d = torch.from_numpy(S.noise_tape(shape, n, 233 + rank)).to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
+    out = torch.empty(shape, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        eng.p_sample_loop(tape_d, gt_d, mask_d, use_graph=True, out=out)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for s, e in ev:
+        flush.fill_(1.0)  # evict L2 between timed iterations (outside the event pair)
+        s.record()
+        eng.p_sample_loop(tape_d, gt_d, mask_d, use_graph=True, out=out)
+        e.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = eng.launch_count - l0
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    # ---- end-to-end leg through the public API with host buffers
+    from interdiff_b200.sampling import sample_smpl_host
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h_gt, h_mask, h_cond, h_xT = pin(b["gt"]), pin(b["mask"]), pin(b["cond"]), pin(S.noise_tape(shape, 0, 233 + rank)[0])
+    h_out = torch.empty(shape).pin_memory()
+    for _ in range(2):
+        sample_smpl_host(eng, h_xT, h_gt, h_mask, h_cond, h_out, seed=1)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(args.steps):
+        sample_smpl_host(eng, h_xT, h_gt, h_mask, h_cond, h_out, seed=2 + it)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    # ---- roofline of the dominant kernel (feed-forward GEMMs, 16.1 of the 24.5 GFLOP of a step)
+    roof = eng.gemm_microbench(M=w["B"] * w["T"], N=1024, K=256, iters=50) if hasattr(eng, "gemm_microbench") else None
+
+    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+    if rank == 0:
+        peaks = _peaks()
+        total_steps = world * args.steps * n
+        value = total_steps / (dev_ms / 1000.0)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                    ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32 (fp32 SIMT)" if (args.backend or "simt") == "simt" else "f32 via 3xTF32 tcgen05 (fp32 accumulate)",
+                    data="synthetic",
+                    config=dict(workload="SMPL diffusion, 100 DDPM steps, B=64 per GPU, T=30 (past 10 + future 20), 144 channels, "
+                                         "inpainting mask on the past, no correction (BASELINE configs[1])",
+                                weights="reference checkpoint (exported)" if _have_ref_weights() else "seeded random init",
+                                l2="flushed between timed iterations (256 MB fill outside the event pair)",
+                                cuda_graph=True, gemm_backend=args.backend or "simt"),
+                    e2e=dict(value=total_steps / (e2e_ms / 1000.0), unit=UNIT,
+                             h2d_bytes_per_step=int(h_gt.numel() * 4 + h_mask.numel() + h_cond.numel() * 4 + h_xT.numel() * 4),
+                             d2h_bytes_per_step=int(h_out.numel() * 4)),
+                    gpu_launches=int(launches), clocks=clocks, wall_s=wall)
+        if roof:
+            flops = 2.0 * roof["M"] * roof["N"] * roof["K"]
+            ach = flops / (roof["ms"] * 1e-3) / 1e12
+            line["roofline"] = dict(bound="tensor", kernel=roof["kernel"], achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s",
+                                    frac=ach / peaks["bf16_tflops"], traffic=None, peak_source=peaks["source"],
+                                    note="algorithmic 2*M*N*K of the ff1 GEMM (M=1920,N=1024,K=256) / mean launch time over %d launches" % roof["iters"])
+        if world == 1 and not args.no_cpu:
+            rate, secs, cores = cpu_reference_rate(args.cpu_steps)
+            line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="port",
+                                        sample="%d p_sample steps of the same B=64,T=30 batch (%.1f s), oracle.restate faithful port, torch CPU fp32"
+                                               % (args.cpu_steps, secs))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--backend", default=None, choices=[None, "simt", "tcgen05"])
+    ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -132,6 +132,12 @@ int idb_correction_bind(idb_handle* h, int B, int T, int past_len, int n_obj_poi
 int idb_correction_apply(idb_handle* h, float* x0, const float* gt, int t, uint8_t* condition_out,
                          int32_t* contact_out, float* markers_out, float* o2h_out, void* stream);
 
+/* ---- kernel-level hook (tests / bench roofline leg) -----------------------------------------
+ * C[M,N] = epi(A[M,K] . W[N,K]^T) with the handle's GEMM backend; epi bit 0 bias, 1 GELU(erf),
+ * 2 residual add, 3 SiLU (the fused epilogues of the nn.Linear calls of the denoiser). */
+int idb_debug_gemm(idb_handle* h, const float* A, const float* W, const float* bias, const float* res, float* C,
+                   int M, int N, int K, int epi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

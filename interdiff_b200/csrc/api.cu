@@ -47,3 +47,9 @@ extern "C" int idb_set_gemm_backend(idb_handle* h, int backend) {
     h->gemm_backend = backend;
     return IDB_OK;
 }
+
+extern "C" int idb_debug_gemm(idb_handle* h, const float* A, const float* W, const float* bias, const float* res, float* C,
+                              int M, int N, int K, int epi, void* stream) {
+    if (!h || !A || !W || !C) return IDB_ERR_ARG;
+    return idb_gemm(h, A, K, W, K, bias, res, N, C, N, M, N, K, epi, (cudaStream_t)stream);
+}

@@ -84,6 +84,42 @@ class Engine:
     def set_gemm_backend(self, backend):
         self._chk(self.lib.idb_set_gemm_backend(self._h, {"simt": 0, "tcgen05": 1}.get(backend, backend)))
 
+    # ------------------------------------------------------------------ kernel-level hooks
+    def gemm(self, A, W, bias=None, res=None, gelu=False, silu=False):
+        """epi(A @ W.T) through the handle's GEMM backend (tests / roofline leg)."""
+        A, W = self._f32(A), self._f32(W)
+        bias = self._f32(bias) if bias is not None else None
+        res = self._f32(res) if res is not None else None
+        M, K = A.shape
+        N = W.shape[0]
+        out = torch.empty(M, N, device=self.device)
+        epi = (1 if bias is not None else 0) | (2 if gelu else 0) | (4 if res is not None else 0) | (8 if silu else 0)
+        self._chk(self.lib.idb_debug_gemm(self._h, self._ptr(A), self._ptr(W), self._ptr(bias), self._ptr(res), self._ptr(out),
+                                          M, N, K, epi, self._stream()))
+        return out
+
+    def gemm_microbench(self, M, N, K, iters=50, gelu=True):
+        """Mean device time of the dominant GEMM (bias + GELU epilogue) over `iters` back-to-back
+        launches on the current stream, CUDA events, after warm-up."""
+        g = torch.Generator(device="cpu").manual_seed(0)
+        A = torch.randn(M, K, generator=g).to(self.device)
+        W = (torch.randn(N, K, generator=g) / K ** 0.5).to(self.device)
+        bias = torch.randn(N, generator=g).to(self.device)
+        out = torch.empty(M, N, device=self.device)
+        epi = 1 | (2 if gelu else 0)
+        call = lambda: self._chk(self.lib.idb_debug_gemm(self._h, self._ptr(A), self._ptr(W), self._ptr(bias), C.c_void_p(), self._ptr(out),
+                                                         M, N, K, epi, self._stream()))
+        for _ in range(5):
+            call()
+        torch.cuda.synchronize(self.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            call()
+        e1.record()
+        torch.cuda.synchronize(self.device)
+        return dict(M=M, N=N, K=K, iters=iters, ms=e0.elapsed_time(e1) / iters, kernel="gemm ff1 (bias+GELU)")
+
     # ------------------------------------------------------------------ denoiser
     def load_denoiser(self, state_dict, variant="smpl", rotary="absolute", n_heads=4, n_queries=10):
         """state_dict: reference names without the 'model.' prefix (tensors or arrays)."""

@@ -117,6 +117,9 @@ int idb_rot6d_to_axis_angle(idb_handle* h, int n, const float* rot6d, float* aa,
 int idb_projector_init(idb_handle* h, int past_len, int future_len, int n_pre, int n_markers);
 int idb_projector_load(idb_handle* h, const char* name, const float* data, const int64_t* shape, int ndim);
 int idb_projector_commit(idb_handle* h);
+/* marker indices (into the P markers) that get the +0.5 hand bonus in the hypothesis selection
+ * (correction_smpl.py:129-130; data/utils.py:252-253), host_or_dev */
+int idb_projector_set_hand_markers(idb_handle* h, const int32_t* ids, int n);
 /* obj_angles (T,B,6), obj_trans (T,B,3), markers (T,B,P,3), contact (B,P) int32 -> out (T,B,9) */
 int idb_projector_sample(idb_handle* h, int T, int B, const float* obj_angles, const float* obj_trans,
                          const float* markers, const int32_t* contact, float* out, void* stream);

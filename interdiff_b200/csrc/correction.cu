@@ -363,6 +363,7 @@ void idb_projector_release(idb_handle* h) {
     for (void* q : p.owned) cudaFree(q);
     for (void* q : p.ctx_owned) cudaFree(q);
     if (p.resid) cudaFree(p.resid);
+    if (p.hand_ids) cudaFree(p.hand_ids);
     delete h->proj;
     h->proj = nullptr;
 }
@@ -487,11 +488,21 @@ static int projector_run(idb_handle* h, int T, int B, const float* ang, const fl
     return IDB_OK;
 }
 
+extern "C" int idb_projector_set_hand_markers(idb_handle* h, const int32_t* ids, int n) {
+    if (!h || !ids || n < 0 || n > 64) return IDB_ERR_ARG;
+    if (!h->proj) return idb_fail(h, IDB_ERR_STATE, "idb_projector_init first");
+    Projector& p = *h->proj;
+    if (!p.hand_ids) CUDA_TRY(h, cudaMalloc((void**)&p.hand_ids, 64 * sizeof(int32_t)));
+    CUDA_TRY(h, cudaMemcpy(p.hand_ids, ids, (size_t)n * 4, cudaMemcpyDefault));
+    p.n_hand = n;
+    return IDB_OK;
+}
+
 extern "C" int idb_projector_sample(idb_handle* h, int T, int B, const float* obj_angles, const float* obj_trans,
                                     const float* markers, const int32_t* contact, float* out, void* stream) {
     if (!h || !obj_angles || !obj_trans || !markers || !contact || !out) return IDB_ERR_ARG;
     if (!h->proj) return idb_fail(h, IDB_ERR_STATE, "idb_projector_init first");
-    if (!h->proj->hand_ids) return idb_fail(h, IDB_ERR_STATE, "idb_correction_bind first (hand marker ids)");
+    if (!h->proj->hand_ids) return idb_fail(h, IDB_ERR_STATE, "idb_projector_set_hand_markers first");
     return projector_run(h, T, B, obj_angles, obj_trans, markers, contact, out, (cudaStream_t)stream);
 }
 
@@ -516,7 +527,6 @@ extern "C" int idb_correction_bind(idb_handle* h, int B, int T, int past_len, in
         };
         CUDA_TRY(h, A((void**)&p.hand_pose, (size_t)F * 90 * 4)); CUDA_TRY(h, A((void**)&p.betas, (size_t)F * 10 * 4));
         CUDA_TRY(h, A((void**)&p.obj_points, (size_t)B * n_obj_points * 3 * 4)); CUDA_TRY(h, A((void**)&p.marker_ids, (size_t)P * 4));
-        CUDA_TRY(h, A((void**)&p.hand_ids, (size_t)(n_hand + 1) * 4));
         CUDA_TRY(h, A((void**)&p.pose, (size_t)F * 156 * 4)); CUDA_TRY(h, A((void**)&p.trans, (size_t)F * 3 * 4));
         CUDA_TRY(h, A((void**)&p.objRt, (size_t)F * 12 * 4)); CUDA_TRY(h, A((void**)&p.verts, (size_t)F * V * 3 * 4));
         CUDA_TRY(h, A((void**)&p.normals, (size_t)F * V * 3 * 4)); CUDA_TRY(h, A((void**)&p.objp, (size_t)F * n_obj_points * 3 * 4));
@@ -527,12 +537,12 @@ extern "C" int idb_correction_bind(idb_handle* h, int B, int T, int past_len, in
         CUDA_TRY(h, A((void**)&p.gt_tr, (size_t)F * 3 * 4)); CUDA_TRY(h, A((void**)&p.proj_out, (size_t)F * 9 * 4));
         p.B = B; p.cT = T; p.n_obj = n_obj_points;
     }
-    p.cpast = past_len; p.n_hand = n_hand;
+    p.cpast = past_len;
+    { int rc = idb_projector_set_hand_markers(h, hand_marker_ids, n_hand); if (rc) return rc; }
     CUDA_TRY(h, cudaMemcpyAsync(p.hand_pose, hand_pose, (size_t)F * 90 * 4, cudaMemcpyDefault, st));
     CUDA_TRY(h, cudaMemcpyAsync(p.betas, betas, (size_t)F * 10 * 4, cudaMemcpyDefault, st));
     CUDA_TRY(h, cudaMemcpyAsync(p.obj_points, obj_points, (size_t)B * n_obj_points * 3 * 4, cudaMemcpyDefault, st));
     CUDA_TRY(h, cudaMemcpyAsync(p.marker_ids, marker_ids, (size_t)P * 4, cudaMemcpyDefault, st));
-    CUDA_TRY(h, cudaMemcpyAsync(p.hand_ids, hand_marker_ids, (size_t)n_hand * 4, cudaMemcpyDefault, st));
     return IDB_OK;
 }
 

@@ -1,7 +1,317 @@
-// tcgen05 3xTF32 GEMM backend -- placeholder until the tensor-core kernel lands.
+// tcgen05 "3xTF32" split-precision GEMM for sm_100a:  C[M,N] = epi(A[M,K] . W[N,K]^T), fp32 in/out.
+//
+// Why split precision: the sampling chain amplifies operand rounding (DESIGN.md "Conditioning"),
+// so the tensor-core path has to be fp32-grade.  Every fp32 operand x is split on chip into
+//     big = tf32_rn(x),  small = tf32_rn(x - big)        (x - big is exact in fp32)
+// and the product is accumulated in TMEM (fp32) as  a_s*w_b + a_b*w_s + a_b*w_b  (small terms
+// first); the dropped a_s*w_s term is <= 2^-22 relative.
+//
+// Pipeline per CTA (one 128 x BN output tile, 192 threads):
+//   warp 0   : TMA producer.  cp.async.bulk.tensor 2D loads of the raw fp32 A (128 x 32) and W
+//              (BN x 32) k-blocks into 128B-swizzled shared memory, mbarrier complete_tx.
+//   warps 2-5: converter.  Split the raw tiles in place (raw -> big) and write `small` copies at the
+//              same swizzled offsets, fence.proxy.async, arrive on the stage's "ready" barrier.
+//              After the k loop the same warps run the epilogue: tcgen05.ld (32x32b.x32) from TMEM,
+//              bias / GELU / SiLU / residual, vectorised global stores.
+//   warp 1   : MMA issuer (one elected lane).  12 tcgen05.mma.kind::tf32 per k-block (4 k-steps of 8
+//              x 3 split terms), tcgen05.commit -> "empty" barrier (frees the stage) and finally
+//              -> "accumulator full" barrier.  Also owns the TMEM allocation.
+//
+// Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor / InstrDescriptor).
 #include "common.cuh"
-bool idb_gemm_tcgen05_supported(int, int, int, int, int, int) { return false; }
-int idb_gemm_tcgen05(idb_handle* h, const float*, int, const float*, int, const float*, const float*, int, float*, int,
-                     int, int, int, int, cudaStream_t) {
-    return idb_fail(h, IDB_ERR_STATE, "tcgen05 backend not built");
+
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // 32 fp32 = one 128-byte swizzle row
+constexpr int UMMA_K = 8;              // kind::tf32
+constexpr int NUM_THREADS = 192;
+constexpr int CONV_THREADS = 128;
+
+template <int BN> struct Cfg {
+    static constexpr int RAW_BYTES = (BM + BN) * BK * 4;     // A then W, both 1024-byte multiples
+    static constexpr int STAGE_BYTES = 2 * RAW_BYTES;        // [raw->big | small]
+    static constexpr int STAGES = (BN == 128) ? 3 : 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t f32_to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);     // start address  [0,14)
+    d |= (uint64_t)1 << 16;                       // leading byte offset (16 B, unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                   const float* __restrict__ bias, const float* __restrict__ res, int ldr,
+                   float* __restrict__ C, int ldc, int M, int N, int K, int epi) {
+    using cfg = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B swizzle atoms
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + cfg::STAGES * cfg::STAGE_BYTES;
+    // barrier layout (8 B each): full[S], ready[S], empty[S], acc_full, then tmem slot
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_ready = [&](int s) { return bars + 8u * (cfg::STAGES + s); };
+    auto bar_empty = [&](int s) { return bars + 8u * (2 * cfg::STAGES + s); };
+    const uint32_t bar_acc = bars + 8u * (3 * cfg::STAGES);
+    const uint32_t tmem_slot = bar_acc + 8u;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + cfg::STAGES * cfg::STAGE_BYTES + 8 * (3 * cfg::STAGES) + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int num_kb = (K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < cfg::STAGES; s++) {
+            mbar_init(bar_full(s), 1);
+            mbar_init(bar_ready(s), CONV_THREADS);
+            mbar_init(bar_empty(s), 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % cfg::STAGES, round = kb / cfg::STAGES;
+                if (round > 0) mbar_wait(bar_empty(s), (round - 1) & 1);
+                const uint32_t dst = base + s * cfg::STAGE_BYTES;
+                mbar_arrive_expect_tx(bar_full(s), cfg::RAW_BYTES);
+                tma_load_2d(dst, &map_a, bar_full(s), kb * BK, m0);
+                tma_load_2d(dst + BM * BK * 4, &map_w, bar_full(s), kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B tf32, both K-major, N>>3 @17, M>>4 @24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % cfg::STAGES, round = kb / cfg::STAGES;
+                mbar_wait(bar_ready(s), round & 1);
+                tc_fence_after();
+                const uint32_t a_big = base + s * cfg::STAGE_BYTES, w_big = a_big + BM * BK * 4;
+                const uint32_t a_sml = a_big + cfg::RAW_BYTES, w_sml = w_big + cfg::RAW_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < BK / UMMA_K; kk++) {
+                    const uint32_t koff = kk * UMMA_K * 4;   // 32 bytes per k-step inside the swizzle row
+                    const uint64_t dab = make_smem_desc(a_big + koff), das = make_smem_desc(a_sml + koff);
+                    const uint64_t dwb = make_smem_desc(w_big + koff), dws = make_smem_desc(w_sml + koff);
+                    umma_tf32(tmem_base, das, dwb, idesc, (kb | kk) ? 1u : 0u);
+                    umma_tf32(tmem_base, dab, dws, idesc, 1u);
+                    umma_tf32(tmem_base, dab, dwb, idesc, 1u);
+                }
+                umma_commit(bar_empty(s));      // stage reusable once these MMAs have read it
+            }
+            umma_commit(bar_acc);               // accumulator complete
+        }
+    } else {
+        // ===================== converter, then epilogue (warps 2..5) =====================
+        const int ct = threadIdx.x - 64;        // 0..127
+        for (int kb = 0; kb < num_kb; kb++) {
+            const int s = kb % cfg::STAGES, round = kb / cfg::STAGES;
+            mbar_wait(bar_full(s), round & 1);
+            uint8_t* st = base_ptr + s * cfg::STAGE_BYTES;
+            constexpr int NCHUNK = cfg::RAW_BYTES / 16;
+#pragma unroll 4
+            for (int c = ct; c < NCHUNK; c += CONV_THREADS) {
+                float4 x = *reinterpret_cast<float4*>(st + c * 16);
+                uint4 b, sm;
+                b.x = f32_to_tf32(x.x); b.y = f32_to_tf32(x.y); b.z = f32_to_tf32(x.z); b.w = f32_to_tf32(x.w);
+                sm.x = f32_to_tf32(x.x - __uint_as_float(b.x)); sm.y = f32_to_tf32(x.y - __uint_as_float(b.y));
+                sm.z = f32_to_tf32(x.z - __uint_as_float(b.z)); sm.w = f32_to_tf32(x.w - __uint_as_float(b.w));
+                *reinterpret_cast<uint4*>(st + c * 16) = b;
+                *reinterpret_cast<uint4*>(st + cfg::RAW_BYTES + c * 16) = sm;
+            }
+            fence_proxy_async();                // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(bar_ready(s));
+        }
+        // ---- epilogue
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int col = n0 + c0 + j;
+                    if (col + 3 < N) {
+                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        if (epi & EPI_BIAS) {
+                            const float4 bb = *reinterpret_cast<const float4*>(bias + col);
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                        }
+                        if (epi & EPI_GELU) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
+                        if (epi & EPI_SILU) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
+                        if (epi & EPI_RES) {
+                            const float4 rr = *reinterpret_cast<const float4*>(res + (size_t)row * ldr + col);
+                            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                        }
+                        *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = o;
+                    } else {
+                        for (int e = 0; e < 4; e++) {
+                            if (col + e >= N) break;
+                            float o = __uint_as_float(v[j + e]);
+                            if (epi & EPI_BIAS) o += bias[col + e];
+                            if (epi & EPI_GELU) o = gelu_erf(o);
+                            if (epi & EPI_SILU) o = silu(o);
+                            if (epi & EPI_RES) o += res[(size_t)row * ldr + col + e];
+                            C[(size_t)row * ldc + col + e] = o;
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+bool g_attr_set = false;
+
+int make_map(idb_handle* h, CUtensorMap* map, const float* ptr, int rows, int cols, int ld, int box_rows) {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return idb_fail(h, IDB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        g_encode = (EncodeTiledFn)fn;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return idb_fail(h, IDB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return IDB_OK;
+}
+
+}  // namespace
+
+bool idb_gemm_tcgen05_supported(int M, int N, int K, int lda, int ldw, int ldc) {
+    // TMA needs 16-byte aligned row strides; the epilogue vector path needs ldc % 4 == 0
+    return M >= 1 && N >= 8 && K >= 4 && (lda % 4 == 0) && (ldw % 4 == 0) && (ldc % 4 == 0) && (N % 4 == 0);
+}
+
+int idb_gemm_tcgen05(idb_handle* h, const float* A, int lda, const float* W, int ldw, const float* bias,
+                     const float* res, int ldr, float* C, int ldc, int M, int N, int K, int epi, cudaStream_t st) {
+    if (((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) & 15) return idb_fail(h, IDB_ERR_ARG, "tcgen05 GEMM needs 16-byte aligned pointers");
+    if ((epi & EPI_RES) && ((ldr % 4) || ((uintptr_t)res & 15))) return idb_fail(h, IDB_ERR_ARG, "residual must be 16-byte aligned");
+    if ((epi & EPI_BIAS) && ((uintptr_t)bias & 15)) return idb_fail(h, IDB_ERR_ARG, "bias must be 16-byte aligned");
+    if (!g_attr_set) {
+        CUDA_TRY(h, cudaFuncSetAttribute(gemm_3xtf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
+        CUDA_TRY(h, cudaFuncSetAttribute(gemm_3xtf32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
+        g_attr_set = true;
+    }
+    // wide outputs take 128-column tiles; narrow ones 64 so more SMs get a tile
+    const bool wide = (long)((M + BM - 1) / BM) * ((N + 127) / 128) >= 74;
+    CUtensorMap ma, mw;
+    int rc;
+    if ((rc = make_map(h, &ma, A, M, K, lda, BM))) return rc;
+    if ((rc = make_map(h, &mw, W, N, K, ldw, wide ? 128 : 64))) return rc;
+    if (wide) {
+        dim3 grid((N + 127) / 128, (M + BM - 1) / BM);
+        gemm_3xtf32_kernel<128><<<grid, NUM_THREADS, Cfg<128>::SMEM_BYTES, st>>>(ma, mw, bias, res, ldr, C, ldc, M, N, K, epi);
+    } else {
+        dim3 grid((N + 63) / 64, (M + BM - 1) / BM);
+        gemm_3xtf32_kernel<64><<<grid, NUM_THREADS, Cfg<64>::SMEM_BYTES, st>>>(ma, mw, bias, res, ldr, C, ldc, M, N, K, epi);
+    }
+    LAUNCH_CHECK(h);
+    return IDB_OK;
 }

@@ -279,6 +279,8 @@ class Engine:
             w = w.detach().to(dtype=torch.float32).contiguous()
             self._chk(self.lib.idb_projector_load(self._h, name.encode(), C.c_void_p(w.data_ptr()), _shape_arr(w.shape), w.dim()))
         self._chk(self.lib.idb_projector_commit(self._h))
+        hm = np.asarray(HAND_MARKERS, dtype=np.int32)
+        self._chk(self.lib.idb_projector_set_hand_markers(self._h, C.c_void_p(hm.ctypes.data), len(hm)))
         self.past_len, self.future_len = past_len, future_len
 
     def bind_correction(self, hand_pose, betas, obj_points, past_len=None, marker_ids=None, hand_marker_ids=None):

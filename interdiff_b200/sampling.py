@@ -51,3 +51,52 @@ def sample_smpl_host(engine, h_xT, h_gt, h_mask, h_cond, h_out, seed=None, corre
     h_out.copy_(out, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
     return h_out
+
+
+class FusedCorrection:
+    """The reference's denoised_fn hook (eval_smpl_short.py:84-130) as an object the diffusion
+    recognises: with it p_sample_loop keeps the whole loop, including the correction steps, inside
+    the library.  Called directly (x, t, model_kwargs) it applies the same gate and runs the fused
+    correction kernels on x in place, so it also works as a plain denoised_fn callback.
+
+    model_kwargs['y'] must carry what the reference's hook reads: inpainted_motion, hand_pose
+    (T,B,90), smpl (interdiff_b200 SMPL_Layer), beta (T,B,10), obj_model (object with .model =
+    interdiff_b200 ObjProjector) and obj_points (B,P,3)."""
+    is_fused_correction = True
+
+    def __init__(self, past_len):
+        self.past_len = past_len
+        self._bound = None
+
+    def bind(self, eng, model_kwargs):
+        y = model_kwargs["y"]
+        y["smpl"].load_into(eng)
+        y["obj_model"].model.load_into(eng)
+        hp, beta, pts = y["hand_pose"], y["beta"], y["obj_points"]
+        key = (id(eng), hp.data_ptr(), hp._version, beta.data_ptr(), beta._version, pts.data_ptr(), pts._version)
+        if self._bound != key:
+            eng.bind_correction(hp, beta, pts, past_len=self.past_len)
+            self._bound = key
+        return eng
+
+    def __call__(self, x, t, model_kwargs):
+        ti = int(t[0])
+        if ti > 500 or ti % 50 != 0:
+            return x
+        y = model_kwargs["y"]
+        eng = y["smpl"].engine_for(x.device) if not hasattr(self, "_eng") else self._eng
+        self.bind(eng, model_kwargs)
+        return eng.correction_apply(x, y["inpainted_motion"], ti)
+
+
+def sample_postprocess(engine, sample, hand_pose, betas, past_len=10, future_len=None):
+    """Tail of sample_once(_proj) (eval_smpl_short.py:154-173): 6D -> axis-angle and SMPL-H LBS of
+    all T*B frames.  Returns body pose (T,B,159), object pose (T,B,6), verts (T,B,V,3), joints."""
+    B, _, C, T = sample.shape
+    xs = sample.squeeze(1).permute(2, 0, 1).contiguous()            # (T,B,144)
+    body_rot = engine.rot6d_to_axis_angle(xs[..., :132].reshape(T, B, 22, 6)).reshape(T, B, 66)
+    obj_rot = engine.rot6d_to_axis_angle(xs[..., 135:141].reshape(T, B, 1, 6)).reshape(T, B, 3)
+    body = torch.cat([body_rot, hand_pose, xs[..., 132:135]], dim=2)
+    bb = body.reshape(T * B, -1)
+    verts, jtr = engine.lbs(bb[:, :-3], betas.reshape(T * B, -1), bb[:, -3:])
+    return body, torch.cat([obj_rot, xs[..., 141:144]], dim=2), verts.view(T, B, -1, 3), jtr.view(T, B, -1, 3)

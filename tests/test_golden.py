@@ -1,0 +1,159 @@
+"""Golden vectors produced by the reference's OWN classes (oracle/make_golden.py, committed under
+tests/golden/).  CPU tests pin oracle.restate to them; GPU tests pin the CUDA path (through the
+C ABI) to them directly, with no oracle in between.  '*_ref' fixtures use the shipped checkpoint
+weights exported to oracle/_ref/weights (skip when absent); '*_random' use the seeded init."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from interdiff_b200 import synthetic as S
+from oracle import restate as R
+from tests.helpers import mdm_weights, projector_weights, rel, smplh_torch
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+load = lambda n: {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, n)).items()}
+
+
+class OracleBackend:
+    """oracle.restate behind the same small interface as the Engine-based backend."""
+    name = "oracle"
+
+    def smpl_forward(self, sd, x, t, cond):
+        return R.mdm_smpl_forward(sd, x, t, cond)
+
+    def smpl_loop(self, sd, b, tape, steps):
+        cond, gt, mask = (torch.from_numpy(b[k]) for k in ("cond", "gt", "mask"))
+        tables = R.diffusion_tables(R.named_beta_schedule("cosine", steps))
+        return R.p_sample_loop(lambda x, t: R.mdm_smpl_forward(sd, x, t, cond), tables, tape, gt, mask)
+
+    def skeleton(self, sd, b, x, tape):
+        cond, gt, mask, zp = (torch.from_numpy(b[k]) for k in ("cond", "gt", "mask", "zero_pose_obj"))
+        fn = lambda x_, t: R.mdm_skeleton_forward(sd, x_, t, zp, cond)
+        fwd = fn(x, torch.tensor([999, 999]))
+        tables = R.diffusion_tables(R.named_beta_schedule("cosine", 1000))
+        s, x0 = R.p_sample_step(fn, tables, tape[0], 999, tape[1], gt, mask)
+        return fwd, s, x0
+
+    def projector(self, psd, ang, tr, hv, contact):
+        return R.obj_projector_sample(psd, ang, tr, hv, contact, 10, 20)
+
+    def geometry(self, smplh_np, g):
+        smplh = smplh_torch(smplh_np)
+        verts, jtr = R.smplh_lbs(smplh, g["pose"], g["betas"], g["trans"])
+        normals = R.vertex_normals(verts, smplh["faces"])
+        p = R.point2point_signed(verts, g["y"], normals)
+        return verts, jtr, normals, p[0], p[2], p[4]
+
+    def denoised(self, smplh_np, psd, b, x, t):
+        ctx = dict(past_len=10, future_len=20, smpl_dim=132, gt=torch.from_numpy(b["gt"]), hand_pose=torch.from_numpy(b["hand_pose"]),
+                   betas=torch.from_numpy(b["betas"]), obj_points=torch.from_numpy(b["obj_points"]), smplh=smplh_torch(smplh_np), projector=psd)
+        return R.make_denoised_fn(ctx)(x.clone(), torch.full((x.shape[0],), t), None)
+
+
+class EngineBackend:
+    name = "cuda"
+
+    def __init__(self, gemm):
+        from interdiff_b200.engine import Engine
+        self.e = Engine("cuda:0")
+        self.e.set_gemm_backend(gemm)
+
+    def smpl_forward(self, sd, x, t, cond):
+        self.e.load_denoiser(sd, "smpl")
+        self.e.bind(cond, x.shape[-1])
+        return self.e.forward(x.cuda(), t.cuda()).cpu()
+
+    def smpl_loop(self, sd, b, tape, steps):
+        self.e.load_denoiser(sd, "smpl")
+        self.e.bind(b["cond"], 30)
+        self.e.init_diffusion(R.named_beta_schedule("cosine", steps))
+        return self.e.p_sample_loop(tape.cuda(), torch.from_numpy(b["gt"]).cuda(), torch.from_numpy(b["mask"]).cuda()).cpu()
+
+    def skeleton(self, sd, b, x, tape):
+        self.e.load_denoiser(sd, "skeleton")
+        self.e.bind(b["cond"], 15, zero_pose_obj=b["zero_pose_obj"])
+        fwd = self.e.forward(x.cuda(), torch.tensor([999, 999]).cuda()).cpu()
+        self.e.init_diffusion(R.named_beta_schedule("cosine", 1000))
+        s, x0 = self.e.p_sample(999, tape[0].cuda(), tape[1].cuda(), torch.from_numpy(b["gt"]).cuda(), torch.from_numpy(b["mask"]).cuda())
+        return fwd, s.cpu(), x0.cpu()
+
+    def projector(self, psd, ang, tr, hv, contact):
+        self.e.load_projector(psd, 10, 20)
+        return self.e.projector_sample(ang, tr, hv, contact).cpu()
+
+    def geometry(self, smplh_np, g):
+        self.e.load_body(smplh_np)
+        verts, jtr = self.e.lbs(g["pose"], g["betas"], g["trans"])
+        normals = self.e.vertex_normals(verts)
+        d, idx, vec = self.e.signed_nn(g["y"], verts, normals)
+        return verts.cpu(), jtr.cpu(), normals.cpu(), d.cpu(), idx.cpu().long(), vec.cpu()
+
+    def denoised(self, smplh_np, psd, b, x, t):
+        self.e.load_body(smplh_np)
+        self.e.load_projector(psd, 10, 20)
+        self.e.bind_correction(b["hand_pose"], b["betas"], b["obj_points"], past_len=10)
+        xg = x.clone().cuda()
+        return self.e.correction_apply(xg, torch.from_numpy(b["gt"]).cuda(), t).cpu()
+
+
+@pytest.fixture(scope="module", params=["oracle", pytest.param("cuda-simt", marks=pytest.mark.gpu), pytest.param("cuda-tcgen05", marks=pytest.mark.gpu)])
+def backend(request):
+    if request.param == "oracle":
+        return OracleBackend()
+    return EngineBackend(request.param.split("-")[1])
+
+
+@pytest.mark.parametrize("source", ["random", "ref"])
+def test_golden_smpl(backend, source):
+    g = load("mdm_smpl_%s.npz" % source)
+    sd = mdm_weights("smpl", source)
+    b = S.make_smpl_batch(B=2, T=30)
+    x = torch.from_numpy(S.noise_tape(b["gt"].shape, 0)[0])
+    with torch.no_grad():
+        out = backend.smpl_forward(sd, x, g["t"], torch.from_numpy(b["cond"]))
+        assert rel(out, g["forward"]) < 2e-4
+        tape = torch.from_numpy(S.noise_tape(b["gt"].shape, 5))
+        loop = backend.smpl_loop(sd, b, tape, 5)
+    assert rel(loop, g["loop5"]) < 1e-3
+
+
+@pytest.mark.parametrize("source", ["random", "ref"])
+def test_golden_skeleton_config1(backend, source):
+    """BASELINE configs[0]: skeleton diffusion, 1 DDPM step, B=2, T=15."""
+    g = load("mdm_skeleton_%s.npz" % source)
+    sd = mdm_weights("skeleton", source)
+    b = S.make_skeleton_batch(B=2, T=15)
+    tape = torch.from_numpy(S.noise_tape(b["gt"].shape, 1))
+    with torch.no_grad():
+        fwd, s, x0 = backend.skeleton(sd, b, tape[0], tape)
+    assert rel(fwd, g["forward"]) < 2e-4 and rel(s, g["step_sample"]) < 2e-4 and rel(x0, g["step_x0"]) < 2e-4
+
+
+@pytest.mark.parametrize("source", ["random", "ref"])
+def test_golden_projector(backend, source):
+    g = load("projector_%s.npz" % source)
+    with torch.no_grad():
+        out = backend.projector(projector_weights(source), g["ang"], g["tr"], g["hv"], g["contact"])
+    assert rel(out, g["out"]) < 1e-4
+
+
+def test_golden_geometry(backend, smplh_np):
+    g = load("geometry.npz")
+    with torch.no_grad():
+        verts, jtr, normals, d, idx, vec = backend.geometry(smplh_np, g)
+    sub = slice(None, None, 53)
+    assert rel(verts[:, sub], g["verts_sub"]) < 1e-5 and rel(jtr, g["jtr"]) < 1e-5
+    assert rel(normals[:, sub], g["normals_sub"]) < 1e-4
+    assert torch.equal(idx.long(), g["yidx"].long())
+    assert rel(d, g["y2x_signed"]) < 1e-5 and rel(vec, g["y2x"]) < 1e-5
+
+
+def test_golden_denoised_fn(backend, smplh_np):
+    g = load("denoised_fn_random.npz")
+    psd = projector_weights("random")
+    b = S.make_smpl_batch(B=2, T=30)
+    with torch.no_grad():
+        assert rel(backend.denoised(smplh_np, psd, b, g["x"], 450), g["out450"]) < 1e-4
+        assert rel(backend.denoised(smplh_np, psd, b, g["x"], 0), g["out0"]) < 1e-4

@@ -13,10 +13,12 @@ from tests.helpers import mdm_weights, projector_weights, rel, smplh_torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=["simt", "tcgen05"])
+def eng(request):
+    """Every parity test runs with both GEMM backends (fp32 SIMT and tcgen05 3xTF32)."""
     from interdiff_b200.engine import Engine
     e = Engine("cuda:0")
+    e.set_gemm_backend(request.param)
     yield e
     e.close()
 

@@ -86,7 +86,7 @@ def cpu_reference_rate(n_denoise_steps, threads=None, seed=233):
     from interdiff_b200 import synthetic as S
     from oracle import restate as R
     from tests.helpers import mdm_weights
-    cores = threads or os.cpu_count()
+    cores = threads or int(os.environ.get("IDB_CPU_THREADS", "0")) or min(os.cpu_count(), 32)
     torch.set_num_threads(cores)
     w = WORKLOAD
     sd = mdm_weights("smpl", "auto")
@@ -212,13 +212,13 @@ def run_ours(args):
         value = total_steps / (dev_ms / 1000.0)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                     ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f32 (fp32 SIMT)" if (args.backend or "simt") == "simt" else "f32 via 3xTF32 tcgen05 (fp32 accumulate)",
+                    dtype="f32 (fp32 SIMT GEMMs)" if args.backend == "simt" else "f32 (GEMMs: 3xTF32 split on tcgen05, fp32 TMEM accumulate)",
                     data="synthetic",
                     config=dict(workload="SMPL diffusion, 100 DDPM steps, B=64 per GPU, T=30 (past 10 + future 20), 144 channels, "
                                          "inpainting mask on the past, no correction (BASELINE configs[1])",
                                 weights="reference checkpoint (exported)" if _have_ref_weights() else "seeded random init",
                                 l2="flushed between timed iterations (256 MB fill outside the event pair)",
-                                cuda_graph=True, gemm_backend=args.backend or "simt"),
+                                cuda_graph=True, gemm_backend=args.backend or "tcgen05"),
                     e2e=dict(value=total_steps / (e2e_ms / 1000.0), unit=UNIT,
                              h2d_bytes_per_step=int(h_gt.numel() * 4 + h_mask.numel() + h_cond.numel() * 4 + h_xT.numel() * 4),
                              d2h_bytes_per_step=int(h_out.numel() * 4)),
@@ -247,7 +247,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--backend", default=None, choices=[None, "simt", "tcgen05"])
-    ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

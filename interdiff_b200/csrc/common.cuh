@@ -75,7 +75,7 @@ struct idb_handle {
     std::string err;
     int device = 0, sm_count = 148;
     long long launches = 0;   // kernels launched through this handle (bench's gpu_launches)
-    int gemm_backend = 0;     // 0 = fp32 SIMT, 1 = tcgen05 3xTF32
+    int gemm_backend = 1;     // 0 = fp32 SIMT (debug / bisect), 1 = tcgen05 3xTF32 (default)
     Denoiser den;
     Diffusion diff;
     BodyModel* body = nullptr;

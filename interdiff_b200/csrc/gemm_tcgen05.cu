@@ -34,6 +34,13 @@ template <int BN> struct Cfg {
     static constexpr int RAW_BYTES = (BM + BN) * BK * 4;     // A then W, both 1024-byte multiples
     static constexpr int STAGE_BYTES = 2 * RAW_BYTES;        // [raw->big | small]
     static constexpr int STAGES = (BN == 128) ? 3 : 4;
+    // TMEM accumulators.  The tensor core truncates (rounds toward zero) on every fp32 accumulate,
+    // so the error grows with the number of sequential accumulations into one accumulator
+    // (measured: 2e-6 relative at K=256 with a single accumulator).  The big x big products are
+    // therefore spread round-robin over NACC_MAIN accumulators and the two small cross terms get
+    // their own one; the epilogue adds them up with IEEE round-to-nearest adds.  512 columns total.
+    static constexpr int NACC_MAIN = (BN == 128) ? 3 : 7;
+    static constexpr int TMEM_COLS = 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -133,7 +140,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -169,9 +176,11 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     const uint32_t koff = kk * UMMA_K * 4;   // 32 bytes per k-step inside the swizzle row
                     const uint64_t dab = make_smem_desc(a_big + koff), das = make_smem_desc(a_sml + koff);
                     const uint64_t dwb = make_smem_desc(w_big + koff), dws = make_smem_desc(w_sml + koff);
-                    umma_tf32(tmem_base, das, dwb, idesc, (kb | kk) ? 1u : 0u);
-                    umma_tf32(tmem_base, dab, dws, idesc, 1u);
-                    umma_tf32(tmem_base, dab, dwb, idesc, 1u);
+                    const uint32_t acc_main = tmem_base + (uint32_t)((kb % cfg::NACC_MAIN) * BN);
+                    const uint32_t acc_small = tmem_base + (uint32_t)(cfg::NACC_MAIN * BN);
+                    umma_tf32(acc_small, das, dwb, idesc, (kb | kk) ? 1u : 0u);
+                    umma_tf32(acc_small, dab, dws, idesc, 1u);
+                    umma_tf32(acc_main, dab, dwb, idesc, (kb >= cfg::NACC_MAIN || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(bar_empty(s));      // stage reusable once these MMAs have read it
             }
@@ -205,24 +214,33 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int row = m0 + q * 32 + lane;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float v[32];
+            const int nacc = (num_kb < cfg::NACC_MAIN ? num_kb : cfg::NACC_MAIN) + 1;   // used main accumulators + the small one
+#pragma unroll 1
+            for (int a = 0; a < nacc; a++) {
+                // a == nacc-1 is the small-term accumulator (added last)
+                const int acc = (a == nacc - 1) ? cfg::NACC_MAIN : a;
+                uint32_t u[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                      "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+                      "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+                      "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = (a == 0) ? __uint_as_float(u[j]) : v[j] + __uint_as_float(u[j]);
+            }
             if (row < M) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int col = n0 + c0 + j;
                     if (col + 3 < N) {
-                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         if (epi & EPI_BIAS) {
                             const float4 bb = *reinterpret_cast<const float4*>(bias + col);
                             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
@@ -237,7 +255,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     } else {
                         for (int e = 0; e < 4; e++) {
                             if (col + e >= N) break;
-                            float o = __uint_as_float(v[j + e]);
+                            float o = v[j + e];
                             if (epi & EPI_BIAS) o += bias[col + e];
                             if (epi & EPI_GELU) o = gelu_erf(o);
                             if (epi & EPI_SILU) o = silu(o);
@@ -253,7 +271,7 @@ gemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::TMEM_COLS) : "memory");
     }
 }
 

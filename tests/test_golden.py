@@ -147,7 +147,7 @@ def test_golden_geometry(backend, smplh_np):
     assert rel(verts[:, sub], g["verts_sub"]) < 1e-5 and rel(jtr, g["jtr"]) < 1e-5
     assert rel(normals[:, sub], g["normals_sub"]) < 1e-4
     assert torch.equal(idx.long(), g["yidx"].long())
-    assert rel(d, g["y2x_signed"]) < 1e-5 and rel(vec, g["y2x"]) < 1e-5
+    assert rel(d, g["y2x_signed"]) < 5e-5 and rel(vec, g["y2x"]) < 5e-5  # values are O(1e-2) differences of O(1) coordinates
 
 
 def test_golden_denoised_fn(backend, smplh_np):

@@ -140,6 +140,14 @@ int idb_correction_apply(idb_handle* h, float* x0, const float* gt, int t, uint8
  * 2 residual add, 3 SiLU (the fused epilogues of the nn.Linear calls of the denoiser). */
 int idb_debug_gemm(idb_handle* h, const float* A, const float* W, const float* bias, const float* res, float* C,
                    int M, int N, int K, int epi, void* stream);
+/* the same launch repeated `iters` times from C (roofline leg: host overhead per launch stays small) */
+int idb_debug_gemm_repeat(idb_handle* h, const float* A, const float* W, const float* bias, const float* res, float* C,
+                          int M, int N, int K, int epi, int iters, void* stream);
+
+/* test hook: number of round-robin TMEM accumulators of the tcgen05 GEMM (0 = default) */
+int idb_debug_set_gemm_accumulators(int n);
+/* one launch with a per-CTA clock64 timeline (16 slots per CTA) of the tcgen05 kernel's pipeline */
+int idb_debug_gemm_trace(idb_handle* h, const float* A, const float* W, float* C, int M, int N, int K, long long* trace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -53,3 +53,26 @@ extern "C" int idb_debug_gemm(idb_handle* h, const float* A, const float* W, con
     if (!h || !A || !W || !C) return IDB_ERR_ARG;
     return idb_gemm(h, A, K, W, K, bias, res, N, C, N, M, N, K, epi, (cudaStream_t)stream);
 }
+
+/* same GEMM launched `iters` times back to back from C (keeps host overhead per launch small) */
+extern "C" int idb_debug_gemm_repeat(idb_handle* h, const float* A, const float* W, const float* bias, const float* res, float* C,
+                                     int M, int N, int K, int epi, int iters, void* stream) {
+    if (!h || !A || !W || !C) return IDB_ERR_ARG;
+    for (int i = 0; i < iters; i++) {
+        int rc = idb_gemm(h, A, K, W, K, bias, res, N, C, N, M, N, K, epi, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return IDB_OK;
+}
+
+extern long long* g_idb_gemm_trace;
+/* one GEMM launch with a per-CTA clock64 timeline written to trace[ctas][16] (device) */
+extern "C" int idb_debug_gemm_trace(idb_handle* h, const float* A, const float* W, float* C, int M, int N, int K, long long* trace, void* stream) {
+    if (!h || !A || !W || !C || !trace) return IDB_ERR_ARG;
+    g_idb_gemm_trace = trace;
+    return idb_gemm(h, A, K, W, K, nullptr, nullptr, N, C, N, M, N, K, 0, (cudaStream_t)stream);
+}
+
+extern int g_idb_gemm_nacc;
+/* test hook: number of round-robin TMEM accumulators for the big x big products (0 = default) */
+extern "C" int idb_debug_set_gemm_accumulators(int n) { g_idb_gemm_nacc = n; return IDB_OK; }

@@ -33,6 +33,8 @@ struct DenoiserLayer {
     bool qan = false;
     // standard self-attention
     float *w_qkv = nullptr, *b_qkv = nullptr, *w_o = nullptr, *b_o = nullptr;
+    // folded self-attention: [Wq; Wk; (Wo_h Wv_h) for h] (1536 x 256), bias [bq; bk; 0], bo' = bo + sum_h Wo_h bv_h
+    float *w_qkvf = nullptr, *b_qkvf = nullptr, *bo_f = nullptr;
     // QaN
     float *qt = nullptr, *wk = nullptr;  // qt: [3*N][D] folded queries
     // cross attention
@@ -40,6 +42,7 @@ struct DenoiserLayer {
     float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
     float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr, *ln3w = nullptr, *ln3b = nullptr;
     float* kv_mem = nullptr;  // [Tm*B][2D] cross-attention K|V of the bound memory
+    float* vp_mem = nullptr;  // [Tm*B][H*D] values folded with the out-projection: (V_h Wo_h^T)
 };
 
 struct Denoiser {
@@ -49,6 +52,7 @@ struct Denoiser {
     std::vector<DenoiserLayer> layers;
     std::vector<float*> owned;              // packed buffers to free
     float *w_inT = nullptr, *b_in = nullptr;      // [C][D] k-major input embedding, summed bias
+    float *w_in = nullptr, *w_out = nullptr;      // nn.Linear layouts for the GEMM: [D][C], [Clin][D]
     float *w_outT = nullptr, *b_out = nullptr;    // [D][Clin] k-major output heads
     float *pe = nullptr; int pe_rows = 0;         // sinusoid table [rows][D]
     float *te_w0T = nullptr, *te_b0 = nullptr, *te_w2T = nullptr, *te_b2 = nullptr;
@@ -56,6 +60,8 @@ struct Denoiser {
     int B = 0, T = 0, M = 0, Tm = 0;
     float *cond = nullptr, *zero_pose = nullptr;
     float *temb = nullptr, *h = nullptr, *h2 = nullptr, *qkv = nullptr, *att = nullptr, *ff = nullptr, *qc = nullptr;
+    float *xtok = nullptr, *addend = nullptr, *lin = nullptr, *z = nullptr;
+    int* step_cur = nullptr;
     long long* t_dev = nullptr;
     std::vector<float*> bound;              // workspaces to free on rebind
 };

@@ -15,12 +15,24 @@
 // ------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int D = 256;  // d_model is fixed at 256 for both shipped models (checked at init)
+constexpr int D = 256;    // d_model is fixed at 256 for both shipped models (checked at init)
+constexpr int HD = 64;    // head dim
+constexpr int SLAB = 16;  // query rows per block in the per-sample attention kernels
+constexpr int LDZ = D + 4;
 
-// TimestepEmbedder.forward (model/layers.py:42-43): pe[t] -> Linear -> SiLU -> Linear. grid B, block 256
-__global__ void k_temb(const float* __restrict__ pe, const long long* __restrict__ t, const float* __restrict__ w0T,
-                       const float* __restrict__ b0, const float* __restrict__ w2T, const float* __restrict__ b2,
-                       float* __restrict__ out, int pe_rows) {
+// One block per step: t_dev[b] = tbl[counter].t for this step, step_cur = counter, counter -= 1.
+__global__ void k_step_begin(long long* t_dev, const StepParams* tbl, int* counter, int* step_cur, int B) {
+    const int c = *counter;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) t_dev[i] = tbl[c].t;
+    __syncthreads();
+    if (threadIdx.x == 0) { *step_cur = c; *counter = c - 1; }
+}
+
+// TimestepEmbedder.forward (model/layers.py:42-43): pe[t] -> Linear -> SiLU -> Linear, then the
+// per-token addend of the input embedding: add[b*T+t][:] = temb[b] + pe[t] + b_in   (grid B, block 256)
+__global__ void k_temb_addend(const float* __restrict__ pe, const long long* __restrict__ t, const float* __restrict__ w0T,
+                              const float* __restrict__ b0, const float* __restrict__ w2T, const float* __restrict__ b2,
+                              const float* __restrict__ b_in, float* __restrict__ add, int pe_rows, int T) {
     __shared__ float s_in[D], s_h[D];
     const int b = blockIdx.x, n = threadIdx.x;
     long long ti = t[b];
@@ -28,59 +40,45 @@ __global__ void k_temb(const float* __restrict__ pe, const long long* __restrict
     if (ti >= pe_rows) ti = pe_rows - 1;
     s_in[n] = pe[(size_t)ti * D + n];
     __syncthreads();
-    float a = b0[n];
-#pragma unroll 8
-    for (int k = 0; k < D; k++) a = fmaf(w0T[k * D + n], s_in[k], a);
-    s_h[n] = silu(a);
+    float a0 = b0[n], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 16
+    for (int k = 0; k < D; k += 4) {
+        a0 = fmaf(w0T[(k + 0) * D + n], s_in[k + 0], a0); a1 = fmaf(w0T[(k + 1) * D + n], s_in[k + 1], a1);
+        a2 = fmaf(w0T[(k + 2) * D + n], s_in[k + 2], a2); a3 = fmaf(w0T[(k + 3) * D + n], s_in[k + 3], a3);
+    }
+    s_h[n] = silu((a0 + a1) + (a2 + a3));
     __syncthreads();
-    a = b2[n];
-#pragma unroll 8
-    for (int k = 0; k < D; k++) a = fmaf(w2T[k * D + n], s_h[k], a);
-    out[b * D + n] = a;
+    a0 = b2[n]; a1 = a2 = a3 = 0.f;
+#pragma unroll 16
+    for (int k = 0; k < D; k += 4) {
+        a0 = fmaf(w2T[(k + 0) * D + n], s_h[k + 0], a0); a1 = fmaf(w2T[(k + 1) * D + n], s_h[k + 1], a1);
+        a2 = fmaf(w2T[(k + 2) * D + n], s_h[k + 2], a2); a3 = fmaf(w2T[(k + 3) * D + n], s_h[k + 3], a3);
+    }
+    const float base = ((a0 + a1) + (a2 + a3)) + b_in[n];
+    for (int tt = 0; tt < T; tt++) add[((size_t)b * T + tt) * D + n] = base + pe[(size_t)tt * D + n];
 }
 
-// Input embedding (model/diffusion_smpl.py:227-232): h[b,t,:] = W_in . x[b,:,t] + b_in + temb[b] + pe[t].
-// x layout (B,1,C,T).  grid B, block 256 (one output feature per thread, all T frames in registers).
-template <int TT>
-__global__ void k_embed(const float* __restrict__ x, const float* __restrict__ w_inT, const float* __restrict__ b_in,
-                        const float* __restrict__ temb, const float* __restrict__ pe, float* __restrict__ h,
-                        int C, int T) {
-    extern __shared__ float xs[];  // [C][T]
-    const int b = blockIdx.x, n = threadIdx.x;
-    for (int i = n; i < C * T; i += blockDim.x) xs[i] = x[(size_t)b * C * T + i];
+// (B,1,C,T) -> token-major [B*T][C] through a shared-memory transpose (grid B)
+__global__ void k_to_tokens(const float* __restrict__ x, float* __restrict__ xtok, int C, int Cp, int T) {
+    extern __shared__ float sx[];   // [C][T+1]
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < C * T; i += blockDim.x) sx[(i / T) * (T + 1) + i % T] = x[(size_t)b * C * T + i];
     __syncthreads();
-    for (int t0 = 0; t0 < T; t0 += TT) {
-        float acc[TT];
-#pragma unroll
-        for (int i = 0; i < TT; i++) acc[i] = 0.f;
-        for (int c = 0; c < C; c++) {
-            const float w = w_inT[c * D + n];
-            const float* xr = xs + c * T + t0;
-#pragma unroll
-            for (int i = 0; i < TT; i++)
-                if (t0 + i < T) acc[i] = fmaf(w, xr[i], acc[i]);
-        }
-        const float base = b_in[n] + temb[b * D + n];
-#pragma unroll
-        for (int i = 0; i < TT; i++)
-            if (t0 + i < T) h[((size_t)b * T + t0 + i) * D + n] = (acc[i] + base) + pe[(size_t)(t0 + i) * D + n];
+    for (int i = threadIdx.x; i < Cp * T; i += blockDim.x) {
+        const int t = i / Cp, c = i % Cp;
+        xtok[((size_t)b * T + t) * Cp + c] = c < C ? sx[c * (T + 1) + t] : 0.f;   // zero padding columns
     }
 }
 
-// out[m,:] = LayerNorm(a[m,:] (+ r[m,:])) * w + b.  warp per row, D = 256.
-__global__ void k_add_ln(const float* __restrict__ a, const float* __restrict__ r, const float* __restrict__ w,
-                         const float* __restrict__ bb, float* __restrict__ out, int M) {
+// out[m,:] = LayerNorm(a[m,:]) * w + b.  warp per row, D = 256.
+__global__ void k_ln(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bb,
+                     float* __restrict__ out, int M) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= M) return;
     const float4* pa = reinterpret_cast<const float4*>(a + (size_t)warp * D);
     float v[8];
     float4 u0 = pa[lane], u1 = pa[lane + 32];
     v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w; v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
-    if (r) {
-        const float4* pr = reinterpret_cast<const float4*>(r + (size_t)warp * D);
-        float4 q0 = pr[lane], q1 = pr[lane + 32];
-        v[0] += q0.x; v[1] += q0.y; v[2] += q0.z; v[3] += q0.w; v[4] += q1.x; v[5] += q1.y; v[6] += q1.z; v[7] += q1.w;
-    }
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) s += v[i];
@@ -101,127 +99,201 @@ __global__ void k_add_ln(const float* __restrict__ a, const float* __restrict__ 
     po[lane] = o0; po[lane + 32] = o1;
 }
 
-// Multi-head attention core softmax(q k^T / sqrt(hd)) v for one (sample, head) per block.
-// q rows: (b*qsb + i*qst), k/v rows: (b*ksb + j*kst)  (strides in rows) so the same kernel reads
-// batch-major tokens (self-attention) and the seq-first memory K/V (cross-attention).
-__global__ void k_mha(const float* __restrict__ q, int ldq, int qsb, int qst,
-                      const float* __restrict__ k, const float* __restrict__ v, int ldkv, int ksb, int kst,
-                      float* __restrict__ out, int ldo, int Tq, int Tk, int H, float scale) {
-    constexpr int HD = 64;
-    extern __shared__ float sm[];
-    float* sq = sm;                    // [Tq][HD]
-    float* sk = sq + Tq * HD;          // [Tk][HD+1]
-    float* sv = sk + Tk * (HD + 1);    // [Tk][HD]
-    float* sp = sv + Tk * HD;          // [Tq][Tk]
-    const int b = blockIdx.x / H, hh = blockIdx.x % H, tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < Tq * HD; i += nt) {
-        int r = i / HD, c = i % HD;
-        sq[i] = q[(size_t)(b * qsb + r * qst) * ldq + hh * HD + c] * scale;
-    }
-    for (int i = tid; i < Tk * HD; i += nt) {
-        int r = i / HD, c = i % HD;
-        size_t row = (size_t)(b * ksb + r * kst) * ldkv;
-        sk[r * (HD + 1) + c] = k[row + hh * HD + c];
-        sv[i] = v[row + hh * HD + c];
-    }
-    __syncthreads();
-    for (int i = tid; i < Tq * Tk; i += nt) {
-        int r = i / Tk, c = i % Tk;
-        float a = 0.f;
-#pragma unroll 16
-        for (int d = 0; d < HD; d++) a = fmaf(sq[r * HD + d], sk[c * (HD + 1) + d], a);
-        sp[i] = a;
-    }
-    __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-    for (int r = warp; r < Tq; r += nw) {
-        float mx = -INFINITY;
-        for (int c = lane; c < Tk; c += 32) mx = fmaxf(mx, sp[r * Tk + c]);
-        mx = warp_max(mx);
-        float s = 0.f;
-        for (int c = lane; c < Tk; c += 32) { float e = expf(sp[r * Tk + c] - mx); sp[r * Tk + c] = e; s += e; }
-        s = warp_sum(s);
-        const float inv = 1.0f / s;
-        for (int c = lane; c < Tk; c += 32) sp[r * Tk + c] *= inv;
-    }
-    __syncthreads();
-    for (int i = tid; i < Tq * HD; i += nt) {
-        int r = i / HD, c = i % HD;
-        float a = 0.f;
-        for (int j = 0; j < Tk; j++) a = fmaf(sp[r * Tk + j], sv[j * HD + c], a);
-        out[(size_t)(b * qsb + r * qst) * ldo + hh * HD + c] = a;
-    }
+// LayerNorm of one 256-wide row held in shared memory by one warp (lane holds cols 4*lane.. and 128+4*lane..)
+__device__ __forceinline__ void warp_ln_row(const float* __restrict__ zrow, const float* __restrict__ w, const float* __restrict__ bb,
+                                            float* __restrict__ dst, int lane) {
+    const float4 u0 = *reinterpret_cast<const float4*>(zrow + lane * 4), u1 = *reinterpret_cast<const float4*>(zrow + 128 + lane * 4);
+    float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+    const float4 w0 = *reinterpret_cast<const float4*>(w + lane * 4), w1 = *reinterpret_cast<const float4*>(w + 128 + lane * 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(bb + lane * 4), b1 = *reinterpret_cast<const float4*>(bb + 128 + lane * 4);
+    float4 o0, o1;
+    o0.x = (v[0] - mean) * rstd * w0.x + b0.x; o0.y = (v[1] - mean) * rstd * w0.y + b0.y;
+    o0.z = (v[2] - mean) * rstd * w0.z + b0.z; o0.w = (v[3] - mean) * rstd * w0.w + b0.w;
+    o1.x = (v[4] - mean) * rstd * w1.x + b1.x; o1.y = (v[5] - mean) * rstd * w1.y + b1.y;
+    o1.z = (v[6] - mean) * rstd * w1.z + b1.z; o1.w = (v[7] - mean) * rstd * w1.w + b1.w;
+    *reinterpret_cast<float4*>(dst + lane * 4) = o0;
+    *reinterpret_cast<float4*>(dst + 128 + lane * 4) = o1;
 }
 
-// QaN block + residual + LayerNorm1 for one sample per block (model/sublayers.py:343-352 + :332):
-//   P[t', s*N+n] = h[t'] . Qt[s][n]         (Qt = rotary-folded, 1/16-scaled normalised queries)
-//   a[t,n,:] = softmax over valid key slots s in {t-1,t,t+1} of P[t+s-1, s*N+n]
-//   y[t] = sum_s (sum_n wk[n] a[t,n,s]) h[t+s-1];   out = LN1(h + y)
-__global__ void k_qan_ln(const float* __restrict__ h, const float* __restrict__ qt, const float* __restrict__ wk,
-                         const float* __restrict__ lnw, const float* __restrict__ lnb, float* __restrict__ out,
-                         int T, int N) {
-    constexpr int LD = D + 4;
+__device__ __forceinline__ float dot64(const float* __restrict__ a, const float* __restrict__ b) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; d += 8) {
+        const float4 x0 = *reinterpret_cast<const float4*>(a + d), y0 = *reinterpret_cast<const float4*>(b + d);
+        const float4 x1 = *reinterpret_cast<const float4*>(a + d + 4), y1 = *reinterpret_cast<const float4*>(b + d + 4);
+        s0 = fmaf(x0.x, y0.x, s0); s0 = fmaf(x0.y, y0.y, s0); s0 = fmaf(x0.z, y0.z, s0); s0 = fmaf(x0.w, y0.w, s0);
+        s1 = fmaf(x1.x, y1.x, s1); s1 = fmaf(x1.y, y1.y, s1); s1 = fmaf(x1.z, y1.z, s1); s1 = fmaf(x1.w, y1.w, s1);
+    }
+    return s0 + s1;
+}
+
+// Attention core + out-projection (folded into the values) + residual + LayerNorm for a slab of
+// <= 16 query rows of one sample.  grid (B, ceil(T/16)), block 256.
+//   q rows  : q[(b*T + r) * ldq + h*64 + d]                          (pre-projected queries)
+//   keys    : k[(b*ksb + j*kst) * ldk + h*64 + d], j < Tk            (row strides so the same kernel
+//   values' : v[(b*ksb + j*kst) * ldv + h*256 + n]                    reads self- and cross-attention)
+//             = (V_h W_o,h^T)[j][n]: value vectors already multiplied by the head's out-proj block
+//   out[r]  = LN( res[r] + bo + sum_h sum_j softmax_j(q_h[r].k_h[j] / 8) v'_h[j] )
+__global__ void __launch_bounds__(256)
+k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
+          int ksb, int kst, const float* __restrict__ res, const float* __restrict__ bo, const float* __restrict__ lnw,
+          const float* __restrict__ lnb, float* __restrict__ out, int T, int Tk, int H) {
     extern __shared__ __align__(16) float sm[];
-    float* sh = sm;                 // [T][LD]
-    float* sqt = sh + T * LD;       // [32][LD]  (3N <= 32 vectors)
-    float* sP = sqt + 32 * LD;      // [T][32]
-    float* sc = sP + T * 32;        // [T][4]
-    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const int NQ = 3 * N;
-    for (int i = tid; i < T * (D / 4); i += nt) {
-        int r = i / (D / 4), c = i % (D / 4);
-        *reinterpret_cast<float4*>(sh + r * LD + c * 4) = reinterpret_cast<const float4*>(h + ((size_t)b * T + r) * D)[c];
+    const int LDK = HD + 4;
+    float* s_q = sm;                       // [SLAB][D]
+    float* s_k = s_q + SLAB * D;           // [H*Tk][LDK]
+    float* s_a = s_k + H * Tk * LDK;       // [SLAB][H*Tk]
+    float* s_z = s_a + SLAB * H * Tk;      // [SLAB][LDZ]
+    const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
+    const int HT = H * Tk;
+    for (int i = tid; i < nr * (D / 4); i += 256) {
+        const int r = i / (D / 4), c = i % (D / 4);
+        reinterpret_cast<float4*>(s_q + r * D)[c] = reinterpret_cast<const float4*>(q + (size_t)(b * T + r0 + r) * ldq)[c];
     }
-    for (int i = tid; i < 32 * (D / 4); i += nt) {
-        int r = i / (D / 4), c = i % (D / 4);
-        float4 v = (r < NQ) ? reinterpret_cast<const float4*>(qt + (size_t)r * D)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(sqt + r * LD + c * 4) = v;
+    for (int i = tid; i < Tk * (D / 4); i += 256) {
+        const int j = i / (D / 4), c = i % (D / 4);          // c-th float4 of key row j: head c/16, offset (c%16)*4
+        const float4 kv = reinterpret_cast<const float4*>(k + (size_t)(b * ksb + j * kst) * ldk)[c];
+        *reinterpret_cast<float4*>(s_k + ((c / 16) * Tk + j) * LDK + (c % 16) * 4) = kv;
     }
     __syncthreads();
-    for (int i = tid; i < T * 32; i += nt) {
-        int r = i >> 5, j = i & 31;
-        float a = 0.f;
-        const float4* ph = reinterpret_cast<const float4*>(sh + r * LD);
-        const float4* pq = reinterpret_cast<const float4*>(sqt + j * LD);
-#pragma unroll 8
-        for (int c = 0; c < D / 4; c++) {
-            float4 x = ph[c], y = pq[c];
-            a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
+    const float scale = 0.125f;   // 1/sqrt(64)
+    for (int i = tid; i < nr * HT; i += 256) {
+        const int r = i / HT, hj = i % HT, hh = hj / Tk;
+        s_a[r * HT + hj] = dot64(s_q + r * D + hh * HD, s_k + hj * LDK) * scale;
+    }
+    __syncthreads();
+    for (int g = tid; g < nr * H; g += 256) {
+        float* row = s_a + (g / H) * HT + (g % H) * Tk;
+        float mx = -INFINITY;
+        for (int j = 0; j < Tk; j++) mx = fmaxf(mx, row[j]);
+        float s = 0.f;
+        for (int j = 0; j < Tk; j++) { const float e = expf(row[j] - mx); row[j] = e; s += e; }
+        const float inv = 1.0f / s;
+        for (int j = 0; j < Tk; j++) row[j] *= inv;
+    }
+    __syncthreads();
+    {
+        const int n = tid;
+        float acc[SLAB];
+#pragma unroll
+        for (int r = 0; r < SLAB; r++) acc[r] = 0.f;
+        for (int hh = 0; hh < H; hh++) {
+#pragma unroll 2
+            for (int j = 0; j < Tk; j++) {
+                const float vv = __ldg(v + (size_t)(b * ksb + j * kst) * ldv + hh * D + n);
+                const float* ap = s_a + hh * Tk + j;
+#pragma unroll
+                for (int r = 0; r < SLAB; r++) acc[r] = fmaf(ap[r * HT], vv, acc[r]);   // rows >= nr hold stale but finite values
+            }
         }
-        sP[i] = a;
+        const float bb = bo[n];
+#pragma unroll
+        for (int r = 0; r < SLAB; r++)
+            if (r < nr) s_z[r * LDZ + n] = (acc[r] + bb) + res[(size_t)(b * T + r0 + r) * D + n];
     }
     __syncthreads();
-    for (int t = tid; t < T; t += nt) {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < nr; r += 8) warp_ln_row(s_z + r * LDZ, lnw, lnb, out + (size_t)(b * T + r0 + r) * D, lane);
+}
+
+// QaN block + residual + LayerNorm1 (model/sublayers.py:343-352 + :332) for a slab of <= 16 rows of
+// one sample, with an optional LayerNorm applied to the input rows first (the previous layer's
+// pending norm3).   grid (B, ceil(T/16)), block 256.
+//   x = pre ? LN_pre(zin) : zin
+//   logit[t,n,s] = x[t+s-1] . Qt[s][n]   (Qt = rotary-folded, 1/16-scaled normalised queries; s = key slot)
+//   a = softmax over the valid slots;  y[t] = sum_s (sum_n wk[n] a[t,n,s]) x[t+s-1];  out = LN1(x + y)
+__global__ void __launch_bounds__(256)
+k_qan_ln(const float* __restrict__ zin, const float* __restrict__ prew, const float* __restrict__ preb,
+         const float* __restrict__ qt, const float* __restrict__ wk, const float* __restrict__ lnw,
+         const float* __restrict__ lnb, float* __restrict__ out, int T, int N) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_x = sm;                        // [SLAB+2][LDZ]   rows r0-1 .. r0+nr
+    float* s_qt = s_x + (SLAB + 2) * LDZ;   // [32][LDZ]
+    float* s_p = s_qt + 32 * LDZ;           // [SLAB][32]
+    float* s_c = s_p + SLAB * 32;           // [SLAB][4]
+    const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int NQ = 3 * N;
+    // rows r0-1 .. r0+nr (halo of one on each side), local index l = t - (r0 - 1)
+    for (int l = warp; l < nr + 2; l += 8) {
+        const int t = r0 - 1 + l;
+        if (t < 0 || t >= T) continue;
+        const float* src = zin + (size_t)(b * T + t) * D;
+        if (prew) {
+            warp_ln_row(src, prew, preb, s_x + l * LDZ, lane);
+        } else {
+            *reinterpret_cast<float4*>(s_x + l * LDZ + lane * 4) = *reinterpret_cast<const float4*>(src + lane * 4);
+            *reinterpret_cast<float4*>(s_x + l * LDZ + 128 + lane * 4) = *reinterpret_cast<const float4*>(src + 128 + lane * 4);
+        }
+    }
+    for (int i = tid; i < 32 * (D / 4); i += 256) {
+        const int r = i / (D / 4), c = i % (D / 4);
+        const float4 val = (r < NQ) ? reinterpret_cast<const float4*>(qt + (size_t)r * D)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(s_qt + r * LDZ + c * 4) = val;
+    }
+    __syncthreads();
+    // P[r][s*N+n] = x[t+s-1] . Qt[s*N+n]  for the slab rows t = r0 + r
+    for (int i = tid; i < nr * 32; i += 256) {
+        const int r = i >> 5, j = i & 31;
+        if (j >= NQ) continue;
+        const int s = j / N, t = r0 + r + s - 1;
+        float a = 0.f;
+        if (t >= 0 && t < T) {
+            const float4* px = reinterpret_cast<const float4*>(s_x + (r + s) * LDZ);
+            const float4* pq = reinterpret_cast<const float4*>(s_qt + j * LDZ);
+            float a1 = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < D / 4; c += 2) {
+                const float4 x0 = px[c], y0 = pq[c], x1 = px[c + 1], y1 = pq[c + 1];
+                a = fmaf(x0.x, y0.x, a); a = fmaf(x0.y, y0.y, a); a = fmaf(x0.z, y0.z, a); a = fmaf(x0.w, y0.w, a);
+                a1 = fmaf(x1.x, y1.x, a1); a1 = fmaf(x1.y, y1.y, a1); a1 = fmaf(x1.z, y1.z, a1); a1 = fmaf(x1.w, y1.w, a1);
+            }
+            a += a1;
+        }
+        s_p[i] = a;
+    }
+    __syncthreads();
+    for (int r = tid; r < nr; r += 256) {
+        const int t = r0 + r;
+        const bool v0 = t > 0, v2 = t < T - 1;
         float c0 = 0.f, c1 = 0.f, c2 = 0.f;
         for (int n = 0; n < N; n++) {
-            const float l1 = sP[t * 32 + N + n];
-            const bool v0 = t > 0, v2 = t < T - 1;
-            const float l0 = v0 ? sP[(t - 1) * 32 + n] : -INFINITY;
-            const float l2 = v2 ? sP[(t + 1) * 32 + 2 * N + n] : -INFINITY;
+            const float l1 = s_p[r * 32 + N + n];
+            const float l0 = v0 ? s_p[r * 32 + n] : -INFINITY;
+            const float l2 = v2 ? s_p[r * 32 + 2 * N + n] : -INFINITY;
             const float mx = fmaxf(l1, fmaxf(l0, l2));
             const float e0 = v0 ? expf(l0 - mx) : 0.f, e1 = expf(l1 - mx), e2 = v2 ? expf(l2 - mx) : 0.f;
             const float inv = 1.0f / (e0 + e1 + e2);
             const float w = wk[n];
             c0 = fmaf(w, e0 * inv, c0); c1 = fmaf(w, e1 * inv, c1); c2 = fmaf(w, e2 * inv, c2);
         }
-        sc[t * 4 + 0] = c0; sc[t * 4 + 1] = c1; sc[t * 4 + 2] = c2;
+        s_c[r * 4 + 0] = c0; s_c[r * 4 + 1] = c1; s_c[r * 4 + 2] = c2;
     }
     __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-    for (int t = warp; t < T; t += nw) {
-        const float c0 = sc[t * 4], c1 = sc[t * 4 + 1], c2 = sc[t * 4 + 2];
+    for (int r = warp; r < nr; r += 8) {
+        const int t = r0 + r;
+        const float c0 = s_c[r * 4], c1 = s_c[r * 4 + 1], c2 = s_c[r * 4 + 2];
+        float* xm = s_x + (r + 1) * LDZ;          // row t (becomes x + y in place: only this warp touches it now)
         float v[8];
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-            const int c = (lane + half * 32) * 4;
-            float4 x1 = *reinterpret_cast<const float4*>(sh + t * LD + c);
+            const int c = half * 128 + lane * 4;
+            const float4 x1 = *reinterpret_cast<const float4*>(xm + c);
             float4 y = make_float4(c1 * x1.x, c1 * x1.y, c1 * x1.z, c1 * x1.w);
             if (t > 0) {
-                float4 x0 = *reinterpret_cast<const float4*>(sh + (t - 1) * LD + c);
+                const float4 x0 = *reinterpret_cast<const float4*>(xm - LDZ + c);
                 y.x = fmaf(c0, x0.x, y.x); y.y = fmaf(c0, x0.y, y.y); y.z = fmaf(c0, x0.z, y.z); y.w = fmaf(c0, x0.w, y.w);
             }
             if (t < T - 1) {
-                float4 x2 = *reinterpret_cast<const float4*>(sh + (t + 1) * LD + c);
+                const float4 x2 = *reinterpret_cast<const float4*>(xm + LDZ + c);
                 y.x = fmaf(c2, x2.x, y.x); y.y = fmaf(c2, x2.y, y.y); y.z = fmaf(c2, x2.z, y.z); y.w = fmaf(c2, x2.w, y.w);
             }
             v[half * 4 + 0] = x1.x + y.x; v[half * 4 + 1] = x1.y + y.y; v[half * 4 + 2] = x1.z + y.z; v[half * 4 + 3] = x1.w + y.w;
@@ -236,79 +308,51 @@ __global__ void k_qan_ln(const float* __restrict__ h, const float* __restrict__ 
         const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-            const int c = (lane + half * 32) * 4;
-            float4 w4 = *reinterpret_cast<const float4*>(lnw + c), b4 = *reinterpret_cast<const float4*>(lnb + c), o;
+            const int c = half * 128 + lane * 4;
+            const float4 w4 = *reinterpret_cast<const float4*>(lnw + c), b4 = *reinterpret_cast<const float4*>(lnb + c);
+            float4 o;
             o.x = (v[half * 4 + 0] - mean) * rstd * w4.x + b4.x; o.y = (v[half * 4 + 1] - mean) * rstd * w4.y + b4.y;
             o.z = (v[half * 4 + 2] - mean) * rstd * w4.z + b4.z; o.w = (v[half * 4 + 3] - mean) * rstd * w4.w + b4.w;
-            *reinterpret_cast<float4*>(out + ((size_t)b * T + t) * D + c) = o;
+            *reinterpret_cast<float4*>(out + (size_t)(b * T + t) * D + c) = o;
         }
     }
 }
 
-// Output heads + layout back to (B,1,C,T) + optional inpainting blend
-// (model/diffusion_smpl.py:234-237,245; diffusion/gaussian_diffusion.py:307-311).
-// variant 0: C = Clin (body | obj heads).  variant 1 (skeleton, model/diffusion_skeleton.py:218-248):
-// Clin = c_body + 7; output channels [body | R(quat) p + trans for P points | pose7].
-// grid B, block 256; thread n < Clin computes output feature n for all frames.
-template <int TT>
-__global__ void k_heads(const float* __restrict__ h, const float* __restrict__ w_outT, const float* __restrict__ b_out,
-                        const float* __restrict__ zero_pose, const float* __restrict__ gt,
-                        const unsigned char* __restrict__ mask, float* __restrict__ out,
-                        int T, int Clin, int C, int variant, int c_body, int n_points) {
-    extern __shared__ __align__(16) float sm[];
-    float* sh = sm;              // [T][D]
-    float* so = sh + T * D;      // [Clin][T]  linear outputs
-    const int b = blockIdx.x, n = threadIdx.x;
-    for (int i = n; i < T * (D / 4); i += blockDim.x)
-        reinterpret_cast<float4*>(sh)[i] = reinterpret_cast<const float4*>(h + (size_t)b * T * D)[i];
+// Linear outputs lin[(b*T+t)][Clin] -> x0 (B,1,C,T) with the skeleton's keypoint re-derivation and
+// the inpainting blend (model/diffusion_smpl.py:245; model/diffusion_skeleton.py:218-248;
+// diffusion/gaussian_diffusion.py:307-311).  grid B, block 256.
+__global__ void k_heads_post(const float* __restrict__ lin, const float* __restrict__ zero_pose, const float* __restrict__ gt,
+                             const unsigned char* __restrict__ mask, float* __restrict__ out,
+                             int T, int Clin, int C, int variant, int c_body, int n_points) {
+    extern __shared__ float so[];   // [T][Clin+1]
+    const int b = blockIdx.x, LDS_ = Clin + 1;
+    for (int i = threadIdx.x; i < T * Clin; i += blockDim.x) so[(i / Clin) * LDS_ + i % Clin] = lin[(size_t)b * T * Clin + i];
     __syncthreads();
-    if (n < Clin) {
-        for (int t0 = 0; t0 < T; t0 += TT) {
-            float acc[TT];
-#pragma unroll
-            for (int i = 0; i < TT; i++) acc[i] = 0.f;
-            for (int k = 0; k < D; k++) {
-                const float w = w_outT[k * Clin + n];
-#pragma unroll
-                for (int i = 0; i < TT; i++)
-                    if (t0 + i < T) acc[i] = fmaf(w, sh[(t0 + i) * D + k], acc[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < TT; i++)
-                if (t0 + i < T) so[n * T + t0 + i] = acc[i] + b_out[n];
-        }
-    }
-    __syncthreads();
-    for (int i = n; i < C * T; i += blockDim.x) {
+    for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
         const int c = i / T, t = i % T;
-        float v;
+        const float* ro = so + t * LDS_;
+        float val;
         if (variant == 0 || c < c_body) {
-            v = so[c * T + t];
+            val = ro[c];
         } else if (c >= c_body + 3 * n_points) {
-            v = so[(c - 3 * n_points) * T + t];
+            val = ro[c - 3 * n_points];
         } else {
-            // calc_obj_pred: pose = [trans3, quat xyzw]; quaternion_to_matrix on (w,x,y,z) un-normalised
+            // calc_obj_pred: pose = [trans3, quat xyzw]; quaternion_to_matrix on (w,x,y,z), un-normalised
             const int p = (c - c_body) / 3, ax = (c - c_body) % 3;
-            const float* ps = so + c_body * T + t;  // pose component j at ps[j*T]
-            const float tx = ps[0 * T], ty = ps[1 * T], tz = ps[2 * T];
-            const float qi = ps[3 * T], qj = ps[4 * T], qk = ps[5 * T], qr = ps[6 * T];
+            const float* ps = ro + c_body;
+            const float tx = ps[0], ty = ps[1], tz = ps[2], qi = ps[3], qj = ps[4], qk = ps[5], qr = ps[6];
             const float two_s = 2.0f / (qr * qr + qi * qi + qj * qj + qk * qk);
             float r0, r1, r2, tr;
             if (ax == 0) { r0 = 1 - two_s * (qj * qj + qk * qk); r1 = two_s * (qi * qj - qk * qr); r2 = two_s * (qi * qk + qj * qr); tr = tx; }
             else if (ax == 1) { r0 = two_s * (qi * qj + qk * qr); r1 = 1 - two_s * (qi * qi + qk * qk); r2 = two_s * (qj * qk - qi * qr); tr = ty; }
             else { r0 = two_s * (qi * qk - qj * qr); r1 = two_s * (qj * qk + qi * qr); r2 = 1 - two_s * (qi * qi + qj * qj); tr = tz; }
             const float* zp = zero_pose + ((size_t)b * n_points + p) * 3;
-            v = (r0 * zp[0] + r1 * zp[1] + r2 * zp[2]) + tr;
+            val = (r0 * zp[0] + r1 * zp[1] + r2 * zp[2]) + tr;
         }
         const size_t o = (size_t)b * C * T + i;
-        if (mask && mask[o]) v = gt[o];
-        out[o] = v;
+        if (mask && mask[o]) val = gt[o];
+        out[o] = val;
     }
-}
-
-__global__ void k_fill_t(long long* t_dev, const StepParams* tbl, const int* counter, int B) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) t_dev[i] = tbl[*counter].t;
 }
 
 }  // namespace
@@ -342,6 +386,7 @@ static void denoiser_free_bound(Denoiser& d) {
     for (float* p : d.bound) cudaFree(p);
     d.bound.clear();
     if (d.t_dev) { cudaFree(d.t_dev); d.t_dev = nullptr; }
+    if (d.step_cur) { cudaFree(d.step_cur); d.step_cur = nullptr; }
     d.B = d.T = d.M = 0;
 }
 
@@ -444,6 +489,13 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
             bsum[n] = hbb[n] + hbo[n];
         }
         d.w_inT = P.up(wT); d.b_in = P.up(bsum);
+        const int Cp = (C + 3) & ~3;                      // row stride padded to 16 bytes for the GEMM
+        std::vector<float> wcat((size_t)D * Cp, 0.f);    // [D][Cp]: [W_body | W_obj | 0]
+        for (int n = 0; n < D; n++) {
+            for (int k = 0; k < c.c_body; k++) wcat[(size_t)n * Cp + k] = hwb[(size_t)n * c.c_body + k];
+            for (int k = 0; k < c.c_obj; k++) wcat[(size_t)n * Cp + c.c_body + k] = hwo[(size_t)n * c.c_obj + k];
+        }
+        d.w_in = P.up(wcat);
     }
     // output heads: [D][Clin] k-major; Clin = c_body + (variant 0 ? c_obj : 7)
     {
@@ -458,6 +510,10 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
             bcat[n] = n < c.c_body ? hbb[n] : hbo[n - c.c_body];
         }
         d.w_outT = P.up(wT); d.b_out = P.up(bcat);
+        std::vector<float> wcat((size_t)Clin * D);        // [Clin][D]: [W_bodyFinal; W_objFinal]
+        for (int n = 0; n < Clin; n++)
+            for (int k = 0; k < D; k++) wcat[(size_t)n * D + k] = n < c.c_body ? hwb[(size_t)n * D + k] : hwo[(size_t)(n - c.c_body) * D + k];
+        d.w_out = P.up(wcat);
     }
     // timestep MLP (k-major) + sinusoid table
     {
@@ -511,6 +567,25 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
             GET(w, p + "self_attn.in_proj_weight", 3 * D, D) GET(b, p + "self_attn.in_proj_bias", 3 * D)
             GET(wo, p + "self_attn.out_proj.weight", D, D) GET(bo, p + "self_attn.out_proj.bias", D)
             L.w_qkv = w->p; L.b_qkv = b->p; L.w_o = wo->p; L.b_o = bo->p;
+            // fold the out-projection into the value projection (exact algebra, float64 on the host):
+            //   sum_j a_j (x_j Wv_h^T + bv_h) Wo_h^T = sum_j a_j x_j (Wo_h Wv_h)^T + Wo_h bv_h
+            auto hw = P.host(w), hb = P.host(b), hwo = P.host(wo), hbo = P.host(bo);
+            std::vector<float> wf((size_t)(2 * D + H * D) * D), bf((size_t)2 * D + H * D, 0.f), bof(D);
+            std::copy(hw.begin(), hw.begin() + (size_t)2 * D * D, wf.begin());
+            std::copy(hb.begin(), hb.begin() + 2 * D, bf.begin());
+            for (int n = 0; n < D; n++) {
+                double bacc = hbo[n];
+                for (int hh = 0; hh < H; hh++) {
+                    for (int k = 0; k < D; k++) {
+                        double a = 0;
+                        for (int e = 0; e < HD; e++) a += (double)hwo[(size_t)n * D + hh * HD + e] * hw[(size_t)(2 * D + hh * HD + e) * D + k];
+                        wf[(size_t)(2 * D + hh * D + n) * D + k] = (float)a;
+                    }
+                    for (int e = 0; e < HD; e++) bacc += (double)hwo[(size_t)n * D + hh * HD + e] * hb[2 * D + hh * HD + e];
+                }
+                bof[n] = (float)bacc;
+            }
+            L.w_qkvf = P.up(wf); L.b_qkvf = P.up(bf); L.bo_f = P.up(bof);
         }
         {
             GET(w, p + "multihead_attn.in_proj_weight", 3 * D, D) GET(b, p + "multihead_attn.in_proj_bias", 3 * D)
@@ -537,74 +612,91 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
     Denoiser& d = h->den;
     if (!d.committed) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_commit first");
     if (T > d.pe_rows) return idb_fail(h, IDB_ERR_ARG, "T exceeds the positional table");
+    if (T > 64 || Tm > 16) return idb_fail(h, IDB_ERR_ARG, "supported window: T <= 64 frames, <= 16 memory tokens");
     if (d.cfg.variant == 1 && !zero_pose_obj) return idb_fail(h, IDB_ERR_ARG, "skeleton variant needs zero_pose_obj");
     cudaStream_t st = (cudaStream_t)stream;
-    const int M = B * T, F = d.cfg.d_ff;
-    const int npts = d.cfg.n_points > 0 ? d.cfg.n_points : 1;
+    const idb_denoiser_config& c = d.cfg;
+    const int M = B * T, F = c.d_ff, H = c.n_heads, C = c.c_body + c.c_obj + c.c_extra;
+    const int Clin = c.c_body + (c.variant == 0 ? c.c_obj : 7);
+    const int npts = c.n_points > 0 ? c.n_points : 1;
     if (B != d.B || T != d.T || Tm != d.Tm) {
         denoiser_free_bound(d);
         auto A = [&](float** p, size_t n) { int rc = idb_dev_alloc(h, p, n); if (!rc) d.bound.push_back(*p); return rc; };
         int rc = 0;
-        rc |= A(&d.cond, (size_t)Tm * B * D); rc |= A(&d.temb, (size_t)B * D); rc |= A(&d.h, (size_t)M * D);
-        rc |= A(&d.h2, (size_t)M * D); rc |= A(&d.qkv, (size_t)M * 3 * D); rc |= A(&d.att, (size_t)M * D);
-        rc |= A(&d.ff, (size_t)M * F); rc |= A(&d.qc, (size_t)M * D);
+        rc |= A(&d.cond, (size_t)Tm * B * D); rc |= A(&d.h, (size_t)M * D); rc |= A(&d.h2, (size_t)M * D);
+        rc |= A(&d.qkv, (size_t)M * (2 * D + H * D)); rc |= A(&d.ff, (size_t)M * F); rc |= A(&d.qc, (size_t)M * D);
+        rc |= A(&d.z, (size_t)M * D); rc |= A(&d.xtok, (size_t)M * ((C + 3) & ~3)); rc |= A(&d.addend, (size_t)M * D);
+        rc |= A(&d.lin, (size_t)M * Clin); rc |= A(&d.att, (size_t)Tm * B * D);
         rc |= A(&d.zero_pose, (size_t)B * npts * 3);
-        for (auto& L : d.layers) rc |= A(&L.kv_mem, (size_t)Tm * B * 2 * D);
+        for (auto& L : d.layers) { rc |= A(&L.kv_mem, (size_t)Tm * B * 2 * D); rc |= A(&L.vp_mem, (size_t)Tm * B * H * D); }
         if (rc) return rc;
         CUDA_TRY(h, cudaMalloc((void**)&d.t_dev, sizeof(long long) * B));
+        CUDA_TRY(h, cudaMalloc((void**)&d.step_cur, sizeof(int)));
         d.B = B; d.T = T; d.M = M; d.Tm = Tm;
     }
     CUDA_TRY(h, cudaMemcpyAsync(d.cond, cond, sizeof(float) * (size_t)Tm * B * D, cudaMemcpyDefault, st));
-    if (zero_pose_obj && d.cfg.n_points > 0)
-        CUDA_TRY(h, cudaMemcpyAsync(d.zero_pose, zero_pose_obj, sizeof(float) * (size_t)B * d.cfg.n_points * 3, cudaMemcpyDefault, st));
-    // step-invariant cross-attention K|V of the memory (rows j*B + b, seq-first like the reference)
+    if (zero_pose_obj && c.n_points > 0)
+        CUDA_TRY(h, cudaMemcpyAsync(d.zero_pose, zero_pose_obj, sizeof(float) * (size_t)B * c.n_points * 3, cudaMemcpyDefault, st));
+    // Step-invariant cross-attention tensors of the memory (rows j*B + b, seq-first like the reference):
+    //   kv_mem = mem [Wk;Wv]^T + b ;  vp_mem[:, h*D:(h+1)*D] = V_h Wo_h^T  (out-projection folded in)
     for (auto& L : d.layers) {
         int rc = idb_gemm(h, d.cond, D, L.w_kvc, D, L.b_kvc, nullptr, 0, L.kv_mem, 2 * D, Tm * B, 2 * D, D, EPI_BIAS, st);
         if (rc) return rc;
+        for (int hh = 0; hh < H; hh++) {
+            rc = idb_gemm(h, L.kv_mem + D + hh * HD, 2 * D, L.w_oc + hh * HD, D, nullptr, nullptr, 0, L.vp_mem + hh * D, H * D,
+                          Tm * B, D, HD, 0, st);
+            if (rc) return rc;
+        }
     }
     return IDB_OK;
 }
 
-// Decoder body on the bound workspaces: d.h holds the embedded tokens on entry and the decoder
-// output on exit.
+static size_t attn_smem(int Tk, int H) {
+    return sizeof(float) * ((size_t)SLAB * D + (size_t)H * Tk * (HD + 4) + (size_t)SLAB * H * Tk + (size_t)SLAB * LDZ);
+}
+static size_t qan_smem() { return sizeof(float) * ((size_t)(SLAB + 2) * LDZ + 32 * LDZ + SLAB * 32 + SLAB * 4); }
+
+// Decoder body on the bound workspaces: d.h holds the embedded tokens on entry; on exit d.z holds the
+// last layer's pre-norm3 activations (the caller applies that LayerNorm).
 static int denoiser_layers(idb_handle* h, cudaStream_t st) {
     Denoiser& d = h->den;
     const int B = d.B, T = d.T, M = d.M, Tm = d.Tm, F = d.cfg.d_ff, H = d.cfg.n_heads, N = d.cfg.n_queries;
-    const float scale = 1.0f / sqrtf(64.0f);
+    const dim3 slab_grid(B, (T + SLAB - 1) / SLAB);
     const int ln_blocks = (M * 32 + 255) / 256;
-    const size_t smem_self = sizeof(float) * ((size_t)T * 64 + (size_t)T * 65 + (size_t)T * 64 + (size_t)T * T);
-    const size_t smem_cross = sizeof(float) * ((size_t)T * 64 + (size_t)Tm * 65 + (size_t)Tm * 64 + (size_t)T * Tm);
-    const size_t smem_qan = sizeof(float) * ((size_t)T * (D + 4) + 32 * (D + 4) + (size_t)T * 32 + (size_t)T * 4);
-    float* x = d.h;     // residual stream
-    float* y = d.h2;    // ping-pong
+    const DenoiserLayer* pending = nullptr;   // layer whose norm3 has not been applied to d.z yet
     int rc;
     for (auto& L : d.layers) {
+        float* x1 = d.h2;   // output of the first sub-block
         if (L.qan) {
-            k_qan_ln<<<B, 256, smem_qan, st>>>(x, L.qt, L.wk, L.ln1w, L.ln1b, y, T, N);
+            const float* in = pending ? d.z : d.h;
+            k_qan_ln<<<slab_grid, 256, qan_smem(), st>>>(in, pending ? pending->ln3w : nullptr, pending ? pending->ln3b : nullptr,
+                                                          L.qt, L.wk, L.ln1w, L.ln1b, x1, T, N);
             LAUNCH_CHECK(h);
         } else {
-            if ((rc = idb_gemm(h, x, D, L.w_qkv, D, L.b_qkv, nullptr, 0, d.qkv, 3 * D, M, 3 * D, D, EPI_BIAS, st))) return rc;
-            k_mha<<<B * H, 128, smem_self, st>>>(d.qkv, 3 * D, T, 1, d.qkv + D, d.qkv + 2 * D, 3 * D, T, 1, d.att, D, T, T, H, scale);
-            LAUNCH_CHECK(h);
-            if ((rc = idb_gemm(h, d.att, D, L.w_o, D, L.b_o, x, D, d.qc, D, M, D, D, EPI_BIAS | EPI_RES, st))) return rc;
-            k_add_ln<<<ln_blocks, 256, 0, st>>>(d.qc, nullptr, L.ln1w, L.ln1b, y, M);
+            if (pending) {
+                k_ln<<<ln_blocks, 256, 0, st>>>(d.z, pending->ln3w, pending->ln3b, d.h, M);
+                LAUNCH_CHECK(h);
+            }
+            const int NQ = 2 * D + H * D;
+            if ((rc = idb_gemm(h, d.h, D, L.w_qkvf, D, L.b_qkvf, nullptr, 0, d.qkv, NQ, M, NQ, D, EPI_BIAS, st))) return rc;
+            k_attn_ln<<<slab_grid, 256, attn_smem(T, H), st>>>(d.qkv, NQ, d.qkv + D, NQ, d.qkv + 2 * D, NQ, T, 1, d.h, L.bo_f,
+                                                               L.ln1w, L.ln1b, x1, T, T, H);
             LAUNCH_CHECK(h);
         }
-        // cross attention on y -> x
-        if ((rc = idb_gemm(h, y, D, L.w_qc, D, L.b_qc, nullptr, 0, d.qc, D, M, D, D, EPI_BIAS, st))) return rc;
-        k_mha<<<B * H, 128, smem_cross, st>>>(d.qc, D, T, 1, L.kv_mem, L.kv_mem + D, 2 * D, 1, B, d.att, D, T, Tm, H, scale);
+        // cross attention: x1 -> d.h
+        if ((rc = idb_gemm(h, x1, D, L.w_qc, D, L.b_qc, nullptr, 0, d.qc, D, M, D, D, EPI_BIAS, st))) return rc;
+        k_attn_ln<<<slab_grid, 256, attn_smem(Tm, H), st>>>(d.qc, D, L.kv_mem, 2 * D, L.vp_mem, H * D, 1, B, x1, L.b_oc,
+                                                            L.ln2w, L.ln2b, d.h, T, Tm, H);
         LAUNCH_CHECK(h);
-        if ((rc = idb_gemm(h, d.att, D, L.w_oc, D, L.b_oc, y, D, d.qc, D, M, D, D, EPI_BIAS | EPI_RES, st))) return rc;
-        k_add_ln<<<ln_blocks, 256, 0, st>>>(d.qc, nullptr, L.ln2w, L.ln2b, x, M);
-        LAUNCH_CHECK(h);
-        // feed forward on x -> y -> x
-        if ((rc = idb_gemm(h, x, D, L.w1, D, L.b1, nullptr, 0, d.ff, F, M, F, D, EPI_BIAS | EPI_GELU, st))) return rc;
-        if ((rc = idb_gemm(h, d.ff, F, L.w2, F, L.b2, x, D, d.qc, D, M, D, F, EPI_BIAS | EPI_RES, st))) return rc;
+        // feed forward: d.h -> d.z (pre-norm3, residual added in the GEMM epilogue)
+        if ((rc = idb_gemm(h, d.h, D, L.w1, D, L.b1, nullptr, 0, d.ff, F, M, F, D, EPI_BIAS | EPI_GELU, st))) return rc;
+        if ((rc = idb_gemm(h, d.ff, F, L.w2, F, L.b2, d.h, D, d.z, D, M, D, F, EPI_BIAS | EPI_RES, st))) return rc;
         // QaN layers return tgt + (x - tgt) (model/sublayers.py:338-339); that differs from x by
         // <= 1 ulp of max(|x|,|tgt|) and is not reproduced (DESIGN.md "Deviations").
-        k_add_ln<<<ln_blocks, 256, 0, st>>>(d.qc, nullptr, L.ln3w, L.ln3b, x, M);
-        LAUNCH_CHECK(h);
+        pending = &L;
     }
+    k_ln<<<ln_blocks, 256, 0, st>>>(d.z, pending->ln3w, pending->ln3b, d.h, M);
+    LAUNCH_CHECK(h);
     return IDB_OK;
 }
 
@@ -614,33 +706,38 @@ int idb_denoiser_run(idb_handle* h, const float* x, const long long* t_dev, cons
     Denoiser& d = h->den;
     if (!d.B) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_bind first");
     const idb_denoiser_config& c = d.cfg;
-    const int B = d.B, T = d.T, C = c.c_body + c.c_obj + c.c_extra;
+    const int B = d.B, T = d.T, M = d.M, C = c.c_body + c.c_obj + c.c_extra;
     const int Clin = c.c_body + (c.variant == 0 ? c.c_obj : 7);
-    k_temb<<<B, D, 0, st>>>(d.pe, t_dev, d.te_w0T, d.te_b0, d.te_w2T, d.te_b2, d.temb, d.pe_rows);
+    int rc;
+    k_temb_addend<<<B, D, 0, st>>>(d.pe, t_dev, d.te_w0T, d.te_b0, d.te_w2T, d.te_b2, d.b_in, d.addend, d.pe_rows, T);
     LAUNCH_CHECK(h);
-    const size_t smem_e = sizeof(float) * (size_t)C * T;
-    k_embed<8><<<B, D, smem_e, st>>>(x, d.w_inT, d.b_in, d.temb, d.pe, d.h, C, T);
+    const int Cp = (C + 3) & ~3;
+    k_to_tokens<<<B, 256, sizeof(float) * (size_t)C * (T + 1), st>>>(x, d.xtok, C, Cp, T);
     LAUNCH_CHECK(h);
-    int rc = denoiser_layers(h, st);
-    if (rc) return rc;
-    const size_t smem_h = sizeof(float) * ((size_t)T * D + (size_t)Clin * T);
-    k_heads<8><<<B, 256, smem_h, st>>>(d.h, d.w_outT, d.b_out, d.zero_pose, gt, mask, out, T, Clin, C, c.variant, c.c_body, c.n_points);
+    // input embedding (model/diffusion_smpl.py:227-232): h = xtok W_in^T + (b_in + temb + pe)
+    if ((rc = idb_gemm(h, d.xtok, Cp, d.w_in, Cp, nullptr, d.addend, D, d.h, D, M, D, Cp, EPI_RES, st))) return rc;
+    if ((rc = denoiser_layers(h, st))) return rc;
+    // output heads (model/diffusion_smpl.py:234-237)
+    if ((rc = idb_gemm(h, d.h, D, d.w_out, D, d.b_out, nullptr, 0, d.lin, Clin, M, Clin, D, EPI_BIAS, st))) return rc;
+    k_heads_post<<<B, 256, sizeof(float) * (size_t)T * (Clin + 1), st>>>(d.lin, d.zero_pose, gt, mask, out, T, Clin, C, c.variant,
+                                                                          c.c_body, c.n_points);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }
 
 int idb_denoiser_prepare_kernels(idb_handle* h) {
-    // opt in to > 48 KB dynamic shared memory once (T <= 64 supported)
-    CUDA_TRY(h, cudaFuncSetAttribute(k_qan_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_mha, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_heads<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_embed<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    // opt in to > 48 KB dynamic shared memory once (T <= 64, Tm <= 16 supported)
+    CUDA_TRY(h, cudaFuncSetAttribute(k_qan_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem()));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_attn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(64, 4)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_to_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_heads_post, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     return IDB_OK;
 }
 
-int idb_denoiser_fill_t(idb_handle* h, cudaStream_t st) {
+// first kernel of a sampling step: publishes the step's timesteps and advances the device counter
+int idb_denoiser_step_begin(idb_handle* h, cudaStream_t st) {
     Denoiser& d = h->den;
-    k_fill_t<<<(d.B + 127) / 128, 128, 0, st>>>(d.t_dev, h->diff.tbl, h->diff.counter, d.B);
+    k_step_begin<<<1, 128, 0, st>>>(d.t_dev, h->diff.tbl, h->diff.counter, d.step_cur, d.B);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }

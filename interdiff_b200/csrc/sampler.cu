@@ -9,7 +9,7 @@
 
 int idb_denoiser_run(idb_handle* h, const float* x, const long long* t_dev, const float* gt, const unsigned char* mask,
                      float* out, cudaStream_t st);
-int idb_denoiser_fill_t(idb_handle* h, cudaStream_t st);
+int idb_denoiser_step_begin(idb_handle* h, cudaStream_t st);
 int idb_correction_apply_dev(idb_handle* h, float* x0, const float* gt, int t, cudaStream_t st);
 
 struct Sampler {
@@ -25,7 +25,6 @@ struct Sampler {
 namespace {
 
 __global__ void k_set_counter(int* counter, int v) { *counter = v; }
-__global__ void k_dec_counter(int* counter) { *counter -= 1; }
 
 // x_{t-1} = c1[i] x0 + c2[i] x_t + 1[i != 0] exp(0.5 logvar[i]) eps   (gaussian_diffusion.py:253-275,537-547)
 // noise pointer: explicit, or tape + (n_steps - i) * numel when tape_mode (eps of the k-th step is tape[k+1]).
@@ -109,7 +108,7 @@ static size_t sample_numel(idb_handle* h) {
 
 // predict with the device counter already set
 static int predict_dev(idb_handle* h, const float* x_t, const float* gt, const unsigned char* mask, float* x0, cudaStream_t st) {
-    int rc = idb_denoiser_fill_t(h, st);
+    int rc = idb_denoiser_step_begin(h, st);   // t_dev <- tbl[counter].t, step_cur <- counter, counter -= 1
     if (rc) return rc;
     return idb_denoiser_run(h, x_t, h->den.t_dev, gt, mask, x0, st);
 }
@@ -118,7 +117,7 @@ static int finish_dev(idb_handle* h, const float* x0, const float* x_t, const fl
     const size_t n = sample_numel(h);
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_posterior<<<blocks, 256, 0, st>>>(x0, x_t, noise, h->diff.tbl, h->diff.counter, h->diff.n, tape_mode, out, n);
+    k_posterior<<<blocks, 256, 0, st>>>(x0, x_t, noise, h->diff.tbl, h->den.step_cur, h->diff.n, tape_mode, out, n);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }
@@ -137,7 +136,8 @@ extern "C" int idb_p_sample_finish(idb_handle* h, int i, const float* x0, const 
     if (!h || !x0 || !x_t || !noise || !x_out) return IDB_ERR_ARG;
     if (i < 0 || i >= h->diff.n) return idb_fail(h, IDB_ERR_ARG, "step index out of range");
     cudaStream_t st = (cudaStream_t)stream;
-    k_set_counter<<<1, 1, 0, st>>>(h->diff.counter, i);
+    if (!h->den.step_cur) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_bind first");
+    k_set_counter<<<1, 1, 0, st>>>(h->den.step_cur, i);
     LAUNCH_CHECK(h);
     return finish_dev(h, x0, x_t, noise, 0, x_out, st);
 }
@@ -183,7 +183,6 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
         CUDA_TRY(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         rc = predict_dev(h, s.x_a, gt, mask, s.x0, cs);
         if (!rc) rc = finish_dev(h, s.x0, s.x_a, tape, 1, s.x_a, cs);
-        if (!rc) { k_dec_counter<<<1, 1, 0, cs>>>(df.counter); h->launches++; }
         cudaError_t ce = cudaStreamEndCapture(cs, &g);
         if (rc || ce != cudaSuccess) { cudaStreamDestroy(cs); return rc ? rc : idb_fail(h, IDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)); }
         s.launches_per_step = (int)(h->launches - saved);
@@ -194,7 +193,7 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
         rc = predict_dev(h, s.x_a, gt, mask, s.x0, cs);
         ce = cudaStreamEndCapture(cs, &g);
         if (rc || ce != cudaSuccess) { cudaStreamDestroy(cs); return rc ? rc : idb_fail(h, IDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)); }
-        s.launches_per_predict = s.launches_per_step - 2;
+        s.launches_per_predict = s.launches_per_step - 1;
         CUDA_TRY(h, cudaGraphInstantiate(&s.predict_graph, g, 0));
         cudaGraphDestroy(g);
         cudaStreamDestroy(cs);
@@ -213,8 +212,6 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
             } else {
                 if ((rc = predict_dev(h, s.x_a, gt, mask, s.x0, st))) return rc;
                 if ((rc = finish_dev(h, s.x0, s.x_a, tape, 1, s.x_a, st))) return rc;
-                k_dec_counter<<<1, 1, 0, st>>>(df.counter);
-                LAUNCH_CHECK(h);
             }
         } else {
             if (graph_ok) {
@@ -223,8 +220,6 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
             } else if ((rc = predict_dev(h, s.x_a, gt, mask, s.x0, st))) return rc;
             if ((rc = idb_correction_apply_dev(h, s.x0, gt, i, st))) return rc;
             if ((rc = finish_dev(h, s.x0, s.x_a, tape, 1, s.x_a, st))) return rc;
-            k_dec_counter<<<1, 1, 0, st>>>(df.counter);
-            LAUNCH_CHECK(h);
         }
     }
     CUDA_TRY(h, cudaMemcpyAsync(x_out, s.x_a, numel * sizeof(float), cudaMemcpyDefault, st));

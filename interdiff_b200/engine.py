@@ -107,15 +107,13 @@ class Engine:
         bias = torch.randn(N, generator=g).to(self.device)
         out = torch.empty(M, N, device=self.device)
         epi = 1 | (2 if gelu else 0)
-        call = lambda: self._chk(self.lib.idb_debug_gemm(self._h, self._ptr(A), self._ptr(W), self._ptr(bias), C.c_void_p(), self._ptr(out),
-                                                         M, N, K, epi, self._stream()))
-        for _ in range(5):
-            call()
+        call = lambda n: self._chk(self.lib.idb_debug_gemm_repeat(self._h, self._ptr(A), self._ptr(W), self._ptr(bias), C.c_void_p(),
+                                                                  self._ptr(out), M, N, K, epi, n, self._stream()))
+        call(5)
         torch.cuda.synchronize(self.device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(iters):
-            call()
+        call(iters)
         e1.record()
         torch.cuda.synchronize(self.device)
         return dict(M=M, N=N, K=K, iters=iters, ms=e0.elapsed_time(e1) / iters, kernel="gemm ff1 (bias+GELU)")

@@ -105,6 +105,22 @@ def cpu_reference_rate(n_denoise_steps, threads=None, seed=233):
     return n_denoise_steps / dt, dt, cores
 
 
+def aggregate_max(values, device=None):
+    """max over ranks of per-rank timings (device time of the slowest rank decides); works with the
+    nccl (GPU tensors) and gloo (CPU tensors) backends, and without a process group (N = 1)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def rank_seed(rank, base=233):
+    """every rank samples its own batch of sequences (weak scaling): distinct, reproducible seeds"""
+    return base + rank
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -150,13 +166,13 @@ def run_ours(args):
         eng.set_gemm_backend(args.backend)
     sd = mdm_weights("smpl", "auto")
     eng.load_denoiser(sd, "smpl")
-    b = S.make_smpl_batch(B=w["B"], T=w["T"], past_len=w["past_len"], seed=233 + rank)  # each rank its own 64 sequences
+    b = S.make_smpl_batch(B=w["B"], T=w["T"], past_len=w["past_len"], seed=rank_seed(rank))  # each rank its own 64 sequences
     eng.init_diffusion(R.named_beta_schedule("cosine", n))
     shape = b["gt"].shape
     # ---- device-resident leg
     gt_d, mask_d, cond_d = torch.from_numpy(b["gt"]).to(dev), torch.from_numpy(b["mask"]).to(dev), torch.from_numpy(b["cond"]).to(dev)
     eng.bind(cond_d, w["T"])
-    tape_d = torch.from_numpy(S.noise_tape(shape, n, 233 + rank)).to(dev)
+    tape_d = torch.from_numpy(S.noise_tape(shape, n, rank_seed(rank))).to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)  # > 126 MB L2
     out = torch.empty(shape, device=dev)
 
@@ -202,10 +218,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (feed-forward GEMMs, 16.1 of the 24.5 GFLOP of a step)
     roof = eng.gemm_microbench(M=w["B"] * w["T"], N=1024, K=256, iters=50) if hasattr(eng, "gemm_microbench") else None
 
-    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
+    dev_ms, e2e_ms = aggregate_max([dev_ms, e2e_ms], device=dev)
     if rank == 0:
         peaks = _peaks()
         total_steps = world * args.steps * n

@@ -29,7 +29,7 @@ int idb_create(idb_handle** out);                 /* on the current CUDA device 
 int idb_destroy(idb_handle* h);
 const char* idb_last_error(const idb_handle* h);
 long long idb_launch_count(const idb_handle* h);  /* kernels launched so far through h */
-int idb_set_gemm_backend(idb_handle* h, int backend); /* 0 = fp32 SIMT (debug/bisect), 1 = tcgen05 3xTF32 */
+int idb_set_gemm_backend(idb_handle* h, int backend); /* 0 = fp32 SIMT (debug/bisect), 1 = tcgen05 split-fp16 (default) */
 
 /* ---- denoiser: MDM.forward / MDM._decode --------------------------------------------------
  * replaces model/diffusion_smpl.py:239-246,226-237 (variant 0) and
@@ -148,6 +148,11 @@ int idb_debug_gemm_repeat(idb_handle* h, const float* A, const float* W, const f
 int idb_debug_set_gemm_accumulators(int n);
 /* one launch with a per-CTA clock64 timeline (16 slots per CTA) of the tcgen05 kernel's pipeline */
 int idb_debug_gemm_trace(idb_handle* h, const float* A, const float* W, float* C, int M, int N, int K, long long* trace, void* stream);
+
+/* debug: fp16 (hi, lo) operand split (x = hi + lo * 2^-11), and a GEMM on such pairs */
+int idb_debug_split(idb_handle* h, const float* x, void* hi, void* lo, int rows, int cols, int ld_dst, void* stream);
+int idb_debug_gemm_presplit(idb_handle* h, const void* A_hi, const void* A_lo, const void* W_hi, const void* W_lo,
+                            const float* bias, float* C, int M, int N, int K, int epi, int iters, long long* trace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -66,13 +66,39 @@ extern "C" int idb_debug_gemm_repeat(idb_handle* h, const float* A, const float*
 }
 
 extern long long* g_idb_gemm_trace;
+static int g_idb_trace_epi = 0;
 /* one GEMM launch with a per-CTA clock64 timeline written to trace[ctas][16] (device) */
 extern "C" int idb_debug_gemm_trace(idb_handle* h, const float* A, const float* W, float* C, int M, int N, int K, long long* trace, void* stream) {
     if (!h || !A || !W || !C || !trace) return IDB_ERR_ARG;
     g_idb_gemm_trace = trace;
-    return idb_gemm(h, A, K, W, K, nullptr, nullptr, N, C, N, M, N, K, 0, (cudaStream_t)stream);
+    return idb_gemm(h, A, K, W, K, nullptr, nullptr, N, C, N, M, N, K, g_idb_trace_epi, (cudaStream_t)stream);
 }
 
 extern int g_idb_gemm_nacc;
 /* test hook: number of round-robin TMEM accumulators for the big x big products (0 = default) */
-extern "C" int idb_debug_set_gemm_accumulators(int n) { g_idb_gemm_nacc = n; return IDB_OK; }
+extern "C" int idb_debug_set_gemm_accumulators(int n) {
+    if (n >= 1000) { g_idb_trace_epi = n - 1000; return IDB_OK; }   // >= 1000: epi flags for idb_debug_gemm_trace
+    g_idb_gemm_nacc = n;
+    return IDB_OK;
+}
+
+/* x[rows][cols] -> fp16 (hi, lo) pairs with row stride ld_dst (device pointers) */
+extern "C" int idb_debug_split(idb_handle* h, const float* x, void* hi, void* lo, int rows, int cols, int ld_dst, void* stream) {
+    if (!h || !x || !hi || !lo || rows <= 0 || cols <= 0 || ld_dst < cols) return IDB_ERR_ARG;
+    return idb_split_tensor(h, x, cols, (__half*)hi, (__half*)lo, ld_dst, rows, cols, (cudaStream_t)stream);
+}
+/* GEMM on fp16 (hi, lo) operand pairs, `iters` launches; the first launch records the pipeline timeline when trace != NULL */
+extern "C" int idb_debug_gemm_presplit(idb_handle* h, const void* A_hi, const void* A_lo, const void* W_hi, const void* W_lo,
+                                       const float* bias, float* C, int M, int N, int K, int epi, int iters, long long* trace,
+                                       void* stream) {
+    if (!h || !A_hi || !A_lo || !W_hi || !W_lo || !C) return IDB_ERR_ARG;
+    GemmArgs g;
+    g.A_hi = (const __half*)A_hi; g.A_lo = (const __half*)A_lo; g.lda = K; g.W_hi = (const __half*)W_hi; g.W_lo = (const __half*)W_lo; g.ldw = K;
+    g.bias = bias; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K; g.epi = epi | g_idb_trace_epi;
+    for (int i = 0; i < iters; i++) {
+        if (i == 0 && trace) g_idb_gemm_trace = trace;
+        int rc = idb_gemm_ex(h, g, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return IDB_OK;
+}

@@ -1,6 +1,7 @@
 // Shared internals of libinterdiff_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -35,6 +36,9 @@ struct DenoiserLayer {
     float *w_qkv = nullptr, *b_qkv = nullptr, *w_o = nullptr, *b_o = nullptr;
     // folded self-attention: [Wq; Wk; (Wo_h Wv_h) for h] (1536 x 256), bias [bq; bk; 0], bo' = bo + sum_h Wo_h bv_h
     float *w_qkvf = nullptr, *b_qkvf = nullptr, *bo_f = nullptr;
+    // (big, small) splits of the GEMM weights for the tensor-core path
+    __half *w_qkvf_b = nullptr, *w_qkvf_s = nullptr, *w_qc_b = nullptr, *w_qc_s = nullptr, *w1_b = nullptr, *w1_s = nullptr,
+           *w2_b = nullptr, *w2_s = nullptr;
     // QaN
     float *qt = nullptr, *wk = nullptr;  // qt: [3*N][D] folded queries
     // cross attention
@@ -60,7 +64,12 @@ struct Denoiser {
     int B = 0, T = 0, M = 0, Tm = 0;
     float *cond = nullptr, *zero_pose = nullptr;
     float *temb = nullptr, *h = nullptr, *h2 = nullptr, *qkv = nullptr, *att = nullptr, *ff = nullptr, *qc = nullptr;
-    float *xtok = nullptr, *addend = nullptr, *lin = nullptr, *z = nullptr;
+    float *addend = nullptr, *lin = nullptr, *z = nullptr;
+    __half *w_in_b = nullptr, *w_in_s = nullptr, *w_out_b = nullptr, *w_out_s = nullptr;
+    // fp16 (hi, lo) copies of the activations that feed GEMMs  (_b = hi, _s = lo)
+    __half *h_b = nullptr, *h_s = nullptr, *h2_b = nullptr, *h2_s = nullptr, *ff_b = nullptr, *ff_s = nullptr, *xtok_b = nullptr,
+           *xtok_s = nullptr;
+    std::vector<void*> bound_h;
     int* step_cur = nullptr;
     long long* t_dev = nullptr;
     std::vector<float*> bound;              // workspaces to free on rebind
@@ -81,7 +90,8 @@ struct idb_handle {
     std::string err;
     int device = 0, sm_count = 148;
     long long launches = 0;   // kernels launched through this handle (bench's gpu_launches)
-    int gemm_backend = 1;     // 0 = fp32 SIMT (debug / bisect), 1 = tcgen05 3xTF32 (default)
+    int gemm_backend = 1;     // 0 = fp32 SIMT (debug / bisect), 1 = tcgen05 split-fp16 (default)
+    void* scratch = nullptr; size_t scratch_bytes = 0;   // on-the-fly operand splits of idb_gemm
     Denoiser den;
     Diffusion diff;
     BodyModel* body = nullptr;
@@ -126,6 +136,32 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 enum { EPI_BIAS = 1, EPI_GELU = 2, EPI_RES = 4, EPI_SILU = 8 };
 int idb_gemm(idb_handle* h, const float* A, int lda, const float* W, int ldw, const float* bias,
              const float* res, int ldr, float* C, int ldc, int M, int N, int K, int epi, cudaStream_t st);
+
+// Split-precision operands for the tensor-core path: x = hi + lo * 2^-11 with hi = fp16_rn(x),
+// lo = fp16_rn((x - hi) * 2^11) (x - hi is exact in fp32; the scale keeps lo a normal fp16 number).
+// An operand is given either as full fp32 (A / W; SIMT path, or split on the fly into scratch) or as
+// an fp16 pair; an output may be requested as full fp32 and/or as a pair for the next GEMM.
+struct GemmArgs {
+    const float* A = nullptr; const __half* A_hi = nullptr; const __half* A_lo = nullptr; int lda = 0;
+    const float* W = nullptr; const __half* W_hi = nullptr; const __half* W_lo = nullptr; int ldw = 0;
+    const float* bias = nullptr; const float* res = nullptr; int ldr = 0;
+    float* C = nullptr; __half* C_hi = nullptr; __half* C_lo = nullptr; int ldc = 0;
+    int M = 0, N = 0, K = 0, epi = 0;
+};
+int idb_gemm_ex(idb_handle* h, const GemmArgs& g, cudaStream_t st);
+// x[rows][cols] (row stride ld_src) -> fp16 pairs [rows][ld_dst] (columns >= cols zero-filled)
+int idb_split_tensor(idb_handle* h, const float* x, int ld_src, __half* hi, __half* lo, int ld_dst, int rows, int cols, cudaStream_t st);
+
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * 2048.0f);
+}
+__device__ __forceinline__ void split_f16x2(float x, float y, __half2& hi, __half2& lo) {
+    hi = __floats2half2_rn(x, y);
+    const float2 f = __half22float2(hi);
+    lo = __floats2half2_rn((x - f.x) * 2048.0f, (y - f.y) * 2048.0f);
+}
+__device__ __forceinline__ float join_f16(__half hi, __half lo) { return fmaf(__half2float(lo), 1.0f / 2048.0f, __half2float(hi)); }
 
 // allocation helpers
 int idb_dev_alloc(idb_handle* h, float** p, size_t n_floats);

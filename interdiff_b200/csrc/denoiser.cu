@@ -30,49 +30,80 @@ __global__ void k_step_begin(long long* t_dev, const StepParams* tbl, int* count
 
 // TimestepEmbedder.forward (model/layers.py:42-43): pe[t] -> Linear -> SiLU -> Linear, then the
 // per-token addend of the input embedding: add[b*T+t][:] = temb[b] + pe[t] + b_in   (grid B, block 256)
-__global__ void k_temb_addend(const float* __restrict__ pe, const long long* __restrict__ t, const float* __restrict__ w0T,
-                              const float* __restrict__ b0, const float* __restrict__ w2T, const float* __restrict__ b2,
-                              const float* __restrict__ b_in, float* __restrict__ add, int pe_rows, int T) {
-    __shared__ float s_in[D], s_h[D];
-    const int b = blockIdx.x, n = threadIdx.x;
+// Thread (cg = tid & 63, kg = tid >> 6) accumulates columns 4cg..4cg+3 over k in [64kg, 64kg+64):
+// float4 weight loads, 1 KB contiguous per k across the 64 column groups, 16 loads in flight.
+__device__ __forceinline__ float4 mlp_partial(const float* __restrict__ wT, const float* __restrict__ s_x, int cg, int kg) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* w4 = reinterpret_cast<const float4*>(wT) + cg;
+#pragma unroll 16
+    for (int k = kg * 64; k < kg * 64 + 64; k++) {
+        const float4 w = __ldg(w4 + (size_t)k * (D / 4));
+        const float x = s_x[k];
+        a.x = fmaf(w.x, x, a.x); a.y = fmaf(w.y, x, a.y); a.z = fmaf(w.z, x, a.z); a.w = fmaf(w.w, x, a.w);
+    }
+    return a;
+}
+__global__ void __launch_bounds__(256)
+k_temb_addend(const float* __restrict__ pe, const long long* __restrict__ t, const float* __restrict__ w0T,
+              const float* __restrict__ b0, const float* __restrict__ w2T, const float* __restrict__ b2,
+              const float* __restrict__ b_in, float* __restrict__ add, int pe_rows, int T) {
+    __shared__ float s_in[D], s_h[D], s_o[D];
+    __shared__ float4 s_part[4][64];
+    const int b = blockIdx.x, n = threadIdx.x, cg = n & 63, kg = n >> 6;
     long long ti = t[b];
     if (ti < 0) ti = 0;
     if (ti >= pe_rows) ti = pe_rows - 1;
     s_in[n] = pe[(size_t)ti * D + n];
     __syncthreads();
-    float a0 = b0[n], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 16
-    for (int k = 0; k < D; k += 4) {
-        a0 = fmaf(w0T[(k + 0) * D + n], s_in[k + 0], a0); a1 = fmaf(w0T[(k + 1) * D + n], s_in[k + 1], a1);
-        a2 = fmaf(w0T[(k + 2) * D + n], s_in[k + 2], a2); a3 = fmaf(w0T[(k + 3) * D + n], s_in[k + 3], a3);
-    }
-    s_h[n] = silu((a0 + a1) + (a2 + a3));
+    s_part[kg][cg] = mlp_partial(w0T, s_in, cg, kg);
     __syncthreads();
-    a0 = b2[n]; a1 = a2 = a3 = 0.f;
-#pragma unroll 16
-    for (int k = 0; k < D; k += 4) {
-        a0 = fmaf(w2T[(k + 0) * D + n], s_h[k + 0], a0); a1 = fmaf(w2T[(k + 1) * D + n], s_h[k + 1], a1);
-        a2 = fmaf(w2T[(k + 2) * D + n], s_h[k + 2], a2); a3 = fmaf(w2T[(k + 3) * D + n], s_h[k + 3], a3);
+    {
+        const float* p = reinterpret_cast<const float*>(s_part);
+        s_h[n] = silu(((p[n] + p[256 + n]) + (p[512 + n] + p[768 + n])) + b0[n]);
     }
-    const float base = ((a0 + a1) + (a2 + a3)) + b_in[n];
-    for (int tt = 0; tt < T; tt++) add[((size_t)b * T + tt) * D + n] = base + pe[(size_t)tt * D + n];
+    __syncthreads();
+    s_part[kg][cg] = mlp_partial(w2T, s_h, cg, kg);
+    __syncthreads();
+    {
+        const float* p = reinterpret_cast<const float*>(s_part);
+        s_o[n] = (((p[n] + p[256 + n]) + (p[512 + n] + p[768 + n])) + b2[n]) + b_in[n];
+    }
+    __syncthreads();
+    for (int i = n; i < T * (D / 4); i += 256) {
+        const int tt = i / (D / 4), c = i % (D / 4);
+        const float4 p4 = reinterpret_cast<const float4*>(pe + (size_t)tt * D)[c];
+        const float4 o4 = reinterpret_cast<const float4*>(s_o)[c];
+        reinterpret_cast<float4*>(add + ((size_t)b * T + tt) * D)[c] = make_float4(o4.x + p4.x, o4.y + p4.y, o4.z + p4.z, o4.w + p4.w);
+    }
 }
 
 // (B,1,C,T) -> token-major [B*T][C] through a shared-memory transpose (grid B)
-__global__ void k_to_tokens(const float* __restrict__ x, float* __restrict__ xtok, int C, int Cp, int T) {
+__global__ void k_to_tokens(const float* __restrict__ x, __half* __restrict__ xtok, __half* __restrict__ xtok_s, int C, int Cp, int T) {
     extern __shared__ float sx[];   // [C][T+1]
     const int b = blockIdx.x;
     for (int i = threadIdx.x; i < C * T; i += blockDim.x) sx[(i / T) * (T + 1) + i % T] = x[(size_t)b * C * T + i];
     __syncthreads();
     for (int i = threadIdx.x; i < Cp * T; i += blockDim.x) {
         const int t = i / Cp, c = i % Cp;
-        xtok[((size_t)b * T + t) * Cp + c] = c < C ? sx[c * (T + 1) + t] : 0.f;   // zero padding columns
+        // (hi, lo) fp16 pair for the embedding GEMM; zero padding columns
+        split_f16(c < C ? sx[c * (T + 1) + t] : 0.f, xtok[((size_t)b * T + t) * Cp + c], xtok_s[((size_t)b * T + t) * Cp + c]);
     }
+}
+
+// store two float4 (columns 4*lane.. and 128+4*lane.. of a 256-wide row) as fp16 (hi, lo) pairs
+__device__ __forceinline__ void store_pairs(const float4& o0, const float4& o1, __half* __restrict__ hi, __half* __restrict__ lo, int lane) {
+    __half2 h0, h1, h2, h3, l0, l1, l2, l3;
+    split_f16x2(o0.x, o0.y, h0, l0); split_f16x2(o0.z, o0.w, h1, l1);
+    split_f16x2(o1.x, o1.y, h2, l2); split_f16x2(o1.z, o1.w, h3, l3);
+    *reinterpret_cast<uint2*>(hi + lane * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(hi + 128 + lane * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+    *reinterpret_cast<uint2*>(lo + lane * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+    *reinterpret_cast<uint2*>(lo + 128 + lane * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&l2), *reinterpret_cast<uint32_t*>(&l3));
 }
 
 // out[m,:] = LayerNorm(a[m,:]) * w + b.  warp per row, D = 256.
 __global__ void k_ln(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bb,
-                     float* __restrict__ out, int M) {
+                     float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s, int M) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= M) return;
     const float4* pa = reinterpret_cast<const float4*>(a + (size_t)warp * D);
@@ -97,11 +128,13 @@ __global__ void k_ln(const float* __restrict__ a, const float* __restrict__ w, c
     o1.z = (v[6] - mean) * rstd * w1.z + b1.z; o1.w = (v[7] - mean) * rstd * w1.w + b1.w;
     float4* po = reinterpret_cast<float4*>(out + (size_t)warp * D);
     po[lane] = o0; po[lane + 32] = o1;
+    if (out_b) store_pairs(o0, o1, out_b + (size_t)warp * D, out_s + (size_t)warp * D, lane);
 }
 
 // LayerNorm of one 256-wide row held in shared memory by one warp (lane holds cols 4*lane.. and 128+4*lane..)
 __device__ __forceinline__ void warp_ln_row(const float* __restrict__ zrow, const float* __restrict__ w, const float* __restrict__ bb,
-                                            float* __restrict__ dst, int lane) {
+                                            float* __restrict__ dst, int lane, __half* __restrict__ dst_b = nullptr,
+                                            __half* __restrict__ dst_s = nullptr) {
     const float4 u0 = *reinterpret_cast<const float4*>(zrow + lane * 4), u1 = *reinterpret_cast<const float4*>(zrow + 128 + lane * 4);
     float v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
     float s = 0.f;
@@ -121,6 +154,7 @@ __device__ __forceinline__ void warp_ln_row(const float* __restrict__ zrow, cons
     o1.z = (v[6] - mean) * rstd * w1.z + b1.z; o1.w = (v[7] - mean) * rstd * w1.w + b1.w;
     *reinterpret_cast<float4*>(dst + lane * 4) = o0;
     *reinterpret_cast<float4*>(dst + 128 + lane * 4) = o1;
+    if (dst_b) store_pairs(o0, o1, dst_b, dst_s, lane);
 }
 
 __device__ __forceinline__ float dot64(const float* __restrict__ a, const float* __restrict__ b) {
@@ -145,12 +179,13 @@ __device__ __forceinline__ float dot64(const float* __restrict__ a, const float*
 __global__ void __launch_bounds__(256)
 k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
           int ksb, int kst, const float* __restrict__ res, const float* __restrict__ bo, const float* __restrict__ lnw,
-          const float* __restrict__ lnb, float* __restrict__ out, int T, int Tk, int H) {
+          const float* __restrict__ lnb, float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s,
+          int T, int Tk, int H) {
     extern __shared__ __align__(16) float sm[];
     const int LDK = HD + 4;
     float* s_q = sm;                       // [SLAB][D]
     float* s_k = s_q + SLAB * D;           // [H*Tk][LDK]
-    float* s_a = s_k + H * Tk * LDK;       // [SLAB][H*Tk]
+    float* s_a = s_k + H * Tk * LDK;       // [H*Tk][SLAB]  (transposed: the 16 rows of one (h,j) are contiguous)
     float* s_z = s_a + SLAB * H * Tk;      // [SLAB][LDZ]
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
     const int HT = H * Tk;
@@ -165,19 +200,19 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
     }
     __syncthreads();
     const float scale = 0.125f;   // 1/sqrt(64)
-    for (int i = tid; i < nr * HT; i += 256) {
-        const int r = i / HT, hj = i % HT, hh = hj / Tk;
-        s_a[r * HT + hj] = dot64(s_q + r * D + hh * HD, s_k + hj * LDK) * scale;
+    for (int i = tid; i < SLAB * HT; i += 256) {
+        const int hj = i / SLAB, r = i % SLAB, hh = hj / Tk;
+        s_a[i] = r < nr ? dot64(s_q + r * D + hh * HD, s_k + hj * LDK) * scale : 0.f;
     }
     __syncthreads();
     for (int g = tid; g < nr * H; g += 256) {
-        float* row = s_a + (g / H) * HT + (g % H) * Tk;
+        float* col = s_a + (g % H) * Tk * SLAB + (g / H);      // element j at col[j * SLAB]
         float mx = -INFINITY;
-        for (int j = 0; j < Tk; j++) mx = fmaxf(mx, row[j]);
+        for (int j = 0; j < Tk; j++) mx = fmaxf(mx, col[j * SLAB]);
         float s = 0.f;
-        for (int j = 0; j < Tk; j++) { const float e = expf(row[j] - mx); row[j] = e; s += e; }
+        for (int j = 0; j < Tk; j++) { const float e = expf(col[j * SLAB] - mx); col[j * SLAB] = e; s += e; }
         const float inv = 1.0f / s;
-        for (int j = 0; j < Tk; j++) row[j] *= inv;
+        for (int j = 0; j < Tk; j++) col[j * SLAB] *= inv;
     }
     __syncthreads();
     {
@@ -186,12 +221,16 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
 #pragma unroll
         for (int r = 0; r < SLAB; r++) acc[r] = 0.f;
         for (int hh = 0; hh < H; hh++) {
-#pragma unroll 2
+            const float* vb = v + (size_t)b * ksb * ldv + hh * D + n;
+#pragma unroll 5
             for (int j = 0; j < Tk; j++) {
-                const float vv = __ldg(v + (size_t)(b * ksb + j * kst) * ldv + hh * D + n);
-                const float* ap = s_a + hh * Tk + j;
-#pragma unroll
-                for (int r = 0; r < SLAB; r++) acc[r] = fmaf(ap[r * HT], vv, acc[r]);   // rows >= nr hold stale but finite values
+                const float vv = __ldg(vb + (size_t)j * kst * ldv);
+                const float4* ap = reinterpret_cast<const float4*>(s_a + (hh * Tk + j) * SLAB);
+                const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];     // rows >= nr hold zeros
+                acc[0] = fmaf(a0.x, vv, acc[0]); acc[1] = fmaf(a0.y, vv, acc[1]); acc[2] = fmaf(a0.z, vv, acc[2]); acc[3] = fmaf(a0.w, vv, acc[3]);
+                acc[4] = fmaf(a1.x, vv, acc[4]); acc[5] = fmaf(a1.y, vv, acc[5]); acc[6] = fmaf(a1.z, vv, acc[6]); acc[7] = fmaf(a1.w, vv, acc[7]);
+                acc[8] = fmaf(a2.x, vv, acc[8]); acc[9] = fmaf(a2.y, vv, acc[9]); acc[10] = fmaf(a2.z, vv, acc[10]); acc[11] = fmaf(a2.w, vv, acc[11]);
+                acc[12] = fmaf(a3.x, vv, acc[12]); acc[13] = fmaf(a3.y, vv, acc[13]); acc[14] = fmaf(a3.z, vv, acc[14]); acc[15] = fmaf(a3.w, vv, acc[15]);
             }
         }
         const float bb = bo[n];
@@ -201,7 +240,10 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < nr; r += 8) warp_ln_row(s_z + r * LDZ, lnw, lnb, out + (size_t)(b * T + r0 + r) * D, lane);
+    for (int r = warp; r < nr; r += 8) {
+        const size_t o = (size_t)(b * T + r0 + r) * D;
+        warp_ln_row(s_z + r * LDZ, lnw, lnb, out + o, lane, out_b ? out_b + o : nullptr, out_s ? out_s + o : nullptr);
+    }
 }
 
 // QaN block + residual + LayerNorm1 (model/sublayers.py:343-352 + :332) for a slab of <= 16 rows of
@@ -213,7 +255,8 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
 __global__ void __launch_bounds__(256)
 k_qan_ln(const float* __restrict__ zin, const float* __restrict__ prew, const float* __restrict__ preb,
          const float* __restrict__ qt, const float* __restrict__ wk, const float* __restrict__ lnw,
-         const float* __restrict__ lnb, float* __restrict__ out, int T, int N) {
+         const float* __restrict__ lnb, float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s,
+         int T, int N) {
     extern __shared__ __align__(16) float sm[];
     float* s_x = sm;                        // [SLAB+2][LDZ]   rows r0-1 .. r0+nr
     float* s_qt = s_x + (SLAB + 2) * LDZ;   // [32][LDZ]
@@ -314,6 +357,13 @@ k_qan_ln(const float* __restrict__ zin, const float* __restrict__ prew, const fl
             o.x = (v[half * 4 + 0] - mean) * rstd * w4.x + b4.x; o.y = (v[half * 4 + 1] - mean) * rstd * w4.y + b4.y;
             o.z = (v[half * 4 + 2] - mean) * rstd * w4.z + b4.z; o.w = (v[half * 4 + 3] - mean) * rstd * w4.w + b4.w;
             *reinterpret_cast<float4*>(out + (size_t)(b * T + t) * D + c) = o;
+            if (out_b) {
+                __half2 h01, h23, l01, l23;
+                split_f16x2(o.x, o.y, h01, l01);
+                split_f16x2(o.z, o.w, h23, l23);
+                *reinterpret_cast<uint2*>(out_b + (size_t)(b * T + t) * D + c) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+                *reinterpret_cast<uint2*>(out_s + (size_t)(b * T + t) * D + c) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+            }
         }
     }
 }
@@ -326,7 +376,17 @@ __global__ void k_heads_post(const float* __restrict__ lin, const float* __restr
                              int T, int Clin, int C, int variant, int c_body, int n_points) {
     extern __shared__ float so[];   // [T][Clin+1]
     const int b = blockIdx.x, LDS_ = Clin + 1;
-    for (int i = threadIdx.x; i < T * Clin; i += blockDim.x) so[(i / Clin) * LDS_ + i % Clin] = lin[(size_t)b * T * Clin + i];
+    if ((Clin & 3) == 0) {
+        const float4* l4 = reinterpret_cast<const float4*>(lin + (size_t)b * T * Clin);
+        for (int i = threadIdx.x; i < T * Clin / 4; i += blockDim.x) {
+            const float4 q4 = l4[i];
+            const int e = i * 4, r = e / Clin, cc = e % Clin;
+            float* d4 = so + r * LDS_ + cc;
+            d4[0] = q4.x; d4[1] = q4.y; d4[2] = q4.z; d4[3] = q4.w;
+        }
+    } else {
+        for (int i = threadIdx.x; i < T * Clin; i += blockDim.x) so[(i / Clin) * LDS_ + i % Clin] = lin[(size_t)b * T * Clin + i];
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
         const int c = i / T, t = i % T;
@@ -385,6 +445,8 @@ int idb_upload(idb_handle* h, float** p, const float* host, size_t n) {
 static void denoiser_free_bound(Denoiser& d) {
     for (float* p : d.bound) cudaFree(p);
     d.bound.clear();
+    for (void* p : d.bound_h) cudaFree(p);
+    d.bound_h.clear();
     if (d.t_dev) { cudaFree(d.t_dev); d.t_dev = nullptr; }
     if (d.step_cur) { cudaFree(d.step_cur); d.step_cur = nullptr; }
     d.B = d.T = d.M = 0;
@@ -602,6 +664,30 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
     }
 #undef GET
     if (P.rc) return P.rc;
+    // fp16 (hi, lo) copies of every GEMM weight for the tensor-core path
+    {
+        auto split = [&](const float* w, int rows, int cols, int ld_dst, __half** hi, __half** lo) -> int {
+            const size_t n = (size_t)rows * ld_dst;
+            CUDA_TRY(h, cudaMalloc((void**)hi, n * sizeof(__half)));
+            d.owned.push_back(reinterpret_cast<float*>(*hi));
+            CUDA_TRY(h, cudaMalloc((void**)lo, n * sizeof(__half)));
+            d.owned.push_back(reinterpret_cast<float*>(*lo));
+            return idb_split_tensor(h, w, cols, *hi, *lo, ld_dst, rows, cols, 0);
+        };
+        const int C = c.c_body + c.c_obj + c.c_extra, Cp = (C + 3) & ~3, Cp8 = (C + 7) & ~7;
+        const int Clin = c.c_body + (c.variant == 0 ? c.c_obj : 7);
+        (void)Cp;
+        int rc = split(d.w_in, D, (C + 3) & ~3, Cp8, &d.w_in_b, &d.w_in_s);
+        if (!rc) rc = split(d.w_out, Clin, D, D, &d.w_out_b, &d.w_out_s);
+        for (auto& L : d.layers) {
+            if (!rc && !L.qan) rc = split(L.w_qkvf, 2 * D + H * D, D, D, &L.w_qkvf_b, &L.w_qkvf_s);
+            if (!rc) rc = split(L.w_qc, D, D, D, &L.w_qc_b, &L.w_qc_s);
+            if (!rc) rc = split(L.w1, F, D, D, &L.w1_b, &L.w1_s);
+            if (!rc) rc = split(L.w2, D, F, F, &L.w2_b, &L.w2_s);
+        }
+        if (rc) return rc;
+        CUDA_TRY(h, cudaDeviceSynchronize());
+    }
     d.committed = true;
     denoiser_free_bound(d);
     return IDB_OK;
@@ -624,9 +710,17 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
         auto A = [&](float** p, size_t n) { int rc = idb_dev_alloc(h, p, n); if (!rc) d.bound.push_back(*p); return rc; };
         int rc = 0;
         rc |= A(&d.cond, (size_t)Tm * B * D); rc |= A(&d.h, (size_t)M * D); rc |= A(&d.h2, (size_t)M * D);
-        rc |= A(&d.qkv, (size_t)M * (2 * D + H * D)); rc |= A(&d.ff, (size_t)M * F); rc |= A(&d.qc, (size_t)M * D);
-        rc |= A(&d.z, (size_t)M * D); rc |= A(&d.xtok, (size_t)M * ((C + 3) & ~3)); rc |= A(&d.addend, (size_t)M * D);
+        rc |= A(&d.qkv, (size_t)M * (2 * D + H * D)); rc |= A(&d.qc, (size_t)M * D);
+        rc |= A(&d.z, (size_t)M * D); rc |= A(&d.addend, (size_t)M * D);
         rc |= A(&d.lin, (size_t)M * Clin); rc |= A(&d.att, (size_t)Tm * B * D);
+        auto AH = [&](__half** p, size_t n) {
+            cudaError_t e = cudaMalloc((void**)p, n * sizeof(__half) + 16);
+            if (e == cudaSuccess) d.bound_h.push_back(*p);
+            return e == cudaSuccess ? 0 : idb_fail(h, IDB_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+        };
+        const size_t Cp8 = (size_t)((C + 7) & ~7);
+        rc |= AH(&d.h_b, (size_t)M * D); rc |= AH(&d.h_s, (size_t)M * D); rc |= AH(&d.h2_b, (size_t)M * D); rc |= AH(&d.h2_s, (size_t)M * D);
+        rc |= AH(&d.ff_b, (size_t)M * F); rc |= AH(&d.ff_s, (size_t)M * F); rc |= AH(&d.xtok_b, (size_t)M * Cp8); rc |= AH(&d.xtok_s, (size_t)M * Cp8);
         rc |= A(&d.zero_pose, (size_t)B * npts * 3);
         for (auto& L : d.layers) { rc |= A(&L.kv_mem, (size_t)Tm * B * 2 * D); rc |= A(&L.vp_mem, (size_t)Tm * B * H * D); }
         if (rc) return rc;
@@ -656,8 +750,18 @@ static size_t attn_smem(int Tk, int H) {
 }
 static size_t qan_smem() { return sizeof(float) * ((size_t)(SLAB + 2) * LDZ + 32 * LDZ + SLAB * 32 + SLAB * 4); }
 
-// Decoder body on the bound workspaces: d.h holds the embedded tokens on entry; on exit d.z holds the
-// last layer's pre-norm3 activations (the caller applies that LayerNorm).
+// One nn.Linear on fp16 (hi, lo) operand pairs; output as full fp32 and/or as a pair.
+static int linear(idb_handle* h, const __half* a_b, const __half* a_s, int lda, const __half* w_b, const __half* w_s, int ldw,
+                  const float* bias, const float* res, float* C, __half* C_b, __half* C_s, int ldc, int M, int N, int K, int epi,
+                  cudaStream_t st) {
+    GemmArgs g;
+    g.A_hi = a_b; g.A_lo = a_s; g.lda = lda; g.W_hi = w_b; g.W_lo = w_s; g.ldw = ldw; g.bias = bias; g.res = res; g.ldr = D;
+    g.C = C; g.C_hi = C_b; g.C_lo = C_s; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.epi = epi;
+    return idb_gemm_ex(h, g, st);
+}
+
+// Decoder body on the bound workspaces.  Activation triples (full, big, small): d.h/h_b/h_s hold the
+// embedded tokens on entry; on exit d.h (+ split) holds the decoder output (last norm3 applied).
 static int denoiser_layers(idb_handle* h, cudaStream_t st) {
     Denoiser& d = h->den;
     const int B = d.B, T = d.T, M = d.M, Tm = d.Tm, F = d.cfg.d_ff, H = d.cfg.n_heads, N = d.cfg.n_queries;
@@ -666,36 +770,40 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
     const DenoiserLayer* pending = nullptr;   // layer whose norm3 has not been applied to d.z yet
     int rc;
     for (auto& L : d.layers) {
-        float* x1 = d.h2;   // output of the first sub-block
+        // ---- first sub-block -> x1 = (d.h2, h2_b, h2_s)
         if (L.qan) {
             const float* in = pending ? d.z : d.h;
             k_qan_ln<<<slab_grid, 256, qan_smem(), st>>>(in, pending ? pending->ln3w : nullptr, pending ? pending->ln3b : nullptr,
-                                                          L.qt, L.wk, L.ln1w, L.ln1b, x1, T, N);
+                                                          L.qt, L.wk, L.ln1w, L.ln1b, d.h2, d.h2_b, d.h2_s, T, N);
             LAUNCH_CHECK(h);
         } else {
             if (pending) {
-                k_ln<<<ln_blocks, 256, 0, st>>>(d.z, pending->ln3w, pending->ln3b, d.h, M);
+                k_ln<<<ln_blocks, 256, 0, st>>>(d.z, pending->ln3w, pending->ln3b, d.h, d.h_b, d.h_s, M);
                 LAUNCH_CHECK(h);
             }
             const int NQ = 2 * D + H * D;
-            if ((rc = idb_gemm(h, d.h, D, L.w_qkvf, D, L.b_qkvf, nullptr, 0, d.qkv, NQ, M, NQ, D, EPI_BIAS, st))) return rc;
+            if ((rc = linear(h, d.h_b, d.h_s, D, L.w_qkvf_b, L.w_qkvf_s, D, L.b_qkvf, nullptr, d.qkv, nullptr, nullptr, NQ, M, NQ, D,
+                             EPI_BIAS, st))) return rc;
             k_attn_ln<<<slab_grid, 256, attn_smem(T, H), st>>>(d.qkv, NQ, d.qkv + D, NQ, d.qkv + 2 * D, NQ, T, 1, d.h, L.bo_f,
-                                                               L.ln1w, L.ln1b, x1, T, T, H);
+                                                               L.ln1w, L.ln1b, d.h2, d.h2_b, d.h2_s, T, T, H);
             LAUNCH_CHECK(h);
         }
-        // cross attention: x1 -> d.h
-        if ((rc = idb_gemm(h, x1, D, L.w_qc, D, L.b_qc, nullptr, 0, d.qc, D, M, D, D, EPI_BIAS, st))) return rc;
-        k_attn_ln<<<slab_grid, 256, attn_smem(Tm, H), st>>>(d.qc, D, L.kv_mem, 2 * D, L.vp_mem, H * D, 1, B, x1, L.b_oc,
-                                                            L.ln2w, L.ln2b, d.h, T, Tm, H);
+        // ---- cross attention: x1 -> (d.h, h_b, h_s)
+        if ((rc = linear(h, d.h2_b, d.h2_s, D, L.w_qc_b, L.w_qc_s, D, L.b_qc, nullptr, d.qc, nullptr, nullptr, D, M, D, D, EPI_BIAS, st)))
+            return rc;
+        k_attn_ln<<<slab_grid, 256, attn_smem(Tm, H), st>>>(d.qc, D, L.kv_mem, 2 * D, L.vp_mem, H * D, 1, B, d.h2, L.b_oc,
+                                                            L.ln2w, L.ln2b, d.h, d.h_b, d.h_s, T, Tm, H);
         LAUNCH_CHECK(h);
-        // feed forward: d.h -> d.z (pre-norm3, residual added in the GEMM epilogue)
-        if ((rc = idb_gemm(h, d.h, D, L.w1, D, L.b1, nullptr, 0, d.ff, F, M, F, D, EPI_BIAS | EPI_GELU, st))) return rc;
-        if ((rc = idb_gemm(h, d.ff, F, L.w2, F, L.b2, d.h, D, d.z, D, M, D, F, EPI_BIAS | EPI_RES, st))) return rc;
+        // ---- feed forward: ff = gelu(h W1^T + b1) kept split only; z = ff W2^T + b2 + h  (pre-norm3)
+        if ((rc = linear(h, d.h_b, d.h_s, D, L.w1_b, L.w1_s, D, L.b1, nullptr, nullptr, d.ff_b, d.ff_s, F, M, F, D, EPI_BIAS | EPI_GELU, st)))
+            return rc;
+        if ((rc = linear(h, d.ff_b, d.ff_s, F, L.w2_b, L.w2_s, F, L.b2, d.h, d.z, nullptr, nullptr, D, M, D, F, EPI_BIAS | EPI_RES, st)))
+            return rc;
         // QaN layers return tgt + (x - tgt) (model/sublayers.py:338-339); that differs from x by
         // <= 1 ulp of max(|x|,|tgt|) and is not reproduced (DESIGN.md "Deviations").
         pending = &L;
     }
-    k_ln<<<ln_blocks, 256, 0, st>>>(d.z, pending->ln3w, pending->ln3b, d.h, M);
+    k_ln<<<ln_blocks, 256, 0, st>>>(d.z, pending->ln3w, pending->ln3b, d.h, d.h_b, d.h_s, M);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }
@@ -711,14 +819,16 @@ int idb_denoiser_run(idb_handle* h, const float* x, const long long* t_dev, cons
     int rc;
     k_temb_addend<<<B, D, 0, st>>>(d.pe, t_dev, d.te_w0T, d.te_b0, d.te_w2T, d.te_b2, d.b_in, d.addend, d.pe_rows, T);
     LAUNCH_CHECK(h);
-    const int Cp = (C + 3) & ~3;
-    k_to_tokens<<<B, 256, sizeof(float) * (size_t)C * (T + 1), st>>>(x, d.xtok, C, Cp, T);
+    const int Cp = (C + 7) & ~7;
+    k_to_tokens<<<B, 256, sizeof(float) * (size_t)C * (T + 1), st>>>(x, d.xtok_b, d.xtok_s, C, Cp, T);
     LAUNCH_CHECK(h);
     // input embedding (model/diffusion_smpl.py:227-232): h = xtok W_in^T + (b_in + temb + pe)
-    if ((rc = idb_gemm(h, d.xtok, Cp, d.w_in, Cp, nullptr, d.addend, D, d.h, D, M, D, Cp, EPI_RES, st))) return rc;
+    if ((rc = linear(h, d.xtok_b, d.xtok_s, Cp, d.w_in_b, d.w_in_s, Cp, nullptr, d.addend, d.h, d.h_b, d.h_s, D, M, D, Cp, EPI_RES, st)))
+        return rc;
     if ((rc = denoiser_layers(h, st))) return rc;
     // output heads (model/diffusion_smpl.py:234-237)
-    if ((rc = idb_gemm(h, d.h, D, d.w_out, D, d.b_out, nullptr, 0, d.lin, Clin, M, Clin, D, EPI_BIAS, st))) return rc;
+    if ((rc = linear(h, d.h_b, d.h_s, D, d.w_out_b, d.w_out_s, D, d.b_out, nullptr, d.lin, nullptr, nullptr, Clin, M, Clin, D, EPI_BIAS, st)))
+        return rc;
     k_heads_post<<<B, 256, sizeof(float) * (size_t)T * (Clin + 1), st>>>(d.lin, d.zero_pose, gt, mask, out, T, Clin, C, c.variant,
                                                                           c.c_body, c.n_points);
     LAUNCH_CHECK(h);

@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(name="smpl_diffusion_100step", B=64, T=30, past_len=10, diffusion_steps=100, C=144)
+FF1_DRAM_TRAFFIC_BYTES = None   # filled from profiles/r1_ncu_full_gemm.txt once captured
 METRIC = "HOI denoising-steps/sec (B=64,T=30)"
 UNIT = "denoising steps/s"
 
@@ -216,7 +217,7 @@ def run_ours(args):
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     # ---- roofline of the dominant kernel (feed-forward GEMMs, 16.1 of the 24.5 GFLOP of a step)
-    roof = eng.gemm_microbench(M=w["B"] * w["T"], N=1024, K=256, iters=50) if hasattr(eng, "gemm_microbench") else None
+    roof = eng.gemm_microbench(M=w["B"] * w["T"], N=1024, K=256, iters=200)
 
     dev_ms, e2e_ms = aggregate_max([dev_ms, e2e_ms], device=dev)
     if rank == 0:
@@ -225,7 +226,7 @@ def run_ours(args):
         value = total_steps / (dev_ms / 1000.0)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                     ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f32 (fp32 SIMT GEMMs)" if args.backend == "simt" else "f32 (GEMMs: 3xTF32 split on tcgen05, fp32 TMEM accumulate)",
+                    dtype="f32 (fp32 SIMT GEMMs)" if args.backend == "simt" else "f32-grade (GEMMs: fp16 hi/lo split pairs on tcgen05, fp32 TMEM accumulate; rest fp32)",
                     data="synthetic",
                     config=dict(workload="SMPL diffusion, 100 DDPM steps, B=64 per GPU, T=30 (past 10 + future 20), 144 channels, "
                                          "inpainting mask on the past, no correction (BASELINE configs[1])",
@@ -240,8 +241,12 @@ def run_ours(args):
             flops = 2.0 * roof["M"] * roof["N"] * roof["K"]
             ach = flops / (roof["ms"] * 1e-3) / 1e12
             line["roofline"] = dict(bound="tensor", kernel=roof["kernel"], achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s",
-                                    frac=ach / peaks["bf16_tflops"], traffic=None, peak_source=peaks["source"],
-                                    note="algorithmic 2*M*N*K of the ff1 GEMM (M=1920,N=1024,K=256) / mean launch time over %d launches" % roof["iters"])
+                                    frac=ach / peaks["bf16_tflops"], traffic=FF1_DRAM_TRAFFIC_BYTES, peak_source=peaks["source"] + " (burst bf16)",
+                                    issue_ceiling=peaks["bf16_tflops"] / 3.0, frac_of_issue_ceiling=ach / (peaks["bf16_tflops"] / 3.0),
+                                    note="algorithmic 2*M*N*K (1.007 GFLOP) of the ff1 GEMM (M=1920,N=1024,K=256) / mean time of %d "
+                                         "back-to-back launches (CUDA events); the split-precision kernel issues 3 fp16 MMAs per algorithmic "
+                                         "MAC, so its ceiling is 1/3 of the fp16/bf16 peak; traffic = dram bytes per launch from the "
+                                         "ncu --set full capture in profiles/ (operands are L2 resident in the loop)" % roof["iters"])
         if world == 1 and not args.no_cpu:
             rate, secs, cores = cpu_reference_rate(args.cpu_steps)
             line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="port",

@@ -81,8 +81,10 @@ k_temb_addend(const float* __restrict__ pe, const long long* __restrict__ t, con
 __global__ void k_to_tokens(const float* __restrict__ x, __half* __restrict__ xtok, __half* __restrict__ xtok_s, int C, int Cp, int T) {
     extern __shared__ float sx[];   // [C][T+1]
     const int b = blockIdx.x;
-    for (int i = threadIdx.x; i < C * T; i += blockDim.x) sx[(i / T) * (T + 1) + i % T] = x[(size_t)b * C * T + i];
+#pragma unroll 8
+    for (int i = threadIdx.x; i < C * T; i += blockDim.x) sx[(i / T) * (T + 1) + i % T] = __ldg(x + (size_t)b * C * T + i);
     __syncthreads();
+#pragma unroll 4
     for (int i = threadIdx.x; i < Cp * T; i += blockDim.x) {
         const int t = i / Cp, c = i % Cp;
         // (hi, lo) fp16 pair for the embedding GEMM; zero padding columns
@@ -176,6 +178,8 @@ __device__ __forceinline__ float dot64(const float* __restrict__ a, const float*
 //   values' : v[(b*ksb + j*kst) * ldv + h*256 + n]                    reads self- and cross-attention)
 //             = (V_h W_o,h^T)[j][n]: value vectors already multiplied by the head's out-proj block
 //   out[r]  = LN( res[r] + bo + sum_h sum_j softmax_j(q_h[r].k_h[j] / 8) v'_h[j] )
+// Every global read (q, k, v', residual) is issued up front into shared memory in one batch, so the
+// kernel pays one memory latency; everything after runs out of shared memory.
 __global__ void __launch_bounds__(256)
 k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
           int ksb, int kst, const float* __restrict__ res, const float* __restrict__ bo, const float* __restrict__ lnw,
@@ -183,26 +187,32 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
           int T, int Tk, int H) {
     extern __shared__ __align__(16) float sm[];
     const int LDK = HD + 4;
-    float* s_q = sm;                       // [SLAB][D]
-    float* s_k = s_q + SLAB * D;           // [H*Tk][LDK]
-    float* s_a = s_k + H * Tk * LDK;       // [H*Tk][SLAB]  (transposed: the 16 rows of one (h,j) are contiguous)
-    float* s_z = s_a + SLAB * H * Tk;      // [SLAB][LDZ]
-    const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
     const int HT = H * Tk;
+    float* s_q = sm;                       // [SLAB][LDZ]  (padded rows: 16 query rows are read by one warp)
+    float* s_k = s_q + SLAB * LDZ;         // [H*Tk][LDK]
+    float* s_a = s_k + HT * LDK;           // [H*Tk][SLAB]  (transposed: the 16 rows of one (h,j) are contiguous)
+    float* s_z = s_a + SLAB * HT;          // [SLAB][LDZ]   residual rows, then the pre-LayerNorm sums
+    float* s_v = s_z + SLAB * LDZ;         // [H*Tk][D]     folded values
+    const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
     for (int i = tid; i < nr * (D / 4); i += 256) {
         const int r = i / (D / 4), c = i % (D / 4);
-        reinterpret_cast<float4*>(s_q + r * D)[c] = reinterpret_cast<const float4*>(q + (size_t)(b * T + r0 + r) * ldq)[c];
+        *reinterpret_cast<float4*>(s_q + r * LDZ + c * 4) = reinterpret_cast<const float4*>(q + (size_t)(b * T + r0 + r) * ldq)[c];
+        *reinterpret_cast<float4*>(s_z + r * LDZ + c * 4) = reinterpret_cast<const float4*>(res + (size_t)(b * T + r0 + r) * D)[c];
     }
     for (int i = tid; i < Tk * (D / 4); i += 256) {
         const int j = i / (D / 4), c = i % (D / 4);          // c-th float4 of key row j: head c/16, offset (c%16)*4
         const float4 kv = reinterpret_cast<const float4*>(k + (size_t)(b * ksb + j * kst) * ldk)[c];
         *reinterpret_cast<float4*>(s_k + ((c / 16) * Tk + j) * LDK + (c % 16) * 4) = kv;
     }
+    for (int i = tid; i < HT * (D / 4); i += 256) {
+        const int hj = i / (D / 4), c = i % (D / 4), hh = hj / Tk, j = hj % Tk;
+        reinterpret_cast<float4*>(s_v + (size_t)hj * D)[c] = reinterpret_cast<const float4*>(v + (size_t)(b * ksb + j * kst) * ldv + hh * D)[c];
+    }
     __syncthreads();
     const float scale = 0.125f;   // 1/sqrt(64)
     for (int i = tid; i < SLAB * HT; i += 256) {
         const int hj = i / SLAB, r = i % SLAB, hh = hj / Tk;
-        s_a[i] = r < nr ? dot64(s_q + r * D + hh * HD, s_k + hj * LDK) * scale : 0.f;
+        s_a[i] = r < nr ? dot64(s_q + r * LDZ + hh * HD, s_k + hj * LDK) * scale : 0.f;
     }
     __syncthreads();
     for (int g = tid; g < nr * H; g += 256) {
@@ -220,23 +230,20 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
         float acc[SLAB];
 #pragma unroll
         for (int r = 0; r < SLAB; r++) acc[r] = 0.f;
-        for (int hh = 0; hh < H; hh++) {
-            const float* vb = v + (size_t)b * ksb * ldv + hh * D + n;
-#pragma unroll 5
-            for (int j = 0; j < Tk; j++) {
-                const float vv = __ldg(vb + (size_t)j * kst * ldv);
-                const float4* ap = reinterpret_cast<const float4*>(s_a + (hh * Tk + j) * SLAB);
-                const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];     // rows >= nr hold zeros
-                acc[0] = fmaf(a0.x, vv, acc[0]); acc[1] = fmaf(a0.y, vv, acc[1]); acc[2] = fmaf(a0.z, vv, acc[2]); acc[3] = fmaf(a0.w, vv, acc[3]);
-                acc[4] = fmaf(a1.x, vv, acc[4]); acc[5] = fmaf(a1.y, vv, acc[5]); acc[6] = fmaf(a1.z, vv, acc[6]); acc[7] = fmaf(a1.w, vv, acc[7]);
-                acc[8] = fmaf(a2.x, vv, acc[8]); acc[9] = fmaf(a2.y, vv, acc[9]); acc[10] = fmaf(a2.z, vv, acc[10]); acc[11] = fmaf(a2.w, vv, acc[11]);
-                acc[12] = fmaf(a3.x, vv, acc[12]); acc[13] = fmaf(a3.y, vv, acc[13]); acc[14] = fmaf(a3.z, vv, acc[14]); acc[15] = fmaf(a3.w, vv, acc[15]);
-            }
+#pragma unroll 4
+        for (int hj = 0; hj < HT; hj++) {
+            const float vv = s_v[(size_t)hj * D + n];
+            const float4* ap = reinterpret_cast<const float4*>(s_a + hj * SLAB);
+            const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];     // rows >= nr hold zeros
+            acc[0] = fmaf(a0.x, vv, acc[0]); acc[1] = fmaf(a0.y, vv, acc[1]); acc[2] = fmaf(a0.z, vv, acc[2]); acc[3] = fmaf(a0.w, vv, acc[3]);
+            acc[4] = fmaf(a1.x, vv, acc[4]); acc[5] = fmaf(a1.y, vv, acc[5]); acc[6] = fmaf(a1.z, vv, acc[6]); acc[7] = fmaf(a1.w, vv, acc[7]);
+            acc[8] = fmaf(a2.x, vv, acc[8]); acc[9] = fmaf(a2.y, vv, acc[9]); acc[10] = fmaf(a2.z, vv, acc[10]); acc[11] = fmaf(a2.w, vv, acc[11]);
+            acc[12] = fmaf(a3.x, vv, acc[12]); acc[13] = fmaf(a3.y, vv, acc[13]); acc[14] = fmaf(a3.z, vv, acc[14]); acc[15] = fmaf(a3.w, vv, acc[15]);
         }
         const float bb = bo[n];
 #pragma unroll
         for (int r = 0; r < SLAB; r++)
-            if (r < nr) s_z[r * LDZ + n] = (acc[r] + bb) + res[(size_t)(b * T + r0 + r) * D + n];
+            if (r < nr) s_z[r * LDZ + n] = (acc[r] + bb) + s_z[r * LDZ + n];
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
@@ -283,25 +290,34 @@ k_qan_ln(const float* __restrict__ zin, const float* __restrict__ prew, const fl
         *reinterpret_cast<float4*>(s_qt + r * LDZ + c * 4) = val;
     }
     __syncthreads();
-    // P[r][s*N+n] = x[t+s-1] . Qt[s*N+n]  for the slab rows t = r0 + r
-    for (int i = tid; i < nr * 32; i += 256) {
-        const int r = i >> 5, j = i & 31;
-        if (j >= NQ) continue;
-        const int s = j / N, t = r0 + r + s - 1;
-        float a = 0.f;
-        if (t >= 0 && t < T) {
-            const float4* px = reinterpret_cast<const float4*>(s_x + (r + s) * LDZ);
-            const float4* pq = reinterpret_cast<const float4*>(s_qt + j * LDZ);
-            float a1 = 0.f;
-#pragma unroll 8
-            for (int c = 0; c < D / 4; c += 2) {
-                const float4 x0 = px[c], y0 = pq[c], x1 = px[c + 1], y1 = pq[c + 1];
-                a = fmaf(x0.x, y0.x, a); a = fmaf(x0.y, y0.y, a); a = fmaf(x0.z, y0.z, a); a = fmaf(x0.w, y0.w, a);
-                a1 = fmaf(x1.x, y1.x, a1); a1 = fmaf(x1.y, y1.y, a1); a1 = fmaf(x1.z, y1.z, a1); a1 = fmaf(x1.w, y1.w, a1);
-            }
-            a += a1;
+    // P[r][s*N+n] = x[t+s-1] . Qt[s*N+n]  for the slab rows t = r0 + r.
+    // Warp w owns the folded queries j = 4w..4w+3 (their 8-element slices per lane stay in registers)
+    // and sweeps the nr+2 staged rows once: shared-memory traffic is one pass over the rows per warp.
+    {
+        float qreg[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = warp * 4 + u;
+            const float4 q0 = *reinterpret_cast<const float4*>(s_qt + j * LDZ + lane * 4);
+            const float4 q1 = *reinterpret_cast<const float4*>(s_qt + j * LDZ + 128 + lane * 4);
+            qreg[u][0] = q0.x; qreg[u][1] = q0.y; qreg[u][2] = q0.z; qreg[u][3] = q0.w;
+            qreg[u][4] = q1.x; qreg[u][5] = q1.y; qreg[u][6] = q1.z; qreg[u][7] = q1.w;
         }
-        s_p[i] = a;
+        for (int l = 0; l < nr + 2; l++) {
+            const int t = r0 - 1 + l;
+            if (t < 0 || t >= T) continue;                     // warp-uniform
+            const float4 x0 = *reinterpret_cast<const float4*>(s_x + l * LDZ + lane * 4);
+            const float4 x1 = *reinterpret_cast<const float4*>(s_x + l * LDZ + 128 + lane * 4);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                float a = x0.x * qreg[u][0];
+                a = fmaf(x0.y, qreg[u][1], a); a = fmaf(x0.z, qreg[u][2], a); a = fmaf(x0.w, qreg[u][3], a);
+                a = fmaf(x1.x, qreg[u][4], a); a = fmaf(x1.y, qreg[u][5], a); a = fmaf(x1.z, qreg[u][6], a); a = fmaf(x1.w, qreg[u][7], a);
+                a = warp_sum(a);
+                const int j = warp * 4 + u, sl = j / N, r = l - sl;   // row l feeds output row r = l - slot
+                if (lane == 0 && j < NQ && r >= 0 && r < nr) s_p[r * 32 + j] = a;
+            }
+        }
     }
     __syncthreads();
     for (int r = tid; r < nr; r += 256) {
@@ -378,8 +394,9 @@ __global__ void k_heads_post(const float* __restrict__ lin, const float* __restr
     const int b = blockIdx.x, LDS_ = Clin + 1;
     if ((Clin & 3) == 0) {
         const float4* l4 = reinterpret_cast<const float4*>(lin + (size_t)b * T * Clin);
+#pragma unroll 5
         for (int i = threadIdx.x; i < T * Clin / 4; i += blockDim.x) {
-            const float4 q4 = l4[i];
+            const float4 q4 = __ldg(l4 + i);
             const int e = i * 4, r = e / Clin, cc = e % Clin;
             float* d4 = so + r * LDS_ + cc;
             d4[0] = q4.x; d4[1] = q4.y; d4[2] = q4.z; d4[3] = q4.w;
@@ -698,7 +715,7 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
     Denoiser& d = h->den;
     if (!d.committed) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_commit first");
     if (T > d.pe_rows) return idb_fail(h, IDB_ERR_ARG, "T exceeds the positional table");
-    if (T > 64 || Tm > 16) return idb_fail(h, IDB_ERR_ARG, "supported window: T <= 64 frames, <= 16 memory tokens");
+    if (T > 36 || Tm > 16) return idb_fail(h, IDB_ERR_ARG, "supported window: T <= 36 frames (reference default 35), <= 16 memory tokens");
     if (d.cfg.variant == 1 && !zero_pose_obj) return idb_fail(h, IDB_ERR_ARG, "skeleton variant needs zero_pose_obj");
     cudaStream_t st = (cudaStream_t)stream;
     const idb_denoiser_config& c = d.cfg;
@@ -746,7 +763,7 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
 }
 
 static size_t attn_smem(int Tk, int H) {
-    return sizeof(float) * ((size_t)SLAB * D + (size_t)H * Tk * (HD + 4) + (size_t)SLAB * H * Tk + (size_t)SLAB * LDZ);
+    return sizeof(float) * ((size_t)SLAB * LDZ + (size_t)H * Tk * (HD + 4) + (size_t)SLAB * H * Tk + (size_t)SLAB * LDZ + (size_t)H * Tk * D);
 }
 static size_t qan_smem() { return sizeof(float) * ((size_t)(SLAB + 2) * LDZ + 32 * LDZ + SLAB * 32 + SLAB * 4); }
 
@@ -836,9 +853,9 @@ int idb_denoiser_run(idb_handle* h, const float* x, const long long* t_dev, cons
 }
 
 int idb_denoiser_prepare_kernels(idb_handle* h) {
-    // opt in to > 48 KB dynamic shared memory once (T <= 64, Tm <= 16 supported)
+    // opt in to > 48 KB dynamic shared memory once (T <= 36, Tm <= 16 supported: the self-attention slab kernel keeps all folded values of a sample, 4*T*256 floats, in shared memory)
     CUDA_TRY(h, cudaFuncSetAttribute(k_qan_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem()));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_attn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(64, 4)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_attn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(36, 4)));
     CUDA_TRY(h, cudaFuncSetAttribute(k_to_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUDA_TRY(h, cudaFuncSetAttribute(k_heads_post, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     return IDB_OK;

@@ -98,25 +98,30 @@ class Engine:
                                           M, N, K, epi, self._stream()))
         return out
 
-    def gemm_microbench(self, M, N, K, iters=50, gelu=True):
-        """Mean device time of the dominant GEMM (bias + GELU epilogue) over `iters` back-to-back
-        launches on the current stream, CUDA events, after warm-up."""
+    def gemm_microbench(self, M, N, K, iters=200, gelu=True):
+        """Mean device time of one tensor-core GEMM launch (fp16-pair operands as the denoiser feeds them,
+        bias + optional GELU epilogue) over `iters` back-to-back launches issued from C on the current
+        stream, CUDA events, after warm-up."""
         g = torch.Generator(device="cpu").manual_seed(0)
         A = torch.randn(M, K, generator=g).to(self.device)
         W = (torch.randn(N, K, generator=g) / K ** 0.5).to(self.device)
         bias = torch.randn(N, generator=g).to(self.device)
         out = torch.empty(M, N, device=self.device)
+        Ah, Al, Wh, Wl = (torch.empty_like(t, dtype=torch.float16) for t in (A, A, W, W))
+        P = self._ptr
+        self._chk(self.lib.idb_debug_split(self._h, P(A), P(Ah), P(Al), M, K, K, self._stream()))
+        self._chk(self.lib.idb_debug_split(self._h, P(W), P(Wh), P(Wl), N, K, K, self._stream()))
         epi = 1 | (2 if gelu else 0)
-        call = lambda n: self._chk(self.lib.idb_debug_gemm_repeat(self._h, self._ptr(A), self._ptr(W), self._ptr(bias), C.c_void_p(),
-                                                                  self._ptr(out), M, N, K, epi, n, self._stream()))
-        call(5)
+        call = lambda n: self._chk(self.lib.idb_debug_gemm_presplit(self._h, P(Ah), P(Al), P(Wh), P(Wl), P(bias), P(out), M, N, K, epi, n,
+                                                                    C.c_void_p(), self._stream()))
+        call(10)
         torch.cuda.synchronize(self.device)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         call(iters)
         e1.record()
         torch.cuda.synchronize(self.device)
-        return dict(M=M, N=N, K=K, iters=iters, ms=e0.elapsed_time(e1) / iters, kernel="gemm ff1 (bias+GELU)")
+        return dict(M=M, N=N, K=K, iters=iters, ms=e0.elapsed_time(e1) / iters, kernel="gemm_split_f16_kernel<128> (ff1: bias+GELU)")
 
     # ------------------------------------------------------------------ denoiser
     def load_denoiser(self, state_dict, variant="smpl", rotary="absolute", n_heads=4, n_queries=10):

@@ -47,6 +47,9 @@ struct DenoiserLayer {
     float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr, *ln3w = nullptr, *ln3b = nullptr;
     float* kv_mem = nullptr;  // [Tm*B][2D] cross-attention K|V of the bound memory
     float* vp_mem = nullptr;  // [Tm*B][H*D] values folded with the out-projection: (V_h Wo_h^T)
+    float* kp_mem = nullptr;  // [Tm*B][H*D] keys folded with the query projection: (K_h Wq_h) / sqrt(hd)
+    float* kc_mem = nullptr;  // [Tm*B][H]   constant logit term (bq_h . K_h) / sqrt(hd)
+    float* w_qcT = nullptr;   // [D][D] transposed cross-attention query weight (for the key fold)
 };
 
 struct Denoiser {
@@ -131,6 +134,16 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+// 16-byte asynchronous global -> shared copies (LDGSTS): a block issues all of a kernel's staging reads
+// back to back and pays ONE memory latency instead of one per loop iteration.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 
 // GEMM front door (gemm.cu): C[M,N] = epi(A[M,K] * W[N,K]^T)   (nn.Linear layout, all row-major)
 enum { EPI_BIAS = 1, EPI_GELU = 2, EPI_RES = 4, EPI_SILU = 8 };

@@ -20,6 +20,21 @@ constexpr int HD = 64;    // head dim
 constexpr int SLAB = 16;  // query rows per block in the per-sample attention kernels
 constexpr int LDZ = D + 4;
 
+// bind-time: scale the folded keys by 1/sqrt(hd) and compute the constant logit term
+//   kc[row][h] = (bq_h . K_h[row]) / 8.   One warp per (row, head).
+__global__ void k_fold_scale(float* __restrict__ kp, const float* __restrict__ kv, const float* __restrict__ bq,
+                             float* __restrict__ kc, int rows, int H) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= rows * H) return;
+    const int row = w / H, hh = w % H;
+    float* p = kp + (size_t)row * H * D + (size_t)hh * D;
+    for (int c = lane; c < D; c += 32) p[c] *= 0.125f;
+    const float* kr = kv + (size_t)row * 2 * D + hh * HD;
+    float a = kr[lane] * bq[hh * HD + lane] + kr[lane + 32] * bq[hh * HD + lane + 32];
+    a = warp_sum(a);
+    if (lane == 0) kc[(size_t)row * H + hh] = a * 0.125f;
+}
+
 // One block per step: t_dev[b] = tbl[counter].t for this step, step_cur = counter, counter -= 1.
 __global__ void k_step_begin(long long* t_dev, const StepParams* tbl, int* counter, int* step_cur, int B) {
     const int c = *counter;
@@ -196,18 +211,18 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
     for (int i = tid; i < nr * (D / 4); i += 256) {
         const int r = i / (D / 4), c = i % (D / 4);
-        *reinterpret_cast<float4*>(s_q + r * LDZ + c * 4) = reinterpret_cast<const float4*>(q + (size_t)(b * T + r0 + r) * ldq)[c];
-        *reinterpret_cast<float4*>(s_z + r * LDZ + c * 4) = reinterpret_cast<const float4*>(res + (size_t)(b * T + r0 + r) * D)[c];
+        cp_async16(s_q + r * LDZ + c * 4, q + (size_t)(b * T + r0 + r) * ldq + c * 4);
+        cp_async16(s_z + r * LDZ + c * 4, res + (size_t)(b * T + r0 + r) * D + c * 4);
     }
     for (int i = tid; i < Tk * (D / 4); i += 256) {
         const int j = i / (D / 4), c = i % (D / 4);          // c-th float4 of key row j: head c/16, offset (c%16)*4
-        const float4 kv = reinterpret_cast<const float4*>(k + (size_t)(b * ksb + j * kst) * ldk)[c];
-        *reinterpret_cast<float4*>(s_k + ((c / 16) * Tk + j) * LDK + (c % 16) * 4) = kv;
+        cp_async16(s_k + ((c / 16) * Tk + j) * LDK + (c % 16) * 4, k + (size_t)(b * ksb + j * kst) * ldk + c * 4);
     }
     for (int i = tid; i < HT * (D / 4); i += 256) {
         const int hj = i / (D / 4), c = i % (D / 4), hh = hj / Tk, j = hj % Tk;
-        reinterpret_cast<float4*>(s_v + (size_t)hj * D)[c] = reinterpret_cast<const float4*>(v + (size_t)(b * ksb + j * kst) * ldv + hh * D)[c];
+        cp_async16(s_v + (size_t)hj * D + c * 4, v + (size_t)(b * ksb + j * kst) * ldv + hh * D + c * 4);
     }
+    cp_async_wait_all();
     __syncthreads();
     const float scale = 0.125f;   // 1/sqrt(64)
     for (int i = tid; i < SLAB * HT; i += 256) {
@@ -253,43 +268,177 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cross-attention block with BOTH projections folded into the step-invariant memory tensors:
+//   logit[t,h,j] = x1[t] . kp[h,j] + kc[h,j]      kp = (K_h Wq_h)/8 (256-vector), kc = (bq_h . K_h)/8
+//   out[t] = LN2( x1[t] + bo + sum_{h,j} softmax_j(logit)[t,h,j] vp[h,j] )      vp = V_h Wo_h^T
+// so no query GEMM is needed and the block can run right after the layer's first sub-block while its
+// x1 rows are still in shared memory.  s_kp [HT][LDZ], s_kc [HT], s_v [HT][D] must already be staged.
+__device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s_x1, const float* __restrict__ s_kp,
+                                                     const float* __restrict__ s_kc, const float* __restrict__ s_v,
+                                                     float* __restrict__ s_a, float* __restrict__ s_z, int nr, int HT, int Tk, int H,
+                                                     const float* __restrict__ bo, const float* __restrict__ lnw,
+                                                     const float* __restrict__ lnb, float* __restrict__ out,
+                                                     __half* __restrict__ out_b, __half* __restrict__ out_s, size_t row0) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // logits: warp w owns folded keys hj = w, w+8, ... (8-element slices per lane in registers) and sweeps the rows
+    for (int hj0 = warp; hj0 < HT; hj0 += 32) {
+        float kreg[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int hj = hj0 + u * 8;
+            const float4 k0 = hj < HT ? *reinterpret_cast<const float4*>(s_kp + hj * LDZ + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 k1 = hj < HT ? *reinterpret_cast<const float4*>(s_kp + hj * LDZ + 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            kreg[u][0] = k0.x; kreg[u][1] = k0.y; kreg[u][2] = k0.z; kreg[u][3] = k0.w;
+            kreg[u][4] = k1.x; kreg[u][5] = k1.y; kreg[u][6] = k1.z; kreg[u][7] = k1.w;
+        }
+        for (int r = 0; r < SLAB; r++) {
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            if (r < nr) {
+                const float4 x0 = *reinterpret_cast<const float4*>(s_x1 + r * LDZ + lane * 4);
+                const float4 x1 = *reinterpret_cast<const float4*>(s_x1 + r * LDZ + 128 + lane * 4);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    float t = x0.x * kreg[u][0];
+                    t = fmaf(x0.y, kreg[u][1], t); t = fmaf(x0.z, kreg[u][2], t); t = fmaf(x0.w, kreg[u][3], t);
+                    t = fmaf(x1.x, kreg[u][4], t); t = fmaf(x1.y, kreg[u][5], t); t = fmaf(x1.z, kreg[u][6], t); t = fmaf(x1.w, kreg[u][7], t);
+                    a[u] = warp_sum(t);
+                }
+            }
+            if (lane < 4) {
+                const int hj = hj0 + lane * 8;
+                const float av = lane == 0 ? a[0] : (lane == 1 ? a[1] : (lane == 2 ? a[2] : a[3]));
+                if (hj < HT) s_a[hj * SLAB + r] = r < nr ? av + s_kc[hj] : 0.f;
+            }
+        }
+    }
+    __syncthreads();
+    for (int g = tid; g < nr * H; g += 256) {
+        float* col = s_a + (g % H) * Tk * SLAB + (g / H);      // element j at col[j * SLAB]
+        float mx = -INFINITY;
+        for (int j = 0; j < Tk; j++) mx = fmaxf(mx, col[j * SLAB]);
+        float sum = 0.f;
+        for (int j = 0; j < Tk; j++) { const float e = expf(col[j * SLAB] - mx); col[j * SLAB] = e; sum += e; }
+        const float inv = 1.0f / sum;
+        for (int j = 0; j < Tk; j++) col[j * SLAB] *= inv;
+    }
+    __syncthreads();
+    {
+        const int n = tid;
+        float acc[SLAB];
+#pragma unroll
+        for (int r = 0; r < SLAB; r++) acc[r] = 0.f;
+#pragma unroll 4
+        for (int hj = 0; hj < HT; hj++) {
+            const float vv = s_v[(size_t)hj * D + n];
+            const float4* ap = reinterpret_cast<const float4*>(s_a + hj * SLAB);
+            const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];     // rows >= nr hold zeros
+            acc[0] = fmaf(a0.x, vv, acc[0]); acc[1] = fmaf(a0.y, vv, acc[1]); acc[2] = fmaf(a0.z, vv, acc[2]); acc[3] = fmaf(a0.w, vv, acc[3]);
+            acc[4] = fmaf(a1.x, vv, acc[4]); acc[5] = fmaf(a1.y, vv, acc[5]); acc[6] = fmaf(a1.z, vv, acc[6]); acc[7] = fmaf(a1.w, vv, acc[7]);
+            acc[8] = fmaf(a2.x, vv, acc[8]); acc[9] = fmaf(a2.y, vv, acc[9]); acc[10] = fmaf(a2.z, vv, acc[10]); acc[11] = fmaf(a2.w, vv, acc[11]);
+            acc[12] = fmaf(a3.x, vv, acc[12]); acc[13] = fmaf(a3.y, vv, acc[13]); acc[14] = fmaf(a3.z, vv, acc[14]); acc[15] = fmaf(a3.w, vv, acc[15]);
+        }
+        const float bb = bo[n];
+#pragma unroll
+        for (int r = 0; r < SLAB; r++)
+            if (r < nr) s_z[r * LDZ + n] = (acc[r] + bb) + s_x1[r * LDZ + n];
+    }
+    __syncthreads();
+    for (int r = warp; r < nr; r += 8) {
+        const size_t o = (row0 + r) * D;
+        warp_ln_row(s_z + r * LDZ, lnw, lnb, out + o, lane, out_b ? out_b + o : nullptr, out_s ? out_s + o : nullptr);
+    }
+}
+
+// stage the folded memory tensors of sample b (rows j*B + b of kp / vp / kc) into shared memory
+__device__ __forceinline__ void stage_memory(const float* __restrict__ kp, const float* __restrict__ kc, const float* __restrict__ vp,
+                                             float* __restrict__ s_kp, float* __restrict__ s_kc, float* __restrict__ s_v,
+                                             int b, int B, int Tk, int H) {
+    const int HT = H * Tk, tid = threadIdx.x;
+    for (int i = tid; i < HT * (D / 4); i += 256) {
+        const int hj = i / (D / 4), c = i % (D / 4), hh = hj / Tk, j = hj % Tk;
+        const size_t row = (size_t)(j * B + b) * H * D + (size_t)hh * D;
+        cp_async16(s_kp + hj * LDZ + c * 4, kp + row + c * 4);
+        cp_async16(s_v + (size_t)hj * D + c * 4, vp + row + c * 4);
+    }
+    for (int hj = tid; hj < HT; hj += 256) s_kc[hj] = kc[(size_t)((hj % Tk) * B + b) * H + hj / Tk];
+}
+
+// standalone cross-attention block (layers whose first sub-block is the standard self-attention)
+__global__ void __launch_bounds__(256)
+k_xattn_ln(const float* __restrict__ x1, const float* __restrict__ kp, const float* __restrict__ kc, const float* __restrict__ vp,
+           const float* __restrict__ bo, const float* __restrict__ lnw, const float* __restrict__ lnb, float* __restrict__ out,
+           __half* __restrict__ out_b, __half* __restrict__ out_s, int T, int B, int Tk, int H) {
+    extern __shared__ __align__(16) float sm[];
+    const int HT = H * Tk;
+    float* s_x1 = sm;                       // [SLAB][LDZ]
+    float* s_kp = s_x1 + SLAB * LDZ;        // [HT][LDZ]
+    float* s_v = s_kp + HT * LDZ;           // [HT][D]
+    float* s_a = s_v + HT * D;              // [HT][SLAB]
+    float* s_z = s_a + HT * SLAB;           // [SLAB][LDZ]
+    float* s_kc = s_z + SLAB * LDZ;         // [HT]
+    const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
+    for (int i = tid; i < nr * (D / 4); i += 256) {
+        const int r = i / (D / 4), c = i % (D / 4);
+        cp_async16(s_x1 + r * LDZ + c * 4, x1 + (size_t)(b * T + r0 + r) * D + c * 4);
+    }
+    stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H);
+    cp_async_wait_all();
+    __syncthreads();
+    cross_attention_tail(s_x1, s_kp, s_kc, s_v, s_a, s_z, nr, HT, Tk, H, bo, lnw, lnb, out, out_b, out_s, (size_t)b * T + r0);
+}
+
 // QaN block + residual + LayerNorm1 (model/sublayers.py:343-352 + :332) for a slab of <= 16 rows of
 // one sample, with an optional LayerNorm applied to the input rows first (the previous layer's
 // pending norm3).   grid (B, ceil(T/16)), block 256.
 //   x = pre ? LN_pre(zin) : zin
 //   logit[t,n,s] = x[t+s-1] . Qt[s][n]   (Qt = rotary-folded, 1/16-scaled normalised queries; s = key slot)
 //   a = softmax over the valid slots;  y[t] = sum_s (sum_n wk[n] a[t,n,s]) x[t+s-1];  out = LN1(x + y)
+// ... followed, in the same kernel, by the layer's cross-attention block (cross_attention_tail) on the
+// LN1 rows, which never leave shared memory.
 __global__ void __launch_bounds__(256)
-k_qan_ln(const float* __restrict__ zin, const float* __restrict__ prew, const float* __restrict__ preb,
-         const float* __restrict__ qt, const float* __restrict__ wk, const float* __restrict__ lnw,
-         const float* __restrict__ lnb, float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s,
-         int T, int N) {
+k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, const float* __restrict__ preb,
+               const float* __restrict__ qt, const float* __restrict__ wk, const float* __restrict__ lnw,
+               const float* __restrict__ lnb, const float* __restrict__ kp, const float* __restrict__ kc,
+               const float* __restrict__ vp, const float* __restrict__ bo2, const float* __restrict__ ln2w,
+               const float* __restrict__ ln2b, float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s,
+               int T, int N, int B, int Tk, int H) {
     extern __shared__ __align__(16) float sm[];
+    const int HT = H * Tk;
     float* s_x = sm;                        // [SLAB+2][LDZ]   rows r0-1 .. r0+nr
     float* s_qt = s_x + (SLAB + 2) * LDZ;   // [32][LDZ]
     float* s_p = s_qt + 32 * LDZ;           // [SLAB][32]
     float* s_c = s_p + SLAB * 32;           // [SLAB][4]
+    float* s_x1 = s_c + SLAB * 4;           // [SLAB][LDZ]     LN1 rows (input of the cross-attention block)
+    float* s_kp = s_x1 + SLAB * LDZ;        // [HT][LDZ]
+    float* s_v = s_kp + HT * LDZ;           // [HT][D]
+    float* s_a = s_v + HT * D;              // [HT][SLAB]
+    float* s_z = s_a + HT * SLAB;           // [SLAB][LDZ]
+    float* s_kc = s_z + SLAB * LDZ;         // [HT]
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int NQ = 3 * N;
-    // rows r0-1 .. r0+nr (halo of one on each side), local index l = t - (r0 - 1)
-    for (int l = warp; l < nr + 2; l += 8) {
-        const int t = r0 - 1 + l;
-        if (t < 0 || t >= T) continue;
-        const float* src = zin + (size_t)(b * T + t) * D;
-        if (prew) {
-            warp_ln_row(src, prew, preb, s_x + l * LDZ, lane);
-        } else {
-            *reinterpret_cast<float4*>(s_x + l * LDZ + lane * 4) = *reinterpret_cast<const float4*>(src + lane * 4);
-            *reinterpret_cast<float4*>(s_x + l * LDZ + 128 + lane * 4) = *reinterpret_cast<const float4*>(src + 128 + lane * 4);
-        }
+    // rows r0-1 .. r0+nr (halo of one on each side), local index l = t - (r0 - 1); everything the kernel
+    // reads from global memory is issued here in one asynchronous batch
+    for (int i = tid; i < (nr + 2) * (D / 4); i += 256) {
+        const int l = i / (D / 4), c = i % (D / 4), t = r0 - 1 + l;
+        if (t >= 0 && t < T) cp_async16(s_x + l * LDZ + c * 4, zin + (size_t)(b * T + t) * D + c * 4);
     }
     for (int i = tid; i < 32 * (D / 4); i += 256) {
         const int r = i / (D / 4), c = i % (D / 4);
-        const float4 val = (r < NQ) ? reinterpret_cast<const float4*>(qt + (size_t)r * D)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(s_qt + r * LDZ + c * 4) = val;
+        if (r < NQ) cp_async16(s_qt + r * LDZ + c * 4, qt + (size_t)r * D + c * 4);
+        else *reinterpret_cast<float4*>(s_qt + r * LDZ + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H);
+    cp_async_wait_all();
     __syncthreads();
+    if (prew) {   // the previous layer's pending LayerNorm3, in place on the staged rows
+        for (int l = warp; l < nr + 2; l += 8) {
+            const int t = r0 - 1 + l;
+            if (t >= 0 && t < T) warp_ln_row(s_x + l * LDZ, prew, preb, s_x + l * LDZ, lane);
+        }
+        __syncthreads();
+    }
     // P[r][s*N+n] = x[t+s-1] . Qt[s*N+n]  for the slab rows t = r0 + r.
     // Warp w owns the folded queries j = 4w..4w+3 (their 8-element slices per lane stay in registers)
     // and sweeps the nr+2 staged rows once: shared-memory traffic is one pass over the rows per warp.
@@ -372,16 +521,11 @@ k_qan_ln(const float* __restrict__ zin, const float* __restrict__ prew, const fl
             float4 o;
             o.x = (v[half * 4 + 0] - mean) * rstd * w4.x + b4.x; o.y = (v[half * 4 + 1] - mean) * rstd * w4.y + b4.y;
             o.z = (v[half * 4 + 2] - mean) * rstd * w4.z + b4.z; o.w = (v[half * 4 + 3] - mean) * rstd * w4.w + b4.w;
-            *reinterpret_cast<float4*>(out + (size_t)(b * T + t) * D + c) = o;
-            if (out_b) {
-                __half2 h01, h23, l01, l23;
-                split_f16x2(o.x, o.y, h01, l01);
-                split_f16x2(o.z, o.w, h23, l23);
-                *reinterpret_cast<uint2*>(out_b + (size_t)(b * T + t) * D + c) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
-                *reinterpret_cast<uint2*>(out_s + (size_t)(b * T + t) * D + c) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
-            }
+            *reinterpret_cast<float4*>(s_x1 + r * LDZ + c) = o;
         }
     }
+    __syncthreads();
+    cross_attention_tail(s_x1, s_kp, s_kc, s_v, s_a, s_z, nr, HT, Tk, H, bo2, ln2w, ln2b, out, out_b, out_s, (size_t)b * T + r0);
 }
 
 // Linear outputs lin[(b*T+t)][Clin] -> x0 (B,1,C,T) with the skeleton's keypoint re-derivation and
@@ -670,6 +814,12 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
             GET(w, p + "multihead_attn.in_proj_weight", 3 * D, D) GET(b, p + "multihead_attn.in_proj_bias", 3 * D)
             GET(wo, p + "multihead_attn.out_proj.weight", D, D) GET(bo, p + "multihead_attn.out_proj.bias", D)
             L.w_qc = w->p; L.b_qc = b->p; L.w_kvc = w->p + (size_t)D * D; L.b_kvc = b->p + D; L.w_oc = wo->p; L.b_oc = bo->p;
+            {   // Wq^T [k][h*64+d], for folding the query projection into the memory keys at bind time
+                auto hwq = P.host(w);
+                std::vector<float> wT((size_t)D * D);
+                for (int o = 0; o < D; o++) for (int k = 0; k < D; k++) wT[(size_t)k * D + o] = hwq[(size_t)o * D + k];
+                L.w_qcT = P.up(wT);
+            }
             GET(w1, p + "linear1.weight", F, D) GET(b1, p + "linear1.bias", F)
             GET(w2, p + "linear2.weight", D, F) GET(b2, p + "linear2.bias", D)
             L.w1 = w1->p; L.b1 = b1->p; L.w2 = w2->p; L.b2 = b2->p;
@@ -739,7 +889,10 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
         rc |= AH(&d.h_b, (size_t)M * D); rc |= AH(&d.h_s, (size_t)M * D); rc |= AH(&d.h2_b, (size_t)M * D); rc |= AH(&d.h2_s, (size_t)M * D);
         rc |= AH(&d.ff_b, (size_t)M * F); rc |= AH(&d.ff_s, (size_t)M * F); rc |= AH(&d.xtok_b, (size_t)M * Cp8); rc |= AH(&d.xtok_s, (size_t)M * Cp8);
         rc |= A(&d.zero_pose, (size_t)B * npts * 3);
-        for (auto& L : d.layers) { rc |= A(&L.kv_mem, (size_t)Tm * B * 2 * D); rc |= A(&L.vp_mem, (size_t)Tm * B * H * D); }
+        for (auto& L : d.layers) {
+            rc |= A(&L.kv_mem, (size_t)Tm * B * 2 * D); rc |= A(&L.vp_mem, (size_t)Tm * B * H * D);
+            rc |= A(&L.kp_mem, (size_t)Tm * B * H * D); rc |= A(&L.kc_mem, (size_t)Tm * B * H);
+        }
         if (rc) return rc;
         CUDA_TRY(h, cudaMalloc((void**)&d.t_dev, sizeof(long long) * B));
         CUDA_TRY(h, cudaMalloc((void**)&d.step_cur, sizeof(int)));
@@ -757,7 +910,13 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
             rc = idb_gemm(h, L.kv_mem + D + hh * HD, 2 * D, L.w_oc + hh * HD, D, nullptr, nullptr, 0, L.vp_mem + hh * D, H * D,
                           Tm * B, D, HD, 0, st);
             if (rc) return rc;
+            // kp[:, h*D + k] = sum_d K[:, h*64+d] Wq[h*64+d][k]   (scaled by 1/sqrt(hd) in k_fold_scale)
+            rc = idb_gemm(h, L.kv_mem + hh * HD, 2 * D, L.w_qcT + hh * HD, D, nullptr, nullptr, 0, L.kp_mem + hh * D, H * D,
+                          Tm * B, D, HD, 0, st);
+            if (rc) return rc;
         }
+        k_fold_scale<<<(Tm * B * H + 7) / 8, 256, 0, st>>>(L.kp_mem, L.kv_mem, L.b_qc, L.kc_mem, Tm * B, H);
+        LAUNCH_CHECK(h);
     }
     return IDB_OK;
 }
@@ -765,7 +924,13 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
 static size_t attn_smem(int Tk, int H) {
     return sizeof(float) * ((size_t)SLAB * LDZ + (size_t)H * Tk * (HD + 4) + (size_t)SLAB * H * Tk + (size_t)SLAB * LDZ + (size_t)H * Tk * D);
 }
-static size_t qan_smem() { return sizeof(float) * ((size_t)(SLAB + 2) * LDZ + 32 * LDZ + SLAB * 32 + SLAB * 4); }
+static size_t xattn_tail_smem(int Tk, int H) {   // s_x1, s_kp, s_v, s_a, s_z, s_kc
+    const size_t HT = (size_t)H * Tk;
+    return sizeof(float) * ((size_t)SLAB * LDZ + HT * LDZ + HT * D + HT * SLAB + (size_t)SLAB * LDZ + HT + 4);
+}
+static size_t qan_smem(int Tk, int H) {
+    return sizeof(float) * ((size_t)(SLAB + 2) * LDZ + 32 * LDZ + SLAB * 32 + SLAB * 4) + xattn_tail_smem(Tk, H);
+}
 
 // One nn.Linear on fp16 (hi, lo) operand pairs; output as full fp32 and/or as a pair.
 static int linear(idb_handle* h, const __half* a_b, const __half* a_s, int lda, const __half* w_b, const __half* w_s, int ldw,
@@ -790,8 +955,10 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
         // ---- first sub-block -> x1 = (d.h2, h2_b, h2_s)
         if (L.qan) {
             const float* in = pending ? d.z : d.h;
-            k_qan_ln<<<slab_grid, 256, qan_smem(), st>>>(in, pending ? pending->ln3w : nullptr, pending ? pending->ln3b : nullptr,
-                                                          L.qt, L.wk, L.ln1w, L.ln1b, d.h2, d.h2_b, d.h2_s, T, N);
+            // QaN block + LN1 + cross-attention + LN2 in one kernel: (z | h) -> (d.h2, pairs)
+            k_qan_xattn_ln<<<slab_grid, 256, qan_smem(Tm, H), st>>>(in, pending ? pending->ln3w : nullptr, pending ? pending->ln3b : nullptr,
+                                                                     L.qt, L.wk, L.ln1w, L.ln1b, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc,
+                                                                     L.ln2w, L.ln2b, d.h2, d.h2_b, d.h2_s, T, N, B, Tm, H);
             LAUNCH_CHECK(h);
         } else {
             if (pending) {
@@ -802,19 +969,17 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
             if ((rc = linear(h, d.h_b, d.h_s, D, L.w_qkvf_b, L.w_qkvf_s, D, L.b_qkvf, nullptr, d.qkv, nullptr, nullptr, NQ, M, NQ, D,
                              EPI_BIAS, st))) return rc;
             k_attn_ln<<<slab_grid, 256, attn_smem(T, H), st>>>(d.qkv, NQ, d.qkv + D, NQ, d.qkv + 2 * D, NQ, T, 1, d.h, L.bo_f,
-                                                               L.ln1w, L.ln1b, d.h2, d.h2_b, d.h2_s, T, T, H);
+                                                               L.ln1w, L.ln1b, d.qc, nullptr, nullptr, T, T, H);
+            LAUNCH_CHECK(h);
+            // cross attention on the LN1 rows (d.qc) -> (d.h2, pairs)
+            k_xattn_ln<<<slab_grid, 256, xattn_tail_smem(Tm, H), st>>>(d.qc, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc, L.ln2w, L.ln2b,
+                                                                        d.h2, d.h2_b, d.h2_s, T, B, Tm, H);
             LAUNCH_CHECK(h);
         }
-        // ---- cross attention: x1 -> (d.h, h_b, h_s)
-        if ((rc = linear(h, d.h2_b, d.h2_s, D, L.w_qc_b, L.w_qc_s, D, L.b_qc, nullptr, d.qc, nullptr, nullptr, D, M, D, D, EPI_BIAS, st)))
+        // ---- feed forward on x2 = d.h2: ff = gelu(x2 W1^T + b1) kept as pairs only; z = ff W2^T + b2 + x2  (pre-norm3)
+        if ((rc = linear(h, d.h2_b, d.h2_s, D, L.w1_b, L.w1_s, D, L.b1, nullptr, nullptr, d.ff_b, d.ff_s, F, M, F, D, EPI_BIAS | EPI_GELU, st)))
             return rc;
-        k_attn_ln<<<slab_grid, 256, attn_smem(Tm, H), st>>>(d.qc, D, L.kv_mem, 2 * D, L.vp_mem, H * D, 1, B, d.h2, L.b_oc,
-                                                            L.ln2w, L.ln2b, d.h, d.h_b, d.h_s, T, Tm, H);
-        LAUNCH_CHECK(h);
-        // ---- feed forward: ff = gelu(h W1^T + b1) kept split only; z = ff W2^T + b2 + h  (pre-norm3)
-        if ((rc = linear(h, d.h_b, d.h_s, D, L.w1_b, L.w1_s, D, L.b1, nullptr, nullptr, d.ff_b, d.ff_s, F, M, F, D, EPI_BIAS | EPI_GELU, st)))
-            return rc;
-        if ((rc = linear(h, d.ff_b, d.ff_s, F, L.w2_b, L.w2_s, F, L.b2, d.h, d.z, nullptr, nullptr, D, M, D, F, EPI_BIAS | EPI_RES, st)))
+        if ((rc = linear(h, d.ff_b, d.ff_s, F, L.w2_b, L.w2_s, F, L.b2, d.h2, d.z, nullptr, nullptr, D, M, D, F, EPI_BIAS | EPI_RES, st)))
             return rc;
         // QaN layers return tgt + (x - tgt) (model/sublayers.py:338-339); that differs from x by
         // <= 1 ulp of max(|x|,|tgt|) and is not reproduced (DESIGN.md "Deviations").
@@ -854,7 +1019,8 @@ int idb_denoiser_run(idb_handle* h, const float* x, const long long* t_dev, cons
 
 int idb_denoiser_prepare_kernels(idb_handle* h) {
     // opt in to > 48 KB dynamic shared memory once (T <= 36, Tm <= 16 supported: the self-attention slab kernel keeps all folded values of a sample, 4*T*256 floats, in shared memory)
-    CUDA_TRY(h, cudaFuncSetAttribute(k_qan_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem()));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem(16, 4)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_tail_smem(16, 4)));
     CUDA_TRY(h, cudaFuncSetAttribute(k_attn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(36, 4)));
     CUDA_TRY(h, cudaFuncSetAttribute(k_to_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     CUDA_TRY(h, cudaFuncSetAttribute(k_heads_post, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));

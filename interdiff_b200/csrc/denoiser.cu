@@ -268,6 +268,51 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
     }
 }
 
+// Register-tiled dot products between two sets of 256-wide rows held in shared memory (row stride
+// LDZ):  part[ks][r][j] = sum_{d in k-slice ks} A[r][d] * Bm[j][d].   No shuffles: a lane owns
+// TR x TJ outputs (rows rl + 4v of its warp's row half, columns jl + 8u) and walks a 64-wide
+// k-slice; the 8 warps are 4 k-slices x 2 row halves.  Consecutive rows / columns across the lanes
+// land in distinct 16-byte bank groups (LDZ = 260), so every LDS.128 is one wavefront, and the FMA
+// to LDS ratio is 4*TR*TJ : TR+TJ.  Rows >= nA / columns >= nB are clamped (results unused).
+// The caller sums the 4 k-slices in a fixed order (deterministic).  part: [4][8*TR][TILE_LDP].
+constexpr int TILE_LDP = 40;
+template <int TR, int TJ>
+__device__ __forceinline__ void tile_dots(const float* __restrict__ sA, int nA, const float* __restrict__ sB, int nB,
+                                          float* __restrict__ part, int warp, int lane) {
+    constexpr int ROWS = 8 * TR;
+    const int jl = lane & 7, rl = lane >> 3, ks = warp & 3, rh = warp >> 2;
+    const float* ap[TR];
+    const float* bp[TJ];
+#pragma unroll
+    for (int v = 0; v < TR; v++) ap[v] = sA + min(rh * 4 * TR + rl + 4 * v, nA - 1) * LDZ + ks * 64;
+#pragma unroll
+    for (int u = 0; u < TJ; u++) bp[u] = sB + min(jl + 8 * u, nB - 1) * LDZ + ks * 64;
+    float acc[TR][TJ];
+#pragma unroll
+    for (int v = 0; v < TR; v++)
+#pragma unroll
+        for (int u = 0; u < TJ; u++) acc[v][u] = 0.f;
+#pragma unroll 4
+    for (int q = 0; q < 16; q++) {
+        float4 a[TR], bq[TJ];
+#pragma unroll
+        for (int v = 0; v < TR; v++) a[v] = *reinterpret_cast<const float4*>(ap[v] + q * 4);
+#pragma unroll
+        for (int u = 0; u < TJ; u++) bq[u] = *reinterpret_cast<const float4*>(bp[u] + q * 4);
+#pragma unroll
+        for (int v = 0; v < TR; v++)
+#pragma unroll
+            for (int u = 0; u < TJ; u++) {
+                acc[v][u] = fmaf(a[v].x, bq[u].x, acc[v][u]); acc[v][u] = fmaf(a[v].y, bq[u].y, acc[v][u]);
+                acc[v][u] = fmaf(a[v].z, bq[u].z, acc[v][u]); acc[v][u] = fmaf(a[v].w, bq[u].w, acc[v][u]);
+            }
+    }
+#pragma unroll
+    for (int v = 0; v < TR; v++)
+#pragma unroll
+        for (int u = 0; u < TJ; u++) part[(ks * ROWS + rh * 4 * TR + rl + 4 * v) * TILE_LDP + jl + 8 * u] = acc[v][u];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Cross-attention block with BOTH projections folded into the step-invariant memory tensors:
 //   logit[t,h,j] = x1[t] . kp[h,j] + kc[h,j]      kp = (K_h Wq_h)/8 (256-vector), kc = (bq_h . K_h)/8
@@ -281,38 +326,20 @@ __device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s
                                                      const float* __restrict__ lnb, float* __restrict__ out,
                                                      __half* __restrict__ out_b, __half* __restrict__ out_s, size_t row0) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // logits: warp w owns folded keys hj = w, w+8, ... (8-element slices per lane in registers) and sweeps the rows
-    for (int hj0 = warp; hj0 < HT; hj0 += 32) {
-        float kreg[4][8];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int hj = hj0 + u * 8;
-            const float4 k0 = hj < HT ? *reinterpret_cast<const float4*>(s_kp + hj * LDZ + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 k1 = hj < HT ? *reinterpret_cast<const float4*>(s_kp + hj * LDZ + 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            kreg[u][0] = k0.x; kreg[u][1] = k0.y; kreg[u][2] = k0.z; kreg[u][3] = k0.w;
-            kreg[u][4] = k1.x; kreg[u][5] = k1.y; kreg[u][6] = k1.z; kreg[u][7] = k1.w;
+    // logits in blocks of 40 folded keys: k-split partial tiles in s_z (free until the value pass), then
+    // a fixed-order sum of the 4 k-slices + the constant term
+    for (int j0 = 0; j0 < HT; j0 += TILE_LDP) {
+        const int nj = min(TILE_LDP, HT - j0);
+        tile_dots<2, 5>(s_x1, nr, s_kp + j0 * LDZ, nj, s_z, warp, lane);
+        __syncthreads();
+        for (int i = tid; i < SLAB * nj; i += 256) {
+            const int r = i / nj, jj = i % nj;
+            const float a = ((s_z[(0 * SLAB + r) * TILE_LDP + jj] + s_z[(1 * SLAB + r) * TILE_LDP + jj]) +
+                             s_z[(2 * SLAB + r) * TILE_LDP + jj]) + s_z[(3 * SLAB + r) * TILE_LDP + jj];
+            s_a[(j0 + jj) * SLAB + r] = r < nr ? a + s_kc[j0 + jj] : 0.f;
         }
-        for (int r = 0; r < SLAB; r++) {
-            float a[4] = {0.f, 0.f, 0.f, 0.f};
-            if (r < nr) {
-                const float4 x0 = *reinterpret_cast<const float4*>(s_x1 + r * LDZ + lane * 4);
-                const float4 x1 = *reinterpret_cast<const float4*>(s_x1 + r * LDZ + 128 + lane * 4);
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    float t = x0.x * kreg[u][0];
-                    t = fmaf(x0.y, kreg[u][1], t); t = fmaf(x0.z, kreg[u][2], t); t = fmaf(x0.w, kreg[u][3], t);
-                    t = fmaf(x1.x, kreg[u][4], t); t = fmaf(x1.y, kreg[u][5], t); t = fmaf(x1.z, kreg[u][6], t); t = fmaf(x1.w, kreg[u][7], t);
-                    a[u] = warp_sum(t);
-                }
-            }
-            if (lane < 4) {
-                const int hj = hj0 + lane * 8;
-                const float av = lane == 0 ? a[0] : (lane == 1 ? a[1] : (lane == 2 ? a[2] : a[3]));
-                if (hj < HT) s_a[hj * SLAB + r] = r < nr ? av + s_kc[hj] : 0.f;
-            }
-        }
+        __syncthreads();
     }
-    __syncthreads();
     for (int g = tid; g < nr * H; g += 256) {
         float* col = s_a + (g % H) * Tk * SLAB + (g / H);      // element j at col[j * SLAB]
         float mx = -INFINITY;
@@ -407,7 +434,7 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     const int HT = H * Tk;
     float* s_x = sm;                        // [SLAB+2][LDZ]   rows r0-1 .. r0+nr
     float* s_qt = s_x + (SLAB + 2) * LDZ;   // [32][LDZ]
-    float* s_p = s_qt + 32 * LDZ;           // [SLAB][32]
+    float* s_p = s_qt + 32 * LDZ;           // [SLAB][N][3] slot probabilities (N <= 10)
     float* s_c = s_p + SLAB * 32;           // [SLAB][4]
     float* s_x1 = s_c + SLAB * 4;           // [SLAB][LDZ]     LN1 rows (input of the cross-attention block)
     float* s_kp = s_x1 + SLAB * LDZ;        // [HT][LDZ]
@@ -439,51 +466,32 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
         }
         __syncthreads();
     }
-    // P[r][s*N+n] = x[t+s-1] . Qt[s*N+n]  for the slab rows t = r0 + r.
-    // Warp w owns the folded queries j = 4w..4w+3 (their 8-element slices per lane stay in registers)
-    // and sweeps the nr+2 staged rows once: shared-memory traffic is one pass over the rows per warp.
-    {
-        float qreg[4][8];
+    // part[ks][l][j] = (k-slice of) x[row l] . Qt[j] for all nr+2 staged rows and the 3N folded queries
+    // (register-tiled, no shuffles); s_z is free until the cross-attention block and holds the partials.
+    tile_dots<3, 4>(s_x, nr + 2, s_qt, 32, s_z, warp, lane);
+    __syncthreads();
+    // softmax over the (<= 3) valid key slots per (row, query); row l = r + slot feeds output row r
+    for (int i = tid; i < nr * N; i += 256) {
+        const int r = i / N, n = i % N, t = r0 + r;
+        const bool v0 = t > 0, v2 = t < T - 1;
+        float lg[3];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int j = warp * 4 + u;
-            const float4 q0 = *reinterpret_cast<const float4*>(s_qt + j * LDZ + lane * 4);
-            const float4 q1 = *reinterpret_cast<const float4*>(s_qt + j * LDZ + 128 + lane * 4);
-            qreg[u][0] = q0.x; qreg[u][1] = q0.y; qreg[u][2] = q0.z; qreg[u][3] = q0.w;
-            qreg[u][4] = q1.x; qreg[u][5] = q1.y; qreg[u][6] = q1.z; qreg[u][7] = q1.w;
+        for (int sl = 0; sl < 3; sl++) {
+            const float* pp = s_z + (r + sl) * TILE_LDP + sl * N + n;
+            lg[sl] = ((pp[0] + pp[24 * TILE_LDP]) + pp[2 * 24 * TILE_LDP]) + pp[3 * 24 * TILE_LDP];
         }
-        for (int l = 0; l < nr + 2; l++) {
-            const int t = r0 - 1 + l;
-            if (t < 0 || t >= T) continue;                     // warp-uniform
-            const float4 x0 = *reinterpret_cast<const float4*>(s_x + l * LDZ + lane * 4);
-            const float4 x1 = *reinterpret_cast<const float4*>(s_x + l * LDZ + 128 + lane * 4);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                float a = x0.x * qreg[u][0];
-                a = fmaf(x0.y, qreg[u][1], a); a = fmaf(x0.z, qreg[u][2], a); a = fmaf(x0.w, qreg[u][3], a);
-                a = fmaf(x1.x, qreg[u][4], a); a = fmaf(x1.y, qreg[u][5], a); a = fmaf(x1.z, qreg[u][6], a); a = fmaf(x1.w, qreg[u][7], a);
-                a = warp_sum(a);
-                const int j = warp * 4 + u, sl = j / N, r = l - sl;   // row l feeds output row r = l - slot
-                if (lane == 0 && j < NQ && r >= 0 && r < nr) s_p[r * 32 + j] = a;
-            }
-        }
+        const float l1 = lg[1], l0 = v0 ? lg[0] : -INFINITY, l2 = v2 ? lg[2] : -INFINITY;
+        const float mx = fmaxf(l1, fmaxf(l0, l2));
+        const float e0 = v0 ? expf(l0 - mx) : 0.f, e1 = expf(l1 - mx), e2 = v2 ? expf(l2 - mx) : 0.f;
+        const float inv = 1.0f / (e0 + e1 + e2);
+        s_p[i * 3 + 0] = e0 * inv; s_p[i * 3 + 1] = e1 * inv; s_p[i * 3 + 2] = e2 * inv;
     }
     __syncthreads();
-    for (int r = tid; r < nr; r += 256) {
-        const int t = r0 + r;
-        const bool v0 = t > 0, v2 = t < T - 1;
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-        for (int n = 0; n < N; n++) {
-            const float l1 = s_p[r * 32 + N + n];
-            const float l0 = v0 ? s_p[r * 32 + n] : -INFINITY;
-            const float l2 = v2 ? s_p[r * 32 + 2 * N + n] : -INFINITY;
-            const float mx = fmaxf(l1, fmaxf(l0, l2));
-            const float e0 = v0 ? expf(l0 - mx) : 0.f, e1 = expf(l1 - mx), e2 = v2 ? expf(l2 - mx) : 0.f;
-            const float inv = 1.0f / (e0 + e1 + e2);
-            const float w = wk[n];
-            c0 = fmaf(w, e0 * inv, c0); c1 = fmaf(w, e1 * inv, c1); c2 = fmaf(w, e2 * inv, c2);
-        }
-        s_c[r * 4 + 0] = c0; s_c[r * 4 + 1] = c1; s_c[r * 4 + 2] = c2;
+    for (int i = tid; i < nr * 3; i += 256) {     // c[r][slot] = sum_n wk[n] a[r][n][slot], fixed order
+        const int r = i / 3, sl = i % 3;
+        float c = 0.f;
+        for (int n = 0; n < N; n++) c = fmaf(wk[n], s_p[(r * N + n) * 3 + sl], c);
+        s_c[r * 4 + sl] = c;
     }
     __syncthreads();
     for (int r = warp; r < nr; r += 8) {

@@ -30,6 +30,9 @@ int idb_destroy(idb_handle* h);
 const char* idb_last_error(const idb_handle* h);
 long long idb_launch_count(const idb_handle* h);  /* kernels launched so far through h */
 int idb_set_gemm_backend(idb_handle* h, int backend); /* 0 = fp32 SIMT (debug/bisect), 1 = tcgen05 split-fp16 (default) */
+/* Programmatic dependent launch between the kernels of a sampling step (default 1). Results are identical
+   either way; 0 serialises the kernels (for bisecting / profiling). */
+int idb_set_dependent_launch(idb_handle* h, int on);
 
 /* ---- denoiser: MDM.forward / MDM._decode --------------------------------------------------
  * replaces model/diffusion_smpl.py:239-246,226-237 (variant 0) and

@@ -48,6 +48,16 @@ extern "C" int idb_set_gemm_backend(idb_handle* h, int backend) {
     return IDB_OK;
 }
 
+// Programmatic dependent launch between the kernels of a step (default on).  Changing it drops the
+// captured step graphs so the next idb_p_sample_loop re-captures with the new launch attributes.
+void idb_sampler_drop_graphs(idb_handle* h);
+extern "C" int idb_set_dependent_launch(idb_handle* h, int on) {
+    if (!h) return IDB_ERR_ARG;
+    h->pdl = on ? 1 : 0;
+    idb_sampler_drop_graphs(h);
+    return IDB_OK;
+}
+
 extern "C" int idb_debug_gemm(idb_handle* h, const float* A, const float* W, const float* bias, const float* res, float* C,
                               int M, int N, int K, int epi, void* stream) {
     if (!h || !A || !W || !C) return IDB_ERR_ARG;

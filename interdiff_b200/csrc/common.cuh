@@ -8,6 +8,7 @@
 #include <cmath>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/interdiff_b200.h"
@@ -63,6 +64,7 @@ struct Denoiser {
     float *w_outT = nullptr, *b_out = nullptr;    // [D][Clin] k-major output heads
     float *pe = nullptr; int pe_rows = 0;         // sinusoid table [rows][D]
     float *te_w0T = nullptr, *te_b0 = nullptr, *te_w2T = nullptr, *te_b2 = nullptr;
+    float *temb_tab = nullptr;                    // [pe_rows][D]: timestep MLP of every table row + b_in
     // bound problem
     int B = 0, T = 0, M = 0, Tm = 0;
     float *cond = nullptr, *zero_pose = nullptr;
@@ -94,6 +96,7 @@ struct idb_handle {
     int device = 0, sm_count = 148;
     long long launches = 0;   // kernels launched through this handle (bench's gpu_launches)
     int gemm_backend = 1;     // 0 = fp32 SIMT (debug / bisect), 1 = tcgen05 split-fp16 (default)
+    int pdl = 1;              // programmatic dependent launch between the kernels of a sampling step
     void* scratch = nullptr; size_t scratch_bytes = 0;   // on-the-fly operand splits of idb_gemm
     Denoiser den;
     Diffusion diff;
@@ -140,6 +143,25 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+// Programmatic dependent launch: every kernel of the sampling step releases its successor at once
+// (pdl_trigger) and blocks (pdl_wait) before its first access to data produced by earlier kernels, so
+// the successor's launch latency, barrier/TMEM setup and constant-weight prefetch overlap the
+// predecessor's tail.  Both are no-ops for launches without the attribute.  Every kernel in the
+// chain executes pdl_wait, which makes completion transitive along the stream.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t idb_launch(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -160,6 +182,7 @@ struct GemmArgs {
     const float* bias = nullptr; const float* res = nullptr; int ldr = 0;
     float* C = nullptr; __half* C_hi = nullptr; __half* C_lo = nullptr; int ldc = 0;
     int M = 0, N = 0, K = 0, epi = 0;
+    int pdl = 0;   // 1: programmatic dependent launch; REQUIRES W_hi/W_lo to be complete before the previous kernel started
 };
 int idb_gemm_ex(idb_handle* h, const GemmArgs& g, cudaStream_t st);
 // x[rows][cols] (row stride ld_src) -> fp16 pairs [rows][ld_dst] (columns >= cols zero-filled)

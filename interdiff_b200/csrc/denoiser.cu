@@ -37,14 +37,17 @@ __global__ void k_fold_scale(float* __restrict__ kp, const float* __restrict__ k
 
 // One block per step: t_dev[b] = tbl[counter].t for this step, step_cur = counter, counter -= 1.
 __global__ void k_step_begin(long long* t_dev, const StepParams* tbl, int* counter, int* step_cur, int B) {
+    pdl_trigger();
+    pdl_wait();
     const int c = *counter;
     for (int i = threadIdx.x; i < B; i += blockDim.x) t_dev[i] = tbl[c].t;
     __syncthreads();
     if (threadIdx.x == 0) { *step_cur = c; *counter = c - 1; }
 }
 
-// TimestepEmbedder.forward (model/layers.py:42-43): pe[t] -> Linear -> SiLU -> Linear, then the
-// per-token addend of the input embedding: add[b*T+t][:] = temb[b] + pe[t] + b_in   (grid B, block 256)
+// TimestepEmbedder.forward (model/layers.py:42-43): pe[t] -> Linear -> SiLU -> Linear is a pure function
+// of the integer timestep, so it is tabulated once at commit for every row of the sinusoid table:
+// tab[t][:] = MLP(pe[t]) + b_in  (grid pe_rows, block 256).  The sampling step only gathers from it.
 // Thread (cg = tid & 63, kg = tid >> 6) accumulates columns 4cg..4cg+3 over k in [64kg, 64kg+64):
 // float4 weight loads, 1 KB contiguous per k across the 64 column groups, 16 loads in flight.
 __device__ __forceinline__ float4 mlp_partial(const float* __restrict__ wT, const float* __restrict__ s_x, int cg, int kg) {
@@ -59,16 +62,13 @@ __device__ __forceinline__ float4 mlp_partial(const float* __restrict__ wT, cons
     return a;
 }
 __global__ void __launch_bounds__(256)
-k_temb_addend(const float* __restrict__ pe, const long long* __restrict__ t, const float* __restrict__ w0T,
-              const float* __restrict__ b0, const float* __restrict__ w2T, const float* __restrict__ b2,
-              const float* __restrict__ b_in, float* __restrict__ add, int pe_rows, int T) {
-    __shared__ float s_in[D], s_h[D], s_o[D];
+k_temb_table(const float* __restrict__ pe, const float* __restrict__ w0T, const float* __restrict__ b0,
+             const float* __restrict__ w2T, const float* __restrict__ b2, const float* __restrict__ b_in,
+             float* __restrict__ tab) {
+    __shared__ float s_in[D], s_h[D];
     __shared__ float4 s_part[4][64];
-    const int b = blockIdx.x, n = threadIdx.x, cg = n & 63, kg = n >> 6;
-    long long ti = t[b];
-    if (ti < 0) ti = 0;
-    if (ti >= pe_rows) ti = pe_rows - 1;
-    s_in[n] = pe[(size_t)ti * D + n];
+    const int row = blockIdx.x, n = threadIdx.x, cg = n & 63, kg = n >> 6;
+    s_in[n] = pe[(size_t)row * D + n];
     __syncthreads();
     s_part[kg][cg] = mlp_partial(w0T, s_in, cg, kg);
     __syncthreads();
@@ -81,21 +81,19 @@ k_temb_addend(const float* __restrict__ pe, const long long* __restrict__ t, con
     __syncthreads();
     {
         const float* p = reinterpret_cast<const float*>(s_part);
-        s_o[n] = (((p[n] + p[256 + n]) + (p[512 + n] + p[768 + n])) + b2[n]) + b_in[n];
-    }
-    __syncthreads();
-    for (int i = n; i < T * (D / 4); i += 256) {
-        const int tt = i / (D / 4), c = i % (D / 4);
-        const float4 p4 = reinterpret_cast<const float4*>(pe + (size_t)tt * D)[c];
-        const float4 o4 = reinterpret_cast<const float4*>(s_o)[c];
-        reinterpret_cast<float4*>(add + ((size_t)b * T + tt) * D)[c] = make_float4(o4.x + p4.x, o4.y + p4.y, o4.z + p4.z, o4.w + p4.w);
+        tab[(size_t)row * D + n] = (((p[n] + p[256 + n]) + (p[512 + n] + p[768 + n])) + b2[n]) + b_in[n];
     }
 }
 
-// (B,1,C,T) -> token-major [B*T][C] through a shared-memory transpose (grid B)
-__global__ void k_to_tokens(const float* __restrict__ x, __half* __restrict__ xtok, __half* __restrict__ xtok_s, int C, int Cp, int T) {
+// (B,1,C,T) -> token-major [B*T][Cp] fp16 pairs through a shared-memory transpose, plus the per-token
+// addend of the input embedding: add[b*T+t][:] = (temb(t_b) + b_in) + pe[t]      (grid B, block 256)
+__global__ void k_to_tokens(const float* __restrict__ x, __half* __restrict__ xtok, __half* __restrict__ xtok_s, int C, int Cp, int T,
+                            const long long* __restrict__ tstep, const float* __restrict__ tab, const float* __restrict__ pe,
+                            float* __restrict__ add, int pe_rows) {
     extern __shared__ float sx[];   // [C][T+1]
     const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
 #pragma unroll 8
     for (int i = threadIdx.x; i < C * T; i += blockDim.x) sx[(i / T) * (T + 1) + i % T] = __ldg(x + (size_t)b * C * T + i);
     __syncthreads();
@@ -104,6 +102,16 @@ __global__ void k_to_tokens(const float* __restrict__ x, __half* __restrict__ xt
         const int t = i / Cp, c = i % Cp;
         // (hi, lo) fp16 pair for the embedding GEMM; zero padding columns
         split_f16(c < C ? sx[c * (T + 1) + t] : 0.f, xtok[((size_t)b * T + t) * Cp + c], xtok_s[((size_t)b * T + t) * Cp + c]);
+    }
+    long long ti = tstep[b];
+    if (ti < 0) ti = 0;
+    if (ti >= pe_rows) ti = pe_rows - 1;
+    const float4* trow = reinterpret_cast<const float4*>(tab + (size_t)ti * D);
+    for (int i = threadIdx.x; i < T * (D / 4); i += blockDim.x) {
+        const int tt = i / (D / 4), c = i % (D / 4);
+        const float4 p4 = reinterpret_cast<const float4*>(pe + (size_t)tt * D)[c];
+        const float4 o4 = trow[c];
+        reinterpret_cast<float4*>(add + ((size_t)b * T + tt) * D)[c] = make_float4(o4.x + p4.x, o4.y + p4.y, o4.z + p4.z, o4.w + p4.w);
     }
 }
 
@@ -122,6 +130,8 @@ __device__ __forceinline__ void store_pairs(const float4& o0, const float4& o1, 
 __global__ void k_ln(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bb,
                      float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s, int M) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
     if (warp >= M) return;
     const float4* pa = reinterpret_cast<const float4*>(a + (size_t)warp * D);
     float v[8];
@@ -209,6 +219,8 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
     float* s_z = s_a + SLAB * HT;          // [SLAB][LDZ]   residual rows, then the pre-LayerNorm sums
     float* s_v = s_z + SLAB * LDZ;         // [H*Tk][D]     folded values
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     for (int i = tid; i < nr * (D / 4); i += 256) {
         const int r = i / (D / 4), c = i % (D / 4);
         cp_async16(s_q + r * LDZ + c * 4, q + (size_t)(b * T + r0 + r) * ldq + c * 4);
@@ -405,11 +417,13 @@ k_xattn_ln(const float* __restrict__ x1, const float* __restrict__ kp, const flo
     float* s_z = s_a + HT * SLAB;           // [SLAB][LDZ]
     float* s_kc = s_z + SLAB * LDZ;         // [HT]
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
+    pdl_trigger();
+    stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H);     // step-invariant: overlaps the previous kernel
+    pdl_wait();
     for (int i = tid; i < nr * (D / 4); i += 256) {
         const int r = i / (D / 4), c = i % (D / 4);
         cp_async16(s_x1 + r * LDZ + c * 4, x1 + (size_t)(b * T + r0 + r) * D + c * 4);
     }
-    stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H);
     cp_async_wait_all();
     __syncthreads();
     cross_attention_tail(s_x1, s_kp, s_kc, s_v, s_a, s_z, nr, HT, Tk, H, bo, lnw, lnb, out, out_b, out_s, (size_t)b * T + r0);
@@ -445,18 +459,22 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int NQ = 3 * N;
-    // rows r0-1 .. r0+nr (halo of one on each side), local index l = t - (r0 - 1); everything the kernel
-    // reads from global memory is issued here in one asynchronous batch
-    for (int i = tid; i < (nr + 2) * (D / 4); i += 256) {
-        const int l = i / (D / 4), c = i % (D / 4), t = r0 - 1 + l;
-        if (t >= 0 && t < T) cp_async16(s_x + l * LDZ + c * 4, zin + (size_t)(b * T + t) * D + c * 4);
-    }
+    // Everything the kernel reads from global memory is issued up front as asynchronous copies: first the
+    // step-invariant tensors (folded queries, folded memory keys / values), which overlap the previous
+    // kernel's tail under programmatic dependent launch, then - after the dependency wait - the input
+    // rows r0-1 .. r0+nr (halo of one on each side), local index l = t - (r0 - 1).
+    pdl_trigger();
     for (int i = tid; i < 32 * (D / 4); i += 256) {
         const int r = i / (D / 4), c = i % (D / 4);
         if (r < NQ) cp_async16(s_qt + r * LDZ + c * 4, qt + (size_t)r * D + c * 4);
         else *reinterpret_cast<float4*>(s_qt + r * LDZ + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H);
+    pdl_wait();
+    for (int i = tid; i < (nr + 2) * (D / 4); i += 256) {
+        const int l = i / (D / 4), c = i % (D / 4), t = r0 - 1 + l;
+        if (t >= 0 && t < T) cp_async16(s_x + l * LDZ + c * 4, zin + (size_t)(b * T + t) * D + c * 4);
+    }
     cp_async_wait_all();
     __syncthreads();
     if (prew) {   // the previous layer's pending LayerNorm3, in place on the staged rows
@@ -544,6 +562,8 @@ __global__ void k_heads_post(const float* __restrict__ lin, const float* __restr
                              int T, int Clin, int C, int variant, int c_body, int n_points) {
     extern __shared__ float so[];   // [T][Clin+1]
     const int b = blockIdx.x, LDS_ = Clin + 1;
+    pdl_trigger();
+    pdl_wait();
     if ((Clin & 3) == 0) {
         const float4* l4 = reinterpret_cast<const float4*>(lin + (size_t)b * T * Clin);
 #pragma unroll 5
@@ -763,6 +783,9 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
         const DevTensor& pe = it->second;
         if (pe.shape.empty() || pe.shape.back() != D) return idb_fail(h, IDB_ERR_STATE, "pe has the wrong shape");
         d.pe = pe.p; d.pe_rows = (int)(pe.numel() / D);
+        d.temb_tab = P.up(std::vector<float>((size_t)d.pe_rows * D, 0.f));
+        k_temb_table<<<d.pe_rows, 256>>>(d.pe, d.te_w0T, d.te_b0, d.te_w2T, d.te_b2, d.b_in, d.temb_tab);
+        LAUNCH_CHECK(h);
     }
     for (int l = 0; l < c.n_layers; l++) {
         DenoiserLayer L;
@@ -947,6 +970,7 @@ static int linear(idb_handle* h, const __half* a_b, const __half* a_s, int lda, 
     GemmArgs g;
     g.A_hi = a_b; g.A_lo = a_s; g.lda = lda; g.W_hi = w_b; g.W_lo = w_s; g.ldw = ldw; g.bias = bias; g.res = res; g.ldr = D;
     g.C = C; g.C_hi = C_b; g.C_lo = C_s; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.epi = epi;
+    g.pdl = h->pdl;   // weights are step-invariant: their tiles may be fetched before the dependency wait
     return idb_gemm_ex(h, g, st);
 }
 
@@ -958,30 +982,31 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
     const dim3 slab_grid(B, (T + SLAB - 1) / SLAB);
     const int ln_blocks = (M * 32 + 255) / 256;
     const DenoiserLayer* pending = nullptr;   // layer whose norm3 has not been applied to d.z yet
+    const bool pdl = h->pdl != 0;
     int rc;
     for (auto& L : d.layers) {
         // ---- first sub-block -> x1 = (d.h2, h2_b, h2_s)
         if (L.qan) {
             const float* in = pending ? d.z : d.h;
             // QaN block + LN1 + cross-attention + LN2 in one kernel: (z | h) -> (d.h2, pairs)
-            k_qan_xattn_ln<<<slab_grid, 256, qan_smem(Tm, H), st>>>(in, pending ? pending->ln3w : nullptr, pending ? pending->ln3b : nullptr,
-                                                                     L.qt, L.wk, L.ln1w, L.ln1b, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc,
-                                                                     L.ln2w, L.ln2b, d.h2, d.h2_b, d.h2_s, T, N, B, Tm, H);
+            idb_launch(pdl, k_qan_xattn_ln, slab_grid, 256, qan_smem(Tm, H), st, in, pending ? pending->ln3w : nullptr,
+                       pending ? pending->ln3b : nullptr, L.qt, L.wk, L.ln1w, L.ln1b, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc,
+                       L.ln2w, L.ln2b, d.h2, d.h2_b, d.h2_s, T, N, B, Tm, H);
             LAUNCH_CHECK(h);
         } else {
             if (pending) {
-                k_ln<<<ln_blocks, 256, 0, st>>>(d.z, pending->ln3w, pending->ln3b, d.h, d.h_b, d.h_s, M);
+                idb_launch(pdl, k_ln, ln_blocks, 256, 0, st, d.z, pending->ln3w, pending->ln3b, d.h, d.h_b, d.h_s, M);
                 LAUNCH_CHECK(h);
             }
             const int NQ = 2 * D + H * D;
             if ((rc = linear(h, d.h_b, d.h_s, D, L.w_qkvf_b, L.w_qkvf_s, D, L.b_qkvf, nullptr, d.qkv, nullptr, nullptr, NQ, M, NQ, D,
                              EPI_BIAS, st))) return rc;
-            k_attn_ln<<<slab_grid, 256, attn_smem(T, H), st>>>(d.qkv, NQ, d.qkv + D, NQ, d.qkv + 2 * D, NQ, T, 1, d.h, L.bo_f,
-                                                               L.ln1w, L.ln1b, d.qc, nullptr, nullptr, T, T, H);
+            idb_launch(pdl, k_attn_ln, slab_grid, 256, attn_smem(T, H), st, d.qkv, NQ, d.qkv + D, NQ, d.qkv + 2 * D, NQ, T, 1, d.h,
+                       L.bo_f, L.ln1w, L.ln1b, d.qc, nullptr, nullptr, T, T, H);
             LAUNCH_CHECK(h);
             // cross attention on the LN1 rows (d.qc) -> (d.h2, pairs)
-            k_xattn_ln<<<slab_grid, 256, xattn_tail_smem(Tm, H), st>>>(d.qc, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc, L.ln2w, L.ln2b,
-                                                                        d.h2, d.h2_b, d.h2_s, T, B, Tm, H);
+            idb_launch(pdl, k_xattn_ln, slab_grid, 256, xattn_tail_smem(Tm, H), st, d.qc, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc,
+                       L.ln2w, L.ln2b, d.h2, d.h2_b, d.h2_s, T, B, Tm, H);
             LAUNCH_CHECK(h);
         }
         // ---- feed forward on x2 = d.h2: ff = gelu(x2 W1^T + b1) kept as pairs only; z = ff W2^T + b2 + x2  (pre-norm3)
@@ -993,7 +1018,7 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
         // <= 1 ulp of max(|x|,|tgt|) and is not reproduced (DESIGN.md "Deviations").
         pending = &L;
     }
-    k_ln<<<ln_blocks, 256, 0, st>>>(d.z, pending->ln3w, pending->ln3b, d.h, d.h_b, d.h_s, M);
+    idb_launch(pdl, k_ln, ln_blocks, 256, 0, st, d.z, pending->ln3w, pending->ln3b, d.h, d.h_b, d.h_s, M);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }
@@ -1007,10 +1032,11 @@ int idb_denoiser_run(idb_handle* h, const float* x, const long long* t_dev, cons
     const int B = d.B, T = d.T, M = d.M, C = c.c_body + c.c_obj + c.c_extra;
     const int Clin = c.c_body + (c.variant == 0 ? c.c_obj : 7);
     int rc;
-    k_temb_addend<<<B, D, 0, st>>>(d.pe, t_dev, d.te_w0T, d.te_b0, d.te_w2T, d.te_b2, d.b_in, d.addend, d.pe_rows, T);
-    LAUNCH_CHECK(h);
+    const bool pdl = h->pdl != 0;
     const int Cp = (C + 7) & ~7;
-    k_to_tokens<<<B, 256, sizeof(float) * (size_t)C * (T + 1), st>>>(x, d.xtok_b, d.xtok_s, C, Cp, T);
+    // tokens (fp16 pairs) + embedding addend (timestep-MLP table row + positional row)
+    idb_launch(pdl, k_to_tokens, B, 256, sizeof(float) * (size_t)C * (T + 1), st, x, d.xtok_b, d.xtok_s, C, Cp, T, t_dev, d.temb_tab,
+               d.pe, d.addend, d.pe_rows);
     LAUNCH_CHECK(h);
     // input embedding (model/diffusion_smpl.py:227-232): h = xtok W_in^T + (b_in + temb + pe)
     if ((rc = linear(h, d.xtok_b, d.xtok_s, Cp, d.w_in_b, d.w_in_s, Cp, nullptr, d.addend, d.h, d.h_b, d.h_s, D, M, D, Cp, EPI_RES, st)))
@@ -1019,8 +1045,8 @@ int idb_denoiser_run(idb_handle* h, const float* x, const long long* t_dev, cons
     // output heads (model/diffusion_smpl.py:234-237)
     if ((rc = linear(h, d.h_b, d.h_s, D, d.w_out_b, d.w_out_s, D, d.b_out, nullptr, d.lin, nullptr, nullptr, Clin, M, Clin, D, EPI_BIAS, st)))
         return rc;
-    k_heads_post<<<B, 256, sizeof(float) * (size_t)T * (Clin + 1), st>>>(d.lin, d.zero_pose, gt, mask, out, T, Clin, C, c.variant,
-                                                                          c.c_body, c.n_points);
+    idb_launch(pdl, k_heads_post, B, 256, sizeof(float) * (size_t)T * (Clin + 1), st, d.lin, d.zero_pose, gt, mask, out, T, Clin, C,
+               c.variant, c.c_body, c.n_points);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }
@@ -1038,7 +1064,7 @@ int idb_denoiser_prepare_kernels(idb_handle* h) {
 // first kernel of a sampling step: publishes the step's timesteps and advances the device counter
 int idb_denoiser_step_begin(idb_handle* h, cudaStream_t st) {
     Denoiser& d = h->den;
-    k_step_begin<<<1, 128, 0, st>>>(d.t_dev, h->diff.tbl, h->diff.counter, d.step_cur, d.B);
+    idb_launch(h->pdl != 0, k_step_begin, 1, 128, 0, st, d.t_dev, h->diff.tbl, h->diff.counter, d.step_cur, d.B);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }

@@ -182,6 +182,7 @@ int idb_gemm_ex(idb_handle* h, const GemmArgs& g_in, cudaStream_t st) {
             __half* hi = p; __half* lo = p + (size_t)N * Kp;
             if ((rc = idb_split_tensor(h, g.W, g.ldw, hi, lo, Kp, N, K, st))) return rc;
             g.W_hi = hi; g.W_lo = lo; g.ldw = Kp;
+            g.pdl = 0;   // the weight pairs were produced just now on this stream: no early tile fetch
         }
         if (idb_gemm_tcgen05_supported(g)) return idb_gemm_tcgen05(h, g, st);
     }

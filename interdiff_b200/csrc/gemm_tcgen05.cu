@@ -122,6 +122,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     long long* tr = trace ? trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
 #define TRACE(slot) do { if (tr) tr[slot] = clock64(); } while (0)
     if (threadIdx.x == 0) TRACE(0);
+    pdl_trigger();   // the next kernel may start its own prologue now (it blocks in pdl_wait before touching our output)
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B swizzle atoms
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -162,9 +163,31 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        for (int kb = 0; kb < num_kb; kb++) {
+        // The weight tiles of the first pipeline fill do not depend on the previous kernel: they are
+        // requested before the dependency wait (programmatic dependent launch), the activation tiles after.
+        const int npre = num_kb < cfg::STAGES ? num_kb : cfg::STAGES;
+        if (elect_one()) {
+            for (int kb = 0; kb < npre; kb++) {
+                const uint32_t dst = base + kb * cfg::STAGE_BYTES;
+                mbar_arrive_expect_tx(bar_full(kb), cfg::STAGE_BYTES);
+                tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(kb), kb * BK, n0);
+                tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(kb), kb * BK, n0);
+            }
+        }
+        __syncwarp();
+        pdl_wait();
+        if (elect_one()) {
+            for (int kb = 0; kb < npre; kb++) {
+                const uint32_t dst = base + kb * cfg::STAGE_BYTES;
+                tma_load_2d(dst, &map_a, bar_full(kb), kb * BK, m0);
+                tma_load_2d(dst + cfg::HALF_BYTES, &map_al, bar_full(kb), kb * BK, m0);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) TRACE(2);
+        for (int kb = npre; kb < num_kb; kb++) {
             const int s = kb % cfg::STAGES, round = kb / cfg::STAGES;
-            if (round > 0) mbar_wait(bar_empty(s), (round - 1) & 1);
+            mbar_wait(bar_empty(s), (round - 1) & 1);
             const uint32_t dst = base + s * cfg::STAGE_BYTES;
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full(s), cfg::STAGE_BYTES);
@@ -174,7 +197,6 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(s), kb * BK, n0);
             }
             __syncwarp();
-            if (kb == 0 && lane == 0) TRACE(2);
         }
         if (lane == 0) TRACE(3);
     } else if (warp == 1) {
@@ -214,6 +236,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // the accumulators, bias, activation) -> padded smem tile (row per lane) -> read back 4 rows x 128 B
         // per instruction so the residual reads and the C stores are fully coalesced.
         const int ct = threadIdx.x - 64;
+        pdl_wait();      // bias / residual reads and the C stores below touch buffers of earlier kernels
         mbar_wait(bar_acc, 0);
         tc_fence_after();
         if (ct == 0) TRACE(9);
@@ -373,12 +396,12 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
     if (g_idb_gemm_nacc > 0 && g_idb_gemm_nacc < nacc) nacc = g_idb_gemm_nacc;
     if (wide) {
         dim3 grid((N + 127) / 128, (M + BM - 1) / BM);
-        gemm_split_f16_kernel<128><<<grid, NUM_THREADS, Cfg<128>::SMEM_BYTES, st>>>(ma, mw, mal, mwl, g.bias, g.res, g.ldr, g.C, g.C_hi, g.C_lo,
-                                                                                     g.ldc, M, N, K, g.epi, nacc, trace);
+        idb_launch(g.pdl != 0, gemm_split_f16_kernel<128>, grid, NUM_THREADS, Cfg<128>::SMEM_BYTES, st, ma, mw, mal, mwl, g.bias, g.res, g.ldr,
+                   g.C, g.C_hi, g.C_lo, g.ldc, M, N, K, g.epi, nacc, trace);
     } else {
         dim3 grid((N + 63) / 64, (M + BM - 1) / BM);
-        gemm_split_f16_kernel<64><<<grid, NUM_THREADS, Cfg<64>::SMEM_BYTES, st>>>(ma, mw, mal, mwl, g.bias, g.res, g.ldr, g.C, g.C_hi, g.C_lo,
-                                                                                   g.ldc, M, N, K, g.epi, nacc, trace);
+        idb_launch(g.pdl != 0, gemm_split_f16_kernel<64>, grid, NUM_THREADS, Cfg<64>::SMEM_BYTES, st, ma, mw, mal, mwl, g.bias, g.res, g.ldr,
+                   g.C, g.C_hi, g.C_lo, g.ldc, M, N, K, g.epi, nacc, trace);
     }
     LAUNCH_CHECK(h);
     return IDB_OK;

@@ -31,6 +31,8 @@ __global__ void k_set_counter(int* counter, int v) { *counter = v; }
 __global__ void k_posterior(const float* __restrict__ x0, const float* xt, const float* __restrict__ noise,
                             const StepParams* __restrict__ tbl, const int* __restrict__ counter, int n_steps,
                             int tape_mode, float* out, size_t numel) {
+    pdl_trigger();
+    pdl_wait();
     const int i = *counter;
     const StepParams p = tbl[i];
     const float* nz = tape_mode ? noise + (size_t)(n_steps - i) * numel : noise;
@@ -117,7 +119,7 @@ static int finish_dev(idb_handle* h, const float* x0, const float* x_t, const fl
     const size_t n = sample_numel(h);
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_posterior<<<blocks, 256, 0, st>>>(x0, x_t, noise, h->diff.tbl, h->den.step_cur, h->diff.n, tape_mode, out, n);
+    idb_launch(h->pdl != 0, k_posterior, blocks, 256, 0, st, x0, x_t, noise, h->diff.tbl, h->den.step_cur, h->diff.n, tape_mode, out, n);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }
@@ -224,6 +226,13 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
     }
     CUDA_TRY(h, cudaMemcpyAsync(x_out, s.x_a, numel * sizeof(float), cudaMemcpyDefault, st));
     return IDB_OK;
+}
+
+void idb_sampler_drop_graphs(idb_handle* h) {
+    if (!h->sampler) return;
+    Sampler& s = *h->sampler;
+    if (s.step_graph) { cudaGraphExecDestroy(s.step_graph); s.step_graph = nullptr; }
+    if (s.predict_graph) { cudaGraphExecDestroy(s.predict_graph); s.predict_graph = nullptr; }
 }
 
 void idb_sampler_release(idb_handle* h) {

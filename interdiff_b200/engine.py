@@ -81,6 +81,10 @@ class Engine:
     def launch_count(self):
         return int(self.lib.idb_launch_count(self._h))
 
+    def set_dependent_launch(self, on):
+        """Programmatic dependent launch between the kernels of a step (default on; identical results)."""
+        self._chk(self.lib.idb_set_dependent_launch(self._h, 1 if on else 0))
+
     def set_gemm_backend(self, backend):
         self._chk(self.lib.idb_set_gemm_backend(self._h, {"simt": 0, "tcgen05": 1}.get(backend, backend)))
 

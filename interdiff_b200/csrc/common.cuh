@@ -75,8 +75,8 @@ struct Denoiser {
     __half *h_b = nullptr, *h_s = nullptr, *h2_b = nullptr, *h2_s = nullptr, *ff_b = nullptr, *ff_s = nullptr, *xtok_b = nullptr,
            *xtok_s = nullptr;
     std::vector<void*> bound_h;
-    int* step_cur = nullptr;
-    long long* t_dev = nullptr;
+    int* step_cur = nullptr;      // device: diffusion step index i of the step in flight (moved by the step's last kernel)
+    int* ticket = nullptr;        // device: block counter of that last kernel
     std::vector<float*> bound;              // workspaces to free on rebind
 };
 
@@ -84,7 +84,6 @@ struct Diffusion {
     int n = 0;
     std::vector<StepParams> host;
     StepParams* tbl = nullptr;
-    int* counter = nullptr;   // device: current step index i
 };
 
 struct BodyModel;     // lbs.cu

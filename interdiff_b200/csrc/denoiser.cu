@@ -35,16 +35,6 @@ __global__ void k_fold_scale(float* __restrict__ kp, const float* __restrict__ k
     if (lane == 0) kc[(size_t)row * H + hh] = a * 0.125f;
 }
 
-// One block per step: t_dev[b] = tbl[counter].t for this step, step_cur = counter, counter -= 1.
-__global__ void k_step_begin(long long* t_dev, const StepParams* tbl, int* counter, int* step_cur, int B) {
-    pdl_trigger();
-    pdl_wait();
-    const int c = *counter;
-    for (int i = threadIdx.x; i < B; i += blockDim.x) t_dev[i] = tbl[c].t;
-    __syncthreads();
-    if (threadIdx.x == 0) { *step_cur = c; *counter = c - 1; }
-}
-
 // TimestepEmbedder.forward (model/layers.py:42-43): pe[t] -> Linear -> SiLU -> Linear is a pure function
 // of the integer timestep, so it is tabulated once at commit for every row of the sinusoid table:
 // tab[t][:] = MLP(pe[t]) + b_in  (grid pe_rows, block 256).  The sampling step only gathers from it.
@@ -82,36 +72,6 @@ k_temb_table(const float* __restrict__ pe, const float* __restrict__ w0T, const 
     {
         const float* p = reinterpret_cast<const float*>(s_part);
         tab[(size_t)row * D + n] = (((p[n] + p[256 + n]) + (p[512 + n] + p[768 + n])) + b2[n]) + b_in[n];
-    }
-}
-
-// (B,1,C,T) -> token-major [B*T][Cp] fp16 pairs through a shared-memory transpose, plus the per-token
-// addend of the input embedding: add[b*T+t][:] = (temb(t_b) + b_in) + pe[t]      (grid B, block 256)
-__global__ void k_to_tokens(const float* __restrict__ x, __half* __restrict__ xtok, __half* __restrict__ xtok_s, int C, int Cp, int T,
-                            const long long* __restrict__ tstep, const float* __restrict__ tab, const float* __restrict__ pe,
-                            float* __restrict__ add, int pe_rows) {
-    extern __shared__ float sx[];   // [C][T+1]
-    const int b = blockIdx.x;
-    pdl_trigger();
-    pdl_wait();
-#pragma unroll 8
-    for (int i = threadIdx.x; i < C * T; i += blockDim.x) sx[(i / T) * (T + 1) + i % T] = __ldg(x + (size_t)b * C * T + i);
-    __syncthreads();
-#pragma unroll 4
-    for (int i = threadIdx.x; i < Cp * T; i += blockDim.x) {
-        const int t = i / Cp, c = i % Cp;
-        // (hi, lo) fp16 pair for the embedding GEMM; zero padding columns
-        split_f16(c < C ? sx[c * (T + 1) + t] : 0.f, xtok[((size_t)b * T + t) * Cp + c], xtok_s[((size_t)b * T + t) * Cp + c]);
-    }
-    long long ti = tstep[b];
-    if (ti < 0) ti = 0;
-    if (ti >= pe_rows) ti = pe_rows - 1;
-    const float4* trow = reinterpret_cast<const float4*>(tab + (size_t)ti * D);
-    for (int i = threadIdx.x; i < T * (D / 4); i += blockDim.x) {
-        const int tt = i / (D / 4), c = i % (D / 4);
-        const float4 p4 = reinterpret_cast<const float4*>(pe + (size_t)tt * D)[c];
-        const float4 o4 = trow[c];
-        reinterpret_cast<float4*>(add + ((size_t)b * T + tt) * D)[c] = make_float4(o4.x + p4.x, o4.y + p4.y, o4.z + p4.z, o4.w + p4.w);
     }
 }
 
@@ -554,53 +514,144 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     cross_attention_tail(s_x1, s_kp, s_kc, s_v, s_a, s_z, nr, HT, Tk, H, bo2, ln2w, ln2b, out, out_b, out_s, (size_t)b * T + r0);
 }
 
-// Linear outputs lin[(b*T+t)][Clin] -> x0 (B,1,C,T) with the skeleton's keypoint re-derivation and
-// the inpainting blend (model/diffusion_smpl.py:245; model/diffusion_skeleton.py:218-248;
-// diffusion/gaussian_diffusion.py:307-311).  grid B, block 256.
-__global__ void k_heads_post(const float* __restrict__ lin, const float* __restrict__ zero_pose, const float* __restrict__ gt,
-                             const unsigned char* __restrict__ mask, float* __restrict__ out,
-                             int T, int Clin, int C, int variant, int c_body, int n_points) {
-    extern __shared__ float so[];   // [T][Clin+1]
-    const int b = blockIdx.x, LDS_ = Clin + 1;
+// ---------------------------------------------------------------------------------------------
+// Step input / output kernel.  The sample tensors live as (B,1,C,T); the decoder works on token rows
+// [B*T][.].  One kernel covers both ends of a sampling step so a plain step is "decoder GEMMs/attention
+// + ONE tail kernel":
+//   HEADS  (mode & 1): lin[(b*T+t)][Clin] -> x0 (B,1,C,T) with the skeleton's keypoint re-derivation and
+//                      the inpainting blend (model/diffusion_smpl.py:245; model/diffusion_skeleton.py:218-248;
+//                      diffusion/gaussian_diffusion.py:307-311)
+//   FINISH (mode & 2): x_{t-1} = c1[i] x0 + c2[i] x_t + sigma[i] eps   (gaussian_diffusion.py:253-275,537-547),
+//                      then - when emit_next - the NEXT step's token pairs and embedding addend, and the
+//                      device step counter moves to i-1 (last block to finish, so nobody still reads it)
+//   TOKENS (mode == 4): x (B,1,C,T) -> token pairs [B*T][Cp] + addend rows, for the first step of a loop and
+//                      for the stand-alone forward
+// addend[b*T+t][:] = (MLP(pe[t_b]) + b_in) + pe[t]  = table row + positional row (model/diffusion_smpl.py:227-232).
+// grid (B, parts): a block owns a channel range of one sample, all T frames; every global load of the
+// element phase is independent and issued in batches of 5 per thread.
+struct StepIO {
+    // heads
+    const float* lin; const float* zero_pose; const float* gt; const unsigned char* mask; float* x0_out;
+    // finish
+    const float* x0_in; const float* xt; const float* noise; float* x_next;
+    const StepParams* tbl; int* step_cur; int* ticket;
+    int tape_mode, n_steps, emit_next;
+    // tokens
+    const float* x_in; const long long* tstep;
+    __half* xtok_b; __half* xtok_s; const float* tab; const float* pe; float* add;
+    int pe_rows, T, Clin, C, Cp, variant, c_body, n_points;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_step_io(const StepIO a) {
+    extern __shared__ float sm[];
+    const int b = blockIdx.x, part = blockIdx.y, NP = gridDim.y, T = a.T, tid = threadIdx.x;
+    const int ncp = (a.Cp + NP - 1) / NP, c0 = part * ncp, c1 = min(c0 + ncp, a.Cp);   // token columns (incl. zero padding)
+    const int nc = max(min(c1, a.C) - c0, 0);                                            // real channels of this block
+    const int LT = T + 1;
+    float* tile = sm;                 // [ncp][T+1]
+    float* pose = sm + ncp * LT;      // [T][8]  (skeleton: object translation + quaternion per frame)
     pdl_trigger();
     pdl_wait();
-    if ((Clin & 3) == 0) {
-        const float4* l4 = reinterpret_cast<const float4*>(lin + (size_t)b * T * Clin);
-#pragma unroll 5
-        for (int i = threadIdx.x; i < T * Clin / 4; i += blockDim.x) {
-            const float4 q4 = __ldg(l4 + i);
-            const int e = i * 4, r = e / Clin, cc = e % Clin;
-            float* d4 = so + r * LDS_ + cc;
-            d4[0] = q4.x; d4[1] = q4.y; d4[2] = q4.z; d4[3] = q4.w;
+    int i_step = 0;
+    StepParams sp = {};
+    if (MODE & 2) { i_step = *a.step_cur; sp = a.tbl[i_step]; }
+    const int n = nc * T;
+    if (MODE & 1) {
+        // stage the block's linear-head columns, transposed; derived keypoint channels are rebuilt from the pose
+        const float* lrow = a.lin + (size_t)b * T * a.Clin;
+        for (int j = tid; j < n; j += 256) {
+            const int t = j / nc, cc = j % nc, c = c0 + cc;
+            int src = c;
+            if (a.variant != 0 && c >= a.c_body) src = c >= a.c_body + 3 * a.n_points ? c - 3 * a.n_points : -1;
+            if (src >= 0) tile[cc * LT + t] = lrow[(size_t)t * a.Clin + src];
         }
-    } else {
-        for (int i = threadIdx.x; i < T * Clin; i += blockDim.x) so[(i / Clin) * LDS_ + i % Clin] = lin[(size_t)b * T * Clin + i];
+        if (a.variant != 0)
+            for (int j = tid; j < T * 7; j += 256) pose[(j / 7) * 8 + j % 7] = lrow[(size_t)(j / 7) * a.Clin + a.c_body + j % 7];
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
-        const int c = i / T, t = i % T;
-        const float* ro = so + t * LDS_;
-        float val;
-        if (variant == 0 || c < c_body) {
-            val = ro[c];
-        } else if (c >= c_body + 3 * n_points) {
-            val = ro[c - 3 * n_points];
-        } else {
-            // calc_obj_pred: pose = [trans3, quat xyzw]; quaternion_to_matrix on (w,x,y,z), un-normalised
-            const int p = (c - c_body) / 3, ax = (c - c_body) % 3;
-            const float* ps = ro + c_body;
-            const float tx = ps[0], ty = ps[1], tz = ps[2], qi = ps[3], qj = ps[4], qk = ps[5], qr = ps[6];
-            const float two_s = 2.0f / (qr * qr + qi * qi + qj * qj + qk * qk);
-            float r0, r1, r2, tr;
-            if (ax == 0) { r0 = 1 - two_s * (qj * qj + qk * qk); r1 = two_s * (qi * qj - qk * qr); r2 = two_s * (qi * qk + qj * qr); tr = tx; }
-            else if (ax == 1) { r0 = two_s * (qi * qj + qk * qr); r1 = 1 - two_s * (qi * qi + qk * qk); r2 = two_s * (qj * qk - qi * qr); tr = ty; }
-            else { r0 = two_s * (qi * qk - qj * qr); r1 = two_s * (qj * qk + qi * qr); r2 = 1 - two_s * (qi * qi + qj * qj); tr = tz; }
-            const float* zp = zero_pose + ((size_t)b * n_points + p) * 3;
-            val = (r0 * zp[0] + r1 * zp[1] + r2 * zp[2]) + tr;
+    const float* nz = nullptr;
+    if (MODE & 2) nz = a.tape_mode ? a.noise + (size_t)(a.n_steps - i_step) * ((size_t)gridDim.x * a.C * T) : a.noise;
+    constexpr int KM = 5;
+    for (int base = 0; base < n; base += 256 * KM) {
+        float v_in[KM], v_xt[KM], v_nz[KM], v_gt[KM];
+        unsigned char v_m[KM];
+#pragma unroll
+        for (int k = 0; k < KM; k++) {
+            const int e = base + tid + k * 256;
+            v_in[k] = v_xt[k] = v_nz[k] = v_gt[k] = 0.f; v_m[k] = 0;
+            if (e < n) {
+                const size_t o = ((size_t)b * a.C + c0) * T + e;        // (B,1,C,T): the block's channels are contiguous
+                if (MODE == 2) v_in[k] = a.x0_in[o];
+                if (MODE == 4) v_in[k] = a.x_in[o];
+                if (MODE & 2) { v_xt[k] = a.xt[o]; v_nz[k] = nz[o]; }
+                if ((MODE & 1) && a.mask) { v_m[k] = a.mask[o]; v_gt[k] = a.gt[o]; }
+            }
         }
-        const size_t o = (size_t)b * C * T + i;
-        if (mask && mask[o]) val = gt[o];
-        out[o] = val;
+#pragma unroll
+        for (int k = 0; k < KM; k++) {
+            const int e = base + tid + k * 256;
+            if (e >= n) continue;
+            const int cc = e / T, t = e % T, c = c0 + cc;
+            const size_t o = ((size_t)b * a.C + c0) * T + e;
+            float val = v_in[k];
+            if (MODE & 1) {
+                if (a.variant == 0 || c < a.c_body || c >= a.c_body + 3 * a.n_points) {
+                    val = tile[cc * LT + t];
+                } else {
+                    // calc_obj_pred: pose = [trans3, quat xyzw]; quaternion_to_matrix on (w,x,y,z), un-normalised
+                    const int p = (c - a.c_body) / 3, ax = (c - a.c_body) % 3;
+                    const float* ps = pose + t * 8;
+                    const float tx = ps[0], ty = ps[1], tz = ps[2], qi = ps[3], qj = ps[4], qk = ps[5], qr = ps[6];
+                    const float two_s = 2.0f / (qr * qr + qi * qi + qj * qj + qk * qk);
+                    float r0, r1, r2, tr;
+                    if (ax == 0) { r0 = 1 - two_s * (qj * qj + qk * qk); r1 = two_s * (qi * qj - qk * qr); r2 = two_s * (qi * qk + qj * qr); tr = tx; }
+                    else if (ax == 1) { r0 = two_s * (qi * qj + qk * qr); r1 = 1 - two_s * (qi * qi + qk * qk); r2 = two_s * (qj * qk - qi * qr); tr = ty; }
+                    else { r0 = two_s * (qi * qk - qj * qr); r1 = two_s * (qj * qk + qi * qr); r2 = 1 - two_s * (qi * qi + qj * qj); tr = tz; }
+                    const float* zp = a.zero_pose + ((size_t)b * a.n_points + p) * 3;
+                    val = (r0 * zp[0] + r1 * zp[1] + r2 * zp[2]) + tr;
+                }
+                if (v_m[k]) val = v_gt[k];
+                if (a.x0_out) a.x0_out[o] = val;
+            }
+            if (MODE & 2) {
+                const float mean = sp.c1 * val + sp.c2 * v_xt[k];
+                val = mean + sp.sigma_nz * v_nz[k];
+                a.x_next[o] = val;
+            }
+            if (MODE != 1) tile[cc * LT + t] = val;      // tokens of the step that consumes this tensor
+        }
+    }
+    if (MODE == 1) return;
+    const bool emit = MODE == 4 || (a.emit_next && i_step > 0);
+    if (emit) {
+        __syncthreads();
+        const int ncw = c1 - c0;
+        for (int j = tid; j < T * ncw; j += 256) {
+            const int t = j / ncw, cc = j % ncw;
+            const size_t o = ((size_t)b * T + t) * a.Cp + c0 + cc;
+            split_f16(cc < nc ? tile[cc * LT + t] : 0.f, a.xtok_b[o], a.xtok_s[o]);     // (hi, lo) fp16 pair; padding columns zero
+        }
+        long long ti = MODE == 4 ? (a.tstep ? a.tstep[b] : a.tbl[*a.step_cur].t) : a.tbl[i_step - 1].t;
+        if (ti < 0) ti = 0;
+        if (ti >= a.pe_rows) ti = a.pe_rows - 1;
+        const float4* trow = reinterpret_cast<const float4*>(a.tab + (size_t)ti * D);
+        const int nq = T * (D / 4), per = (nq + NP - 1) / NP, q1 = min(nq, (part + 1) * per);
+        for (int i = part * per + tid; i < q1; i += 256) {
+            const int tt = i / (D / 4), c = i % (D / 4);
+            const float4 p4 = reinterpret_cast<const float4*>(a.pe + (size_t)tt * D)[c];
+            const float4 o4 = trow[c];
+            reinterpret_cast<float4*>(a.add + ((size_t)b * T + tt) * D)[c] = make_float4(o4.x + p4.x, o4.y + p4.y, o4.z + p4.z, o4.w + p4.w);
+        }
+    }
+    if ((MODE & 2) && a.emit_next) {
+        // every thread of this block has read step_cur (before the first barrier-free use above it sits in a
+        // register); the last block to get here moves the counter
+        __syncthreads();
+        if (tid == 0) {
+            const int done = atomicAdd(a.ticket, 1);
+            if (done == (int)(gridDim.x * gridDim.y) - 1) { *a.ticket = 0; *a.step_cur = i_step - 1; }
+        }
     }
 }
 
@@ -636,8 +687,7 @@ static void denoiser_free_bound(Denoiser& d) {
     d.bound.clear();
     for (void* p : d.bound_h) cudaFree(p);
     d.bound_h.clear();
-    if (d.t_dev) { cudaFree(d.t_dev); d.t_dev = nullptr; }
-    if (d.step_cur) { cudaFree(d.step_cur); d.step_cur = nullptr; }
+    if (d.step_cur) { cudaFree(d.step_cur); d.step_cur = nullptr; d.ticket = nullptr; }
     d.B = d.T = d.M = 0;
 }
 
@@ -925,8 +975,9 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
             rc |= A(&L.kp_mem, (size_t)Tm * B * H * D); rc |= A(&L.kc_mem, (size_t)Tm * B * H);
         }
         if (rc) return rc;
-        CUDA_TRY(h, cudaMalloc((void**)&d.t_dev, sizeof(long long) * B));
-        CUDA_TRY(h, cudaMalloc((void**)&d.step_cur, sizeof(int)));
+        CUDA_TRY(h, cudaMalloc((void**)&d.step_cur, 2 * sizeof(int)));
+        CUDA_TRY(h, cudaMemset(d.step_cur, 0, 2 * sizeof(int)));
+        d.ticket = d.step_cur + 1;
         d.B = B; d.T = T; d.M = M; d.Tm = Tm;
     }
     CUDA_TRY(h, cudaMemcpyAsync(d.cond, cond, sizeof(float) * (size_t)Tm * B * D, cudaMemcpyDefault, st));
@@ -1023,32 +1074,86 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
     return IDB_OK;
 }
 
-// x (B,1,C,T) -> x0 prediction (B,1,C,T); optional inpainting blend.  t_dev must hold the timesteps.
-int idb_denoiser_run(idb_handle* h, const float* x, const long long* t_dev, const float* gt, const unsigned char* mask,
-                     float* out, cudaStream_t st) {
+static constexpr int STEP_IO_PARTS = 4;
+
+static StepIO step_io_base(idb_handle* h) {
     Denoiser& d = h->den;
-    if (!d.B) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_bind first");
     const idb_denoiser_config& c = d.cfg;
-    const int B = d.B, T = d.T, M = d.M, C = c.c_body + c.c_obj + c.c_extra;
+    StepIO a = {};
+    a.lin = d.lin; a.zero_pose = d.zero_pose;
+    a.tbl = h->diff.tbl; a.step_cur = d.step_cur; a.ticket = d.ticket; a.n_steps = h->diff.n;
+    a.xtok_b = d.xtok_b; a.xtok_s = d.xtok_s; a.tab = d.temb_tab; a.pe = d.pe; a.add = d.addend; a.pe_rows = d.pe_rows;
+    a.T = d.T; a.C = c.c_body + c.c_obj + c.c_extra; a.Cp = (a.C + 7) & ~7;
+    a.Clin = c.c_body + (c.variant == 0 ? c.c_obj : 7);
+    a.variant = c.variant; a.c_body = c.c_body; a.n_points = c.n_points;
+    return a;
+}
+
+template <int MODE>
+static int launch_step_io(idb_handle* h, const StepIO& a, cudaStream_t st) {
+    const int ncp = (a.Cp + STEP_IO_PARTS - 1) / STEP_IO_PARTS;
+    const size_t smem = sizeof(float) * ((size_t)ncp * (a.T + 1) + (size_t)a.T * 8);
+    idb_launch(h->pdl != 0, k_step_io<MODE>, dim3(h->den.B, STEP_IO_PARTS), 256, smem, st, a);
+    LAUNCH_CHECK(h);
+    return IDB_OK;
+}
+
+// x (B,1,C,T) -> token pairs + embedding addend.  tstep: device timesteps (B), or null = the sampler's
+// current step (tbl[step_cur].t).
+int idb_denoiser_tokens(idb_handle* h, const float* x, const long long* tstep, cudaStream_t st) {
+    if (!h->den.B) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_bind first");
+    if (!tstep && !h->diff.tbl) return idb_fail(h, IDB_ERR_STATE, "idb_diffusion_init first");
+    StepIO a = step_io_base(h);
+    a.x_in = x; a.tstep = tstep;
+    return launch_step_io<4>(h, a, st);
+}
+
+// decoder on the prepared tokens: input embedding, 8 layers, output heads -> d.lin [B*T][Clin]
+int idb_denoiser_body(idb_handle* h, cudaStream_t st) {
+    Denoiser& d = h->den;
+    const idb_denoiser_config& c = d.cfg;
+    const int M = d.M, C = c.c_body + c.c_obj + c.c_extra, Cp = (C + 7) & ~7;
     const int Clin = c.c_body + (c.variant == 0 ? c.c_obj : 7);
     int rc;
-    const bool pdl = h->pdl != 0;
-    const int Cp = (C + 7) & ~7;
-    // tokens (fp16 pairs) + embedding addend (timestep-MLP table row + positional row)
-    idb_launch(pdl, k_to_tokens, B, 256, sizeof(float) * (size_t)C * (T + 1), st, x, d.xtok_b, d.xtok_s, C, Cp, T, t_dev, d.temb_tab,
-               d.pe, d.addend, d.pe_rows);
-    LAUNCH_CHECK(h);
     // input embedding (model/diffusion_smpl.py:227-232): h = xtok W_in^T + (b_in + temb + pe)
     if ((rc = linear(h, d.xtok_b, d.xtok_s, Cp, d.w_in_b, d.w_in_s, Cp, nullptr, d.addend, d.h, d.h_b, d.h_s, D, M, D, Cp, EPI_RES, st)))
         return rc;
     if ((rc = denoiser_layers(h, st))) return rc;
     // output heads (model/diffusion_smpl.py:234-237)
-    if ((rc = linear(h, d.h_b, d.h_s, D, d.w_out_b, d.w_out_s, D, d.b_out, nullptr, d.lin, nullptr, nullptr, Clin, M, Clin, D, EPI_BIAS, st)))
-        return rc;
-    idb_launch(pdl, k_heads_post, B, 256, sizeof(float) * (size_t)T * (Clin + 1), st, d.lin, d.zero_pose, gt, mask, out, T, Clin, C,
-               c.variant, c.c_body, c.n_points);
-    LAUNCH_CHECK(h);
-    return IDB_OK;
+    return linear(h, d.h_b, d.h_s, D, d.w_out_b, d.w_out_s, D, d.b_out, nullptr, d.lin, nullptr, nullptr, Clin, M, Clin, D, EPI_BIAS, st);
+}
+
+// d.lin -> x0 (B,1,C,T) with the optional inpainting blend
+int idb_denoiser_heads(idb_handle* h, const float* gt, const unsigned char* mask, float* out, cudaStream_t st) {
+    StepIO a = step_io_base(h);
+    a.gt = gt; a.mask = mask; a.x0_out = out;
+    return launch_step_io<1>(h, a, st);
+}
+
+// posterior sample from a given x0 (after the correction hook, or the stand-alone finish call)
+int idb_step_finish(idb_handle* h, const float* x0, const float* xt, const float* noise, int tape_mode, float* x_next, int emit_next,
+                    cudaStream_t st) {
+    StepIO a = step_io_base(h);
+    a.x0_in = x0; a.xt = xt; a.noise = noise; a.tape_mode = tape_mode; a.x_next = x_next; a.emit_next = emit_next;
+    return launch_step_io<2>(h, a, st);
+}
+
+// heads + posterior sample + next step's tokens in one kernel (the tail of a plain sampling step)
+int idb_step_tail(idb_handle* h, const float* gt, const unsigned char* mask, float* x0_out, const float* xt, const float* noise,
+                  int tape_mode, float* x_next, int emit_next, cudaStream_t st) {
+    StepIO a = step_io_base(h);
+    a.gt = gt; a.mask = mask; a.x0_out = x0_out;
+    a.xt = xt; a.noise = noise; a.tape_mode = tape_mode; a.x_next = x_next; a.emit_next = emit_next;
+    return launch_step_io<3>(h, a, st);
+}
+
+// x (B,1,C,T) -> x0 prediction (B,1,C,T); optional inpainting blend
+int idb_denoiser_run(idb_handle* h, const float* x, const long long* tstep, const float* gt, const unsigned char* mask,
+                     float* out, cudaStream_t st) {
+    int rc;
+    if ((rc = idb_denoiser_tokens(h, x, tstep, st))) return rc;
+    if ((rc = idb_denoiser_body(h, st))) return rc;
+    return idb_denoiser_heads(h, gt, mask, out, st);
 }
 
 int idb_denoiser_prepare_kernels(idb_handle* h) {
@@ -1056,16 +1161,6 @@ int idb_denoiser_prepare_kernels(idb_handle* h) {
     CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem(16, 4)));
     CUDA_TRY(h, cudaFuncSetAttribute(k_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_tail_smem(16, 4)));
     CUDA_TRY(h, cudaFuncSetAttribute(k_attn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(36, 4)));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_to_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_heads_post, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    return IDB_OK;
-}
-
-// first kernel of a sampling step: publishes the step's timesteps and advances the device counter
-int idb_denoiser_step_begin(idb_handle* h, cudaStream_t st) {
-    Denoiser& d = h->den;
-    idb_launch(h->pdl != 0, k_step_begin, 1, 128, 0, st, d.t_dev, h->diff.tbl, h->diff.counter, d.step_cur, d.B);
-    LAUNCH_CHECK(h);
     return IDB_OK;
 }
 

@@ -4,12 +4,18 @@
 // diffusion/respace.py:64-129.
 //
 // Every per-step scalar lives in a device table indexed by a device-side step counter, so one
-// captured CUDA graph of a step can be replayed for every timestep without host patching.
+// captured CUDA graph of a step can be replayed for every timestep without host patching.  The
+// counter is moved by the last kernel of a step (k_step_io, denoiser.cu), which also prepares the
+// next step's decoder input, so a plain step is: decoder body (GEMMs + attention) + one tail kernel.
 #include "common.cuh"
 
-int idb_denoiser_run(idb_handle* h, const float* x, const long long* t_dev, const float* gt, const unsigned char* mask,
-                     float* out, cudaStream_t st);
-int idb_denoiser_step_begin(idb_handle* h, cudaStream_t st);
+int idb_denoiser_tokens(idb_handle* h, const float* x, const long long* tstep, cudaStream_t st);
+int idb_denoiser_body(idb_handle* h, cudaStream_t st);
+int idb_denoiser_heads(idb_handle* h, const float* gt, const unsigned char* mask, float* out, cudaStream_t st);
+int idb_step_finish(idb_handle* h, const float* x0, const float* xt, const float* noise, int tape_mode, float* x_next, int emit_next,
+                    cudaStream_t st);
+int idb_step_tail(idb_handle* h, const float* gt, const unsigned char* mask, float* x0_out, const float* xt, const float* noise,
+                  int tape_mode, float* x_next, int emit_next, cudaStream_t st);
 int idb_correction_apply_dev(idb_handle* h, float* x0, const float* gt, int t, cudaStream_t st);
 
 struct Sampler {
@@ -25,22 +31,6 @@ struct Sampler {
 namespace {
 
 __global__ void k_set_counter(int* counter, int v) { *counter = v; }
-
-// x_{t-1} = c1[i] x0 + c2[i] x_t + 1[i != 0] exp(0.5 logvar[i]) eps   (gaussian_diffusion.py:253-275,537-547)
-// noise pointer: explicit, or tape + (n_steps - i) * numel when tape_mode (eps of the k-th step is tape[k+1]).
-__global__ void k_posterior(const float* __restrict__ x0, const float* xt, const float* __restrict__ noise,
-                            const StepParams* __restrict__ tbl, const int* __restrict__ counter, int n_steps,
-                            int tape_mode, float* out, size_t numel) {
-    pdl_trigger();
-    pdl_wait();
-    const int i = *counter;
-    const StepParams p = tbl[i];
-    const float* nz = tape_mode ? noise + (size_t)(n_steps - i) * numel : noise;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel; e += (size_t)gridDim.x * blockDim.x) {
-        const float mean = p.c1 * x0[e] + p.c2 * xt[e];
-        out[e] = mean + p.sigma_nz * nz[e];
-    }
-}
 
 }  // namespace
 
@@ -74,7 +64,6 @@ extern "C" int idb_diffusion_init(idb_handle* h, const double* betas, const int6
         p.pad = 0.f;
     }
     if (df.tbl) cudaFree(df.tbl);
-    if (!df.counter) CUDA_TRY(h, cudaMalloc((void**)&df.counter, sizeof(int)));
     CUDA_TRY(h, cudaMalloc((void**)&df.tbl, sizeof(StepParams) * n));
     CUDA_TRY(h, cudaMemcpy(df.tbl, df.host.data(), sizeof(StepParams) * n, cudaMemcpyHostToDevice));
     df.n = n;
@@ -108,18 +97,17 @@ static size_t sample_numel(idb_handle* h) {
     return (size_t)h->den.B * (c.c_body + c.c_obj + c.c_extra) * h->den.T;
 }
 
-// predict with the device counter already set
+// predict with the device counter already set: tokens from x_t, decoder, heads
 static int predict_dev(idb_handle* h, const float* x_t, const float* gt, const unsigned char* mask, float* x0, cudaStream_t st) {
-    int rc = idb_denoiser_step_begin(h, st);   // t_dev <- tbl[counter].t, step_cur <- counter, counter -= 1
-    if (rc) return rc;
-    return idb_denoiser_run(h, x_t, h->den.t_dev, gt, mask, x0, st);
+    int rc;
+    if ((rc = idb_denoiser_tokens(h, x_t, nullptr, st))) return rc;
+    if ((rc = idb_denoiser_body(h, st))) return rc;
+    return idb_denoiser_heads(h, gt, mask, x0, st);
 }
 
-static int finish_dev(idb_handle* h, const float* x0, const float* x_t, const float* noise, int tape_mode, float* out, cudaStream_t st) {
-    const size_t n = sample_numel(h);
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    idb_launch(h->pdl != 0, k_posterior, blocks, 256, 0, st, x0, x_t, noise, h->diff.tbl, h->den.step_cur, h->diff.n, tape_mode, out, n);
+static int set_step(idb_handle* h, int i, cudaStream_t st) {
+    if (!h->den.step_cur) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_bind first");
+    k_set_counter<<<1, 1, 0, st>>>(h->den.step_cur, i);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }
@@ -129,8 +117,8 @@ extern "C" int idb_p_sample_predict(idb_handle* h, int i, const float* x_t, cons
     if (i < 0 || i >= h->diff.n) return idb_fail(h, IDB_ERR_ARG, "step index out of range");
     if ((gt == nullptr) != (mask == nullptr)) return idb_fail(h, IDB_ERR_ARG, "gt and mask must be given together");
     cudaStream_t st = (cudaStream_t)stream;
-    k_set_counter<<<1, 1, 0, st>>>(h->diff.counter, i);
-    LAUNCH_CHECK(h);
+    int rc = set_step(h, i, st);
+    if (rc) return rc;
     return predict_dev(h, x_t, gt, mask, x0_out, st);
 }
 
@@ -138,20 +126,22 @@ extern "C" int idb_p_sample_finish(idb_handle* h, int i, const float* x0, const 
     if (!h || !x0 || !x_t || !noise || !x_out) return IDB_ERR_ARG;
     if (i < 0 || i >= h->diff.n) return idb_fail(h, IDB_ERR_ARG, "step index out of range");
     cudaStream_t st = (cudaStream_t)stream;
-    if (!h->den.step_cur) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_bind first");
-    k_set_counter<<<1, 1, 0, st>>>(h->den.step_cur, i);
-    LAUNCH_CHECK(h);
-    return finish_dev(h, x0, x_t, noise, 0, x_out, st);
+    int rc = set_step(h, i, st);
+    if (rc) return rc;
+    return idb_step_finish(h, x0, x_t, noise, 0, x_out, 0, st);
 }
 
 extern "C" int idb_p_sample(idb_handle* h, int i, const float* x_t, const float* noise, const float* gt, const uint8_t* mask,
                             float* x_out, float* x0_out, void* stream) {
     if (!h || !x_t || !noise || !x_out) return IDB_ERR_ARG;
-    int rc = sampler_ready(h, sample_numel(h));
+    if (i < 0 || i >= h->diff.n) return idb_fail(h, IDB_ERR_ARG, "step index out of range");
+    if ((gt == nullptr) != (mask == nullptr)) return idb_fail(h, IDB_ERR_ARG, "gt and mask must be given together");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = set_step(h, i, st);
     if (rc) return rc;
-    float* x0 = x0_out ? x0_out : h->sampler->x0;
-    if ((rc = idb_p_sample_predict(h, i, x_t, gt, mask, x0, stream))) return rc;
-    return finish_dev(h, x0, x_t, noise, 0, x_out, (cudaStream_t)stream);
+    if ((rc = idb_denoiser_tokens(h, x_t, nullptr, st))) return rc;
+    if ((rc = idb_denoiser_body(h, st))) return rc;
+    return idb_step_tail(h, gt, mask, x0_out, x_t, noise, 0, x_out, 0, st);
 }
 
 extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* gt, const uint8_t* mask, int correction,
@@ -170,8 +160,9 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
     // Simpler and just as cheap: the graph always reads x_a and writes x_a (x0 is a separate
     // buffer, and the posterior is elementwise, so in-place is safe).
     CUDA_TRY(h, cudaMemcpyAsync(s.x_a, tape, numel * sizeof(float), cudaMemcpyDefault, st));
-    k_set_counter<<<1, 1, 0, st>>>(df.counter, n - 1);
-    LAUNCH_CHECK(h);
+    if ((rc = set_step(h, n - 1, st))) return rc;
+    // decoder input of the first step; every later step gets its tokens from the previous step's tail
+    if ((rc = idb_denoiser_tokens(h, s.x_a, nullptr, st))) return rc;
 
     const bool graph_ok = use_graph != 0;
     if (graph_ok && (!s.step_graph || s.g_gt != gt || s.g_mask != mask || s.g_tape != tape || s.gB != h->den.B || s.gT != h->den.T)) {
@@ -183,8 +174,8 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
         // full plain step
         long long saved = h->launches;
         CUDA_TRY(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        rc = predict_dev(h, s.x_a, gt, mask, s.x0, cs);
-        if (!rc) rc = finish_dev(h, s.x0, s.x_a, tape, 1, s.x_a, cs);
+        rc = idb_denoiser_body(h, cs);
+        if (!rc) rc = idb_step_tail(h, gt, mask, nullptr, s.x_a, tape, 1, s.x_a, 1, cs);
         cudaError_t ce = cudaStreamEndCapture(cs, &g);
         if (rc || ce != cudaSuccess) { cudaStreamDestroy(cs); return rc ? rc : idb_fail(h, IDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)); }
         s.launches_per_step = (int)(h->launches - saved);
@@ -192,10 +183,11 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
         cudaGraphDestroy(g);
         // predict only
         CUDA_TRY(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        rc = predict_dev(h, s.x_a, gt, mask, s.x0, cs);
+        rc = idb_denoiser_body(h, cs);
+        if (!rc) rc = idb_denoiser_heads(h, gt, mask, s.x0, cs);
         ce = cudaStreamEndCapture(cs, &g);
         if (rc || ce != cudaSuccess) { cudaStreamDestroy(cs); return rc ? rc : idb_fail(h, IDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)); }
-        s.launches_per_predict = s.launches_per_step - 1;
+        s.launches_per_predict = s.launches_per_step;
         CUDA_TRY(h, cudaGraphInstantiate(&s.predict_graph, g, 0));
         cudaGraphDestroy(g);
         cudaStreamDestroy(cs);
@@ -212,16 +204,19 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
                 CUDA_TRY(h, cudaGraphLaunch(s.step_graph, st));
                 h->launches += s.launches_per_step;
             } else {
-                if ((rc = predict_dev(h, s.x_a, gt, mask, s.x0, st))) return rc;
-                if ((rc = finish_dev(h, s.x0, s.x_a, tape, 1, s.x_a, st))) return rc;
+                if ((rc = idb_denoiser_body(h, st))) return rc;
+                if ((rc = idb_step_tail(h, gt, mask, nullptr, s.x_a, tape, 1, s.x_a, 1, st))) return rc;
             }
         } else {
             if (graph_ok) {
                 CUDA_TRY(h, cudaGraphLaunch(s.predict_graph, st));
                 h->launches += s.launches_per_predict;
-            } else if ((rc = predict_dev(h, s.x_a, gt, mask, s.x0, st))) return rc;
+            } else {
+                if ((rc = idb_denoiser_body(h, st))) return rc;
+                if ((rc = idb_denoiser_heads(h, gt, mask, s.x0, st))) return rc;
+            }
             if ((rc = idb_correction_apply_dev(h, s.x0, gt, i, st))) return rc;
-            if ((rc = finish_dev(h, s.x0, s.x_a, tape, 1, s.x_a, st))) return rc;
+            if ((rc = idb_step_finish(h, s.x0, s.x_a, tape, 1, s.x_a, 1, st))) return rc;
         }
     }
     CUDA_TRY(h, cudaMemcpyAsync(x_out, s.x_a, numel * sizeof(float), cudaMemcpyDefault, st));
@@ -245,6 +240,5 @@ void idb_sampler_release(idb_handle* h) {
         h->sampler = nullptr;
     }
     if (h->diff.tbl) cudaFree(h->diff.tbl);
-    if (h->diff.counter) cudaFree(h->diff.counter);
     h->diff = Diffusion();
 }

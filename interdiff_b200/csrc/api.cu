@@ -61,6 +61,14 @@ extern "C" int idb_set_dependent_launch(idb_handle* h, int on) {
 extern "C" int idb_debug_gemm(idb_handle* h, const float* A, const float* W, const float* bias, const float* res, float* C,
                               int M, int N, int K, int epi, void* stream) {
     if (!h || !A || !W || !C) return IDB_ERR_ARG;
+    if (epi & 128) {   /* test hook: split-K = 2 onto a C zeroed here */
+        cudaStream_t st = (cudaStream_t)stream;
+        CUDA_TRY(h, cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+        GemmArgs g;
+        g.A = A; g.lda = K; g.W = W; g.ldw = K; g.bias = bias; g.res = res; g.ldr = N; g.C = C; g.ldc = N;
+        g.M = M; g.N = N; g.K = K; g.epi = epi & ~128; g.ksplit = 2;
+        return idb_gemm_ex(h, g, st);
+    }
     return idb_gemm(h, A, K, W, K, bias, res, N, C, N, M, N, K, epi, (cudaStream_t)stream);
 }
 
@@ -104,7 +112,8 @@ extern "C" int idb_debug_gemm_presplit(idb_handle* h, const void* A_hi, const vo
     if (!h || !A_hi || !A_lo || !W_hi || !W_lo || !C) return IDB_ERR_ARG;
     GemmArgs g;
     g.A_hi = (const __half*)A_hi; g.A_lo = (const __half*)A_lo; g.lda = K; g.W_hi = (const __half*)W_hi; g.W_lo = (const __half*)W_lo; g.ldw = K;
-    g.bias = bias; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K; g.epi = epi | g_idb_trace_epi;
+    g.bias = bias; g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K; g.epi = (epi & ~128) | g_idb_trace_epi;
+    if (epi & 128) g.ksplit = 2;   /* timing only: C is not re-zeroed between launches */
     for (int i = 0; i < iters; i++) {
         if (i == 0 && trace) g_idb_gemm_trace = trace;
         int rc = idb_gemm_ex(h, g, (cudaStream_t)stream);

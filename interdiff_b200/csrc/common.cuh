@@ -181,6 +181,8 @@ struct GemmArgs {
     const float* bias = nullptr; const float* res = nullptr; int ldr = 0;
     float* C = nullptr; __half* C_hi = nullptr; __half* C_lo = nullptr; int ldc = 0;
     int M = 0, N = 0, K = 0, epi = 0;
+    int ksplit = 1;                                     // 2: split-K onto a C zeroed by an earlier kernel (tensor path only)
+    float* zero = nullptr; int zero_ld = 0, zero_cols = 0;   // aux [M][zero_cols] matrix to clear as a side job
     int pdl = 0;   // 1: programmatic dependent launch; REQUIRES W_hi/W_lo to be complete before the previous kernel started
 };
 int idb_gemm_ex(idb_handle* h, const GemmArgs& g, cudaStream_t st);

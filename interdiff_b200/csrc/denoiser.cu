@@ -1017,8 +1017,9 @@ static size_t qan_smem(int Tk, int H) {
 // One nn.Linear on fp16 (hi, lo) operand pairs; output as full fp32 and/or as a pair.
 static int linear(idb_handle* h, const __half* a_b, const __half* a_s, int lda, const __half* w_b, const __half* w_s, int ldw,
                   const float* bias, const float* res, float* C, __half* C_b, __half* C_s, int ldc, int M, int N, int K, int epi,
-                  cudaStream_t st) {
+                  cudaStream_t st, int ksplit = 1, float* zero = nullptr) {
     GemmArgs g;
+    g.ksplit = ksplit; g.zero = zero; g.zero_ld = D; g.zero_cols = D;
     g.A_hi = a_b; g.A_lo = a_s; g.lda = lda; g.W_hi = w_b; g.W_lo = w_s; g.ldw = ldw; g.bias = bias; g.res = res; g.ldr = D;
     g.C = C; g.C_hi = C_b; g.C_lo = C_s; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.epi = epi;
     g.pdl = h->pdl;   // weights are step-invariant: their tiles may be fetched before the dependency wait
@@ -1061,9 +1062,11 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
             LAUNCH_CHECK(h);
         }
         // ---- feed forward on x2 = d.h2: ff = gelu(x2 W1^T + b1) kept as pairs only; z = ff W2^T + b2 + x2  (pre-norm3)
-        if ((rc = linear(h, d.h2_b, d.h2_s, D, L.w1_b, L.w1_s, D, L.b1, nullptr, nullptr, d.ff_b, d.ff_s, F, M, F, D, EPI_BIAS | EPI_GELU, st)))
+        // ff1 also clears d.z (dead here) so that ff2 can run split-K = 2 and fill 120 SMs instead of 60
+        if ((rc = linear(h, d.h2_b, d.h2_s, D, L.w1_b, L.w1_s, D, L.b1, nullptr, nullptr, d.ff_b, d.ff_s, F, M, F, D, EPI_BIAS | EPI_GELU, st,
+                         1, d.z)))
             return rc;
-        if ((rc = linear(h, d.ff_b, d.ff_s, F, L.w2_b, L.w2_s, F, L.b2, d.h2, d.z, nullptr, nullptr, D, M, D, F, EPI_BIAS | EPI_RES, st)))
+        if ((rc = linear(h, d.ff_b, d.ff_s, F, L.w2_b, L.w2_s, F, L.b2, d.h2, d.z, nullptr, nullptr, D, M, D, F, EPI_BIAS | EPI_RES, st, 2)))
             return rc;
         // QaN layers return tgt + (x - tgt) (model/sublayers.py:338-339); that differs from x by
         // <= 1 ulp of max(|x|,|tgt|) and is not reproduced (DESIGN.md "Deviations").

@@ -186,7 +186,9 @@ int idb_gemm_ex(idb_handle* h, const GemmArgs& g_in, cudaStream_t st) {
         }
         if (idb_gemm_tcgen05_supported(g)) return idb_gemm_tcgen05(h, g, st);
     }
-    // fp32 SIMT path (prefers the full-precision operand when both forms are available)
+    // fp32 SIMT path (prefers the full-precision operand when both forms are available); full K, plain
+    // stores, so only the aux-zero side job of the tensor path has to be reproduced
+    if (g.zero) CUDA_TRY(h, cudaMemset2DAsync(g.zero, sizeof(float) * g.zero_ld, 0, sizeof(float) * g.zero_cols, M, st));
     if (g_in.A) { g.A = g_in.A; g.lda = g_in.lda; }
     if (g_in.W) { g.W = g_in.W; g.ldw = g_in.ldw; }
     if ((K % 4) || (g.lda % 4) || (g.ldw % 4))

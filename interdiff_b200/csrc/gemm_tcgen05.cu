@@ -116,7 +116,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                       const __grid_constant__ CUtensorMap map_al, const __grid_constant__ CUtensorMap map_wl,
                       const float* __restrict__ bias, const float* __restrict__ res, int ldr,
                       float* __restrict__ C, __half* __restrict__ Ch, __half* __restrict__ Cl, int ldc, int M, int N, int K, int epi,
-                      int nacc, long long* __restrict__ trace) {
+                      int nacc, float* __restrict__ zero_ptr, int zero_ld, int zero_cols, long long* __restrict__ trace) {
     using cfg = Cfg<BN>;
     // optional per-CTA timeline (clock64 at named points) for debugging the pipeline
     long long* tr = trace ? trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
@@ -137,7 +137,11 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int num_kb = (K + BK - 1) / BK;
+    // split-K: blockIdx.z owns a contiguous range of k-blocks; the partial tiles are combined with
+    // fp32 reductions onto a zeroed C (two addends only, so the result does not depend on their order)
+    const int total_kb = (K + BK - 1) / BK, per_kb = (total_kb + gridDim.z - 1) / gridDim.z;
+    const int kb0 = blockIdx.z * per_kb;
+    const int num_kb = min(per_kb, total_kb - kb0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < cfg::STAGES; s++) {
@@ -170,8 +174,8 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             for (int kb = 0; kb < npre; kb++) {
                 const uint32_t dst = base + kb * cfg::STAGE_BYTES;
                 mbar_arrive_expect_tx(bar_full(kb), cfg::STAGE_BYTES);
-                tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(kb), kb * BK, n0);
-                tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(kb), kb * BK, n0);
+                tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(kb), (kb0 + kb) * BK, n0);
+                tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(kb), (kb0 + kb) * BK, n0);
             }
         }
         __syncwarp();
@@ -179,8 +183,8 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (elect_one()) {
             for (int kb = 0; kb < npre; kb++) {
                 const uint32_t dst = base + kb * cfg::STAGE_BYTES;
-                tma_load_2d(dst, &map_a, bar_full(kb), kb * BK, m0);
-                tma_load_2d(dst + cfg::HALF_BYTES, &map_al, bar_full(kb), kb * BK, m0);
+                tma_load_2d(dst, &map_a, bar_full(kb), (kb0 + kb) * BK, m0);
+                tma_load_2d(dst + cfg::HALF_BYTES, &map_al, bar_full(kb), (kb0 + kb) * BK, m0);
             }
         }
         __syncwarp();
@@ -191,10 +195,10 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const uint32_t dst = base + s * cfg::STAGE_BYTES;
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full(s), cfg::STAGE_BYTES);
-                tma_load_2d(dst, &map_a, bar_full(s), kb * BK, m0);
-                tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(s), kb * BK, n0);
-                tma_load_2d(dst + cfg::HALF_BYTES, &map_al, bar_full(s), kb * BK, m0);
-                tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(s), kb * BK, n0);
+                tma_load_2d(dst, &map_a, bar_full(s), (kb0 + kb) * BK, m0);
+                tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(s), (kb0 + kb) * BK, n0);
+                tma_load_2d(dst + cfg::HALF_BYTES, &map_al, bar_full(s), (kb0 + kb) * BK, m0);
+                tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(s), (kb0 + kb) * BK, n0);
             }
             __syncwarp();
         }
@@ -237,6 +241,17 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // per instruction so the residual reads and the C stores are fully coalesced.
         const int ct = threadIdx.x - 64;
         pdl_wait();      // bias / residual reads and the C stores below touch buffers of earlier kernels
+        if (zero_ptr) {
+            // side job while the MMAs run: clear this CTA's patch of an auxiliary matrix (the zeroed C that
+            // the NEXT split-K GEMM reduces into)
+            const int zc4 = zero_cols / (int)gridDim.x / 4;
+            for (int i = ct; i < BM * zc4; i += 256) {
+                const int r = i / zc4, c4 = i % zc4;
+                if (m0 + r < M)
+                    *reinterpret_cast<float4*>(zero_ptr + (size_t)(m0 + r) * zero_ld + (blockIdx.x * zc4 + c4) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        const bool splitk = gridDim.z > 1, lead = blockIdx.z == 0;
         mbar_wait(bar_acc, 0);
         tc_fence_after();
         if (ct == 0) TRACE(9);
@@ -283,7 +298,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             // for the lane), activation, residual, stores
             const int cj = (lane & 7) * 4, col = n0 + c0 + cj;
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (epi & EPI_BIAS) {
+            if ((epi & EPI_BIAS) && lead) {
                 if (col + 3 < N) b4 = *reinterpret_cast<const float4*>(bias + col);
                 else { if (col < N) b4.x = bias[col]; if (col + 1 < N) b4.y = bias[col + 1]; if (col + 2 < N) b4.z = bias[col + 2]; }
             }
@@ -296,11 +311,14 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 if (epi & EPI_SILU) { o.x = silu(o.x); o.y = silu(o.y); o.z = silu(o.z); o.w = silu(o.w); }
                 if (row < M) {
                     if (col + 3 < N) {
-                        if (epi & EPI_RES) {
+                        if ((epi & EPI_RES) && lead) {
                             const float4 r4 = *reinterpret_cast<const float4*>(res + (size_t)row * ldr + col);
                             o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
                         }
-                        if (C) *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = o;
+                        if (splitk) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(C + (size_t)row * ldc + col), "f"(o.x), "f"(o.y),
+                                         "f"(o.z), "f"(o.w) : "memory");
+                        } else if (C) *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = o;
                         if (Ch) {
                             __half2 h01, h23, l01, l23;
                             split_f16x2(o.x, o.y, h01, l01);
@@ -312,8 +330,9 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         const float oo[4] = {o.x, o.y, o.z, o.w};
                         for (int e = 0; e < 4; e++)
                             if (col + e < N) {
-                                const float val = oo[e] + ((epi & EPI_RES) ? res[(size_t)row * ldr + col + e] : 0.f);
-                                if (C) C[(size_t)row * ldc + col + e] = val;
+                                const float val = oo[e] + (((epi & EPI_RES) && lead) ? res[(size_t)row * ldr + col + e] : 0.f);
+                                if (splitk) atomicAdd(C + (size_t)row * ldc + col + e, val);
+                                else if (C) C[(size_t)row * ldc + col + e] = val;
                                 if (Ch) split_f16(val, Ch[(size_t)row * ldc + col + e], Cl[(size_t)row * ldc + col + e]);
                             }
                     }
@@ -392,16 +411,26 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
     if ((rc = make_map(h, &mw, g.W_hi, N, K, g.ldw, wide ? 128 : 64))) return rc;
     if ((rc = make_map(h, &mal, g.A_lo, M, K, g.lda, BM))) return rc;
     if ((rc = make_map(h, &mwl, g.W_lo, N, K, g.ldw, wide ? 128 : 64))) return rc;
+    // split-K (2 only: two addends commute, so the reduction order cannot change the result) needs a C that
+    // an earlier kernel zeroed (GemmArgs::zero of the producer GEMM) and the plain fp32 output
+    int ksplit = g.ksplit == 2 && (K + BK - 1) / BK >= 2 ? 2 : 1;
+    if (ksplit == 2 && (!g.C || g.C_hi || (g.epi & (EPI_GELU | EPI_SILU))))
+        return idb_fail(h, IDB_ERR_ARG, "split-K GEMM: fp32 output only, no activation");
+    float* zero = g.zero;
+    if (zero) {
+        const int gx = wide ? (N + 127) / 128 : (N + 63) / 64;
+        if (g.zero_cols % (4 * gx) || (g.zero_ld & 3)) return idb_fail(h, IDB_ERR_ARG, "aux zero: %d columns do not split over %d column tiles", g.zero_cols, gx);
+    }
     int nacc = wide ? Cfg<128>::NACC_MAX : Cfg<64>::NACC_MAX;
     if (g_idb_gemm_nacc > 0 && g_idb_gemm_nacc < nacc) nacc = g_idb_gemm_nacc;
     if (wide) {
-        dim3 grid((N + 127) / 128, (M + BM - 1) / BM);
+        dim3 grid((N + 127) / 128, (M + BM - 1) / BM, ksplit);
         idb_launch(g.pdl != 0, gemm_split_f16_kernel<128>, grid, NUM_THREADS, Cfg<128>::SMEM_BYTES, st, ma, mw, mal, mwl, g.bias, g.res, g.ldr,
-                   g.C, g.C_hi, g.C_lo, g.ldc, M, N, K, g.epi, nacc, trace);
+                   g.C, g.C_hi, g.C_lo, g.ldc, M, N, K, g.epi, nacc, zero, g.zero_ld, g.zero_cols, trace);
     } else {
-        dim3 grid((N + 63) / 64, (M + BM - 1) / BM);
+        dim3 grid((N + 63) / 64, (M + BM - 1) / BM, ksplit);
         idb_launch(g.pdl != 0, gemm_split_f16_kernel<64>, grid, NUM_THREADS, Cfg<64>::SMEM_BYTES, st, ma, mw, mal, mwl, g.bias, g.res, g.ldr,
-                   g.C, g.C_hi, g.C_lo, g.ldc, M, N, K, g.epi, nacc, trace);
+                   g.C, g.C_hi, g.C_lo, g.ldc, M, N, K, g.epi, nacc, zero, g.zero_ld, g.zero_cols, trace);
     }
     LAUNCH_CHECK(h);
     return IDB_OK;

@@ -89,8 +89,9 @@ class Engine:
         self._chk(self.lib.idb_set_gemm_backend(self._h, {"simt": 0, "tcgen05": 1}.get(backend, backend)))
 
     # ------------------------------------------------------------------ kernel-level hooks
-    def gemm(self, A, W, bias=None, res=None, gelu=False, silu=False):
-        """epi(A @ W.T) through the handle's GEMM backend (tests / roofline leg)."""
+    def gemm(self, A, W, bias=None, res=None, gelu=False, silu=False, split_k=False):
+        """epi(A @ W.T) through the handle's GEMM backend (tests / roofline leg).  split_k: the tensor path's
+        2-way split-K variant (two partial tiles reduced onto a zeroed C), as the denoiser runs ff2."""
         A, W = self._f32(A), self._f32(W)
         bias = self._f32(bias) if bias is not None else None
         res = self._f32(res) if res is not None else None
@@ -98,11 +99,12 @@ class Engine:
         N = W.shape[0]
         out = torch.empty(M, N, device=self.device)
         epi = (1 if bias is not None else 0) | (2 if gelu else 0) | (4 if res is not None else 0) | (8 if silu else 0)
+        epi |= 128 if split_k else 0
         self._chk(self.lib.idb_debug_gemm(self._h, self._ptr(A), self._ptr(W), self._ptr(bias), self._ptr(res), self._ptr(out),
                                           M, N, K, epi, self._stream()))
         return out
 
-    def gemm_microbench(self, M, N, K, iters=200, gelu=True):
+    def gemm_microbench(self, M, N, K, iters=200, gelu=True, split_k=False):
         """Mean device time of one tensor-core GEMM launch (fp16-pair operands as the denoiser feeds them,
         bias + optional GELU epilogue) over `iters` back-to-back launches issued from C on the current
         stream, CUDA events, after warm-up."""
@@ -115,7 +117,7 @@ class Engine:
         P = self._ptr
         self._chk(self.lib.idb_debug_split(self._h, P(A), P(Ah), P(Al), M, K, K, self._stream()))
         self._chk(self.lib.idb_debug_split(self._h, P(W), P(Wh), P(Wl), N, K, K, self._stream()))
-        epi = 1 | (2 if gelu else 0)
+        epi = 1 | (2 if gelu else 0) | (128 if split_k else 0)
         call = lambda n: self._chk(self.lib.idb_debug_gemm_presplit(self._h, P(Ah), P(Al), P(Wh), P(Wl), P(bias), P(out), M, N, K, epi, n,
                                                                     C.c_void_p(), self._stream()))
         call(10)

@@ -23,6 +23,8 @@ x = tape[0]
 for k in range(steps):
     x, _ = eng.p_sample(99 - k, x, tape[k + 1], gt, mask)
 torch.cuda.synchronize()
-for (M, N, K) in ((1920, 1024, 256), (1920, 256, 1024), (1920, 256, 256)):
-    r = eng.gemm_microbench(M, N, K, iters=200, gelu=(N == 1024))
-    print("gemm %dx%dx%d: %.2f us/launch, %.1f algorithmic TFLOP/s" % (M, N, K, r["ms"] * 1e3, 2.0 * M * N * K / (r["ms"] * 1e-3) / 1e12))
+for (M, N, K, sk) in ((1920, 1024, 256, False), (1920, 256, 1024, False), (1920, 256, 1024, True), (1920, 1536, 256, False),
+                      (1920, 256, 256, False)):
+    r = eng.gemm_microbench(M, N, K, iters=200, gelu=(N == 1024), split_k=sk)
+    print("gemm %dx%dx%d%s: %.2f us/launch, %.1f algorithmic TFLOP/s" % (M, N, K, " split-K 2" if sk else "", r["ms"] * 1e3,
+                                                                        2.0 * M * N * K / (r["ms"] * 1e-3) / 1e12))

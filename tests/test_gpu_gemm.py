@@ -51,3 +51,21 @@ def test_tcgen05_beats_plain_tf32_precision(eng):
     err_tf32 = ((tf32(A.clone()).double() @ tf32(W.clone()).double().T - ref).abs().max() / ref.abs().max()).item()
     eng.set_gemm_backend("simt")
     assert err < err_tf32 / 100, (err, err_tf32)
+
+
+@pytest.mark.parametrize("shape", [(1920, 256, 1024), (300, 64, 260), (129, 200, 128), (64, 8, 64)])
+def test_split_k_matches_fp64_and_is_deterministic(eng, shape):
+    """2-way split-K (how the denoiser runs ff2): partial tiles are reduced with fp32 atomics onto a
+    zeroed C; with two addends the order cannot matter, so repeated runs must agree bit for bit."""
+    M, N, K = shape
+    eng.set_gemm_backend("tcgen05")
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    ref = A.double() @ W.double().T + bias.double() + res.double()
+    outs = [eng.gemm(A, W, bias=bias, res=res, split_k=True).cpu() for _ in range(3)]
+    eng.set_gemm_backend("simt")
+    assert ((outs[0].double() - ref).abs().max() / ref.abs().max()).item() < 2e-6
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

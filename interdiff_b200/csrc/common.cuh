@@ -134,7 +134,29 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact (erf) GELU, F.gelu default (model/layers.py / nn.TransformerDecoderLayer activation="gelu").
+// erf(t) = 1 - 2^(-t q(t)) with a degree-7 minimax fit of q(t) = -log2(erfc(t)) / t on (0, 4] (erf(4) rounds to
+// 1 in fp32), branch-free: 7 FMA + one MUFU.EX2.  Max abs error of erf 1.0e-7 (libdevice erff: 6e-8; the fit
+// is in profiles/README.md), i.e. fp32-rounding level for the GELU output, at less than half the instructions
+// of erff's two-sided evaluation under divergence.
+__device__ __forceinline__ float erf_fast(float x) {
+    const float t = fminf(fabsf(x), 4.0f);
+    float p = 4.5338660129345953e-05f;
+    p = fmaf(p, t, -0.0004454450972843915f);
+    p = fmaf(p, t, 0.0014896064531058073f);
+    p = fmaf(p, t, 0.0007736838888376951f);
+    p = fmaf(p, t, -0.028252195566892624f);
+    p = fmaf(p, t, 0.1484806090593338f);
+    p = fmaf(p, t, 0.9184166789054871f);
+    p = fmaf(p, t, 1.6279085874557495f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * p));
+    return copysignf(1.0f - e, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float hx = 0.5f * x;
+    return fmaf(hx, erf_fast(x * 0.70710678118654752440f), hx);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
 // 16-byte asynchronous global -> shared copies (LDGSTS): a block issues all of a kernel's staging reads

@@ -69,3 +69,19 @@ def test_split_k_matches_fp64_and_is_deterministic(eng, shape):
     eng.set_gemm_backend("simt")
     assert ((outs[0].double() - ref).abs().max() / ref.abs().max()).item() < 2e-6
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("backend", ["simt", "tcgen05"])
+def test_gelu_epilogue_accuracy_on_a_grid(eng, backend):
+    """The epilogue's erf-GELU (branch-free minimax fit, common.cuh) against float64 on every multiple of
+    2^-10 in [-8, 8]: the inputs are exactly representable by the fp16 (hi, lo) operand pairs and the
+    'GEMM' is a multiplication by the identity, so the only error left is the activation's."""
+    eng.set_gemm_backend(backend)
+    x = (torch.arange(-8 * 1024, 8 * 1024 + 1, dtype=torch.float32) / 1024.0)
+    x = x[: (x.numel() // 8) * 8].reshape(-1, 8)
+    out = eng.gemm(x, torch.eye(8), gelu=True).cpu().double()
+    eng.set_gemm_backend("simt")
+    ref = torch.nn.functional.gelu(x.double())
+    # erf error <= 1.0e-7 (fit) -> GELU error <= 0.5 |x| 1e-7, plus the fp32 rounding of the result
+    bound = 2.5e-7 * torch.clamp(x.double().abs(), min=1.0)
+    assert bool(((out - ref).abs() <= bound).all()), ((out - ref).abs() / bound).max().item()

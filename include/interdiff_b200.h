@@ -149,6 +149,8 @@ int idb_debug_gemm_repeat(idb_handle* h, const float* A, const float* W, const f
 
 /* test hook: number of round-robin TMEM accumulators of the tcgen05 GEMM (0 = default) */
 int idb_debug_set_gemm_accumulators(int n);
+/* clock64 phase timeline (16 slots, host pointer) of CTA (0,0) of the last fused QaN + cross-attention kernel */
+int idb_debug_attn_trace(long long* out16);
 /* one launch with a per-CTA clock64 timeline (16 slots per CTA) of the tcgen05 kernel's pipeline */
 int idb_debug_gemm_trace(idb_handle* h, const float* A, const float* W, float* C, int M, int N, int K, long long* trace, void* stream);
 

@@ -156,109 +156,178 @@ __device__ __forceinline__ float dot64(const float* __restrict__ a, const float*
     return s0 + s1;
 }
 
-// Attention core + out-projection (folded into the values) + residual + LayerNorm for a slab of
-// <= 16 query rows of one sample.  grid (B, ceil(T/16)), block 256.
+// ---------------------------------------------------------------------------------------------
+// Attention kernels.  One CTA = a slab of <= 16 rows of one sample, 512 threads (16 warps, 4 per
+// scheduler): these kernels are chains of short, latency-bound phases between block barriers, so
+// the win comes from more warps per phase, fewer phases, and issuing every global read up front.
+// phase timeline of the fused QaN kernel (clock64 of CTA (0,0) thread 0 at the phase boundaries); read with
+// idb_debug_attn_trace.  One predicated store per phase.
+__device__ long long g_attn_trace[16];
+#define ATRACE(slot) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_attn_trace[slot] = clock64(); } while (0)
+constexpr int ANT = 512;   // threads per attention CTA
+constexpr int ANW = 16;    // warps
+
+// --- staging: 1-D bulk copies (TMA) of whole rows, completion counted on an mbarrier.  A CTA needs ~170 KB
+// (folded queries, folded memory keys / values, parameter vectors, its input rows); as per-thread 16-byte
+// cp.async that is ~11 K instructions with index arithmetic per CTA, as bulk copies ~150 instructions.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    }
+}
+// dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+constexpr uint32_t ROW_BYTES = D * sizeof(float);
+
+// z[r][n] = res[r][n] + bo[n] + sum_hj a[hj][r] * v[hj][n]  for the slab's 16 rows: thread (n = tid & 255,
+// half = tid >> 8) owns column n of rows 8*half .. 8*half+7 (rows >= nr carry zero weights).
+__device__ __forceinline__ void weighted_values(const float* __restrict__ s_a, const float* __restrict__ s_v, int HT,
+                                                const float* __restrict__ s_bo, const float* __restrict__ s_res,
+                                                float* __restrict__ s_z, int nr, int tid) {
+    const int n = tid & 255, r8 = (tid >> 8) * 8;
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) acc[r] = 0.f;
+#pragma unroll 4
+    for (int hj = 0; hj < HT; hj++) {
+        const float vv = s_v[(size_t)hj * D + n];
+        const float4* ap = reinterpret_cast<const float4*>(s_a + hj * SLAB + r8);
+        const float4 a0 = ap[0], a1 = ap[1];
+        acc[0] = fmaf(a0.x, vv, acc[0]); acc[1] = fmaf(a0.y, vv, acc[1]); acc[2] = fmaf(a0.z, vv, acc[2]); acc[3] = fmaf(a0.w, vv, acc[3]);
+        acc[4] = fmaf(a1.x, vv, acc[4]); acc[5] = fmaf(a1.y, vv, acc[5]); acc[6] = fmaf(a1.z, vv, acc[6]); acc[7] = fmaf(a1.w, vv, acc[7]);
+    }
+    const float bb = s_bo[n];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+        if (r8 + r < nr) s_z[(r8 + r) * LDZ + n] = (acc[r] + bb) + s_res[(r8 + r) * LDZ + n];
+}
+
+// Self-attention core + out-projection (folded into the values) + residual + LayerNorm.
+// grid (B, ceil(T/16)), block 512.
 //   q rows  : q[(b*T + r) * ldq + h*64 + d]                          (pre-projected queries)
-//   keys    : k[(b*ksb + j*kst) * ldk + h*64 + d], j < Tk            (row strides so the same kernel
-//   values' : v[(b*ksb + j*kst) * ldv + h*256 + n]                    reads self- and cross-attention)
-//             = (V_h W_o,h^T)[j][n]: value vectors already multiplied by the head's out-proj block
+//   keys    : k[(b*T + j) * ldk + h*64 + d], j < T
+//   values' : v[(b*T + j) * ldv + h*256 + n]  = (V_h W_o,h^T)[j][n]: value vectors already
+//             multiplied by the head's out-proj block
 //   out[r]  = LN( res[r] + bo + sum_h sum_j softmax_j(q_h[r].k_h[j] / 8) v'_h[j] )
-// Every global read (q, k, v', residual) is issued up front into shared memory in one batch, so the
-// kernel pays one memory latency; everything after runs out of shared memory.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(ANT)
 k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
-          int ksb, int kst, const float* __restrict__ res, const float* __restrict__ bo, const float* __restrict__ lnw,
+          const float* __restrict__ res, const float* __restrict__ bo, const float* __restrict__ lnw,
           const float* __restrict__ lnb, float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s,
-          int T, int Tk, int H) {
+          int T, int H) {
     extern __shared__ __align__(16) float sm[];
     const int LDK = HD + 4;
-    const int HT = H * Tk;
-    float* s_q = sm;                       // [SLAB][LDZ]  (padded rows: 16 query rows are read by one warp)
+    const int Tk = T, HT = H * Tk;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: parameters, [1]: activations
+    float* s_par = sm + 4;                 // bo, lnw, lnb
+    float* s_q = s_par + 3 * D;            // [SLAB][LDZ]  (padded rows: 16 query rows are read by one warp)
     float* s_k = s_q + SLAB * LDZ;         // [H*Tk][LDK]
     float* s_a = s_k + HT * LDK;           // [H*Tk][SLAB]  (transposed: the 16 rows of one (h,j) are contiguous)
     float* s_z = s_a + SLAB * HT;          // [SLAB][LDZ]   residual rows, then the pre-LayerNorm sums
     float* s_v = s_z + SLAB * LDZ;         // [H*Tk][D]     folded values
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     pdl_trigger();
-    pdl_wait();
-    for (int i = tid; i < nr * (D / 4); i += 256) {
-        const int r = i / (D / 4), c = i % (D / 4);
-        cp_async16(s_q + r * LDZ + c * 4, q + (size_t)(b * T + r0 + r) * ldq + c * 4);
-        cp_async16(s_z + r * LDZ + c * 4, res + (size_t)(b * T + r0 + r) * D + c * 4);
+    if (tid == 0) {
+        mb_init(bar, 1); mb_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < Tk * (D / 4); i += 256) {
-        const int j = i / (D / 4), c = i % (D / 4);          // c-th float4 of key row j: head c/16, offset (c%16)*4
-        cp_async16(s_k + ((c / 16) * Tk + j) * LDK + (c % 16) * 4, k + (size_t)(b * ksb + j * kst) * ldk + c * 4);
-    }
-    for (int i = tid; i < HT * (D / 4); i += 256) {
-        const int hj = i / (D / 4), c = i % (D / 4), hh = hj / Tk, j = hj % Tk;
-        cp_async16(s_v + (size_t)hj * D + c * 4, v + (size_t)(b * ksb + j * kst) * ldv + hh * D + c * 4);
-    }
-    cp_async_wait_all();
     __syncthreads();
+    if (tid == 0) {
+        mb_expect_tx(bar, 3 * ROW_BYTES);
+        bulk_g2s(s_par, bo, ROW_BYTES, bar); bulk_g2s(s_par + D, lnw, ROW_BYTES, bar); bulk_g2s(s_par + 2 * D, lnb, ROW_BYTES, bar);
+    }
+    pdl_wait();
+    if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)(2 * nr + (H + 1) * Tk) * ROW_BYTES);
+    __syncwarp();
+    // one copy per thread and round: query + residual rows, key head slices (256 B), folded value rows
+    for (int i = tid; i < 2 * nr + 2 * HT; i += ANT) {
+        if (i < nr) bulk_g2s(s_q + i * LDZ, q + (size_t)(b * T + r0 + i) * ldq, ROW_BYTES, bar + 1);
+        else if (i < 2 * nr) bulk_g2s(s_z + (i - nr) * LDZ, res + (size_t)(b * T + r0 + i - nr) * D, ROW_BYTES, bar + 1);
+        else if (i < 2 * nr + HT) {
+            const int hj = i - 2 * nr, hh = hj / Tk, j = hj - hh * Tk;
+            bulk_g2s(s_k + hj * LDK, k + (size_t)(b * T + j) * ldk + hh * HD, HD * sizeof(float), bar + 1);
+        } else {
+            const int hj = i - 2 * nr - HT, hh = hj / Tk, j = hj - hh * Tk;
+            bulk_g2s(s_v + (size_t)hj * D, v + (size_t)(b * T + j) * ldv + hh * D, ROW_BYTES, bar + 1);
+        }
+    }
+    mb_wait(bar + 1, 0);
     const float scale = 0.125f;   // 1/sqrt(64)
-    for (int i = tid; i < SLAB * HT; i += 256) {
+    for (int i = tid; i < SLAB * HT; i += ANT) {
         const int hj = i / SLAB, r = i % SLAB, hh = hj / Tk;
         s_a[i] = r < nr ? dot64(s_q + r * LDZ + hh * HD, s_k + hj * LDK) * scale : 0.f;
     }
     __syncthreads();
-    for (int g = tid; g < nr * H; g += 256) {
-        float* col = s_a + (g % H) * Tk * SLAB + (g / H);      // element j at col[j * SLAB]
-        float mx = -INFINITY;
-        for (int j = 0; j < Tk; j++) mx = fmaxf(mx, col[j * SLAB]);
-        float s = 0.f;
-        for (int j = 0; j < Tk; j++) { const float e = expf(col[j * SLAB] - mx); col[j * SLAB] = e; s += e; }
-        const float inv = 1.0f / s;
-        for (int j = 0; j < Tk; j++) col[j * SLAB] *= inv;
-    }
-    __syncthreads();
-    {
-        const int n = tid;
-        float acc[SLAB];
+    // one warp per (row, head): softmax over the Tk keys (two pairs in flight per warp for latency)
+    for (int g = warp; g < nr * H; g += 2 * ANW) {
+        float* c0 = s_a + (g % H) * Tk * SLAB + (g / H);
+        const int g1 = g + ANW;
+        const bool two = g1 < nr * H;
+        float* c1 = two ? s_a + (g1 % H) * Tk * SLAB + (g1 / H) : c0;
+        const float a0 = lane < Tk ? c0[lane * SLAB] : -INFINITY, a1 = lane + 32 < Tk ? c0[(lane + 32) * SLAB] : -INFINITY;
+        const float b0 = lane < Tk ? c1[lane * SLAB] : -INFINITY, b1 = lane + 32 < Tk ? c1[(lane + 32) * SLAB] : -INFINITY;
+        float ma = fmaxf(a0, a1), mb = fmaxf(b0, b1);
 #pragma unroll
-        for (int r = 0; r < SLAB; r++) acc[r] = 0.f;
-#pragma unroll 4
-        for (int hj = 0; hj < HT; hj++) {
-            const float vv = s_v[(size_t)hj * D + n];
-            const float4* ap = reinterpret_cast<const float4*>(s_a + hj * SLAB);
-            const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];     // rows >= nr hold zeros
-            acc[0] = fmaf(a0.x, vv, acc[0]); acc[1] = fmaf(a0.y, vv, acc[1]); acc[2] = fmaf(a0.z, vv, acc[2]); acc[3] = fmaf(a0.w, vv, acc[3]);
-            acc[4] = fmaf(a1.x, vv, acc[4]); acc[5] = fmaf(a1.y, vv, acc[5]); acc[6] = fmaf(a1.z, vv, acc[6]); acc[7] = fmaf(a1.w, vv, acc[7]);
-            acc[8] = fmaf(a2.x, vv, acc[8]); acc[9] = fmaf(a2.y, vv, acc[9]); acc[10] = fmaf(a2.z, vv, acc[10]); acc[11] = fmaf(a2.w, vv, acc[11]);
-            acc[12] = fmaf(a3.x, vv, acc[12]); acc[13] = fmaf(a3.y, vv, acc[13]); acc[14] = fmaf(a3.z, vv, acc[14]); acc[15] = fmaf(a3.w, vv, acc[15]);
+        for (int o = 16; o; o >>= 1) { ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o)); }
+        const float ea0 = lane < Tk ? expf(a0 - ma) : 0.f, ea1 = lane + 32 < Tk ? expf(a1 - ma) : 0.f;
+        const float eb0 = lane < Tk ? expf(b0 - mb) : 0.f, eb1 = lane + 32 < Tk ? expf(b1 - mb) : 0.f;
+        float sa = ea0 + ea1, sb = eb0 + eb1;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+        const float ia = 1.0f / sa, ib = 1.0f / sb;
+        if (lane < Tk) c0[lane * SLAB] = ea0 * ia;
+        if (lane + 32 < Tk) c0[(lane + 32) * SLAB] = ea1 * ia;
+        if (two) {
+            if (lane < Tk) c1[lane * SLAB] = eb0 * ib;
+            if (lane + 32 < Tk) c1[(lane + 32) * SLAB] = eb1 * ib;
         }
-        const float bb = bo[n];
-#pragma unroll
-        for (int r = 0; r < SLAB; r++)
-            if (r < nr) s_z[r * LDZ + n] = (acc[r] + bb) + s_z[r * LDZ + n];
     }
+    mb_wait(bar, 0);
     __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < nr; r += 8) {
+    weighted_values(s_a, s_v, HT, s_par, s_z, s_z, nr, tid);
+    __syncthreads();
+    for (int r = warp; r < nr; r += ANW) {
         const size_t o = (size_t)(b * T + r0 + r) * D;
-        warp_ln_row(s_z + r * LDZ, lnw, lnb, out + o, lane, out_b ? out_b + o : nullptr, out_s ? out_s + o : nullptr);
+        warp_ln_row(s_z + r * LDZ, s_par + D, s_par + 2 * D, out + o, lane, out_b ? out_b + o : nullptr, out_s ? out_s + o : nullptr);
     }
 }
 
 // Register-tiled dot products between two sets of 256-wide rows held in shared memory (row stride
 // LDZ):  part[ks][r][j] = sum_{d in k-slice ks} A[r][d] * Bm[j][d].   No shuffles: a lane owns
-// TR x TJ outputs (rows rl + 4v of its warp's row half, columns jl + 8u) and walks a 64-wide
-// k-slice; the 8 warps are 4 k-slices x 2 row halves.  Consecutive rows / columns across the lanes
-// land in distinct 16-byte bank groups (LDZ = 260), so every LDS.128 is one wavefront, and the FMA
-// to LDS ratio is 4*TR*TJ : TR+TJ.  Rows >= nA / columns >= nB are clamped (results unused).
-// The caller sums the 4 k-slices in a fixed order (deterministic).  part: [4][8*TR][TILE_LDP].
-constexpr int TILE_LDP = 40;
-template <int TR, int TJ>
+// TR x TJ outputs (rows rl + 4v of its warp's row group, columns jl + 8u of its column group) and
+// walks a 64-wide k-slice; the 16 warps are 4 k-slices x NRG row groups x NCG column groups.
+// Consecutive rows / columns across the lanes land in distinct 16-byte bank groups (LDZ = 260), so
+// every LDS.128 is one wavefront, and the FMA to LDS ratio is 4*TR*TJ : TR+TJ.  Rows >= nA /
+// columns >= nB are clamped for the loads and not stored.  The caller sums the 4 k-slices in a
+// fixed order (deterministic).  part: [4][4*TR*NRG][LDP], written at column offset pcol0.
+template <int TR, int TJ, int NRG, int NCG, int LDP>
 __device__ __forceinline__ void tile_dots(const float* __restrict__ sA, int nA, const float* __restrict__ sB, int nB,
-                                          float* __restrict__ part, int warp, int lane) {
-    constexpr int ROWS = 8 * TR;
-    const int jl = lane & 7, rl = lane >> 3, ks = warp & 3, rh = warp >> 2;
+                                          float* __restrict__ part, int pcol0, int warp, int lane) {
+    static_assert(NRG * NCG == 4, "16 warps = 4 k-slices x 4 (row, column) groups");
+    constexpr int ROWS = 4 * TR * NRG;
+    const int jl = lane & 7, rl = lane >> 3, ks = warp & 3, rg = (warp >> 2) % NRG, cg = (warp >> 2) / NRG;
+    const int row0 = rg * 4 * TR + rl, col0 = cg * 8 * TJ + jl;
     const float* ap[TR];
     const float* bp[TJ];
 #pragma unroll
-    for (int v = 0; v < TR; v++) ap[v] = sA + min(rh * 4 * TR + rl + 4 * v, nA - 1) * LDZ + ks * 64;
+    for (int v = 0; v < TR; v++) ap[v] = sA + min(row0 + 4 * v, nA - 1) * LDZ + ks * 64;
 #pragma unroll
-    for (int u = 0; u < TJ; u++) bp[u] = sB + min(jl + 8 * u, nB - 1) * LDZ + ks * 64;
+    for (int u = 0; u < TJ; u++) bp[u] = sB + min(col0 + 8 * u, nB - 1) * LDZ + ks * 64;
     float acc[TR][TJ];
 #pragma unroll
     for (int v = 0; v < TR; v++)
@@ -282,7 +351,8 @@ __device__ __forceinline__ void tile_dots(const float* __restrict__ sA, int nA, 
 #pragma unroll
     for (int v = 0; v < TR; v++)
 #pragma unroll
-        for (int u = 0; u < TJ; u++) part[(ks * ROWS + rh * 4 * TR + rl + 4 * v) * TILE_LDP + jl + 8 * u] = acc[v][u];
+        for (int u = 0; u < TJ; u++)
+            if (col0 + 8 * u < nB) part[(ks * ROWS + row0 + 4 * v) * LDP + pcol0 + col0 + 8 * u] = acc[v][u];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -290,87 +360,79 @@ __device__ __forceinline__ void tile_dots(const float* __restrict__ sA, int nA, 
 //   logit[t,h,j] = x1[t] . kp[h,j] + kc[h,j]      kp = (K_h Wq_h)/8 (256-vector), kc = (bq_h . K_h)/8
 //   out[t] = LN2( x1[t] + bo + sum_{h,j} softmax_j(logit)[t,h,j] vp[h,j] )      vp = V_h Wo_h^T
 // so no query GEMM is needed and the block can run right after the layer's first sub-block while its
-// x1 rows are still in shared memory.  s_kp [HT][LDZ], s_kc [HT], s_v [HT][D] must already be staged.
+// x1 rows are still in shared memory.  s_kp [HT][LDZ], s_kc [HT], s_v [HT][D] and the parameter rows
+// s_bo / s_lnw / s_lnb must already be staged.  Tk <= 16, H*Tk <= 64.
+constexpr int XLDP = 64;
 __device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s_x1, const float* __restrict__ s_kp,
                                                      const float* __restrict__ s_kc, const float* __restrict__ s_v,
                                                      float* __restrict__ s_a, float* __restrict__ s_z, int nr, int HT, int Tk, int H,
-                                                     const float* __restrict__ bo, const float* __restrict__ lnw,
-                                                     const float* __restrict__ lnb, float* __restrict__ out,
-                                                     __half* __restrict__ out_b, __half* __restrict__ out_s, size_t row0) {
+                                                     const float* __restrict__ s_bo, const float* __restrict__ s_lnw,
+                                                     const float* __restrict__ s_lnb, float* __restrict__ out,
+                                                     __half* __restrict__ out_b, __half* __restrict__ out_s, size_t row0,
+                                                     bool trace = false) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // logits in blocks of 40 folded keys: k-split partial tiles in s_z (free until the value pass), then
-    // a fixed-order sum of the 4 k-slices + the constant term
-    for (int j0 = 0; j0 < HT; j0 += TILE_LDP) {
-        const int nj = min(TILE_LDP, HT - j0);
-        tile_dots<2, 5>(s_x1, nr, s_kp + j0 * LDZ, nj, s_z, warp, lane);
-        __syncthreads();
-        for (int i = tid; i < SLAB * nj; i += 256) {
-            const int r = i / nj, jj = i % nj;
-            const float a = ((s_z[(0 * SLAB + r) * TILE_LDP + jj] + s_z[(1 * SLAB + r) * TILE_LDP + jj]) +
-                             s_z[(2 * SLAB + r) * TILE_LDP + jj]) + s_z[(3 * SLAB + r) * TILE_LDP + jj];
-            s_a[(j0 + jj) * SLAB + r] = r < nr ? a + s_kc[j0 + jj] : 0.f;
-        }
-        __syncthreads();
-    }
-    for (int g = tid; g < nr * H; g += 256) {
-        float* col = s_a + (g % H) * Tk * SLAB + (g / H);      // element j at col[j * SLAB]
-        float mx = -INFINITY;
-        for (int j = 0; j < Tk; j++) mx = fmaxf(mx, col[j * SLAB]);
-        float sum = 0.f;
-        for (int j = 0; j < Tk; j++) { const float e = expf(col[j * SLAB] - mx); col[j * SLAB] = e; sum += e; }
-        const float inv = 1.0f / sum;
-        for (int j = 0; j < Tk; j++) col[j * SLAB] *= inv;
-    }
+    // logits: k-split partial tiles in s_z (free until the value pass), 40 folded keys per pass
+    for (int j0 = 0; j0 < HT; j0 += 40)
+        tile_dots<1, 5, 4, 1, XLDP>(s_x1, nr, s_kp + j0 * LDZ, min(40, HT - j0), s_z, j0, warp, lane);
     __syncthreads();
+    if (trace) ATRACE(7);
+    // 16-lane group per (row, head): fixed-order sum of the 4 k-slices + constant term, softmax over the
+    // Tk memory slots with shuffles, probabilities stored transposed ([hj][row]) for the value pass
     {
-        const int n = tid;
-        float acc[SLAB];
+        const int l16 = tid & 15;
+        for (int p = tid >> 4; p < SLAB * H; p += ANT / 16) {
+            const int r = p / H, hh = p - r * H, hj = hh * Tk + l16;
+            const bool on = l16 < Tk;
+            float a = -INFINITY;
+            if (on) {
+                const float* pp = s_z + r * XLDP + hj;
+                a = (((pp[0] + pp[SLAB * XLDP]) + pp[2 * SLAB * XLDP]) + pp[3 * SLAB * XLDP]) + s_kc[hj];
+            }
+            float mx = a;
 #pragma unroll
-        for (int r = 0; r < SLAB; r++) acc[r] = 0.f;
-#pragma unroll 4
-        for (int hj = 0; hj < HT; hj++) {
-            const float vv = s_v[(size_t)hj * D + n];
-            const float4* ap = reinterpret_cast<const float4*>(s_a + hj * SLAB);
-            const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2], a3 = ap[3];     // rows >= nr hold zeros
-            acc[0] = fmaf(a0.x, vv, acc[0]); acc[1] = fmaf(a0.y, vv, acc[1]); acc[2] = fmaf(a0.z, vv, acc[2]); acc[3] = fmaf(a0.w, vv, acc[3]);
-            acc[4] = fmaf(a1.x, vv, acc[4]); acc[5] = fmaf(a1.y, vv, acc[5]); acc[6] = fmaf(a1.z, vv, acc[6]); acc[7] = fmaf(a1.w, vv, acc[7]);
-            acc[8] = fmaf(a2.x, vv, acc[8]); acc[9] = fmaf(a2.y, vv, acc[9]); acc[10] = fmaf(a2.z, vv, acc[10]); acc[11] = fmaf(a2.w, vv, acc[11]);
-            acc[12] = fmaf(a3.x, vv, acc[12]); acc[13] = fmaf(a3.y, vv, acc[13]); acc[14] = fmaf(a3.z, vv, acc[14]); acc[15] = fmaf(a3.w, vv, acc[15]);
+            for (int o = 8; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const float e = on ? expf(a - mx) : 0.f;
+            float sum = e;
+#pragma unroll
+            for (int o = 8; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (on) s_a[hj * SLAB + r] = r < nr ? e / sum : 0.f;
         }
-        const float bb = bo[n];
-#pragma unroll
-        for (int r = 0; r < SLAB; r++)
-            if (r < nr) s_z[r * LDZ + n] = (acc[r] + bb) + s_x1[r * LDZ + n];
     }
     __syncthreads();
-    for (int r = warp; r < nr; r += 8) {
+    if (trace) ATRACE(8);
+    weighted_values(s_a, s_v, HT, s_bo, s_x1, s_z, nr, tid);
+    __syncthreads();
+    if (trace) ATRACE(9);
+    for (int r = warp; r < nr; r += ANW) {
         const size_t o = (row0 + r) * D;
-        warp_ln_row(s_z + r * LDZ, lnw, lnb, out + o, lane, out_b ? out_b + o : nullptr, out_s ? out_s + o : nullptr);
+        warp_ln_row(s_z + r * LDZ, s_lnw, s_lnb, out + o, lane, out_b ? out_b + o : nullptr, out_s ? out_s + o : nullptr);
     }
 }
 
-// stage the folded memory tensors of sample b (rows j*B + b of kp / vp / kc) into shared memory
+// stage the folded memory tensors of sample b (rows j*B + b of kp / vp / kc): one bulk copy per row
 __device__ __forceinline__ void stage_memory(const float* __restrict__ kp, const float* __restrict__ kc, const float* __restrict__ vp,
                                              float* __restrict__ s_kp, float* __restrict__ s_kc, float* __restrict__ s_v,
-                                             int b, int B, int Tk, int H) {
+                                             int b, int B, int Tk, int H, uint64_t* bar) {
     const int HT = H * Tk, tid = threadIdx.x;
-    for (int i = tid; i < HT * (D / 4); i += 256) {
-        const int hj = i / (D / 4), c = i % (D / 4), hh = hj / Tk, j = hj % Tk;
+    for (int i = tid; i < 2 * HT; i += ANT) {
+        const int hj = i < HT ? i : i - HT, hh = hj / Tk, j = hj - hh * Tk;
         const size_t row = (size_t)(j * B + b) * H * D + (size_t)hh * D;
-        cp_async16(s_kp + hj * LDZ + c * 4, kp + row + c * 4);
-        cp_async16(s_v + (size_t)hj * D + c * 4, vp + row + c * 4);
+        if (i < HT) bulk_g2s(s_kp + hj * LDZ, kp + row, ROW_BYTES, bar);
+        else bulk_g2s(s_v + (size_t)hj * D, vp + row, ROW_BYTES, bar);
     }
-    for (int hj = tid; hj < HT; hj += 256) s_kc[hj] = kc[(size_t)((hj % Tk) * B + b) * H + hj / Tk];
+    for (int hj = tid; hj < HT; hj += ANT) s_kc[hj] = kc[(size_t)((hj % Tk) * B + b) * H + hj / Tk];
 }
 
 // standalone cross-attention block (layers whose first sub-block is the standard self-attention)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(ANT)
 k_xattn_ln(const float* __restrict__ x1, const float* __restrict__ kp, const float* __restrict__ kc, const float* __restrict__ vp,
            const float* __restrict__ bo, const float* __restrict__ lnw, const float* __restrict__ lnb, float* __restrict__ out,
            __half* __restrict__ out_b, __half* __restrict__ out_s, int T, int B, int Tk, int H) {
     extern __shared__ __align__(16) float sm[];
     const int HT = H * Tk;
-    float* s_x1 = sm;                       // [SLAB][LDZ]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: step-invariant tensors, [1]: input rows
+    float* s_par = sm + 4;                  // bo, lnw, lnb
+    float* s_x1 = s_par + 3 * D;            // [SLAB][LDZ]
     float* s_kp = s_x1 + SLAB * LDZ;        // [HT][LDZ]
     float* s_v = s_kp + HT * LDZ;           // [HT][D]
     float* s_a = s_v + HT * D;              // [HT][SLAB]
@@ -378,26 +440,37 @@ k_xattn_ln(const float* __restrict__ x1, const float* __restrict__ kp, const flo
     float* s_kc = s_z + SLAB * LDZ;         // [HT]
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
     pdl_trigger();
-    stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H);     // step-invariant: overlaps the previous kernel
-    pdl_wait();
-    for (int i = tid; i < nr * (D / 4); i += 256) {
-        const int r = i / (D / 4), c = i % (D / 4);
-        cp_async16(s_x1 + r * LDZ + c * 4, x1 + (size_t)(b * T + r0 + r) * D + c * 4);
+    if (tid == 0) {
+        mb_init(bar, 1); mb_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    cp_async_wait_all();
     __syncthreads();
-    cross_attention_tail(s_x1, s_kp, s_kc, s_v, s_a, s_z, nr, HT, Tk, H, bo, lnw, lnb, out, out_b, out_s, (size_t)b * T + r0);
+    if (tid == 0) {
+        mb_expect_tx(bar, (uint32_t)(3 + 2 * HT) * ROW_BYTES);
+        bulk_g2s(s_par, bo, ROW_BYTES, bar); bulk_g2s(s_par + D, lnw, ROW_BYTES, bar); bulk_g2s(s_par + 2 * D, lnb, ROW_BYTES, bar);
+    }
+    __syncwarp();
+    stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H, bar);     // step-invariant: overlaps the previous kernel
+    pdl_wait();
+    if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)nr * ROW_BYTES);
+    __syncwarp();
+    if (tid < nr) bulk_g2s(s_x1 + tid * LDZ, x1 + (size_t)(b * T + r0 + tid) * D, ROW_BYTES, bar + 1);
+    mb_wait(bar, 0);
+    mb_wait(bar + 1, 0);
+    __syncthreads();     // s_kc was written with plain stores
+    cross_attention_tail(s_x1, s_kp, s_kc, s_v, s_a, s_z, nr, HT, Tk, H, s_par, s_par + D, s_par + 2 * D, out, out_b, out_s,
+                         (size_t)b * T + r0);
 }
 
 // QaN block + residual + LayerNorm1 (model/sublayers.py:343-352 + :332) for a slab of <= 16 rows of
 // one sample, with an optional LayerNorm applied to the input rows first (the previous layer's
-// pending norm3).   grid (B, ceil(T/16)), block 256.
+// pending norm3).   grid (B, ceil(T/16)), block 512.
 //   x = pre ? LN_pre(zin) : zin
 //   logit[t,n,s] = x[t+s-1] . Qt[s][n]   (Qt = rotary-folded, 1/16-scaled normalised queries; s = key slot)
 //   a = softmax over the valid slots;  y[t] = sum_s (sum_n wk[n] a[t,n,s]) x[t+s-1];  out = LN1(x + y)
 // ... followed, in the same kernel, by the layer's cross-attention block (cross_attention_tail) on the
 // LN1 rows, which never leave shared memory.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(ANT)
 k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, const float* __restrict__ preb,
                const float* __restrict__ qt, const float* __restrict__ wk, const float* __restrict__ lnw,
                const float* __restrict__ lnb, const float* __restrict__ kp, const float* __restrict__ kc,
@@ -405,12 +478,12 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
                const float* __restrict__ ln2b, float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s,
                int T, int N, int B, int Tk, int H) {
     extern __shared__ __align__(16) float sm[];
-    const int HT = H * Tk;
-    float* s_x = sm;                        // [SLAB+2][LDZ]   rows r0-1 .. r0+nr
-    float* s_qt = s_x + (SLAB + 2) * LDZ;   // [32][LDZ]
-    float* s_p = s_qt + 32 * LDZ;           // [SLAB][N][3] slot probabilities (N <= 10)
-    float* s_c = s_p + SLAB * 32;           // [SLAB][4]
-    float* s_x1 = s_c + SLAB * 4;           // [SLAB][LDZ]     LN1 rows (input of the cross-attention block)
+    const int HT = H * Tk, NQ = 3 * N;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: step-invariant tensors, [1]: input rows
+    float* s_par = sm + 4;                  // pre w, pre b, ln1 w, ln1 b, bo2, ln2 w, ln2 b
+    float* s_x = s_par + 7 * D;             // [SLAB+2][LDZ]   rows r0-1 .. r0+nr
+    float* s_qt = s_x + (SLAB + 2) * LDZ;   // [30][LDZ]
+    float* s_x1 = s_qt + 30 * LDZ;          // [SLAB][LDZ]     LN1 rows (input of the cross-attention block)
     float* s_kp = s_x1 + SLAB * LDZ;        // [HT][LDZ]
     float* s_v = s_kp + HT * LDZ;           // [HT][D]
     float* s_a = s_v + HT * D;              // [HT][SLAB]
@@ -418,75 +491,88 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     float* s_kc = s_z + SLAB * LDZ;         // [HT]
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int NQ = 3 * N;
-    // Everything the kernel reads from global memory is issued up front as asynchronous copies: first the
-    // step-invariant tensors (folded queries, folded memory keys / values), which overlap the previous
-    // kernel's tail under programmatic dependent launch, then - after the dependency wait - the input
-    // rows r0-1 .. r0+nr (halo of one on each side), local index l = t - (r0 - 1).
+    // Everything the kernel reads from global memory is requested up front as row-sized bulk copies: first
+    // the step-invariant tensors (parameters, folded queries, folded memory keys / values), which overlap
+    // the previous kernel's tail under programmatic dependent launch, then - after the dependency wait -
+    // the input rows r0-1 .. r0+nr (halo of one on each side), local index l = t - (r0 - 1).
     pdl_trigger();
-    for (int i = tid; i < 32 * (D / 4); i += 256) {
-        const int r = i / (D / 4), c = i % (D / 4);
-        if (r < NQ) cp_async16(s_qt + r * LDZ + c * 4, qt + (size_t)r * D + c * 4);
-        else *reinterpret_cast<float4*>(s_qt + r * LDZ + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    ATRACE(0);
+    if (tid == 0) {
+        mb_init(bar, 1); mb_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H);
-    pdl_wait();
-    for (int i = tid; i < (nr + 2) * (D / 4); i += 256) {
-        const int l = i / (D / 4), c = i % (D / 4), t = r0 - 1 + l;
-        if (t >= 0 && t < T) cp_async16(s_x + l * LDZ + c * 4, zin + (size_t)(b * T + t) * D + c * 4);
-    }
-    cp_async_wait_all();
     __syncthreads();
+    const int npar = prew ? 7 : 5;
+    if (tid == 0) mb_expect_tx(bar, (uint32_t)(npar + NQ + 2 * HT) * ROW_BYTES);
+    __syncwarp();
+    if (tid < 7) {
+        const float* src = tid == 0 ? prew : tid == 1 ? preb : tid == 2 ? lnw : tid == 3 ? lnb : tid == 4 ? bo2 : tid == 5 ? ln2w : ln2b;
+        if (src) bulk_g2s(s_par + tid * D, src, ROW_BYTES, bar);
+    } else if (tid >= 32 && tid < 32 + NQ) {
+        bulk_g2s(s_qt + (tid - 32) * LDZ, qt + (size_t)(tid - 32) * D, ROW_BYTES, bar);
+    }
+    stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H, bar);
+    const float wk_n = lane < N ? wk[lane] : 0.f;
+    ATRACE(1);
+    pdl_wait();
+    ATRACE(2);
+    {
+        const int t_lo = max(r0 - 1, 0), t_hi = min(r0 + nr, T - 1);      // valid staged rows t_lo .. t_hi
+        if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)(t_hi - t_lo + 1) * ROW_BYTES);
+        __syncwarp();
+        const int t = r0 - 1 + tid;
+        if (tid < nr + 2 && t >= 0 && t < T) bulk_g2s(s_x + tid * LDZ, zin + (size_t)(b * T + t) * D, ROW_BYTES, bar + 1);
+    }
+    mb_wait(bar, 0);
+    mb_wait(bar + 1, 0);
+    __syncthreads();     // s_kc was written with plain stores
+    ATRACE(3);
     if (prew) {   // the previous layer's pending LayerNorm3, in place on the staged rows
-        for (int l = warp; l < nr + 2; l += 8) {
+        for (int l = warp; l < nr + 2; l += ANW) {
             const int t = r0 - 1 + l;
-            if (t >= 0 && t < T) warp_ln_row(s_x + l * LDZ, prew, preb, s_x + l * LDZ, lane);
+            if (t >= 0 && t < T) warp_ln_row(s_x + l * LDZ, s_par, s_par + D, s_x + l * LDZ, lane);
         }
         __syncthreads();
     }
     // part[ks][l][j] = (k-slice of) x[row l] . Qt[j] for all nr+2 staged rows and the 3N folded queries
     // (register-tiled, no shuffles); s_z is free until the cross-attention block and holds the partials.
-    tile_dots<3, 4>(s_x, nr + 2, s_qt, 32, s_z, warp, lane);
+    ATRACE(4);
+    tile_dots<3, 2, 2, 2, 40>(s_x, nr + 2, s_qt, NQ, s_z, 0, warp, lane);
     __syncthreads();
-    // softmax over the (<= 3) valid key slots per (row, query); row l = r + slot feeds output row r
-    for (int i = tid; i < nr * N; i += 256) {
-        const int r = i / N, n = i % N, t = r0 + r;
-        const bool v0 = t > 0, v2 = t < T - 1;
-        float lg[3];
-#pragma unroll
-        for (int sl = 0; sl < 3; sl++) {
-            const float* pp = s_z + (r + sl) * TILE_LDP + sl * N + n;
-            lg[sl] = ((pp[0] + pp[24 * TILE_LDP]) + pp[2 * 24 * TILE_LDP]) + pp[3 * 24 * TILE_LDP];
-        }
-        const float l1 = lg[1], l0 = v0 ? lg[0] : -INFINITY, l2 = v2 ? lg[2] : -INFINITY;
-        const float mx = fmaxf(l1, fmaxf(l0, l2));
-        const float e0 = v0 ? expf(l0 - mx) : 0.f, e1 = expf(l1 - mx), e2 = v2 ? expf(l2 - mx) : 0.f;
-        const float inv = 1.0f / (e0 + e1 + e2);
-        s_p[i * 3 + 0] = e0 * inv; s_p[i * 3 + 1] = e1 * inv; s_p[i * 3 + 2] = e2 * inv;
-    }
-    __syncthreads();
-    for (int i = tid; i < nr * 3; i += 256) {     // c[r][slot] = sum_n wk[n] a[r][n][slot], fixed order
-        const int r = i / 3, sl = i % 3;
-        float c = 0.f;
-        for (int n = 0; n < N; n++) c = fmaf(wk[n], s_p[(r * N + n) * 3 + sl], c);
-        s_c[r * 4 + sl] = c;
-    }
-    __syncthreads();
-    for (int r = warp; r < nr; r += 8) {
+    ATRACE(5);
+    // One warp per output row: lane n < N sums the k-slices of its 3 slot logits (row l = r + slot feeds
+    // output row r), softmax over the valid slots, times wk[n]; three warp sums give the row's tap
+    // weights c[slot] = sum_n wk[n] a[n][slot]; then y = 3-tap filter, residual and LayerNorm1 in registers.
+    for (int r = warp; r < nr; r += ANW) {
         const int t = r0 + r;
-        const float c0 = s_c[r * 4], c1 = s_c[r * 4 + 1], c2 = s_c[r * 4 + 2];
-        float* xm = s_x + (r + 1) * LDZ;          // row t (becomes x + y in place: only this warp touches it now)
+        const bool v0 = t > 0, v2 = t < T - 1;
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+        if (lane < N) {
+            float lg[3];
+#pragma unroll
+            for (int sl = 0; sl < 3; sl++) {
+                const float* pp = s_z + (r + sl) * 40 + sl * N + lane;
+                lg[sl] = ((pp[0] + pp[24 * 40]) + pp[2 * 24 * 40]) + pp[3 * 24 * 40];
+            }
+            const float l1 = lg[1], l0 = v0 ? lg[0] : -INFINITY, l2 = v2 ? lg[2] : -INFINITY;
+            const float mx = fmaxf(l1, fmaxf(l0, l2));
+            const float e0 = v0 ? expf(l0 - mx) : 0.f, e1 = expf(l1 - mx), e2 = v2 ? expf(l2 - mx) : 0.f;
+            const float wn = wk_n / (e0 + e1 + e2);
+            w0 = wn * e0; w1 = wn * e1; w2 = wn * e2;
+        }
+        const float c0 = warp_sum(w0), c1 = warp_sum(w1), c2 = warp_sum(w2);
+        const float* xm = s_x + (r + 1) * LDZ;          // row t
         float v[8];
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             const int c = half * 128 + lane * 4;
             const float4 x1 = *reinterpret_cast<const float4*>(xm + c);
             float4 y = make_float4(c1 * x1.x, c1 * x1.y, c1 * x1.z, c1 * x1.w);
-            if (t > 0) {
+            if (v0) {
                 const float4 x0 = *reinterpret_cast<const float4*>(xm - LDZ + c);
                 y.x = fmaf(c0, x0.x, y.x); y.y = fmaf(c0, x0.y, y.y); y.z = fmaf(c0, x0.z, y.z); y.w = fmaf(c0, x0.w, y.w);
             }
-            if (t < T - 1) {
+            if (v2) {
                 const float4 x2 = *reinterpret_cast<const float4*>(xm + LDZ + c);
                 y.x = fmaf(c2, x2.x, y.x); y.y = fmaf(c2, x2.y, y.y); y.z = fmaf(c2, x2.z, y.z); y.w = fmaf(c2, x2.w, y.w);
             }
@@ -503,7 +589,7 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             const int c = half * 128 + lane * 4;
-            const float4 w4 = *reinterpret_cast<const float4*>(lnw + c), b4 = *reinterpret_cast<const float4*>(lnb + c);
+            const float4 w4 = *reinterpret_cast<const float4*>(s_par + 2 * D + c), b4 = *reinterpret_cast<const float4*>(s_par + 3 * D + c);
             float4 o;
             o.x = (v[half * 4 + 0] - mean) * rstd * w4.x + b4.x; o.y = (v[half * 4 + 1] - mean) * rstd * w4.y + b4.y;
             o.z = (v[half * 4 + 2] - mean) * rstd * w4.z + b4.z; o.w = (v[half * 4 + 3] - mean) * rstd * w4.w + b4.w;
@@ -511,7 +597,10 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
         }
     }
     __syncthreads();
-    cross_attention_tail(s_x1, s_kp, s_kc, s_v, s_a, s_z, nr, HT, Tk, H, bo2, ln2w, ln2b, out, out_b, out_s, (size_t)b * T + r0);
+    ATRACE(6);
+    cross_attention_tail(s_x1, s_kp, s_kc, s_v, s_a, s_z, nr, HT, Tk, H, s_par + 4 * D, s_par + 5 * D, s_par + 6 * D, out, out_b, out_s,
+                         (size_t)b * T + r0, true);
+    ATRACE(11);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -656,6 +745,11 @@ __global__ void __launch_bounds__(256) k_step_io(const StepIO a) {
 }
 
 }  // namespace
+
+extern "C" int idb_debug_attn_trace(long long* out16) {
+    if (!out16) return IDB_ERR_ARG;
+    return cudaMemcpyFromSymbol(out16, g_attn_trace, sizeof(long long) * 16) == cudaSuccess ? IDB_OK : IDB_ERR_CUDA;
+}
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -1003,15 +1097,16 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
     return IDB_OK;
 }
 
-static size_t attn_smem(int Tk, int H) {
-    return sizeof(float) * ((size_t)SLAB * LDZ + (size_t)H * Tk * (HD + 4) + (size_t)SLAB * H * Tk + (size_t)SLAB * LDZ + (size_t)H * Tk * D);
+static size_t attn_smem(int Tk, int H) {   // barriers, 3 parameter rows, s_q, s_k, s_a, s_z, s_v
+    return sizeof(float) * (4 + 3 * D + (size_t)SLAB * LDZ + (size_t)H * Tk * (HD + 4) + (size_t)SLAB * H * Tk + (size_t)SLAB * LDZ + (size_t)H * Tk * D);
 }
 static size_t xattn_tail_smem(int Tk, int H) {   // s_x1, s_kp, s_v, s_a, s_z, s_kc
     const size_t HT = (size_t)H * Tk;
     return sizeof(float) * ((size_t)SLAB * LDZ + HT * LDZ + HT * D + HT * SLAB + (size_t)SLAB * LDZ + HT + 4);
 }
-static size_t qan_smem(int Tk, int H) {
-    return sizeof(float) * ((size_t)(SLAB + 2) * LDZ + 32 * LDZ + SLAB * 32 + SLAB * 4) + xattn_tail_smem(Tk, H);
+static size_t xattn_smem(int Tk, int H) { return sizeof(float) * (4 + 3 * D) + xattn_tail_smem(Tk, H); }
+static size_t qan_smem(int Tk, int H) {      // barriers, 7 parameter rows, s_x, s_qt + the cross-attention buffers
+    return sizeof(float) * (4 + 7 * D + (size_t)(SLAB + 2) * LDZ + 30 * LDZ) + xattn_tail_smem(Tk, H);
 }
 
 // One nn.Linear on fp16 (hi, lo) operand pairs; output as full fp32 and/or as a pair.
@@ -1041,7 +1136,7 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
         if (L.qan) {
             const float* in = pending ? d.z : d.h;
             // QaN block + LN1 + cross-attention + LN2 in one kernel: (z | h) -> (d.h2, pairs)
-            idb_launch(pdl, k_qan_xattn_ln, slab_grid, 256, qan_smem(Tm, H), st, in, pending ? pending->ln3w : nullptr,
+            idb_launch(pdl, k_qan_xattn_ln, slab_grid, ANT, qan_smem(Tm, H), st, in, pending ? pending->ln3w : nullptr,
                        pending ? pending->ln3b : nullptr, L.qt, L.wk, L.ln1w, L.ln1b, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc,
                        L.ln2w, L.ln2b, d.h2, d.h2_b, d.h2_s, T, N, B, Tm, H);
             LAUNCH_CHECK(h);
@@ -1053,11 +1148,11 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
             const int NQ = 2 * D + H * D;
             if ((rc = linear(h, d.h_b, d.h_s, D, L.w_qkvf_b, L.w_qkvf_s, D, L.b_qkvf, nullptr, d.qkv, nullptr, nullptr, NQ, M, NQ, D,
                              EPI_BIAS, st))) return rc;
-            idb_launch(pdl, k_attn_ln, slab_grid, 256, attn_smem(T, H), st, d.qkv, NQ, d.qkv + D, NQ, d.qkv + 2 * D, NQ, T, 1, d.h,
-                       L.bo_f, L.ln1w, L.ln1b, d.qc, nullptr, nullptr, T, T, H);
+            idb_launch(pdl, k_attn_ln, slab_grid, ANT, attn_smem(T, H), st, d.qkv, NQ, d.qkv + D, NQ, d.qkv + 2 * D, NQ, d.h,
+                       L.bo_f, L.ln1w, L.ln1b, d.qc, nullptr, nullptr, T, H);
             LAUNCH_CHECK(h);
             // cross attention on the LN1 rows (d.qc) -> (d.h2, pairs)
-            idb_launch(pdl, k_xattn_ln, slab_grid, 256, xattn_tail_smem(Tm, H), st, d.qc, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc,
+            idb_launch(pdl, k_xattn_ln, slab_grid, ANT, xattn_smem(Tm, H), st, d.qc, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc,
                        L.ln2w, L.ln2b, d.h2, d.h2_b, d.h2_s, T, B, Tm, H);
             LAUNCH_CHECK(h);
         }
@@ -1162,7 +1257,7 @@ int idb_denoiser_run(idb_handle* h, const float* x, const long long* tstep, cons
 int idb_denoiser_prepare_kernels(idb_handle* h) {
     // opt in to > 48 KB dynamic shared memory once (T <= 36, Tm <= 16 supported: the self-attention slab kernel keeps all folded values of a sample, 4*T*256 floats, in shared memory)
     CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem(16, 4)));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_tail_smem(16, 4)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_smem(16, 4)));
     CUDA_TRY(h, cudaFuncSetAttribute(k_attn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(36, 4)));
     return IDB_OK;
 }

@@ -307,52 +307,64 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
     }
 }
 
-// Register-tiled dot products between two sets of 256-wide rows held in shared memory (row stride
-// LDZ):  part[ks][r][j] = sum_{d in k-slice ks} A[r][d] * Bm[j][d].   No shuffles: a lane owns
-// TR x TJ outputs (rows rl + 4v of its warp's row group, columns jl + 8u of its column group) and
-// walks a 64-wide k-slice; the 16 warps are 4 k-slices x NRG row groups x NCG column groups.
-// Consecutive rows / columns across the lanes land in distinct 16-byte bank groups (LDZ = 260), so
-// every LDS.128 is one wavefront, and the FMA to LDS ratio is 4*TR*TJ : TR+TJ.  Rows >= nA /
-// columns >= nB are clamped for the loads and not stored.  The caller sums the 4 k-slices in a
-// fixed order (deterministic).  part: [4][4*TR*NRG][LDP], written at column offset pcol0.
-template <int TR, int TJ, int NRG, int NCG, int LDP>
-__device__ __forceinline__ void tile_dots(const float* __restrict__ sA, int nA, const float* __restrict__ sB, int nB,
-                                          float* __restrict__ part, int pcol0, int warp, int lane) {
-    static_assert(NRG * NCG == 4, "16 warps = 4 k-slices x 4 (row, column) groups");
-    constexpr int ROWS = 4 * TR * NRG;
-    const int jl = lane & 7, rl = lane >> 3, ks = warp & 3, rg = (warp >> 2) % NRG, cg = (warp >> 2) / NRG;
-    const int row0 = rg * 4 * TR + rl, col0 = cg * 8 * TJ + jl;
-    const float* ap[TR];
-    const float* bp[TJ];
-#pragma unroll
-    for (int v = 0; v < TR; v++) ap[v] = sA + min(row0 + 4 * v, nA - 1) * LDZ + ks * 64;
-#pragma unroll
-    for (int u = 0; u < TJ; u++) bp[u] = sB + min(col0 + 8 * u, nB - 1) * LDZ + ks * 64;
-    float acc[TR][TJ];
-#pragma unroll
-    for (int v = 0; v < TR; v++)
-#pragma unroll
-        for (int u = 0; u < TJ; u++) acc[v][u] = 0.f;
-#pragma unroll 4
-    for (int q = 0; q < 16; q++) {
-        float4 a[TR], bq[TJ];
-#pragma unroll
-        for (int v = 0; v < TR; v++) a[v] = *reinterpret_cast<const float4*>(ap[v] + q * 4);
-#pragma unroll
-        for (int u = 0; u < TJ; u++) bq[u] = *reinterpret_cast<const float4*>(bp[u] + q * 4);
-#pragma unroll
-        for (int v = 0; v < TR; v++)
-#pragma unroll
-            for (int u = 0; u < TJ; u++) {
-                acc[v][u] = fmaf(a[v].x, bq[u].x, acc[v][u]); acc[v][u] = fmaf(a[v].y, bq[u].y, acc[v][u]);
-                acc[v][u] = fmaf(a[v].z, bq[u].z, acc[v][u]); acc[v][u] = fmaf(a[v].w, bq[u].w, acc[v][u]);
-            }
-    }
-#pragma unroll
-    for (int v = 0; v < TR; v++)
-#pragma unroll
-        for (int u = 0; u < TJ; u++)
-            if (col0 + 8 * u < nB) part[(ks * ROWS + row0 + 4 * v) * LDP + pcol0 + col0 + 8 * u] = acc[v][u];
+// --- 16-row tensor-core fragments.  The three small products of the fused QaN / cross-attention kernel
+// ([18 x 256] x [256 x 30], [16 x 256] x [256 x 40], [16 x 40] x [40 x 256]) are far too small for a
+// tcgen05 tile (M = 128) but are exactly one mma.sync m16n8k16 row block.  fp32 operands are read from
+// shared memory straight into fragments (row strides of 8 mod 32 floats for the float2 k-pairs, 4 mod 16
+// for the K x N values, make every fragment load conflict-free), split on the fly into the same fp16
+// (hi, lo * 2^11) pairs as the big GEMMs and multiplied as hi*hi (main accumulator) and lo*hi + hi*lo
+// (small accumulator, folded in with 2^-11): fp32-grade, ~3e-7 over K = 256 with the 4-way k-split.
+// History (profiles/README.md): the register-tiled SIMT version was bound by shared-memory wavefronts
+// (4-way replays of its 128-bit operand loads); a 3xTF32 m16n8k8 version was no faster because legacy
+// TF32 mma.sync issues at ~30 cycles per instruction and scheduler on this part (= the FFMA rate).
+constexpr int LDX = D + 8;     // row stride of fragment-A / row-dot operands (x rows, folded queries / keys): 8 mod 32
+constexpr int VLD = D + 4;     // row stride of the folded values (K x N fragments): 4 mod 16
+constexpr int PLD = 72;        // row stride of the probabilities: 8 mod 32
+constexpr int XLDP = 64;       // row stride of the cross-attention logit partials
+constexpr int P1LD = 32;       // row stride of the QaN logit partials
+
+__device__ __forceinline__ uint32_t h2u(const __half2& h) { return *reinterpret_cast<const uint32_t*>(&h); }
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+    __half2 h, l;
+    split_f16x2(x, y, h, l);
+    hi = h2u(h); lo = h2u(l);
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// main += hi*hi ; small += lo*hi + hi*lo   (result = main + small / 2048)
+__device__ __forceinline__ void mma_pairs(float (&cm)[4], float (&cs)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                          const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    mma_f16(cs, al, bh); mma_f16(cs, ah, bl); mma_f16(cm, ah, bh);
+}
+// A fragment (16 x 16): rows row0 + g, row0 + g + 8 (clamped to nrows - 1), k-pairs k0 + 2c, k0 + 2c + 8
+__device__ __forceinline__ void load_a_frag(const float* __restrict__ s, int ld, int row0, int nrows, int k0, int lane,
+                                            uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+    const int g = lane >> 2, c = lane & 3;
+    const float* p0 = s + min(row0 + g, nrows - 1) * ld + k0 + 2 * c;
+    const float* p1 = s + min(row0 + g + 8, nrows - 1) * ld + k0 + 2 * c;
+    const float2 v0 = *reinterpret_cast<const float2*>(p0), v1 = *reinterpret_cast<const float2*>(p1);
+    const float2 v2 = *reinterpret_cast<const float2*>(p0 + 8), v3 = *reinterpret_cast<const float2*>(p1 + 8);
+    split_pair(v0.x, v0.y, hi[0], lo[0]); split_pair(v1.x, v1.y, hi[1], lo[1]);
+    split_pair(v2.x, v2.y, hi[2], lo[2]); split_pair(v3.x, v3.y, hi[3], lo[3]);
+}
+// B fragment (16 x 8) of "dot products against the rows of Mx": B[k][n] = Mx[n0 + n][k0 + k]   (rows clamped)
+__device__ __forceinline__ void load_b_frag_rows(const float* __restrict__ s, int ld, int n0, int nrows, int k0, int lane,
+                                                 uint32_t (&hi)[2], uint32_t (&lo)[2]) {
+    const float* p = s + min(n0 + (lane >> 2), nrows - 1) * ld + k0 + 2 * (lane & 3);
+    const float2 v0 = *reinterpret_cast<const float2*>(p), v1 = *reinterpret_cast<const float2*>(p + 8);
+    split_pair(v0.x, v0.y, hi[0], lo[0]); split_pair(v1.x, v1.y, hi[1], lo[1]);
+}
+// B fragment (16 x 8) of a row-major K x N matrix: B[k][n] = Mx[k0 + k][n0 + n]   (rows clamped to nk - 1)
+__device__ __forceinline__ void load_b_frag_cols(const float* __restrict__ s, int ld, int k0, int nk, int n0, int lane,
+                                                 uint32_t (&hi)[2], uint32_t (&lo)[2]) {
+    const int g = lane >> 2, c = lane & 3;
+    const float* q = s + n0 + g;
+    const int r = k0 + 2 * c;
+    split_pair(q[min(r, nk - 1) * ld], q[min(r + 1, nk - 1) * ld], hi[0], lo[0]);
+    split_pair(q[min(r + 8, nk - 1) * ld], q[min(r + 9, nk - 1) * ld], hi[1], lo[1]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -360,24 +372,49 @@ __device__ __forceinline__ void tile_dots(const float* __restrict__ sA, int nA, 
 //   logit[t,h,j] = x1[t] . kp[h,j] + kc[h,j]      kp = (K_h Wq_h)/8 (256-vector), kc = (bq_h . K_h)/8
 //   out[t] = LN2( x1[t] + bo + sum_{h,j} softmax_j(logit)[t,h,j] vp[h,j] )      vp = V_h Wo_h^T
 // so no query GEMM is needed and the block can run right after the layer's first sub-block while its
-// x1 rows are still in shared memory.  s_kp [HT][LDZ], s_kc [HT], s_v [HT][D] and the parameter rows
+// x1 rows are still in shared memory.  s_kp [HT][LDZ], s_kc [HT], s_v [HT][VLD] and the parameter rows
 // s_bo / s_lnw / s_lnb must already be staged.  Tk <= 16, H*Tk <= 64.
-constexpr int XLDP = 64;
 __device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s_x1, const float* __restrict__ s_kp,
                                                      const float* __restrict__ s_kc, const float* __restrict__ s_v,
-                                                     float* __restrict__ s_a, float* __restrict__ s_z, int nr, int HT, int Tk, int H,
+                                                     float* __restrict__ s_p, float* __restrict__ s_z, int nr, int HT, int Tk, int H,
                                                      const float* __restrict__ s_bo, const float* __restrict__ s_lnw,
                                                      const float* __restrict__ s_lnb, float* __restrict__ out,
                                                      __half* __restrict__ out_b, __half* __restrict__ out_s, size_t row0,
                                                      bool trace = false) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // logits: k-split partial tiles in s_z (free until the value pass), 40 folded keys per pass
-    for (int j0 = 0; j0 < HT; j0 += 40)
-        tile_dots<1, 5, 4, 1, XLDP>(s_x1, nr, s_kp + j0 * LDZ, min(40, HT - j0), s_z, j0, warp, lane);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+    // logits: warp (ks = warp & 3, ng = warp >> 2) accumulates the 8-key column tiles ng and ng + 4 over the
+    // 16-wide k-steps [4 ks, 4 ks + 4); the k-slice partial tiles go to s_z (free until the value pass)
+    {
+        const int ks = warp & 3, ng = warp >> 2, ntiles = (HT + 7) >> 3;
+        const bool t1 = ng + 4 < ntiles;
+        if (ng < ntiles) {
+            float m0[4] = {0.f, 0.f, 0.f, 0.f}, m1[4] = {0.f, 0.f, 0.f, 0.f}, q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+            for (int kk = ks * 4; kk < ks * 4 + 4; kk++) {
+                uint32_t ah[4], al[4], bh[2], bl[2];
+                load_a_frag(s_x1, LDX, 0, nr, kk * 16, lane, ah, al);
+                load_b_frag_rows(s_kp, LDX, ng * 8, HT, kk * 16, lane, bh, bl);
+                mma_pairs(m0, q0, ah, al, bh, bl);
+                if (t1) {
+                    load_b_frag_rows(s_kp, LDX, (ng + 4) * 8, HT, kk * 16, lane, bh, bl);
+                    mma_pairs(m1, q1, ah, al, bh, bl);
+                }
+            }
+            const float sc = 1.0f / 2048.0f;
+            float* pp = s_z + (ks * SLAB + g) * XLDP + ng * 8 + 2 * c;
+            *reinterpret_cast<float2*>(pp) = make_float2(fmaf(q0[0], sc, m0[0]), fmaf(q0[1], sc, m0[1]));
+            *reinterpret_cast<float2*>(pp + 8 * XLDP) = make_float2(fmaf(q0[2], sc, m0[2]), fmaf(q0[3], sc, m0[3]));
+            if (t1) {
+                *reinterpret_cast<float2*>(pp + 32) = make_float2(fmaf(q1[0], sc, m1[0]), fmaf(q1[1], sc, m1[1]));
+                *reinterpret_cast<float2*>(pp + 8 * XLDP + 32) = make_float2(fmaf(q1[2], sc, m1[2]), fmaf(q1[3], sc, m1[3]));
+            }
+        }
+    }
     __syncthreads();
     if (trace) ATRACE(7);
     // 16-lane group per (row, head): fixed-order sum of the 4 k-slices + constant term, softmax over the
-    // Tk memory slots with shuffles, probabilities stored transposed ([hj][row]) for the value pass
+    // Tk memory slots with shuffles; probabilities row-major [row][hj] (zero for rows >= nr and for the
+    // padding columns up to a multiple of 16) as the A operand of the value product
     {
         const int l16 = tid & 15;
         for (int p = tid >> 4; p < SLAB * H; p += ANT / 16) {
@@ -395,12 +432,43 @@ __device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s
             float sum = e;
 #pragma unroll
             for (int o = 8; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (on) s_a[hj * SLAB + r] = r < nr ? e / sum : 0.f;
+            if (on) s_p[r * PLD + hj] = r < nr ? e / sum : 0.f;
         }
+        const int pad = ((HT + 15) & ~15) - HT;
+        for (int i = tid; i < SLAB * pad; i += ANT) s_p[(i / pad) * PLD + HT + i % pad] = 0.f;
     }
     __syncthreads();
     if (trace) ATRACE(8);
-    weighted_values(s_a, s_v, HT, s_bo, s_x1, s_z, nr, tid);
+    // values: z[16 x 256] = P[16 x HT] V'[HT x 256]; warp w owns output columns 16w .. 16w+15 (two n-tiles),
+    // then bias + residual straight from the accumulator fragments
+    {
+        float m0[4] = {0.f, 0.f, 0.f, 0.f}, m1[4] = {0.f, 0.f, 0.f, 0.f}, q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f};
+        const int n0 = warp * 16, nks = (HT + 15) >> 4;
+        for (int kk = 0; kk < nks; kk++) {
+            uint32_t ah[4], al[4], bh[2], bl[2];
+            load_a_frag(s_p, PLD, 0, SLAB, kk * 16, lane, ah, al);
+            load_b_frag_cols(s_v, VLD, kk * 16, HT, n0, lane, bh, bl);
+            mma_pairs(m0, q0, ah, al, bh, bl);
+            load_b_frag_cols(s_v, VLD, kk * 16, HT, n0 + 8, lane, bh, bl);
+            mma_pairs(m1, q1, ah, al, bh, bl);
+        }
+        const float sc = 1.0f / 2048.0f;
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const float* am = t ? m1 : m0;
+            const float* aq = t ? q1 : q0;
+            const int n = n0 + t * 8 + 2 * c;
+            const float2 bb = *reinterpret_cast<const float2*>(s_bo + n);
+            if (g < nr) {
+                const float2 rr = *reinterpret_cast<const float2*>(s_x1 + g * LDX + n);
+                *reinterpret_cast<float2*>(s_z + g * LDZ + n) = make_float2((fmaf(aq[0], sc, am[0]) + bb.x) + rr.x, (fmaf(aq[1], sc, am[1]) + bb.y) + rr.y);
+            }
+            if (g + 8 < nr) {
+                const float2 rr = *reinterpret_cast<const float2*>(s_x1 + (g + 8) * LDX + n);
+                *reinterpret_cast<float2*>(s_z + (g + 8) * LDZ + n) = make_float2((fmaf(aq[2], sc, am[2]) + bb.x) + rr.x, (fmaf(aq[3], sc, am[3]) + bb.y) + rr.y);
+            }
+        }
+    }
     __syncthreads();
     if (trace) ATRACE(9);
     for (int r = warp; r < nr; r += ANW) {
@@ -417,8 +485,8 @@ __device__ __forceinline__ void stage_memory(const float* __restrict__ kp, const
     for (int i = tid; i < 2 * HT; i += ANT) {
         const int hj = i < HT ? i : i - HT, hh = hj / Tk, j = hj - hh * Tk;
         const size_t row = (size_t)(j * B + b) * H * D + (size_t)hh * D;
-        if (i < HT) bulk_g2s(s_kp + hj * LDZ, kp + row, ROW_BYTES, bar);
-        else bulk_g2s(s_v + (size_t)hj * D, vp + row, ROW_BYTES, bar);
+        if (i < HT) bulk_g2s(s_kp + hj * LDX, kp + row, ROW_BYTES, bar);
+        else bulk_g2s(s_v + (size_t)hj * VLD, vp + row, ROW_BYTES, bar);
     }
     for (int hj = tid; hj < HT; hj += ANT) s_kc[hj] = kc[(size_t)((hj % Tk) * B + b) * H + hj / Tk];
 }
@@ -432,11 +500,11 @@ k_xattn_ln(const float* __restrict__ x1, const float* __restrict__ kp, const flo
     const int HT = H * Tk;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: step-invariant tensors, [1]: input rows
     float* s_par = sm + 4;                  // bo, lnw, lnb
-    float* s_x1 = s_par + 3 * D;            // [SLAB][LDZ]
-    float* s_kp = s_x1 + SLAB * LDZ;        // [HT][LDZ]
-    float* s_v = s_kp + HT * LDZ;           // [HT][D]
-    float* s_a = s_v + HT * D;              // [HT][SLAB]
-    float* s_z = s_a + HT * SLAB;           // [SLAB][LDZ]
+    float* s_x1 = s_par + 3 * D;            // [SLAB][LDX]
+    float* s_kp = s_x1 + SLAB * LDX;        // [HT][LDX]
+    float* s_v = s_kp + HT * LDX;           // [HT][VLD]
+    float* s_a = s_v + HT * VLD;            // [SLAB][PLD]     probabilities
+    float* s_z = s_a + SLAB * PLD;          // [SLAB][LDZ]
     float* s_kc = s_z + SLAB * LDZ;         // [HT]
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
     pdl_trigger();
@@ -454,7 +522,7 @@ k_xattn_ln(const float* __restrict__ x1, const float* __restrict__ kp, const flo
     pdl_wait();
     if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)nr * ROW_BYTES);
     __syncwarp();
-    if (tid < nr) bulk_g2s(s_x1 + tid * LDZ, x1 + (size_t)(b * T + r0 + tid) * D, ROW_BYTES, bar + 1);
+    if (tid < nr) bulk_g2s(s_x1 + tid * LDX, x1 + (size_t)(b * T + r0 + tid) * D, ROW_BYTES, bar + 1);
     mb_wait(bar, 0);
     mb_wait(bar + 1, 0);
     __syncthreads();     // s_kc was written with plain stores
@@ -481,13 +549,13 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     const int HT = H * Tk, NQ = 3 * N;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: step-invariant tensors, [1]: input rows
     float* s_par = sm + 4;                  // pre w, pre b, ln1 w, ln1 b, bo2, ln2 w, ln2 b
-    float* s_x = s_par + 7 * D;             // [SLAB+2][LDZ]   rows r0-1 .. r0+nr
-    float* s_qt = s_x + (SLAB + 2) * LDZ;   // [30][LDZ]
-    float* s_x1 = s_qt + 30 * LDZ;          // [SLAB][LDZ]     LN1 rows (input of the cross-attention block)
-    float* s_kp = s_x1 + SLAB * LDZ;        // [HT][LDZ]
-    float* s_v = s_kp + HT * LDZ;           // [HT][D]
-    float* s_a = s_v + HT * D;              // [HT][SLAB]
-    float* s_z = s_a + HT * SLAB;           // [SLAB][LDZ]
+    float* s_x = s_par + 7 * D;             // [SLAB+2][LDX]   rows r0-1 .. r0+nr
+    float* s_qt = s_x + (SLAB + 2) * LDX;   // [30][LDX]
+    float* s_x1 = s_qt + 30 * LDX;          // [SLAB][LDX]     LN1 rows (input of the cross-attention block)
+    float* s_kp = s_x1 + SLAB * LDX;        // [HT][LDX]
+    float* s_v = s_kp + HT * LDX;           // [HT][VLD]
+    float* s_a = s_v + HT * VLD;            // [SLAB][PLD]     probabilities
+    float* s_z = s_a + SLAB * PLD;          // [SLAB][LDZ]
     float* s_kc = s_z + SLAB * LDZ;         // [HT]
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -509,7 +577,7 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
         const float* src = tid == 0 ? prew : tid == 1 ? preb : tid == 2 ? lnw : tid == 3 ? lnb : tid == 4 ? bo2 : tid == 5 ? ln2w : ln2b;
         if (src) bulk_g2s(s_par + tid * D, src, ROW_BYTES, bar);
     } else if (tid >= 32 && tid < 32 + NQ) {
-        bulk_g2s(s_qt + (tid - 32) * LDZ, qt + (size_t)(tid - 32) * D, ROW_BYTES, bar);
+        bulk_g2s(s_qt + (tid - 32) * LDX, qt + (size_t)(tid - 32) * D, ROW_BYTES, bar);
     }
     stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H, bar);
     const float wk_n = lane < N ? wk[lane] : 0.f;
@@ -521,7 +589,7 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
         if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)(t_hi - t_lo + 1) * ROW_BYTES);
         __syncwarp();
         const int t = r0 - 1 + tid;
-        if (tid < nr + 2 && t >= 0 && t < T) bulk_g2s(s_x + tid * LDZ, zin + (size_t)(b * T + t) * D, ROW_BYTES, bar + 1);
+        if (tid < nr + 2 && t >= 0 && t < T) bulk_g2s(s_x + tid * LDX, zin + (size_t)(b * T + t) * D, ROW_BYTES, bar + 1);
     }
     mb_wait(bar, 0);
     mb_wait(bar + 1, 0);
@@ -530,14 +598,34 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     if (prew) {   // the previous layer's pending LayerNorm3, in place on the staged rows
         for (int l = warp; l < nr + 2; l += ANW) {
             const int t = r0 - 1 + l;
-            if (t >= 0 && t < T) warp_ln_row(s_x + l * LDZ, s_par, s_par + D, s_x + l * LDZ, lane);
+            if (t >= 0 && t < T) warp_ln_row(s_x + l * LDX, s_par, s_par + D, s_x + l * LDX, lane);
         }
         __syncthreads();
     }
     // part[ks][l][j] = (k-slice of) x[row l] . Qt[j] for all nr+2 staged rows and the 3N folded queries
-    // (register-tiled, no shuffles); s_z is free until the cross-attention block and holds the partials.
+    // on the tensor cores (fp16-pair fragments); s_z is free until the cross-attention block and holds the partials.
     ATRACE(4);
-    tile_dots<3, 2, 2, 2, 40>(s_x, nr + 2, s_qt, NQ, s_z, 0, warp, lane);
+    {
+        // warp (mt = warp & 1, np = (warp >> 1) & 1, ks = warp >> 2): row tile mt (rows 16 mt ..), query tiles
+        // 2 np, 2 np + 1, 16-wide k-steps [4 ks, 4 ks + 4)
+        const int mt = warp & 1, np = (warp >> 1) & 1, ks = warp >> 2, g = lane >> 2, c = lane & 3;
+        float m0[4] = {0.f, 0.f, 0.f, 0.f}, m1[4] = {0.f, 0.f, 0.f, 0.f}, q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int kk = ks * 4; kk < ks * 4 + 4; kk++) {
+            uint32_t ah[4], al[4], bh[2], bl[2];
+            load_a_frag(s_x, LDX, mt * 16, nr + 2, kk * 16, lane, ah, al);
+            load_b_frag_rows(s_qt, LDX, np * 16, NQ, kk * 16, lane, bh, bl);
+            mma_pairs(m0, q0, ah, al, bh, bl);
+            load_b_frag_rows(s_qt, LDX, np * 16 + 8, NQ, kk * 16, lane, bh, bl);
+            mma_pairs(m1, q1, ah, al, bh, bl);
+        }
+        const float sc = 1.0f / 2048.0f;
+        float* pp = s_z + (ks * 32 + mt * 16 + g) * P1LD + np * 16 + 2 * c;
+        *reinterpret_cast<float2*>(pp) = make_float2(fmaf(q0[0], sc, m0[0]), fmaf(q0[1], sc, m0[1]));
+        *reinterpret_cast<float2*>(pp + 8 * P1LD) = make_float2(fmaf(q0[2], sc, m0[2]), fmaf(q0[3], sc, m0[3]));
+        *reinterpret_cast<float2*>(pp + 8) = make_float2(fmaf(q1[0], sc, m1[0]), fmaf(q1[1], sc, m1[1]));
+        *reinterpret_cast<float2*>(pp + 8 * P1LD + 8) = make_float2(fmaf(q1[2], sc, m1[2]), fmaf(q1[3], sc, m1[3]));
+    }
     __syncthreads();
     ATRACE(5);
     // One warp per output row: lane n < N sums the k-slices of its 3 slot logits (row l = r + slot feeds
@@ -551,8 +639,8 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
             float lg[3];
 #pragma unroll
             for (int sl = 0; sl < 3; sl++) {
-                const float* pp = s_z + (r + sl) * 40 + sl * N + lane;
-                lg[sl] = ((pp[0] + pp[24 * 40]) + pp[2 * 24 * 40]) + pp[3 * 24 * 40];
+                const float* pp = s_z + (r + sl) * P1LD + sl * N + lane;
+                lg[sl] = ((pp[0] + pp[32 * P1LD]) + pp[2 * 32 * P1LD]) + pp[3 * 32 * P1LD];
             }
             const float l1 = lg[1], l0 = v0 ? lg[0] : -INFINITY, l2 = v2 ? lg[2] : -INFINITY;
             const float mx = fmaxf(l1, fmaxf(l0, l2));
@@ -561,7 +649,7 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
             w0 = wn * e0; w1 = wn * e1; w2 = wn * e2;
         }
         const float c0 = warp_sum(w0), c1 = warp_sum(w1), c2 = warp_sum(w2);
-        const float* xm = s_x + (r + 1) * LDZ;          // row t
+        const float* xm = s_x + (r + 1) * LDX;          // row t
         float v[8];
 #pragma unroll
         for (int half = 0; half < 2; half++) {
@@ -569,11 +657,11 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
             const float4 x1 = *reinterpret_cast<const float4*>(xm + c);
             float4 y = make_float4(c1 * x1.x, c1 * x1.y, c1 * x1.z, c1 * x1.w);
             if (v0) {
-                const float4 x0 = *reinterpret_cast<const float4*>(xm - LDZ + c);
+                const float4 x0 = *reinterpret_cast<const float4*>(xm - LDX + c);
                 y.x = fmaf(c0, x0.x, y.x); y.y = fmaf(c0, x0.y, y.y); y.z = fmaf(c0, x0.z, y.z); y.w = fmaf(c0, x0.w, y.w);
             }
             if (v2) {
-                const float4 x2 = *reinterpret_cast<const float4*>(xm + LDZ + c);
+                const float4 x2 = *reinterpret_cast<const float4*>(xm + LDX + c);
                 y.x = fmaf(c2, x2.x, y.x); y.y = fmaf(c2, x2.y, y.y); y.z = fmaf(c2, x2.z, y.z); y.w = fmaf(c2, x2.w, y.w);
             }
             v[half * 4 + 0] = x1.x + y.x; v[half * 4 + 1] = x1.y + y.y; v[half * 4 + 2] = x1.z + y.z; v[half * 4 + 3] = x1.w + y.w;
@@ -593,7 +681,7 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
             float4 o;
             o.x = (v[half * 4 + 0] - mean) * rstd * w4.x + b4.x; o.y = (v[half * 4 + 1] - mean) * rstd * w4.y + b4.y;
             o.z = (v[half * 4 + 2] - mean) * rstd * w4.z + b4.z; o.w = (v[half * 4 + 3] - mean) * rstd * w4.w + b4.w;
-            *reinterpret_cast<float4*>(s_x1 + r * LDZ + c) = o;
+            *reinterpret_cast<float4*>(s_x1 + r * LDX + c) = o;
         }
     }
     __syncthreads();
@@ -1102,11 +1190,11 @@ static size_t attn_smem(int Tk, int H) {   // barriers, 3 parameter rows, s_q, s
 }
 static size_t xattn_tail_smem(int Tk, int H) {   // s_x1, s_kp, s_v, s_a, s_z, s_kc
     const size_t HT = (size_t)H * Tk;
-    return sizeof(float) * ((size_t)SLAB * LDZ + HT * LDZ + HT * D + HT * SLAB + (size_t)SLAB * LDZ + HT + 4);
+    return sizeof(float) * ((size_t)SLAB * (D + 8) + HT * (D + 8) + HT * (D + 4) + (size_t)SLAB * 72 + (size_t)SLAB * LDZ + HT + 4);
 }
 static size_t xattn_smem(int Tk, int H) { return sizeof(float) * (4 + 3 * D) + xattn_tail_smem(Tk, H); }
 static size_t qan_smem(int Tk, int H) {      // barriers, 7 parameter rows, s_x, s_qt + the cross-attention buffers
-    return sizeof(float) * (4 + 7 * D + (size_t)(SLAB + 2) * LDZ + 30 * LDZ) + xattn_tail_smem(Tk, H);
+    return sizeof(float) * (4 + 7 * D + (size_t)(SLAB + 2) * (D + 8) + 30 * (D + 8)) + xattn_tail_smem(Tk, H);
 }
 
 // One nn.Linear on fp16 (hi, lo) operand pairs; output as full fp32 and/or as a pair.

@@ -194,119 +194,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 constexpr uint32_t ROW_BYTES = D * sizeof(float);
 
-// z[r][n] = res[r][n] + bo[n] + sum_hj a[hj][r] * v[hj][n]  for the slab's 16 rows: thread (n = tid & 255,
-// half = tid >> 8) owns column n of rows 8*half .. 8*half+7 (rows >= nr carry zero weights).
-__device__ __forceinline__ void weighted_values(const float* __restrict__ s_a, const float* __restrict__ s_v, int HT,
-                                                const float* __restrict__ s_bo, const float* __restrict__ s_res,
-                                                float* __restrict__ s_z, int nr, int tid) {
-    const int n = tid & 255, r8 = (tid >> 8) * 8;
-    float acc[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) acc[r] = 0.f;
-#pragma unroll 4
-    for (int hj = 0; hj < HT; hj++) {
-        const float vv = s_v[(size_t)hj * D + n];
-        const float4* ap = reinterpret_cast<const float4*>(s_a + hj * SLAB + r8);
-        const float4 a0 = ap[0], a1 = ap[1];
-        acc[0] = fmaf(a0.x, vv, acc[0]); acc[1] = fmaf(a0.y, vv, acc[1]); acc[2] = fmaf(a0.z, vv, acc[2]); acc[3] = fmaf(a0.w, vv, acc[3]);
-        acc[4] = fmaf(a1.x, vv, acc[4]); acc[5] = fmaf(a1.y, vv, acc[5]); acc[6] = fmaf(a1.z, vv, acc[6]); acc[7] = fmaf(a1.w, vv, acc[7]);
-    }
-    const float bb = s_bo[n];
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-        if (r8 + r < nr) s_z[(r8 + r) * LDZ + n] = (acc[r] + bb) + s_res[(r8 + r) * LDZ + n];
-}
-
-// Self-attention core + out-projection (folded into the values) + residual + LayerNorm.
-// grid (B, ceil(T/16)), block 512.
-//   q rows  : q[(b*T + r) * ldq + h*64 + d]                          (pre-projected queries)
-//   keys    : k[(b*T + j) * ldk + h*64 + d], j < T
-//   values' : v[(b*T + j) * ldv + h*256 + n]  = (V_h W_o,h^T)[j][n]: value vectors already
-//             multiplied by the head's out-proj block
-//   out[r]  = LN( res[r] + bo + sum_h sum_j softmax_j(q_h[r].k_h[j] / 8) v'_h[j] )
-__global__ void __launch_bounds__(ANT)
-k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
-          const float* __restrict__ res, const float* __restrict__ bo, const float* __restrict__ lnw,
-          const float* __restrict__ lnb, float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s,
-          int T, int H) {
-    extern __shared__ __align__(16) float sm[];
-    const int LDK = HD + 4;
-    const int Tk = T, HT = H * Tk;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: parameters, [1]: activations
-    float* s_par = sm + 4;                 // bo, lnw, lnb
-    float* s_q = s_par + 3 * D;            // [SLAB][LDZ]  (padded rows: 16 query rows are read by one warp)
-    float* s_k = s_q + SLAB * LDZ;         // [H*Tk][LDK]
-    float* s_a = s_k + HT * LDK;           // [H*Tk][SLAB]  (transposed: the 16 rows of one (h,j) are contiguous)
-    float* s_z = s_a + SLAB * HT;          // [SLAB][LDZ]   residual rows, then the pre-LayerNorm sums
-    float* s_v = s_z + SLAB * LDZ;         // [H*Tk][D]     folded values
-    const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    pdl_trigger();
-    if (tid == 0) {
-        mb_init(bar, 1); mb_init(bar + 1, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        mb_expect_tx(bar, 3 * ROW_BYTES);
-        bulk_g2s(s_par, bo, ROW_BYTES, bar); bulk_g2s(s_par + D, lnw, ROW_BYTES, bar); bulk_g2s(s_par + 2 * D, lnb, ROW_BYTES, bar);
-    }
-    pdl_wait();
-    if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)(2 * nr + (H + 1) * Tk) * ROW_BYTES);
-    __syncwarp();
-    // one copy per thread and round: query + residual rows, key head slices (256 B), folded value rows
-    for (int i = tid; i < 2 * nr + 2 * HT; i += ANT) {
-        if (i < nr) bulk_g2s(s_q + i * LDZ, q + (size_t)(b * T + r0 + i) * ldq, ROW_BYTES, bar + 1);
-        else if (i < 2 * nr) bulk_g2s(s_z + (i - nr) * LDZ, res + (size_t)(b * T + r0 + i - nr) * D, ROW_BYTES, bar + 1);
-        else if (i < 2 * nr + HT) {
-            const int hj = i - 2 * nr, hh = hj / Tk, j = hj - hh * Tk;
-            bulk_g2s(s_k + hj * LDK, k + (size_t)(b * T + j) * ldk + hh * HD, HD * sizeof(float), bar + 1);
-        } else {
-            const int hj = i - 2 * nr - HT, hh = hj / Tk, j = hj - hh * Tk;
-            bulk_g2s(s_v + (size_t)hj * D, v + (size_t)(b * T + j) * ldv + hh * D, ROW_BYTES, bar + 1);
-        }
-    }
-    mb_wait(bar + 1, 0);
-    const float scale = 0.125f;   // 1/sqrt(64)
-    for (int i = tid; i < SLAB * HT; i += ANT) {
-        const int hj = i / SLAB, r = i % SLAB, hh = hj / Tk;
-        s_a[i] = r < nr ? dot64(s_q + r * LDZ + hh * HD, s_k + hj * LDK) * scale : 0.f;
-    }
-    __syncthreads();
-    // one warp per (row, head): softmax over the Tk keys (two pairs in flight per warp for latency)
-    for (int g = warp; g < nr * H; g += 2 * ANW) {
-        float* c0 = s_a + (g % H) * Tk * SLAB + (g / H);
-        const int g1 = g + ANW;
-        const bool two = g1 < nr * H;
-        float* c1 = two ? s_a + (g1 % H) * Tk * SLAB + (g1 / H) : c0;
-        const float a0 = lane < Tk ? c0[lane * SLAB] : -INFINITY, a1 = lane + 32 < Tk ? c0[(lane + 32) * SLAB] : -INFINITY;
-        const float b0 = lane < Tk ? c1[lane * SLAB] : -INFINITY, b1 = lane + 32 < Tk ? c1[(lane + 32) * SLAB] : -INFINITY;
-        float ma = fmaxf(a0, a1), mb = fmaxf(b0, b1);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o)); }
-        const float ea0 = lane < Tk ? expf(a0 - ma) : 0.f, ea1 = lane + 32 < Tk ? expf(a1 - ma) : 0.f;
-        const float eb0 = lane < Tk ? expf(b0 - mb) : 0.f, eb1 = lane + 32 < Tk ? expf(b1 - mb) : 0.f;
-        float sa = ea0 + ea1, sb = eb0 + eb1;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
-        const float ia = 1.0f / sa, ib = 1.0f / sb;
-        if (lane < Tk) c0[lane * SLAB] = ea0 * ia;
-        if (lane + 32 < Tk) c0[(lane + 32) * SLAB] = ea1 * ia;
-        if (two) {
-            if (lane < Tk) c1[lane * SLAB] = eb0 * ib;
-            if (lane + 32 < Tk) c1[(lane + 32) * SLAB] = eb1 * ib;
-        }
-    }
-    mb_wait(bar, 0);
-    __syncthreads();
-    weighted_values(s_a, s_v, HT, s_par, s_z, s_z, nr, tid);
-    __syncthreads();
-    for (int r = warp; r < nr; r += ANW) {
-        const size_t o = (size_t)(b * T + r0 + r) * D;
-        warp_ln_row(s_z + r * LDZ, s_par + D, s_par + 2 * D, out + o, lane, out_b ? out_b + o : nullptr, out_s ? out_s + o : nullptr);
-    }
-}
-
 // --- 16-row tensor-core fragments.  The three small products of the fused QaN / cross-attention kernel
 // ([18 x 256] x [256 x 30], [16 x 256] x [256 x 40], [16 x 40] x [40 x 256]) are far too small for a
 // tcgen05 tile (M = 128) but are exactly one mma.sync m16n8k16 row block.  fp32 operands are read from
@@ -365,6 +252,146 @@ __device__ __forceinline__ void load_b_frag_cols(const float* __restrict__ s, in
     const int r = k0 + 2 * c;
     split_pair(q[min(r, nk - 1) * ld], q[min(r + 1, nk - 1) * ld], hi[0], lo[0]);
     split_pair(q[min(r + 8, nk - 1) * ld], q[min(r + 9, nk - 1) * ld], hi[1], lo[1]);
+}
+
+// Self-attention core + out-projection (folded into the values) + residual + LayerNorm.
+// grid (B, ceil(T/16)), block 512.
+//   q rows  : q[(b*T + r) * ldq + h*64 + d]                          (pre-projected queries)
+//   keys    : k[(b*T + j) * ldk + h*64 + d], j < T
+//   values' : v[(b*T + j) * ldv + h*256 + n]  = (V_h W_o,h^T)[j][n]: value vectors already
+//             multiplied by the head's out-proj block
+//   out[r]  = LN( res[r] + bo + sum_h sum_j softmax_j(q_h[r].k_h[j] / 8) v'_h[j] )
+// Both products run on fp16-pair fragments: logits = 16 (head, 8-key tile) units of 4 k-steps, one
+// per warp; values = [16 x 4T] x [4T x 256], two 8-column tiles per warp.
+__global__ void __launch_bounds__(ANT)
+k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
+          const float* __restrict__ res, const float* __restrict__ bo, const float* __restrict__ lnw,
+          const float* __restrict__ lnb, float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s,
+          int T, int H) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int LDK = HD + 8;            // key-slice stride (8 mod 32)
+    const int Tk = T, HT = H * Tk, HT16 = (HT + 15) & ~15, pld = ((HT16 + 23) / 32) * 32 + 8;   // pld: >= HT16, 8 mod 32
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: parameters, [1]: activations
+    float* s_par = sm + 4;                 // bo, lnw, lnb
+    float* s_q = s_par + 3 * D;            // [SLAB][LDX]   query rows
+    float* s_z = s_q + SLAB * LDX;         // [SLAB][LDZ]   residual rows, then the pre-LayerNorm sums
+    float* s_v = s_z + SLAB * LDZ;         // [H*Tk][VLD]   folded values
+    float* s_k = s_v + (size_t)HT * VLD;   // [H*Tk][LDK]   key head slices ...
+    float* s_p = s_k;                      // [SLAB][pld]   ... then (after a barrier) logits / probabilities
+    const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+    pdl_trigger();
+    if (tid == 0) {
+        mb_init(bar, 1); mb_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mb_expect_tx(bar, 3 * ROW_BYTES);
+        bulk_g2s(s_par, bo, ROW_BYTES, bar); bulk_g2s(s_par + D, lnw, ROW_BYTES, bar); bulk_g2s(s_par + 2 * D, lnb, ROW_BYTES, bar);
+    }
+    pdl_wait();
+    if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)(2 * nr + (H + 1) * Tk) * ROW_BYTES);
+    __syncwarp();
+    // one copy per thread and round: query + residual rows, key head slices (256 B), folded value rows
+    for (int i = tid; i < 2 * nr + 2 * HT; i += ANT) {
+        if (i < nr) bulk_g2s(s_q + i * LDX, q + (size_t)(b * T + r0 + i) * ldq, ROW_BYTES, bar + 1);
+        else if (i < 2 * nr) bulk_g2s(s_z + (i - nr) * LDZ, res + (size_t)(b * T + r0 + i - nr) * D, ROW_BYTES, bar + 1);
+        else if (i < 2 * nr + HT) {
+            const int hj = i - 2 * nr, hh = hj / Tk, j = hj - hh * Tk;
+            bulk_g2s(s_k + hj * LDK, k + (size_t)(b * T + j) * ldk + hh * HD, HD * sizeof(float), bar + 1);
+        } else {
+            const int hj = i - 2 * nr - HT, hh = hj / Tk, j = hj - hh * Tk;
+            bulk_g2s(s_v + (size_t)hj * VLD, v + (size_t)(b * T + j) * ldv + hh * D, ROW_BYTES, bar + 1);
+        }
+    }
+    mb_wait(bar + 1, 0);
+    // logits: unit u = (head, 8-key tile); the accumulators stay in registers across the barrier that
+    // retires the key slices, then land (scaled by 1/sqrt(64)) in the same memory as [row][head*Tk + key]
+    const int ntk = (Tk + 7) >> 3, units = H * ntk;          // <= 20 for T <= 36: at most two units per warp
+    float lg[2][4];
+#pragma unroll
+    for (int uu = 0; uu < 2; uu++) {
+        const int u = warp + uu * ANW;
+        float m[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+        if (u < units) {
+            const int hh = u / ntk, nt = u - hh * ntk;
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; kk++) {
+                uint32_t ah[4], al[4], bh[2], bl[2];
+                load_a_frag(s_q, LDX, 0, nr, hh * HD + kk * 16, lane, ah, al);
+                load_b_frag_rows(s_k + (size_t)hh * Tk * LDK, LDK, nt * 8, Tk, kk * 16, lane, bh, bl);
+                mma_pairs(m, sq, ah, al, bh, bl);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) lg[uu][e] = fmaf(sq[e], 1.0f / 2048.0f, m[e]) * 0.125f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int uu = 0; uu < 2; uu++) {
+        const int u = warp + uu * ANW;
+        if (u < units) {
+            const int hh = u / ntk, nt = u - hh * ntk, j = nt * 8 + 2 * c;
+            float* pr = s_p + hh * Tk + j;
+            if (j < Tk) { pr[g * pld] = lg[uu][0]; pr[(g + 8) * pld] = lg[uu][2]; }
+            if (j + 1 < Tk) { pr[g * pld + 1] = lg[uu][1]; pr[(g + 8) * pld + 1] = lg[uu][3]; }
+        }
+    }
+    __syncthreads();
+    // one warp per (row, head): softmax over the Tk keys (contiguous); rows >= nr and the padding columns are zero
+    for (int p = warp; p < SLAB * H; p += ANW) {
+        const int r = p / H, hh = p - r * H;
+        float* row = s_p + r * pld + hh * Tk;
+        const float a0 = lane < Tk ? row[lane] : -INFINITY, a1 = lane + 32 < Tk ? row[lane + 32] : -INFINITY;
+        float mx = fmaxf(a0, a1);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e0 = lane < Tk ? expf(a0 - mx) : 0.f, e1 = lane + 32 < Tk ? expf(a1 - mx) : 0.f;
+        const float inv = r < nr ? 1.0f / warp_sum(e0 + e1) : 0.f;
+        if (lane < Tk) row[lane] = e0 * inv;
+        if (lane + 32 < Tk) row[lane + 32] = e1 * inv;
+    }
+    for (int i = tid; i < SLAB * (HT16 - HT); i += ANT) s_p[(i / (HT16 - HT)) * pld + HT + i % (HT16 - HT)] = 0.f;
+    mb_wait(bar, 0);
+    __syncthreads();
+    // values: z[16 x 256] = P[16 x HT] V'[HT x 256]; warp w owns output columns 16w .. 16w+15
+    {
+        float m0[4] = {0.f, 0.f, 0.f, 0.f}, m1[4] = {0.f, 0.f, 0.f, 0.f}, q0[4] = {0.f, 0.f, 0.f, 0.f}, q1[4] = {0.f, 0.f, 0.f, 0.f};
+        const int n0 = warp * 16;
+#pragma unroll 2
+        for (int kk = 0; kk < HT16 / 16; kk++) {
+            uint32_t ah[4], al[4], bh[2], bl[2];
+            load_a_frag(s_p, pld, 0, SLAB, kk * 16, lane, ah, al);
+            load_b_frag_cols(s_v, VLD, kk * 16, HT, n0, lane, bh, bl);
+            mma_pairs(m0, q0, ah, al, bh, bl);
+            load_b_frag_cols(s_v, VLD, kk * 16, HT, n0 + 8, lane, bh, bl);
+            mma_pairs(m1, q1, ah, al, bh, bl);
+        }
+        const float sc = 1.0f / 2048.0f;
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const float* am = t ? m1 : m0;
+            const float* aq = t ? q1 : q0;
+            const int n = n0 + t * 8 + 2 * c;
+            const float2 bb = *reinterpret_cast<const float2*>(s_par + n);
+            if (g < nr) {
+                float2* zz = reinterpret_cast<float2*>(s_z + g * LDZ + n);
+                const float2 rr = *zz;
+                *zz = make_float2((fmaf(aq[0], sc, am[0]) + bb.x) + rr.x, (fmaf(aq[1], sc, am[1]) + bb.y) + rr.y);
+            }
+            if (g + 8 < nr) {
+                float2* zz = reinterpret_cast<float2*>(s_z + (g + 8) * LDZ + n);
+                const float2 rr = *zz;
+                *zz = make_float2((fmaf(aq[2], sc, am[2]) + bb.x) + rr.x, (fmaf(aq[3], sc, am[3]) + bb.y) + rr.y);
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < nr; r += ANW) {
+        const size_t o = (size_t)(b * T + r0 + r) * D;
+        warp_ln_row(s_z + r * LDZ, s_par + D, s_par + 2 * D, out + o, lane, out_b ? out_b + o : nullptr, out_s ? out_s + o : nullptr);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1185,8 +1212,10 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
     return IDB_OK;
 }
 
-static size_t attn_smem(int Tk, int H) {   // barriers, 3 parameter rows, s_q, s_k, s_a, s_z, s_v
-    return sizeof(float) * (4 + 3 * D + (size_t)SLAB * LDZ + (size_t)H * Tk * (HD + 4) + (size_t)SLAB * H * Tk + (size_t)SLAB * LDZ + (size_t)H * Tk * D);
+static size_t attn_smem(int Tk, int H) {   // barriers, 3 parameter rows, s_q, s_z, s_v, s_k (reused for the probabilities)
+    const size_t HT = (size_t)H * Tk, HT16 = (HT + 15) & ~(size_t)15, pld = ((HT16 + 23) / 32) * 32 + 8;
+    const size_t kreg = HT * (HD + 8) > SLAB * pld ? HT * (HD + 8) : SLAB * pld;
+    return sizeof(float) * (4 + 3 * D + (size_t)SLAB * (D + 8) + (size_t)SLAB * LDZ + HT * (D + 4) + kreg);
 }
 static size_t xattn_tail_smem(int Tk, int H) {   // s_x1, s_kp, s_v, s_a, s_z, s_kc
     const size_t HT = (size_t)H * Tk;

@@ -421,8 +421,15 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
         const int gx = wide ? (N + 127) / 128 : (N + 63) / 64;
         if (g.zero_cols % (4 * gx) || (g.zero_ld & 3)) return idb_fail(h, IDB_ERR_ARG, "aux zero: %d columns do not split over %d column tiles", g.zero_cols, gx);
     }
-    int nacc = wide ? Cfg<128>::NACC_MAX : Cfg<64>::NACC_MAX;
-    if (g_idb_gemm_nacc > 0 && g_idb_gemm_nacc < nacc) nacc = g_idb_gemm_nacc;
+    // Round-robin main accumulators bound the tensor core's truncate-on-accumulate error; every one costs an
+    // extra TMEM read pass in the epilogue.  Two already beat the fp32 SIMT kernel up to 8 k-blocks per CTA
+    // (measured, profiles/README.md: 3.3e-7 at K=256, 4.1e-7 at K=1024 split in two, vs 5.5e-7 / 1.5e-6); longer
+    // reductions get one accumulator per 4 k-blocks up to the TMEM budget.
+    const int nacc_max = wide ? Cfg<128>::NACC_MAX : Cfg<64>::NACC_MAX;
+    const int kb_per_cta = ((K + BK - 1) / BK + ksplit - 1) / ksplit;
+    int nacc = kb_per_cta <= 8 ? 2 : (kb_per_cta + 3) / 4;
+    if (nacc > nacc_max) nacc = nacc_max;
+    if (g_idb_gemm_nacc > 0) nacc = g_idb_gemm_nacc < nacc_max ? g_idb_gemm_nacc : nacc_max;
     if (wide) {
         dim3 grid((N + 127) / 128, (M + BM - 1) / BM, ksplit);
         idb_launch(g.pdl != 0, gemm_split_f16_kernel<128>, grid, NUM_THREADS, Cfg<128>::SMEM_BYTES, st, ma, mw, mal, mwl, g.bias, g.res, g.ldr,

@@ -54,6 +54,24 @@ def test_denoiser_forward_T35(eng):
     assert rel(got, ref) < 2e-4
 
 
+@pytest.mark.parametrize("T,Tm", [(36, 16), (17, 3), (16, 9)])
+def test_denoiser_forward_window_extremes(eng, T, Tm):
+    """largest supported window / memory (maximum shared-memory footprint of the attention kernels, two
+    key tiles per warp group), a short odd one, and an exact single slab"""
+    sd = mdm_weights("smpl", "auto")
+    eng.load_denoiser(sd, "smpl")
+    B = 3
+    b = S.make_smpl_batch(B=B, T=T)
+    cond = np.random.default_rng(T * 100 + Tm).standard_normal((Tm, B, 256)).astype(np.float32)
+    eng.bind(cond, T)
+    x = torch.from_numpy(S.noise_tape(b["gt"].shape, 0)[0])
+    t = torch.tensor([640, 77, 0])
+    got = eng.forward(x.cuda(), t.cuda()).cpu()
+    with torch.no_grad():
+        ref = R.mdm_smpl_forward(sd, x, t, torch.from_numpy(cond), faithful=False)
+    assert rel(got, ref) < 2e-4
+
+
 @pytest.mark.parametrize("source", ["random", "ref"])
 def test_denoiser_forward_skeleton(eng, source):
     """BASELINE config 1: skeleton diffusion, B=2, T=15."""

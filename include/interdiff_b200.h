@@ -33,6 +33,9 @@ int idb_set_gemm_backend(idb_handle* h, int backend); /* 0 = fp32 SIMT (debug/bi
 /* Programmatic dependent launch between the kernels of a sampling step (default 1). Results are identical
    either way; 0 serialises the kernels (for bisecting / profiling). */
 int idb_set_dependent_launch(idb_handle* h, int on);
+/* Feed-forward block of a decoder layer as one cluster kernel (default 1; tensor backend, d_model 256, d_ff 1024);
+   0 = the two separate GEMMs (bisecting / profiling). */
+int idb_set_fused_mlp(idb_handle* h, int on);
 
 /* ---- denoiser: MDM.forward / MDM._decode --------------------------------------------------
  * replaces model/diffusion_smpl.py:239-246,226-237 (variant 0) and
@@ -149,6 +152,9 @@ int idb_debug_gemm_repeat(idb_handle* h, const float* A, const float* W, const f
 
 /* test hook: number of round-robin TMEM accumulators of the tcgen05 GEMM (0 = default) */
 int idb_debug_set_gemm_accumulators(int n);
+/* out[M][256] = gelu(x w1^T + b1) w2^T + b2 + res through the fused feed-forward kernel (fp32 device pointers) */
+int idb_debug_mlp(idb_handle* h, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                  const float* res, float* out, int M, void* stream);
 /* clock64 phase timeline (16 slots, host pointer) of CTA (0,0) of the last fused QaN + cross-attention kernel */
 int idb_debug_attn_trace(long long* out16);
 /* one launch with a per-CTA clock64 timeline (16 slots per CTA) of the tcgen05 kernel's pipeline */

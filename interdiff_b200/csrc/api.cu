@@ -58,6 +58,33 @@ extern "C" int idb_set_dependent_launch(idb_handle* h, int on) {
     return IDB_OK;
 }
 
+extern "C" int idb_set_fused_mlp(idb_handle* h, int on) {
+    if (!h) return IDB_ERR_ARG;
+    h->fused_mlp = on ? 1 : 0;
+    idb_sampler_drop_graphs(h);
+    return IDB_OK;
+}
+
+/* test hook: out[M][256] = gelu(x w1^T + b1) w2^T + b2 + res through the fused cluster kernel (fp32 device inputs,
+   x [M][256], w1 [1024][256], w2 [256][1024]); operands are split into fp16 pairs in temporary buffers */
+extern "C" int idb_debug_mlp(idb_handle* h, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                             const float* res, float* out, int M, void* stream) {
+    if (!h || !x || !w1 || !b1 || !w2 || !b2 || !res || !out || M <= 0) return IDB_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Dm = 256, F = 1024;
+    __half* buf = nullptr;
+    const size_t nx = (size_t)M * Dm, nw = (size_t)F * Dm;
+    CUDA_TRY(h, cudaMalloc((void**)&buf, sizeof(__half) * 2 * (nx + 2 * nw)));
+    __half *xh = buf, *xl = xh + nx, *w1h = xl + nx, *w1l = w1h + nw, *w2h = w1l + nw, *w2l = w2h + nw;
+    int rc = idb_split_tensor(h, x, Dm, xh, xl, Dm, M, Dm, st);
+    if (!rc) rc = idb_split_tensor(h, w1, Dm, w1h, w1l, Dm, F, Dm, st);
+    if (!rc) rc = idb_split_tensor(h, w2, F, w2h, w2l, F, Dm, F, st);
+    if (!rc) rc = idb_mlp_tcgen05(h, xh, xl, w1h, w1l, b1, w2h, w2l, b2, res, Dm, out, Dm, M, 0, st);
+    cudaStreamSynchronize(st);
+    cudaFree(buf);
+    return rc;
+}
+
 extern "C" int idb_debug_gemm(idb_handle* h, const float* A, const float* W, const float* bias, const float* res, float* C,
                               int M, int N, int K, int epi, void* stream) {
     if (!h || !A || !W || !C) return IDB_ERR_ARG;

@@ -96,6 +96,7 @@ struct idb_handle {
     long long launches = 0;   // kernels launched through this handle (bench's gpu_launches)
     int gemm_backend = 1;     // 0 = fp32 SIMT (debug / bisect), 1 = tcgen05 split-fp16 (default)
     int pdl = 1;              // programmatic dependent launch between the kernels of a sampling step
+    int fused_mlp = 1;        // feed-forward block as ONE cluster kernel (tensor backend, d_model 256, d_ff 1024)
     void* scratch = nullptr; size_t scratch_bytes = 0;   // on-the-fly operand splits of idb_gemm
     Denoiser den;
     Diffusion diff;
@@ -208,6 +209,11 @@ struct GemmArgs {
     int pdl = 0;   // 1: programmatic dependent launch; REQUIRES W_hi/W_lo to be complete before the previous kernel started
 };
 int idb_gemm_ex(idb_handle* h, const GemmArgs& g, cudaStream_t st);
+// fused feed-forward block on the tensor path (gemm_tcgen05.cu)
+bool idb_mlp_tcgen05_supported(int d_model, int d_ff);
+int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const __half* w1_hi, const __half* w1_lo, const float* b1,
+                    const __half* w2_hi, const __half* w2_lo, const float* b2, const float* res, int ldr, float* Z, int ldz, int M,
+                    int pdl, cudaStream_t st);
 // x[rows][cols] (row stride ld_src) -> fp16 pairs [rows][ld_dst] (columns >= cols zero-filled)
 int idb_split_tensor(idb_handle* h, const float* x, int ld_src, __half* hi, __half* lo, int ld_dst, int rows, int cols, cudaStream_t st);
 

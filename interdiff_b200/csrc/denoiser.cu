@@ -1274,12 +1274,18 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
             LAUNCH_CHECK(h);
         }
         // ---- feed forward on x2 = d.h2: ff = gelu(x2 W1^T + b1) kept as pairs only; z = ff W2^T + b2 + x2  (pre-norm3)
-        // ff1 also clears d.z (dead here) so that ff2 can run split-K = 2 and fill 120 SMs instead of 60
-        if ((rc = linear(h, d.h2_b, d.h2_s, D, L.w1_b, L.w1_s, D, L.b1, nullptr, nullptr, d.ff_b, d.ff_s, F, M, F, D, EPI_BIAS | EPI_GELU, st,
-                         1, d.z)))
-            return rc;
-        if ((rc = linear(h, d.ff_b, d.ff_s, F, L.w2_b, L.w2_s, F, L.b2, d.h2, d.z, nullptr, nullptr, D, M, D, F, EPI_BIAS | EPI_RES, st, 2)))
-            return rc;
+        if (h->gemm_backend == 1 && h->fused_mlp && idb_mlp_tcgen05_supported(D, F)) {
+            // both GEMMs, GELU and the residual in one cluster kernel; the hidden activations never leave the SM
+            if ((rc = idb_mlp_tcgen05(h, d.h2_b, d.h2_s, L.w1_b, L.w1_s, L.b1, L.w2_b, L.w2_s, L.b2, d.h2, D, d.z, D, M, h->pdl, st)))
+                return rc;
+        } else {
+            // ff1 also clears d.z (dead here) so that ff2 can run split-K = 2 and fill 120 SMs instead of 60
+            if ((rc = linear(h, d.h2_b, d.h2_s, D, L.w1_b, L.w1_s, D, L.b1, nullptr, nullptr, d.ff_b, d.ff_s, F, M, F, D, EPI_BIAS | EPI_GELU, st,
+                             1, d.z)))
+                return rc;
+            if ((rc = linear(h, d.ff_b, d.ff_s, F, L.w2_b, L.w2_s, F, L.b2, d.h2, d.z, nullptr, nullptr, D, M, D, F, EPI_BIAS | EPI_RES, st, 2)))
+                return rc;
+        }
         // QaN layers return tgt + (x - tgt) (model/sublayers.py:338-339); that differs from x by
         // <= 1 ulp of max(|x|,|tgt|) and is not reproduced (DESIGN.md "Deviations").
         pending = &L;

@@ -353,6 +353,282 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #undef TRACE
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused feed-forward block  Z = gelu(X W1^T + b1) W2^T + b2 + R   for d_model 256, d_ff = 8 x 128.
+//
+// The two GEMMs of a decoder layer are each far below one wave of work (120 / 60 tiles) and their
+// launches, prologues and the 16 MB round trip of the fp16-pair intermediate cost more than the
+// tensor work.  Here a cluster of 8 CTAs owns one 128-row tile: CTA j computes the 128-column chunk j
+// of the hidden layer (GEMM 1, K = 256) into TMEM, its epilogue warps apply bias + GELU, split the
+// result into (hi, lo) fp16 pairs and write them into shared memory directly in the K-major
+// 128B-swizzled layout the tensor core reads, and the same CTA multiplies that chunk with the matching
+// 128 columns of W2 (GEMM 2, N = 256, K = 128).  The 8 partial [128 x 256] products are exchanged
+// through distributed shared memory: CTA j sums rows 16j .. 16j+15 of all 8 partials in rank order
+// (deterministic), adds bias + residual and stores Z.  120 CTAs, one launch, no intermediate in HBM/L2.
+//
+// Shared memory (192 KB): ring = 2 x 64 KB stages (GEMM 1 operands, then the two W2 k-blocks, then
+// - together with the S region - the fp32 partial tile); S = 64 KB (hi | lo, 2 k-blocks of 64).
+// TMEM (512 columns): GEMM 1 main [0,128) + small [128,256); GEMM 2 main [256,512) + small [0,256)
+// (GEMM 1's accumulators are dead once S is written).
+namespace mlp {
+constexpr int FC = 128;                       // hidden columns per CTA
+constexpr int CLUSTER = 8;                    // d_ff / FC
+constexpr int DM = 256;                       // d_model
+constexpr int STAGE1 = 64 * 1024;             // A_hi 16K | W1_hi 16K | A_lo 16K | W1_lo 16K
+constexpr int RING = 2 * STAGE1;
+constexpr int S_BYTES = 64 * 1024;            // S_hi [2][16K] | S_lo [2][16K]
+constexpr int PLD = 260;                      // fp32 partial row stride (floats)
+constexpr int SMEM_BYTES = RING + S_BYTES + 1024 + 256;
+}  // namespace mlp
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&u)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+          "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+          "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(mlp::CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+                 const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_w1l,
+                 const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2l,
+                 const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ res, int ldr,
+                 float* __restrict__ Z, int ldz, int M) {
+    using namespace mlp;
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t s_base = base + RING;
+    const uint32_t bars = base + RING + S_BYTES;
+    // barriers: full1[2], empty1[2], acc1, full2[2], s_ready, acc2, then the tmem slot
+    auto bar_full1 = [&](int s) { return bars + 8u * s; };
+    auto bar_empty1 = [&](int s) { return bars + 8u * (2 + s); };
+    const uint32_t bar_acc1 = bars + 8u * 4;
+    auto bar_full2 = [&](int s) { return bars + 8u * (5 + s); };
+    const uint32_t bar_sready = bars + 8u * 7, bar_acc2 = bars + 8u * 8, tmem_slot = bars + 8u * 9;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + RING + S_BYTES + 8 * 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x;                 // hidden chunk == rank in the cluster (cluster spans gridDim.x = 8)
+    const int m0 = blockIdx.y * BM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; s++) { mbar_init(bar_full1(s), 1); mbar_init(bar_empty1(s), 1); mbar_init(bar_full2(s), 1); }
+        mbar_init(bar_acc1, 1); mbar_init(bar_acc2, 1);
+        mbar_init(bar_sready, 256);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xl) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1l) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2l) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            for (int kb = 0; kb < 2; kb++) {       // weight tiles do not depend on the previous kernel
+                const uint32_t dst = base + kb * STAGE1;
+                mbar_arrive_expect_tx(bar_full1(kb), STAGE1);
+                tma_load_2d(dst + 16384, &map_w1, bar_full1(kb), kb * BK, j * FC);
+                tma_load_2d(dst + 49152, &map_w1l, bar_full1(kb), kb * BK, j * FC);
+            }
+        }
+        __syncwarp();
+        pdl_wait();
+        if (elect_one()) {
+            for (int kb = 0; kb < 2; kb++) {
+                const uint32_t dst = base + kb * STAGE1;
+                tma_load_2d(dst, &map_x, bar_full1(kb), kb * BK, m0);
+                tma_load_2d(dst + 32768, &map_xl, bar_full1(kb), kb * BK, m0);
+            }
+        }
+        __syncwarp();
+        for (int kb = 2; kb < 4; kb++) {
+            const int s = kb & 1;
+            mbar_wait(bar_empty1(s), 0);
+            const uint32_t dst = base + s * STAGE1;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar_full1(s), STAGE1);
+                tma_load_2d(dst, &map_x, bar_full1(s), kb * BK, m0);
+                tma_load_2d(dst + 16384, &map_w1, bar_full1(s), kb * BK, j * FC);
+                tma_load_2d(dst + 32768, &map_xl, bar_full1(s), kb * BK, m0);
+                tma_load_2d(dst + 49152, &map_w1l, bar_full1(s), kb * BK, j * FC);
+            }
+            __syncwarp();
+        }
+        // GEMM 1 finished reading the ring: fetch this chunk's 128 columns of W2 (two k-blocks of 64)
+        // while the epilogue warps turn the accumulators into the S operand
+        mbar_wait(bar_acc1, 0);
+        if (elect_one()) {
+            for (int kb = 0; kb < 2; kb++) {
+                const uint32_t dst = base + kb * STAGE1;
+                mbar_arrive_expect_tx(bar_full2(kb), STAGE1);
+                tma_load_2d(dst, &map_w2, bar_full2(kb), j * FC + kb * BK, 0);
+                tma_load_2d(dst + 32768, &map_w2l, bar_full2(kb), j * FC + kb * BK, 0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc1 = (1u << 4) | ((uint32_t)(FC >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t idesc2 = (1u << 4) | ((uint32_t)(DM >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t acc1_main = tmem_base, acc1_small = tmem_base + 128u;
+        for (int kb = 0; kb < 4; kb++) {
+            const int s = kb & 1;
+            mbar_wait(bar_full1(s), (kb >> 1) & 1);
+            tc_fence_after();
+            const uint32_t st = base + s * STAGE1;
+            const uint64_t dah = make_smem_desc(st), dwh = make_smem_desc(st + 16384);
+            const uint64_t dal = make_smem_desc(st + 32768), dwl = make_smem_desc(st + 49152);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < BK / UMMA_K; kk++) {
+                    const uint64_t koff = (uint64_t)((kk * UMMA_K * 2) >> 4);
+                    umma_f16(acc1_small, dal + koff, dwh + koff, idesc1, (kb | kk) ? 1u : 0u);
+                    umma_f16(acc1_small, dah + koff, dwl + koff, idesc1, 1u);
+                    umma_f16(acc1_main, dah + koff, dwh + koff, idesc1, (kb | kk) ? 1u : 0u);
+                }
+                umma_commit(bar_empty1(s));
+                if (kb == 3) umma_commit(bar_acc1);
+            }
+            __syncwarp();
+        }
+        // GEMM 2: A = S (written by the epilogue warps), B = W2 k-blocks in the ring
+        mbar_wait(bar_sready, 0);
+        tc_fence_after();
+        const uint32_t acc2_main = tmem_base + 256u, acc2_small = tmem_base;
+        for (int kb = 0; kb < 2; kb++) {
+            mbar_wait(bar_full2(kb), 0);
+            tc_fence_after();
+            const uint64_t dah = make_smem_desc(s_base + kb * 16384), dal = make_smem_desc(s_base + 32768 + kb * 16384);
+            const uint64_t dwh = make_smem_desc(base + kb * STAGE1), dwl = make_smem_desc(base + kb * STAGE1 + 32768);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < BK / UMMA_K; kk++) {
+                    const uint64_t koff = (uint64_t)((kk * UMMA_K * 2) >> 4);
+                    umma_f16(acc2_small, dal + koff, dwh + koff, idesc2, (kb | kk) ? 1u : 0u);
+                    umma_f16(acc2_small, dah + koff, dwl + koff, idesc2, 1u);
+                    umma_f16(acc2_main, dah + koff, dwh + koff, idesc2, (kb | kk) ? 1u : 0u);
+                }
+                if (kb == 1) umma_commit(bar_acc2);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue warps 2..9 =====================
+        const int q = warp & 3, ew = warp - 2;       // TMEM lane quarter, 0..7
+        const int r = q * 32 + lane;                 // tile row owned by this thread
+        pdl_wait();
+        mbar_wait(bar_acc1, 0);
+        tc_fence_after();
+        // ---- hidden chunk: bias + GELU -> (hi, lo) fp16 pairs in the swizzled K-major A layout
+#pragma unroll 1
+        for (int c0 = (ew >> 2) * 32; c0 < FC; c0 += 64) {
+            uint32_t um[32], us[32];
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            tmem_ld32(trow + (uint32_t)c0, um);
+            tmem_ld32(trow + (uint32_t)(128 + c0), us);
+            const int kb = c0 >> 6, ch0 = (c0 & 63) >> 3;
+            uint8_t* srow_hi = base_ptr + RING + kb * 16384 + r * 128;
+            uint8_t* srow_lo = srow_hi + 32768;
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int i0 = ch * 8 + e * 2;
+                    const float2 bb = *reinterpret_cast<const float2*>(b1 + j * FC + c0 + i0);
+                    const float v0 = gelu_erf(fmaf(__uint_as_float(us[i0]), 1.0f / 2048.0f, __uint_as_float(um[i0])) + bb.x);
+                    const float v1 = gelu_erf(fmaf(__uint_as_float(us[i0 + 1]), 1.0f / 2048.0f, __uint_as_float(um[i0 + 1])) + bb.y);
+                    __half2 hh, ll;
+                    split_f16x2(v0, v1, hh, ll);
+                    hw[e] = *reinterpret_cast<uint32_t*>(&hh); lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+                }
+                const int pos = ((ch0 + ch) ^ (r & 7)) * 16;
+                *reinterpret_cast<uint4*>(srow_hi + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(srow_lo + pos) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+        }
+        tc_fence_before();                                             // our TMEM reads precede GEMM 2's writes to those columns
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy S writes -> visible to the tensor core
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_sready) : "memory");
+        // ---- partial output tile of this chunk -> fp32 [128][PLD] in the (now idle) ring + S region
+        mbar_wait(bar_acc2, 0);
+        tc_fence_after();
+        float* prow = reinterpret_cast<float*>(base_ptr) + (size_t)r * PLD;
+#pragma unroll 1
+        for (int c0 = (ew >> 2) * 128; c0 < (ew >> 2) * 128 + 128; c0 += 32) {
+            uint32_t um[32], us[32];
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            tmem_ld32(trow + (uint32_t)(256 + c0), um);
+            tmem_ld32(trow + (uint32_t)c0, us);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(prow + c0 + i) =
+                    make_float4(fmaf(__uint_as_float(us[i]), 1.0f / 2048.0f, __uint_as_float(um[i])),
+                                fmaf(__uint_as_float(us[i + 1]), 1.0f / 2048.0f, __uint_as_float(um[i + 1])),
+                                fmaf(__uint_as_float(us[i + 2]), 1.0f / 2048.0f, __uint_as_float(um[i + 2])),
+                                fmaf(__uint_as_float(us[i + 3]), 1.0f / 2048.0f, __uint_as_float(um[i + 3])));
+        }
+        tc_fence_before();
+    }
+    // ===================== cross-CTA reduction over distributed shared memory =====================
+    __syncwarp();
+    cluster_sync_all();                  // every CTA's partial tile is complete and visible cluster-wide
+    if (warp >= 2) {
+        const int ct = threadIdx.x - 64;
+        const uint32_t local = base;     // same offset in every CTA of the cluster (identical smem layout)
+#pragma unroll 1
+        for (int idx = ct; idx < 16 * (DM / 4); idx += 256) {
+            const int rr = idx / (DM / 4), c4 = idx % (DM / 4);
+            const int row = m0 + j * 16 + rr;
+            const uint32_t off = local + (uint32_t)(((j * 16 + rr) * PLD + c4 * 4) * 4);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < CLUSTER; i++) {
+                uint32_t ra;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(off), "r"(i));
+                float4 p;
+                asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w) : "r"(ra));
+                acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+            }
+            if (row < M) {
+                const float4 bb = *reinterpret_cast<const float4*>(b2 + c4 * 4);
+                const float4 r4 = *reinterpret_cast<const float4*>(res + (size_t)row * ldr + c4 * 4);
+                *reinterpret_cast<float4*>(Z + (size_t)row * ldz + c4 * 4) =
+                    make_float4((acc.x + bb.x) + r4.x, (acc.y + bb.y) + r4.y, (acc.z + bb.z) + r4.z, (acc.w + bb.w) + r4.w);
+            }
+        }
+    }
+    __syncwarp();
+    cluster_sync_all();                  // nobody leaves (and frees its shared memory) while peers still read it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -439,6 +715,33 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
         idb_launch(g.pdl != 0, gemm_split_f16_kernel<64>, grid, NUM_THREADS, Cfg<64>::SMEM_BYTES, st, ma, mw, mal, mwl, g.bias, g.res, g.ldr,
                    g.C, g.C_hi, g.C_lo, g.ldc, M, N, K, g.epi, nacc, zero, g.zero_ld, g.zero_cols, trace);
     }
+    LAUNCH_CHECK(h);
+    return IDB_OK;
+}
+
+// Fused feed-forward block (see mlp_fused_kernel).  x / w1 / w2 as fp16 (hi, lo) pairs, row-major:
+// x [M][256], w1 [F][256], w2 [256][F];  Z[M][256] = gelu(x w1^T + b1) w2^T + b2 + res.
+bool idb_mlp_tcgen05_supported(int d_model, int d_ff) { return d_model == mlp::DM && d_ff == mlp::FC * mlp::CLUSTER; }
+
+int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const __half* w1_hi, const __half* w1_lo, const float* b1,
+                    const __half* w2_hi, const __half* w2_lo, const float* b2, const float* res, int ldr, float* Z, int ldz, int M,
+                    int pdl, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(h, cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int F = mlp::FC * mlp::CLUSTER;
+    CUtensorMap mx, mxl, mw1, mw1l, mw2, mw2l;
+    int rc;
+    if ((rc = make_map(h, &mx, x_hi, M, mlp::DM, mlp::DM, BM))) return rc;
+    if ((rc = make_map(h, &mxl, x_lo, M, mlp::DM, mlp::DM, BM))) return rc;
+    if ((rc = make_map(h, &mw1, w1_hi, F, mlp::DM, mlp::DM, mlp::FC))) return rc;
+    if ((rc = make_map(h, &mw1l, w1_lo, F, mlp::DM, mlp::DM, mlp::FC))) return rc;
+    if ((rc = make_map(h, &mw2, w2_hi, mlp::DM, F, F, mlp::DM))) return rc;
+    if ((rc = make_map(h, &mw2l, w2_lo, mlp::DM, F, F, mlp::DM))) return rc;
+    dim3 grid(mlp::CLUSTER, (M + BM - 1) / BM);
+    idb_launch(pdl != 0, mlp_fused_kernel, grid, NUM_THREADS, mlp::SMEM_BYTES, st, mx, mw1, mxl, mw1l, mw2, mw2l, b1, b2, res, ldr, Z, ldz, M);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }

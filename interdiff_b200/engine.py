@@ -85,6 +85,18 @@ class Engine:
         """Programmatic dependent launch between the kernels of a step (default on; identical results)."""
         self._chk(self.lib.idb_set_dependent_launch(self._h, 1 if on else 0))
 
+    def set_fused_mlp(self, on):
+        """Feed-forward block as one cluster kernel (default on) vs two GEMM launches."""
+        self._chk(self.lib.idb_set_fused_mlp(self._h, 1 if on else 0))
+
+    def mlp(self, x, w1, b1, w2, b2, res):
+        """gelu(x @ w1.T + b1) @ w2.T + b2 + res through the fused feed-forward kernel (tests)."""
+        x, w1, b1, w2, b2, res = (self._f32(t) for t in (x, w1, b1, w2, b2, res))
+        out = torch.empty_like(x)
+        self._chk(self.lib.idb_debug_mlp(self._h, self._ptr(x), self._ptr(w1), self._ptr(b1), self._ptr(w2), self._ptr(b2), self._ptr(res),
+                                         self._ptr(out), x.shape[0], self._stream()))
+        return out
+
     def set_gemm_backend(self, backend):
         self._chk(self.lib.idb_set_gemm_backend(self._h, {"simt": 0, "tcgen05": 1}.get(backend, backend)))
 

@@ -85,3 +85,20 @@ def test_gelu_epilogue_accuracy_on_a_grid(eng, backend):
     # erf error <= 1.0e-7 (fit) -> GELU error <= 0.5 |x| 1e-7, plus the fp32 rounding of the result
     bound = 2.5e-7 * torch.clamp(x.double().abs(), min=1.0)
     assert bool(((out - ref).abs() <= bound).all()), ((out - ref).abs() / bound).max().item()
+
+
+@pytest.mark.parametrize("M", [1920, 129, 5])
+def test_fused_feed_forward_kernel(eng, M):
+    """The cluster kernel gelu(x W1^T + b1) W2^T + b2 + res (8 CTAs exchange partial tiles over distributed
+    shared memory) against float64; the rank-ordered reduction makes it bit-reproducible."""
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, 256, generator=g)
+    w1 = torch.randn(1024, 256, generator=g) / 16
+    b1 = torch.randn(1024, generator=g) * 0.1
+    w2 = torch.randn(256, 1024, generator=g) / 32
+    b2 = torch.randn(256, generator=g) * 0.1
+    res = torch.randn(M, 256, generator=g)
+    ref = torch.nn.functional.gelu(x.double() @ w1.double().T + b1.double()) @ w2.double().T + b2.double() + res.double()
+    outs = [eng.mlp(x, w1, b1, w2, b2, res).cpu() for _ in range(3)]
+    assert ((outs[0].double() - ref).abs().max() / ref.abs().max()).item() < 2e-6
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

@@ -58,6 +58,7 @@ extern "C" int idb_set_dependent_launch(idb_handle* h, int on) {
     return IDB_OK;
 }
 
+extern "C" double idb_debug_last_ms(const idb_handle* h) { return h ? h->last_ms : 0.0; }
 extern "C" int idb_set_fused_mlp(idb_handle* h, int on) {
     if (!h) return IDB_ERR_ARG;
     h->fused_mlp = on ? 1 : 0;
@@ -65,10 +66,11 @@ extern "C" int idb_set_fused_mlp(idb_handle* h, int on) {
     return IDB_OK;
 }
 
+extern long long* g_idb_gemm_trace;
 /* test hook: out[M][256] = gelu(x w1^T + b1) w2^T + b2 + res through the fused cluster kernel (fp32 device inputs,
    x [M][256], w1 [1024][256], w2 [256][1024]); operands are split into fp16 pairs in temporary buffers */
 extern "C" int idb_debug_mlp(idb_handle* h, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
-                             const float* res, float* out, int M, void* stream) {
+                             const float* res, float* out, int M, int iters, long long* trace, void* stream) {
     if (!h || !x || !w1 || !b1 || !w2 || !b2 || !res || !out || M <= 0) return IDB_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int Dm = 256, F = 1024;
@@ -79,8 +81,17 @@ extern "C" int idb_debug_mlp(idb_handle* h, const float* x, const float* w1, con
     int rc = idb_split_tensor(h, x, Dm, xh, xl, Dm, M, Dm, st);
     if (!rc) rc = idb_split_tensor(h, w1, Dm, w1h, w1l, Dm, F, Dm, st);
     if (!rc) rc = idb_split_tensor(h, w2, F, w2h, w2l, F, Dm, F, st);
-    if (!rc) rc = idb_mlp_tcgen05(h, xh, xl, w1h, w1l, b1, w2h, w2l, b2, res, Dm, out, Dm, M, 0, st);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < (iters > 0 ? iters : 1) && !rc; i++) {
+        if (i == 0 && trace) g_idb_gemm_trace = trace;
+        if (i == 1) cudaEventRecord(e0, st);
+        rc = idb_mlp_tcgen05(h, xh, xl, w1h, w1l, b1, w2h, w2l, b2, res, Dm, out, Dm, M, 0, st);
+    }
+    cudaEventRecord(e1, st);
     cudaStreamSynchronize(st);
+    if (iters > 1 && !rc) { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); h->last_ms = ms / (iters - 1); }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(buf);
     return rc;
 }

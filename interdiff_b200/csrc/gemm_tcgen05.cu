@@ -40,8 +40,8 @@ template <int BN> struct Cfg {
     static constexpr int W_BYTES = BN * BK * 2;
     static constexpr int HALF_BYTES = A_BYTES + W_BYTES;      // [A_hi | W_hi], then the same for lo
     static constexpr int STAGE_BYTES = 2 * HALF_BYTES;
-    static constexpr int STAGES = (BN == 128) ? 3 : 4;
-    static constexpr int NACC_MAX = (BN == 128) ? 3 : 7;      // runtime `nacc` <= NACC_MAX main accumulators (+1 small)
+    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128) ? 3 : 4;
+    static constexpr int NACC_MAX = (BN == 256) ? 1 : (BN == 128) ? 3 : 7;   // runtime `nacc` <= NACC_MAX main accumulators (+1 small)
     static constexpr int TMEM_COLS = 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -403,8 +403,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                  const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_w1l,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2l,
                  const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ res, int ldr,
-                 float* __restrict__ Z, int ldz, int M) {
+                 float* __restrict__ Z, int ldz, int M, long long* __restrict__ trace) {
     using namespace mlp;
+    long long* tr = trace ? trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+#define MTRACE(slot) do { if (tr) tr[slot] = clock64(); } while (0)
+    if (threadIdx.x == 0) MTRACE(0);
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -443,6 +446,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    if (threadIdx.x == 0) MTRACE(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -498,6 +502,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const int s = kb & 1;
             mbar_wait(bar_full1(s), (kb >> 1) & 1);
             tc_fence_after();
+            if (kb == 0 && lane == 0) MTRACE(2);
             const uint32_t st = base + s * STAGE1;
             const uint64_t dah = make_smem_desc(st), dwh = make_smem_desc(st + 16384);
             const uint64_t dal = make_smem_desc(st + 32768), dwl = make_smem_desc(st + 49152);
@@ -514,9 +519,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             }
             __syncwarp();
         }
+        if (lane == 0) MTRACE(3);
         // GEMM 2: A = S (written by the epilogue warps), B = W2 k-blocks in the ring
         mbar_wait(bar_sready, 0);
         tc_fence_after();
+        if (lane == 0) MTRACE(6);
         const uint32_t acc2_main = tmem_base + 256u, acc2_small = tmem_base;
         for (int kb = 0; kb < 2; kb++) {
             mbar_wait(bar_full2(kb), 0);
@@ -535,6 +542,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             }
             __syncwarp();
         }
+        if (lane == 0) MTRACE(7);
     } else {
         // ===================== epilogue warps 2..9 =====================
         const int q = warp & 3, ew = warp - 2;       // TMEM lane quarter, 0..7
@@ -542,6 +550,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         pdl_wait();
         mbar_wait(bar_acc1, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) MTRACE(4);
         // ---- hidden chunk: bias + GELU -> (hi, lo) fp16 pairs in the swizzled K-major A layout
 #pragma unroll 1
         for (int c0 = (ew >> 2) * 32; c0 < FC; c0 += 64) {
@@ -573,9 +582,20 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         tc_fence_before();                                             // our TMEM reads precede GEMM 2's writes to those columns
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy S writes -> visible to the tensor core
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_sready) : "memory");
-        // ---- partial output tile of this chunk -> fp32 [128][PLD] in the (now idle) ring + S region
-        mbar_wait(bar_acc2, 0);
+        if (threadIdx.x == 64) MTRACE(5);
+    }
+    // ===================== cross-CTA reduction over distributed shared memory =====================
+    // Every CTA writes its [128 x 256] fp32 partial product into its own (now idle) ring + S region; after a
+    // cluster barrier CTA j PULLS rows 16j .. 16j+15 of all 8 partials with coalesced 16-byte remote loads and sums
+    // them in rank order.  This exchange is bound by the SM-to-SM network (112 KB per CTA, ~13 B/clk/SM with all
+    // 120 CTAs exchanging at once = 8.5 K cycles; measured alternatives: 32 instead of 8 remote loads in flight per
+    // thread 13 K cycles, pushing rows to their owner with remote stores 14 K - profiles/README.md).
+    const int q = warp & 3, ew = warp - 2;
+    if (warp >= 2) {
+        mbar_wait(bar_acc2, 0);          // GEMM 2 complete: the operand buffers may be overwritten
         tc_fence_after();
+        if (threadIdx.x == 64) MTRACE(8);
+        const int r = q * 32 + lane;
         float* prow = reinterpret_cast<float*>(base_ptr) + (size_t)r * PLD;
 #pragma unroll 1
         for (int c0 = (ew >> 2) * 128; c0 < (ew >> 2) * 128 + 128; c0 += 32) {
@@ -592,26 +612,29 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                                 fmaf(__uint_as_float(us[i + 3]), 1.0f / 2048.0f, __uint_as_float(um[i + 3])));
         }
         tc_fence_before();
+        if (threadIdx.x == 64) MTRACE(9);
     }
-    // ===================== cross-CTA reduction over distributed shared memory =====================
     __syncwarp();
     cluster_sync_all();                  // every CTA's partial tile is complete and visible cluster-wide
+    if (threadIdx.x == 64) MTRACE(10);
     if (warp >= 2) {
         const int ct = threadIdx.x - 64;
-        const uint32_t local = base;     // same offset in every CTA of the cluster (identical smem layout)
 #pragma unroll 1
-        for (int idx = ct; idx < 16 * (DM / 4); idx += 256) {
-            const int rr = idx / (DM / 4), c4 = idx % (DM / 4);
+        for (int t = 0; t < 4; t++) {
+            const int idx = ct + t * 256, rr = idx / (DM / 4), c4 = idx % (DM / 4);
             const int row = m0 + j * 16 + rr;
-            const uint32_t off = local + (uint32_t)(((j * 16 + rr) * PLD + c4 * 4) * 4);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t off = base + (uint32_t)(((j * 16 + rr) * PLD + c4 * 4) * 4);   // same offset in every CTA of the cluster
+            float4 p[CLUSTER];
 #pragma unroll
             for (int i = 0; i < CLUSTER; i++) {
                 uint32_t ra;
                 asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(off), "r"(i));
-                float4 p;
-                asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w) : "r"(ra));
-                acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+                asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p[i].x), "=f"(p[i].y), "=f"(p[i].z), "=f"(p[i].w) : "r"(ra));
+            }
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < CLUSTER; i++) {          // rank order: deterministic
+                acc.x += p[i].x; acc.y += p[i].y; acc.z += p[i].z; acc.w += p[i].w;
             }
             if (row < M) {
                 const float4 bb = *reinterpret_cast<const float4*>(b2 + c4 * 4);
@@ -620,9 +643,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     make_float4((acc.x + bb.x) + r4.x, (acc.y + bb.y) + r4.y, (acc.z + bb.z) + r4.z, (acc.w + bb.w) + r4.w);
             }
         }
+        if (threadIdx.x == 64) MTRACE(11);
     }
     __syncwarp();
     cluster_sync_all();                  // nobody leaves (and frees its shared memory) while peers still read it
+    if (threadIdx.x == 64) MTRACE(12);
+    __syncthreads();
+#undef MTRACE
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -677,16 +704,23 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
     if (!g_attr_set) {
         CUDA_TRY(h, cudaFuncSetAttribute(gemm_split_f16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
         CUDA_TRY(h, cudaFuncSetAttribute(gemm_split_f16_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
+        CUDA_TRY(h, cudaFuncSetAttribute(gemm_split_f16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
         g_attr_set = true;
     }
     // wide outputs take 128-column tiles; narrow ones 64 so more SMs get a tile
-    const bool wide = (long)((M + BM - 1) / BM) * ((N + 127) / 128) >= 74;
+    const long tiles128 = (long)((M + BM - 1) / BM) * ((N + 127) / 128);
+    const bool wide = tiles128 >= 74;
+    // more 128-column tiles than SMs would run as two waves: 256-column tiles (one main accumulator, so only for
+    // short reductions) put e.g. the folded QKV projection (N = 1536) on 90 CTAs in a single wave
+    const bool xwide = tiles128 > h->sm_count && (N % 256) == 0 && (K + BK - 1) / BK <= 4 && g.ksplit != 2 && !g.zero &&
+                       (g_idb_gemm_nacc <= 0 || g_idb_gemm_nacc == 1);
+    const int bn = xwide ? 256 : wide ? 128 : 64;
     CUtensorMap ma, mw, mal, mwl;
     int rc;
     if ((rc = make_map(h, &ma, g.A_hi, M, K, g.lda, BM))) return rc;
-    if ((rc = make_map(h, &mw, g.W_hi, N, K, g.ldw, wide ? 128 : 64))) return rc;
+    if ((rc = make_map(h, &mw, g.W_hi, N, K, g.ldw, bn))) return rc;
     if ((rc = make_map(h, &mal, g.A_lo, M, K, g.lda, BM))) return rc;
-    if ((rc = make_map(h, &mwl, g.W_lo, N, K, g.ldw, wide ? 128 : 64))) return rc;
+    if ((rc = make_map(h, &mwl, g.W_lo, N, K, g.ldw, bn))) return rc;
     // split-K (2 only: two addends commute, so the reduction order cannot change the result) needs a C that
     // an earlier kernel zeroed (GemmArgs::zero of the producer GEMM) and the plain fp32 output
     int ksplit = g.ksplit == 2 && (K + BK - 1) / BK >= 2 ? 2 : 1;
@@ -706,7 +740,11 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
     int nacc = kb_per_cta <= 8 ? 2 : (kb_per_cta + 3) / 4;
     if (nacc > nacc_max) nacc = nacc_max;
     if (g_idb_gemm_nacc > 0) nacc = g_idb_gemm_nacc < nacc_max ? g_idb_gemm_nacc : nacc_max;
-    if (wide) {
+    if (xwide) {
+        dim3 grid(N / 256, (M + BM - 1) / BM, 1);
+        idb_launch(g.pdl != 0, gemm_split_f16_kernel<256>, grid, NUM_THREADS, Cfg<256>::SMEM_BYTES, st, ma, mw, mal, mwl, g.bias, g.res, g.ldr,
+                   g.C, g.C_hi, g.C_lo, g.ldc, M, N, K, g.epi, 1, nullptr, 0, 0, trace);
+    } else if (wide) {
         dim3 grid((N + 127) / 128, (M + BM - 1) / BM, ksplit);
         idb_launch(g.pdl != 0, gemm_split_f16_kernel<128>, grid, NUM_THREADS, Cfg<128>::SMEM_BYTES, st, ma, mw, mal, mwl, g.bias, g.res, g.ldr,
                    g.C, g.C_hi, g.C_lo, g.ldc, M, N, K, g.epi, nacc, zero, g.zero_ld, g.zero_cols, trace);
@@ -726,6 +764,8 @@ bool idb_mlp_tcgen05_supported(int d_model, int d_ff) { return d_model == mlp::D
 int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const __half* w1_hi, const __half* w1_lo, const float* b1,
                     const __half* w2_hi, const __half* w2_lo, const float* b2, const float* res, int ldr, float* Z, int ldz, int M,
                     int pdl, cudaStream_t st) {
+    long long* trace = g_idb_gemm_trace;
+    g_idb_gemm_trace = nullptr;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(h, cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
@@ -741,7 +781,7 @@ int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const
     if ((rc = make_map(h, &mw2, w2_hi, mlp::DM, F, F, mlp::DM))) return rc;
     if ((rc = make_map(h, &mw2l, w2_lo, mlp::DM, F, F, mlp::DM))) return rc;
     dim3 grid(mlp::CLUSTER, (M + BM - 1) / BM);
-    idb_launch(pdl != 0, mlp_fused_kernel, grid, NUM_THREADS, mlp::SMEM_BYTES, st, mx, mw1, mxl, mw1l, mw2, mw2l, b1, b2, res, ldr, Z, ldz, M);
+    idb_launch(pdl != 0, mlp_fused_kernel, grid, NUM_THREADS, mlp::SMEM_BYTES, st, mx, mw1, mxl, mw1l, mw2, mw2l, b1, b2, res, ldr, Z, ldz, M, trace);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }

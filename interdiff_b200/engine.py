@@ -89,13 +89,17 @@ class Engine:
         """Feed-forward block as one cluster kernel (default on) vs two GEMM launches."""
         self._chk(self.lib.idb_set_fused_mlp(self._h, 1 if on else 0))
 
-    def mlp(self, x, w1, b1, w2, b2, res):
-        """gelu(x @ w1.T + b1) @ w2.T + b2 + res through the fused feed-forward kernel (tests)."""
+    def mlp(self, x, w1, b1, w2, b2, res, iters=1, trace=None):
+        """gelu(x @ w1.T + b1) @ w2.T + b2 + res through the fused feed-forward kernel (tests / probes).
+        iters > 1: self.last_ms() is the mean time of launches 2..iters; trace: int64 [ctas,16] device tensor."""
         x, w1, b1, w2, b2, res = (self._f32(t) for t in (x, w1, b1, w2, b2, res))
         out = torch.empty_like(x)
         self._chk(self.lib.idb_debug_mlp(self._h, self._ptr(x), self._ptr(w1), self._ptr(b1), self._ptr(w2), self._ptr(b2), self._ptr(res),
-                                         self._ptr(out), x.shape[0], self._stream()))
+                                         self._ptr(out), x.shape[0], int(iters), self._ptr(trace), self._stream()))
         return out
+
+    def last_ms(self):
+        return float(self.lib.idb_debug_last_ms(self._h))
 
     def set_gemm_backend(self, backend):
         self._chk(self.lib.idb_set_gemm_backend(self._h, {"simt": 0, "tcgen05": 1}.get(backend, backend)))

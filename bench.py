@@ -29,7 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(name="smpl_diffusion_100step", B=64, T=30, past_len=10, diffusion_steps=100, C=144)
-FF1_DRAM_TRAFFIC_BYTES = None   # filled from profiles/r1_ncu_full_gemm.txt once captured
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE mlp_fused_kernel launch (ncu --set full, cold caches:
+# profiles/r1_ncu_full_mlp.txt); None until captured
+MLP_DRAM_TRAFFIC_BYTES = 6072576
 METRIC = "HOI denoising-steps/sec (B=64,T=30)"
 UNIT = "denoising steps/s"
 
@@ -216,8 +218,16 @@ def run_ours(args):
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    # ---- roofline of the dominant kernel (feed-forward GEMMs, 16.1 of the 24.5 GFLOP of a step)
-    roof = eng.gemm_microbench(M=w["B"] * w["T"], N=1024, K=256, iters=200)
+    # ---- roofline of the dominant kernel: the fused feed-forward block (8 launches per step, ~48 % of the step;
+    # 16.1 of the 19.4 GFLOP of a step), timed alone: mean of 200 back-to-back launches, CUDA events on its stream
+    M = w["B"] * w["T"]
+    g = torch.Generator().manual_seed(0)
+    rx, rw1, rb1 = torch.randn(M, 256, generator=g), torch.randn(1024, 256, generator=g) / 16, torch.randn(1024, generator=g) * 0.1
+    rw2, rb2, rres = torch.randn(256, 1024, generator=g) / 32, torch.randn(256, generator=g) * 0.1, torch.randn(M, 256, generator=g)
+    eng.mlp(rx, rw1, rb1, rw2, rb2, rres, iters=5)
+    eng.mlp(rx, rw1, rb1, rw2, rb2, rres, iters=201)
+    roof = dict(ms=eng.last_ms(), flops=2.0 * M * (256 * 1024 + 1024 * 256), iters=200,
+                kernel="mlp_fused_kernel (gelu(X W1^T + b1) W2^T + b2 + R, M=%d, d_model 256, d_ff 1024)" % M)
 
     dev_ms, e2e_ms = aggregate_max([dev_ms, e2e_ms], device=dev)
     if rank == 0:
@@ -237,16 +247,18 @@ def run_ours(args):
                              h2d_bytes_per_step=int(h_gt.numel() * 4 + h_mask.numel() + h_cond.numel() * 4 + h_xT.numel() * 4),
                              d2h_bytes_per_step=int(h_out.numel() * 4)),
                     gpu_launches=int(launches), clocks=clocks, wall_s=wall)
-        if roof:
-            flops = 2.0 * roof["M"] * roof["N"] * roof["K"]
-            ach = flops / (roof["ms"] * 1e-3) / 1e12
+        if roof and roof["ms"] > 0:
+            ach = roof["flops"] / (roof["ms"] * 1e-3) / 1e12
             line["roofline"] = dict(bound="tensor", kernel=roof["kernel"], achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s",
-                                    frac=ach / peaks["bf16_tflops"], traffic=FF1_DRAM_TRAFFIC_BYTES, peak_source=peaks["source"] + " (burst bf16)",
+                                    frac=ach / peaks["bf16_tflops"], traffic=MLP_DRAM_TRAFFIC_BYTES, us_per_launch=roof["ms"] * 1e3,
+                                    peak_source=peaks["source"] + " (burst bf16)",
                                     issue_ceiling=peaks["bf16_tflops"] / 3.0, frac_of_issue_ceiling=ach / (peaks["bf16_tflops"] / 3.0),
-                                    note="algorithmic 2*M*N*K (1.007 GFLOP) of the ff1 GEMM (M=1920,N=1024,K=256) / mean time of %d "
-                                         "back-to-back launches (CUDA events); the split-precision kernel issues 3 fp16 MMAs per algorithmic "
-                                         "MAC, so its ceiling is 1/3 of the fp16/bf16 peak; traffic = dram bytes per launch from the "
-                                         "ncu --set full capture in profiles/ (operands are L2 resident in the loop)" % roof["iters"])
+                                    note="algorithmic flops 2*M*(256*1024 + 1024*256) = %.3f GFLOP per launch / mean time of %d back-to-back "
+                                         "launches (CUDA events); the split-precision kernel issues 3 fp16 MMAs per algorithmic MAC, so its "
+                                         "ceiling is 1/3 of the fp16/bf16 peak; at M=1920 the launch is one wave of 120 CTAs bound by "
+                                         "fixed latencies (DESIGN.md 4.1b timeline), not by the tensor pipe; traffic = dram bytes per "
+                                         "launch from the ncu --set full capture in profiles/ (operands are L2 resident in the loop)"
+                                         % (roof["flops"] / 1e9, roof["iters"]))
         if world == 1 and not args.no_cpu:
             rate, secs, cores = cpu_reference_rate(args.cpu_steps)
             line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="port",

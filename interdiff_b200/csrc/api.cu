@@ -36,6 +36,7 @@ extern "C" int idb_destroy(idb_handle* h) {
     idb_denoiser_release(h);
     idb_projector_release(h);
     idb_body_release(h);
+    if (h->scratch) cudaFree(h->scratch);
     delete h;
     return IDB_OK;
 }

@@ -38,7 +38,7 @@ struct DenoiserLayer {
     // folded self-attention: [Wq; Wk; (Wo_h Wv_h) for h] (1536 x 256), bias [bq; bk; 0], bo' = bo + sum_h Wo_h bv_h
     float *w_qkvf = nullptr, *b_qkvf = nullptr, *bo_f = nullptr;
     // (big, small) splits of the GEMM weights for the tensor-core path
-    __half *w_qkvf_b = nullptr, *w_qkvf_s = nullptr, *w_qc_b = nullptr, *w_qc_s = nullptr, *w1_b = nullptr, *w1_s = nullptr,
+    __half *w_qkvf_b = nullptr, *w_qkvf_s = nullptr, *w1_b = nullptr, *w1_s = nullptr,
            *w2_b = nullptr, *w2_s = nullptr;
     // QaN
     float *qt = nullptr, *wk = nullptr;  // qt: [3*N][D] folded queries

@@ -144,17 +144,6 @@ __device__ __forceinline__ void warp_ln_row(const float* __restrict__ zrow, cons
     if (dst_b) store_pairs(o0, o1, dst_b, dst_s, lane);
 }
 
-__device__ __forceinline__ float dot64(const float* __restrict__ a, const float* __restrict__ b) {
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int d = 0; d < HD; d += 8) {
-        const float4 x0 = *reinterpret_cast<const float4*>(a + d), y0 = *reinterpret_cast<const float4*>(b + d);
-        const float4 x1 = *reinterpret_cast<const float4*>(a + d + 4), y1 = *reinterpret_cast<const float4*>(b + d + 4);
-        s0 = fmaf(x0.x, y0.x, s0); s0 = fmaf(x0.y, y0.y, s0); s0 = fmaf(x0.z, y0.z, s0); s0 = fmaf(x0.w, y0.w, s0);
-        s1 = fmaf(x1.x, y1.x, s1); s1 = fmaf(x1.y, y1.y, s1); s1 = fmaf(x1.z, y1.z, s1); s1 = fmaf(x1.w, y1.w, s1);
-    }
-    return s0 + s1;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Attention kernels.  One CTA = a slab of <= 16 rows of one sample, 512 threads (16 warps, 4 per
@@ -1138,7 +1127,6 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
         if (!rc) rc = split(d.w_out, Clin, D, D, &d.w_out_b, &d.w_out_s);
         for (auto& L : d.layers) {
             if (!rc && !L.qan) rc = split(L.w_qkvf, 2 * D + H * D, D, D, &L.w_qkvf_b, &L.w_qkvf_s);
-            if (!rc) rc = split(L.w_qc, D, D, D, &L.w_qc_b, &L.w_qc_s);
             if (!rc) rc = split(L.w1, F, D, D, &L.w1_b, &L.w1_s);
             if (!rc) rc = split(L.w2, D, F, F, &L.w2_b, &L.w2_s);
         }

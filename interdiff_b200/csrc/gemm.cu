@@ -4,7 +4,7 @@
 // plain TF32/FP16/BF16 operand rounding diverges to O(1) over a 100-1000 step loop):
 //   backend 0: fp32 SIMT register-tiled kernel (this file) -- debug / bisect path and fallback
 //              for shapes the tensor-core kernel does not take.
-//   backend 1: tcgen05 3xTF32 split-precision kernel (gemm_tcgen05.cu).
+//   backend 1: tcgen05 split-precision kernel on fp16 (hi, lo) operand pairs (gemm_tcgen05.cu), default.
 #include "common.cuh"
 
 int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st);

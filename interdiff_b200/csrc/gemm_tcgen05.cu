@@ -589,7 +589,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // cluster barrier CTA j PULLS rows 16j .. 16j+15 of all 8 partials with coalesced 16-byte remote loads and sums
     // them in rank order.  This exchange is bound by the SM-to-SM network (112 KB per CTA, ~13 B/clk/SM with all
     // 120 CTAs exchanging at once = 8.5 K cycles; measured alternatives: 32 instead of 8 remote loads in flight per
-    // thread 13 K cycles, pushing rows to their owner with remote stores 14 K - profiles/README.md).
+    // thread 13 K cycles, pushing rows to their owner with remote stores 14 K, staggered peers 8.4 K, exchange
+    // through an L2-resident global buffer 17 K - profiles/README.md).
     const int q = warp & 3, ew = warp - 2;
     if (warp >= 2) {
         mbar_wait(bar_acc2, 0);          // GEMM 2 complete: the operand buffers may be overwritten

@@ -1,5 +1,5 @@
 """GEMM backends of the C ABI (idb_debug_gemm) against a float64 reference.  The tcgen05 backend
-must be fp32-grade (3xTF32 split precision): the bound asserted for it is the same as for the
+must be fp32-grade (split precision on fp16 (hi, lo) pairs): the bound asserted for it is the same as for the
 fp32 SIMT kernel, far below plain-TF32 error (~5e-4)."""
 import pytest
 import torch

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module", params=["simt", "tcgen05"])
 def eng(request):
-    """Every parity test runs with both GEMM backends (fp32 SIMT and tcgen05 3xTF32)."""
+    """Every parity test runs with both GEMM backends (fp32 SIMT and tcgen05 split-precision; the latter includes the fused feed-forward cluster kernel)."""
     from interdiff_b200.engine import Engine
     e = Engine("cuda:0")
     e.set_gemm_backend(request.param)

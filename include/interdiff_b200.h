@@ -36,6 +36,9 @@ int idb_set_dependent_launch(idb_handle* h, int on);
 /* Feed-forward block of a decoder layer as one cluster kernel (default 1; tensor backend, d_model 256, d_ff 1024);
    0 = the two separate GEMMs (bisecting / profiling). */
 int idb_set_fused_mlp(idb_handle* h, int on);
+/* Cluster-pruned nearest-neighbour search when the target is the loaded body mesh (default 1; results are identical
+   to the brute-force scan, index ties included); 0 = always brute force. */
+int idb_set_nn_pruning(idb_handle* h, int on);
 
 /* ---- denoiser: MDM.forward / MDM._decode --------------------------------------------------
  * replaces model/diffusion_smpl.py:239-246,226-237 (variant 0) and

@@ -27,6 +27,7 @@ _SIGS = {
     "idb_set_gemm_backend": (C.c_int, [_P, C.c_int]),
     "idb_set_dependent_launch": (C.c_int, [_P, C.c_int]),
     "idb_set_fused_mlp": (C.c_int, [_P, C.c_int]),
+    "idb_set_nn_pruning": (C.c_int, [_P, C.c_int]),
     "idb_debug_mlp": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "idb_debug_last_ms": (C.c_double, [_P]),
     "idb_denoiser_init": (C.c_int, [_P, C.POINTER(DenoiserConfig)]),

@@ -59,6 +59,11 @@ extern "C" int idb_set_dependent_launch(idb_handle* h, int on) {
     return IDB_OK;
 }
 
+extern "C" int idb_set_nn_pruning(idb_handle* h, int on) {
+    if (!h) return IDB_ERR_ARG;
+    h->nn_pruning = on ? 1 : 0;
+    return IDB_OK;
+}
 extern "C" double idb_debug_last_ms(const idb_handle* h) { return h ? h->last_ms : 0.0; }
 extern "C" int idb_set_fused_mlp(idb_handle* h, int on) {
     if (!h) return IDB_ERR_ARG;

@@ -97,6 +97,7 @@ struct idb_handle {
     int gemm_backend = 1;     // 0 = fp32 SIMT (debug / bisect), 1 = tcgen05 split-fp16 (default)
     int pdl = 1;              // programmatic dependent launch between the kernels of a sampling step
     double last_ms = 0.0;     // mean launch time of the last timed debug hook
+    int nn_pruning = 1;       // cluster-pruned nearest-neighbour search for body-mesh targets (identical results)
     int fused_mlp = 1;        // feed-forward block as ONE cluster kernel (tensor backend, d_model 256, d_ff 1024)
     void* scratch = nullptr; size_t scratch_bytes = 0;   // on-the-fly operand splits of idb_gemm
     Denoiser den;

@@ -82,6 +82,137 @@ k_signed_nn(const float* __restrict__ query, const float* __restrict__ target, c
     if (vec_out) { vec_out[o * 3] = vx; vec_out[o * 3 + 1] = vy; vec_out[o * 3 + 2] = vz; }
 }
 
+// Same result as k_signed_nn, bit for bit, with most of the 6890 candidates pruned.  The target vertices come
+// grouped into NN_CLUSTERS clusters (BodyModel::nn_vid / nn_off).  One block = one frame x a chunk of queries:
+// it stages the frame's vertices cluster-sorted in shared memory and computes a bounding sphere per cluster
+// from the POSED vertices; then one warp per query: (1) squared centre distances for 8 clusters per lane, (2) the
+// cluster with the nearest centre is scanned to seed the minimum d0, (3) only clusters with |q - c| <= sqrt(d0) + r
+// (1e-4 relative slack on the safe side) are scanned.  Candidate
+// distances use exactly the brute-force expression, candidates compare lexicographically on (distance, vertex
+// id), and a cluster holding a vertex at the final minimum distance can never be skipped (that distance is <= d0),
+// so the FIRST minimum of the brute-force scan is reproduced.
+__device__ __forceinline__ float nn_dist2(float qx, float qy, float qz, float x, float y, float z) {
+    const float dx = qx - x, dy = qy - y, dz = qz - z;
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+__global__ void __launch_bounds__(512)
+k_signed_nn_pruned(const float* __restrict__ query, const float* __restrict__ target, const float* __restrict__ tnormals,
+                   float* __restrict__ sdist, int32_t* __restrict__ idx_out, float* __restrict__ vec_out, int Pq, int Pt,
+                   const uint16_t* __restrict__ vid_sorted, const int32_t* __restrict__ coff, int qchunk) {
+    extern __shared__ __align__(16) float nsm[];
+    const int Ptp = (Pt + 3) & ~3;
+    float* xs = nsm; float* ys = xs + Ptp; float* zs = ys + Ptp;
+    float4* cen = reinterpret_cast<float4*>(zs + Ptp);                 // centre xyz, radius (< 0: empty cluster)
+    int32_t* off = reinterpret_cast<int32_t*>(cen + NN_CLUSTERS);       // [NN_CLUSTERS + 1] (+3 pad)
+    uint16_t* vid = reinterpret_cast<uint16_t*>(off + NN_CLUSTERS + 4);
+    const int f = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* qb = query + (size_t)f * Pq * 3;
+    const float* tb = target + (size_t)f * Pt * 3;
+    for (int i = tid; i < Pt; i += 512) {
+        const int v = vid_sorted[i];
+        vid[i] = (uint16_t)v;
+        xs[i] = tb[(size_t)v * 3]; ys[i] = tb[(size_t)v * 3 + 1]; zs[i] = tb[(size_t)v * 3 + 2];
+    }
+    for (int i = tid; i <= NN_CLUSTERS; i += 512) off[i] = coff[i];
+    __syncthreads();
+    for (int c = tid; c < NN_CLUSTERS; c += 512) {
+        const int b = off[c], e = off[c + 1];
+        float4 o = make_float4(0.f, 0.f, 0.f, -1.f);
+        if (e > b) {
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            for (int i = b; i < e; i++) { sx += xs[i]; sy += ys[i]; sz += zs[i]; }
+            const float inv = 1.0f / (float)(e - b);
+            o.x = sx * inv; o.y = sy * inv; o.z = sz * inv;
+            float r2 = 0.f;
+            for (int i = b; i < e; i++) r2 = fmaxf(r2, nn_dist2(o.x, o.y, o.z, xs[i], ys[i], zs[i]));
+            o.w = sqrtf(r2) * 1.00001f + 1e-7f;
+        }
+        cen[c] = o;
+    }
+    __syncthreads();
+    const int q0 = blockIdx.x * qchunk, q1 = min(Pq, q0 + qchunk);
+    unsigned* cand = reinterpret_cast<unsigned*>(vid + Ptp) + warp * (NN_CLUSTERS / 32);     // per-warp candidate bit sets
+    for (int q = q0 + warp; q < q1; q += 16) {
+        const float qx = qb[q * 3], qy = qb[q * 3 + 1], qz = qb[q * 3 + 2];
+        // squared distances to the centres of clusters lane + 32k; the nearest centre seeds the search
+        float dc2[NN_CLUSTERS / 32], rad[NN_CLUSTERS / 32];
+        float dcmin = INFINITY; int cmin = 0;
+#pragma unroll
+        for (int k = 0; k < NN_CLUSTERS / 32; k++) {
+            const int c = lane + 32 * k;
+            const float4 cc = cen[c];
+            rad[k] = cc.w;
+            dc2[k] = nn_dist2(qx, qy, qz, cc.x, cc.y, cc.z);
+            if (cc.w >= 0.f && dc2[k] < dcmin) { dcmin = dc2[k]; cmin = c; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, dcmin, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, cmin, o);
+            if (od < dcmin || (od == dcmin && oc < cmin)) { dcmin = od; cmin = oc; }
+        }
+        float bd = INFINITY; int bi = 0x7fffffff;
+        {
+            const int b = off[cmin], e = off[cmin + 1];
+            for (int i = b + lane; i < e; i += 32) {
+                const float d = nn_dist2(qx, qy, qz, xs[i], ys[i], zs[i]);
+                const int v = vid[i];
+                if (d < bd || (d == bd && v < bi)) { bd = d; bi = v; }
+            }
+        }
+        float bound = bd;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) bound = fminf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+        // a cluster can hold a vertex at distance^2 <= bound only if |q - c| <= sqrt(bound) + r; the test is done on
+        // squares with a 1e-4 relative slack on the safe side (the computed quantities are good to ~1e-6)
+        float sb;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sb) : "f"(bound));
+        sb *= 1.0001f;
+#pragma unroll
+        for (int k = 0; k < NN_CLUSTERS / 32; k++) {
+            const float lim = sb + rad[k];
+            const unsigned m = __ballot_sync(0xffffffffu, rad[k] >= 0.f && dc2[k] * 0.9999f <= lim * lim && (lane + 32 * k) != cmin);
+            if (lane == 0) cand[k] = m;
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int k = 0; k < NN_CLUSTERS / 32; k++) {
+            unsigned m = cand[k];
+            while (m) {
+                const int c = __ffs(m) - 1 + 32 * k;
+                m &= m - 1;
+                const int b = off[c], e = off[c + 1];
+                for (int i = b + lane; i < e; i += 32) {
+                    const float d = nn_dist2(qx, qy, qz, xs[i], ys[i], zs[i]);
+                    const int v = vid[i];
+                    if (d < bd || (d == bd && v < bi)) { bd = d; bi = v; }
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (lane == 0) {
+            if (bi == 0x7fffffff) bi = 0;      // no finite distance (NaN input): same answer as the brute-force scan
+            const float vx = qx - tb[(size_t)bi * 3], vy = qy - tb[(size_t)bi * 3 + 1], vz = qz - tb[(size_t)bi * 3 + 2];
+            float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
+            if (tnormals) {
+                const float* n = tnormals + ((size_t)f * Pt + bi) * 3;
+                const float dot = __fadd_rn(__fadd_rn(__fmul_rn(n[0], vx), __fmul_rn(n[1], vy)), __fmul_rn(n[2], vz));
+                d *= (dot > 0.f) ? 1.0f : ((dot < 0.f) ? -1.0f : 0.0f);
+            }
+            const size_t o = (size_t)f * Pq + q;
+            if (sdist) sdist[o] = d;
+            if (idx_out) idx_out[o] = bi;
+            if (vec_out) { vec_out[o * 3] = vx; vec_out[o * 3 + 1] = vy; vec_out[o * 3 + 2] = vz; }
+        }
+    }
+}
+
 }  // namespace
 
 namespace {
@@ -109,6 +240,22 @@ extern "C" int idb_vertex_normals(idb_handle* h, int F, const float* verts, floa
 extern "C" int idb_signed_nn(idb_handle* h, int F, int Pq, int Pt, const float* query, const float* target,
                              const float* target_normals, float* signed_dist, int32_t* idx, float* vec, void* stream) {
     if (!h || !query || !target || F <= 0 || Pq <= 0 || Pt <= 0) return IDB_ERR_ARG;
+    // body-mesh targets take the cluster-pruned search (identical results, ~8x fewer candidate evaluations)
+    if (h->nn_pruning && h->body && h->body->nn_vid && Pt == h->body->V && Pt <= 12000) {
+        const int Ptp = (Pt + 3) & ~3;
+        const size_t smem = sizeof(float) * 3 * Ptp + sizeof(float4) * NN_CLUSTERS + sizeof(int32_t) * (NN_CLUSTERS + 4) + sizeof(uint16_t) * Ptp + sizeof(unsigned) * 16 * (NN_CLUSTERS / 32);
+        static bool attr = false;
+        if (!attr) {
+            CUDA_TRY(h, cudaFuncSetAttribute(k_signed_nn_pruned, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr = true;
+        }
+        const int qchunk = 1024;
+        dim3 grid((Pq + qchunk - 1) / qchunk, F);
+        k_signed_nn_pruned<<<grid, 512, smem, (cudaStream_t)stream>>>(query, target, target_normals, signed_dist, idx, vec, Pq, Pt,
+                                                                      h->body->nn_vid, h->body->nn_off, qchunk);
+        LAUNCH_CHECK(h);
+        return IDB_OK;
+    }
     dim3 grid((Pq + 255) / 256, F);
     k_signed_nn<<<grid, 256, 0, (cudaStream_t)stream>>>(query, target, target_normals, signed_dist, idx, vec, Pq, Pt);
     LAUNCH_CHECK(h);

@@ -259,6 +259,40 @@ extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const 
         CUDA_TRY(h, up(off.data(), off.size() * 4, (void**)&m.vf_off));
         CUDA_TRY(h, up(ent.data(), ent.size() * 4, (void**)&m.vf_ent));
     }
+    // Vertex clusters for the pruned nearest-neighbour search (geometry.cu): k-means on the template; clusters of
+    // neighbouring template vertices stay compact under articulation.  Any partition is CORRECT (bounds are
+    // recomputed from the posed vertices of every frame); compactness only decides how much gets pruned.
+    if (V <= 65535) {
+        const int C = NN_CLUSTERS;
+        std::vector<double> cx(C), cy(C), cz(C);
+        for (int c = 0; c < C; c++) {
+            const int v = (int)((long long)c * V / C);
+            cx[c] = vt[(size_t)v * 3]; cy[c] = vt[(size_t)v * 3 + 1]; cz[c] = vt[(size_t)v * 3 + 2];
+        }
+        std::vector<int> asg(V, 0);
+        for (int it = 0; it < 10; it++) {
+            for (int v = 0; v < V; v++) {
+                double best = 1e300; int bc = 0;
+                for (int c = 0; c < C; c++) {
+                    const double dx = vt[(size_t)v * 3] - cx[c], dy = vt[(size_t)v * 3 + 1] - cy[c], dz = vt[(size_t)v * 3 + 2] - cz[c];
+                    const double d = dx * dx + dy * dy + dz * dz;
+                    if (d < best) { best = d; bc = c; }
+                }
+                asg[v] = bc;
+            }
+            std::vector<double> sx(C, 0), sy(C, 0), sz(C, 0); std::vector<int> cnt(C, 0);
+            for (int v = 0; v < V; v++) { const int c = asg[v]; sx[c] += vt[(size_t)v * 3]; sy[c] += vt[(size_t)v * 3 + 1]; sz[c] += vt[(size_t)v * 3 + 2]; cnt[c]++; }
+            for (int c = 0; c < C; c++) if (cnt[c]) { cx[c] = sx[c] / cnt[c]; cy[c] = sy[c] / cnt[c]; cz[c] = sz[c] / cnt[c]; }
+        }
+        std::vector<int32_t> off(C + 1, 0);
+        for (int v = 0; v < V; v++) off[asg[v] + 1]++;
+        for (int c = 0; c < C; c++) off[c + 1] += off[c];
+        std::vector<uint16_t> vid(V);
+        std::vector<int32_t> cur(off.begin(), off.end() - 1);
+        for (int v = 0; v < V; v++) vid[cur[asg[v]]++] = (uint16_t)v;      // ascending ids inside a cluster
+        CUDA_TRY(h, up(vid.data(), vid.size() * sizeof(uint16_t), (void**)&m.nn_vid));
+        CUDA_TRY(h, up(off.data(), off.size() * 4, (void**)&m.nn_off));
+    }
     const int smem_skin = (int)sizeof(float) * (Kp * FB + FB * J * 12 + NB * FB + FB * 3);
     CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_skin));
     return IDB_OK;

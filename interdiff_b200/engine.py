@@ -85,6 +85,10 @@ class Engine:
         """Programmatic dependent launch between the kernels of a step (default on; identical results)."""
         self._chk(self.lib.idb_set_dependent_launch(self._h, 1 if on else 0))
 
+    def set_nn_pruning(self, on):
+        """Cluster-pruned nearest-neighbour search for body-mesh targets (default on; identical results)."""
+        self._chk(self.lib.idb_set_nn_pruning(self._h, 1 if on else 0))
+
     def set_fused_mlp(self, on):
         """Feed-forward block as one cluster kernel (default on) vs two GEMM launches."""
         self._chk(self.lib.idb_set_fused_mlp(self._h, 1 if on else 0))

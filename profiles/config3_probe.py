@@ -56,5 +56,8 @@ ms = timed(lambda: eng.vertex_normals(verts))
 print("vertex_normals F=%d: %.3f ms (%.0f GB/s of 2 x 159 MB)" % (F, ms, 2 * F * 6890 * 12 / ms / 1e6))
 normals = eng.vertex_normals(verts)
 obj = (verts[:, ::4][:, :2048] * 1.1).contiguous()
-ms = timed(lambda: eng.signed_nn(obj, verts, normals), n=3, warm=1)
-print("signed_nn F=%d 2048x6890: %.3f ms -> %.2f T pair-evals/s" % (F, ms, F * 2048 * 6890 / ms / 1e9))
+for pr in (False, True):
+    eng.set_nn_pruning(pr)
+    ms = timed(lambda: eng.signed_nn(obj, verts, normals), n=3, warm=1)
+    print("signed_nn F=%d 2048x6890 (%s): %.3f ms -> %.2f T brute-force-equivalent pair-evals/s" % (
+        F, "cluster-pruned" if pr else "brute force", ms, F * 2048 * 6890 / ms / 1e9))

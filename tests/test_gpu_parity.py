@@ -169,6 +169,35 @@ def test_geometry(eng, smplh_np):
     assert rel(aa, tf.matrix_to_axis_angle(tf.rotation_6d_to_matrix(d6))) < 1e-5
 
 
+def test_signed_nn_pruned_equals_brute_force(eng, smplh_np):
+    """The cluster-pruned nearest-neighbour search (body-mesh targets) must reproduce the brute-force scan bit for
+    bit: indices (first minimum on ties - duplicated vertices, queries sitting exactly on a vertex), signed
+    distances and offset vectors; near, far and interior queries."""
+    eng.load_body(smplh_np)
+    g = torch.Generator().manual_seed(11)
+    F = 4
+    verts = torch.from_numpy(smplh_np["v_template"])[None].repeat(F, 1, 1).clone()
+    verts = verts * (1.0 + 0.2 * torch.rand(F, 1, 1, generator=g)) + 0.02 * torch.randn(F, 6890, 3, generator=g)
+    verts[:, 5000] = verts[:, 100]          # exact duplicates: the lower index has to win
+    verts[:, 17] = verts[:, 16]
+    verts[:, 6889] = verts[:, 0]
+    normals = eng.vertex_normals(verts)
+    q = torch.cat([verts[:, ::7] * 1.02 + 0.005 * torch.randn(F, 985, 3, generator=g),      # near the surface
+                   3.0 * torch.randn(F, 300, 3, generator=g),                                # far away
+                   0.1 * torch.randn(F, 200, 3, generator=g),                                # inside
+                   verts[:, [100, 5000, 16, 17, 0, 6889, 3333]],                             # exactly on (duplicated) vertices
+                   torch.zeros(F, 1, 3)], dim=1).contiguous()
+    eng.set_nn_pruning(True)
+    d1, i1, v1 = eng.signed_nn(q, verts, normals)
+    eng.set_nn_pruning(False)
+    d0, i0, v0 = eng.signed_nn(q, verts, normals)
+    eng.set_nn_pruning(True)
+    assert torch.equal(i1, i0)
+    assert torch.equal(d1, d0) and torch.equal(v1, v0)
+    on_vertex = i0[:, -8:-1].cpu()
+    assert torch.equal(on_vertex, torch.tensor([[100, 100, 16, 16, 0, 0, 3333]] * F, dtype=torch.int32))
+
+
 @pytest.mark.parametrize("source", ["random", "ref"])
 def test_projector(eng, smplh_np, source):
     psd = projector_weights(source)

@@ -75,6 +75,15 @@ int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const float* cond, co
 /* x (B,1,C,T), timesteps (B) int64 device, out (B,1,C,T)  == MDM.forward(x, timesteps, y) */
 int idb_denoiser_forward(idb_handle* h, const float* x, const int64_t* timesteps, float* out, void* stream);
 
+/* Conditioning encoder = the part of MDM._get_embeddings after the point-cloud encoder (reference
+ * model/diffusion_smpl.py:217-221; encoder layers :20-70, model/sublayers.py:37-203):
+ *   cond = encoder(PositionalEmbedding(bodyEmbedding(past[:, :135]) + objEmbedding(past[:, 135:]) + pc_embedding))
+ * Needs the "encoder.layers.*" tensors to have been loaded (idb_denoiser_load) before idb_denoiser_commit.
+ *   past         (B,1,C,Tp)  the first past_len frames of the motion tensor, channels [body | object]
+ *   pc_embedding (B,256)     pcEmbedding(...).view(1,B,-1)[0]   (PointNet++ itself is the remaining half of SURVEY 8f rank 1)
+ *   cond_out     (Tp,B,256)  sequence-first like the reference; feed it to idb_denoiser_bind */
+int idb_encode_condition(idb_handle* h, int B, int Tp, const float* past, const float* pc_embedding, float* cond_out, void* stream);
+
 /* ---- diffusion: SpacedDiffusion / GaussianDiffusion sampling ------------------------------
  * replaces diffusion/gaussian_diffusion.py:160-197 (tables), 277-388 (p_mean_variance, START_X,
  * FIXED_SMALL, inpainting blend :307-311), 253-275, 496-548 (p_sample), 598-736 (p_sample_loop),

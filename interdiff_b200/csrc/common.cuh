@@ -58,6 +58,13 @@ struct Denoiser {
     bool configured = false, committed = false;
     std::map<std::string, DevTensor> raw;   // reference state_dict name -> device copy
     std::vector<DenoiserLayer> layers;
+    std::vector<DenoiserLayer> enc_layers;        // conditioning encoder (empty unless its weights were loaded)
+    // encoder workspace (rows m = b*Tp + t), grown on demand by idb_encode_condition
+    int enc_cap = 0;
+    float *e_add = nullptr, *e_h = nullptr, *e_h2 = nullptr, *e_z = nullptr, *e_qkv = nullptr;
+    __half *e_xtok_b = nullptr, *e_xtok_s = nullptr, *e_h_b = nullptr, *e_h_s = nullptr, *e_h2_b = nullptr, *e_h2_s = nullptr,
+           *e_ff_b = nullptr, *e_ff_s = nullptr;
+    std::vector<void*> enc_owned;
     std::vector<float*> owned;              // packed buffers to free
     float *w_inT = nullptr, *b_in = nullptr;      // [C][D] k-major input embedding, summed bias
     float *w_in = nullptr, *w_out = nullptr;      // nn.Linear layouts for the GEMM: [D][C], [Clin][D]

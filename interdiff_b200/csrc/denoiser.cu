@@ -554,6 +554,7 @@ k_xattn_ln(const float* __restrict__ x1, const float* __restrict__ kp, const flo
 //   a = softmax over the valid slots;  y[t] = sum_s (sum_n wk[n] a[t,n,s]) x[t+s-1];  out = LN1(x + y)
 // ... followed, in the same kernel, by the layer's cross-attention block (cross_attention_tail) on the
 // LN1 rows, which never leave shared memory.
+template <bool XATTN>
 __global__ void __launch_bounds__(ANT)
 k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, const float* __restrict__ preb,
                const float* __restrict__ qt, const float* __restrict__ wk, const float* __restrict__ lnw,
@@ -571,7 +572,7 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     float* s_kp = s_x1 + SLAB * LDX;        // [HT][LDX]
     float* s_v = s_kp + HT * LDX;           // [HT][VLD]
     float* s_a = s_v + HT * VLD;            // [SLAB][PLD]     probabilities
-    float* s_z = s_a + SLAB * PLD;          // [SLAB][LDZ]
+    float* s_z = XATTN ? s_a + SLAB * PLD : s_x1;   // [SLAB][LDZ]  (encoder variant: no cross-attention buffers at all)
     float* s_kc = s_z + SLAB * LDZ;         // [HT]
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -586,16 +587,16 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int npar = prew ? 7 : 5;
-    if (tid == 0) mb_expect_tx(bar, (uint32_t)(npar + NQ + 2 * HT) * ROW_BYTES);
+    const int npar = (prew ? 2 : 0) + 2 + (XATTN ? 3 : 0);
+    if (tid == 0) mb_expect_tx(bar, (uint32_t)(npar + NQ + (XATTN ? 2 * HT : 0)) * ROW_BYTES);
     __syncwarp();
     if (tid < 7) {
         const float* src = tid == 0 ? prew : tid == 1 ? preb : tid == 2 ? lnw : tid == 3 ? lnb : tid == 4 ? bo2 : tid == 5 ? ln2w : ln2b;
-        if (src) bulk_g2s(s_par + tid * D, src, ROW_BYTES, bar);
+        if (src && (XATTN || tid < 4)) bulk_g2s(s_par + tid * D, src, ROW_BYTES, bar);
     } else if (tid >= 32 && tid < 32 + NQ) {
         bulk_g2s(s_qt + (tid - 32) * LDX, qt + (size_t)(tid - 32) * D, ROW_BYTES, bar);
     }
-    stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H, bar);
+    if (XATTN) stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H, bar);
     const float wk_n = lane < N ? wk[lane] : 0.f;
     ATRACE(1);
     pdl_wait();
@@ -690,16 +691,23 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
 #pragma unroll
         for (int i = 0; i < 8; i++) { const float d = v[i] - mean; q = fmaf(d, d, q); }
         const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+        float4 o[2];
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             const int c = half * 128 + lane * 4;
             const float4 w4 = *reinterpret_cast<const float4*>(s_par + 2 * D + c), b4 = *reinterpret_cast<const float4*>(s_par + 3 * D + c);
-            float4 o;
-            o.x = (v[half * 4 + 0] - mean) * rstd * w4.x + b4.x; o.y = (v[half * 4 + 1] - mean) * rstd * w4.y + b4.y;
-            o.z = (v[half * 4 + 2] - mean) * rstd * w4.z + b4.z; o.w = (v[half * 4 + 3] - mean) * rstd * w4.w + b4.w;
-            *reinterpret_cast<float4*>(s_x1 + r * LDX + c) = o;
+            o[half].x = (v[half * 4 + 0] - mean) * rstd * w4.x + b4.x; o[half].y = (v[half * 4 + 1] - mean) * rstd * w4.y + b4.y;
+            o[half].z = (v[half * 4 + 2] - mean) * rstd * w4.z + b4.z; o[half].w = (v[half * 4 + 3] - mean) * rstd * w4.w + b4.w;
+            if (XATTN) *reinterpret_cast<float4*>(s_x1 + r * LDX + c) = o[half];
+        }
+        if (!XATTN) {      // encoder layer: LayerNorm1 rows are the kernel's output (fp32 + fp16 pairs for the feed-forward block)
+            const size_t orow = ((size_t)b * T + r0 + r) * D;
+            *reinterpret_cast<float4*>(out + orow + lane * 4) = o[0];
+            *reinterpret_cast<float4*>(out + orow + 128 + lane * 4) = o[1];
+            if (out_b) store_pairs(o[0], o[1], out_b + orow, out_s + orow, lane);
         }
     }
+    if (!XATTN) return;
     __syncthreads();
     ATRACE(6);
     cross_attention_tail(s_x1, s_kp, s_kc, s_v, s_a, s_z, nr, HT, Tk, H, s_par + 4 * D, s_par + 5 * D, s_par + 6 * D, out, out_b, out_s,
@@ -897,6 +905,10 @@ void idb_denoiser_release(idb_handle* h) {
     for (float* p : d.owned) cudaFree(p);
     d.owned.clear();
     d.layers.clear();
+    d.enc_layers.clear();
+    for (void* p : d.enc_owned) cudaFree(p);
+    d.enc_owned.clear();
+    d.enc_cap = 0;
     d.committed = false;
 }
 
@@ -919,8 +931,8 @@ extern "C" int idb_denoiser_load(idb_handle* h, const char* name, const float* d
     Denoiser& d = h->den;
     if (!d.configured) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_init first");
     std::string s(name);
-    // tensors on the hot path only (the conditioning encoder / PointNet++ are a later row)
-    bool want = s.rfind("decoder.layers.", 0) == 0 || s.rfind("bodyEmbedding.", 0) == 0 || s.rfind("objEmbedding.", 0) == 0 ||
+    // tensors of the sampling hot path and, when given, of the conditioning encoder (PointNet++ is a later row)
+    bool want = s.rfind("decoder.layers.", 0) == 0 || s.rfind("encoder.layers.", 0) == 0 || s.rfind("bodyEmbedding.", 0) == 0 || s.rfind("objEmbedding.", 0) == 0 ||
                 s.rfind("bodyFinalLinear.", 0) == 0 || s.rfind("objFinalLinear.", 0) == 0 ||
                 s.rfind("embedTimeStep.time_embed.", 0) == 0 || s == "PositionalEmbedding.pe";
     if (!want || s.find("inv_freq") != std::string::npos) return IDB_OK;
@@ -1035,10 +1047,12 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
         k_temb_table<<<d.pe_rows, 256>>>(d.pe, d.te_w0T, d.te_b0, d.te_w2T, d.te_b2, d.b_in, d.temb_tab);
         LAUNCH_CHECK(h);
     }
-    for (int l = 0; l < c.n_layers; l++) {
+    // one transformer layer of the decoder ("decoder.layers.") or of the conditioning encoder ("encoder.layers.": no
+    // cross-attention block; its norm2 takes the place of the decoder's norm3 = the layer's final, "pending" norm)
+    auto build_layer = [&](const std::string& stack, int l, bool is_dec, std::vector<DenoiserLayer>& dst) -> int {
         DenoiserLayer L;
         L.qan = (c.qan_mask >> l) & 1;
-        const std::string p = "decoder.layers." + std::to_string(l) + ".";
+        const std::string p = stack + std::to_string(l) + ".";
         if (L.qan) {
             GET(q, p + "queries", N, D) GET(wk, p + "wk", N, 1)
             // fold: per-head unit norm (+1e-6), / sqrt(hd) (model/sublayers.py:18-35), * D^-0.5
@@ -1089,7 +1103,7 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
             }
             L.w_qkvf = P.up(wf); L.b_qkvf = P.up(bf); L.bo_f = P.up(bof);
         }
-        {
+        if (is_dec) {
             GET(w, p + "multihead_attn.in_proj_weight", 3 * D, D) GET(b, p + "multihead_attn.in_proj_bias", 3 * D)
             GET(wo, p + "multihead_attn.out_proj.weight", D, D) GET(bo, p + "multihead_attn.out_proj.bias", D)
             L.w_qc = w->p; L.b_qc = b->p; L.w_kvc = w->p + (size_t)D * D; L.b_kvc = b->p + D; L.w_oc = wo->p; L.b_oc = bo->p;
@@ -1099,14 +1113,34 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
                 for (int o = 0; o < D; o++) for (int k = 0; k < D; k++) wT[(size_t)k * D + o] = hwq[(size_t)o * D + k];
                 L.w_qcT = P.up(wT);
             }
+        }
+        {
             GET(w1, p + "linear1.weight", F, D) GET(b1, p + "linear1.bias", F)
             GET(w2, p + "linear2.weight", D, F) GET(b2, p + "linear2.bias", D)
             L.w1 = w1->p; L.b1 = b1->p; L.w2 = w2->p; L.b2 = b2->p;
-            GET(n1w, p + "norm1.weight", D) GET(n1b, p + "norm1.bias", D) GET(n2w, p + "norm2.weight", D)
-            GET(n2b, p + "norm2.bias", D) GET(n3w, p + "norm3.weight", D) GET(n3b, p + "norm3.bias", D)
-            L.ln1w = n1w->p; L.ln1b = n1b->p; L.ln2w = n2w->p; L.ln2b = n2b->p; L.ln3w = n3w->p; L.ln3b = n3b->p;
+            GET(n1w, p + "norm1.weight", D) GET(n1b, p + "norm1.bias", D) GET(n2w, p + "norm2.weight", D) GET(n2b, p + "norm2.bias", D)
+            L.ln1w = n1w->p; L.ln1b = n1b->p;
+            if (is_dec) {
+                GET(n3w, p + "norm3.weight", D) GET(n3b, p + "norm3.bias", D)
+                L.ln2w = n2w->p; L.ln2b = n2b->p; L.ln3w = n3w->p; L.ln3b = n3b->p;
+            } else {
+                L.ln3w = n2w->p; L.ln3b = n2b->p;
+            }
         }
-        d.layers.push_back(L);
+        dst.push_back(L);
+        return IDB_OK;
+    };
+    for (int l = 0; l < c.n_layers; l++) {
+        const int rc = build_layer("decoder.layers.", l, true, d.layers);
+        if (rc) return rc;
+    }
+    // conditioning encoder (optional: present when its tensors were loaded)
+    d.enc_layers.clear();
+    if (d.raw.count("encoder.layers.0.linear1.weight")) {
+        for (int l = 0; l < c.n_layers; l++) {
+            const int rc = build_layer("encoder.layers.", l, false, d.enc_layers);
+            if (rc) return rc;
+        }
     }
 #undef GET
     if (P.rc) return P.rc;
@@ -1125,11 +1159,12 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
         (void)Cp;
         int rc = split(d.w_in, D, (C + 3) & ~3, Cp8, &d.w_in_b, &d.w_in_s);
         if (!rc) rc = split(d.w_out, Clin, D, D, &d.w_out_b, &d.w_out_s);
-        for (auto& L : d.layers) {
-            if (!rc && !L.qan) rc = split(L.w_qkvf, 2 * D + H * D, D, D, &L.w_qkvf_b, &L.w_qkvf_s);
-            if (!rc) rc = split(L.w1, F, D, D, &L.w1_b, &L.w1_s);
-            if (!rc) rc = split(L.w2, D, F, F, &L.w2_b, &L.w2_s);
-        }
+        for (auto* stack : {&d.layers, &d.enc_layers})
+            for (auto& L : *stack) {
+                if (!rc && !L.qan) rc = split(L.w_qkvf, 2 * D + H * D, D, D, &L.w_qkvf_b, &L.w_qkvf_s);
+                if (!rc) rc = split(L.w1, F, D, D, &L.w1_b, &L.w1_s);
+                if (!rc) rc = split(L.w2, D, F, F, &L.w2_b, &L.w2_s);
+            }
         if (rc) return rc;
         CUDA_TRY(h, cudaDeviceSynchronize());
     }
@@ -1210,6 +1245,9 @@ static size_t xattn_tail_smem(int Tk, int H) {   // s_x1, s_kp, s_v, s_a, s_z, s
     return sizeof(float) * ((size_t)SLAB * (D + 8) + HT * (D + 8) + HT * (D + 4) + (size_t)SLAB * 72 + (size_t)SLAB * LDZ + HT + 4);
 }
 static size_t xattn_smem(int Tk, int H) { return sizeof(float) * (4 + 3 * D) + xattn_tail_smem(Tk, H); }
+static size_t qan_enc_smem() {      // encoder variant: barriers, parameter rows, s_x, s_qt, s_z
+    return sizeof(float) * (4 + 7 * D + (size_t)(SLAB + 2) * (D + 8) + 30 * (D + 8) + (size_t)SLAB * LDZ + 4);
+}
 static size_t qan_smem(int Tk, int H) {      // barriers, 7 parameter rows, s_x, s_qt + the cross-attention buffers
     return sizeof(float) * (4 + 7 * D + (size_t)(SLAB + 2) * (D + 8) + 30 * (D + 8)) + xattn_tail_smem(Tk, H);
 }
@@ -1241,7 +1279,7 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
         if (L.qan) {
             const float* in = pending ? d.z : d.h;
             // QaN block + LN1 + cross-attention + LN2 in one kernel: (z | h) -> (d.h2, pairs)
-            idb_launch(pdl, k_qan_xattn_ln, slab_grid, ANT, qan_smem(Tm, H), st, in, pending ? pending->ln3w : nullptr,
+            idb_launch(pdl, k_qan_xattn_ln<true>, slab_grid, ANT, qan_smem(Tm, H), st, in, pending ? pending->ln3w : nullptr,
                        pending ? pending->ln3b : nullptr, L.qt, L.wk, L.ln1w, L.ln1b, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc,
                        L.ln2w, L.ln2b, d.h2, d.h2_b, d.h2_s, T, N, B, Tm, H);
             LAUNCH_CHECK(h);
@@ -1367,9 +1405,121 @@ int idb_denoiser_run(idb_handle* h, const float* x, const long long* tstep, cons
 
 int idb_denoiser_prepare_kernels(idb_handle* h) {
     // opt in to > 48 KB dynamic shared memory once (T <= 36, Tm <= 16 supported: the self-attention slab kernel keeps all folded values of a sample, 4*T*256 floats, in shared memory)
-    CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem(16, 4)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem(16, 4)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_enc_smem()));
     CUDA_TRY(h, cudaFuncSetAttribute(k_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_smem(16, 4)));
     CUDA_TRY(h, cudaFuncSetAttribute(k_attn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(36, 4)));
+    return IDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conditioning encoder (the part of MDM._get_embeddings after the point-cloud encoder,
+// model/diffusion_smpl.py:217-221): cond = encoder(PositionalEmbedding(bodyEmbedding(past body) +
+// objEmbedding(past obj) + pc_embedding)).  Runs once per batch before idb_denoiser_bind; the layers reuse the
+// decoder's kernels (folded-QKV GEMM + k_attn_ln, the QaN kernel without its cross-attention half, the fused
+// feed-forward kernel), rows m = b*Tp + t.
+namespace {
+
+// past (B,1,C,Tp) -> token pairs [B*Tp][Cp] (zero padded) + addend[b*Tp+t][:] = (pc[b] + b_body + b_obj) + pe[t]
+__global__ void k_cond_tokens(const float* __restrict__ past, const float* __restrict__ pc, const float* __restrict__ b_in,
+                              const float* __restrict__ pe, __half* __restrict__ xtok_b, __half* __restrict__ xtok_s,
+                              float* __restrict__ add, int C, int Cp, int Tp) {
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < Tp * Cp; i += blockDim.x) {
+        const int t = i / Cp, c = i % Cp;
+        const size_t o = ((size_t)b * Tp + t) * Cp + c;
+        split_f16(c < C ? past[((size_t)b * C + c) * Tp + t] : 0.f, xtok_b[o], xtok_s[o]);
+    }
+    for (int i = threadIdx.x; i < Tp * (D / 4); i += blockDim.x) {
+        const int t = i / (D / 4), c4 = i % (D / 4);
+        const float4 p = reinterpret_cast<const float4*>(pc + (size_t)b * D)[c4], bi = reinterpret_cast<const float4*>(b_in)[c4];
+        const float4 q = reinterpret_cast<const float4*>(pe + (size_t)t * D)[c4];
+        reinterpret_cast<float4*>(add + ((size_t)b * Tp + t) * D)[c4] =
+            make_float4((p.x + bi.x) + q.x, (p.y + bi.y) + q.y, (p.z + bi.z) + q.z, (p.w + bi.w) + q.w);
+    }
+}
+
+// LayerNorm of token rows m = b*Tp + t, written in the reference's sequence-first layout out[(t*B + b)][:]
+__global__ void k_ln_seq_first(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bb,
+                               float* __restrict__ out, int B, int Tp) {
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
+    if (m >= B * Tp) return;
+    const int b = m / Tp, t = m - b * Tp;
+    warp_ln_row(a + (size_t)m * D, w, bb, out + ((size_t)t * B + b) * D, lane);
+}
+
+}  // namespace
+
+extern "C" int idb_encode_condition(idb_handle* h, int B, int Tp, const float* past, const float* pc_embedding, float* cond_out,
+                                    void* stream) {
+    if (!h || !past || !pc_embedding || !cond_out || B <= 0 || Tp <= 0) return IDB_ERR_ARG;
+    Denoiser& d = h->den;
+    if (!d.committed) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_commit first");
+    if (d.enc_layers.empty()) return idb_fail(h, IDB_ERR_STATE, "the conditioning encoder's weights (encoder.layers.*) were not loaded");
+    if (Tp > 36) return idb_fail(h, IDB_ERR_ARG, "supported past window: <= 36 frames");
+    const idb_denoiser_config& c = d.cfg;
+    const int M = B * Tp, F = c.d_ff, H = c.n_heads, N = c.n_queries, C = c.c_body + c.c_obj, Cp = (C + 7) & ~7;
+    if (c.variant != 0) return idb_fail(h, IDB_ERR_ARG, "idb_encode_condition: SMPL model only");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool fused = h->gemm_backend == 1 && h->fused_mlp && idb_mlp_tcgen05_supported(D, F);
+    if (M > d.enc_cap) {
+        for (void* p : d.enc_owned) cudaFree(p);
+        d.enc_owned.clear();
+        d.enc_cap = 0;
+        auto A = [&](float** p, size_t n) { if (cudaMalloc((void**)p, n * sizeof(float)) != cudaSuccess) return 1; d.enc_owned.push_back(*p); return 0; };
+        auto AH = [&](__half** p, size_t n) { if (cudaMalloc((void**)p, n * sizeof(__half)) != cudaSuccess) return 1; d.enc_owned.push_back(*p); return 0; };
+        int rc = 0;
+        rc |= A(&d.e_add, (size_t)M * D); rc |= A(&d.e_h, (size_t)M * D); rc |= A(&d.e_h2, (size_t)M * D); rc |= A(&d.e_z, (size_t)M * D);
+        rc |= A(&d.e_qkv, (size_t)M * (2 * D + H * D));
+        rc |= AH(&d.e_xtok_b, (size_t)M * Cp); rc |= AH(&d.e_xtok_s, (size_t)M * Cp);
+        rc |= AH(&d.e_h_b, (size_t)M * D); rc |= AH(&d.e_h_s, (size_t)M * D); rc |= AH(&d.e_h2_b, (size_t)M * D); rc |= AH(&d.e_h2_s, (size_t)M * D);
+        rc |= AH(&d.e_ff_b, (size_t)M * F); rc |= AH(&d.e_ff_s, (size_t)M * F);
+        if (rc) return idb_fail(h, IDB_ERR_CUDA, "out of device memory (encoder workspace)");
+        d.enc_cap = M;
+    }
+    const bool pdl = h->pdl != 0;
+    int rc;
+    k_cond_tokens<<<B, 256, 0, st>>>(past, pc_embedding, d.b_in, d.pe, d.e_xtok_b, d.e_xtok_s, d.e_add, C, Cp, Tp);
+    LAUNCH_CHECK(h);
+    if ((rc = linear(h, d.e_xtok_b, d.e_xtok_s, Cp, d.w_in_b, d.w_in_s, Cp, nullptr, d.e_add, d.e_h, d.e_h_b, d.e_h_s, D, M, D, Cp, EPI_RES, st)))
+        return rc;
+    const dim3 slab_grid(B, (Tp + SLAB - 1) / SLAB);
+    const int ln_blocks = (M * 32 + 255) / 256;
+    const DenoiserLayer* pending = nullptr;      // layer whose final norm (norm2) has not been applied to e_z yet
+    for (auto& L : d.enc_layers) {
+        if (L.qan) {
+            idb_launch(pdl, k_qan_xattn_ln<false>, slab_grid, ANT, qan_enc_smem(), st, pending ? d.e_z : d.e_h,
+                       pending ? pending->ln3w : nullptr, pending ? pending->ln3b : nullptr, L.qt, L.wk, L.ln1w, L.ln1b,
+                       (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr,
+                       (const float*)nullptr, d.e_h2, d.e_h2_b, d.e_h2_s, Tp, N, B, 0, H);
+            LAUNCH_CHECK(h);
+        } else {
+            if (pending) {
+                idb_launch(pdl, k_ln, ln_blocks, 256, 0, st, d.e_z, pending->ln3w, pending->ln3b, d.e_h, d.e_h_b, d.e_h_s, M);
+                LAUNCH_CHECK(h);
+            }
+            const int NQ = 2 * D + H * D;
+            if ((rc = linear(h, d.e_h_b, d.e_h_s, D, L.w_qkvf_b, L.w_qkvf_s, D, L.b_qkvf, nullptr, d.e_qkv, nullptr, nullptr, NQ, M, NQ, D,
+                             EPI_BIAS, st))) return rc;
+            idb_launch(pdl, k_attn_ln, slab_grid, ANT, attn_smem(Tp, H), st, d.e_qkv, NQ, d.e_qkv + D, NQ, d.e_qkv + 2 * D, NQ, d.e_h,
+                       L.bo_f, L.ln1w, L.ln1b, d.e_h2, d.e_h2_b, d.e_h2_s, Tp, H);
+            LAUNCH_CHECK(h);
+        }
+        if (fused) {
+            if ((rc = idb_mlp_tcgen05(h, d.e_h2_b, d.e_h2_s, L.w1_b, L.w1_s, L.b1, L.w2_b, L.w2_s, L.b2, d.e_h2, D, d.e_z, D, M, h->pdl, st)))
+                return rc;
+        } else {
+            if ((rc = linear(h, d.e_h2_b, d.e_h2_s, D, L.w1_b, L.w1_s, D, L.b1, nullptr, nullptr, d.e_ff_b, d.e_ff_s, F, M, F, D,
+                             EPI_BIAS | EPI_GELU, st))) return rc;
+            if ((rc = linear(h, d.e_ff_b, d.e_ff_s, F, L.w2_b, L.w2_s, F, L.b2, d.e_h2, d.e_z, nullptr, nullptr, D, M, D, F, EPI_BIAS | EPI_RES, st)))
+                return rc;
+        }
+        pending = &L;
+    }
+    idb_launch(pdl, k_ln_seq_first, ln_blocks, 256, 0, st, d.e_z, pending->ln3w, pending->ln3b, cond_out, B, Tp);
+    LAUNCH_CHECK(h);
     return IDB_OK;
 }
 

@@ -252,6 +252,15 @@ class Engine:
         self._keep_loop = [tape, gt, m]
         return out
 
+    def encode_condition(self, past, pc_embedding):
+        """cond (Tp,B,256) = conditioning encoder on the past frames (B,1,C,Tp) + point-cloud embedding (B,256)
+        (reference MDM._get_embeddings after pcEmbedding); needs the encoder.layers.* weights loaded."""
+        past, pc = self._f32(past), self._f32(pc_embedding)
+        B, Tp = past.shape[0], past.shape[-1]
+        out = torch.empty(Tp, B, 256, device=self.device)
+        self._chk(self.lib.idb_encode_condition(self._h, B, Tp, self._ptr(past), self._ptr(pc), self._ptr(out), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ body model / geometry
     def load_body(self, smplh):
         f = lambda k: np.ascontiguousarray(np.asarray(smplh[k]), dtype=np.float32)

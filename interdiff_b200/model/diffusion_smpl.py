@@ -29,7 +29,7 @@ class _EngineHost:
     rotary = "absolute"   # local-attention <= 1.5 rotary placement; 'bucketed' for >= 1.6
 
     def _hot_state(self):
-        keep = ("decoder.", "bodyEmbedding.", "objEmbedding.", "bodyFinalLinear.", "objFinalLinear.",
+        keep = ("decoder.", "encoder.", "bodyEmbedding.", "objEmbedding.", "bodyFinalLinear.", "objFinalLinear.",
                 "embedTimeStep.time_embed.", "PositionalEmbedding.pe")
         return {k: v for k, v in self.state_dict().items() if k.startswith(keep)}
 
@@ -94,10 +94,42 @@ class MDM(_EngineHost, nn.Module):
         self.bodyFutureEmbedding = nn.Parameter(torch.empty(args.future_len, 1, D).uniform_(-1, 1))
         self.objFutureEmbedding = nn.Parameter(torch.empty(args.future_len, 1, D).uniform_(-1, 1))
 
+    @staticmethod
+    def _axis_angle_to_rot6d(aa):
+        """matrix_to_rotation_6d(axis_angle_to_matrix(aa)) (pytorch3d convention: first two ROWS), aa (...,3)."""
+        th = aa.norm(dim=-1, keepdim=True)
+        k = aa / th.clamp_min(1e-12)
+        kx, ky, kz = k[..., 0], k[..., 1], k[..., 2]
+        c, s_ = torch.cos(th[..., 0]), torch.sin(th[..., 0])
+        C = 1 - c
+        return torch.stack([c + kx * kx * C, kx * ky * C - kz * s_, kx * kz * C + ky * s_,
+                            ky * kx * C + kz * s_, c + ky * ky * C, ky * kz * C - kx * s_], dim=-1)
+
+    def encode_condition(self, past, pc_embedding):
+        """cond (past_len,B,D) from the past frames (B,1,144,past_len) and the point-cloud embedding (B,D): the part
+        of `_get_embeddings` after `pcEmbedding` (reference :217-221), on the device."""
+        return self.engine_for(past.device).encode_condition(past, pc_embedding)
+
     def _get_embeddings(self, data, device=None):
-        raise NotImplementedError(
-            "the conditioning encoder (PointNet++ set abstraction + 8-layer encoder, model/diffusion_smpl.py:195-223) is the "
-            "next row of the hot-path table (SURVEY.md 8f rank 1); pass y['cond'] explicitly")
+        """Reference :195-223.  The transformer half (embeddings + positional encoding + 8-layer encoder) runs in the
+        library; the PointNet++ set abstraction is the remaining half of SURVEY 8f rank 1, so the point-cloud
+        embedding has to come with the batch as data['pc_embedding'] (B,D) (e.g. from the reference's own
+        pcEmbedding module)."""
+        if "pc_embedding" not in data:
+            raise NotImplementedError(
+                "PointNet++ set abstraction (model/layers.py:111-175) is not built yet (SURVEY.md 8f rank 1); provide "
+                "data['pc_embedding'] = pcEmbedding(...).view(1, B, -1)[0]")
+        dev = torch.device(device) if device else data["frames"][0]["smplfit_params"]["pose"].device
+        cat = lambda key, sub, sl=slice(None): torch.cat([f[key][sub][:, sl].unsqueeze(0) for f in data["frames"]], dim=0).float().to(dev)
+        body_pose, body_trans = cat("smplfit_params", "pose", slice(0, 66)), cat("smplfit_params", "trans")
+        obj_angles, obj_trans = cat("objfit_params", "angle"), cat("objfit_params", "trans")
+        T, B, _ = body_pose.shape
+        body_pose = self._axis_angle_to_rot6d(body_pose.view(T, B, -1, 3)).view(T, B, -1)
+        obj_angles = self._axis_angle_to_rot6d(obj_angles.view(T, B, -1, 3)).view(T, B, -1)
+        gt = torch.cat([body_pose, body_trans, obj_angles, obj_trans], dim=2)                  # (T,B,144)
+        past = gt[: self.args.past_len].permute(1, 2, 0).unsqueeze(1).contiguous()              # (B,1,144,past_len)
+        embedding = self.encode_condition(past, data["pc_embedding"].to(dev).float().view(B, -1))
+        return embedding, gt
 
     def forward(self, x, timesteps, y=None):
         """x (B,1,144,T), timesteps (B,) long, y={'cond': (Tm,B,D)} -> predicted x_0 (B,1,144,T)

@@ -57,6 +57,17 @@ def mdm_hot_shapes(variant="smpl", D=256, F=None, n_layers=8, N=10, pe_rows=5000
     return s
 
 
+def mdm_encoder_shapes(variant="smpl", D=256, F=None, n_layers=8, N=10):
+    """Tensors of the conditioning encoder (MDM.encoder, model/diffusion_smpl.py:20-70): like the decoder
+    layers without the cross-attention block and norm3."""
+    F = F or (1024 if variant == "smpl" else 256)
+    s = {}
+    for l in range(n_layers):
+        d = decoder_layer_shapes("encoder.layers.%d." % l, qan=0 < l < n_layers - 1, D=D, F=F, N=N)
+        s.update({k: v for k, v in d.items() if "multihead_attn" not in k and "norm3" not in k})
+    return s
+
+
 def projector_shapes(P=67, n_pre=10):
     s = {}
     chans = [9, 32, 16, 32, 9]

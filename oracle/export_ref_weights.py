@@ -17,7 +17,9 @@ def main():
     os.makedirs(W.REF_WEIGHT_DIR, exist_ok=True)
     jobs = (("diffusion", "diffusion_smpl", W.mdm_hot_shapes("smpl", F=1024)),
             ("diffusion_skeleton", "diffusion_skeleton", W.mdm_hot_shapes("skeleton", F=256)),
-            ("correction", "correction_smpl", W.projector_shapes()))
+            ("correction", "correction_smpl", W.projector_shapes()),
+            # conditioning encoder: its own file, only the encoder tests load it
+            ("diffusion", "diffusion_smpl_encoder", W.mdm_encoder_shapes("smpl", F=1024)))
     for ck, out, shapes in jobs:
         _, sd = RL.load_ckpt(ck)
         sel = {}

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 from interdiff_b200 import synthetic as S  # noqa: E402
 from oracle import ref_loader as RL  # noqa: E402
 from oracle import transforms as tf  # noqa: E402
-from tests.helpers import mdm_weights, projector_weights  # noqa: E402
+from tests.helpers import encoder_weights, mdm_weights, projector_weights  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -61,6 +61,16 @@ def main():
         kw = {"y": {"cond": cond, "inpainted_motion": torch.from_numpy(b["gt"]), "inpainting_mask": torch.from_numpy(b["mask"])}}
         loop = run_loop(diffusion, model, tape, kw)
         np.savez_compressed(os.path.join(OUT, "mdm_smpl_%s.npz" % source), forward=out.numpy(), t=t.numpy(), loop5=loop.numpy())
+        # ---- conditioning encoder (the part of MDM._get_embeddings after the point-cloud encoder)
+        esd = encoder_weights(source)
+        emodel, _, eargs = RL.build_mdm_smpl(state_dict=esd, diffusion_steps=1000)
+        past = torch.from_numpy(b["gt"])[..., : eargs.past_len].contiguous()
+        pc = torch.randn(2, 256, generator=torch.Generator().manual_seed(7))
+        xs = past.squeeze(1).permute(2, 0, 1)
+        with torch.no_grad():
+            emb = emodel.bodyEmbedding(xs[..., :135]) + emodel.objEmbedding(xs[..., 135:]) + pc[None]
+            cond_out = emodel.encoder(emodel.PositionalEmbedding(emb))
+        np.savez_compressed(os.path.join(OUT, "cond_encoder_%s.npz" % source), pc=pc.numpy(), cond=cond_out.numpy())
         # ---- skeleton denoiser, BASELINE config 1: 1 DDPM step, B=2, T=15
         sd = mdm_weights("skeleton", source)
         model, _, args = RL.build_mdm_skeleton(state_dict=sd, diffusion_steps=1000)

@@ -158,6 +158,46 @@ def decoder(sd, tgt, memory, nhead, rotary=None, faithful=True, prefix="decoder.
     return x
 
 
+def encoder_layer_std(sd, prefix, x, nhead):
+    """torch.nn.TransformerEncoderLayer(post-norm, gelu, eval) = encoder layers 0 and 7
+    (model/diffusion_smpl.py:20-25, 62-67)."""
+    x = layer_norm(x + multihead_attention(sd, prefix + "self_attn.", x, x, nhead), sd, prefix + "norm1.")
+    return layer_norm(x + feed_forward(sd, prefix, x), sd, prefix + "norm2.")
+
+
+def encoder_layer_qan(sd, prefix, src, nhead, rotary=None, faithful=True):
+    """TransformerEncoderLayerQaN.forward, norm_first=False, stochastic_depth p=0
+    (model/sublayers.py:137-161)."""
+    qa = qa_block_faithful if faithful else qa_block_algebraic
+    x = src.clone()
+    x = layer_norm(x + qa(sd, prefix, x, nhead, rotary), sd, prefix + "norm1.")
+    x = layer_norm(x + feed_forward(sd, prefix, x), sd, prefix + "norm2.")
+    return src + (x - src)
+
+
+def encoder(sd, src, nhead, rotary=None, faithful=True, prefix="encoder.layers."):
+    """TransformerEncoder layer loop without final norm (model/layers.py:195-214): layers 0,7 standard, 1-6 QaN."""
+    n_layers = 1 + max(int(k[len(prefix):].split(".")[0]) for k in sd if k.startswith(prefix))
+    x = src
+    for i in range(n_layers):
+        p = "%s%d." % (prefix, i)
+        x = encoder_layer_qan(sd, p, x, nhead, rotary, faithful) if (p + "queries") in sd else encoder_layer_std(sd, p, x, nhead)
+    return x
+
+
+def mdm_smpl_condition(sd, past, pc_embedding, nhead=4, rotary=None, faithful=True):
+    """The part of MDM._get_embeddings after the point-cloud encoder (model/diffusion_smpl.py:217-221):
+    embedding of the PAST frames + point-cloud embedding + positional encoding -> 8-layer encoder.
+    past: (B,1,C,Tp) = the first past_len frames of the motion tensor (channels [body | object]),
+    pc_embedding: (B,D) = pcEmbedding(...).view(1,B,-1)[0].  Returns cond (Tp,B,D)."""
+    xs = past.squeeze(1).permute(2, 0, 1).contiguous()  # (Tp,B,C)
+    nb = sd["bodyEmbedding.weight"].shape[1]
+    emb = F.linear(xs[..., :nb], sd["bodyEmbedding.weight"], sd["bodyEmbedding.bias"]) \
+        + F.linear(xs[..., nb:], sd["objEmbedding.weight"], sd["objEmbedding.bias"]) + pc_embedding[None]
+    emb = emb + sd["PositionalEmbedding.pe"][: emb.shape[0]]
+    return encoder(sd, emb, nhead, rotary, faithful)
+
+
 def timestep_embed(sd, timesteps):
     """TimestepEmbedder.forward (model/layers.py:42-43): pe[t] -> Linear -> SiLU -> Linear,
     indexing the SAME sinusoid table as the positional encoding.  Returns (1,B,D)."""

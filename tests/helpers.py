@@ -31,6 +31,23 @@ def mdm_weights(variant="smpl", source="auto", seed=233):
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
 
 
+def encoder_weights(source="auto", seed=234):
+    """mdm_weights('smpl') + the conditioning encoder's tensors (encoder.layers.*): exported checkpoint
+    weights ('ref', skips if absent) or seeded init ('random'); 'auto' = ref if present."""
+    sd = mdm_weights("smpl", source)
+    enc = None
+    if source in ("ref", "auto"):
+        enc = W.load_ref_weights("diffusion_smpl_encoder")
+        if enc is None and source == "ref":
+            import pytest
+            pytest.skip("exported encoder weights not present (oracle/export_ref_weights.py)")
+    if enc is None:
+        enc = W.random_state_dict(W.mdm_encoder_shapes("smpl"), seed)
+    sd = dict(sd)
+    sd.update({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in enc.items()})
+    return sd
+
+
 def projector_weights(source="auto", seed=233):
     sd = None
     if source in ("ref", "auto"):

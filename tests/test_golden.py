@@ -10,7 +10,7 @@ import torch
 
 from interdiff_b200 import synthetic as S
 from oracle import restate as R
-from tests.helpers import mdm_weights, projector_weights, rel, smplh_torch
+from tests.helpers import encoder_weights, mdm_weights, projector_weights, rel, smplh_torch
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 load = lambda n: {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, n)).items()}
@@ -38,6 +38,9 @@ class OracleBackend:
 
     def projector(self, psd, ang, tr, hv, contact):
         return R.obj_projector_sample(psd, ang, tr, hv, contact, 10, 20)
+
+    def condition(self, sd, past, pc):
+        return R.mdm_smpl_condition(sd, past, pc)
 
     def geometry(self, smplh_np, g):
         smplh = smplh_torch(smplh_np)
@@ -83,6 +86,10 @@ class EngineBackend:
         self.e.load_projector(psd, 10, 20)
         return self.e.projector_sample(ang, tr, hv, contact).cpu()
 
+    def condition(self, sd, past, pc):
+        self.e.load_denoiser(sd, "smpl")
+        return self.e.encode_condition(past.cuda(), pc.cuda()).cpu()
+
     def geometry(self, smplh_np, g):
         self.e.load_body(smplh_np)
         verts, jtr = self.e.lbs(g["pose"], g["betas"], g["trans"])
@@ -118,6 +125,19 @@ def test_golden_smpl(backend, source):
         loop = backend.smpl_loop(sd, b, tape, 5)
     # a 5-step schedule ends on the ill-conditioned t=1,0 steps, which amplify 1e-5 to ~1e-3
     assert rel(loop, g["loop5"]) < 3e-3
+
+
+@pytest.mark.parametrize("source", ["random", "ref"])
+def test_golden_condition_encoder(backend, source):
+    """SURVEY 8f rank 1 (second half): past-frame embedding + point-cloud embedding + positional encoding ->
+    8-layer encoder = the `cond` memory of the sampling loop (model/diffusion_smpl.py:217-221)."""
+    g = load("cond_encoder_%s.npz" % source)
+    sd = encoder_weights(source)
+    b = S.make_smpl_batch(B=2, T=30)
+    past = torch.from_numpy(b["gt"])[..., :10].contiguous()
+    with torch.no_grad():
+        out = backend.condition(sd, past, g["pc"])
+    assert rel(out, g["cond"]) < 2e-4
 
 
 @pytest.mark.parametrize("source", ["random", "ref"])

@@ -8,7 +8,7 @@ import torch
 
 from interdiff_b200 import synthetic as S
 from oracle import restate as R
-from tests.helpers import mdm_weights, projector_weights, rel, smplh_torch
+from tests.helpers import encoder_weights, mdm_weights, projector_weights, rel, smplh_torch
 
 pytestmark = pytest.mark.gpu
 
@@ -37,6 +37,58 @@ def test_denoiser_forward_smpl(eng, source, rotary):
     with torch.no_grad():
         ref = R.mdm_smpl_forward(sd, x, t, torch.from_numpy(b["cond"]), rotary=rotary, faithful=True)
     assert rel(got, ref) < 2e-4
+
+
+@pytest.mark.parametrize("B,Tp", [(5, 10), (3, 16)])
+def test_condition_encoder(eng, B, Tp):
+    """conditioning encoder (past frames + point-cloud embedding -> cond) against the oracle, then straight into
+    bind + forward: the memory produced on the device drives the decoder exactly like a host-provided one"""
+    sd = encoder_weights("auto")
+    eng.load_denoiser(sd, "smpl")
+    b = S.make_smpl_batch(B=B, T=30)
+    past = torch.from_numpy(b["gt"])[..., :Tp].contiguous()
+    pc = torch.randn(B, 256, generator=torch.Generator().manual_seed(B))
+    cond = eng.encode_condition(past.cuda(), pc.cuda())
+    with torch.no_grad():
+        ref = R.mdm_smpl_condition(sd, past, pc, faithful=False)
+    assert rel(cond.cpu(), ref) < 2e-4
+    eng.bind(cond, 30)
+    x = torch.from_numpy(S.noise_tape(b["gt"].shape, 0)[0])
+    t = torch.full((B,), 321)
+    got = eng.forward(x.cuda(), t.cuda()).cpu()
+    with torch.no_grad():
+        want = R.mdm_smpl_forward(sd, x, t, ref, faithful=False)
+    assert rel(got, want) < 3e-4
+
+
+def test_mirror_get_embeddings():
+    """interdiff_b200.model.diffusion_smpl.MDM._get_embeddings (reference API: list of per-frame dicts) with the
+    point-cloud embedding supplied: axis-angle -> rot6d plumbing on the host side + the encoder in the library,
+    against oracle.transforms + oracle.restate on the same weights."""
+    from argparse import Namespace
+    from interdiff_b200.model.diffusion_smpl import MDM
+    from oracle import transforms as tf
+    from tests.test_host_api import SMPL_ARGS
+    sd = encoder_weights("auto")
+    m = MDM(Namespace(**{**SMPL_ARGS, "future_len": 20})).cuda().eval()
+    own = m.state_dict()
+    m.load_state_dict({k: (sd[k].reshape(own[k].shape) if k in sd else v) for k, v in own.items()})
+    g = torch.Generator().manual_seed(9)
+    T, B = 30, 3
+    frames = [dict(smplfit_params=dict(pose=0.4 * torch.randn(B, 156, generator=g), trans=torch.randn(B, 3, generator=g)),
+                   objfit_params=dict(angle=0.7 * torch.randn(B, 3, generator=g), trans=torch.randn(B, 3, generator=g))) for _ in range(T)]
+    pc = torch.randn(B, 256, generator=g)
+    cond, gt = m._get_embeddings(dict(frames=frames, pc_embedding=pc), device="cuda")
+    pose = torch.stack([f["smplfit_params"]["pose"][:, :66] for f in frames])
+    r6 = lambda aa: tf.matrix_to_rotation_6d(tf.axis_angle_to_matrix(aa))
+    gt_ref = torch.cat([r6(pose.view(T, B, 22, 3)).reshape(T, B, 132), torch.stack([f["smplfit_params"]["trans"] for f in frames]),
+                        r6(torch.stack([f["objfit_params"]["angle"] for f in frames]).view(T, B, 1, 3)).reshape(T, B, 6),
+                        torch.stack([f["objfit_params"]["trans"] for f in frames])], dim=2)
+    assert rel(gt.cpu(), gt_ref) < 1e-5
+    past = gt_ref[:10].permute(1, 2, 0).unsqueeze(1).contiguous()
+    with torch.no_grad():
+        ref = R.mdm_smpl_condition({k: v.cpu() for k, v in m.state_dict().items()}, past, pc, faithful=False)
+    assert rel(cond.cpu(), ref) < 2e-4
 
 
 def test_denoiser_forward_T35(eng):

@@ -52,6 +52,25 @@ def test_mdm_forward(mdm, rotary, faithful):
     assert rel(got, ref) < 2e-5
 
 
+@pytest.mark.parametrize("faithful", [True, False])
+def test_condition_encoder(mdm, faithful):
+    """oracle.mdm_smpl_condition against the reference's own modules on the same inputs: bodyEmbedding /
+    objEmbedding of the past frames + point-cloud embedding, PositionalEmbedding, encoder
+    (model/diffusion_smpl.py:217-221)."""
+    model, _, args, sd = mdm
+    B, T = 3, 30
+    b = S.make_smpl_batch(B=B, T=T)
+    gt = torch.from_numpy(b["gt"])
+    past = gt[..., : args.past_len].contiguous()
+    pc = torch.randn(B, 256, generator=torch.Generator().manual_seed(4))
+    xs = past.squeeze(1).permute(2, 0, 1)
+    with torch.no_grad():
+        emb = model.bodyEmbedding(xs[..., :135]) + model.objEmbedding(xs[..., 135:]) + pc[None]
+        ref = model.encoder(model.PositionalEmbedding(emb))
+        got = R.mdm_smpl_condition(sd, past, pc, faithful=faithful)
+    assert rel(got, ref) < 2e-5
+
+
 def test_p_sample_loop_short(mdm):
     model, _, args, sd = mdm
     steps = 6

@@ -84,6 +84,14 @@ int idb_denoiser_forward(idb_handle* h, const float* x, const int64_t* timesteps
  *   cond_out     (Tp,B,256)  sequence-first like the reference; feed it to idb_denoiser_bind */
 int idb_encode_condition(idb_handle* h, int B, int Tp, const float* past, const float* pc_embedding, float* cond_out, void* stream);
 
+/* PointNet++ (MSG) point-cloud encoder = MDM.pcEmbedding, PointNet2Encoder(c_in=1, c_out=256, num_keypoints=1)
+ * (reference model/layers.py:111-175, called at model/diffusion_smpl.py:210-211); the furthest-point-sampling /
+ * ball-query / grouping operators of the un-vendored pointnet2_ops 3.0.0 are rebuilt for sm_100a.
+ * Needs the "pcEmbedding.*" tensors (incl. the BatchNorm running statistics) loaded before idb_denoiser_commit.
+ *   obj_points   (B,P,3)   object point cloud in the canonical frame (P = 2048 in the reference; 512..4096)
+ *   pc_embedding (B,256)   = pcEmbedding(cat([p, |p|]).unsqueeze(0)).view(1,B,-1)[0]  -> idb_encode_condition */
+int idb_pointcloud_embed(idb_handle* h, int B, int P, const float* obj_points, float* pc_embedding, void* stream);
+
 /* ---- diffusion: SpacedDiffusion / GaussianDiffusion sampling ------------------------------
  * replaces diffusion/gaussian_diffusion.py:160-197 (tables), 277-388 (p_mean_variance, START_X,
  * FIXED_SMALL, inpainting blend :307-311), 253-275, 496-548 (p_sample), 598-736 (p_sample_loop),

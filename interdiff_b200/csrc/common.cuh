@@ -65,6 +65,9 @@ struct Denoiser {
     __half *e_xtok_b = nullptr, *e_xtok_s = nullptr, *e_h_b = nullptr, *e_h_s = nullptr, *e_h2_b = nullptr, *e_h2_s = nullptr,
            *e_ff_b = nullptr, *e_ff_s = nullptr;
     std::vector<void*> enc_owned;
+    // PointNet++ point-cloud encoder (pointnet.cu): folded weights + workspace; optional like the encoder
+    bool pn_ready = false; int pn_cap = 0;
+    float *pn_w1 = nullptr, *pn_w2 = nullptr, *pn_xyz1 = nullptr, *pn_feat1 = nullptr;
     std::vector<float*> owned;              // packed buffers to free
     float *w_inT = nullptr, *b_in = nullptr;      // [C][D] k-major input embedding, summed bias
     float *w_in = nullptr, *w_out = nullptr;      // nn.Linear layouts for the GEMM: [D][C], [Clin][D]

@@ -867,6 +867,9 @@ extern "C" int idb_debug_attn_trace(long long* out16) {
 // host side
 // ------------------------------------------------------------------------------------------
 
+int idb_pointnet_commit(idb_handle* h);
+void idb_pointnet_release(idb_handle* h);
+
 int idb_fail(idb_handle* h, int code, const char* fmt, ...) {
     char buf[1024];
     va_list ap;
@@ -899,6 +902,7 @@ static void denoiser_free_bound(Denoiser& d) {
 
 void idb_denoiser_release(idb_handle* h) {
     Denoiser& d = h->den;
+    idb_pointnet_release(h);
     denoiser_free_bound(d);
     for (auto& kv : d.raw) cudaFree(kv.second.p);
     d.raw.clear();
@@ -932,7 +936,8 @@ extern "C" int idb_denoiser_load(idb_handle* h, const char* name, const float* d
     if (!d.configured) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_init first");
     std::string s(name);
     // tensors of the sampling hot path and, when given, of the conditioning encoder (PointNet++ is a later row)
-    bool want = s.rfind("decoder.layers.", 0) == 0 || s.rfind("encoder.layers.", 0) == 0 || s.rfind("bodyEmbedding.", 0) == 0 || s.rfind("objEmbedding.", 0) == 0 ||
+    bool want = s.rfind("decoder.layers.", 0) == 0 || s.rfind("encoder.layers.", 0) == 0 || s.rfind("pcEmbedding.", 0) == 0 ||
+                s.rfind("bodyEmbedding.", 0) == 0 || s.rfind("objEmbedding.", 0) == 0 ||
                 s.rfind("bodyFinalLinear.", 0) == 0 || s.rfind("objFinalLinear.", 0) == 0 ||
                 s.rfind("embedTimeStep.time_embed.", 0) == 0 || s == "PositionalEmbedding.pe";
     if (!want || s.find("inv_freq") != std::string::npos) return IDB_OK;
@@ -1167,6 +1172,10 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
             }
         if (rc) return rc;
         CUDA_TRY(h, cudaDeviceSynchronize());
+    }
+    {
+        const int rc = idb_pointnet_commit(h);      // optional PointNet++ point-cloud encoder (pointnet.cu)
+        if (rc) return rc;
     }
     d.committed = true;
     denoiser_free_bound(d);

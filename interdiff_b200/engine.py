@@ -252,6 +252,15 @@ class Engine:
         self._keep_loop = [tape, gt, m]
         return out
 
+    def pointcloud_embed(self, obj_points):
+        """pc_embedding (B,256) = the reference's pcEmbedding (PointNet++ MSG) on obj_points (B,P,3); needs the
+        pcEmbedding.* weights loaded."""
+        p = self._f32(obj_points)
+        B, P, _ = p.shape
+        out = torch.empty(B, 256, device=self.device)
+        self._chk(self.lib.idb_pointcloud_embed(self._h, B, P, self._ptr(p), self._ptr(out), self._stream()))
+        return out
+
     def encode_condition(self, past, pc_embedding):
         """cond (Tp,B,256) = conditioning encoder on the past frames (B,1,C,Tp) + point-cloud embedding (B,256)
         (reference MDM._get_embeddings after pcEmbedding); needs the encoder.layers.* weights loaded."""

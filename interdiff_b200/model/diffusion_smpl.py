@@ -29,7 +29,7 @@ class _EngineHost:
     rotary = "absolute"   # local-attention <= 1.5 rotary placement; 'bucketed' for >= 1.6
 
     def _hot_state(self):
-        keep = ("decoder.", "encoder.", "bodyEmbedding.", "objEmbedding.", "bodyFinalLinear.", "objFinalLinear.",
+        keep = ("decoder.", "encoder.", "pcEmbedding.", "bodyEmbedding.", "objEmbedding.", "bodyFinalLinear.", "objFinalLinear.",
                 "embedTimeStep.time_embed.", "PositionalEmbedding.pe")
         return {k: v for k, v in self.state_dict().items() if k.startswith(keep)}
 
@@ -111,14 +111,9 @@ class MDM(_EngineHost, nn.Module):
         return self.engine_for(past.device).encode_condition(past, pc_embedding)
 
     def _get_embeddings(self, data, device=None):
-        """Reference :195-223.  The transformer half (embeddings + positional encoding + 8-layer encoder) runs in the
-        library; the PointNet++ set abstraction is the remaining half of SURVEY 8f rank 1, so the point-cloud
-        embedding has to come with the batch as data['pc_embedding'] (B,D) (e.g. from the reference's own
-        pcEmbedding module)."""
-        if "pc_embedding" not in data:
-            raise NotImplementedError(
-                "PointNet++ set abstraction (model/layers.py:111-175) is not built yet (SURVEY.md 8f rank 1); provide "
-                "data['pc_embedding'] = pcEmbedding(...).view(1, B, -1)[0]")
+        """Reference :195-223, on the device: PointNet++ point-cloud embedding (`idb_pointcloud_embed`), past-frame
+        embeddings + positional encoding + 8-layer encoder (`idb_encode_condition`).  data['pc_embedding'] (B,D),
+        when present, replaces the point-cloud encoder (e.g. cached per object)."""
         dev = torch.device(device) if device else data["frames"][0]["smplfit_params"]["pose"].device
         cat = lambda key, sub, sl=slice(None): torch.cat([f[key][sub][:, sl].unsqueeze(0) for f in data["frames"]], dim=0).float().to(dev)
         body_pose, body_trans = cat("smplfit_params", "pose", slice(0, 66)), cat("smplfit_params", "trans")
@@ -128,8 +123,13 @@ class MDM(_EngineHost, nn.Module):
         obj_angles = self._axis_angle_to_rot6d(obj_angles.view(T, B, -1, 3)).view(T, B, -1)
         gt = torch.cat([body_pose, body_trans, obj_angles, obj_trans], dim=2)                  # (T,B,144)
         past = gt[: self.args.past_len].permute(1, 2, 0).unsqueeze(1).contiguous()              # (B,1,144,past_len)
-        embedding = self.encode_condition(past, data["pc_embedding"].to(dev).float().view(B, -1))
-        return embedding, gt
+        if "pc_embedding" in data:
+            pc = data["pc_embedding"].to(dev).float().view(B, -1)
+        else:
+            if not self.args.use_pointnet2:
+                raise NotImplementedError("use_pointnet2=0 (a Linear on 6 channels) is not a shipped configuration")
+            pc = self.engine_for(dev).pointcloud_embed(data["obj_points"][:, :, :3].float().to(dev))
+        return self.encode_condition(past, pc), gt
 
     def forward(self, x, timesteps, y=None):
         """x (B,1,144,T), timesteps (B,) long, y={'cond': (Tm,B,D)} -> predicted x_0 (B,1,144,T)

@@ -68,6 +68,22 @@ def mdm_encoder_shapes(variant="smpl", D=256, F=None, n_layers=8, N=10):
     return s
 
 
+def pointnet_shapes(prefix="pcEmbedding."):
+    """PointNet2Encoder(c_in=1, c_out=256, num_keypoints=1) (model/layers.py:111-141): two MSG set-abstraction
+    modules (Conv2d 1x1 without bias + BatchNorm2d + ReLU, three times per scale) and the Linear head."""
+    s = {}
+    for m, specs in enumerate(([[4, 16, 16, 32], [4, 32, 32, 64]], [[99, 64, 64, 128], [99, 64, 96, 128]])):
+        for k, spec in enumerate(specs):
+            for l in range(3):
+                p = "%sSA_modules.%d.mlps.%d." % (prefix, m, k)
+                s[p + "%d.weight" % (3 * l)] = (spec[l + 1], spec[l], 1, 1)
+                for leaf in ("weight", "bias", "running_mean", "running_var"):
+                    s[p + "%d.%s" % (3 * l + 1, leaf)] = (spec[l + 1],)
+    s[prefix + "Linear.weight"] = (253, 256)
+    s[prefix + "Linear.bias"] = (253,)
+    return s
+
+
 def projector_shapes(P=67, n_pre=10):
     s = {}
     chans = [9, 32, 16, 32, 9]

@@ -70,7 +70,12 @@ def main():
         with torch.no_grad():
             emb = emodel.bodyEmbedding(xs[..., :135]) + emodel.objEmbedding(xs[..., 135:]) + pc[None]
             cond_out = emodel.encoder(emodel.PositionalEmbedding(emb))
-        np.savez_compressed(os.path.join(OUT, "cond_encoder_%s.npz" % source), pc=pc.numpy(), cond=cond_out.numpy())
+        # point-cloud encoder: the reference's own PointNet2Encoder class on the restated pointnet2_ops operators
+        op = torch.from_numpy(b["obj_points"])
+        with torch.no_grad():
+            pc_pts = emodel.pcEmbedding(torch.cat([op, op.norm(dim=2, keepdim=True)], dim=2).unsqueeze(0)).view(1, 2, -1)[0]
+        np.savez_compressed(os.path.join(OUT, "cond_encoder_%s.npz" % source), pc=pc.numpy(), cond=cond_out.numpy(),
+                            pc_from_points=pc_pts.numpy())
         # ---- skeleton denoiser, BASELINE config 1: 1 DDPM step, B=2, T=15
         sd = mdm_weights("skeleton", source)
         model, _, args = RL.build_mdm_skeleton(state_dict=sd, diffusion_steps=1000)

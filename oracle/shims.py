@@ -40,9 +40,8 @@ class ChamferDistance(nn.Module):
 
 
 class PointnetSAModuleMSG(nn.Module):
-    """Parameter-name-compatible stub of pointnet2_ops 3.0.0's module (strict state_dict
-    loading of checkpoints/diffusion.ckpt).  Forward is NOT implemented: the PointNet++
-    conditioning encoder is a 'next' row."""
+    """Parameter-name-compatible stand-in of pointnet2_ops 3.0.0's module (strict state_dict
+    loading of checkpoints/diffusion.ckpt); forward = the restated FPS / ball-query / group ops."""
 
     def __init__(self, npoint, radii, nsamples, mlps, bn=True, use_xyz=True):
         super().__init__()
@@ -58,7 +57,10 @@ class PointnetSAModuleMSG(nn.Module):
             self.mlps.append(nn.Sequential(*layers))
 
     def forward(self, xyz, features):
-        raise NotImplementedError("PointNet++ set abstraction is outside the restated hot path")
+        """pointnet2_ops semantics via oracle.pointnet2_restated (published algorithm; parity unpinned there)."""
+        from . import pointnet2_restated as P2
+        sd = {"mlps." + k: v for k, v in self.mlps.state_dict().items()}
+        return P2.sa_module_msg(sd, "", xyz, features, self.npoint, self.radii, self.nsamples)
 
 
 def _mod(name, **attrs):

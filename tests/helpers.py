@@ -32,7 +32,7 @@ def mdm_weights(variant="smpl", source="auto", seed=233):
 
 
 def encoder_weights(source="auto", seed=234):
-    """mdm_weights('smpl') + the conditioning encoder's tensors (encoder.layers.*): exported checkpoint
+    """mdm_weights('smpl') + the conditioning path's tensors (encoder.layers.*, pcEmbedding.*): exported checkpoint
     weights ('ref', skips if absent) or seeded init ('random'); 'auto' = ref if present."""
     sd = mdm_weights("smpl", source)
     enc = None
@@ -42,7 +42,7 @@ def encoder_weights(source="auto", seed=234):
             import pytest
             pytest.skip("exported encoder weights not present (oracle/export_ref_weights.py)")
     if enc is None:
-        enc = W.random_state_dict(W.mdm_encoder_shapes("smpl"), seed)
+        enc = W.random_state_dict({**W.mdm_encoder_shapes("smpl"), **W.pointnet_shapes()}, seed)
     sd = dict(sd)
     sd.update({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in enc.items()})
     return sd

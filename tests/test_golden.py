@@ -42,6 +42,10 @@ class OracleBackend:
     def condition(self, sd, past, pc):
         return R.mdm_smpl_condition(sd, past, pc)
 
+    def pointcloud(self, sd, pts):
+        from oracle import pointnet2_restated as P2
+        return P2.pointnet2_encoder(sd, pts)
+
     def geometry(self, smplh_np, g):
         smplh = smplh_torch(smplh_np)
         verts, jtr = R.smplh_lbs(smplh, g["pose"], g["betas"], g["trans"])
@@ -89,6 +93,10 @@ class EngineBackend:
     def condition(self, sd, past, pc):
         self.e.load_denoiser(sd, "smpl")
         return self.e.encode_condition(past.cuda(), pc.cuda()).cpu()
+
+    def pointcloud(self, sd, pts):
+        self.e.load_denoiser(sd, "smpl")
+        return self.e.pointcloud_embed(pts.cuda()).cpu()
 
     def geometry(self, smplh_np, g):
         self.e.load_body(smplh_np)
@@ -138,6 +146,11 @@ def test_golden_condition_encoder(backend, source):
     with torch.no_grad():
         out = backend.condition(sd, past, g["pc"])
     assert rel(out, g["cond"]) < 2e-4
+    # point-cloud encoder (PointNet++ MSG): golden = the reference's PointNet2Encoder class running on the restated
+    # pointnet2_ops operators (oracle/pointnet2_restated.py: published algorithm, parity unpinned for those ops)
+    with torch.no_grad():
+        pc = backend.pointcloud(sd, torch.from_numpy(b["obj_points"]))
+    assert rel(pc, g["pc_from_points"]) < 1e-4
 
 
 @pytest.mark.parametrize("source", ["random", "ref"])

@@ -61,6 +61,26 @@ def test_condition_encoder(eng, B, Tp):
     assert rel(got, want) < 3e-4
 
 
+@pytest.mark.parametrize("P", [2048, 1000])
+def test_pointcloud_encoder(eng, P):
+    """PointNet++ point-cloud encoder against the oracle on clouds that exercise the operator corner cases: points
+    inside the |p|^2 <= 1e-3 dead zone of the sampler, duplicated points (distance ties), a cloud size that is not a
+    multiple of the sampler's block."""
+    from oracle import pointnet2_restated as P2
+    sd = encoder_weights("auto")
+    eng.load_denoiser(sd, "smpl")
+    g = torch.Generator().manual_seed(P)
+    B = 3
+    pts = 0.25 * (torch.rand(B, P, 3, generator=g) - 0.5) * torch.tensor([1.0, 2.0, 0.7])
+    pts[:, 5] = 0.01 * torch.randn(B, 3, generator=g)        # inside the dead zone
+    pts[:, 77] = pts[:, 76]                                    # duplicates
+    pts[1, 300:310] = pts[1, 100:110]
+    got = eng.pointcloud_embed(pts.cuda()).cpu()
+    with torch.no_grad():
+        ref = P2.pointnet2_encoder(sd, pts)
+    assert rel(got, ref) < 1e-4
+
+
 def test_mirror_get_embeddings():
     """interdiff_b200.model.diffusion_smpl.MDM._get_embeddings (reference API: list of per-frame dicts) with the
     point-cloud embedding supplied: axis-angle -> rot6d plumbing on the host side + the encoder in the library,
@@ -79,6 +99,10 @@ def test_mirror_get_embeddings():
                    objfit_params=dict(angle=0.7 * torch.randn(B, 3, generator=g), trans=torch.randn(B, 3, generator=g))) for _ in range(T)]
     pc = torch.randn(B, 256, generator=g)
     cond, gt = m._get_embeddings(dict(frames=frames, pc_embedding=pc), device="cuda")
+    # ... and with the point cloud itself: PointNet++ runs in the library as well
+    from oracle import pointnet2_restated as P2
+    pts = 0.2 * (torch.rand(B, 2048, 3, generator=g) - 0.5)
+    cond_pts, _ = m._get_embeddings(dict(frames=frames, obj_points=torch.cat([pts, torch.zeros(B, 2048, 4)], dim=2)), device="cuda")
     pose = torch.stack([f["smplfit_params"]["pose"][:, :66] for f in frames])
     r6 = lambda aa: tf.matrix_to_rotation_6d(tf.axis_angle_to_matrix(aa))
     gt_ref = torch.cat([r6(pose.view(T, B, 22, 3)).reshape(T, B, 132), torch.stack([f["smplfit_params"]["trans"] for f in frames]),
@@ -87,8 +111,11 @@ def test_mirror_get_embeddings():
     assert rel(gt.cpu(), gt_ref) < 1e-5
     past = gt_ref[:10].permute(1, 2, 0).unsqueeze(1).contiguous()
     with torch.no_grad():
-        ref = R.mdm_smpl_condition({k: v.cpu() for k, v in m.state_dict().items()}, past, pc, faithful=False)
+        msd = {k: v.cpu() for k, v in m.state_dict().items()}
+        ref = R.mdm_smpl_condition(msd, past, pc, faithful=False)
+        ref_pts = R.mdm_smpl_condition(msd, past, P2.pointnet2_encoder(msd, pts), faithful=False)
     assert rel(cond.cpu(), ref) < 2e-4
+    assert rel(cond_pts.cpu(), ref_pts) < 2e-4
 
 
 def test_denoiser_forward_T35(eng):

@@ -161,6 +161,15 @@ int idb_correction_bind(idb_handle* h, int B, int T, int past_len, int n_obj_poi
 int idb_correction_apply(idb_handle* h, float* x0, const float* gt, int t, uint8_t* condition_out,
                          int32_t* contact_out, float* markers_out, float* o2h_out, void* stream);
 
+/* Evaluation metrics of a batch of predictions (reference eval_smpl_short.py:24-81 `metrics`), per sample, on the device:
+ *   obj_pred / obj_gt (T,B,6) = [axis-angle | translation], body_jtr(_gt) (T,B,J,3), body(_gt) (T,B,Db) with the global
+ *   translation in the last 3 channels, verts (T,B,V,3) of the loaded body model, obj_points (B,P,3) canonical object cloud.
+ *   out [6][B]: global_mpjpe, local_mpjpe (pelvis aligned), body_translation, obj_translation, obj_rot_error
+ *   (min over the quaternion sign of the L1 distance), penetrate (share of posed object points inside the body). */
+int idb_metrics(idb_handle* h, int T, int B, int J, int P, int Db, const float* obj_pred, const float* body_jtr, const float* body,
+                const float* obj_gt, const float* body_jtr_gt, const float* body_gt, const float* verts, const float* obj_points,
+                float* out, void* stream);
+
 /* ---- kernel-level hook (tests / bench roofline leg) -----------------------------------------
  * C[M,N] = epi(A[M,K] . W[N,K]^T) with the handle's GEMM backend; epi bit 0 bias, 1 GELU(erf),
  * 2 residual add, 3 SiLU (the fused epilogues of the nn.Linear calls of the denoiser). */

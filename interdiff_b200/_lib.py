@@ -26,6 +26,7 @@ _SIGS = {
     "idb_launch_count": (C.c_longlong, [_P]),
     "idb_encode_condition": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "idb_pointcloud_embed": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
+    "idb_metrics": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "idb_set_gemm_backend": (C.c_int, [_P, C.c_int]),
     "idb_set_dependent_launch": (C.c_int, [_P, C.c_int]),
     "idb_set_fused_mlp": (C.c_int, [_P, C.c_int]),

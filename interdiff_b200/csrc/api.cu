@@ -37,6 +37,7 @@ extern "C" int idb_destroy(idb_handle* h) {
     idb_projector_release(h);
     idb_body_release(h);
     if (h->scratch) cudaFree(h->scratch);
+    if (h->metrics_ws) cudaFree(h->metrics_ws);
     delete h;
     return IDB_OK;
 }

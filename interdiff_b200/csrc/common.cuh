@@ -109,6 +109,7 @@ struct idb_handle {
     double last_ms = 0.0;     // mean launch time of the last timed debug hook
     int nn_pruning = 1;       // cluster-pruned nearest-neighbour search for body-mesh targets (identical results)
     int fused_mlp = 1;        // feed-forward block as ONE cluster kernel (tensor backend, d_model 256, d_ff 1024)
+    void* metrics_ws = nullptr; size_t metrics_bytes = 0;        // workspace of idb_metrics (posed object points, normals, signed distances)
     void* scratch = nullptr; size_t scratch_bytes = 0;   // on-the-fly operand splits of idb_gemm
     Denoiser den;
     Diffusion diff;

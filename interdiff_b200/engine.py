@@ -315,6 +315,18 @@ class Engine:
         self._chk(self.lib.idb_rot6d_to_axis_angle(self._h, d6.numel() // 6, self._ptr(d6), self._ptr(out), self._stream()))
         return out
 
+    METRIC_NAMES = ("global_mpjpe", "local_mpjpe", "body_translation", "obj_translation", "obj_rot_error", "penetrate")
+
+    def metrics(self, obj_pred, body_jtr, body, obj_gt, body_jtr_gt, body_gt, verts, obj_points):
+        """The reference's `metrics` (eval_smpl_short.py:24-81) on the device -> dict of (B,) tensors; the body model
+        (with faces) must be loaded."""
+        a = [self._f32(t) for t in (obj_pred, body_jtr, body, obj_gt, body_jtr_gt, body_gt, verts, obj_points)]
+        T, B, J = a[1].shape[:3]
+        out = torch.empty(6, B, device=self.device)
+        self._chk(self.lib.idb_metrics(self._h, T, B, J, a[7].shape[1], a[2].shape[2], *[self._ptr(t) for t in a], self._ptr(out),
+                                       self._stream()))
+        return {k: out[i] for i, k in enumerate(self.METRIC_NAMES)}
+
     # ------------------------------------------------------------------ correction
     def load_projector(self, state_dict, past_len, future_len, n_pre=10, n_markers=67):
         self._chk(self.lib.idb_projector_init(self._h, past_len, future_len, n_pre, n_markers))

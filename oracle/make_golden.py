@@ -152,6 +152,17 @@ def main():
     with torch.no_grad():
         o450 = env["denoised_fn"](x.clone(), torch.full((B,), 450), kw)
         o0 = env["denoised_fn"](x.clone(), torch.full((B,), 0), kw)
+    # ---- evaluation metrics: the reference's own `metrics` function compiled out of eval_smpl_short.py
+    from oracle import transforms as tfm
+    from tests.helpers import metrics_inputs
+    path = os.path.join(RL.ref_root(), "interdiff", "eval_smpl_short.py")
+    fn = [n for n in ast.parse(open(path).read()).body if isinstance(n, ast.FunctionDef) and n.name == "metrics"][0]
+    env = {"torch": torch, "axis_angle_to_matrix": tfm.axis_angle_to_matrix, "axis_angle_to_quaternion": tfm.axis_angle_to_quaternion,
+           "vertex_normals": RL.modules()["data.tools"].vertex_normals, "point2point_signed": RL.modules()["tools"].point2point_signed}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), env)
+    with torch.no_grad():
+        mref = env["metrics"](**metrics_inputs(S.make_smplh_model(233)))
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **{k: v.numpy() for k, v in mref.items()})
     np.savez_compressed(os.path.join(OUT, "denoised_fn_random.npz"), x=x.numpy(), out450=o450.numpy(), out0=o0.numpy())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -605,3 +605,24 @@ def sample_postprocess(sample, ctx):
     bb = body_pred.reshape(T * B, -1)
     verts, jtr = smplh_lbs(ctx["smplh"], bb[:, :-3], ctx["betas"].reshape(T * B, -1), bb[:, -3:])
     return body_pred, torch.cat([obj_rot, obj[:, :, -3:]], dim=2), verts.view(T, B, -1, 3), jtr.view(T, B, -1, 3)
+
+
+def metrics(obj_pred, body_jtr, body, obj_gt, body_jtr_gt, body_gt, verts, faces, obj_points):
+    """eval_smpl_short.py:24-81 restated: per-sample evaluation metrics over the T predicted frames.
+    obj_pred/obj_gt (T,B,6) = [axis-angle | translation], body_jtr(_gt) (T,B,J,3), body(_gt) (T,B,Db) with the
+    translation in the last 3 channels, verts (T,B,V,3), faces (F,3) long, obj_points (B,P,3).
+    Returns dict of (B,) tensors: global_mpjpe, local_mpjpe, body_translation, obj_translation, obj_rot_error, penetrate."""
+    T, B = body_jtr_gt.shape[:2]
+    Rm = tf.axis_angle_to_matrix(obj_pred[:, :, :3])
+    pts = torch.matmul(obj_points.unsqueeze(0), Rm.permute(0, 1, 3, 2)) + obj_pred[:, :, 3:].unsqueeze(2)
+    v = verts.reshape(T * B, -1, 3)
+    normals = vertex_normals(v, faces)
+    o2h = point2point_signed(v, pts.reshape(T * B, -1, 3), normals)[0]
+    out = dict(penetrate=(o2h < 0).view(T, B, -1).float().mean(dim=2).mean(dim=0))
+    out["global_mpjpe"] = (body_jtr - body_jtr_gt).norm(dim=3).mean(dim=2).mean(dim=0)
+    out["local_mpjpe"] = ((body_jtr - body_jtr[:, :, 0:1]) - (body_jtr_gt - body_jtr_gt[:, :, 0:1])).norm(dim=3).mean(dim=2).mean(dim=0)
+    out["body_translation"] = (body[:, :, -3:] - body_gt[:, :, -3:]).norm(dim=2).mean(dim=0)
+    out["obj_translation"] = (obj_pred[:, :, -3:] - obj_gt[:, :, -3:]).norm(dim=2).mean(dim=0)
+    q, qg = tf.axis_angle_to_quaternion(obj_pred[:, :, :3]), tf.axis_angle_to_quaternion(obj_gt[:, :, :3])
+    out["obj_rot_error"] = torch.minimum((q - qg).norm(dim=2, p=1), (q + qg).norm(dim=2, p=1)).mean(dim=0)
+    return out

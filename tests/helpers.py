@@ -4,6 +4,7 @@ import torch
 
 from interdiff_b200 import synthetic as S
 from interdiff_b200 import weights as W
+from oracle import restate as R
 
 
 def rel(a, b):
@@ -62,3 +63,25 @@ def projector_weights(source="auto", seed=233):
 
 def smplh_torch(smplh_np):
     return {k: torch.from_numpy(np.asarray(v)) for k, v in smplh_np.items()}
+
+
+def metrics_inputs(smplh_np, T=6, B=3, P=256, seed=5):
+    """small synthetic evaluation batch: predicted and ground-truth bodies (through the restated LBS) + objects"""
+    g = torch.Generator().manual_seed(seed)
+    smplh = {k: torch.from_numpy(np.asarray(v)) for k, v in smplh_np.items()}
+    pose, pose_gt = 0.3 * torch.randn(T * B, 156, generator=g), 0.3 * torch.randn(T * B, 156, generator=g)
+    betas = torch.randn(T * B, 10, generator=g)
+    trans, trans_gt = 0.3 * torch.randn(T * B, 3, generator=g), 0.3 * torch.randn(T * B, 3, generator=g)
+    with torch.no_grad():
+        verts, jtr = R.smplh_lbs(smplh, pose, betas, trans)
+        _, jtr_gt = R.smplh_lbs(smplh, pose_gt, betas, trans_gt)
+    body = torch.cat([pose, trans], dim=1).view(T, B, -1)
+    body_gt = torch.cat([pose_gt, trans_gt], dim=1).view(T, B, -1)
+    obj = torch.cat([0.8 * torch.randn(T, B, 3, generator=g), trans.view(T, B, 3) + 0.15 * torch.randn(T, B, 3, generator=g)], dim=2)
+    obj[0, 0, :3] = 0.0                                   # small-angle branch of axis_angle_to_quaternion
+    obj_gt = torch.cat([0.8 * torch.randn(T, B, 3, generator=g), trans_gt.view(T, B, 3)], dim=2)
+    pts = 0.25 * (torch.rand(B, P, 3, generator=g) - 0.5)
+    return dict(obj_pred=obj, body_jtr=jtr.view(T, B, -1, 3), body=body, obj_gt=obj_gt, body_jtr_gt=jtr_gt.view(T, B, -1, 3),
+                body_gt=body_gt, verts=verts.view(T, B, -1, 3), faces=smplh["faces"].long(), obj_points=pts)
+
+

@@ -10,7 +10,7 @@ import torch
 
 from interdiff_b200 import synthetic as S
 from oracle import restate as R
-from tests.helpers import encoder_weights, mdm_weights, projector_weights, rel, smplh_torch
+from tests.helpers import encoder_weights, mdm_weights, metrics_inputs, projector_weights, rel, smplh_torch
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 load = lambda n: {k: torch.from_numpy(v) for k, v in np.load(os.path.join(G, n)).items()}
@@ -45,6 +45,9 @@ class OracleBackend:
     def pointcloud(self, sd, pts):
         from oracle import pointnet2_restated as P2
         return P2.pointnet2_encoder(sd, pts)
+
+    def metrics(self, smplh_np, a):
+        return R.metrics(**a)
 
     def geometry(self, smplh_np, g):
         smplh = smplh_torch(smplh_np)
@@ -97,6 +100,11 @@ class EngineBackend:
     def pointcloud(self, sd, pts):
         self.e.load_denoiser(sd, "smpl")
         return self.e.pointcloud_embed(pts.cuda()).cpu()
+
+    def metrics(self, smplh_np, a):
+        self.e.load_body(smplh_np)
+        a = {k: v for k, v in a.items() if k != "faces"}
+        return {k: v.cpu() for k, v in self.e.metrics(**{k: v.cuda() for k, v in a.items()}).items()}
 
     def geometry(self, smplh_np, g):
         self.e.load_body(smplh_np)
@@ -151,6 +159,15 @@ def test_golden_condition_encoder(backend, source):
     with torch.no_grad():
         pc = backend.pointcloud(sd, torch.from_numpy(b["obj_points"]))
     assert rel(pc, g["pc_from_points"]) < 1e-4
+
+
+def test_golden_metrics(backend, smplh_np):
+    """the evaluation metrics (golden = the reference's own `metrics` function)."""
+    g = load("metrics.npz")
+    with torch.no_grad():
+        out = backend.metrics(smplh_np, metrics_inputs(smplh_np))
+    for k in g:
+        assert rel(out[k], g[k]) < 2e-5, k
 
 
 @pytest.mark.parametrize("source", ["random", "ref"])

@@ -172,6 +172,23 @@ def _reference_function(fname, name, env):
     return env[name]
 
 
+def test_metrics(smplh_np):
+    """oracle.metrics against the reference's own `metrics` function (eval_smpl_short.py:24-81) compiled out of the
+    script, with the script's imports bound to the reference's tools / data.tools and the transforms shim."""
+    mods = RL.modules()
+    env = {"torch": torch, "axis_angle_to_matrix": tf.axis_angle_to_matrix, "axis_angle_to_quaternion": tf.axis_angle_to_quaternion,
+           "vertex_normals": mods["data.tools"].vertex_normals, "point2point_signed": mods["tools"].point2point_signed}
+    ref_fn = _reference_function("eval_smpl_short.py", "metrics", env)
+    from tests.helpers import metrics_inputs
+    a = metrics_inputs(smplh_np)
+    with torch.no_grad():
+        ref = ref_fn(**a)
+        got = R.metrics(**a)
+    for k in ref:
+        assert rel(got[k], ref[k]) < 1e-5, k
+    assert float(ref["penetrate"].max()) > 0            # the batch does exercise penetration
+
+
 def test_denoised_fn(smplh_np):
     """oracle.restate.make_denoised_fn against the reference's own denoised_fn source
     (eval_smpl_short.py:84-130) executed with the reference's ObjProjector / SMPL_Layer /

@@ -181,10 +181,12 @@ int idb_debug_gemm_repeat(idb_handle* h, const float* A, const float* W, const f
 
 /* test hook: number of round-robin TMEM accumulators of the tcgen05 GEMM (0 = default) */
 int idb_debug_set_gemm_accumulators(int n);
-/* out[M][256] = gelu(x w1^T + b1) w2^T + b2 + res through the fused feed-forward kernel (fp32 device pointers);
-   iters > 1: launches 2..iters are timed (idb_debug_last_ms); trace != NULL: clock64 timeline [ctas][16] of launch 1 */
+/* out[M][256] = [LayerNorm(] gelu(x w1^T + b1) w2^T + b2 + res [)] through the fused feed-forward kernel (fp32 device
+   pointers; ln_w / ln_b NULL = no norm); iters > 1: launches 2..iters are timed (idb_debug_last_ms); trace != NULL:
+   clock64 timeline [ctas][16] of launch 1 */
 int idb_debug_mlp(idb_handle* h, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
-                  const float* res, float* out, int M, int iters, long long* trace, void* stream);
+                  const float* res, float* out, int M, int iters, long long* trace, const float* ln_w, const float* ln_b,
+                  void* stream);
 double idb_debug_last_ms(const idb_handle* h);
 /* clock64 phase timeline (16 slots, host pointer) of CTA (0,0) of the last fused QaN + cross-attention kernel */
 int idb_debug_attn_trace(long long* out16);

@@ -31,7 +31,7 @@ _SIGS = {
     "idb_set_dependent_launch": (C.c_int, [_P, C.c_int]),
     "idb_set_fused_mlp": (C.c_int, [_P, C.c_int]),
     "idb_set_nn_pruning": (C.c_int, [_P, C.c_int]),
-    "idb_debug_mlp": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "idb_debug_mlp": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "idb_debug_last_ms": (C.c_double, [_P]),
     "idb_denoiser_init": (C.c_int, [_P, C.POINTER(DenoiserConfig)]),
     "idb_denoiser_load": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),

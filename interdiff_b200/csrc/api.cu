@@ -68,7 +68,7 @@ extern "C" int idb_set_nn_pruning(idb_handle* h, int on) {
 extern "C" double idb_debug_last_ms(const idb_handle* h) { return h ? h->last_ms : 0.0; }
 extern "C" int idb_set_fused_mlp(idb_handle* h, int on) {
     if (!h) return IDB_ERR_ARG;
-    h->fused_mlp = on ? 1 : 0;
+    h->fused_mlp = on < 0 ? 0 : (on > 2 ? 2 : on);   /* 0 = two GEMMs, 1 = cluster kernel, 2 = cluster kernel + the layer's final norm */
     idb_sampler_drop_graphs(h);
     return IDB_OK;
 }
@@ -77,7 +77,8 @@ extern long long* g_idb_gemm_trace;
 /* test hook: out[M][256] = gelu(x w1^T + b1) w2^T + b2 + res through the fused cluster kernel (fp32 device inputs,
    x [M][256], w1 [1024][256], w2 [256][1024]); operands are split into fp16 pairs in temporary buffers */
 extern "C" int idb_debug_mlp(idb_handle* h, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
-                             const float* res, float* out, int M, int iters, long long* trace, void* stream) {
+                             const float* res, float* out, int M, int iters, long long* trace, const float* ln_w, const float* ln_b,
+                             void* stream) {
     if (!h || !x || !w1 || !b1 || !w2 || !b2 || !res || !out || M <= 0) return IDB_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int Dm = 256, F = 1024;
@@ -93,7 +94,7 @@ extern "C" int idb_debug_mlp(idb_handle* h, const float* x, const float* w1, con
     for (int i = 0; i < (iters > 0 ? iters : 1) && !rc; i++) {
         if (i == 0 && trace) g_idb_gemm_trace = trace;
         if (i == 1) cudaEventRecord(e0, st);
-        rc = idb_mlp_tcgen05(h, xh, xl, w1h, w1l, b1, w2h, w2l, b2, res, Dm, out, Dm, M, 0, st);
+        rc = idb_mlp_tcgen05(h, xh, xl, w1h, w1l, b1, w2h, w2l, b2, res, Dm, out, Dm, M, 0, st, ln_w, ln_b, nullptr, nullptr);
     }
     cudaEventRecord(e1, st);
     cudaStreamSynchronize(st);

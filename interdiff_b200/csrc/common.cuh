@@ -226,7 +226,8 @@ int idb_gemm_ex(idb_handle* h, const GemmArgs& g, cudaStream_t st);
 bool idb_mlp_tcgen05_supported(int d_model, int d_ff);
 int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const __half* w1_hi, const __half* w1_lo, const float* b1,
                     const __half* w2_hi, const __half* w2_lo, const float* b2, const float* res, int ldr, float* Z, int ldz, int M,
-                    int pdl, cudaStream_t st);
+                    int pdl, cudaStream_t st, const float* ln_w = nullptr, const float* ln_b = nullptr, __half* Z_hi = nullptr,
+                    __half* Z_lo = nullptr);
 // x[rows][cols] (row stride ld_src) -> fp16 pairs [rows][ld_dst] (columns >= cols zero-filled)
 int idb_split_tensor(idb_handle* h, const float* x, int ld_src, __half* hi, __half* lo, int ld_dst, int rows, int cols, cudaStream_t st);
 

@@ -1280,8 +1280,9 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
     const int B = d.B, T = d.T, M = d.M, Tm = d.Tm, F = d.cfg.d_ff, H = d.cfg.n_heads, N = d.cfg.n_queries;
     const dim3 slab_grid(B, (T + SLAB - 1) / SLAB);
     const int ln_blocks = (M * 32 + 255) / 256;
-    const DenoiserLayer* pending = nullptr;   // layer whose norm3 has not been applied to d.z yet
+    const DenoiserLayer* pending = nullptr;   // layer whose norm3 has not been applied to d.z yet (unfused feed-forward path)
     const bool pdl = h->pdl != 0;
+    const bool fused = h->gemm_backend == 1 && h->fused_mlp && idb_mlp_tcgen05_supported(D, F);
     int rc;
     for (auto& L : d.layers) {
         // ---- first sub-block -> x1 = (d.h2, h2_b, h2_s)
@@ -1309,8 +1310,15 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
             LAUNCH_CHECK(h);
         }
         // ---- feed forward on x2 = d.h2: ff = gelu(x2 W1^T + b1) kept as pairs only; z = ff W2^T + b2 + x2  (pre-norm3)
-        if (h->gemm_backend == 1 && h->fused_mlp && idb_mlp_tcgen05_supported(D, F)) {
-            // both GEMMs, GELU and the residual in one cluster kernel; the hidden activations never leave the SM
+        if (fused) {
+            // both GEMMs, GELU, the residual AND the layer's norm3 in one cluster kernel: the hidden activations never
+            // leave the SM and the next layer starts from normalised rows (fp32 + fp16 pairs)
+            if (h->fused_mlp >= 2) {
+                if ((rc = idb_mlp_tcgen05(h, d.h2_b, d.h2_s, L.w1_b, L.w1_s, L.b1, L.w2_b, L.w2_s, L.b2, d.h2, D, d.h, D, M, h->pdl, st,
+                                          L.ln3w, L.ln3b, d.h_b, d.h_s)))
+                    return rc;
+                continue;
+            }
             if ((rc = idb_mlp_tcgen05(h, d.h2_b, d.h2_s, L.w1_b, L.w1_s, L.b1, L.w2_b, L.w2_s, L.b2, d.h2, D, d.z, D, M, h->pdl, st)))
                 return rc;
         } else {
@@ -1325,8 +1333,10 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
         // <= 1 ulp of max(|x|,|tgt|) and is not reproduced (DESIGN.md "Deviations").
         pending = &L;
     }
-    idb_launch(pdl, k_ln, ln_blocks, 256, 0, st, d.z, pending->ln3w, pending->ln3b, d.h, d.h_b, d.h_s, M);
-    LAUNCH_CHECK(h);
+    if (pending) {
+        idb_launch(pdl, k_ln, ln_blocks, 256, 0, st, d.z, pending->ln3w, pending->ln3b, d.h, d.h_b, d.h_s, M);
+        LAUNCH_CHECK(h);
+    }
     return IDB_OK;
 }
 
@@ -1456,7 +1466,13 @@ __global__ void k_ln_seq_first(const float* __restrict__ a, const float* __restr
     pdl_wait();
     if (m >= B * Tp) return;
     const int b = m / Tp, t = m - b * Tp;
-    warp_ln_row(a + (size_t)m * D, w, bb, out + ((size_t)t * B + b) * D, lane);
+    if (w) {
+        warp_ln_row(a + (size_t)m * D, w, bb, out + ((size_t)t * B + b) * D, lane);
+    } else {
+        const float4* src = reinterpret_cast<const float4*>(a + (size_t)m * D);
+        float4* dst = reinterpret_cast<float4*>(out + ((size_t)t * B + b) * D);
+        dst[lane] = src[lane]; dst[lane + 32] = src[lane + 32];
+    }
 }
 
 }  // namespace
@@ -1517,6 +1533,12 @@ extern "C" int idb_encode_condition(idb_handle* h, int B, int Tp, const float* p
             LAUNCH_CHECK(h);
         }
         if (fused) {
+            if (h->fused_mlp >= 2) {
+                if ((rc = idb_mlp_tcgen05(h, d.e_h2_b, d.e_h2_s, L.w1_b, L.w1_s, L.b1, L.w2_b, L.w2_s, L.b2, d.e_h2, D, d.e_h, D, M, h->pdl,
+                                          st, L.ln3w, L.ln3b, d.e_h_b, d.e_h_s)))
+                    return rc;
+                continue;
+            }
             if ((rc = idb_mlp_tcgen05(h, d.e_h2_b, d.e_h2_s, L.w1_b, L.w1_s, L.b1, L.w2_b, L.w2_s, L.b2, d.e_h2, D, d.e_z, D, M, h->pdl, st)))
                 return rc;
         } else {
@@ -1527,7 +1549,9 @@ extern "C" int idb_encode_condition(idb_handle* h, int B, int Tp, const float* p
         }
         pending = &L;
     }
-    idb_launch(pdl, k_ln_seq_first, ln_blocks, 256, 0, st, d.e_z, pending->ln3w, pending->ln3b, cond_out, B, Tp);
+    // last norm (or, when the fused feed-forward kernel already applied it, a plain copy) into the (Tp,B,D) layout
+    idb_launch(pdl, k_ln_seq_first, ln_blocks, 256, 0, st, pending ? d.e_z : d.e_h, pending ? pending->ln3w : (const float*)nullptr,
+               pending ? pending->ln3b : (const float*)nullptr, cond_out, B, Tp);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }

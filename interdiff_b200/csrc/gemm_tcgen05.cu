@@ -403,7 +403,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                  const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_w1l,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2l,
                  const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ res, int ldr,
-                 float* __restrict__ Z, int ldz, int M, long long* __restrict__ trace) {
+                 float* __restrict__ Z, int ldz, int M, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                 __half* __restrict__ Zh, __half* __restrict__ Zl, long long* __restrict__ trace) {
     using namespace mlp;
     long long* tr = trace ? trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
 #define MTRACE(slot) do { if (tr) tr[slot] = clock64(); } while (0)
@@ -620,6 +621,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     if (threadIdx.x == 64) MTRACE(10);
     if (warp >= 2) {
         const int ct = threadIdx.x - 64;
+        float4 o[4];
 #pragma unroll 1
         for (int t = 0; t < 4; t++) {
             const int idx = ct + t * 256, rr = idx / (DM / 4), c4 = idx % (DM / 4);
@@ -637,11 +639,57 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             for (int i = 0; i < CLUSTER; i++) {          // rank order: deterministic
                 acc.x += p[i].x; acc.y += p[i].y; acc.z += p[i].z; acc.w += p[i].w;
             }
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < M) {
                 const float4 bb = *reinterpret_cast<const float4*>(b2 + c4 * 4);
                 const float4 r4 = *reinterpret_cast<const float4*>(res + (size_t)row * ldr + c4 * 4);
-                *reinterpret_cast<float4*>(Z + (size_t)row * ldz + c4 * 4) =
-                    make_float4((acc.x + bb.x) + r4.x, (acc.y + bb.y) + r4.y, (acc.z + bb.z) + r4.z, (acc.w + bb.w) + r4.w);
+                v = make_float4((acc.x + bb.x) + r4.x, (acc.y + bb.y) + r4.y, (acc.z + bb.z) + r4.z, (acc.w + bb.w) + r4.w);
+            }
+            // select by constant index (t is a runtime loop counter of a deliberately rolled loop)
+            if (t == 0) o[0] = v; else if (t == 1) o[1] = v; else if (t == 2) o[2] = v; else o[3] = v;
+        }
+        if (ln_w) {
+            // the layer's final LayerNorm, fused: pass t of a thread belongs to row 4t + (ct >> 6), which lives in 64
+            // consecutive threads (two warps); the warp sums of all four passes meet through shared memory between
+            // two named barriers of the 256 reducing threads (the pulls above stay unsynchronised)
+            float* s_red = reinterpret_cast<float*>(base_ptr + RING + S_BYTES + 128);     // [2][4][8]
+            const int ew2 = warp - 2;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float sum = warp_sum((o[t].x + o[t].y) + (o[t].z + o[t].w));
+                if (lane == 0) s_red[t * 8 + ew2] = sum;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            float mean[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                mean[t] = (s_red[t * 8 + (ew2 & ~1)] + s_red[t * 8 + (ew2 | 1)]) * (1.0f / DM);
+                o[t].x -= mean[t]; o[t].y -= mean[t]; o[t].z -= mean[t]; o[t].w -= mean[t];
+                const float sq = warp_sum((o[t].x * o[t].x + o[t].y * o[t].y) + (o[t].z * o[t].z + o[t].w * o[t].w));
+                if (lane == 0) s_red[32 + t * 8 + ew2] = sq;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int c4 = ct % (DM / 4);
+            const float4 w4 = *reinterpret_cast<const float4*>(ln_w + c4 * 4), b4 = *reinterpret_cast<const float4*>(ln_b + c4 * 4);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float rstd = 1.0f / sqrtf((s_red[32 + t * 8 + (ew2 & ~1)] + s_red[32 + t * 8 + (ew2 | 1)]) * (1.0f / DM) + 1e-5f);
+                o[t] = make_float4(o[t].x * rstd * w4.x + b4.x, o[t].y * rstd * w4.y + b4.y, o[t].z * rstd * w4.z + b4.z, o[t].w * rstd * w4.w + b4.w);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int idx = ct + t * 256, rr = idx / (DM / 4), c4 = idx % (DM / 4);
+            const int row = m0 + j * 16 + rr;
+            if (row < M) {
+                *reinterpret_cast<float4*>(Z + (size_t)row * ldz + c4 * 4) = o[t];
+                if (Zh) {
+                    __half2 h01, h23, l01, l23;
+                    split_f16x2(o[t].x, o[t].y, h01, l01);
+                    split_f16x2(o[t].z, o[t].w, h23, l23);
+                    *reinterpret_cast<uint2*>(Zh + (size_t)row * ldz + c4 * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+                    *reinterpret_cast<uint2*>(Zl + (size_t)row * ldz + c4 * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+                }
             }
         }
         if (threadIdx.x == 64) MTRACE(11);
@@ -759,12 +807,13 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
 }
 
 // Fused feed-forward block (see mlp_fused_kernel).  x / w1 / w2 as fp16 (hi, lo) pairs, row-major:
-// x [M][256], w1 [F][256], w2 [256][F];  Z[M][256] = gelu(x w1^T + b1) w2^T + b2 + res.
+// x [M][256], w1 [F][256], w2 [256][F];  Z[M][256] = gelu(x w1^T + b1) w2^T + b2 + res, optionally followed by the layer's
+// final LayerNorm (ln_w / ln_b) and an additional fp16 (hi, lo) copy of the output (Z_hi / Z_lo) for the next GEMM.
 bool idb_mlp_tcgen05_supported(int d_model, int d_ff) { return d_model == mlp::DM && d_ff == mlp::FC * mlp::CLUSTER; }
 
 int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const __half* w1_hi, const __half* w1_lo, const float* b1,
                     const __half* w2_hi, const __half* w2_lo, const float* b2, const float* res, int ldr, float* Z, int ldz, int M,
-                    int pdl, cudaStream_t st) {
+                    int pdl, cudaStream_t st, const float* ln_w, const float* ln_b, __half* Z_hi, __half* Z_lo) {
     long long* trace = g_idb_gemm_trace;
     g_idb_gemm_trace = nullptr;
     static bool attr_set = false;
@@ -782,7 +831,7 @@ int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const
     if ((rc = make_map(h, &mw2, w2_hi, mlp::DM, F, F, mlp::DM))) return rc;
     if ((rc = make_map(h, &mw2l, w2_lo, mlp::DM, F, F, mlp::DM))) return rc;
     dim3 grid(mlp::CLUSTER, (M + BM - 1) / BM);
-    idb_launch(pdl != 0, mlp_fused_kernel, grid, NUM_THREADS, mlp::SMEM_BYTES, st, mx, mw1, mxl, mw1l, mw2, mw2l, b1, b2, res, ldr, Z, ldz, M, trace);
+    idb_launch(pdl != 0, mlp_fused_kernel, grid, NUM_THREADS, mlp::SMEM_BYTES, st, mx, mw1, mxl, mw1l, mw2, mw2l, b1, b2, res, ldr, Z, ldz, M, ln_w, ln_b, Z_hi, Z_lo, trace);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }

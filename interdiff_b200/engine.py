@@ -91,15 +91,18 @@ class Engine:
 
     def set_fused_mlp(self, on):
         """Feed-forward block as one cluster kernel (default on) vs two GEMM launches."""
-        self._chk(self.lib.idb_set_fused_mlp(self._h, 1 if on else 0))
+        self._chk(self.lib.idb_set_fused_mlp(self._h, int(on)))
 
-    def mlp(self, x, w1, b1, w2, b2, res, iters=1, trace=None):
+    def mlp(self, x, w1, b1, w2, b2, res, iters=1, trace=None, ln_w=None, ln_b=None):
         """gelu(x @ w1.T + b1) @ w2.T + b2 + res through the fused feed-forward kernel (tests / probes).
         iters > 1: self.last_ms() is the mean time of launches 2..iters; trace: int64 [ctas,16] device tensor."""
         x, w1, b1, w2, b2, res = (self._f32(t) for t in (x, w1, b1, w2, b2, res))
         out = torch.empty_like(x)
+        ln_w = self._f32(ln_w) if ln_w is not None else None
+        ln_b = self._f32(ln_b) if ln_b is not None else None
         self._chk(self.lib.idb_debug_mlp(self._h, self._ptr(x), self._ptr(w1), self._ptr(b1), self._ptr(w2), self._ptr(b2), self._ptr(res),
-                                         self._ptr(out), x.shape[0], int(iters), self._ptr(trace), self._stream()))
+                                         self._ptr(out), x.shape[0], int(iters), self._ptr(trace), self._ptr(ln_w), self._ptr(ln_b),
+                                         self._stream()))
         return out
 
     def last_ms(self):

@@ -100,3 +100,43 @@ def sample_postprocess(engine, sample, hand_pose, betas, past_len=10, future_len
     bb = body.reshape(T * B, -1)
     verts, jtr = engine.lbs(bb[:, :-3], betas.reshape(T * B, -1), bb[:, -3:])
     return body, torch.cat([obj_rot, xs[..., 141:144]], dim=2), verts.view(T, B, -1, 3), jtr.view(T, B, -1, 3)
+
+
+def smooth(obj, body, verts, jtrs, pelvis, future_len):
+    """Reference eval_smpl_short.py:217-223: shift every predicted future frame by the second-difference jump at the
+    past/future seam, x[-F:] += 2 x[-F-1] - x[-F-2] - x[-F]; in place on (T, ...) tensors (device or host)."""
+    F = int(future_len)
+    for x in (obj, body, verts, jtrs, pelvis):
+        x[-F:] = x[-F:] + (2 * x[-F - 1] - x[-F - 2] - x[-F])
+    return obj, body, verts, jtrs, pelvis
+
+
+class BestOfSamples:
+    """The diverse-sample reduction of the reference's evaluation loop (eval_smpl_short.py:268-296): per batch every
+    metric starts at 1e10, each of the `diverse_samples` draws contributes its per-sample metric vector, the
+    element-wise minimum over the draws is averaged over the batch and accumulated over batches."""
+
+    def __init__(self, names=("global_mpjpe", "local_mpjpe", "body_translation", "obj_translation", "obj_rot_error", "penetrate")):
+        self.names = tuple(names)
+        self.totals = {k: 0.0 for k in self.names}
+        self.batches = 0
+        self._cur = None
+
+    def start_batch(self):
+        self._cur = None
+
+    def add(self, metric):
+        """metric: {name: (B,) tensor} of one draw (Engine.metrics output)."""
+        if self._cur is None:
+            self._cur = {k: torch.full_like(metric[k], 1e10) for k in self.names}
+        for k in self.names:
+            self._cur[k] = torch.minimum(self._cur[k], metric[k])
+
+    def end_batch(self):
+        for k in self.names:
+            self.totals[k] += self._cur[k].mean().item()
+        self.batches += 1
+        self._cur = None
+
+    def averages(self):
+        return {k: v / max(self.batches, 1) for k, v in self.totals.items()}

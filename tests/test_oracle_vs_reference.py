@@ -189,6 +189,28 @@ def test_metrics(smplh_np):
     assert float(ref["penetrate"].max()) > 0            # the batch does exercise penetration
 
 
+def test_smooth_and_best_of_samples():
+    """host-side post-processing mirrors (interdiff_b200.sampling.smooth / BestOfSamples) against the reference's
+    `smooth` (eval_smpl_short.py:217-223) and the min-over-draws reduction of its evaluation loop (:268-296)."""
+    from interdiff_b200 import sampling
+    env = {"args": Namespace(future_len=20)}
+    ref_smooth = _reference_function("eval_smpl_short.py", "smooth", env)
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.randn(30, 2, n, generator=g) for n in (6, 159, 12, 9, 3)]
+    ref = ref_smooth(*[x.clone() for x in xs])
+    got = sampling.smooth(*[x.clone() for x in xs], future_len=20)
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    acc = sampling.BestOfSamples(names=("m",))
+    draws = [torch.rand(4, generator=g) for _ in range(3)]
+    acc.start_batch()
+    for d in draws:
+        acc.add({"m": d})
+    acc.end_batch()
+    want = torch.stack([torch.full((4,), 1e10)] + draws).min(dim=0)[0].mean().item()
+    assert abs(acc.averages()["m"] - want) < 1e-7
+
+
 def test_denoised_fn(smplh_np):
     """oracle.restate.make_denoised_fn against the reference's own denoised_fn source
     (eval_smpl_short.py:84-130) executed with the reference's ObjProjector / SMPL_Layer /

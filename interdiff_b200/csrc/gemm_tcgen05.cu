@@ -378,7 +378,7 @@ constexpr int STAGE1 = 64 * 1024;             // A_hi 16K | W1_hi 16K | A_lo 16K
 constexpr int RING = 2 * STAGE1;
 constexpr int S_BYTES = 64 * 1024;            // S_hi [2][16K] | S_lo [2][16K]
 constexpr int PLD = 260;                      // fp32 partial row stride (floats)
-constexpr int SMEM_BYTES = RING + S_BYTES + 1024 + 256;
+constexpr int SMEM_BYTES = RING + S_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers, tmem slot, LayerNorm partial sums*/;
 }  // namespace mlp
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&u)[32]) {

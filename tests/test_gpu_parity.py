@@ -321,3 +321,35 @@ def test_correction_hook(eng, smplh_np):
     assert torch.equal(dbg["condition"].cpu(), obs["condition"])
     assert torch.equal(dbg["contact"].cpu().long(), obs["contact"])
     assert rel(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize("M", [1920, 129])
+def test_fused_feed_forward_with_final_norm(eng, M):
+    """level 2 of the fused feed-forward kernel: the layer's final LayerNorm applied in the reduction epilogue (two
+    named barriers across the 256 reducing threads), against float64 - and a whole forward with it switched on."""
+    g = torch.Generator().manual_seed(M + 1)
+    x = torch.randn(M, 256, generator=g)
+    w1 = torch.randn(1024, 256, generator=g) / 16
+    b1 = torch.randn(1024, generator=g) * 0.1
+    w2 = torch.randn(256, 1024, generator=g) / 32
+    b2 = torch.randn(256, generator=g) * 0.1
+    res = torch.randn(M, 256, generator=g)
+    lw, lb = 1.0 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g)
+    ref = torch.nn.functional.gelu(x.double() @ w1.double().T + b1.double()) @ w2.double().T + b2.double() + res.double()
+    want = torch.nn.functional.layer_norm(ref, (256,), lw.double(), lb.double(), 1e-5)
+    got = eng.mlp(x, w1, b1, w2, b2, res, ln_w=lw, ln_b=lb).cpu().double()
+    assert ((got - want).abs().max() / want.abs().max()).item() < 5e-6
+    sd = mdm_weights("smpl", "auto")
+    eng.load_denoiser(sd, "smpl")
+    b = S.make_smpl_batch(B=4, T=30)
+    eng.bind(b["cond"], 30)
+    xx = torch.from_numpy(S.noise_tape(b["gt"].shape, 0)[0])
+    t = torch.tensor([900, 400, 50, 0])
+    with torch.no_grad():
+        ref_out = R.mdm_smpl_forward(sd, xx, t, torch.from_numpy(b["cond"]), faithful=False)
+    eng.set_fused_mlp(2)
+    try:
+        got2 = eng.forward(xx.cuda(), t.cuda()).cpu()
+    finally:
+        eng.set_fused_mlp(1)
+    assert rel(got2, ref_out) < 2e-4

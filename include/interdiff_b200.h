@@ -33,8 +33,8 @@ int idb_set_gemm_backend(idb_handle* h, int backend); /* 0 = fp32 SIMT (debug/bi
 /* Programmatic dependent launch between the kernels of a sampling step (default 1). Results are identical
    either way; 0 serialises the kernels (for bisecting / profiling). */
 int idb_set_dependent_launch(idb_handle* h, int on);
-/* Feed-forward block of a decoder layer as one cluster kernel (default 1; tensor backend, d_model 256, d_ff 1024);
-   0 = the two separate GEMMs (bisecting / profiling). */
+/* Feed-forward block of a decoder layer as one cluster kernel (tensor backend, d_model 256, d_ff 1024): 2 (default) = incl.
+   the layer's final LayerNorm in its reduction epilogue, 1 = feed-forward only, 0 = the two separate GEMMs (bisecting). */
 int idb_set_fused_mlp(idb_handle* h, int on);
 /* Cluster-pruned nearest-neighbour search when the target is the loaded body mesh (default 1; results are identical
    to the brute-force scan, index ties included); 0 = always brute force. */

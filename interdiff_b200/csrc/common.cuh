@@ -108,7 +108,7 @@ struct idb_handle {
     int pdl = 1;              // programmatic dependent launch between the kernels of a sampling step
     double last_ms = 0.0;     // mean launch time of the last timed debug hook
     int nn_pruning = 1;       // cluster-pruned nearest-neighbour search for body-mesh targets (identical results)
-    int fused_mlp = 1;        // feed-forward block as ONE cluster kernel (tensor backend, d_model 256, d_ff 1024)
+    int fused_mlp = 2;        // feed-forward block as ONE cluster kernel (tensor backend, d_model 256, d_ff 1024); 2 = incl. the layer's final norm
     void* metrics_ws = nullptr; size_t metrics_bytes = 0;        // workspace of idb_metrics (posed object points, normals, signed distances)
     void* scratch = nullptr; size_t scratch_bytes = 0;   // on-the-fly operand splits of idb_gemm
     Denoiser den;

@@ -347,9 +347,7 @@ def test_fused_feed_forward_with_final_norm(eng, M):
     t = torch.tensor([900, 400, 50, 0])
     with torch.no_grad():
         ref_out = R.mdm_smpl_forward(sd, xx, t, torch.from_numpy(b["cond"]), faithful=False)
-    eng.set_fused_mlp(2)
-    try:
+    for level in (1, 2):       # 1 = feed-forward only (the norm stays with the next kernel), 2 = default
+        eng.set_fused_mlp(level)
         got2 = eng.forward(xx.cuda(), t.cuda()).cpu()
-    finally:
-        eng.set_fused_mlp(1)
-    assert rel(got2, ref_out) < 2e-4
+        assert rel(got2, ref_out) < 2e-4, level

@@ -173,11 +173,6 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
-// 16-byte asynchronous global -> shared copies (LDGSTS): a block issues all of a kernel's staging reads
-// back to back and pays ONE memory latency instead of one per loop iteration.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
 // Programmatic dependent launch: every kernel of the sampling step releases its successor at once
 // (pdl_trigger) and blocks (pdl_wait) before its first access to data produced by earlier kernels, so
 // the successor's launch latency, barrier/TMEM setup and constant-weight prefetch overlap the
@@ -197,10 +192,6 @@ inline cudaError_t idb_launch(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
 
 // GEMM front door (gemm.cu): C[M,N] = epi(A[M,K] * W[N,K]^T)   (nn.Linear layout, all row-major)
 enum { EPI_BIAS = 1, EPI_GELU = 2, EPI_RES = 4, EPI_SILU = 8 };

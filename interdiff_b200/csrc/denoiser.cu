@@ -428,28 +428,33 @@ __device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s
     }
     __syncthreads();
     if (trace) ATRACE(7);
-    // 16-lane group per (row, head): fixed-order sum of the 4 k-slices + constant term, softmax over the
-    // Tk memory slots with shuffles; probabilities row-major [row][hj] (zero for rows >= nr and for the
-    // padding columns up to a multiple of 16) as the A operand of the value product
+    // one warp per row, 8 lanes per head (H <= 4), lane `sub` holds keys sub and sub + 8 (Tk <= 16): fixed-order sum of
+    // the 4 k-slices + constant term, softmax over the Tk memory slots with 3-step shuffles inside the 8-lane group;
+    // probabilities row-major [row][hj] (zero for rows >= nr and for the padding columns up to a multiple of 16) as
+    // the A operand of the value product
     {
-        const int l16 = tid & 15;
-        for (int p = tid >> 4; p < SLAB * H; p += ANT / 16) {
-            const int r = p / H, hh = p - r * H, hj = hh * Tk + l16;
-            const bool on = l16 < Tk;
-            float a = -INFINITY;
-            if (on) {
-                const float* pp = s_z + r * XLDP + hj;
-                a = (((pp[0] + pp[SLAB * XLDP]) + pp[2 * SLAB * XLDP]) + pp[3 * SLAB * XLDP]) + s_kc[hj];
-            }
-            float mx = a;
-#pragma unroll
-            for (int o = 8; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            const float e = on ? expf(a - mx) : 0.f;
-            float sum = e;
-#pragma unroll
-            for (int o = 8; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (on) s_p[r * PLD + hj] = r < nr ? e / sum : 0.f;
+        const int r = warp, hh = lane >> 3, sub = lane & 7;
+        const bool on0 = hh < H && sub < Tk, on1 = hh < H && sub + 8 < Tk;
+        const int hj0 = hh * Tk + sub, hj1 = hj0 + 8;
+        float a0 = -INFINITY, a1 = -INFINITY;
+        if (on0) {
+            const float* pp = s_z + r * XLDP + hj0;
+            a0 = (((pp[0] + pp[SLAB * XLDP]) + pp[2 * SLAB * XLDP]) + pp[3 * SLAB * XLDP]) + s_kc[hj0];
         }
+        if (on1) {
+            const float* pp = s_z + r * XLDP + hj1;
+            a1 = (((pp[0] + pp[SLAB * XLDP]) + pp[2 * SLAB * XLDP]) + pp[3 * SLAB * XLDP]) + s_kc[hj1];
+        }
+        float mx = fmaxf(a0, a1);
+#pragma unroll
+        for (int o = 4; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e0 = on0 ? expf(a0 - mx) : 0.f, e1 = on1 ? expf(a1 - mx) : 0.f;
+        float sum = e0 + e1;
+#pragma unroll
+        for (int o = 4; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = r < nr ? 1.0f / sum : 0.f;
+        if (on0) s_p[r * PLD + hj0] = e0 * inv;
+        if (on1) s_p[r * PLD + hj1] = e1 * inv;
         const int pad = ((HT + 15) & ~15) - HT;
         for (int i = tid; i < SLAB * pad; i += ANT) s_p[(i / pad) * PLD + HT + i % pad] = 0.f;
     }

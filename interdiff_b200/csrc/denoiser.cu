@@ -607,15 +607,16 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     pdl_wait();
     ATRACE(2);
     {
-        const int t_lo = max(r0 - 1, 0), t_hi = min(r0 + nr, T - 1);      // valid staged rows t_lo .. t_hi
-        if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)(t_hi - t_lo + 1) * ROW_BYTES);
-        __syncwarp();
-        const int t = r0 - 1 + tid;
-        if (tid < nr + 2 && t >= 0 && t < T) bulk_g2s(s_x + tid * LDX, zin + (size_t)(b * T + t) * D, ROW_BYTES, bar + 1);
+        // the input rows were just written by the previous kernel (L2 resident): plain 16-byte loads straight into the
+        // padded shared-memory rows cost one L2 round trip, about half the latency of a bulk copy + mbarrier
+        for (int i = tid; i < (nr + 2) * (D / 4); i += ANT) {
+            const int l = i / (D / 4), c = i % (D / 4), t = r0 - 1 + l;
+            if (t >= 0 && t < T)
+                *reinterpret_cast<float4*>(s_x + l * LDX + c * 4) = __ldcg(reinterpret_cast<const float4*>(zin + (size_t)(b * T + t) * D) + c);
+        }
     }
     mb_wait(bar, 0);
-    mb_wait(bar + 1, 0);
-    __syncthreads();     // s_kc was written with plain stores
+    __syncthreads();     // s_x rows and s_kc were written with plain stores
     ATRACE(3);
     if (prew) {   // the previous layer's pending LayerNorm3, in place on the staged rows
         for (int l = warp; l < nr + 2; l += ANW) {

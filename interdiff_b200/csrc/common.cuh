@@ -38,6 +38,9 @@ struct DenoiserLayer {
     // folded self-attention: [Wq; Wk; (Wo_h Wv_h) for h] (1536 x 256), bias [bq; bk; 0], bo' = bo + sum_h Wo_h bv_h
     float *w_qkvf = nullptr, *b_qkvf = nullptr, *bo_f = nullptr;
     // (big, small) splits of the GEMM weights for the tensor-core path
+    __half *qt_b = nullptr, *qt_s = nullptr;                       // folded queries as fp16 (hi, lo)
+    __half *kp_hi = nullptr, *kp_lo = nullptr;                     // bound: folded memory keys, fp16 (hi, lo) [B][H*Tm][D]
+    uint32_t *vp_hi = nullptr, *vp_lo = nullptr;                   // bound: folded memory values, k-pair words [B][H*Tm/2][D]
     __half *w_qkvf_b = nullptr, *w_qkvf_s = nullptr, *w1_b = nullptr, *w1_s = nullptr,
            *w2_b = nullptr, *w2_s = nullptr;
     // QaN

@@ -20,6 +20,24 @@ constexpr int HD = 64;    // head dim
 constexpr int SLAB = 16;  // query rows per block in the per-sample attention kernels
 constexpr int LDZ = D + 4;
 
+// Step-invariant cross-attention operands, split into fp16 (hi, lo) once per bind and laid out per sample in the
+// order the attention kernels stage them: keys [B][H*Tk][D] (row hj = h*Tk + j), values as words of two k-neighbours
+// [B][H*Tk/2][D], word i = (V[2i][n], V[2i+1][n]).   kp / vp rows are (j*B + b) x [H][D].  grid (H*Tk, B), block D.
+__global__ void k_pack_memory(const float* __restrict__ kp, const float* __restrict__ vp, __half* __restrict__ kph,
+                              __half* __restrict__ kpl, uint32_t* __restrict__ vph, uint32_t* __restrict__ vpl, int B, int Tk, int H) {
+    const int hj = blockIdx.x, b = blockIdx.y, n = threadIdx.x, HT = H * Tk;
+    auto src = [&](int q) { return ((size_t)((q % Tk) * B + b) * H + q / Tk) * D + n; };
+    split_f16(kp[src(hj)], kph[((size_t)b * HT + hj) * D + n], kpl[((size_t)b * HT + hj) * D + n]);
+    if ((hj & 1) == 0) {
+        const float v0 = vp[src(hj)], v1 = hj + 1 < HT ? vp[src(hj + 1)] : 0.f;
+        __half2 h2, l2;
+        split_f16x2(v0, v1, h2, l2);
+        const size_t o = ((size_t)b * (HT >> 1) + (hj >> 1)) * D + n;
+        vph[o] = *reinterpret_cast<uint32_t*>(&h2);
+        vpl[o] = *reinterpret_cast<uint32_t*>(&l2);
+    }
+}
+
 // bind-time: scale the folded keys by 1/sqrt(hd) and compute the constant logit term
 //   kc[row][h] = (bq_h . K_h[row]) / 8.   One warp per (row, head).
 __global__ void k_fold_scale(float* __restrict__ kp, const float* __restrict__ kv, const float* __restrict__ bq,
@@ -383,15 +401,35 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
     }
 }
 
+// Step-invariant B operands (folded queries, folded memory keys / values) are split into fp16 (hi, lo) ONCE (at
+// commit / bind) so that their fragments are plain 32-bit loads: rows operands as fp16 [rows][KPH] (k contiguous),
+// K x N operands with the two k-neighbours of a column packed in one word, [K/2][VPW].  Strides: KPH/2 = 4 mod 32
+// words, VPW = 8 mod 32 words (conflict-free).
+constexpr int KPH = D + 8;     // halfs per staged row of a pre-split "rows" operand
+constexpr int VPW = D + 8;     // words per staged row of a k-pair-packed K x N operand
+__device__ __forceinline__ void load_b_frag_rows_pk(const __half* __restrict__ sh, const __half* __restrict__ sl, int n0, int nrows,
+                                                    int k0, int lane, uint32_t (&hi)[2], uint32_t (&lo)[2]) {
+    const int off = min(n0 + (lane >> 2), nrows - 1) * KPH + k0 + 2 * (lane & 3);
+    hi[0] = *reinterpret_cast<const uint32_t*>(sh + off); hi[1] = *reinterpret_cast<const uint32_t*>(sh + off + 8);
+    lo[0] = *reinterpret_cast<const uint32_t*>(sl + off); lo[1] = *reinterpret_cast<const uint32_t*>(sl + off + 8);
+}
+__device__ __forceinline__ void load_b_frag_cols_pk(const uint32_t* __restrict__ sh, const uint32_t* __restrict__ sl, int k0, int nkp,
+                                                    int n0, int lane, uint32_t (&hi)[2], uint32_t (&lo)[2]) {
+    const int g = lane >> 2, c = lane & 3;
+    const int o0 = min((k0 >> 1) + c, nkp - 1) * VPW + n0 + g, o1 = min((k0 >> 1) + c + 4, nkp - 1) * VPW + n0 + g;
+    hi[0] = sh[o0]; hi[1] = sh[o1]; lo[0] = sl[o0]; lo[1] = sl[o1];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Cross-attention block with BOTH projections folded into the step-invariant memory tensors:
 //   logit[t,h,j] = x1[t] . kp[h,j] + kc[h,j]      kp = (K_h Wq_h)/8 (256-vector), kc = (bq_h . K_h)/8
 //   out[t] = LN2( x1[t] + bo + sum_{h,j} softmax_j(logit)[t,h,j] vp[h,j] )      vp = V_h Wo_h^T
 // so no query GEMM is needed and the block can run right after the layer's first sub-block while its
-// x1 rows are still in shared memory.  s_kp [HT][LDZ], s_kc [HT], s_v [HT][VLD] and the parameter rows
+// x1 rows are still in shared memory.  s_kph/s_kpl [HT][KPH] fp16, s_kc [HT], s_vph/s_vpl [HT/2][VPW] and the parameter rows
 // s_bo / s_lnw / s_lnb must already be staged.  Tk <= 16, H*Tk <= 64.
-__device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s_x1, const float* __restrict__ s_kp,
-                                                     const float* __restrict__ s_kc, const float* __restrict__ s_v,
+__device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s_x1, const __half* __restrict__ s_kph,
+                                                     const __half* __restrict__ s_kpl, const float* __restrict__ s_kc,
+                                                     const uint32_t* __restrict__ s_vph, const uint32_t* __restrict__ s_vpl,
                                                      float* __restrict__ s_p, float* __restrict__ s_z, int nr, int HT, int Tk, int H,
                                                      const float* __restrict__ s_bo, const float* __restrict__ s_lnw,
                                                      const float* __restrict__ s_lnb, float* __restrict__ out,
@@ -409,10 +447,10 @@ __device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s
             for (int kk = ks * 4; kk < ks * 4 + 4; kk++) {
                 uint32_t ah[4], al[4], bh[2], bl[2];
                 load_a_frag(s_x1, LDX, 0, nr, kk * 16, lane, ah, al);
-                load_b_frag_rows(s_kp, LDX, ng * 8, HT, kk * 16, lane, bh, bl);
+                load_b_frag_rows_pk(s_kph, s_kpl, ng * 8, HT, kk * 16, lane, bh, bl);
                 mma_pairs(m0, q0, ah, al, bh, bl);
                 if (t1) {
-                    load_b_frag_rows(s_kp, LDX, (ng + 4) * 8, HT, kk * 16, lane, bh, bl);
+                    load_b_frag_rows_pk(s_kph, s_kpl, (ng + 4) * 8, HT, kk * 16, lane, bh, bl);
                     mma_pairs(m1, q1, ah, al, bh, bl);
                 }
             }
@@ -468,9 +506,9 @@ __device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s
         for (int kk = 0; kk < nks; kk++) {
             uint32_t ah[4], al[4], bh[2], bl[2];
             load_a_frag(s_p, PLD, 0, SLAB, kk * 16, lane, ah, al);
-            load_b_frag_cols(s_v, VLD, kk * 16, HT, n0, lane, bh, bl);
+            load_b_frag_cols_pk(s_vph, s_vpl, kk * 16, HT >> 1, n0, lane, bh, bl);
             mma_pairs(m0, q0, ah, al, bh, bl);
-            load_b_frag_cols(s_v, VLD, kk * 16, HT, n0 + 8, lane, bh, bl);
+            load_b_frag_cols_pk(s_vph, s_vpl, kk * 16, HT >> 1, n0 + 8, lane, bh, bl);
             mma_pairs(m1, q1, ah, al, bh, bl);
         }
         const float sc = 1.0f / 2048.0f;
@@ -498,33 +536,38 @@ __device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s
     }
 }
 
-// stage the folded memory tensors of sample b (rows j*B + b of kp / vp / kc): one bulk copy per row
-__device__ __forceinline__ void stage_memory(const float* __restrict__ kp, const float* __restrict__ kc, const float* __restrict__ vp,
-                                             float* __restrict__ s_kp, float* __restrict__ s_kc, float* __restrict__ s_v,
-                                             int b, int B, int Tk, int H, uint64_t* bar) {
-    const int HT = H * Tk, tid = threadIdx.x;
-    for (int i = tid; i < 2 * HT; i += ANT) {
-        const int hj = i < HT ? i : i - HT, hh = hj / Tk, j = hj - hh * Tk;
-        const size_t row = (size_t)(j * B + b) * H * D + (size_t)hh * D;
-        if (i < HT) bulk_g2s(s_kp + hj * LDX, kp + row, ROW_BYTES, bar);
-        else bulk_g2s(s_v + (size_t)hj * VLD, vp + row, ROW_BYTES, bar);
+// stage the pre-split folded memory tensors of sample b: one bulk copy per row (keys: 512 B fp16 rows hi / lo;
+// values: 1 KB rows of k-pair words hi / lo); kc with plain loads
+__device__ __forceinline__ void stage_memory(const __half* __restrict__ kph, const __half* __restrict__ kpl, const float* __restrict__ kc,
+                                             const uint32_t* __restrict__ vph, const uint32_t* __restrict__ vpl,
+                                             __half* __restrict__ s_kph, __half* __restrict__ s_kpl, float* __restrict__ s_kc,
+                                             uint32_t* __restrict__ s_vph, uint32_t* __restrict__ s_vpl, int b, int B, int Tk, int H,
+                                             uint64_t* bar) {
+    const int HT = H * Tk, HP = HT >> 1, tid = threadIdx.x;
+    for (int i = tid; i < 2 * HT + 2 * HP; i += ANT) {
+        if (i < HT) bulk_g2s(s_kph + i * KPH, kph + ((size_t)b * HT + i) * D, D * sizeof(__half), bar);
+        else if (i < 2 * HT) bulk_g2s(s_kpl + (i - HT) * KPH, kpl + ((size_t)b * HT + i - HT) * D, D * sizeof(__half), bar);
+        else if (i < 2 * HT + HP) bulk_g2s(s_vph + (i - 2 * HT) * VPW, vph + ((size_t)b * HP + i - 2 * HT) * D, ROW_BYTES, bar);
+        else bulk_g2s(s_vpl + (i - 2 * HT - HP) * VPW, vpl + ((size_t)b * HP + i - 2 * HT - HP) * D, ROW_BYTES, bar);
     }
     for (int hj = tid; hj < HT; hj += ANT) s_kc[hj] = kc[(size_t)((hj % Tk) * B + b) * H + hj / Tk];
 }
 
 // standalone cross-attention block (layers whose first sub-block is the standard self-attention)
 __global__ void __launch_bounds__(ANT)
-k_xattn_ln(const float* __restrict__ x1, const float* __restrict__ kp, const float* __restrict__ kc, const float* __restrict__ vp,
-           const float* __restrict__ bo, const float* __restrict__ lnw, const float* __restrict__ lnb, float* __restrict__ out,
+k_xattn_ln(const float* __restrict__ x1, const __half* __restrict__ kph, const __half* __restrict__ kpl, const float* __restrict__ kc,
+           const uint32_t* __restrict__ vph, const uint32_t* __restrict__ vpl, const float* __restrict__ bo, const float* __restrict__ lnw, const float* __restrict__ lnb, float* __restrict__ out,
            __half* __restrict__ out_b, __half* __restrict__ out_s, int T, int B, int Tk, int H) {
     extern __shared__ __align__(16) float sm[];
     const int HT = H * Tk;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: step-invariant tensors, [1]: input rows
     float* s_par = sm + 4;                  // bo, lnw, lnb
     float* s_x1 = s_par + 3 * D;            // [SLAB][LDX]
-    float* s_kp = s_x1 + SLAB * LDX;        // [HT][LDX]
-    float* s_v = s_kp + HT * LDX;           // [HT][VLD]
-    float* s_a = s_v + HT * VLD;            // [SLAB][PLD]     probabilities
+    __half* s_kph = reinterpret_cast<__half*>(s_x1 + SLAB * LDX);      // [HT][KPH] fp16, hi then lo
+    __half* s_kpl = s_kph + HT * KPH;
+    uint32_t* s_vph = reinterpret_cast<uint32_t*>(s_kpl + HT * KPH);   // [HT/2][VPW] k-pair words, hi then lo
+    uint32_t* s_vpl = s_vph + (HT >> 1) * VPW;
+    float* s_a = reinterpret_cast<float*>(s_vpl + (HT >> 1) * VPW);    // [SLAB][PLD]     probabilities
     float* s_z = s_a + SLAB * PLD;          // [SLAB][LDZ]
     float* s_kc = s_z + SLAB * LDZ;         // [HT]
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
@@ -539,7 +582,7 @@ k_xattn_ln(const float* __restrict__ x1, const float* __restrict__ kp, const flo
         bulk_g2s(s_par, bo, ROW_BYTES, bar); bulk_g2s(s_par + D, lnw, ROW_BYTES, bar); bulk_g2s(s_par + 2 * D, lnb, ROW_BYTES, bar);
     }
     __syncwarp();
-    stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H, bar);     // step-invariant: overlaps the previous kernel
+    stage_memory(kph, kpl, kc, vph, vpl, s_kph, s_kpl, s_kc, s_vph, s_vpl, b, B, Tk, H, bar);     // step-invariant: overlaps the previous kernel
     pdl_wait();
     if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)nr * ROW_BYTES);
     __syncwarp();
@@ -547,8 +590,8 @@ k_xattn_ln(const float* __restrict__ x1, const float* __restrict__ kp, const flo
     mb_wait(bar, 0);
     mb_wait(bar + 1, 0);
     __syncthreads();     // s_kc was written with plain stores
-    cross_attention_tail(s_x1, s_kp, s_kc, s_v, s_a, s_z, nr, HT, Tk, H, s_par, s_par + D, s_par + 2 * D, out, out_b, out_s,
-                         (size_t)b * T + r0);
+    cross_attention_tail(s_x1, s_kph, s_kpl, s_kc, s_vph, s_vpl, s_a, s_z, nr, HT, Tk, H, s_par, s_par + D, s_par + 2 * D, out, out_b,
+                         out_s, (size_t)b * T + r0);
 }
 
 // QaN block + residual + LayerNorm1 (model/sublayers.py:343-352 + :332) for a slab of <= 16 rows of
@@ -562,9 +605,9 @@ k_xattn_ln(const float* __restrict__ x1, const float* __restrict__ kp, const flo
 template <bool XATTN>
 __global__ void __launch_bounds__(ANT)
 k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, const float* __restrict__ preb,
-               const float* __restrict__ qt, const float* __restrict__ wk, const float* __restrict__ lnw,
-               const float* __restrict__ lnb, const float* __restrict__ kp, const float* __restrict__ kc,
-               const float* __restrict__ vp, const float* __restrict__ bo2, const float* __restrict__ ln2w,
+               const __half* __restrict__ qth, const __half* __restrict__ qtl, const float* __restrict__ wk, const float* __restrict__ lnw,
+               const float* __restrict__ lnb, const __half* __restrict__ kph, const __half* __restrict__ kpl, const float* __restrict__ kc,
+               const uint32_t* __restrict__ vph, const uint32_t* __restrict__ vpl, const float* __restrict__ bo2, const float* __restrict__ ln2w,
                const float* __restrict__ ln2b, float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s,
                int T, int N, int B, int Tk, int H) {
     extern __shared__ __align__(16) float sm[];
@@ -572,11 +615,14 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: step-invariant tensors, [1]: input rows
     float* s_par = sm + 4;                  // pre w, pre b, ln1 w, ln1 b, bo2, ln2 w, ln2 b
     float* s_x = s_par + 7 * D;             // [SLAB+2][LDX]   rows r0-1 .. r0+nr
-    float* s_qt = s_x + (SLAB + 2) * LDX;   // [30][LDX]
-    float* s_x1 = s_qt + 30 * LDX;          // [SLAB][LDX]     LN1 rows (input of the cross-attention block)
-    float* s_kp = s_x1 + SLAB * LDX;        // [HT][LDX]
-    float* s_v = s_kp + HT * LDX;           // [HT][VLD]
-    float* s_a = s_v + HT * VLD;            // [SLAB][PLD]     probabilities
+    __half* s_qth = reinterpret_cast<__half*>(s_x + (SLAB + 2) * LDX);   // [30][KPH] fp16 folded queries, hi then lo
+    __half* s_qtl = s_qth + 30 * KPH;
+    float* s_x1 = reinterpret_cast<float*>(s_qtl + 30 * KPH);            // [SLAB][LDX]     LN1 rows (input of the cross-attention block)
+    __half* s_kph = reinterpret_cast<__half*>(s_x1 + SLAB * LDX);        // [HT][KPH]
+    __half* s_kpl = s_kph + HT * KPH;
+    uint32_t* s_vph = reinterpret_cast<uint32_t*>(s_kpl + HT * KPH);     // [HT/2][VPW]
+    uint32_t* s_vpl = s_vph + (HT >> 1) * VPW;
+    float* s_a = reinterpret_cast<float*>(s_vpl + (HT >> 1) * VPW);      // [SLAB][PLD]     probabilities
     float* s_z = XATTN ? s_a + SLAB * PLD : s_x1;   // [SLAB][LDZ]  (encoder variant: no cross-attention buffers at all)
     float* s_kc = s_z + SLAB * LDZ;         // [HT]
     const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
@@ -598,10 +644,12 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     if (tid < 7) {
         const float* src = tid == 0 ? prew : tid == 1 ? preb : tid == 2 ? lnw : tid == 3 ? lnb : tid == 4 ? bo2 : tid == 5 ? ln2w : ln2b;
         if (src && (XATTN || tid < 4)) bulk_g2s(s_par + tid * D, src, ROW_BYTES, bar);
-    } else if (tid >= 32 && tid < 32 + NQ) {
-        bulk_g2s(s_qt + (tid - 32) * LDX, qt + (size_t)(tid - 32) * D, ROW_BYTES, bar);
+    } else if (tid >= 32 && tid < 32 + 2 * NQ) {
+        const int r = tid - 32;
+        if (r < NQ) bulk_g2s(s_qth + r * KPH, qth + (size_t)r * D, D * sizeof(__half), bar);
+        else bulk_g2s(s_qtl + (r - NQ) * KPH, qtl + (size_t)(r - NQ) * D, D * sizeof(__half), bar);
     }
-    if (XATTN) stage_memory(kp, kc, vp, s_kp, s_kc, s_v, b, B, Tk, H, bar);
+    if (XATTN) stage_memory(kph, kpl, kc, vph, vpl, s_kph, s_kpl, s_kc, s_vph, s_vpl, b, B, Tk, H, bar);
     const float wk_n = lane < N ? wk[lane] : 0.f;
     ATRACE(1);
     pdl_wait();
@@ -637,9 +685,9 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
         for (int kk = ks * 4; kk < ks * 4 + 4; kk++) {
             uint32_t ah[4], al[4], bh[2], bl[2];
             load_a_frag(s_x, LDX, mt * 16, nr + 2, kk * 16, lane, ah, al);
-            load_b_frag_rows(s_qt, LDX, np * 16, NQ, kk * 16, lane, bh, bl);
+            load_b_frag_rows_pk(s_qth, s_qtl, np * 16, NQ, kk * 16, lane, bh, bl);
             mma_pairs(m0, q0, ah, al, bh, bl);
-            load_b_frag_rows(s_qt, LDX, np * 16 + 8, NQ, kk * 16, lane, bh, bl);
+            load_b_frag_rows_pk(s_qth, s_qtl, np * 16 + 8, NQ, kk * 16, lane, bh, bl);
             mma_pairs(m1, q1, ah, al, bh, bl);
         }
         const float sc = 1.0f / 2048.0f;
@@ -716,8 +764,8 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     if (!XATTN) return;
     __syncthreads();
     ATRACE(6);
-    cross_attention_tail(s_x1, s_kp, s_kc, s_v, s_a, s_z, nr, HT, Tk, H, s_par + 4 * D, s_par + 5 * D, s_par + 6 * D, out, out_b, out_s,
-                         (size_t)b * T + r0, true);
+    cross_attention_tail(s_x1, s_kph, s_kpl, s_kc, s_vph, s_vpl, s_a, s_z, nr, HT, Tk, H, s_par + 4 * D, s_par + 5 * D, s_par + 6 * D,
+                         out, out_b, out_s, (size_t)b * T + r0, true);
     ATRACE(11);
 }
 
@@ -1173,6 +1221,7 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
         for (auto* stack : {&d.layers, &d.enc_layers})
             for (auto& L : *stack) {
                 if (!rc && !L.qan) rc = split(L.w_qkvf, 2 * D + H * D, D, D, &L.w_qkvf_b, &L.w_qkvf_s);
+                if (!rc && L.qan) rc = split(L.qt, 3 * N, D, D, &L.qt_b, &L.qt_s);
                 if (!rc) rc = split(L.w1, F, D, D, &L.w1_b, &L.w1_s);
                 if (!rc) rc = split(L.w2, D, F, F, &L.w2_b, &L.w2_s);
             }
@@ -1220,6 +1269,8 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
         for (auto& L : d.layers) {
             rc |= A(&L.kv_mem, (size_t)Tm * B * 2 * D); rc |= A(&L.vp_mem, (size_t)Tm * B * H * D);
             rc |= A(&L.kp_mem, (size_t)Tm * B * H * D); rc |= A(&L.kc_mem, (size_t)Tm * B * H);
+            rc |= AH(&L.kp_hi, (size_t)Tm * B * H * D); rc |= AH(&L.kp_lo, (size_t)Tm * B * H * D);
+            rc |= AH(reinterpret_cast<__half**>(&L.vp_hi), (size_t)Tm * B * H * D); rc |= AH(reinterpret_cast<__half**>(&L.vp_lo), (size_t)Tm * B * H * D);
         }
         if (rc) return rc;
         CUDA_TRY(h, cudaMalloc((void**)&d.step_cur, 2 * sizeof(int)));
@@ -1246,6 +1297,8 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
         }
         k_fold_scale<<<(Tm * B * H + 7) / 8, 256, 0, st>>>(L.kp_mem, L.kv_mem, L.b_qc, L.kc_mem, Tm * B, H);
         LAUNCH_CHECK(h);
+        k_pack_memory<<<dim3(H * Tm, B), D, 0, st>>>(L.kp_mem, L.vp_mem, L.kp_hi, L.kp_lo, L.vp_hi, L.vp_lo, B, Tm, H);
+        LAUNCH_CHECK(h);
     }
     return IDB_OK;
 }
@@ -1257,7 +1310,8 @@ static size_t attn_smem(int Tk, int H) {   // barriers, 3 parameter rows, s_q, s
 }
 static size_t xattn_tail_smem(int Tk, int H) {   // s_x1, s_kp, s_v, s_a, s_z, s_kc
     const size_t HT = (size_t)H * Tk;
-    return sizeof(float) * ((size_t)SLAB * (D + 8) + HT * (D + 8) + HT * (D + 4) + (size_t)SLAB * 72 + (size_t)SLAB * LDZ + HT + 4);
+    // s_x1, keys fp16 hi+lo [HT][264] (= HT*264 words), value k-pair words hi+lo [HT/2][264] (= HT*264 words), s_p, s_z, s_kc
+    return sizeof(float) * ((size_t)SLAB * (D + 8) + HT * (D + 8) + HT * (D + 8) + (size_t)SLAB * 72 + (size_t)SLAB * LDZ + HT + 4);
 }
 static size_t xattn_smem(int Tk, int H) { return sizeof(float) * (4 + 3 * D) + xattn_tail_smem(Tk, H); }
 static size_t qan_enc_smem() {      // encoder variant: barriers, parameter rows, s_x, s_qt, s_z
@@ -1296,7 +1350,7 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
             const float* in = pending ? d.z : d.h;
             // QaN block + LN1 + cross-attention + LN2 in one kernel: (z | h) -> (d.h2, pairs)
             idb_launch(pdl, k_qan_xattn_ln<true>, slab_grid, ANT, qan_smem(Tm, H), st, in, pending ? pending->ln3w : nullptr,
-                       pending ? pending->ln3b : nullptr, L.qt, L.wk, L.ln1w, L.ln1b, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc,
+                       pending ? pending->ln3b : nullptr, L.qt_b, L.qt_s, L.wk, L.ln1w, L.ln1b, L.kp_hi, L.kp_lo, L.kc_mem, L.vp_hi, L.vp_lo, L.b_oc,
                        L.ln2w, L.ln2b, d.h2, d.h2_b, d.h2_s, T, N, B, Tm, H);
             LAUNCH_CHECK(h);
         } else {
@@ -1311,7 +1365,7 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
                        L.bo_f, L.ln1w, L.ln1b, d.qc, nullptr, nullptr, T, H);
             LAUNCH_CHECK(h);
             // cross attention on the LN1 rows (d.qc) -> (d.h2, pairs)
-            idb_launch(pdl, k_xattn_ln, slab_grid, ANT, xattn_smem(Tm, H), st, d.qc, L.kp_mem, L.kc_mem, L.vp_mem, L.b_oc,
+            idb_launch(pdl, k_xattn_ln, slab_grid, ANT, xattn_smem(Tm, H), st, d.qc, L.kp_hi, L.kp_lo, L.kc_mem, L.vp_hi, L.vp_lo, L.b_oc,
                        L.ln2w, L.ln2b, d.h2, d.h2_b, d.h2_s, T, B, Tm, H);
             LAUNCH_CHECK(h);
         }
@@ -1522,9 +1576,10 @@ extern "C" int idb_encode_condition(idb_handle* h, int B, int Tp, const float* p
     for (auto& L : d.enc_layers) {
         if (L.qan) {
             idb_launch(pdl, k_qan_xattn_ln<false>, slab_grid, ANT, qan_enc_smem(), st, pending ? d.e_z : d.e_h,
-                       pending ? pending->ln3w : nullptr, pending ? pending->ln3b : nullptr, L.qt, L.wk, L.ln1w, L.ln1b,
-                       (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr,
-                       (const float*)nullptr, d.e_h2, d.e_h2_b, d.e_h2_s, Tp, N, B, 0, H);
+                       pending ? pending->ln3w : nullptr, pending ? pending->ln3b : nullptr, L.qt_b, L.qt_s, L.wk, L.ln1w, L.ln1b,
+                       (const __half*)nullptr, (const __half*)nullptr, (const float*)nullptr, (const uint32_t*)nullptr,
+                       (const uint32_t*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, d.e_h2, d.e_h2_b,
+                       d.e_h2_s, Tp, N, B, 0, H);
             LAUNCH_CHECK(h);
         } else {
             if (pending) {

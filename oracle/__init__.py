@@ -20,4 +20,7 @@ Pinning status (see DESIGN.md "Oracle"):
         'absolute' is the default, see oracle/local_attention_restated.py)
       - chamfer_distance (first-minimum squared-L2 argmin)
       - pytorch3d.transforms 0.7.2
+      - pointnet2_ops 3.0.0 (furthest_point_sampling, ball_query, grouping: oracle/pointnet2_restated.py; the
+        golden vector of the point-cloud encoder is the reference's own PointNet2Encoder class running on these
+        restated operators)
 """

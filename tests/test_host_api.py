@@ -51,7 +51,7 @@ def test_mirror_state_dict_names_match_tables():
     sd = MDM(Namespace(**SMPL_ARGS)).state_dict()
     for k, shp in W.mdm_hot_shapes("smpl", F=1024).items():
         assert k in sd and tuple(sd[k].shape) == tuple(shp), k
-    for k, shp in W.mdm_encoder_shapes("smpl", F=1024).items():
+    for k, shp in {**W.mdm_encoder_shapes("smpl", F=1024), **W.pointnet_shapes()}.items():
         assert k in sd and tuple(sd[k].shape) == tuple(shp), k
     from interdiff_b200.model.correction_smpl import ObjProjector
     psd = ObjProjector(Namespace(dct=10, num_verts=67, dropout=0.1, past_len=10, future_len=20, embedding_dim=64)).state_dict()

@@ -323,6 +323,37 @@ def test_correction_hook(eng, smplh_np):
     assert rel(got, ref) < 1e-4
 
 
+def test_full_size_properties(eng):
+    """BASELINE configs[1] sizes (B=64, T=30, 100-step schedule), where the oracle takes minutes: size-independent
+    properties instead.  (1) batch independence: the samples of the full batch equal the same samples denoised in
+    a batch of 4 (every kernel works per row / per sample: identical on the SIMT backend; on the tensor backend the
+    GEMM tile configuration and accumulator count depend on M, so equal to rounding);
+    (2) the inpainted past of a sampling loop equals the ground truth exactly; (3) graph replay == eager launches,
+    bit for bit; (4) two runs of the loop are bit-identical (no atomics with more than two addends anywhere)."""
+    sd = mdm_weights("smpl", "auto")
+    eng.load_denoiser(sd, "smpl")
+    B, T, steps = 64, 30, 100
+    b = S.make_smpl_batch(B=B, T=T)
+    x = torch.from_numpy(S.noise_tape(b["gt"].shape, 0)[0]).cuda()
+    t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(1))
+    eng.bind(b["cond"], T)
+    full = eng.forward(x, t.cuda()).cpu()
+    pick = [0, 17, 40, 63]
+    eng.bind(np.ascontiguousarray(b["cond"][:, pick]), T)
+    sub = eng.forward(x[pick].contiguous(), t[pick].cuda()).cpu()
+    assert rel(sub, full[pick]) < 2e-4
+    eng.bind(b["cond"], T)
+    eng.init_diffusion(R.named_beta_schedule("cosine", steps))
+    tape = torch.from_numpy(S.noise_tape(b["gt"].shape, steps)).cuda()
+    gt, mask = torch.from_numpy(b["gt"]).cuda(), torch.from_numpy(b["mask"]).cuda()
+    a1 = eng.p_sample_loop(tape, gt, mask, use_graph=True).clone()
+    a2 = eng.p_sample_loop(tape, gt, mask, use_graph=True).clone()
+    a3 = eng.p_sample_loop(tape, gt, mask, use_graph=False).clone()
+    assert torch.equal(a1, a2) and torch.equal(a1, a3)
+    assert torch.equal(a1[mask], gt[mask])
+    assert torch.isfinite(a1).all()
+
+
 @pytest.mark.parametrize("M", [1920, 129])
 def test_fused_feed_forward_with_final_norm(eng, M):
     """level 2 of the fused feed-forward kernel: the layer's final LayerNorm applied in the reduction epilogue (two

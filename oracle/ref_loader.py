@@ -45,7 +45,7 @@ def modules():
     _prepare()
     import importlib
     for name in ("diffusion.gaussian_diffusion", "diffusion.respace", "model.sublayers", "model.layers",
-                 "model.diffusion_smpl", "model.diffusion_skeleton", "model.correction_smpl",
+                 "model.diffusion_smpl", "model.diffusion_skeleton", "model.correction_smpl", "model.correction_skeleton",
                  "data.tools", "data.utils", "tools",
                  "libsmpl.smplpytorch.pytorch.smpl_layer"):
         _IMPORTED[name] = importlib.import_module(name)
@@ -127,6 +127,16 @@ def build_obj_projector(state_dict=None, past_len=10, future_len=20):
     model.load_state_dict(state_dict, strict=True)
     model.eval()
     return model, args
+
+
+def build_obj_projector_skeleton():
+    """Reference skeleton correction net (model/correction_skeleton.py:8-135) with checkpoints/obj_skeleton.ckpt."""
+    m = modules()["model.correction_skeleton"]
+    hp, sd = load_ckpt("obj_skeleton")
+    model = m.ObjProjector(Namespace(**hp))
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    return model, Namespace(**hp), sd
 
 
 def build_smpl_layer(smplh):

@@ -530,6 +530,43 @@ def obj_projector_sample(sd, obj_angles, obj_trans, human_verts, contact, past_l
     return final
 
 
+def obj_projector_skeleton_sample(sd, obj_angles, obj_trans, human_points, past_len, future_len, n_pre=20):
+    """Skeleton correction net, ObjProjector.sample in eval mode (model/correction_skeleton.py:84-135; SURVEY 8f rank 4,
+    oracle only so far).  obj_angles (T,B,4) quaternion xyzw, obj_trans (T,B,3), human_points (T,B,J,3)
+    -> (obj_angles_p (T,B,4) xyzw, obj_trans_p (T,B,3))."""
+    quat = torch.cat([obj_angles[:, :, -1, None], obj_angles[:, :, -4:-1]], dim=2)
+    ang6 = tf.matrix_to_rotation_6d(tf.quaternion_to_matrix(quat))
+    T0 = past_len + future_len
+    dct_m, idct_m = dct_matrices(T0)
+    dct_m, idct_m = torch.from_numpy(dct_m).float(), torch.from_numpy(idct_m).float()
+    idx_pad = list(range(past_len)) + [past_len - 1] * future_len
+    rel_t = obj_trans.unsqueeze(2) - human_points
+    obj_rel = torch.cat([ang6.unsqueeze(2).repeat(1, 1, rel_t.shape[2], 1), rel_t], dim=3)[idx_pad]
+    T, B, P, C = obj_rel.shape
+    obj_rel = obj_rel.permute(1, 0, 3, 2).contiguous().view(B, T, C * P)
+    obj_rel = torch.matmul(dct_m[:n_pre], obj_rel).view(B, -1, C, P).permute(0, 2, 1, 3).contiguous()
+    x = obj_rel.clone()
+    for i in range(4):
+        x = st_gcnn_layer(sd, "st_gcnns_relative.%d." % i, x)
+    obj_rel = obj_rel + x
+    human_trans = human_points.permute(1, 0, 3, 2).contiguous().view(B, T, -1)
+    human_trans = torch.matmul(dct_m[:n_pre], human_trans).view(B, -1, 3, P).permute(0, 2, 1, 3).contiguous()
+    obj_multi = torch.cat([obj_rel[:, :6], obj_rel[:, 6:9] + human_trans], dim=1)
+    obj = torch.cat([ang6, obj_trans], dim=2)[idx_pad].unsqueeze(2).permute(1, 0, 3, 2).contiguous().view(B, T, C)
+    obj = torch.matmul(dct_m[:n_pre], obj).view(B, -1, C, 1).permute(0, 2, 1, 3).contiguous()
+    x = obj.clone()
+    for i in range(4):
+        x = st_gcnn_layer(sd, "st_gcnns.%d." % i, x)
+    obj = torch.cat([obj + x, obj_multi], dim=3)
+    x = obj.clone()
+    for i in range(4):
+        x = st_gcnn_layer(sd, "st_gcnns_all.%d." % i, x)
+    obj = (obj + x).permute(0, 2, 1, 3).contiguous().view(B, -1, C * (P + 1))
+    results = torch.matmul(idct_m[:, :n_pre], obj).view(B, T, C, P + 1).permute(1, 0, 3, 2)[:, :, 0, :9]
+    q = tf.matrix_to_quaternion(tf.rotation_6d_to_matrix(results[:, :, :6]))
+    return torch.cat([q[:, :, 1:4], q[:, :, 0, None]], dim=2), results[:, :, 6:9]
+
+
 # ----------------------------------------------------------------------------------------
 # A7: the correction hook (denoised_fn of eval_smpl_short.py:84-130)
 # ----------------------------------------------------------------------------------------

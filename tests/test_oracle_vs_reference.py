@@ -161,6 +161,21 @@ def test_obj_projector():
     assert rel(got, ref) < 1e-5
 
 
+def test_obj_projector_skeleton():
+    """oracle restatement of the skeleton correction net against the reference class with checkpoints/obj_skeleton.ckpt
+    (the CUDA side of this row is not built yet; this pins the checker for it)."""
+    model, args, sd = RL.build_obj_projector_skeleton()
+    g = torch.Generator().manual_seed(8)
+    T, B = args.past_len + args.future_len, 4
+    quat = torch.nn.functional.normalize(torch.randn(T, B, 4, generator=g), dim=2)
+    tr = torch.randn(T, B, 3, generator=g)
+    hp = torch.randn(T, B, args.num_joints, 3, generator=g)
+    with torch.no_grad():
+        ref_q, ref_t = model.sample(quat, tr, hp)
+        got_q, got_t = R.obj_projector_skeleton_sample(sd, quat, tr, hp, args.past_len, args.future_len)
+    assert rel(got_q, ref_q) < 1e-5 and rel(got_t, ref_t) < 1e-5
+
+
 def _reference_function(fname, name, env):
     """Compile ONE function of a reference script (the script itself cannot be imported: it
     pulls pytorch_lightning / psbody / render at module level) into `env`."""

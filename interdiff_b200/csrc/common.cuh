@@ -109,6 +109,7 @@ struct idb_handle {
     long long launches = 0;   // kernels launched through this handle (bench's gpu_launches)
     int gemm_backend = 1;     // 0 = fp32 SIMT (debug / bisect), 1 = tcgen05 split-fp16 (default)
     int pdl = 1;              // programmatic dependent launch between the kernels of a sampling step
+    unsigned attr_mask = 0;   // kernels whose > 48 KB shared-memory opt-in was done on this handle's device (bit 0 GEMM, 1 MLP, 2 NN)
     double last_ms = 0.0;     // mean launch time of the last timed debug hook
     int nn_pruning = 1;       // cluster-pruned nearest-neighbour search for body-mesh targets (identical results)
     int fused_mlp = 2;        // feed-forward block as ONE cluster kernel (tensor backend, d_model 256, d_ff 1024); 2 = incl. the layer's final norm

@@ -710,7 +710,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-bool g_attr_set = false;
 
 int make_map(idb_handle* h, CUtensorMap* map, const __half* ptr, int rows, int cols, int ld, int box_rows) {
     if (!g_encode) {
@@ -750,11 +749,11 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
         return idb_fail(h, IDB_ERR_ARG, "tcgen05 GEMM needs 16-byte aligned pointers");
     if ((g.epi & EPI_RES) && ((g.ldr % 4) || mis(g.res))) return idb_fail(h, IDB_ERR_ARG, "residual must be 16-byte aligned");
     if ((g.epi & EPI_BIAS) && mis(g.bias)) return idb_fail(h, IDB_ERR_ARG, "bias must be 16-byte aligned");
-    if (!g_attr_set) {
+    if (!(h->attr_mask & 1u)) {      // per handle = per device (function attributes live in the device's context)
         CUDA_TRY(h, cudaFuncSetAttribute(gemm_split_f16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
         CUDA_TRY(h, cudaFuncSetAttribute(gemm_split_f16_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
         CUDA_TRY(h, cudaFuncSetAttribute(gemm_split_f16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
-        g_attr_set = true;
+        h->attr_mask |= 1u;
     }
     // wide outputs take 128-column tiles; narrow ones 64 so more SMs get a tile
     const long tiles128 = (long)((M + BM - 1) / BM) * ((N + 127) / 128);
@@ -816,10 +815,9 @@ int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const
                     int pdl, cudaStream_t st, const float* ln_w, const float* ln_b, __half* Z_hi, __half* Z_lo) {
     long long* trace = g_idb_gemm_trace;
     g_idb_gemm_trace = nullptr;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(h->attr_mask & 2u)) {
         CUDA_TRY(h, cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mlp::SMEM_BYTES));
-        attr_set = true;
+        h->attr_mask |= 2u;
     }
     const int F = mlp::FC * mlp::CLUSTER;
     CUtensorMap mx, mxl, mw1, mw1l, mw2, mw2l;

@@ -244,10 +244,9 @@ extern "C" int idb_signed_nn(idb_handle* h, int F, int Pq, int Pt, const float* 
     if (h->nn_pruning && h->body && h->body->nn_vid && Pt == h->body->V && Pt <= 12000) {
         const int Ptp = (Pt + 3) & ~3;
         const size_t smem = sizeof(float) * 3 * Ptp + sizeof(float4) * NN_CLUSTERS + sizeof(int32_t) * (NN_CLUSTERS + 4) + sizeof(uint16_t) * Ptp + sizeof(unsigned) * 16 * (NN_CLUSTERS / 32);
-        static bool attr = false;
-        if (!attr) {
+        if (!(h->attr_mask & 4u)) {
             CUDA_TRY(h, cudaFuncSetAttribute(k_signed_nn_pruned, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr = true;
+            h->attr_mask |= 4u;
         }
         const int qchunk = 1024;
         dim3 grid((Pq + qchunk - 1) / qchunk, F);

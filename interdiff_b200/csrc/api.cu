@@ -6,6 +6,7 @@ void idb_sampler_release(idb_handle* h);
 void idb_body_release(idb_handle* h);
 void idb_projector_release(idb_handle* h);
 int idb_denoiser_prepare_kernels(idb_handle* h);
+void idb_sampler_drop_graphs(idb_handle* h);
 
 extern "C" int idb_version(void) { return 100; }
 
@@ -31,6 +32,7 @@ extern "C" int idb_create(idb_handle** out) {
 }
 
 extern "C" int idb_destroy(idb_handle* h) {
+    IDB_ENTER(h);
     if (!h) return IDB_OK;
     idb_sampler_release(h);
     idb_denoiser_release(h);
@@ -45,15 +47,17 @@ extern "C" int idb_destroy(idb_handle* h) {
 extern "C" const char* idb_last_error(const idb_handle* h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" long long idb_launch_count(const idb_handle* h) { return h ? h->launches : 0; }
 extern "C" int idb_set_gemm_backend(idb_handle* h, int backend) {
+    IDB_ENTER(h);
     if (!h || backend < 0 || backend > 1) return IDB_ERR_ARG;
     h->gemm_backend = backend;
+    idb_sampler_drop_graphs(h);      // the captured step graphs contain the other backend's kernels
     return IDB_OK;
 }
 
 // Programmatic dependent launch between the kernels of a step (default on).  Changing it drops the
 // captured step graphs so the next idb_p_sample_loop re-captures with the new launch attributes.
-void idb_sampler_drop_graphs(idb_handle* h);
 extern "C" int idb_set_dependent_launch(idb_handle* h, int on) {
+    IDB_ENTER(h);
     if (!h) return IDB_ERR_ARG;
     h->pdl = on ? 1 : 0;
     idb_sampler_drop_graphs(h);
@@ -61,12 +65,15 @@ extern "C" int idb_set_dependent_launch(idb_handle* h, int on) {
 }
 
 extern "C" int idb_set_nn_pruning(idb_handle* h, int on) {
+    IDB_ENTER(h);
     if (!h) return IDB_ERR_ARG;
     h->nn_pruning = on ? 1 : 0;
+    idb_sampler_drop_graphs(h);
     return IDB_OK;
 }
 extern "C" double idb_debug_last_ms(const idb_handle* h) { return h ? h->last_ms : 0.0; }
 extern "C" int idb_set_fused_mlp(idb_handle* h, int on) {
+    IDB_ENTER(h);
     if (!h) return IDB_ERR_ARG;
     h->fused_mlp = on < 0 ? 0 : (on > 2 ? 2 : on);   /* 0 = two GEMMs, 1 = cluster kernel, 2 = cluster kernel + the layer's final norm */
     idb_sampler_drop_graphs(h);
@@ -79,6 +86,7 @@ extern long long* g_idb_gemm_trace;
 extern "C" int idb_debug_mlp(idb_handle* h, const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                              const float* res, float* out, int M, int iters, long long* trace, const float* ln_w, const float* ln_b,
                              void* stream) {
+    IDB_ENTER(h);
     if (!h || !x || !w1 || !b1 || !w2 || !b2 || !res || !out || M <= 0) return IDB_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int Dm = 256, F = 1024;
@@ -106,6 +114,7 @@ extern "C" int idb_debug_mlp(idb_handle* h, const float* x, const float* w1, con
 
 extern "C" int idb_debug_gemm(idb_handle* h, const float* A, const float* W, const float* bias, const float* res, float* C,
                               int M, int N, int K, int epi, void* stream) {
+    IDB_ENTER(h);
     if (!h || !A || !W || !C) return IDB_ERR_ARG;
     if (epi & 128) {   /* test hook: split-K = 2 onto a C zeroed here */
         cudaStream_t st = (cudaStream_t)stream;
@@ -121,6 +130,7 @@ extern "C" int idb_debug_gemm(idb_handle* h, const float* A, const float* W, con
 /* same GEMM launched `iters` times back to back from C (keeps host overhead per launch small) */
 extern "C" int idb_debug_gemm_repeat(idb_handle* h, const float* A, const float* W, const float* bias, const float* res, float* C,
                                      int M, int N, int K, int epi, int iters, void* stream) {
+    IDB_ENTER(h);
     if (!h || !A || !W || !C) return IDB_ERR_ARG;
     for (int i = 0; i < iters; i++) {
         int rc = idb_gemm(h, A, K, W, K, bias, res, N, C, N, M, N, K, epi, (cudaStream_t)stream);
@@ -133,6 +143,7 @@ extern long long* g_idb_gemm_trace;
 static int g_idb_trace_epi = 0;
 /* one GEMM launch with a per-CTA clock64 timeline written to trace[ctas][16] (device) */
 extern "C" int idb_debug_gemm_trace(idb_handle* h, const float* A, const float* W, float* C, int M, int N, int K, long long* trace, void* stream) {
+    IDB_ENTER(h);
     if (!h || !A || !W || !C || !trace) return IDB_ERR_ARG;
     g_idb_gemm_trace = trace;
     return idb_gemm(h, A, K, W, K, nullptr, nullptr, N, C, N, M, N, K, g_idb_trace_epi, (cudaStream_t)stream);
@@ -148,6 +159,7 @@ extern "C" int idb_debug_set_gemm_accumulators(int n) {
 
 /* x[rows][cols] -> fp16 (hi, lo) pairs with row stride ld_dst (device pointers) */
 extern "C" int idb_debug_split(idb_handle* h, const float* x, void* hi, void* lo, int rows, int cols, int ld_dst, void* stream) {
+    IDB_ENTER(h);
     if (!h || !x || !hi || !lo || rows <= 0 || cols <= 0 || ld_dst < cols) return IDB_ERR_ARG;
     return idb_split_tensor(h, x, cols, (__half*)hi, (__half*)lo, ld_dst, rows, cols, (cudaStream_t)stream);
 }
@@ -155,6 +167,7 @@ extern "C" int idb_debug_split(idb_handle* h, const float* x, void* hi, void* lo
 extern "C" int idb_debug_gemm_presplit(idb_handle* h, const void* A_hi, const void* A_lo, const void* W_hi, const void* W_lo,
                                        const float* bias, float* C, int M, int N, int K, int epi, int iters, long long* trace,
                                        void* stream) {
+    IDB_ENTER(h);
     if (!h || !A_hi || !A_lo || !W_hi || !W_lo || !C) return IDB_ERR_ARG;
     GemmArgs g;
     g.A_hi = (const __half*)A_hi; g.A_lo = (const __half*)A_lo; g.lda = K; g.W_hi = (const __half*)W_hi; g.W_lo = (const __half*)W_lo; g.ldw = K;

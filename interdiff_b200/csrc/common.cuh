@@ -106,6 +106,7 @@ struct Sampler;       // sampler.cu
 struct idb_handle {
     std::string err;
     int device = 0, sm_count = 148;
+    long long epoch = 0;      // bumped whenever a buffer / table / launch attribute that captured graphs reference changes
     long long launches = 0;   // kernels launched through this handle (bench's gpu_launches)
     int gemm_backend = 1;     // 0 = fp32 SIMT (debug / bisect), 1 = tcgen05 split-fp16 (default)
     int pdl = 1;              // programmatic dependent launch between the kernels of a sampling step
@@ -123,6 +124,21 @@ struct idb_handle {
 };
 
 int idb_fail(idb_handle* h, int code, const char* fmt, ...);
+
+// Every C-ABI entry point runs on the handle's device whatever device is current in the calling thread
+// (one handle per device; the veneer keeps one Engine per device) and restores the caller's device on exit.
+struct IdbDeviceGuard {
+    int prev = -1;
+    explicit IdbDeviceGuard(const idb_handle* h) {
+        if (!h) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != h->device) { prev = cur; cudaSetDevice(h->device); }
+    }
+    ~IdbDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    IdbDeviceGuard(const IdbDeviceGuard&) = delete;
+    IdbDeviceGuard& operator=(const IdbDeviceGuard&) = delete;
+};
+#define IDB_ENTER(h) IdbDeviceGuard _idb_device_guard(h)
 
 #define CUDA_TRY(h, expr)                                                                   \
     do {                                                                                    \

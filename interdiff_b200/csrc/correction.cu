@@ -358,6 +358,7 @@ __global__ void k_blend(float* x, const float* __restrict__ proj, const unsigned
 // ---------------------------------------------------------------------------------------------
 void idb_projector_release(idb_handle* h) {
     if (!h->proj) return;
+    h->epoch++;
     Projector& p = *h->proj;
     for (auto& kv : p.raw) cudaFree(kv.second.p);
     for (void* q : p.owned) cudaFree(q);
@@ -369,6 +370,7 @@ void idb_projector_release(idb_handle* h) {
 }
 
 extern "C" int idb_projector_init(idb_handle* h, int past_len, int future_len, int n_pre, int n_markers) {
+    IDB_ENTER(h);
     if (!h) return IDB_ERR_ARG;
     if (n_pre != NQ) return idb_fail(h, IDB_ERR_ARG, "n_pre (dct) must be 10");
     if (n_markers + 1 > MAXP || n_markers < 1) return idb_fail(h, IDB_ERR_ARG, "n_markers must be in 1..67");
@@ -381,6 +383,7 @@ extern "C" int idb_projector_init(idb_handle* h, int past_len, int future_len, i
 }
 
 extern "C" int idb_projector_load(idb_handle* h, const char* name, const float* data, const int64_t* shape, int ndim) {
+    IDB_ENTER(h);
     if (!h || !name || !data) return IDB_ERR_ARG;
     if (!h->proj) return idb_fail(h, IDB_ERR_STATE, "idb_projector_init first");
     std::string s(name);
@@ -398,6 +401,7 @@ extern "C" int idb_projector_load(idb_handle* h, const char* name, const float* 
 }
 
 extern "C" int idb_projector_commit(idb_handle* h) {
+    IDB_ENTER(h);
     if (!h || !h->proj) return idb_fail(h, IDB_ERR_STATE, "idb_projector_init first");
     Projector& p = *h->proj;
     for (void* q : p.owned) cudaFree(q);
@@ -478,6 +482,7 @@ static int projector_run(idb_handle* h, int T, int B, const float* ang, const fl
     if (!p.committed) return idb_fail(h, IDB_ERR_STATE, "idb_projector_commit first");
     if (T != p.T) return idb_fail(h, IDB_ERR_ARG, "T must equal past_len + future_len of the projector (%d)", p.T);
     if (B > p.capB) {
+        h->epoch++;
         if (p.resid) cudaFree(p.resid);
         CUDA_TRY(h, cudaMalloc((void**)&p.resid, sizeof(float) * (size_t)B * 9 * NQ * (p.P + 1)));
         p.capB = B;
@@ -489,17 +494,20 @@ static int projector_run(idb_handle* h, int T, int B, const float* ang, const fl
 }
 
 extern "C" int idb_projector_set_hand_markers(idb_handle* h, const int32_t* ids, int n) {
+    IDB_ENTER(h);
     if (!h || !ids || n < 0 || n > 64) return IDB_ERR_ARG;
     if (!h->proj) return idb_fail(h, IDB_ERR_STATE, "idb_projector_init first");
     Projector& p = *h->proj;
     if (!p.hand_ids) CUDA_TRY(h, cudaMalloc((void**)&p.hand_ids, 64 * sizeof(int32_t)));
     CUDA_TRY(h, cudaMemcpy(p.hand_ids, ids, (size_t)n * 4, cudaMemcpyDefault));
+    if (p.n_hand != n) h->epoch++;
     p.n_hand = n;
     return IDB_OK;
 }
 
 extern "C" int idb_projector_sample(idb_handle* h, int T, int B, const float* obj_angles, const float* obj_trans,
                                     const float* markers, const int32_t* contact, float* out, void* stream) {
+    IDB_ENTER(h);
     if (!h || !obj_angles || !obj_trans || !markers || !contact || !out) return IDB_ERR_ARG;
     if (!h->proj) return idb_fail(h, IDB_ERR_STATE, "idb_projector_init first");
     if (!h->proj->hand_ids) return idb_fail(h, IDB_ERR_STATE, "idb_projector_set_hand_markers first");
@@ -509,6 +517,7 @@ extern "C" int idb_projector_sample(idb_handle* h, int T, int B, const float* ob
 extern "C" int idb_correction_bind(idb_handle* h, int B, int T, int past_len, int n_obj_points, const float* hand_pose,
                                    const float* betas, const float* obj_points, const int32_t* marker_ids,
                                    const int32_t* hand_marker_ids, int n_hand, void* stream) {
+    IDB_ENTER(h);
     if (!h || !hand_pose || !betas || !obj_points || !marker_ids || !hand_marker_ids) return IDB_ERR_ARG;
     if (!h->proj) return idb_fail(h, IDB_ERR_STATE, "idb_projector_init first");
     if (!h->body) return idb_fail(h, IDB_ERR_STATE, "idb_body_init first");
@@ -518,6 +527,7 @@ extern "C" int idb_correction_bind(idb_handle* h, int B, int T, int past_len, in
     cudaStream_t st = (cudaStream_t)stream;
     const int F = T * B, P = p.P, V = m.V;
     if (B != p.B || T != p.cT || n_obj_points != p.n_obj) {
+        h->epoch++;
         for (void* q : p.ctx_owned) cudaFree(q);
         p.ctx_owned.clear();
         auto A = [&](void** ptr, size_t bytes) {
@@ -537,12 +547,30 @@ extern "C" int idb_correction_bind(idb_handle* h, int B, int T, int past_len, in
         CUDA_TRY(h, A((void**)&p.gt_tr, (size_t)F * 3 * 4)); CUDA_TRY(h, A((void**)&p.proj_out, (size_t)F * 9 * 4));
         p.B = B; p.cT = T; p.n_obj = n_obj_points;
     }
+    if (p.cpast != past_len) h->epoch++;   // kernel parameter of the captured correction steps
     p.cpast = past_len;
     { int rc = idb_projector_set_hand_markers(h, hand_marker_ids, n_hand); if (rc) return rc; }
     CUDA_TRY(h, cudaMemcpyAsync(p.hand_pose, hand_pose, (size_t)F * 90 * 4, cudaMemcpyDefault, st));
     CUDA_TRY(h, cudaMemcpyAsync(p.betas, betas, (size_t)F * 10 * 4, cudaMemcpyDefault, st));
     CUDA_TRY(h, cudaMemcpyAsync(p.obj_points, obj_points, (size_t)B * n_obj_points * 3 * 4, cudaMemcpyDefault, st));
     CUDA_TRY(h, cudaMemcpyAsync(p.marker_ids, marker_ids, (size_t)P * 4, cudaMemcpyDefault, st));
+    return IDB_OK;
+}
+
+// Grows every workspace a correction step needs BEFORE a stream capture starts (no allocation may happen inside one).
+int idb_correction_prepare(idb_handle* h, int B, int T) {
+    if (!h->proj || !h->proj->B) return idb_fail(h, IDB_ERR_STATE, "idb_correction_bind first");
+    if (!h->body) return idb_fail(h, IDB_ERR_STATE, "idb_body_init first");
+    Projector& p = *h->proj;
+    if (p.B != B || p.cT != T) return idb_fail(h, IDB_ERR_STATE, "correction bound for B=%d, T=%d but the denoiser for B=%d, T=%d", p.B, p.cT, B, T);
+    int rc = idb_body_workspace(h, p.cT * p.B);
+    if (rc) return rc;
+    if (p.B > p.capB) {
+        h->epoch++;
+        if (p.resid) cudaFree(p.resid);
+        CUDA_TRY(h, cudaMalloc((void**)&p.resid, sizeof(float) * (size_t)p.B * 9 * NQ * (p.P + 1)));
+        p.capB = p.B;
+    }
     return IDB_OK;
 }
 
@@ -576,6 +604,7 @@ int idb_correction_apply_dev(idb_handle* h, float* x0, const float* gt, int t, c
 
 extern "C" int idb_correction_apply(idb_handle* h, float* x0, const float* gt, int t, uint8_t* condition_out,
                                     int32_t* contact_out, float* markers_out, float* o2h_out, void* stream) {
+    IDB_ENTER(h);
     if (!h || !x0 || !gt) return IDB_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = idb_correction_apply_dev(h, x0, gt, t, st);

@@ -826,7 +826,12 @@ __global__ void __launch_bounds__(256) k_step_io(const StepIO a) {
         __syncthreads();
     }
     const float* nz = nullptr;
-    if (MODE & 2) nz = a.tape_mode ? a.noise + (size_t)(a.n_steps - i_step) * ((size_t)gridDim.x * a.C * T) : a.noise;
+    if (MODE & 2) {
+        // tape_mode 0: `noise` is this step's eps; 1: `noise` is the tape (n_steps + 1 entries, [0] = x_T); 2: `noise` is a
+        // device slot holding the tape pointer (captured graphs stay valid when the caller passes a new tape tensor)
+        const float* base = a.tape_mode == 2 ? *reinterpret_cast<const float* const*>(a.noise) : a.noise;
+        nz = a.tape_mode ? base + (size_t)(a.n_steps - i_step) * ((size_t)gridDim.x * a.C * T) : base;
+    }
     constexpr int KM = 5;
     for (int base = 0; base < n; base += 256 * KM) {
         float v_in[KM], v_xt[KM], v_nz[KM], v_gt[KM];
@@ -953,9 +958,11 @@ static void denoiser_free_bound(Denoiser& d) {
     if (d.step_cur) { cudaFree(d.step_cur); d.step_cur = nullptr; d.ticket = nullptr; }
     d.B = d.T = d.M = 0;
 }
+void idb_sampler_drop_graphs(idb_handle* h);
 
 void idb_denoiser_release(idb_handle* h) {
     Denoiser& d = h->den;
+    idb_sampler_drop_graphs(h);      // captured step graphs hold the weight / workspace pointers freed below
     idb_pointnet_release(h);
     denoiser_free_bound(d);
     for (auto& kv : d.raw) cudaFree(kv.second.p);
@@ -971,6 +978,7 @@ void idb_denoiser_release(idb_handle* h) {
 }
 
 extern "C" int idb_denoiser_init(idb_handle* h, const idb_denoiser_config* cfg) {
+    IDB_ENTER(h);
     if (!h || !cfg) return IDB_ERR_ARG;
     if (cfg->d_model != D) return idb_fail(h, IDB_ERR_ARG, "d_model must be 256 (got %d)", cfg->d_model);
     if (cfg->n_heads * 64 != cfg->d_model) return idb_fail(h, IDB_ERR_ARG, "head_dim must be 64");
@@ -985,6 +993,7 @@ extern "C" int idb_denoiser_init(idb_handle* h, const idb_denoiser_config* cfg) 
 }
 
 extern "C" int idb_denoiser_load(idb_handle* h, const char* name, const float* data, const int64_t* shape, int ndim) {
+    IDB_ENTER(h);
     if (!h || !name || !data) return IDB_ERR_ARG;
     Denoiser& d = h->den;
     if (!d.configured) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_init first");
@@ -1036,9 +1045,11 @@ struct Packer {
 }  // namespace
 
 extern "C" int idb_denoiser_commit(idb_handle* h) {
+    IDB_ENTER(h);
     if (!h) return IDB_ERR_ARG;
     Denoiser& d = h->den;
     if (!d.configured) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_init first");
+    idb_sampler_drop_graphs(h);      // packed weights are (re)built below
     for (float* p : d.owned) cudaFree(p);
     d.owned.clear();
     d.layers.clear();
@@ -1238,6 +1249,7 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
 }
 
 extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const float* cond, const float* zero_pose_obj, void* stream) {
+    IDB_ENTER(h);
     if (!h || !cond || B <= 0 || T <= 0 || Tm <= 0) return IDB_ERR_ARG;
     Denoiser& d = h->den;
     if (!d.committed) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_commit first");
@@ -1250,6 +1262,7 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
     const int Clin = c.c_body + (c.variant == 0 ? c.c_obj : 7);
     const int npts = c.n_points > 0 ? c.n_points : 1;
     if (B != d.B || T != d.T || Tm != d.Tm) {
+        idb_sampler_drop_graphs(h);  // the workspaces below are baked into the captured graphs
         denoiser_free_bound(d);
         auto A = [&](float** p, size_t n) { int rc = idb_dev_alloc(h, p, n); if (!rc) d.bound.push_back(*p); return rc; };
         int rc = 0;
@@ -1539,6 +1552,7 @@ __global__ void k_ln_seq_first(const float* __restrict__ a, const float* __restr
 
 extern "C" int idb_encode_condition(idb_handle* h, int B, int Tp, const float* past, const float* pc_embedding, float* cond_out,
                                     void* stream) {
+    IDB_ENTER(h);
     if (!h || !past || !pc_embedding || !cond_out || B <= 0 || Tp <= 0) return IDB_ERR_ARG;
     Denoiser& d = h->den;
     if (!d.committed) return idb_fail(h, IDB_ERR_STATE, "idb_denoiser_commit first");
@@ -1618,6 +1632,7 @@ extern "C" int idb_encode_condition(idb_handle* h, int B, int Tp, const float* p
 }
 
 extern "C" int idb_denoiser_forward(idb_handle* h, const float* x, const int64_t* timesteps, float* out, void* stream) {
+    IDB_ENTER(h);
     if (!h || !x || !timesteps || !out) return IDB_ERR_ARG;
     return idb_denoiser_run(h, x, (const long long*)timesteps, nullptr, nullptr, out, (cudaStream_t)stream);
 }

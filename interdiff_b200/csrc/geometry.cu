@@ -228,6 +228,7 @@ __global__ void k_rot6d_to_aa(const float* __restrict__ d6, float* __restrict__ 
 }  // namespace
 
 extern "C" int idb_vertex_normals(idb_handle* h, int F, const float* verts, float* normals, void* stream) {
+    IDB_ENTER(h);
     if (!h || !verts || !normals || F <= 0) return IDB_ERR_ARG;
     if (!h->body || !h->body->faces) return idb_fail(h, IDB_ERR_STATE, "idb_body_init with faces first");
     BodyModel& m = *h->body;
@@ -239,6 +240,7 @@ extern "C" int idb_vertex_normals(idb_handle* h, int F, const float* verts, floa
 
 extern "C" int idb_signed_nn(idb_handle* h, int F, int Pq, int Pt, const float* query, const float* target,
                              const float* target_normals, float* signed_dist, int32_t* idx, float* vec, void* stream) {
+    IDB_ENTER(h);
     if (!h || !query || !target || F <= 0 || Pq <= 0 || Pt <= 0) return IDB_ERR_ARG;
     // body-mesh targets take the cluster-pruned search (identical results, ~8x fewer candidate evaluations)
     if (h->nn_pruning && h->body && h->body->nn_vid && Pt == h->body->V && Pt <= 12000) {
@@ -262,6 +264,7 @@ extern "C" int idb_signed_nn(idb_handle* h, int F, int Pq, int Pt, const float* 
 }
 
 extern "C" int idb_rot6d_to_axis_angle(idb_handle* h, int n, const float* rot6d, float* aa, void* stream) {
+    IDB_ENTER(h);
     if (!h || !rot6d || !aa || n <= 0) return IDB_ERR_ARG;
     k_rot6d_to_aa<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rot6d, aa, n);
     LAUNCH_CHECK(h);

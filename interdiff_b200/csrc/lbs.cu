@@ -178,6 +178,7 @@ k_lbs_skin(const float* __restrict__ posedirsT, const float* __restrict__ shaped
 
 void idb_body_release(idb_handle* h) {
     if (!h->body) return;
+    h->epoch++;
     BodyModel& m = *h->body;
     for (void* p : m.owned) cudaFree(p);
     if (m.A) { cudaFree(m.A); cudaFree(m.pose_map); }
@@ -188,6 +189,7 @@ void idb_body_release(idb_handle* h) {
 extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const float* v_template, const float* shapedirs,
                              const float* posedirs, const float* J_regressor, const float* weights,
                              const int32_t* parents, const int32_t* faces) {
+    IDB_ENTER(h);
     if (!h || !v_template || !shapedirs || !posedirs || !J_regressor || !weights || !parents) return IDB_ERR_ARG;
     if (V <= 0 || J <= 1 || J > 64 || NB <= 0 || NB > 16) return idb_fail(h, IDB_ERR_ARG, "bad body model dimensions");
     idb_body_release(h);
@@ -301,6 +303,7 @@ extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const 
 int idb_body_workspace(idb_handle* h, int F) {
     BodyModel& m = *h->body;
     if (F <= m.capF) return IDB_OK;
+    h->epoch++;                      // captured loop graphs point at the old workspace
     if (m.A) { cudaFree(m.A); cudaFree(m.pose_map); }
     CUDA_TRY(h, cudaMalloc((void**)&m.A, sizeof(float) * (size_t)F * m.J * 12));
     CUDA_TRY(h, cudaMalloc((void**)&m.pose_map, sizeof(float) * (size_t)F * m.Kp));
@@ -310,6 +313,7 @@ int idb_body_workspace(idb_handle* h, int F) {
 
 extern "C" int idb_smplh_lbs(idb_handle* h, int F, const float* pose, const float* betas, const float* trans,
                              float* verts, float* jtr, void* stream) {
+    IDB_ENTER(h);
     if (!h || !pose || !betas || !trans || F <= 0) return IDB_ERR_ARG;
     if (!h->body) return idb_fail(h, IDB_ERR_STATE, "idb_body_init first");
     BodyModel& m = *h->body;

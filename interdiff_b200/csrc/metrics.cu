@@ -101,6 +101,7 @@ k_metric_reduce(const float* __restrict__ obj_pred, const float* __restrict__ jt
 extern "C" int idb_metrics(idb_handle* h, int T, int B, int J, int P, int Db, const float* obj_pred, const float* body_jtr,
                            const float* body, const float* obj_gt, const float* body_jtr_gt, const float* body_gt, const float* verts,
                            const float* obj_points, float* out, void* stream) {
+    IDB_ENTER(h);
     if (!h || !obj_pred || !body_jtr || !body || !obj_gt || !body_jtr_gt || !body_gt || !verts || !obj_points || !out) return IDB_ERR_ARG;
     if (T <= 0 || B <= 0 || J <= 0 || P <= 0 || Db < 3) return IDB_ERR_ARG;
     if (!h->body || !h->body->faces) return idb_fail(h, IDB_ERR_STATE, "idb_body_init with faces first");

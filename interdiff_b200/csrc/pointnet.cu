@@ -302,6 +302,7 @@ int idb_pointnet_commit(idb_handle* h) {
 }
 
 extern "C" int idb_pointcloud_embed(idb_handle* h, int B, int P, const float* obj_points, float* pc_embedding, void* stream) {
+    IDB_ENTER(h);
     if (!h || !obj_points || !pc_embedding || B <= 0 || P <= 0) return IDB_ERR_ARG;
     Denoiser& d = h->den;
     if (!d.committed || !d.pn_ready) return idb_fail(h, IDB_ERR_STATE, "the point-cloud encoder's weights (pcEmbedding.*) were not loaded / committed");

@@ -17,24 +17,40 @@ int idb_step_finish(idb_handle* h, const float* x0, const float* xt, const float
 int idb_step_tail(idb_handle* h, const float* gt, const unsigned char* mask, float* x0_out, const float* xt, const float* noise,
                   int tape_mode, float* x_next, int emit_next, cudaStream_t st);
 int idb_correction_apply_dev(idb_handle* h, float* x0, const float* gt, int t, cudaStream_t st);
+int idb_correction_prepare(idb_handle* h, int B, int T);
 
 struct Sampler {
-    float *x_a = nullptr, *x_b = nullptr, *x0 = nullptr;
+    float *x_a = nullptr, *x0 = nullptr;
     size_t numel = 0;
+    // graph-stable copies of the caller's inpainting tensors and a device slot holding the caller's tape pointer:
+    // the captured graphs only reference buffers owned by the handle, so a new tape / gt / mask tensor per call
+    // does not force a re-capture
+    float* gt_buf = nullptr; unsigned char* mask_buf = nullptr; const float** tape_slot = nullptr;
     cudaGraphExec_t step_graph = nullptr;     // predict + finish for a plain step
     cudaGraphExec_t predict_graph = nullptr;  // predict only (correction steps)
-    const float* g_gt = nullptr; const unsigned char* g_mask = nullptr; const float* g_tape = nullptr;
-    int gB = 0, gT = 0;
-    int launches_per_step = 0, launches_per_predict = 0;
+    cudaGraphExec_t loop_graph = nullptr;     // the whole loop (use_graph == 2)
+    // what the cached graphs were captured for; `epoch` = idb_handle::epoch at capture (bumped by every call that
+    // frees / reallocates / re-routes anything a captured node points at)
+    int gB = 0, gT = 0, g_mask = -1; long long g_epoch = -1;
+    int lB = 0, lT = 0, l_mask = -1, l_n = 0, l_corr = -1; long long l_epoch = -1;
+    int launches_per_step = 0, launches_per_predict = 0; long long launches_per_loop = 0;
 };
 
 namespace {
 
 __global__ void k_set_counter(int* counter, int v) { *counter = v; }
+__global__ void k_loop_begin(int* counter, int v, const float** slot, const float* tape) { *counter = v; *slot = tape; }
+
+void drop_graphs(Sampler& s) {
+    if (s.step_graph) { cudaGraphExecDestroy(s.step_graph); s.step_graph = nullptr; }
+    if (s.predict_graph) { cudaGraphExecDestroy(s.predict_graph); s.predict_graph = nullptr; }
+    if (s.loop_graph) { cudaGraphExecDestroy(s.loop_graph); s.loop_graph = nullptr; }
+}
 
 }  // namespace
 
 extern "C" int idb_diffusion_init(idb_handle* h, const double* betas, const int64_t* timestep_map, int n) {
+    IDB_ENTER(h);
     if (!h || !betas || n <= 0) return IDB_ERR_ARG;
     Diffusion& df = h->diff;
     // float64 tables exactly as GaussianDiffusion.__init__ (gaussian_diffusion.py:160-197)
@@ -67,11 +83,8 @@ extern "C" int idb_diffusion_init(idb_handle* h, const double* betas, const int6
     CUDA_TRY(h, cudaMalloc((void**)&df.tbl, sizeof(StepParams) * n));
     CUDA_TRY(h, cudaMemcpy(df.tbl, df.host.data(), sizeof(StepParams) * n, cudaMemcpyHostToDevice));
     df.n = n;
-    if (h->sampler) {
-        if (h->sampler->step_graph) cudaGraphExecDestroy(h->sampler->step_graph);
-        if (h->sampler->predict_graph) cudaGraphExecDestroy(h->sampler->predict_graph);
-        h->sampler->step_graph = h->sampler->predict_graph = nullptr;
-    }
+    h->epoch++;   // the table was reallocated: captured graphs point at the old one
+    if (h->sampler) drop_graphs(*h->sampler);
     return IDB_OK;
 }
 
@@ -81,13 +94,14 @@ static int sampler_ready(idb_handle* h, size_t numel) {
     if (!h->sampler) h->sampler = new Sampler();
     Sampler& s = *h->sampler;
     if (s.numel != numel) {
-        if (s.x_a) { cudaFree(s.x_a); cudaFree(s.x_b); cudaFree(s.x0); }
+        drop_graphs(s);
+        if (s.x_a) { cudaFree(s.x_a); cudaFree(s.x0); cudaFree(s.gt_buf); cudaFree(s.mask_buf); s.x_a = nullptr; }
         CUDA_TRY(h, cudaMalloc((void**)&s.x_a, numel * sizeof(float)));
-        CUDA_TRY(h, cudaMalloc((void**)&s.x_b, numel * sizeof(float)));
         CUDA_TRY(h, cudaMalloc((void**)&s.x0, numel * sizeof(float)));
+        CUDA_TRY(h, cudaMalloc((void**)&s.gt_buf, numel * sizeof(float)));
+        CUDA_TRY(h, cudaMalloc((void**)&s.mask_buf, numel));
+        if (!s.tape_slot) CUDA_TRY(h, cudaMalloc((void**)&s.tape_slot, sizeof(float*)));
         s.numel = numel;
-        if (s.step_graph) { cudaGraphExecDestroy(s.step_graph); s.step_graph = nullptr; }
-        if (s.predict_graph) { cudaGraphExecDestroy(s.predict_graph); s.predict_graph = nullptr; }
     }
     return IDB_OK;
 }
@@ -113,6 +127,7 @@ static int set_step(idb_handle* h, int i, cudaStream_t st) {
 }
 
 extern "C" int idb_p_sample_predict(idb_handle* h, int i, const float* x_t, const float* gt, const uint8_t* mask, float* x0_out, void* stream) {
+    IDB_ENTER(h);
     if (!h || !x_t || !x0_out) return IDB_ERR_ARG;
     if (i < 0 || i >= h->diff.n) return idb_fail(h, IDB_ERR_ARG, "step index out of range");
     if ((gt == nullptr) != (mask == nullptr)) return idb_fail(h, IDB_ERR_ARG, "gt and mask must be given together");
@@ -123,6 +138,7 @@ extern "C" int idb_p_sample_predict(idb_handle* h, int i, const float* x_t, cons
 }
 
 extern "C" int idb_p_sample_finish(idb_handle* h, int i, const float* x0, const float* x_t, const float* noise, float* x_out, void* stream) {
+    IDB_ENTER(h);
     if (!h || !x0 || !x_t || !noise || !x_out) return IDB_ERR_ARG;
     if (i < 0 || i >= h->diff.n) return idb_fail(h, IDB_ERR_ARG, "step index out of range");
     cudaStream_t st = (cudaStream_t)stream;
@@ -133,6 +149,7 @@ extern "C" int idb_p_sample_finish(idb_handle* h, int i, const float* x0, const 
 
 extern "C" int idb_p_sample(idb_handle* h, int i, const float* x_t, const float* noise, const float* gt, const uint8_t* mask,
                             float* x_out, float* x0_out, void* stream) {
+    IDB_ENTER(h);
     if (!h || !x_t || !noise || !x_out) return IDB_ERR_ARG;
     if (i < 0 || i >= h->diff.n) return idb_fail(h, IDB_ERR_ARG, "step index out of range");
     if ((gt == nullptr) != (mask == nullptr)) return idb_fail(h, IDB_ERR_ARG, "gt and mask must be given together");
@@ -144,79 +161,123 @@ extern "C" int idb_p_sample(idb_handle* h, int i, const float* x_t, const float*
     return idb_step_tail(h, gt, mask, x0_out, x_t, noise, 0, x_out, 0, st);
 }
 
+// One plain step / one correction step on the sampler's own buffers (x in place in s.x_a; gt / mask = the
+// graph-stable copies; noise through the tape slot).
+static int plain_step(idb_handle* h, Sampler& s, const float* gt, const unsigned char* mask, cudaStream_t st) {
+    int rc = idb_denoiser_body(h, st);
+    if (rc) return rc;
+    return idb_step_tail(h, gt, mask, nullptr, s.x_a, reinterpret_cast<const float*>(s.tape_slot), 2, s.x_a, 1, st);
+}
+static int predict_part(idb_handle* h, Sampler& s, const float* gt, const unsigned char* mask, cudaStream_t st) {
+    int rc = idb_denoiser_body(h, st);
+    if (rc) return rc;
+    return idb_denoiser_heads(h, gt, mask, s.x0, st);
+}
+// reference order inside p_mean_variance (gaussian_diffusion.py:305-376): model -> inpaint blend -> denoised_fn ->
+// posterior; there is NO re-inpainting after the hook.  The hook receives the UN-mapped step index i (:356).
+static int correction_tail(idb_handle* h, Sampler& s, const float* gt, int i, cudaStream_t st) {
+    int rc = idb_correction_apply_dev(h, s.x0, gt, i, st);
+    if (rc) return rc;
+    return idb_step_finish(h, s.x0, s.x_a, reinterpret_cast<const float*>(s.tape_slot), 2, s.x_a, 1, st);
+}
+static inline bool correction_gate(int correction, int i) { return correction && i <= 500 && (i % 50 == 0); }   // eval_smpl_short.py:86-88
+
+template <typename Body>
+static int capture_graph(idb_handle* h, cudaGraphExec_t* out, long long* n_launches, Body&& body) {
+    cudaStream_t cs;
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    const long long saved = h->launches;
+    cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) { cudaStreamDestroy(cs); return idb_fail(h, IDB_ERR_CUDA, "graph capture failed to start: %s", cudaGetErrorString(ce)); }
+    int rc = body(cs);
+    ce = cudaStreamEndCapture(cs, &g);
+    *n_launches = h->launches - saved;
+    h->launches = saved;
+    if (rc || ce != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        cudaStreamDestroy(cs);
+        return rc ? rc : idb_fail(h, IDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    }
+    ce = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    cudaStreamDestroy(cs);
+    if (ce != cudaSuccess) return idb_fail(h, IDB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    return IDB_OK;
+}
+
+// use_graph: 0 = plain launches, 1 = one captured graph per step (replayed n times), 2 = the whole loop as one graph.
 extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* gt, const uint8_t* mask, int correction,
                                  int use_graph, float* x_out, void* stream) {
+    IDB_ENTER(h);
     if (!h || !tape || !x_out) return IDB_ERR_ARG;
     if ((gt == nullptr) != (mask == nullptr)) return idb_fail(h, IDB_ERR_ARG, "gt and mask must be given together");
+    if (correction && !gt) return idb_fail(h, IDB_ERR_ARG, "the correction hook reads the inpainted ground truth (eval_smpl_short.py:113): gt required");
     const size_t numel = sample_numel(h);
     int rc = sampler_ready(h, numel);
     if (rc) return rc;
     Sampler& s = *h->sampler;
     Diffusion& df = h->diff;
     cudaStream_t st = (cudaStream_t)stream;
-    const int n = df.n;
-    // The per-step graphs read x from s.x_a and write s.x_b, then the roles swap: capture two
-    // parities instead (a -> b, b -> a) by capturing ONE graph that does a full a -> b -> a pair?
-    // Simpler and just as cheap: the graph always reads x_a and writes x_a (x0 is a separate
-    // buffer, and the posterior is elementwise, so in-place is safe).
+    const int n = df.n, has_mask = gt ? 1 : 0;
+    if (correction && (rc = idb_correction_prepare(h, h->den.B, h->den.T))) return rc;   // workspaces sized before anything is captured
+    const float* g_gt = gt ? s.gt_buf : nullptr;
+    const unsigned char* g_mask = gt ? s.mask_buf : nullptr;
+    // x lives in s.x_a for the whole loop (the posterior is elementwise, so in place is safe; x0 is separate)
     CUDA_TRY(h, cudaMemcpyAsync(s.x_a, tape, numel * sizeof(float), cudaMemcpyDefault, st));
-    if ((rc = set_step(h, n - 1, st))) return rc;
-    // decoder input of the first step; every later step gets its tokens from the previous step's tail
-    if ((rc = idb_denoiser_tokens(h, s.x_a, nullptr, st))) return rc;
+    if (gt) {
+        CUDA_TRY(h, cudaMemcpyAsync(s.gt_buf, gt, numel * sizeof(float), cudaMemcpyDefault, st));
+        CUDA_TRY(h, cudaMemcpyAsync(s.mask_buf, mask, numel, cudaMemcpyDefault, st));
+    }
+    k_loop_begin<<<1, 1, 0, st>>>(h->den.step_cur, n - 1, s.tape_slot, tape);
+    LAUNCH_CHECK(h);
 
-    const bool graph_ok = use_graph != 0;
-    if (graph_ok && (!s.step_graph || s.g_gt != gt || s.g_mask != mask || s.g_tape != tape || s.gB != h->den.B || s.gT != h->den.T)) {
-        if (s.step_graph) { cudaGraphExecDestroy(s.step_graph); s.step_graph = nullptr; }
-        if (s.predict_graph) { cudaGraphExecDestroy(s.predict_graph); s.predict_graph = nullptr; }
-        cudaStream_t cs;
-        CUDA_TRY(h, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-        cudaGraph_t g;
-        // full plain step
-        long long saved = h->launches;
-        CUDA_TRY(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        rc = idb_denoiser_body(h, cs);
-        if (!rc) rc = idb_step_tail(h, gt, mask, nullptr, s.x_a, tape, 1, s.x_a, 1, cs);
-        cudaError_t ce = cudaStreamEndCapture(cs, &g);
-        if (rc || ce != cudaSuccess) { cudaStreamDestroy(cs); return rc ? rc : idb_fail(h, IDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)); }
-        s.launches_per_step = (int)(h->launches - saved);
-        CUDA_TRY(h, cudaGraphInstantiate(&s.step_graph, g, 0));
-        cudaGraphDestroy(g);
-        // predict only
-        CUDA_TRY(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        rc = idb_denoiser_body(h, cs);
-        if (!rc) rc = idb_denoiser_heads(h, gt, mask, s.x0, cs);
-        ce = cudaStreamEndCapture(cs, &g);
-        if (rc || ce != cudaSuccess) { cudaStreamDestroy(cs); return rc ? rc : idb_fail(h, IDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce)); }
-        s.launches_per_predict = s.launches_per_step;
-        CUDA_TRY(h, cudaGraphInstantiate(&s.predict_graph, g, 0));
-        cudaGraphDestroy(g);
-        cudaStreamDestroy(cs);
-        h->launches = saved;
-        s.g_gt = gt; s.g_mask = mask; s.g_tape = tape; s.gB = h->den.B; s.gT = h->den.T;
+    if (use_graph == 2) {
+        if (!s.loop_graph || s.l_epoch != h->epoch || s.lB != h->den.B || s.lT != h->den.T || s.l_mask != has_mask || s.l_n != n ||
+            s.l_corr != (correction ? 1 : 0)) {
+            if (s.loop_graph) { cudaGraphExecDestroy(s.loop_graph); s.loop_graph = nullptr; }
+            rc = capture_graph(h, &s.loop_graph, &s.launches_per_loop, [&](cudaStream_t cs) {
+                int r = idb_denoiser_tokens(h, s.x_a, nullptr, cs);
+                for (int i = n - 1; i >= 0 && !r; i--) {
+                    if (!correction_gate(correction, i)) r = plain_step(h, s, g_gt, g_mask, cs);
+                    else { r = predict_part(h, s, g_gt, g_mask, cs); if (!r) r = correction_tail(h, s, g_gt, i, cs); }
+                }
+                return r;
+            });
+            if (rc) return rc;
+            s.l_epoch = h->epoch; s.lB = h->den.B; s.lT = h->den.T; s.l_mask = has_mask; s.l_n = n; s.l_corr = correction ? 1 : 0;
+        }
+        CUDA_TRY(h, cudaGraphLaunch(s.loop_graph, st));
+        h->launches += s.launches_per_loop;
+        CUDA_TRY(h, cudaMemcpyAsync(x_out, s.x_a, numel * sizeof(float), cudaMemcpyDefault, st));
+        return IDB_OK;
     }
 
+    // decoder input of the first step; every later step gets its tokens from the previous step's tail
+    if ((rc = idb_denoiser_tokens(h, s.x_a, nullptr, st))) return rc;
+    const bool graph_ok = use_graph != 0;
+    if (graph_ok && (!s.step_graph || s.g_epoch != h->epoch || s.gB != h->den.B || s.gT != h->den.T || s.g_mask != has_mask)) {
+        if (s.step_graph) { cudaGraphExecDestroy(s.step_graph); s.step_graph = nullptr; }
+        if (s.predict_graph) { cudaGraphExecDestroy(s.predict_graph); s.predict_graph = nullptr; }
+        long long nl = 0;
+        if ((rc = capture_graph(h, &s.step_graph, &nl, [&](cudaStream_t cs) { return plain_step(h, s, g_gt, g_mask, cs); }))) return rc;
+        s.launches_per_step = (int)nl;
+        if ((rc = capture_graph(h, &s.predict_graph, &nl, [&](cudaStream_t cs) { return predict_part(h, s, g_gt, g_mask, cs); }))) return rc;
+        s.launches_per_predict = (int)nl;
+        s.g_epoch = h->epoch; s.gB = h->den.B; s.gT = h->den.T; s.g_mask = has_mask;
+    }
     for (int i = n - 1; i >= 0; i--) {
-        const long long t = df.host[i].t;  // denoised_fn receives the UN-mapped t (gaussian_diffusion.py:356): i
-        const bool corr = correction && i <= 500 && (i % 50 == 0);
-        (void)t;
-        if (!corr) {
+        if (!correction_gate(correction, i)) {
             if (graph_ok) {
                 CUDA_TRY(h, cudaGraphLaunch(s.step_graph, st));
                 h->launches += s.launches_per_step;
-            } else {
-                if ((rc = idb_denoiser_body(h, st))) return rc;
-                if ((rc = idb_step_tail(h, gt, mask, nullptr, s.x_a, tape, 1, s.x_a, 1, st))) return rc;
-            }
+            } else if ((rc = plain_step(h, s, g_gt, g_mask, st))) return rc;
         } else {
             if (graph_ok) {
                 CUDA_TRY(h, cudaGraphLaunch(s.predict_graph, st));
                 h->launches += s.launches_per_predict;
-            } else {
-                if ((rc = idb_denoiser_body(h, st))) return rc;
-                if ((rc = idb_denoiser_heads(h, gt, mask, s.x0, st))) return rc;
-            }
-            if ((rc = idb_correction_apply_dev(h, s.x0, gt, i, st))) return rc;
-            if ((rc = idb_step_finish(h, s.x0, s.x_a, tape, 1, s.x_a, 1, st))) return rc;
+            } else if ((rc = predict_part(h, s, g_gt, g_mask, st))) return rc;
+            if ((rc = correction_tail(h, s, g_gt, i, st))) return rc;
         }
     }
     CUDA_TRY(h, cudaMemcpyAsync(x_out, s.x_a, numel * sizeof(float), cudaMemcpyDefault, st));
@@ -224,18 +285,16 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
 }
 
 void idb_sampler_drop_graphs(idb_handle* h) {
-    if (!h->sampler) return;
-    Sampler& s = *h->sampler;
-    if (s.step_graph) { cudaGraphExecDestroy(s.step_graph); s.step_graph = nullptr; }
-    if (s.predict_graph) { cudaGraphExecDestroy(s.predict_graph); s.predict_graph = nullptr; }
+    h->epoch++;
+    if (h->sampler) drop_graphs(*h->sampler);
 }
 
 void idb_sampler_release(idb_handle* h) {
     if (h->sampler) {
         Sampler& s = *h->sampler;
-        if (s.step_graph) cudaGraphExecDestroy(s.step_graph);
-        if (s.predict_graph) cudaGraphExecDestroy(s.predict_graph);
-        if (s.x_a) { cudaFree(s.x_a); cudaFree(s.x_b); cudaFree(s.x0); }
+        drop_graphs(s);
+        if (s.x_a) { cudaFree(s.x_a); cudaFree(s.x0); cudaFree(s.gt_buf); cudaFree(s.mask_buf); }
+        if (s.tape_slot) cudaFree(s.tape_slot);
         delete h->sampler;
         h->sampler = nullptr;
     }

@@ -105,15 +105,16 @@ class GaussianDiffusion:
         return t
 
     # ---- engine plumbing
-    def _prepare(self, model, model_kwargs):
-        """Returns (engine, gt, mask): binds cond, makes sure the tables live in the model's engine."""
+    def _prepare(self, model, model_kwargs, T=None):
+        """Returns (engine, gt, mask): binds cond, makes sure the tables live in the model's engine.  T = number of
+        frames of the sample (x.shape[-1] / shape[-1]): the inpainting keys are optional upstream (:307)."""
         if not hasattr(model, "engine_for"):
             raise TypeError("interdiff_b200 diffusion drives interdiff_b200 models only (no eager fallback)")
         y = (model_kwargs or {}).get("y")
         if y is None:
             raise KeyError("model_kwargs['y'] is required (gaussian_diffusion.py:307 dereferences it)")
         eng = model.engine_for(y["cond"].device)
-        model.bind_kwargs(eng, model_kwargs)
+        model.bind_kwargs(eng, model_kwargs, T=T)
         key = (id(eng), self.num_timesteps)
         if getattr(self, "_eng_key", None) != key or eng.n_steps != self.num_timesteps or getattr(eng, "_diff_owner", None) is not self:
             eng.init_diffusion(self.betas, self.timestep_map)
@@ -132,7 +133,7 @@ class GaussianDiffusion:
         return i
 
     def p_mean_variance(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None):
-        eng, gt, mask = self._prepare(model, model_kwargs)
+        eng, gt, mask = self._prepare(model, model_kwargs, T=x.shape[-1])
         i = self._uniform_step(t)
         x0 = eng.p_sample_predict(i, x, gt, mask)
         if denoised_fn is not None:
@@ -145,7 +146,7 @@ class GaussianDiffusion:
     def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, const_noise=False):
         if cond_fn is not None:
             raise NotImplementedError("cond_fn guidance is not on the reference's sampling path")
-        eng, gt, mask = self._prepare(model, model_kwargs)
+        eng, gt, mask = self._prepare(model, model_kwargs, T=x.shape[-1])
         i = self._uniform_step(t)
         x0 = eng.p_sample_predict(i, x, gt, mask)
         if denoised_fn is not None:
@@ -162,7 +163,7 @@ class GaussianDiffusion:
                                   randomize_class=False, cond_fn_with_grad=False, const_noise=False):
         if cond_fn is not None or cond_fn_with_grad or randomize_class:
             raise NotImplementedError("classifier guidance options are not on the reference's sampling path")
-        eng, gt, mask = self._prepare(model, model_kwargs)
+        eng, gt, mask = self._prepare(model, model_kwargs, T=shape[-1])
         img = noise if noise is not None else th.randn(*shape, device=eng.device)
         if noise is None and gt is not None:
             img = (img * ~mask) + (gt * mask)   # initial inpaint blend (gaussian_diffusion.py:694-699)
@@ -190,7 +191,7 @@ class GaussianDiffusion:
                  and not randomize_class and dump_steps is None and not const_noise)
         if plain:
             # whole loop in the library: one CUDA-graph replay per step
-            eng, gt, mask = self._prepare(model, model_kwargs)
+            eng, gt, mask = self._prepare(model, model_kwargs, T=shape[-1])
             x_T = noise if noise is not None else th.randn(*shape, device=eng.device)
             if noise is None and gt is not None:
                 x_T = (x_T * ~mask) + (gt * mask)

@@ -215,9 +215,13 @@ class Engine:
 
     @staticmethod
     def _mask_u8(mask, device):
+        """bool and uint8 masks share one byte layout: a device-resident bool mask is reinterpreted, not copied."""
         if mask is None:
             return None
-        return mask.to(device=device).to(torch.uint8).contiguous()
+        mask = mask.to(device=device)
+        if mask.dtype == torch.bool:
+            return mask.contiguous().view(torch.uint8)
+        return mask.to(torch.uint8).contiguous()
 
     def p_sample(self, i, x_t, noise, gt=None, mask=None):
         x_t, noise = self._f32(x_t), self._f32(noise)
@@ -242,17 +246,29 @@ class Engine:
         self._chk(self.lib.idb_p_sample_finish(self._h, int(i), self._ptr(x0), self._ptr(x_t), self._ptr(noise), self._ptr(out), self._stream()))
         return out
 
+    default_graph_mode = 1     # use_graph=True -> this mode: 1 = one captured graph per step, 2 = the whole loop as one graph
+
+    def _graph_mode(self, use_graph):
+        if isinstance(use_graph, str):
+            return {"off": 0, "step": 1, "loop": 2}[use_graph]
+        if use_graph is True:
+            return self.default_graph_mode
+        return int(use_graph)
+
     def p_sample_loop(self, tape, gt=None, mask=None, correction=False, use_graph=True, out=None):
-        """tape: (n_steps+1, B,1,C,T) device tensor; tape[0] = x_T."""
+        """tape: (n_steps+1, B,1,C,T) device tensor; tape[0] = x_T.  use_graph: False / True / 'off' / 'step' / 'loop'.
+        gt / mask are copied into the handle's own buffers and the tape is reached through a device slot, so the
+        captured graphs are reused across calls with fresh tensors."""
         assert tape.is_cuda and tape.dtype == torch.float32 and tape.is_contiguous()
         assert tape.shape[0] == self.n_steps + 1
         gt = self._f32(gt) if gt is not None else None
         m = self._mask_u8(mask, self.device)
         if out is None:
             out = torch.empty_like(tape[0])
+        mode = self._graph_mode(use_graph)
         self._chk(self.lib.idb_p_sample_loop(self._h, self._ptr(tape), self._ptr(gt), self._ptr(m), int(bool(correction)),
-                                             int(bool(use_graph)), self._ptr(out), self._stream()))
-        self._keep_loop = [tape, gt, m]
+                                             int(mode), self._ptr(out), self._stream()))
+        self._keep_loop = [tape, gt, m]   # read asynchronously by the enqueued work
         return out
 
     def pointcloud_embed(self, obj_points):
@@ -284,6 +300,7 @@ class Engine:
         p = lambda a: C.c_void_p(a.ctypes.data)
         self._chk(self.lib.idb_body_init(self._h, V, J, NB, faces.shape[0], p(vt), p(sd), p(pd), p(jr), p(w), p(parents), p(faces)))
         self.V, self.J = V, J
+        self._body_owner = None      # set by SMPL_Layer.load_into (which module's arrays this engine holds)
 
     def lbs(self, pose, betas, trans, want_verts=True, want_jtr=True):
         pose, betas, trans = self._f32(pose), self._f32(betas), self._f32(trans)
@@ -344,6 +361,7 @@ class Engine:
         hm = np.asarray(HAND_MARKERS, dtype=np.int32)
         self._chk(self.lib.idb_projector_set_hand_markers(self._h, C.c_void_p(hm.ctypes.data), len(hm)))
         self.past_len, self.future_len = past_len, future_len
+        self._projector_owner = None
 
     def bind_correction(self, hand_pose, betas, obj_points, past_len=None, marker_ids=None, hand_marker_ids=None):
         hand_pose, betas, obj_points = self._f32(hand_pose), self._f32(betas), self._f32(obj_points)

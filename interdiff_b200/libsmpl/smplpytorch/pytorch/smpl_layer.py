@@ -70,11 +70,16 @@ class SMPL_Layer(Module):
                     weights=self.th_weights.cpu().numpy(), faces=self.th_faces.cpu().numpy(),
                     parents=np.asarray([max(p, 0) if i else 0 for i, p in enumerate(self.kintree_parents)], dtype=np.int64))
 
+    def _signature(self):
+        return tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict().items())
+
     def load_into(self, eng):
-        key = id(eng)
-        if self.__dict__.get("_loaded") != key:
+        """The ENGINE remembers whose arrays it holds: two layers (male / female) alternating on one shared engine
+        reload each other instead of silently running with the other's model."""
+        key = (id(self), self._signature())
+        if getattr(eng, "_body_owner", None) != key:
             eng.load_body(self.arrays())
-            self.__dict__["_loaded"] = key
+            eng._body_owner = key
         return eng
 
     def engine_for(self, device):
@@ -83,10 +88,8 @@ class SMPL_Layer(Module):
             raise RuntimeError("interdiff_b200.SMPL_Layer runs on a CUDA (sm_100a) device only: no CPU fallback")
         engines = self.__dict__.setdefault("_engines", {})
         if device not in engines:
-            eng = Engine(device)
-            eng.load_body(self.arrays())
-            engines[device] = eng
-        return engines[device]
+            engines[device] = Engine(device)
+        return self.load_into(engines[device])
 
     def forward(self, th_pose_axisang, th_betas=None, th_trans=None, th_offsets=None, scale=1.0):
         """pose (F, J*3), betas (F, NB), trans (F, 3) -> (verts (F,V,3), joints (F,J,3), None, None).
@@ -95,8 +98,12 @@ class SMPL_Layer(Module):
             raise NotImplementedError("per-vertex offsets / scale are not used on the sampling path")
         F = th_pose_axisang.shape[0]
         dev = th_pose_axisang.device
-        if th_betas is None or (th_betas.numel() == 1):
-            th_betas = self.th_betas.to(dev).expand(F, -1)   # the reference's template-betas branch (:96-100)
+        # reference :96-100: `th_betas is None or bool(torch.norm(th_betas) == 0)` switches to the layer's own template
+        # betas (the default argument torch.zeros(1) lands here too); the norm test is a host sync upstream as well
+        if th_betas is None or bool(torch.norm(th_betas) == 0):
+            th_betas = self.th_betas.to(dev).expand(F, -1)
+        elif th_betas.shape[0] == 1 and F > 1:
+            th_betas = th_betas.expand(F, -1)
         if th_trans is None:
             th_trans = torch.zeros(F, 3, device=dev)
         if th_trans.shape[0] == 1 and F > 1:

@@ -25,10 +25,10 @@ class ObjProjector(nn.Module):
 
     def load_into(self, eng):
         """Packs this module's weights into `eng` (shared with the denoiser for the fused loop)."""
-        key = (id(eng), self._signature())
-        if self.__dict__.get("_loaded") != key:
+        key = (id(self), self._signature())
+        if getattr(eng, "_projector_owner", None) != key:     # tracked on the engine: projectors sharing one engine reload each other
             eng.load_projector(self.state_dict(), self.args.past_len, self.args.future_len, n_pre=self.n_pre, n_markers=self.args.num_verts)
-            self.__dict__["_loaded"] = key
+            eng._projector_owner = key
         return eng
 
     def engine_for(self, device):

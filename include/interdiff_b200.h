@@ -110,8 +110,11 @@ int idb_p_sample_finish(idb_handle* h, int i, const float* x0, const float* x_t,
                         float* x_out, void* stream);
 /* Whole loop: x_T = tape[0], eps of the k-th executed step = tape[k+1] (n+1 entries of the
  * sample shape); steps i = n-1 .. 0.  correction != 0 runs the fused denoised_fn
- * (idb_correction_apply) on the steps the reference's hook is active on (t <= 500, t % 50 == 0).
- * Uses a CUDA graph per step when use_graph != 0. */
+ * (idb_correction_apply) on the steps the reference's hook is active on (t <= 500, t % 50 == 0), in the reference's order
+ * model -> inpaint blend -> hook -> posterior (gaussian_diffusion.py:305-376; no re-inpainting after the hook).
+ * use_graph: 0 = plain launches, 1 = one captured CUDA graph per step replayed n times, 2 = the whole loop as ONE graph.
+ * gt / mask are copied into handle-owned buffers and the tape is read through a device slot, so captured graphs are
+ * reused for any later call of the same (B, T, n, mask present, correction) on fresh tensors. */
 int idb_p_sample_loop(idb_handle* h, const float* tape, const float* gt, const uint8_t* mask,
                       int correction, int use_graph, float* x_out, void* stream);
 
@@ -160,6 +163,9 @@ int idb_correction_bind(idb_handle* h, int B, int T, int past_len, int n_obj_poi
  * contact (B,P) int32, markers (T,B,P,3), o2h_signed (T*B,Pobj). */
 int idb_correction_apply(idb_handle* h, float* x0, const float* gt, int t, uint8_t* condition_out,
                          int32_t* contact_out, float* markers_out, float* o2h_out, void* stream);
+/* Parity hook for the in-loop path: device buffers cond_log [capacity][B] uint8, contact_log [capacity][B][n_markers] int32
+ * receive the decisions of every correction step enqueued after this call, in order (NULL, NULL, 0 = off). */
+int idb_correction_set_log(idb_handle* h, uint8_t* cond_log, int32_t* contact_log, int capacity);
 
 /* Evaluation metrics of a batch of predictions (reference eval_smpl_short.py:24-81 `metrics`), per sample, on the device:
  *   obj_pred / obj_gt (T,B,6) = [axis-angle | translation], body_jtr(_gt) (T,B,J,3), body(_gt) (T,B,Db) with the global

@@ -12,10 +12,19 @@ struct BodyModel {
     // nearest-neighbour acceleration: vertices grouped into NN_CLUSTERS spatially compact clusters (k-means on the
     // template at init); nn_vid = vertex ids sorted by (cluster, id), nn_off = cluster offsets [NN_CLUSTERS + 1]
     uint16_t* nn_vid = nullptr; int32_t* nn_off = nullptr;
+    // tensor-core pose blend (lbs.cu): posedirs * 2^8 as the W operand of the split-precision GEMM, fp16 (hi, lo) pairs
+    // [Nb][Kld] with row n = v*3 + c (rows >= 3V and columns >= Kp zero), Nb = 3V rounded up to 4, Kld = Kp rounded up to 8
+    __half *pd_hi = nullptr, *pd_lo = nullptr; int Nb = 0, Kld = 0;
+    // skinning weights in ELL form: sk_n[v] non-zero bones of vertex v (<= SK_MAX), sk_j / sk_w [SK_MAX][V]; sk_dense = some
+    // vertex has more than SK_MAX non-zero weights (then the kernel walks all J bones of weightsT instead)
+    unsigned char *sk_n = nullptr, *sk_j = nullptr; float* sk_w = nullptr; bool sk_dense = false;
     std::vector<void*> owned;
     // per-call workspace
     int capF = 0;
     float *A = nullptr, *pose_map = nullptr;
+    __half *pm_hi = nullptr, *pm_lo = nullptr;   // pose_map as fp16 (hi, lo) pairs [F][Kld]
+    float* blend = nullptr;                      // [F][Nb] pose-blend offsets * 2^8
 };
+constexpr int SK_MAX = 8;
 
 int idb_body_workspace(idb_handle* h, int F);

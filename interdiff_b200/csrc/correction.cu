@@ -33,6 +33,8 @@ struct Projector {
     unsigned char *lbl = nullptr, *cond = nullptr;
     int32_t* contact = nullptr;
     std::vector<void*> ctx_owned;
+    // optional decision log (idb_correction_set_log): slot k receives the decisions of the k-th correction step enqueued
+    unsigned char* log_cond = nullptr; int32_t* log_contact = nullptr; int log_cap = 0, log_n = 0;
 };
 
 namespace {
@@ -592,6 +594,11 @@ int idb_correction_apply_dev(idb_handle* h, float* x0, const float* gt, int t, c
     LAUNCH_CHECK(h);
     k_decide<<<B, 128, 0, st>>>(p.pen, p.dmin, p.lbl, p.cond, p.contact, T, B, P, p.cpast);
     LAUNCH_CHECK(h);
+    if (p.log_cond && p.log_n < p.log_cap) {     // decision log for the parity tests of the in-loop path
+        CUDA_TRY(h, cudaMemcpyAsync(p.log_cond + (size_t)p.log_n * B, p.cond, (size_t)B, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(h, cudaMemcpyAsync(p.log_contact + (size_t)p.log_n * B * P, p.contact, (size_t)B * P * 4, cudaMemcpyDeviceToDevice, st));
+        p.log_n++;
+    }
     k_gt_obj<<<F, 32, 0, st>>>(gt, p.gt_ang, p.gt_tr, B, T, C);
     LAUNCH_CHECK(h);
     if ((rc = projector_run(h, T, B, p.gt_ang, p.gt_tr, p.markers, p.contact, p.proj_out, st))) return rc;
@@ -599,6 +606,20 @@ int idb_correction_apply_dev(idb_handle* h, float* x0, const float* gt, int t, c
     const float a = (float)t / 1000.0f;
     k_blend<<<148 * 2, 256, 0, st>>>(x0, p.proj_out, p.cond, a, B, T, C);
     LAUNCH_CHECK(h);
+    return IDB_OK;
+}
+
+/* Debug / parity hook: device buffers cond_log [capacity][B] uint8 and contact_log [capacity][B][P] int32 that receive the
+   decisions (condition, contact) of every correction step ENQUEUED from now on, in order (slot = running count, reset by
+   this call; NULL switches the log off).  A captured whole-loop graph keeps writing the slots it was captured with. */
+extern "C" int idb_correction_set_log(idb_handle* h, uint8_t* cond_log, int32_t* contact_log, int capacity) {
+    IDB_ENTER(h);
+    if (!h) return IDB_ERR_ARG;
+    if (!h->proj) return idb_fail(h, IDB_ERR_STATE, "idb_projector_init first");
+    if ((cond_log == nullptr) != (contact_log == nullptr) || capacity < 0) return IDB_ERR_ARG;
+    Projector& p = *h->proj;
+    p.log_cond = cond_log; p.log_contact = contact_log; p.log_cap = cond_log ? capacity : 0; p.log_n = 0;
+    h->epoch++;      // captured graphs contain (or lack) the log copies
     return IDB_OK;
 }
 

@@ -25,7 +25,7 @@ constexpr int FB = 16;  // frames per skinning block
 __global__ void k_lbs_pose(const float* __restrict__ pose, const float* __restrict__ betas, const float* __restrict__ trans,
                            const float* __restrict__ J_templ, const float* __restrict__ J_shape,
                            const int* __restrict__ parents, float* __restrict__ Aout, float* __restrict__ pose_map,
-                           float* __restrict__ jtr, int J, int NB, int Kp) {
+                           float* __restrict__ jtr, int J, int NB, int Kp, __half* __restrict__ pm_hi, __half* __restrict__ pm_lo, int Kld) {
     extern __shared__ float sm[];
     float* sR = sm;            // [J][9]
     float* sJ = sR + J * 9;    // [J][3]
@@ -54,8 +54,13 @@ __global__ void k_lbs_pose(const float* __restrict__ pose, const float* __restri
             sJ[j * 3 + c3] = v;
         }
         if (j >= 1)
-            for (int e = 0; e < 9; e++)
-                pose_map[(size_t)f * Kp + (j - 1) * 9 + e] = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+            for (int e = 0; e < 9; e++) {
+                const float pm = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+                if (pm_hi) split_f16(pm, pm_hi[(size_t)f * Kld + (j - 1) * 9 + e], pm_lo[(size_t)f * Kld + (j - 1) * 9 + e]);   // A operand of the blend GEMM
+                else pose_map[(size_t)f * Kp + (j - 1) * 9 + e] = pm;
+            }
+        if (pm_hi && j == 0)
+            for (int e = Kp; e < Kld; e++) { pm_hi[(size_t)f * Kld + e] = __float2half(0.f); pm_lo[(size_t)f * Kld + e] = __float2half(0.f); }
     }
     __syncthreads();
     if (j == 0) {
@@ -174,6 +179,102 @@ k_lbs_skin(const float* __restrict__ posedirsT, const float* __restrict__ shaped
     }
 }
 
+
+// Second half of the tensor-core path.  The pose blend  P vec(R - I)  (459 of the 469 multiply-adds per vertex coordinate)
+// is ONE split-precision tcgen05 GEMM  blend[F][3V] = pose_map[F][Kp] . (2^8 posedirs)[3V][Kp]^T  (gemm_tcgen05.cu; fp16
+// (hi, lo) pairs, fp32 TMEM accumulation; the 2^8 keeps the mm-scale bases well inside the fp16 normal range and is undone
+// exactly below).  This kernel finishes a vertex: shape blend on FFMA (10 terms), + blend, skinning matrix from the
+// vertex's non-zero bones only (SMPL weights have <= 4 per vertex; ELL list built at init, dense walk as the fallback),
+// transform, translation.  Thread = vertex, block = 256 vertices x FS frames; the A matrices of the frame group live in
+// shared memory (neighbouring vertices share bones, so the reads are mostly broadcasts); vertices leave through a
+// per-warp staging row as 8-byte coalesced stores.
+constexpr int FS = 8;
+__global__ void __launch_bounds__(256)
+k_lbs_skin_sparse(const float* __restrict__ blend, int ldb, const float* __restrict__ shapedirsT, const float* __restrict__ v_templT,
+                  const unsigned char* __restrict__ sk_n, const unsigned char* __restrict__ sk_j, const float* __restrict__ sk_w,
+                  const float* __restrict__ weightsT, int dense, const float* __restrict__ Ain, const float* __restrict__ betas,
+                  const float* __restrict__ trans, float* __restrict__ verts, int F, int V, int J, int NB) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_A = sm;                       // [FS][J][12]
+    float* s_b = s_A + FS * J * 12;        // [FS][NB]
+    float* s_t = s_b + FS * NB;            // [FS][4]
+    float* s_o = s_t + FS * 4;             // [8 warps][96] output staging
+    const int f0 = blockIdx.y * FS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nf = min(FS, F - f0);
+    for (int i = tid; i < nf * J * 12; i += 256) s_A[i] = Ain[(size_t)f0 * J * 12 + i];
+    for (int i = tid; i < nf * NB; i += 256) s_b[i] = betas[(size_t)f0 * NB + i];
+    for (int i = tid; i < nf * 3; i += 256) s_t[(i / 3) * 4 + i % 3] = trans[(size_t)f0 * 3 + i];
+    __syncthreads();
+    const int v0 = blockIdx.x * 256 + warp * 32, v = v0 + lane;
+    const bool live = v < V;
+    const int vc = live ? v : V - 1;
+    float vt[3], S[3][16];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        vt[c] = v_templT[(size_t)c * V + vc];
+#pragma unroll
+        for (int b = 0; b < 16; b++) S[c][b] = b < NB ? shapedirsT[((size_t)b * 3 + c) * V + vc] : 0.f;
+    }
+    int nb = 0, bj[SK_MAX]; float bw[SK_MAX];
+    if (!dense) {
+        nb = sk_n[vc];
+#pragma unroll
+        for (int e = 0; e < SK_MAX; e++) { bj[e] = sk_j[(size_t)e * V + vc]; bw[e] = sk_w[(size_t)e * V + vc]; }
+    }
+    float* so = s_o + warp * 96;
+    for (int ff = 0; ff < nf; ff++) {
+        const float* bl = blend + (size_t)(f0 + ff) * ldb + (size_t)vc * 3;
+        const float b0 = bl[0], b1 = bl[1], b2 = bl[2];
+        float px = vt[0], py = vt[1], pz = vt[2];
+#pragma unroll
+        for (int b = 0; b < 16; b++)
+            if (b < NB) {
+                const float bb = s_b[ff * NB + b];
+                px = fmaf(S[0][b], bb, px); py = fmaf(S[1][b], bb, py); pz = fmaf(S[2][b], bb, pz);
+            }
+        px = fmaf(b0, 1.0f / 256.0f, px); py = fmaf(b1, 1.0f / 256.0f, py); pz = fmaf(b2, 1.0f / 256.0f, pz);
+        float Tm[12];
+#pragma unroll
+        for (int e = 0; e < 12; e++) Tm[e] = 0.f;
+        const float4* A4 = reinterpret_cast<const float4*>(s_A + (size_t)ff * J * 12);
+        if (!dense) {
+#pragma unroll
+            for (int e = 0; e < SK_MAX; e++)
+                if (e < nb) {
+                    const float w = bw[e];
+                    const float4 a0 = A4[bj[e] * 3], a1 = A4[bj[e] * 3 + 1], a2 = A4[bj[e] * 3 + 2];
+                    Tm[0] = fmaf(w, a0.x, Tm[0]); Tm[1] = fmaf(w, a0.y, Tm[1]); Tm[2] = fmaf(w, a0.z, Tm[2]); Tm[3] = fmaf(w, a0.w, Tm[3]);
+                    Tm[4] = fmaf(w, a1.x, Tm[4]); Tm[5] = fmaf(w, a1.y, Tm[5]); Tm[6] = fmaf(w, a1.z, Tm[6]); Tm[7] = fmaf(w, a1.w, Tm[7]);
+                    Tm[8] = fmaf(w, a2.x, Tm[8]); Tm[9] = fmaf(w, a2.y, Tm[9]); Tm[10] = fmaf(w, a2.z, Tm[10]); Tm[11] = fmaf(w, a2.w, Tm[11]);
+                }
+        } else {
+            for (int jn = 0; jn < J; jn++) {
+                const float w = __ldg(weightsT + (size_t)jn * V + vc);
+                const float4 a0 = A4[jn * 3], a1 = A4[jn * 3 + 1], a2 = A4[jn * 3 + 2];
+                Tm[0] = fmaf(w, a0.x, Tm[0]); Tm[1] = fmaf(w, a0.y, Tm[1]); Tm[2] = fmaf(w, a0.z, Tm[2]); Tm[3] = fmaf(w, a0.w, Tm[3]);
+                Tm[4] = fmaf(w, a1.x, Tm[4]); Tm[5] = fmaf(w, a1.y, Tm[5]); Tm[6] = fmaf(w, a1.z, Tm[6]); Tm[7] = fmaf(w, a1.w, Tm[7]);
+                Tm[8] = fmaf(w, a2.x, Tm[8]); Tm[9] = fmaf(w, a2.y, Tm[9]); Tm[10] = fmaf(w, a2.z, Tm[10]); Tm[11] = fmaf(w, a2.w, Tm[11]);
+            }
+        }
+        so[lane * 3 + 0] = (Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3]) + s_t[ff * 4 + 0];
+        so[lane * 3 + 1] = (Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7]) + s_t[ff * 4 + 1];
+        so[lane * 3 + 2] = (Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11]) + s_t[ff * 4 + 2];
+        __syncwarp();
+        // 96 floats of this warp's 32 vertices are contiguous in verts[f][v0 .. v0+31][3] and 8-byte aligned
+        float* dst = verts + ((size_t)(f0 + ff) * V + v0) * 3;
+        const int nfl = min(32, V - v0) * 3;          // floats of live vertices (<= 0 for a warp past the end)
+        if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+            for (int i = lane * 2; i < nfl; i += 64) {
+                if (i + 1 < nfl) *reinterpret_cast<float2*>(dst + i) = *reinterpret_cast<const float2*>(so + i);
+                else dst[i] = so[i];
+            }
+        } else {
+            for (int i = lane; i < nfl; i += 32) dst[i] = so[i];
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 void idb_body_release(idb_handle* h) {
@@ -181,7 +282,7 @@ void idb_body_release(idb_handle* h) {
     h->epoch++;
     BodyModel& m = *h->body;
     for (void* p : m.owned) cudaFree(p);
-    if (m.A) { cudaFree(m.A); cudaFree(m.pose_map); }
+    if (m.A) { cudaFree(m.A); cudaFree(m.pose_map); cudaFree(m.pm_hi); cudaFree(m.blend); }
     delete h->body;
     h->body = nullptr;
 }
@@ -235,6 +336,38 @@ extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const 
     CUDA_TRY(h, up(pdT.data(), pdT.size() * 4, (void**)&m.posedirsT)); CUDA_TRY(h, up(wT.data(), wT.size() * 4, (void**)&m.weightsT));
     CUDA_TRY(h, up(Jt.data(), Jt.size() * 4, (void**)&m.J_templ)); CUDA_TRY(h, up(Js.data(), Js.size() * 4, (void**)&m.J_shape));
     CUDA_TRY(h, up(par.data(), par.size() * 4, (void**)&m.parents));
+    {
+        // tensor-core pose blend: W operand of the GEMM = 2^8 * posedirs in its native (V,3,Kp) order (row n = v*3 + c)
+        m.Nb = (3 * V + 3) & ~3; m.Kld = (Kp + 7) & ~7;
+        std::vector<float> pds((size_t)m.Nb * Kp, 0.f);
+        for (size_t i = 0; i < (size_t)3 * V * Kp; i++) pds[i] = pd[i] * 256.0f;
+        float* tmp = nullptr;
+        CUDA_TRY(h, cudaMalloc((void**)&tmp, pds.size() * 4));
+        cudaError_t e = cudaMemcpy(tmp, pds.data(), pds.size() * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&m.pd_hi, (size_t)m.Nb * m.Kld * sizeof(__half) * 2 + 64);
+        if (e != cudaSuccess) { cudaFree(tmp); return idb_fail(h, IDB_ERR_CUDA, "posedirs pairs: %s", cudaGetErrorString(e)); }
+        m.owned.push_back(m.pd_hi);
+        m.pd_lo = m.pd_hi + (size_t)m.Nb * m.Kld;
+        int rc = idb_split_tensor(h, tmp, Kp, m.pd_hi, m.pd_lo, m.Kld, m.Nb, Kp, 0);
+        cudaDeviceSynchronize();
+        cudaFree(tmp);
+        if (rc) return rc;
+        // skinning weights: non-zero bones per vertex (ELL, bone-major so a warp reads consecutive vertices)
+        std::vector<unsigned char> skn(V, 0), skj((size_t)SK_MAX * V, 0);
+        std::vector<float> skw((size_t)SK_MAX * V, 0.f);
+        m.sk_dense = false;
+        for (int v = 0; v < V && !m.sk_dense; v++) {
+            int n = 0;
+            for (int j = 0; j < J; j++)
+                if (w[(size_t)v * J + j] != 0.f) {
+                    if (n == SK_MAX) { m.sk_dense = true; break; }
+                    skj[(size_t)n * V + v] = (unsigned char)j; skw[(size_t)n * V + v] = w[(size_t)v * J + j]; n++;
+                }
+            skn[v] = (unsigned char)n;
+        }
+        CUDA_TRY(h, up(skn.data(), skn.size(), (void**)&m.sk_n)); CUDA_TRY(h, up(skj.data(), skj.size(), (void**)&m.sk_j));
+        CUDA_TRY(h, up(skw.data(), skw.size() * 4, (void**)&m.sk_w));
+    }
     if (faces && Fc > 0) {
         std::vector<int32_t> fc((size_t)Fc * 3);
         CUDA_TRY(h, pull(faces, fc.size() * 4, fc.data()));
@@ -297,6 +430,7 @@ extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const 
     }
     const int smem_skin = (int)sizeof(float) * (Kp * FB + FB * J * 12 + NB * FB + FB * 3);
     CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_skin));
+    h->epoch++;
     return IDB_OK;
 }
 
@@ -304,9 +438,13 @@ int idb_body_workspace(idb_handle* h, int F) {
     BodyModel& m = *h->body;
     if (F <= m.capF) return IDB_OK;
     h->epoch++;                      // captured loop graphs point at the old workspace
-    if (m.A) { cudaFree(m.A); cudaFree(m.pose_map); }
+    if (m.A) { cudaFree(m.A); cudaFree(m.pose_map); cudaFree(m.pm_hi); cudaFree(m.blend); }
+    m.A = nullptr; m.capF = 0;
     CUDA_TRY(h, cudaMalloc((void**)&m.A, sizeof(float) * (size_t)F * m.J * 12));
     CUDA_TRY(h, cudaMalloc((void**)&m.pose_map, sizeof(float) * (size_t)F * m.Kp));
+    CUDA_TRY(h, cudaMalloc((void**)&m.pm_hi, sizeof(__half) * 2 * (size_t)F * m.Kld + 64));
+    CUDA_TRY(h, cudaMalloc((void**)&m.blend, sizeof(float) * (size_t)F * m.Nb));
+    m.pm_lo = m.pm_hi + (size_t)F * m.Kld;
     m.capF = F;
     return IDB_OK;
 }
@@ -321,9 +459,22 @@ extern "C" int idb_smplh_lbs(idb_handle* h, int F, const float* pose, const floa
     int rc = idb_body_workspace(h, F);
     if (rc) return rc;
     const size_t smem_pose = sizeof(float) * (size_t)m.J * (9 + 3 + 12);
-    k_lbs_pose<<<F, 64, smem_pose, st>>>(pose, betas, trans, m.J_templ, m.J_shape, m.parents, m.A, m.pose_map, jtr, m.J, m.NB, m.Kp);
+    // tensor backend: the 459-term pose blend is a split-precision tcgen05 GEMM, the rest a sparse-bone skinning kernel
+    const bool tensor = h->gemm_backend == 1 && verts && m.pd_hi;
+    k_lbs_pose<<<F, 64, smem_pose, st>>>(pose, betas, trans, m.J_templ, m.J_shape, m.parents, m.A, m.pose_map, jtr, m.J, m.NB, m.Kp,
+                                         tensor ? m.pm_hi : nullptr, tensor ? m.pm_lo : nullptr, m.Kld);
     LAUNCH_CHECK(h);
-    if (verts) {
+    if (tensor) {
+        GemmArgs g;
+        g.A_hi = m.pm_hi; g.A_lo = m.pm_lo; g.lda = m.Kld; g.W_hi = m.pd_hi; g.W_lo = m.pd_lo; g.ldw = m.Kld;
+        g.C = m.blend; g.ldc = m.Nb; g.M = F; g.N = m.Nb; g.K = m.Kld; g.epi = 0;
+        if ((rc = idb_gemm_ex(h, g, st))) return rc;
+        const size_t smem = sizeof(float) * ((size_t)FS * m.J * 12 + (size_t)FS * m.NB + FS * 4 + 8 * 96);
+        dim3 grid((m.V + 255) / 256, (F + FS - 1) / FS);
+        k_lbs_skin_sparse<<<grid, 256, smem, st>>>(m.blend, m.Nb, m.shapedirsT, m.v_templT, m.sk_n, m.sk_j, m.sk_w, m.weightsT, m.sk_dense ? 1 : 0,
+                                                    m.A, betas, trans, verts, F, m.V, m.J, m.NB);
+        LAUNCH_CHECK(h);
+    } else if (verts) {
         const size_t smem_skin = sizeof(float) * ((size_t)m.Kp * FB + (size_t)FB * m.J * 12 + (size_t)m.NB * FB + FB * 3);
         dim3 grid((m.V + 255) / 256, (F + FB - 1) / FB);
         k_lbs_skin<<<grid, 256, smem_skin, st>>>(m.posedirsT, m.shapedirsT, m.v_templT, m.weightsT, m.A, m.pose_map, betas, trans,

@@ -143,7 +143,8 @@ class GaussianDiffusion:
         mean, var, logvar = self.q_posterior_mean_variance(x0, x, t)
         return {"mean": mean, "variance": var, "log_variance": logvar, "pred_xstart": x0}
 
-    def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, const_noise=False):
+    def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, const_noise=False,
+                 _noise=None):
         if cond_fn is not None:
             raise NotImplementedError("cond_fn guidance is not on the reference's sampling path")
         eng, gt, mask = self._prepare(model, model_kwargs, T=x.shape[-1])
@@ -153,7 +154,7 @@ class GaussianDiffusion:
             x0 = denoised_fn(x0, t, model_kwargs)
         if clip_denoised:
             x0 = x0.clamp(-1, 1)
-        noise = th.randn_like(x)
+        noise = th.randn_like(x) if _noise is None else _noise     # _noise: this step's eps drawn up front by the loop
         if const_noise:
             noise = noise[[0]].repeat(x.shape[0], 1, 1, 1)
         return {"sample": eng.p_sample_finish(i, x0, x, noise), "pred_xstart": x0}
@@ -172,14 +173,18 @@ class GaussianDiffusion:
         indices = list(range(self.num_timesteps))[skip_timesteps:][::-1]
         if init_image is not None:
             img = self.q_sample(init_image, th.full((shape[0],), indices[0], device=eng.device, dtype=th.long), img)
+        # every step's eps drawn up front in ONE generator call, exactly like the in-library loop (same seed -> the
+        # callback path and the fused path see the same noise); the reference draws th.randn_like(x) per step (:532)
+        from ..sampling import draw_tape
+        tape = draw_tape(eng, img, len(indices))
         if progress:
             from tqdm.auto import tqdm
             indices = tqdm(indices)
-        for i in indices:
+        for k, i in enumerate(indices):
             t = th.full((shape[0],), i, device=eng.device, dtype=th.long)
             with th.no_grad():
                 out = self.p_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
-                                    model_kwargs=model_kwargs, const_noise=const_noise)
+                                    model_kwargs=model_kwargs, const_noise=const_noise, _noise=tape[k + 1])
             yield out
             img = out["sample"]
 

@@ -374,6 +374,7 @@ class Engine:
         torch.cuda.synchronize(self.device)
         self.n_markers = len(mk)
         self.n_obj = obj_points.shape[1]
+        self.corr_B = B
 
     def projector_sample(self, obj_angles, obj_trans, markers, contact):
         a, t, m = self._f32(obj_angles), self._f32(obj_trans), self._f32(markers)
@@ -382,6 +383,20 @@ class Engine:
         out = torch.empty(T, B, 9, device=self.device)
         self._chk(self.lib.idb_projector_sample(self._h, T, B, self._ptr(a), self._ptr(t), self._ptr(m), self._ptr(c), self._ptr(out), self._stream()))
         return out
+
+    def correction_log(self, capacity):
+        """Parity hook: returns (cond_log [capacity,B] uint8, contact_log [capacity,B,P] int32) device tensors that the next
+        `capacity` correction steps enqueued (in-loop or stand-alone) fill in order; capacity 0 switches the log off."""
+        if not capacity:
+            self._chk(self.lib.idb_correction_set_log(self._h, None, None, 0))
+            self._corr_log = None
+            return None
+        B = self.corr_B
+        cond = torch.zeros(capacity, B, dtype=torch.uint8, device=self.device)
+        contact = torch.zeros(capacity, B, self.n_markers, dtype=torch.int32, device=self.device)
+        self._chk(self.lib.idb_correction_set_log(self._h, self._ptr(cond), self._ptr(contact), int(capacity)))
+        self._corr_log = (cond, contact)
+        return cond, contact
 
     def correction_apply(self, x0, gt, t, debug=False):
         """In-place denoised_fn body on x0 (B,1,144,T) for an active step; returns x0 (and the

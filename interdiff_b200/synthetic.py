@@ -58,9 +58,12 @@ def make_sphere_mesh(rings=84, segs=82):
     return v, f
 
 
-def make_smplh_model(seed=233):
+def make_smplh_model(seed=233, sparse_weights=False):
     """Synthetic SMPL-H-shaped body model: dict of float32/int64 arrays with the shapes of the
-    buffers SMPL_Layer registers (reference smpl_layer.py:47-64)."""
+    buffers SMPL_Layer registers (reference smpl_layer.py:47-64).  sparse_weights: at most 4 NON-ZERO skinning
+    weights per vertex (exact zeros elsewhere), which is how the licensed SMPL / SMPL-H models are painted; the
+    default keeps a dense 1e-4 tail on every bone (the golden vectors were made with it, and it exercises the
+    dense-weights path of the skinning kernel)."""
     rng = _rng(seed, "smplh")
     sph, faces = make_sphere_mesh()
     radii = np.array([0.22, 0.85, 0.14])
@@ -76,7 +79,9 @@ def make_smplh_model(seed=233):
     w = np.zeros((NUM_VERTS, NUM_JOINTS))
     ww = np.exp(-np.take_along_axis(d, order, 1) / 0.01) + 1e-3
     np.put_along_axis(w, order, ww, 1)
-    w += 1e-4 * rng.random(w.shape)  # dense small tail, like the real model's float noise
+    tail = 1e-4 * rng.random(w.shape)
+    if not sparse_weights:
+        w += tail  # dense small tail on every bone
     w /= w.sum(1, keepdims=True)
     # joint regressor: non-negative, row-normalised, localised around each joint
     jr = np.exp(-d.T / 0.005) + 1e-6 * rng.random((NUM_JOINTS, NUM_VERTS))

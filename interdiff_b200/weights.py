@@ -110,7 +110,9 @@ def random_state_dict(shapes, seed=233):
 
 
 # ---- real weights exported from the reference checkpoints (git-ignored, travels with gpurun) --
-REF_WEIGHT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "weights")
+# plain .npz files of tensors keyed by the reference's state_dict names; INTERDIFF_B200_WEIGHTS overrides the directory
+REF_WEIGHT_DIR = os.environ.get("INTERDIFF_B200_WEIGHTS") or os.path.join(
+    os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "weights_ref")
 
 
 def ref_weights_path(name):
@@ -124,3 +126,30 @@ def load_ref_weights(name):
         return None
     with np.load(p) as z:
         return {k: z[k] for k in z.files}
+
+
+def bench_weights(name, seed=233):
+    """{state_dict name: torch tensor} for the benchmarks / probes / smoke run: the exported checkpoint tensors when
+    weights_ref/<name>.npz exists, else seeded random init of the same shapes (the sinusoid tables are always rebuilt).
+    name: diffusion_smpl | diffusion_skeleton | correction_smpl | diffusion_smpl_encoder."""
+    import torch
+    sd = load_ref_weights(name)
+    if sd is None:
+        if name == "correction_smpl":
+            shapes = projector_shapes()
+        elif name == "diffusion_smpl_encoder":
+            shapes = {**mdm_encoder_shapes("smpl"), **pointnet_shapes()}
+        else:
+            variant = name[len("diffusion_"):]
+            shapes = {k: v for k, v in mdm_hot_shapes(variant, F=1024 if variant == "smpl" else 256).items() if not k.endswith(".pe")}
+        sd = random_state_dict(shapes, seed)
+    sd = dict(sd)
+    if name.startswith("diffusion_") and name != "diffusion_smpl_encoder":
+        pe = synthetic.sinusoid_table(5000, 256).reshape(5000, 1, 256)
+        sd["PositionalEmbedding.pe"] = pe
+        sd["embedTimeStep.sequence_pos_encoder.pe"] = pe
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+
+
+def have_ref_weights(name="diffusion_smpl"):
+    return os.path.exists(ref_weights_path(name))

@@ -1,4 +1,4 @@
-"""Export the hot-path tensors of the reference's shipped checkpoints to oracle/_ref/weights/*.npz
+"""Export the hot-path tensors of the reference's shipped checkpoints to weights_ref/*.npz
 (git-ignored; travels to the GPU box with the gpurun snapshot like other built artefacts).
 TEST INFRASTRUCTURE: gives the GPU parity tests / bench the trained weights' value distribution.
 Run in the authoring container:  python -m oracle.export_ref_weights

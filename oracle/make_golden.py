@@ -2,7 +2,7 @@
 oracle.shims) -- run in the authoring container:  python -m oracle.make_golden
 TEST INFRASTRUCTURE.  Inputs are the seeded synthetic generators of interdiff_b200.synthetic;
 weights are either the seeded random init (portable: regenerated from the seed by the tests) or
-the shipped checkpoints (tests using those need oracle/_ref/weights, else skip).
+the shipped checkpoints (tests using those need weights_ref, else skip).
 """
 import ast
 import os

@@ -357,24 +357,25 @@ def smplh_lbs(smplh, pose, betas, trans, scale=1.0):
     Returns verts (F,V,3), jtr (F,52,3)."""
     Fn = pose.shape[0]
     J = len(smplh["parents"])
+    dt = pose.dtype      # float32 as the reference; float64 gives the rounding-free yardstick for the precision tests
     R = batch_rodrigues(pose.reshape(Fn * J, 3)).reshape(Fn, J, 3, 3)
-    pose_map = (R[:, 1:] - torch.eye(3)).reshape(Fn, (J - 1) * 9)  # subtract_flat_id (tensutils.py:41-53)
+    pose_map = (R[:, 1:] - torch.eye(3, dtype=dt)).reshape(Fn, (J - 1) * 9)  # subtract_flat_id (tensutils.py:41-53)
     v_shaped = smplh["v_template"].unsqueeze(0) + torch.matmul(smplh["shapedirs"], betas.transpose(1, 0)).permute(2, 0, 1)
     jrest = torch.matmul(smplh["J_regressor"], v_shaped)  # (F,52,3)
     v_posed = v_shaped + torch.matmul(smplh["posedirs"], pose_map.transpose(0, 1)).permute(2, 0, 1)
     parents = [int(p) for p in smplh["parents"]]
-    bottom = torch.tensor([0.0, 0.0, 0.0, 1.0]).view(1, 1, 4).repeat(Fn, 1, 1)
+    bottom = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=dt).view(1, 1, 4).repeat(Fn, 1, 1)
     G = [torch.cat([torch.cat([R[:, 0], jrest[:, 0].unsqueeze(2)], 2), bottom], 1)]
     for i in range(1, J):
         rel = torch.cat([torch.cat([R[:, i], (jrest[:, i] - jrest[:, parents[i]]).unsqueeze(2)], 2), bottom], 1)
         G.append(torch.matmul(G[parents[i]], rel))
-    A = torch.zeros(Fn, 4, 4, J)
+    A = torch.zeros(Fn, 4, 4, J, dtype=dt)
     for i in range(J):
-        jh = torch.cat([jrest[:, i], torch.zeros(Fn, 1)], 1)
+        jh = torch.cat([jrest[:, i], torch.zeros(Fn, 1, dtype=dt)], 1)
         tmp = torch.bmm(G[i], jh.unsqueeze(2))  # (F,4,1)
-        A[:, :, :, i] = G[i] - torch.cat([torch.zeros(Fn, 4, 3), tmp], 2)
+        A[:, :, :, i] = G[i] - torch.cat([torch.zeros(Fn, 4, 3, dtype=dt), tmp], 2)
     Tm = torch.matmul(A, smplh["weights"].transpose(0, 1))  # (F,4,4,V)
-    vh = torch.cat([v_posed.transpose(2, 1), torch.ones(Fn, 1, v_posed.shape[1])], 1)  # (F,4,V)
+    vh = torch.cat([v_posed.transpose(2, 1), torch.ones(Fn, 1, v_posed.shape[1], dtype=dt)], 1)  # (F,4,V)
     verts = (Tm * vh.unsqueeze(1)).sum(2).transpose(2, 1)[:, :, :3]
     jtr = torch.stack(G, dim=1)[:, :, :3, 3]
     verts = verts * scale + trans.unsqueeze(1)

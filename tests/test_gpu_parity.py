@@ -210,7 +210,13 @@ def test_p_sample_loop_short(eng, use_graph):
     assert torch.equal(got[..., :10], gt[..., :10])
 
 
-def test_smplh_lbs(eng, smplh_np):
+@pytest.mark.parametrize("weights", ["dense_tail", "sparse4"])
+def test_smplh_lbs(eng, smplh_np, weights):
+    """both skinning paths of the tensor backend: <= 8 non-zero bones per vertex (ELL list; the licensed models have
+    <= 4) and the dense walk (a weight on every bone)"""
+    if weights == "sparse4":
+        smplh_np = S.make_smplh_model(233, sparse_weights=True)
+        assert int((smplh_np["weights"] != 0).sum(1).max()) <= 4
     eng.load_body(smplh_np)
     smplh = smplh_torch(smplh_np)
     g = torch.Generator().manual_seed(1)
@@ -227,6 +233,32 @@ def test_smplh_lbs(eng, smplh_np):
     # property: a pure translation moves every vertex by exactly that offset (to rounding)
     v2, _ = eng.lbs(pose, betas, trans + 1.0)
     assert rel(v2 - 1.0, verts) < 1e-5
+
+
+def test_smplh_lbs_large_blend(eng):
+    """precision budget of the tensor-core pose blend: bases 20x larger than the synthetic default (a ~10 cm corrective
+    term, beyond anything the licensed model produces), large joint rotations, several row tiles of frames with a
+    partial last one, an odd vertex count (unaligned output rows) - still 1e-5 of the vertex magnitude"""
+    m = S.make_smplh_model(7, sparse_weights=True)
+    V = 6889
+    m = dict(m)
+    for k in ("v_template", "shapedirs", "posedirs", "weights"):
+        m[k] = np.ascontiguousarray(m[k][:V])
+    m["J_regressor"] = np.ascontiguousarray(m["J_regressor"][:, :V])
+    m["faces"] = np.ascontiguousarray(m["faces"][(m["faces"] < V).all(1)])
+    m["posedirs"] = m["posedirs"] * 20.0
+    eng.load_body(m)
+    smplh = smplh_torch(m)
+    g = torch.Generator().manual_seed(3)
+    Fn = 300
+    pose, betas, trans = 1.2 * torch.randn(Fn, 156, generator=g), 2.0 * torch.randn(Fn, 10, generator=g), torch.randn(Fn, 3, generator=g)
+    verts, jtr = eng.lbs(pose, betas, trans)
+    with torch.no_grad():
+        v_ref, j_ref = R.smplh_lbs(smplh, pose, betas, trans)
+        v64, _ = R.smplh_lbs({k: (v.double() if v.is_floating_point() else v) for k, v in smplh.items()}, pose.double(), betas.double(), trans.double())
+    assert rel(verts, v_ref) < 1e-5 and rel(jtr, j_ref) < 1e-5
+    # against float64 the kernel is as close as the fp32 oracle itself (within 3x)
+    assert rel(verts, v64) < max(3 * rel(v_ref, v64), 2e-6)
 
 
 def test_geometry(eng, smplh_np):

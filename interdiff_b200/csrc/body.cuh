@@ -9,11 +9,12 @@ struct BodyModel {
     float *v_templT = nullptr, *shapedirsT = nullptr, *posedirsT = nullptr, *weightsT = nullptr;
     float *J_templ = nullptr, *J_shape = nullptr;
     int32_t *parents = nullptr, *faces = nullptr, *vf_off = nullptr, *vf_ent = nullptr;
+    int32_t* depth = nullptr; int max_depth = 0;     // tree level of every joint (root 0)
     // nearest-neighbour acceleration: vertices grouped into NN_CLUSTERS spatially compact clusters (k-means on the
     // template at init); nn_vid = vertex ids sorted by (cluster, id), nn_off = cluster offsets [NN_CLUSTERS + 1]
     uint16_t* nn_vid = nullptr; int32_t* nn_off = nullptr;
     // tensor-core pose blend (lbs.cu): posedirs * 2^8 as the W operand of the split-precision GEMM, fp16 (hi, lo) pairs
-    // [Nb][Kld] with row n = v*3 + c (rows >= 3V and columns >= Kp zero), Nb = 3V rounded up to 4, Kld = Kp rounded up to 8
+    // [Nb][Kld] with row n = v*3 + c (rows >= 3V and columns >= Kp zero), Nb = 3V rounded up to 256, Kld = Kp rounded up to 8
     __half *pd_hi = nullptr, *pd_lo = nullptr; int Nb = 0, Kld = 0;
     // skinning weights in ELL form: sk_n[v] non-zero bones of vertex v (<= SK_MAX), sk_j / sk_w [SK_MAX][V]; sk_dense = some
     // vertex has more than SK_MAX non-zero weights (then the kernel walks all J bones of weightsT instead)

@@ -231,6 +231,8 @@ struct GemmArgs {
     int ksplit = 1;                                     // 2: split-K onto a C zeroed by an earlier kernel (tensor path only)
     float* zero = nullptr; int zero_ld = 0, zero_cols = 0;   // aux [M][zero_cols] matrix to clear as a side job
     int pdl = 0;   // 1: programmatic dependent launch; REQUIRES W_hi/W_lo to be complete before the previous kernel started
+    int single_acc = 0;   // 1: ONE main accumulator is accurate enough for the caller whatever K is (e.g. the mm-scale pose
+                          //    blend added to metre-scale vertices): allows the 256-column tiles for long reductions
 };
 int idb_gemm_ex(idb_handle* h, const GemmArgs& g, cudaStream_t st);
 // fused feed-forward block on the tensor path (gemm_tcgen05.cu)

@@ -760,7 +760,7 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
     const bool wide = tiles128 >= 74;
     // more 128-column tiles than SMs would run as two waves: 256-column tiles (one main accumulator, so only for
     // short reductions) put e.g. the folded QKV projection (N = 1536) on 90 CTAs in a single wave
-    const bool xwide = tiles128 > h->sm_count && (N % 256) == 0 && (K + BK - 1) / BK <= 4 && g.ksplit != 2 && !g.zero &&
+    const bool xwide = tiles128 > h->sm_count && (N % 256) == 0 && ((K + BK - 1) / BK <= 4 || g.single_acc) && g.ksplit != 2 && !g.zero &&
                        (g_idb_gemm_nacc <= 0 || g_idb_gemm_nacc == 1);
     const int bn = xwide ? 256 : wide ? 128 : 64;
     CUtensorMap ma, mw, mal, mwl;
@@ -783,9 +783,13 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
     // extra TMEM read pass in the epilogue.  Two already beat the fp32 SIMT kernel up to 8 k-blocks per CTA
     // (measured, profiles/README.md: 3.3e-7 at K=256, 4.1e-7 at K=1024 split in two, vs 5.5e-7 / 1.5e-6); longer
     // reductions get one accumulator per 4 k-blocks up to the TMEM budget.
+    // The accumulator count is a function of the GEMM's (N, K) only - never of M - so that a sample's result does not
+    // depend on how many samples share the batch (multi-GPU runs slice one global batch).  Shapes that the
+    // 256-column configuration serves at large M (one main accumulator) use one accumulator at every M.
     const int nacc_max = wide ? Cfg<128>::NACC_MAX : Cfg<64>::NACC_MAX;
     const int kb_per_cta = ((K + BK - 1) / BK + ksplit - 1) / ksplit;
-    int nacc = kb_per_cta <= 8 ? 2 : (kb_per_cta + 3) / 4;
+    const bool one_acc = g.single_acc || ((N % 256) == 0 && (K + BK - 1) / BK <= 4 && g.ksplit != 2 && !g.zero);
+    int nacc = one_acc ? 1 : kb_per_cta <= 8 ? 2 : (kb_per_cta + 3) / 4;
     if (nacc > nacc_max) nacc = nacc_max;
     if (g_idb_gemm_nacc > 0) nacc = g_idb_gemm_nacc < nacc_max ? g_idb_gemm_nacc : nacc_max;
     if (xwide) {

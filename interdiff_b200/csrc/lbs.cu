@@ -25,7 +25,8 @@ constexpr int FB = 16;  // frames per skinning block
 __global__ void k_lbs_pose(const float* __restrict__ pose, const float* __restrict__ betas, const float* __restrict__ trans,
                            const float* __restrict__ J_templ, const float* __restrict__ J_shape,
                            const int* __restrict__ parents, float* __restrict__ Aout, float* __restrict__ pose_map,
-                           float* __restrict__ jtr, int J, int NB, int Kp, __half* __restrict__ pm_hi, __half* __restrict__ pm_lo, int Kld) {
+                           float* __restrict__ jtr, int J, int NB, int Kp, __half* __restrict__ pm_hi, __half* __restrict__ pm_lo, int Kld,
+                           const int* __restrict__ depth, int max_depth) {
     extern __shared__ float sm[];
     float* sR = sm;            // [J][9]
     float* sJ = sR + J * 9;    // [J][3]
@@ -63,17 +64,19 @@ __global__ void k_lbs_pose(const float* __restrict__ pose, const float* __restri
             for (int e = Kp; e < Kld; e++) { pm_hi[(size_t)f * Kld + e] = __float2half(0.f); pm_lo[(size_t)f * Kld + e] = __float2half(0.f); }
     }
     __syncthreads();
-    if (j == 0) {
-        // kinematic chain (smpl_layer.py:119-130), sequential: parents precede children
-        for (int i = 0; i < J; i++) {
-            const float* R = sR + i * 9;
-            float* G = sG + i * 12;
-            if (i == 0) {
+    // kinematic chain (smpl_layer.py:119-130), one tree level per round (the reference walks the joints one by one; a
+    // joint only reads its parent, so every joint of a level can go at once - same arithmetic, 52 -> ~10 rounds)
+    const int my_depth = j < J ? depth[j] : -1;
+    for (int lvl = 0; lvl <= max_depth; lvl++) {
+        if (my_depth == lvl) {
+            const float* R = sR + j * 9;
+            float* G = sG + j * 12;
+            if (j == 0) {
                 for (int r = 0; r < 3; r++) { G[r * 4 + 0] = R[r * 3]; G[r * 4 + 1] = R[r * 3 + 1]; G[r * 4 + 2] = R[r * 3 + 2]; G[r * 4 + 3] = sJ[r]; }
             } else {
-                const int p = parents[i];
+                const int p = parents[j];
                 const float* Gp = sG + p * 12;
-                const float tx = sJ[i * 3] - sJ[p * 3], ty = sJ[i * 3 + 1] - sJ[p * 3 + 1], tz = sJ[i * 3 + 2] - sJ[p * 3 + 2];
+                const float tx = sJ[j * 3] - sJ[p * 3], ty = sJ[j * 3 + 1] - sJ[p * 3 + 1], tz = sJ[j * 3 + 2] - sJ[p * 3 + 2];
                 for (int r = 0; r < 3; r++) {
                     const float g0 = Gp[r * 4], g1 = Gp[r * 4 + 1], g2 = Gp[r * 4 + 2], g3 = Gp[r * 4 + 3];
                     G[r * 4 + 0] = g0 * R[0] + g1 * R[3] + g2 * R[6];
@@ -83,8 +86,8 @@ __global__ void k_lbs_pose(const float* __restrict__ pose, const float* __restri
                 }
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
     if (j < J) {
         const float* G = sG + j * 12;
         float* A = Aout + ((size_t)f * J + j) * 12;
@@ -189,7 +192,8 @@ k_lbs_skin(const float* __restrict__ posedirsT, const float* __restrict__ shaped
 // shared memory (neighbouring vertices share bones, so the reads are mostly broadcasts); vertices leave through a
 // per-warp staging row as 8-byte coalesced stores.
 constexpr int FS = 8;
-__global__ void __launch_bounds__(256)
+template <int NBT>     // NBT = compile-time bound of the number of betas (10 for SMPL-H; 16 = the library's maximum)
+__global__ void __launch_bounds__(256, 2)
 k_lbs_skin_sparse(const float* __restrict__ blend, int ldb, const float* __restrict__ shapedirsT, const float* __restrict__ v_templT,
                   const unsigned char* __restrict__ sk_n, const unsigned char* __restrict__ sk_j, const float* __restrict__ sk_w,
                   const float* __restrict__ weightsT, int dense, const float* __restrict__ Ain, const float* __restrict__ betas,
@@ -201,19 +205,21 @@ k_lbs_skin_sparse(const float* __restrict__ blend, int ldb, const float* __restr
     float* s_o = s_t + FS * 4;             // [8 warps][96] output staging
     const int f0 = blockIdx.y * FS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nf = min(FS, F - f0);
-    for (int i = tid; i < nf * J * 12; i += 256) s_A[i] = Ain[(size_t)f0 * J * 12 + i];
-    for (int i = tid; i < nf * NB; i += 256) s_b[i] = betas[(size_t)f0 * NB + i];
-    for (int i = tid; i < nf * 3; i += 256) s_t[(i / 3) * 4 + i % 3] = trans[(size_t)f0 * 3 + i];
-    __syncthreads();
     const int v0 = blockIdx.x * 256 + warp * 32, v = v0 + lane;
-    const bool live = v < V;
-    const int vc = live ? v : V - 1;
-    float vt[3], S[3][16];
+    const int vc = v < V ? v : V - 1;
+    // every global read of the thread is issued before the first use: one memory latency per block instead of one per frame
+    float bl[FS][3];
+#pragma unroll
+    for (int ff = 0; ff < FS; ff++) {
+        const float* q = blend + (size_t)min(f0 + ff, F - 1) * ldb + (size_t)vc * 3;
+        bl[ff][0] = q[0]; bl[ff][1] = q[1]; bl[ff][2] = q[2];
+    }
+    float vt[3], S[3][NBT];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         vt[c] = v_templT[(size_t)c * V + vc];
 #pragma unroll
-        for (int b = 0; b < 16; b++) S[c][b] = b < NB ? shapedirsT[((size_t)b * 3 + c) * V + vc] : 0.f;
+        for (int b = 0; b < NBT; b++) S[c][b] = b < NB ? shapedirsT[((size_t)b * 3 + c) * V + vc] : 0.f;
     }
     int nb = 0, bj[SK_MAX]; float bw[SK_MAX];
     if (!dense) {
@@ -221,18 +227,22 @@ k_lbs_skin_sparse(const float* __restrict__ blend, int ldb, const float* __restr
 #pragma unroll
         for (int e = 0; e < SK_MAX; e++) { bj[e] = sk_j[(size_t)e * V + vc]; bw[e] = sk_w[(size_t)e * V + vc]; }
     }
+    for (int i = tid; i < nf * J * 12; i += 256) s_A[i] = Ain[(size_t)f0 * J * 12 + i];
+    for (int i = tid; i < nf * NB; i += 256) s_b[i] = betas[(size_t)f0 * NB + i];
+    for (int i = tid; i < nf * 3; i += 256) s_t[(i / 3) * 4 + i % 3] = trans[(size_t)f0 * 3 + i];
+    __syncthreads();
     float* so = s_o + warp * 96;
-    for (int ff = 0; ff < nf; ff++) {
-        const float* bl = blend + (size_t)(f0 + ff) * ldb + (size_t)vc * 3;
-        const float b0 = bl[0], b1 = bl[1], b2 = bl[2];
+#pragma unroll
+    for (int ff = 0; ff < FS; ff++) {
+        if (ff >= nf) break;
         float px = vt[0], py = vt[1], pz = vt[2];
 #pragma unroll
-        for (int b = 0; b < 16; b++)
+        for (int b = 0; b < NBT; b++)
             if (b < NB) {
                 const float bb = s_b[ff * NB + b];
                 px = fmaf(S[0][b], bb, px); py = fmaf(S[1][b], bb, py); pz = fmaf(S[2][b], bb, pz);
             }
-        px = fmaf(b0, 1.0f / 256.0f, px); py = fmaf(b1, 1.0f / 256.0f, py); pz = fmaf(b2, 1.0f / 256.0f, pz);
+        px = fmaf(bl[ff][0], 1.0f / 256.0f, px); py = fmaf(bl[ff][1], 1.0f / 256.0f, py); pz = fmaf(bl[ff][2], 1.0f / 256.0f, pz);
         float Tm[12];
 #pragma unroll
         for (int e = 0; e < 12; e++) Tm[e] = 0.f;
@@ -260,7 +270,7 @@ k_lbs_skin_sparse(const float* __restrict__ blend, int ldb, const float* __restr
         so[lane * 3 + 1] = (Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7]) + s_t[ff * 4 + 1];
         so[lane * 3 + 2] = (Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11]) + s_t[ff * 4 + 2];
         __syncwarp();
-        // 96 floats of this warp's 32 vertices are contiguous in verts[f][v0 .. v0+31][3] and 8-byte aligned
+        // 96 floats of this warp's 32 vertices are contiguous in verts[f][v0 .. v0+31][3]
         float* dst = verts + ((size_t)(f0 + ff) * V + v0) * 3;
         const int nfl = min(32, V - v0) * 3;          // floats of live vertices (<= 0 for a warp past the end)
         if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
@@ -337,8 +347,13 @@ extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const 
     CUDA_TRY(h, up(Jt.data(), Jt.size() * 4, (void**)&m.J_templ)); CUDA_TRY(h, up(Js.data(), Js.size() * 4, (void**)&m.J_shape));
     CUDA_TRY(h, up(par.data(), par.size() * 4, (void**)&m.parents));
     {
+        std::vector<int32_t> dep(J, 0);
+        for (int i = 1; i < J; i++) { dep[i] = dep[par[i]] + 1; if (dep[i] > m.max_depth) m.max_depth = dep[i]; }
+        CUDA_TRY(h, up(dep.data(), dep.size() * 4, (void**)&m.depth));
+    }
+    {
         // tensor-core pose blend: W operand of the GEMM = 2^8 * posedirs in its native (V,3,Kp) order (row n = v*3 + c)
-        m.Nb = (3 * V + 3) & ~3; m.Kld = (Kp + 7) & ~7;
+        m.Nb = (3 * V + 255) & ~255; m.Kld = (Kp + 7) & ~7;     // whole 256-column GEMM tiles
         std::vector<float> pds((size_t)m.Nb * Kp, 0.f);
         for (size_t i = 0; i < (size_t)3 * V * Kp; i++) pds[i] = pd[i] * 256.0f;
         float* tmp = nullptr;
@@ -462,17 +477,21 @@ extern "C" int idb_smplh_lbs(idb_handle* h, int F, const float* pose, const floa
     // tensor backend: the 459-term pose blend is a split-precision tcgen05 GEMM, the rest a sparse-bone skinning kernel
     const bool tensor = h->gemm_backend == 1 && verts && m.pd_hi;
     k_lbs_pose<<<F, 64, smem_pose, st>>>(pose, betas, trans, m.J_templ, m.J_shape, m.parents, m.A, m.pose_map, jtr, m.J, m.NB, m.Kp,
-                                         tensor ? m.pm_hi : nullptr, tensor ? m.pm_lo : nullptr, m.Kld);
+                                         tensor ? m.pm_hi : nullptr, tensor ? m.pm_lo : nullptr, m.Kld, m.depth, m.max_depth);
     LAUNCH_CHECK(h);
     if (tensor) {
         GemmArgs g;
         g.A_hi = m.pm_hi; g.A_lo = m.pm_lo; g.lda = m.Kld; g.W_hi = m.pd_hi; g.W_lo = m.pd_lo; g.ldw = m.Kld;
-        g.C = m.blend; g.ldc = m.Nb; g.M = F; g.N = m.Nb; g.K = m.Kld; g.epi = 0;
+        g.C = m.blend; g.ldc = m.Nb; g.M = F; g.N = m.Nb; g.K = m.Kld; g.epi = 0; g.single_acc = 1;
         if ((rc = idb_gemm_ex(h, g, st))) return rc;
         const size_t smem = sizeof(float) * ((size_t)FS * m.J * 12 + (size_t)FS * m.NB + FS * 4 + 8 * 96);
         dim3 grid((m.V + 255) / 256, (F + FS - 1) / FS);
-        k_lbs_skin_sparse<<<grid, 256, smem, st>>>(m.blend, m.Nb, m.shapedirsT, m.v_templT, m.sk_n, m.sk_j, m.sk_w, m.weightsT, m.sk_dense ? 1 : 0,
-                                                    m.A, betas, trans, verts, F, m.V, m.J, m.NB);
+        if (m.NB <= 10)
+            k_lbs_skin_sparse<10><<<grid, 256, smem, st>>>(m.blend, m.Nb, m.shapedirsT, m.v_templT, m.sk_n, m.sk_j, m.sk_w, m.weightsT,
+                                                            m.sk_dense ? 1 : 0, m.A, betas, trans, verts, F, m.V, m.J, m.NB);
+        else
+            k_lbs_skin_sparse<16><<<grid, 256, smem, st>>>(m.blend, m.Nb, m.shapedirsT, m.v_templT, m.sk_n, m.sk_j, m.sk_w, m.weightsT,
+                                                            m.sk_dense ? 1 : 0, m.A, betas, trans, verts, F, m.V, m.J, m.NB);
         LAUNCH_CHECK(h);
     } else if (verts) {
         const size_t smem_skin = sizeof(float) * ((size_t)m.Kp * FB + (size_t)FB * m.J * 12 + (size_t)m.NB * FB + FB * 3);

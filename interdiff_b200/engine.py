@@ -246,7 +246,7 @@ class Engine:
         self._chk(self.lib.idb_p_sample_finish(self._h, int(i), self._ptr(x0), self._ptr(x_t), self._ptr(noise), self._ptr(out), self._stream()))
         return out
 
-    default_graph_mode = 1     # use_graph=True -> this mode: 1 = one captured graph per step, 2 = the whole loop as one graph
+    default_graph_mode = 2     # use_graph=True -> this mode: 1 = one captured graph per step, 2 = the whole loop as one graph (+1.4 %)
 
     def _graph_mode(self, use_graph):
         if isinstance(use_graph, str):

@@ -64,7 +64,18 @@ def _oracle_config2(sd, b, steps):
         with torch.no_grad():
             _, traj = R.p_sample_loop(lambda x, t: R.mdm_smpl_forward(sd, x, t, cond, faithful=False), tables, tape, gt, mask,
                                       return_trajectory=True)
-        _ORACLE_CACHE[key] = (tape, traj)
+            # the SAME steps from the same x_t in float64: the rounding-free yardstick for pred_xstart (one forward of
+            # this model amplifies fp32 rounding by up to ~1e3 on the early steps of the 100-step schedule, where x_t is
+            # noise but t says "almost clean": the float32 oracle itself is up to 1e-3 away from this)
+            sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+            truth = []
+            x_in = tape[0]
+            for k in range(steps):
+                _, x0_64 = R.p_sample_step(lambda x, t: R.mdm_smpl_forward(sd64, x, t, cond.double(), faithful=False), tables, x_in.double(),
+                                           steps - 1 - k, tape[k + 1].double(), gt.double(), mask)
+                truth.append(x0_64)
+                x_in = traj[k][0]
+        _ORACLE_CACHE[key] = (tape, traj, truth)
     return _ORACLE_CACHE[key]
 
 
@@ -79,20 +90,31 @@ def test_config2_full_loop(eng, backend):
     b = S.make_smpl_batch(B=B, T=T)
     eng.bind(b["cond"], T)
     eng.init_diffusion(R.named_beta_schedule("cosine", steps))
-    tape, traj = _oracle_config2(key_sd, b, steps)
+    tape, traj, truth = _oracle_config2(key_sd, b, steps)
     gt, mask = torch.from_numpy(b["gt"]).cuda(), torch.from_numpy(b["mask"]).cuda()
     tape_d = tape.cuda()
-    # (1) teacher-forced: every step starts from the ORACLE's x_t
-    worst, worst_k = 0.0, -1
+    # (1) teacher-forced: every one of the 100 steps starts from the ORACLE's x_t.
+    #     sample x_{t-1}: 2e-4 against the oracle on every step.
+    #     pred_xstart: measured against the float64 evaluation of the same step; this implementation may not be further
+    #     from it than a small multiple of the float32 oracle's own distance (or 2e-4), and on (geometric) average over
+    #     the 100 steps not further than the float32 oracle.
+    worst, worst_k, e_gpu, e_f32 = 0.0, -1, [], []
     x_ref = tape[0]
     for k in range(steps):
         i = steps - 1 - k
         got, got0 = eng.p_sample(i, x_ref.cuda(), tape_d[k + 1], gt, mask)
-        e = max(rel(got, traj[k][0]), rel(got0, traj[k][1]))
+        e = rel(got, traj[k][0])
         if e > worst:
             worst, worst_k = e, k
+        e_gpu.append(rel(got0, truth[k]))
+        e_f32.append(rel(traj[k][1], truth[k]))
         x_ref = traj[k][0]
     assert worst < 2e-4, (worst, worst_k)
+    bad = [(k, a, c) for k, (a, c) in enumerate(zip(e_gpu, e_f32)) if a > max(2e-4, 5.0 * c)]
+    assert not bad, bad[:5]
+    assert max(e_gpu) < 2e-3
+    gmean = float(np.exp(np.mean(np.log(np.maximum(e_gpu, 1e-9)) - np.log(np.maximum(e_f32, 1e-9)))))
+    assert gmean < 2.0, gmean
     # (2) free-running, step by step (the p_sample chain is what the loop replays), curve against the oracle
     x = tape_d[0].clone()
     curve = []
@@ -102,7 +124,8 @@ def test_config2_full_loop(eng, backend):
     cut, self_curve = _cutoff()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "config2_curve_%s.json" % backend), "w") as f:
-        json.dump(dict(backend=backend, teacher_forced_worst=worst, teacher_forced_worst_step=worst_k, free_running_vs_oracle=curve,
+        json.dump(dict(backend=backend, teacher_forced_sample_worst=worst, teacher_forced_sample_worst_step=worst_k,
+                       teacher_forced_x0_vs_f64=e_gpu, oracle_f32_x0_vs_f64=e_f32, x0_error_ratio_geomean=gmean, free_running_vs_oracle=curve,
                        reference_f32_vs_f64=self_curve, cutoff_step=cut), f)
     bad = [(k, v) for k, v in enumerate(curve[:cut]) if v > 1e-3]
     assert not bad, ("free-running divergence above 1e-3 before the reference's own self-disagreement exceeds 1e-4", bad[:5], cut)
@@ -132,44 +155,67 @@ def _logging_denoised_fn(ctx, log):
     return fn
 
 
+@pytest.mark.parametrize("source", ["random", "ref"])
 @pytest.mark.parametrize("mode", ["step", "loop", "off"])
-def test_config3_loop_with_correction(eng, smplh_np, mode):
+def test_config3_loop_with_correction(eng, smplh_np, mode, source):
     """The product path of configs[2]: idb_p_sample_loop(correction=1) - gate (i <= 500 and i % 50 == 0), predict ->
     hook -> posterior with no re-inpainting, the (t/1000) blend - against the oracle loop with the restated hook, on a
-    52-step schedule (hook active at i = 50 and i = 0).  Decisions must agree exactly."""
+    52-step schedule (hook active at i = 50 and i = 0).
+      * decisions (condition / contact) of both hook steps: exact, for both weight sets;
+      * the fused loop equals the step-by-step composition of the single-step entry points (each pinned to the oracle
+        teacher-forced elsewhere in this file) bit for bit;
+      * final sample against the oracle at 1e-3 with the seeded random-init denoiser, whose chain is well conditioned
+        (its float32 and float64 oracle runs end 9e-7 apart).  With the shipped checkpoint the 52-step chain is chaotic
+        like configs[1]'s (float32 vs float64 ORACLE runs end 0.19 apart, profiles/r2_conditioning_probe.txt), so there
+        the final sample is only checked to be finite."""
     B, T, steps = 3, 30, 52
-    sd, psd = mdm_weights("smpl", "auto"), projector_weights("auto")
+    sd, psd = mdm_weights("smpl", source), projector_weights("auto")
     eng.load_denoiser(sd, "smpl")
     eng.load_body(smplh_np)
     eng.load_projector(psd, 10, 20)
     b = S.make_smpl_batch(B=B, T=T)
     eng.bind(b["cond"], T)
     eng.bind_correction(b["hand_pose"], b["betas"], b["obj_points"], past_len=10)
-    eng.init_diffusion(R.named_beta_schedule("cosine", steps))
+    betas = R.named_beta_schedule("cosine", steps)
+    eng.init_diffusion(betas)
     gt, mask, cond = torch.from_numpy(b["gt"]), torch.from_numpy(b["mask"]), torch.from_numpy(b["cond"])
     tape = torch.from_numpy(S.noise_tape(b["gt"].shape, steps))
-    key = ("c3", steps)
+    key = ("c3", steps, source)
     if key not in _ORACLE_CACHE:
         log = []
         ctx = _correction_ctx(b, smplh_np, psd)
+        fwd = lambda x, t: R.mdm_smpl_forward(sd, x, t, cond, faithful=False)
         with torch.no_grad():
-            ref = R.p_sample_loop(lambda x, t: R.mdm_smpl_forward(sd, x, t, cond, faithful=False), R.diffusion_tables(R.named_beta_schedule("cosine", steps)),
-                                  tape, gt, mask, denoised_fn=_logging_denoised_fn(ctx, log))
-            plain = R.p_sample_loop(lambda x, t: R.mdm_smpl_forward(sd, x, t, cond, faithful=False), R.diffusion_tables(R.named_beta_schedule("cosine", steps)),
-                                    tape, gt, mask)
+            ref = R.p_sample_loop(fwd, R.diffusion_tables(betas), tape, gt, mask, denoised_fn=_logging_denoised_fn(ctx, log))
+            plain = R.p_sample_loop(fwd, R.diffusion_tables(betas), tape, gt, mask)
         _ORACLE_CACHE[key] = (ref, plain, log)
     ref, plain, log = _ORACLE_CACHE[key]
     assert [t for t, _, _ in log] == [50, 0]
+    gtd, maskd, taped = gt.cuda(), mask.cuda(), tape.cuda()
     cond_log, contact_log = eng.correction_log(4)
-    got = eng.p_sample_loop(tape.cuda(), gt.cuda(), mask.cuda(), correction=True, use_graph=mode).cpu()
+    got = eng.p_sample_loop(taped, gtd, maskd, correction=True, use_graph=mode).cpu()
+    n_ok = 0
     for k, (_, c_ref, ct_ref) in enumerate(log):
         assert torch.equal(cond_log[k].cpu().bool(), c_ref), k
         assert torch.equal(contact_log[k].cpu().long(), ct_ref), k
-    assert int(cond_log[2:].sum()) == 0 and int(contact_log[2:].abs().sum()) == 0      # exactly two hook steps ran
+        n_ok += 1
+    assert n_ok == 2 and int(cond_log[2:].sum()) == 0 and int(contact_log[2:].abs().sum()) == 0      # exactly two hook steps ran
     eng.correction_log(0)
-    assert rel(got, ref) < 1e-3
-    if any(bool(c.any()) for _, c, _ in log):
-        assert rel(plain, ref) > 1e-3    # the hook changed the sample: the comparison above is not vacuous
+    # the same loop composed from the single-step entry points of the C ABI
+    x = taped[0].clone()
+    for k, i in enumerate(reversed(range(steps))):
+        if i <= 500 and i % 50 == 0:
+            x0 = eng.p_sample_predict(i, x, gtd, maskd)
+            eng.correction_apply(x0, gtd, i)
+            x = eng.p_sample_finish(i, x0, x, taped[k + 1])
+        else:
+            x, _ = eng.p_sample(i, x, taped[k + 1], gtd, maskd)
+    assert torch.equal(got, x.cpu())
+    assert torch.isfinite(got).all()
+    if source == "random":
+        assert rel(got, ref) < 1e-3
+        if any(bool(c.any()) for _, c, _ in log):
+            assert rel(plain, ref) > 1e-3    # the hook changed the sample: the comparison above is not vacuous
     # at i = 0 the sample IS the corrected pred_xstart (coef1 = 1, coef2 = 0, sigma = 0): where condition holds the object's
     # PAST frames were replaced by the projector blend and NOT re-inpainted (gaussian_diffusion.py:354-376)
     c0 = log[-1][1]
@@ -219,11 +265,11 @@ SMPL_ARGS = dict(embedding_dim=256, smpl_dim=132, use_pointnet2=1, dropout=0.0, 
                  sigma_small=True, weight_v=0.2)
 
 
-def _mirror_model(steps):
+def _mirror_model(steps, source="auto"):
     from interdiff_b200.model.diffusion_smpl import create_model_and_diffusion
     args = Namespace(**{**SMPL_ARGS, "diffusion_steps": steps})
     model, diffusion = create_model_and_diffusion(args)
-    sd = encoder_weights("auto")
+    sd = encoder_weights(source)
     own = model.state_dict()
     model.load_state_dict({k: (sd[k].reshape(own[k].shape) if k in sd else v) for k, v in own.items()})
     return model.cuda().eval(), diffusion, {k: v for k, v in model.state_dict().items()}
@@ -299,7 +345,9 @@ def test_veneer_sample_once_proj(smplh_np, steps):
     from interdiff_b200.libsmpl.smplpytorch.pytorch.smpl_layer import SMPL_Layer
     from interdiff_b200.sampling import FusedCorrection, draw_tape
     B, T, past = 3, 30, 10
-    model, diffusion, msd = _mirror_model(steps)
+    # 52 steps: seeded random-init weights (a well-conditioned chain, so the end-to-end oracle comparison below means
+    # something; with the shipped checkpoint a 52-step chain amplifies rounding to O(0.1), see test_config3_loop_with_correction)
+    model, diffusion, msd = _mirror_model(steps, "auto" if steps == 12 else "random")
     proj, psd = _mirror_projector()
     smpl = SMPL_Layer.from_arrays(smplh_np).cuda()
     b = S.make_smpl_batch(B=B, T=T)
@@ -488,3 +536,27 @@ def test_engine_on_non_current_device():
     assert torch.equal(outs[0], outs[1])
     e0.close()
     e1.close()
+
+
+def test_batch_slices_bit_identical(eng):
+    """multi-GPU runs slice ONE global batch (contiguous B/G samples per rank, noise keyed by the global sample
+    index).  A sample's trajectory must not depend on which other samples share its batch: the two halves of a B=64 batch
+    (M = 1920 rows: 256-column GEMM tiles) sampled as B=32 batches (M = 960: 128-column tiles) reproduce the full-batch
+    result bit for bit, and so do B=8 slices."""
+    sd = mdm_weights("smpl", "auto")
+    eng.load_denoiser(sd, "smpl")
+    B, T, steps = 64, 30, 10
+    b = S.make_smpl_batch(B=B, T=T)
+    eng.init_diffusion(R.named_beta_schedule("cosine", steps))
+    tape = torch.from_numpy(S.noise_tape(b["gt"].shape, steps)).cuda()
+    gt, mask = torch.from_numpy(b["gt"]).cuda(), torch.from_numpy(b["mask"]).cuda()
+    eng.bind(b["cond"], T)
+    full = eng.p_sample_loop(tape, gt, mask).clone()
+    for G in (2, 8):
+        n = B // G
+        parts = []
+        for r in range(G):
+            sl = slice(r * n, (r + 1) * n)
+            eng.bind(np.ascontiguousarray(b["cond"][:, sl]), T)
+            parts.append(eng.p_sample_loop(tape[:, sl].contiguous(), gt[sl].contiguous(), mask[sl].contiguous()).clone())
+        assert torch.equal(torch.cat(parts, dim=0), full), G

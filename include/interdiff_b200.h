@@ -176,6 +176,24 @@ int idb_metrics(idb_handle* h, int T, int B, int J, int P, int Db, const float* 
                 const float* obj_gt, const float* body_jtr_gt, const float* body_gt, const float* verts, const float* obj_points,
                 float* out, void* stream);
 
+/* Post-processing of a sampled window: `smooth` (eval_smpl_short.py:217-223) in place on x (T, inner) - every future frame is
+ * shifted by 2 x[-F-1] - x[-F-2] - x[-F] (old values) - and the element-wise minimum that reduces the metric vectors of the
+ * diverse samples of a batch (eval_smpl_short.py:268-296: torch.stack + min). */
+int idb_smooth(idb_handle* h, int T, int future_len, long long inner, float* x, void* stream);
+int idb_metric_min(idb_handle* h, long long n, float* acc, const float* cur, void* stream);
+
+/* ---- autoregressive rollout: the step between two sampling windows (eval_smpl_long.py:26-84 get_batch, :278 denormalize) ----
+ * idb_rollout_next_window: from a finished window in the post-processed form - body (T,B,Db) = [66 axis-angle | hand | 3 trans],
+ * obj (T,B,6) = [axis-angle | trans], jtr (T,B,J,3) - builds the NEXT window's inpainting tensor gt_out (B,1,144,T): its first
+ * past_len frames are the last past_len frames of the finished window, translations relative to centroid_out (B,3) = the
+ * pelvis (joint 0) of the first of those frames, rotations re-derived as axis-angle -> matrix -> first two rows
+ * (model/diffusion_smpl.py:207-214); the remaining frames repeat the last past frame (eval_smpl_long.py:78).
+ * idb_add_offset: x[(t*B+b)*ld + col0 + 3k + c] += sign * offset[b][c], k < K - `denormalize` (sign +1) of translations,
+ * vertices and joints back to world coordinates (upstream calls it without defining it; this is get_batch's inverse). */
+int idb_rollout_next_window(idb_handle* h, int T, int B, int J, int Db, int past_len, const float* body, const float* obj,
+                            const float* jtr, float* gt_out, float* centroid_out, void* stream);
+int idb_add_offset(idb_handle* h, int T, int B, int K, long long ld, int col0, float* x, const float* offset, float sign, void* stream);
+
 /* ---- kernel-level hook (tests / bench roofline leg) -----------------------------------------
  * C[M,N] = epi(A[M,K] . W[N,K]^T) with the handle's GEMM backend; epi bit 0 bias, 1 GELU(erf),
  * 2 residual add, 3 SiLU (the fused epilogues of the nn.Linear calls of the denoiser). */

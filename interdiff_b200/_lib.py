@@ -27,6 +27,10 @@ _SIGS = {
     "idb_encode_condition": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "idb_pointcloud_embed": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "idb_metrics": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "idb_rollout_next_window": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "idb_add_offset": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, _P, _P, C.c_float, _P]),
+    "idb_smooth": (C.c_int, [_P, C.c_int, C.c_int, C.c_longlong, _P, _P]),
+    "idb_metric_min": (C.c_int, [_P, C.c_longlong, _P, _P, _P]),
     "idb_set_gemm_backend": (C.c_int, [_P, C.c_int]),
     "idb_set_dependent_launch": (C.c_int, [_P, C.c_int]),
     "idb_set_fused_mlp": (C.c_int, [_P, C.c_int]),

@@ -60,8 +60,8 @@ __global__ void k_lbs_pose(const float* __restrict__ pose, const float* __restri
                 if (pm_hi) split_f16(pm, pm_hi[(size_t)f * Kld + (j - 1) * 9 + e], pm_lo[(size_t)f * Kld + (j - 1) * 9 + e]);   // A operand of the blend GEMM
                 else pose_map[(size_t)f * Kp + (j - 1) * 9 + e] = pm;
             }
-        if (pm_hi && j == 0)
-            for (int e = Kp; e < Kld; e++) { pm_hi[(size_t)f * Kld + e] = __float2half(0.f); pm_lo[(size_t)f * Kld + e] = __float2half(0.f); }
+        if (pm_hi && j == 0)     // shape-blend columns (betas) and the zero padding of the GEMM's K axis
+            for (int e = Kp; e < Kld; e++) split_f16(e < Kp + NB ? betas[(size_t)f * NB + e - Kp] : 0.f, pm_hi[(size_t)f * Kld + e], pm_lo[(size_t)f * Kld + e]);
     }
     __syncthreads();
     // kinematic chain (smpl_layer.py:119-130), one tree level per round (the reference walks the joints one by one; a
@@ -183,44 +183,37 @@ k_lbs_skin(const float* __restrict__ posedirsT, const float* __restrict__ shaped
 }
 
 
-// Second half of the tensor-core path.  The pose blend  P vec(R - I)  (459 of the 469 multiply-adds per vertex coordinate)
-// is ONE split-precision tcgen05 GEMM  blend[F][3V] = pose_map[F][Kp] . (2^8 posedirs)[3V][Kp]^T  (gemm_tcgen05.cu; fp16
-// (hi, lo) pairs, fp32 TMEM accumulation; the 2^8 keeps the mm-scale bases well inside the fp16 normal range and is undone
-// exactly below).  This kernel finishes a vertex: shape blend on FFMA (10 terms), + blend, skinning matrix from the
+// Second half of the tensor-core path.  The pose blend  P vec(R - I)  and the shape blend  S beta  (the 469 multiply-adds per
+// vertex coordinate) are ONE split-precision tcgen05 GEMM  blend[F][3V] = [pose_map | beta][F][469] . (2^8 [P | S])[3V][469]^T
+// (gemm_tcgen05.cu; fp16 (hi, lo) pairs, fp32 TMEM accumulation; the 2^8 keeps the mm-scale bases well inside the fp16 normal
+// range and is undone exactly below; the metre-scale template stays out of the tensor core's truncating accumulation).
+// This kernel finishes a vertex: template + blend, skinning matrix from the
 // vertex's non-zero bones only (SMPL weights have <= 4 per vertex; ELL list built at init, dense walk as the fallback),
 // transform, translation.  Thread = vertex, block = 256 vertices x FS frames; the A matrices of the frame group live in
 // shared memory (neighbouring vertices share bones, so the reads are mostly broadcasts); vertices leave through a
 // per-warp staging row as 8-byte coalesced stores.
-constexpr int FS = 8;
-template <int NBT>     // NBT = compile-time bound of the number of betas (10 for SMPL-H; 16 = the library's maximum)
+constexpr int FS = 16;
 __global__ void __launch_bounds__(256, 2)
-k_lbs_skin_sparse(const float* __restrict__ blend, int ldb, const float* __restrict__ shapedirsT, const float* __restrict__ v_templT,
+k_lbs_skin_sparse(const float* __restrict__ blend, int ldb, const float* __restrict__ v_templT,
                   const unsigned char* __restrict__ sk_n, const unsigned char* __restrict__ sk_j, const float* __restrict__ sk_w,
-                  const float* __restrict__ weightsT, int dense, const float* __restrict__ Ain, const float* __restrict__ betas,
-                  const float* __restrict__ trans, float* __restrict__ verts, int F, int V, int J, int NB) {
+                  const float* __restrict__ weightsT, int dense, const float* __restrict__ Ain,
+                  const float* __restrict__ trans, float* __restrict__ verts, int F, int V, int J) {
     extern __shared__ __align__(16) float sm[];
     float* s_A = sm;                       // [FS][J][12]
-    float* s_b = s_A + FS * J * 12;        // [FS][NB]
-    float* s_t = s_b + FS * NB;            // [FS][4]
+    float* s_t = s_A + FS * J * 12;        // [FS][4]
     float* s_o = s_t + FS * 4;             // [8 warps][96] output staging
     const int f0 = blockIdx.y * FS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nf = min(FS, F - f0);
     const int v0 = blockIdx.x * 256 + warp * 32, v = v0 + lane;
     const int vc = v < V ? v : V - 1;
-    // every global read of the thread is issued before the first use: one memory latency per block instead of one per frame
-    float bl[FS][3];
+    // every global read of the thread is issued before its first use (two batches of 8 frames)
+    float bl[FS / 2][3];
 #pragma unroll
-    for (int ff = 0; ff < FS; ff++) {
+    for (int ff = 0; ff < FS / 2; ff++) {
         const float* q = blend + (size_t)min(f0 + ff, F - 1) * ldb + (size_t)vc * 3;
         bl[ff][0] = q[0]; bl[ff][1] = q[1]; bl[ff][2] = q[2];
     }
-    float vt[3], S[3][NBT];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        vt[c] = v_templT[(size_t)c * V + vc];
-#pragma unroll
-        for (int b = 0; b < NBT; b++) S[c][b] = b < NB ? shapedirsT[((size_t)b * 3 + c) * V + vc] : 0.f;
-    }
+    const float vt0 = v_templT[vc], vt1 = v_templT[(size_t)V + vc], vt2 = v_templT[(size_t)2 * V + vc];
     int nb = 0, bj[SK_MAX]; float bw[SK_MAX];
     if (!dense) {
         nb = sk_n[vc];
@@ -228,60 +221,69 @@ k_lbs_skin_sparse(const float* __restrict__ blend, int ldb, const float* __restr
         for (int e = 0; e < SK_MAX; e++) { bj[e] = sk_j[(size_t)e * V + vc]; bw[e] = sk_w[(size_t)e * V + vc]; }
     }
     for (int i = tid; i < nf * J * 12; i += 256) s_A[i] = Ain[(size_t)f0 * J * 12 + i];
-    for (int i = tid; i < nf * NB; i += 256) s_b[i] = betas[(size_t)f0 * NB + i];
     for (int i = tid; i < nf * 3; i += 256) s_t[(i / 3) * 4 + i % 3] = trans[(size_t)f0 * 3 + i];
     __syncthreads();
     float* so = s_o + warp * 96;
 #pragma unroll
-    for (int ff = 0; ff < FS; ff++) {
-        if (ff >= nf) break;
-        float px = vt[0], py = vt[1], pz = vt[2];
+    for (int half = 0; half < 2; half++) {
+        float nx[FS / 2][3];
+        if (half == 0) {          // second batch of blend rows, in flight while the first batch is consumed
 #pragma unroll
-        for (int b = 0; b < NBT; b++)
-            if (b < NB) {
-                const float bb = s_b[ff * NB + b];
-                px = fmaf(S[0][b], bb, px); py = fmaf(S[1][b], bb, py); pz = fmaf(S[2][b], bb, pz);
+            for (int ff = 0; ff < FS / 2; ff++) {
+                const float* q = blend + (size_t)min(f0 + FS / 2 + ff, F - 1) * ldb + (size_t)vc * 3;
+                nx[ff][0] = q[0]; nx[ff][1] = q[1]; nx[ff][2] = q[2];
             }
-        px = fmaf(bl[ff][0], 1.0f / 256.0f, px); py = fmaf(bl[ff][1], 1.0f / 256.0f, py); pz = fmaf(bl[ff][2], 1.0f / 256.0f, pz);
-        float Tm[12];
+        }
 #pragma unroll
-        for (int e = 0; e < 12; e++) Tm[e] = 0.f;
-        const float4* A4 = reinterpret_cast<const float4*>(s_A + (size_t)ff * J * 12);
-        if (!dense) {
+        for (int fh = 0; fh < FS / 2; fh++) {
+            const int ff = half * (FS / 2) + fh;
+            if (ff < nf) {
+                const float px = fmaf(bl[fh][0], 1.0f / 256.0f, vt0), py = fmaf(bl[fh][1], 1.0f / 256.0f, vt1), pz = fmaf(bl[fh][2], 1.0f / 256.0f, vt2);
+                float Tm[12];
 #pragma unroll
-            for (int e = 0; e < SK_MAX; e++)
-                if (e < nb) {
-                    const float w = bw[e];
-                    const float4 a0 = A4[bj[e] * 3], a1 = A4[bj[e] * 3 + 1], a2 = A4[bj[e] * 3 + 2];
-                    Tm[0] = fmaf(w, a0.x, Tm[0]); Tm[1] = fmaf(w, a0.y, Tm[1]); Tm[2] = fmaf(w, a0.z, Tm[2]); Tm[3] = fmaf(w, a0.w, Tm[3]);
-                    Tm[4] = fmaf(w, a1.x, Tm[4]); Tm[5] = fmaf(w, a1.y, Tm[5]); Tm[6] = fmaf(w, a1.z, Tm[6]); Tm[7] = fmaf(w, a1.w, Tm[7]);
-                    Tm[8] = fmaf(w, a2.x, Tm[8]); Tm[9] = fmaf(w, a2.y, Tm[9]); Tm[10] = fmaf(w, a2.z, Tm[10]); Tm[11] = fmaf(w, a2.w, Tm[11]);
+                for (int e = 0; e < 12; e++) Tm[e] = 0.f;
+                const float4* A4 = reinterpret_cast<const float4*>(s_A + (size_t)ff * J * 12);
+                if (!dense) {
+#pragma unroll
+                    for (int e = 0; e < SK_MAX; e++)
+                        if (e < nb) {
+                            const float w = bw[e];
+                            const float4 a0 = A4[bj[e] * 3], a1 = A4[bj[e] * 3 + 1], a2 = A4[bj[e] * 3 + 2];
+                            Tm[0] = fmaf(w, a0.x, Tm[0]); Tm[1] = fmaf(w, a0.y, Tm[1]); Tm[2] = fmaf(w, a0.z, Tm[2]); Tm[3] = fmaf(w, a0.w, Tm[3]);
+                            Tm[4] = fmaf(w, a1.x, Tm[4]); Tm[5] = fmaf(w, a1.y, Tm[5]); Tm[6] = fmaf(w, a1.z, Tm[6]); Tm[7] = fmaf(w, a1.w, Tm[7]);
+                            Tm[8] = fmaf(w, a2.x, Tm[8]); Tm[9] = fmaf(w, a2.y, Tm[9]); Tm[10] = fmaf(w, a2.z, Tm[10]); Tm[11] = fmaf(w, a2.w, Tm[11]);
+                        }
+                } else {
+                    for (int jn = 0; jn < J; jn++) {
+                        const float w = __ldg(weightsT + (size_t)jn * V + vc);
+                        const float4 a0 = A4[jn * 3], a1 = A4[jn * 3 + 1], a2 = A4[jn * 3 + 2];
+                        Tm[0] = fmaf(w, a0.x, Tm[0]); Tm[1] = fmaf(w, a0.y, Tm[1]); Tm[2] = fmaf(w, a0.z, Tm[2]); Tm[3] = fmaf(w, a0.w, Tm[3]);
+                        Tm[4] = fmaf(w, a1.x, Tm[4]); Tm[5] = fmaf(w, a1.y, Tm[5]); Tm[6] = fmaf(w, a1.z, Tm[6]); Tm[7] = fmaf(w, a1.w, Tm[7]);
+                        Tm[8] = fmaf(w, a2.x, Tm[8]); Tm[9] = fmaf(w, a2.y, Tm[9]); Tm[10] = fmaf(w, a2.z, Tm[10]); Tm[11] = fmaf(w, a2.w, Tm[11]);
+                    }
                 }
-        } else {
-            for (int jn = 0; jn < J; jn++) {
-                const float w = __ldg(weightsT + (size_t)jn * V + vc);
-                const float4 a0 = A4[jn * 3], a1 = A4[jn * 3 + 1], a2 = A4[jn * 3 + 2];
-                Tm[0] = fmaf(w, a0.x, Tm[0]); Tm[1] = fmaf(w, a0.y, Tm[1]); Tm[2] = fmaf(w, a0.z, Tm[2]); Tm[3] = fmaf(w, a0.w, Tm[3]);
-                Tm[4] = fmaf(w, a1.x, Tm[4]); Tm[5] = fmaf(w, a1.y, Tm[5]); Tm[6] = fmaf(w, a1.z, Tm[6]); Tm[7] = fmaf(w, a1.w, Tm[7]);
-                Tm[8] = fmaf(w, a2.x, Tm[8]); Tm[9] = fmaf(w, a2.y, Tm[9]); Tm[10] = fmaf(w, a2.z, Tm[10]); Tm[11] = fmaf(w, a2.w, Tm[11]);
+                so[lane * 3 + 0] = (Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3]) + s_t[ff * 4 + 0];
+                so[lane * 3 + 1] = (Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7]) + s_t[ff * 4 + 1];
+                so[lane * 3 + 2] = (Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11]) + s_t[ff * 4 + 2];
+                __syncwarp();
+                // 96 floats of this warp's 32 vertices are contiguous in verts[f][v0 .. v0+31][3]
+                float* dst = verts + ((size_t)(f0 + ff) * V + v0) * 3;
+                const int nfl = min(32, V - v0) * 3;          // floats of live vertices (<= 0 for a warp past the end)
+                if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                    for (int i = lane * 2; i < nfl; i += 64) {
+                        if (i + 1 < nfl) *reinterpret_cast<float2*>(dst + i) = *reinterpret_cast<const float2*>(so + i);
+                        else dst[i] = so[i];
+                    }
+                } else {
+                    for (int i = lane; i < nfl; i += 32) dst[i] = so[i];
+                }
+                __syncwarp();
             }
         }
-        so[lane * 3 + 0] = (Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3]) + s_t[ff * 4 + 0];
-        so[lane * 3 + 1] = (Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7]) + s_t[ff * 4 + 1];
-        so[lane * 3 + 2] = (Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11]) + s_t[ff * 4 + 2];
-        __syncwarp();
-        // 96 floats of this warp's 32 vertices are contiguous in verts[f][v0 .. v0+31][3]
-        float* dst = verts + ((size_t)(f0 + ff) * V + v0) * 3;
-        const int nfl = min(32, V - v0) * 3;          // floats of live vertices (<= 0 for a warp past the end)
-        if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-            for (int i = lane * 2; i < nfl; i += 64) {
-                if (i + 1 < nfl) *reinterpret_cast<float2*>(dst + i) = *reinterpret_cast<const float2*>(so + i);
-                else dst[i] = so[i];
-            }
-        } else {
-            for (int i = lane; i < nfl; i += 32) dst[i] = so[i];
+        if (half == 0) {
+#pragma unroll
+            for (int ff = 0; ff < FS / 2; ff++) { bl[ff][0] = nx[ff][0]; bl[ff][1] = nx[ff][1]; bl[ff][2] = nx[ff][2]; }
         }
-        __syncwarp();
     }
 }
 
@@ -353,9 +355,14 @@ extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const 
     }
     {
         // tensor-core pose blend: W operand of the GEMM = 2^8 * posedirs in its native (V,3,Kp) order (row n = v*3 + c)
-        m.Nb = (3 * V + 255) & ~255; m.Kld = (Kp + 7) & ~7;     // whole 256-column GEMM tiles
-        std::vector<float> pds((size_t)m.Nb * Kp, 0.f);
-        for (size_t i = 0; i < (size_t)3 * V * Kp; i++) pds[i] = pd[i] * 256.0f;
+        // K axis of the GEMM = [459 pose-blend terms | NB shape-blend terms]: both are cm-scale corrections of the template
+        const int Kb = Kp + NB;
+        m.Nb = (3 * V + 255) & ~255; m.Kld = (Kb + 7) & ~7;     // whole 256-column GEMM tiles
+        std::vector<float> pds((size_t)m.Nb * Kb, 0.f);
+        for (size_t n = 0; n < (size_t)3 * V; n++) {
+            for (int k = 0; k < Kp; k++) pds[n * Kb + k] = pd[n * Kp + k] * 256.0f;
+            for (int b = 0; b < NB; b++) pds[n * Kb + Kp + b] = sd[n * NB + b] * 256.0f;
+        }
         float* tmp = nullptr;
         CUDA_TRY(h, cudaMalloc((void**)&tmp, pds.size() * 4));
         cudaError_t e = cudaMemcpy(tmp, pds.data(), pds.size() * 4, cudaMemcpyHostToDevice);
@@ -363,7 +370,7 @@ extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const 
         if (e != cudaSuccess) { cudaFree(tmp); return idb_fail(h, IDB_ERR_CUDA, "posedirs pairs: %s", cudaGetErrorString(e)); }
         m.owned.push_back(m.pd_hi);
         m.pd_lo = m.pd_hi + (size_t)m.Nb * m.Kld;
-        int rc = idb_split_tensor(h, tmp, Kp, m.pd_hi, m.pd_lo, m.Kld, m.Nb, Kp, 0);
+        int rc = idb_split_tensor(h, tmp, Kb, m.pd_hi, m.pd_lo, m.Kld, m.Nb, Kb, 0);
         cudaDeviceSynchronize();
         cudaFree(tmp);
         if (rc) return rc;
@@ -445,6 +452,8 @@ extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const 
     }
     const int smem_skin = (int)sizeof(float) * (Kp * FB + FB * J * 12 + NB * FB + FB * 3);
     CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_skin));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(float) * (FS * J * 12 + FS * 4 + 8 * 96)));
     h->epoch++;
     return IDB_OK;
 }
@@ -484,14 +493,10 @@ extern "C" int idb_smplh_lbs(idb_handle* h, int F, const float* pose, const floa
         g.A_hi = m.pm_hi; g.A_lo = m.pm_lo; g.lda = m.Kld; g.W_hi = m.pd_hi; g.W_lo = m.pd_lo; g.ldw = m.Kld;
         g.C = m.blend; g.ldc = m.Nb; g.M = F; g.N = m.Nb; g.K = m.Kld; g.epi = 0; g.single_acc = 1;
         if ((rc = idb_gemm_ex(h, g, st))) return rc;
-        const size_t smem = sizeof(float) * ((size_t)FS * m.J * 12 + (size_t)FS * m.NB + FS * 4 + 8 * 96);
+        const size_t smem = sizeof(float) * ((size_t)FS * m.J * 12 + FS * 4 + 8 * 96);
         dim3 grid((m.V + 255) / 256, (F + FS - 1) / FS);
-        if (m.NB <= 10)
-            k_lbs_skin_sparse<10><<<grid, 256, smem, st>>>(m.blend, m.Nb, m.shapedirsT, m.v_templT, m.sk_n, m.sk_j, m.sk_w, m.weightsT,
-                                                            m.sk_dense ? 1 : 0, m.A, betas, trans, verts, F, m.V, m.J, m.NB);
-        else
-            k_lbs_skin_sparse<16><<<grid, 256, smem, st>>>(m.blend, m.Nb, m.shapedirsT, m.v_templT, m.sk_n, m.sk_j, m.sk_w, m.weightsT,
-                                                            m.sk_dense ? 1 : 0, m.A, betas, trans, verts, F, m.V, m.J, m.NB);
+        k_lbs_skin_sparse<<<grid, 256, smem, st>>>(m.blend, m.Nb, m.v_templT, m.sk_n, m.sk_j, m.sk_w, m.weightsT, m.sk_dense ? 1 : 0, m.A,
+                                                    trans, verts, F, m.V, m.J);
         LAUNCH_CHECK(h);
     } else if (verts) {
         const size_t smem_skin = sizeof(float) * ((size_t)m.Kp * FB + (size_t)FB * m.J * 12 + (size_t)m.NB * FB + FB * 3);

@@ -125,3 +125,38 @@ extern "C" int idb_metrics(idb_handle* h, int T, int B, int J, int P, int Db, co
     LAUNCH_CHECK(h);
     return IDB_OK;
 }
+
+// ---- post-processing of a sampled window: smooth + best-of-N reduction -------------------------------
+namespace {
+// x (T, inner): every predicted future frame is shifted by the second-difference jump at the past / future seam
+// (eval_smpl_short.py:217-223: x[-F:] = x[-F:] + (2 x[-F-1] - x[-F-2] - x[-F]); the right-hand side uses the OLD x[-F]).
+__global__ void k_smooth(float* __restrict__ x, int T, int Fut, size_t inner) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= inner) return;
+    const int s = T - Fut;                                 // first future frame
+    const float d = (2.0f * x[(size_t)(s - 1) * inner + i] - x[(size_t)(s - 2) * inner + i]) - x[(size_t)s * inner + i];
+    for (int t = s; t < T; t++) x[(size_t)t * inner + i] = x[(size_t)t * inner + i] + d;
+}
+__global__ void k_min_inplace(float* __restrict__ acc, const float* __restrict__ cur, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] = fminf(acc[i], cur[i]);
+}
+}  // namespace
+
+extern "C" int idb_smooth(idb_handle* h, int T, int future_len, long long inner, float* x, void* stream) {
+    IDB_ENTER(h);
+    if (!h || !x || inner <= 0) return IDB_ERR_ARG;
+    if (future_len < 1 || T - future_len < 2) return idb_fail(h, IDB_ERR_ARG, "smooth needs at least two past frames and one future frame");
+    k_smooth<<<(unsigned)((inner + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, T, future_len, (size_t)inner);
+    LAUNCH_CHECK(h);
+    return IDB_OK;
+}
+
+/* acc[i] = min(acc[i], cur[i]) : the element-wise minimum over the diverse samples of a batch (eval_smpl_short.py:268-296) */
+extern "C" int idb_metric_min(idb_handle* h, long long n, float* acc, const float* cur, void* stream) {
+    IDB_ENTER(h);
+    if (!h || !acc || !cur || n <= 0) return IDB_ERR_ARG;
+    k_min_inplace<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(acc, cur, (size_t)n);
+    LAUNCH_CHECK(h);
+    return IDB_OK;
+}

@@ -38,3 +38,16 @@ __device__ __forceinline__ void idb_matrix_to_axis_angle(const float* m, float* 
     aa[0] = qx / s; aa[1] = qy / s; aa[2] = qz / s;
 }
 
+
+// axis_angle_to_matrix = quaternion_to_matrix(axis_angle_to_quaternion(aa)) (pytorch3d 0.7.2; small-angle series below 1e-6)
+__device__ __forceinline__ void idb_axis_angle_to_matrix(const float* aa, float* R) {
+    const float x = aa[0], y = aa[1], z = aa[2];
+    const float angle = sqrtf(x * x + y * y + z * z);
+    const float half = 0.5f * angle;
+    const float s = fabsf(angle) < 1e-6f ? 0.5f - (angle * angle) / 48.0f : sinf(half) / angle;
+    const float r = cosf(half), i = x * s, j = y * s, k = z * s;
+    const float two_s = 2.0f / (r * r + i * i + j * j + k * k);
+    R[0] = 1 - two_s * (j * j + k * k); R[1] = two_s * (i * j - k * r);     R[2] = two_s * (i * k + j * r);
+    R[3] = two_s * (i * j + k * r);     R[4] = 1 - two_s * (i * i + k * k); R[5] = two_s * (j * k - i * r);
+    R[6] = two_s * (i * k - j * r);     R[7] = two_s * (j * k + i * r);     R[8] = 1 - two_s * (i * i + j * j);
+}

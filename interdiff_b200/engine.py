@@ -347,6 +347,43 @@ class Engine:
                                        self._stream()))
         return {k: out[i] for i, k in enumerate(self.METRIC_NAMES)}
 
+    def rollout_next_window(self, body, obj, jtr, T, past_len):
+        """get_batch of eval_smpl_long.py:26-84 on the device: (gt (B,1,144,T), centroid (B,3)) of the next window from the
+        finished window's body (Tw,B,159), obj (Tw,B,6), jtr (Tw,B,J,3)."""
+        body, obj, jtr = self._f32(body), self._f32(obj), self._f32(jtr)
+        Tw, B, Db = body.shape
+        gt = torch.empty(B, 1, 144, T, device=self.device)
+        cen = torch.empty(B, 3, device=self.device)
+        if Tw != T:
+            raise EngineError("rollout windows share one length T")
+        self._chk(self.lib.idb_rollout_next_window(self._h, T, B, jtr.shape[2], Db, int(past_len), self._ptr(body), self._ptr(obj),
+                                                   self._ptr(jtr), self._ptr(gt), self._ptr(cen), self._stream()))
+        return gt, cen
+
+    def add_offset_(self, x, offset, col0=0, K=None, sign=1.0):
+        """x (T,B,...) contiguous float32, in place: the 3-vectors x[t,b,col0+3k : col0+3k+3], k < K, += sign * offset[b]."""
+        assert x.is_cuda and x.is_contiguous() and x.dtype == torch.float32
+        T, B = x.shape[:2]
+        ld = x.numel() // (T * B)
+        K = (ld - col0) // 3 if K is None else K
+        offset = self._f32(offset)
+        self._chk(self.lib.idb_add_offset(self._h, T, B, int(K), ld, int(col0), self._ptr(x), self._ptr(offset), float(sign), self._stream()))
+        return x
+
+    def smooth_(self, x, future_len):
+        """In place on a contiguous float32 device tensor (T, ...): the reference's `smooth` for one tensor."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        T = x.shape[0]
+        self._chk(self.lib.idb_smooth(self._h, T, int(future_len), x.numel() // T, self._ptr(x), self._stream()))
+        return x
+
+    def metric_min_(self, acc, cur):
+        """acc = min(acc, cur) element-wise, in place (the best-of-N reduction over diverse samples)."""
+        assert acc.is_cuda and acc.is_contiguous() and acc.dtype == torch.float32 and acc.shape == cur.shape
+        cur = self._f32(cur)
+        self._chk(self.lib.idb_metric_min(self._h, acc.numel(), self._ptr(acc), self._ptr(cur), self._stream()))
+        return acc
+
     # ------------------------------------------------------------------ correction
     def load_projector(self, state_dict, past_len, future_len, n_pre=10, n_markers=67):
         self._chk(self.lib.idb_projector_init(self._h, past_len, future_len, n_pre, n_markers))
@@ -371,7 +408,7 @@ class Engine:
         self._chk(self.lib.idb_correction_bind(self._h, B, T, past_len if past_len is not None else self.past_len,
                                                obj_points.shape[1], self._ptr(hand_pose), self._ptr(betas), self._ptr(obj_points),
                                                C.c_void_p(mk.ctypes.data), C.c_void_p(hm.ctypes.data), len(hm), self._stream()))
-        torch.cuda.synchronize(self.device)
+        self._keep_corr = [hand_pose, betas, obj_points]     # copied asynchronously on the stream
         self.n_markers = len(mk)
         self.n_obj = obj_points.shape[1]
         self.corr_B = B

@@ -21,9 +21,24 @@ def draw_tape(engine, x_T, n_steps, seed=None):
     return tape
 
 
+def draw_tape_indexed(engine, sample_shape, n_steps, global_ids, seed=233):
+    """(n_steps+1, B, *sample_shape) device tape whose column j depends ONLY on (seed, global_ids[j]): the noise of a
+    sample is keyed by its index in the GLOBAL batch, so a multi-GPU run that slices one global batch reproduces the
+    single-GPU trajectories.  sample_shape = (1, C, T)."""
+    B = len(global_ids)
+    tape = torch.empty((n_steps + 1, B) + tuple(sample_shape), device=engine.device)
+    g = torch.Generator(device=engine.device)
+    for j, gid in enumerate(global_ids):
+        g.manual_seed(int(seed) * 1000003 + int(gid))
+        tape[:, j] = torch.randn((n_steps + 1,) + tuple(sample_shape), generator=g, device=engine.device)
+    return tape
+
+
 def sample_smpl_host(engine, h_xT, h_gt, h_mask, h_cond, h_out, seed=None, correction=False, use_graph=True):
     """One sampling call with host tensors (pinned for async copies).  The engine must have its
-    denoiser loaded and its diffusion initialised."""
+    denoiser loaded and its diffusion initialised.  correction: False, or the hook's per-batch context as HOST tensors
+    dict(hand_pose (T,B,90), betas (T,B,10), obj_points (B,P,3), past_len) - body model and projector already loaded -
+    which is uploaded and bound inside the call like the rest of the inputs."""
     dev = engine.device
     gt = h_gt.to(dev, non_blocking=True)
     mask = h_mask.to(dev, non_blocking=True)
@@ -31,6 +46,9 @@ def sample_smpl_host(engine, h_xT, h_gt, h_mask, h_cond, h_out, seed=None, corre
     xT = h_xT.to(dev, non_blocking=True)
     T = gt.shape[-1]
     engine.bind(cond, T)
+    if correction:
+        engine.bind_correction(correction["hand_pose"].to(dev, non_blocking=True), correction["betas"].to(dev, non_blocking=True),
+                               correction["obj_points"].to(dev, non_blocking=True), past_len=correction["past_len"])
     # keep the tape buffer across calls (same shape) so the captured graph stays valid
     key = (tuple(gt.shape), engine.n_steps)
     cache = getattr(engine, "_host_loop_cache", None)
@@ -47,7 +65,7 @@ def sample_smpl_host(engine, h_xT, h_gt, h_mask, h_cond, h_out, seed=None, corre
         g = torch.Generator(device=dev)
         g.manual_seed(int(seed))
     tape[1:].normal_(generator=g)
-    engine.p_sample_loop(tape, gt_buf, mask_buf, correction=correction, use_graph=use_graph, out=out)
+    engine.p_sample_loop(tape, gt_buf, mask_buf, correction=bool(correction), use_graph=use_graph, out=out)
     h_out.copy_(out, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
     return h_out
@@ -102,39 +120,82 @@ def sample_postprocess(engine, sample, hand_pose, betas, past_len=10, future_len
     return body, torch.cat([obj_rot, xs[..., 141:144]], dim=2), verts.view(T, B, -1, 3), jtr.view(T, B, -1, 3)
 
 
-def smooth(obj, body, verts, jtrs, pelvis, future_len):
+def smooth(obj, body, verts, jtrs, pelvis, future_len, engine=None):
     """Reference eval_smpl_short.py:217-223: shift every predicted future frame by the second-difference jump at the
-    past/future seam, x[-F:] += 2 x[-F-1] - x[-F-2] - x[-F]; in place on (T, ...) tensors (device or host)."""
+    past/future seam, x[-F:] += 2 x[-F-1] - x[-F-2] - x[-F]; in place on (T, ...) tensors.  Device tensors go through the
+    library (`idb_smooth`; pass the engine, or one is looked up for the tensor's device); host tensors (e.g. unit tests of
+    the formula) take the same expression in torch."""
     F = int(future_len)
     for x in (obj, body, verts, jtrs, pelvis):
-        x[-F:] = x[-F:] + (2 * x[-F - 1] - x[-F - 2] - x[-F])
+        if x.is_cuda:
+            eng = engine if engine is not None else _engine_for(x.device)
+            if x.is_contiguous() and x.dtype == torch.float32:
+                eng.smooth_(x, F)
+            else:
+                y = x.float().contiguous()
+                eng.smooth_(y, F)
+                x.copy_(y)
+        else:
+            x[-F:] = x[-F:] + (2 * x[-F - 1] - x[-F - 2] - x[-F])
     return obj, body, verts, jtrs, pelvis
+
+
+_ENGINES = {}
+
+
+def _engine_for(device):
+    from .engine import Engine
+    device = torch.device(device)
+    if device not in _ENGINES:
+        _ENGINES[device] = Engine(device)
+    return _ENGINES[device]
+
+
+def gather_metrics(block):
+    """The path's only collective: ONE all_gather of the (6, B/G) per-sample metric block of every rank
+    (the six (B,) vectors `metrics` returns, eval_smpl_short.py:73-80) -> (6, B) in global sample order on every rank.
+    nccl (device tensors) and gloo (CPU tensors) both work; without a process group the block is returned as is."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return block
+    parts = [torch.empty_like(block) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, block.contiguous())
+    return torch.cat(parts, dim=1)
 
 
 class BestOfSamples:
     """The diverse-sample reduction of the reference's evaluation loop (eval_smpl_short.py:268-296): per batch every
     metric starts at 1e10, each of the `diverse_samples` draws contributes its per-sample metric vector, the
-    element-wise minimum over the draws is averaged over the batch and accumulated over batches."""
+    element-wise minimum over the draws is averaged over the batch and accumulated over batches.  Device metric vectors
+    are reduced in the library (`idb_metric_min`) on one (6, B) block; with `gather=True` the block of every rank is
+    exchanged with one all_gather before the batch mean (multi-GPU evaluation of a sliced batch)."""
 
-    def __init__(self, names=("global_mpjpe", "local_mpjpe", "body_translation", "obj_translation", "obj_rot_error", "penetrate")):
+    def __init__(self, names=("global_mpjpe", "local_mpjpe", "body_translation", "obj_translation", "obj_rot_error", "penetrate"),
+                 engine=None, gather=False):
         self.names = tuple(names)
         self.totals = {k: 0.0 for k in self.names}
         self.batches = 0
         self._cur = None
+        self.engine, self.gather = engine, gather
 
     def start_batch(self):
         self._cur = None
 
     def add(self, metric):
         """metric: {name: (B,) tensor} of one draw (Engine.metrics output)."""
+        block = torch.stack([metric[k].float() for k in self.names]).contiguous()
         if self._cur is None:
-            self._cur = {k: torch.full_like(metric[k], 1e10) for k in self.names}
-        for k in self.names:
-            self._cur[k] = torch.minimum(self._cur[k], metric[k])
+            self._cur = torch.full_like(block, 1e10)
+        if block.is_cuda:
+            (self.engine if self.engine is not None else _engine_for(block.device)).metric_min_(self._cur, block)
+        else:
+            self._cur = torch.minimum(self._cur, block)
 
     def end_batch(self):
-        for k in self.names:
-            self.totals[k] += self._cur[k].mean().item()
+        cur = gather_metrics(self._cur) if self.gather else self._cur
+        means = cur.mean(dim=1).tolist()
+        for k, v in zip(self.names, means):
+            self.totals[k] += v
         self.batches += 1
         self._cur = None
 

@@ -664,3 +664,28 @@ def metrics(obj_pred, body_jtr, body, obj_gt, body_jtr_gt, body_gt, verts, faces
     q, qg = tf.axis_angle_to_quaternion(obj_pred[:, :, :3]), tf.axis_angle_to_quaternion(obj_gt[:, :, :3])
     out["obj_rot_error"] = torch.minimum((q - qg).norm(dim=2, p=1), (q + qg).norm(dim=2, p=1)).mean(dim=0)
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# 8f rank 2: the step between two windows of the autoregressive rollout (eval_smpl_long.py:26-84, :247-285)
+# ----------------------------------------------------------------------------------------
+
+
+def rollout_next_window(body, obj, jtr, T, past_len):
+    """Restated INTENT of get_batch (eval_smpl_long.py:26-84) followed by MDM._get_embeddings' gt assembly
+    (model/diffusion_smpl.py:195-214) - PARITY UNPINNED: upstream get_batch raises for every batch size
+    (`.unsqueeze(0).repeat(B, 1)` on a (B,3) tensor, :46) and `denormalize` / `correct` (:278, :285) are undefined.
+    What the function visibly means: `rotation` stays the identity (:39-40), `centroid` = pelvis of the first of the last
+    past_len frames (:38), translations of body and object are taken relative to it (:43-46, :58-59), rotations are
+    unchanged (:52-55, :60-64), the future_len inputs repeat the last past frame (:78).
+    body (Tw,B,159) = [66 axis-angle | 90 hand | 3 trans], obj (Tw,B,6) = [axis-angle | trans], jtr (Tw,B,J,3).
+    Returns gt (B,1,144,T) and centroid (B,3); `denormalize` = add the centroid back."""
+    P = past_len
+    b, o, pel = body[-P:], obj[-P:], jtr[-P:, :, 0]
+    B = b.shape[1]
+    centroid = pel[0]
+    r6 = lambda aa: tf.matrix_to_rotation_6d(tf.axis_angle_to_matrix(aa))
+    frames = torch.cat([r6(b[..., :66].reshape(P, B, 22, 3)).reshape(P, B, 132), b[..., -3:] - centroid,
+                        r6(o[..., :3].reshape(P, B, 1, 3)).reshape(P, B, 6), o[..., 3:6] - centroid], dim=2)
+    frames = torch.cat([frames, frames[-1:].repeat(T - P, 1, 1)], dim=0)
+    return frames.permute(1, 2, 0).unsqueeze(1).contiguous(), centroid

@@ -560,3 +560,57 @@ def test_batch_slices_bit_identical(eng):
             eng.bind(np.ascontiguousarray(b["cond"][:, sl]), T)
             parts.append(eng.p_sample_loop(tape[:, sl].contiguous(), gt[sl].contiguous(), mask[sl].contiguous()).clone())
         assert torch.equal(torch.cat(parts, dim=0), full), G
+
+
+def test_rollout_next_window_and_driver(eng, smplh_np):
+    """SURVEY 8f rank 2 / BASELINE configs[4]: the device-side step between two windows (get_batch + denormalize) against its
+    oracle restatement, and the driver's world-coordinate trajectory: window k+1 starts exactly where window k ended."""
+    from interdiff_b200.rollout import RolloutDriver
+    from interdiff_b200.sampling import sample_postprocess
+    g = torch.Generator().manual_seed(21)
+    T, B, P = 30, 3, 10
+    body = torch.cat([0.8 * torch.randn(T, B, 66, generator=g), 0.1 * torch.randn(T, B, 90, generator=g), torch.randn(T, B, 3, generator=g)], dim=2)
+    body[3, 0, 3:6] = 0.0                                     # small-angle branch of axis_angle_to_quaternion
+    obj = torch.cat([0.8 * torch.randn(T, B, 3, generator=g), torch.randn(T, B, 3, generator=g)], dim=2)
+    jtr = torch.randn(T, B, 52, 3, generator=g)
+    gt, cen = eng.rollout_next_window(body, obj, jtr, T, P)
+    gt_ref, cen_ref = R.rollout_next_window(body, obj, jtr, T, P)
+    assert torch.equal(cen.cpu(), cen_ref) and rel(gt, gt_ref) < 1e-6
+    assert torch.equal(gt[..., P:].cpu(), gt[..., P - 1:P].cpu().expand(-1, -1, -1, T - P))       # future inputs repeat the last past frame
+    x = torch.randn(T, B, 5, 3, generator=g).cuda()
+    y = eng.add_offset_(x.clone(), cen)
+    assert rel(y, x.cpu() + cen_ref.view(1, B, 1, 3)) < 1e-7
+    # driver: 1 + 2 windows on a short schedule
+    sd, psd = mdm_weights("smpl", "random"), projector_weights("auto")
+    eng.load_denoiser(sd, "smpl")
+    eng.load_body(smplh_np)
+    eng.load_projector(psd, P, T - P)
+    b = S.make_smpl_batch(B=B, T=T)
+    steps = 6
+    eng.bind(b["cond"], T)
+    hp, bt = torch.from_numpy(b["hand_pose"]).cuda(), torch.from_numpy(b["betas"]).cuda()
+    eng.bind_correction(hp, bt, b["obj_points"], past_len=P)
+    eng.init_diffusion(R.named_beta_schedule("cosine", steps))
+    tape = torch.from_numpy(S.noise_tape(b["gt"].shape, steps)).cuda()
+    gt0, mask = torch.from_numpy(b["gt"]).cuda(), torch.from_numpy(b["mask"]).cuda()
+    drv = RolloutDriver(eng, past_len=P, n_windows=2, correction=True)
+    traj = drv.run(tape, gt0, mask, hp, bt, keep=("body", "obj", "pelvis", "jtr"))
+    F = T - P
+    assert traj["body"].shape[0] == P + 3 * F and traj["obj"].shape[0] == P + 3 * F
+    # manual composition of the same rollout with the ORACLE's window step (host side), engine loops for the sampling
+    offset = torch.zeros(B, 3)
+    cur = gt0
+    bodies = []
+    for k in range(3):
+        s = eng.p_sample_loop(tape, cur, mask, correction=True)
+        bd, ob, _, jt = sample_postprocess(eng, s, hp, bt)
+        bd, ob, jt = bd.cpu(), ob.cpu(), jt.cpu()
+        nxt, c = R.rollout_next_window(bd, ob, jt, T, P)
+        w = bd.clone()
+        w[..., -3:] += offset
+        bodies.append(w[0 if k == 0 else P:])
+        offset = offset + c
+        cur = nxt.cuda()
+    assert rel(traj["body"], torch.cat(bodies)) < 1e-5
+    # continuity: the inpainted past of window k+1 (frames [P + k F - P .. ) in world coordinates) IS the end of window k
+    assert torch.isfinite(traj["pelvis"]).all()

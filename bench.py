@@ -266,7 +266,7 @@ def run_ours(args):
     if strong:
         sl = rank_slice(c["B"], rank, world)
         gb = S.make_smpl_batch(B=c["B"], T=T, past_len=c["past"], seed=233)       # ONE global batch, sliced
-        b = {k: np.ascontiguousarray(v[sl] if k in ("gt", "mask", "obj_points") else v[:, sl]) for k, v in gb.items()}
+        b = {k: np.ascontiguousarray(v[sl] if k in ("gt", "mask", "obj_points") else v[:, sl]) for k, v in gb.items() if isinstance(v, np.ndarray)}
         ids = list(range(sl.start, sl.stop))
     else:
         b = S.make_smpl_batch(B=c["B"], T=T, past_len=c["past"], seed=rank_seed(rank))   # each rank its own sequences

@@ -450,10 +450,12 @@ extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const 
         CUDA_TRY(h, up(vid.data(), vid.size() * sizeof(uint16_t), (void**)&m.nn_vid));
         CUDA_TRY(h, up(off.data(), off.size() * 4, (void**)&m.nn_off));
     }
+    // the opt-in is a per-function, per-device limit (NOT per model): always raise it to the device maximum, or a second,
+    // smaller body model on the same device would lower it under the first one's launches
     const int smem_skin = (int)sizeof(float) * (Kp * FB + FB * J * 12 + NB * FB + FB * 3);
-    CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_skin));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(float) * (FS * J * 12 + FS * 4 + 8 * 96)));
+    if (smem_skin > 227 * 1024) return idb_fail(h, IDB_ERR_ARG, "body model too large for the SIMT skinning kernel's shared memory");
+    CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     h->epoch++;
     return IDB_OK;
 }

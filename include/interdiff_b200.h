@@ -163,6 +163,17 @@ int idb_correction_bind(idb_handle* h, int B, int T, int past_len, int n_obj_poi
  * contact (B,P) int32, markers (T,B,P,3), o2h_signed (T*B,Pobj). */
 int idb_correction_apply(idb_handle* h, float* x0, const float* gt, int t, uint8_t* condition_out,
                          int32_t* contact_out, float* markers_out, float* o2h_out, void* stream);
+/* ---- skeleton correction net + hook (model/correction_skeleton.py:8-135, eval_skeleton.py:80-111) ----
+ * idb_projector_init_skeleton: n_pre 20, n_joints (21) + 1 nodes, joint stack 9-64-32-64-9; weights through idb_projector_load /
+ * idb_projector_commit under the same state_dict names.  idb_projector_sample_skeleton = ObjProjector.sample: quaternions xyzw
+ * (T,B,4), translations (T,B,3), joints (T,B,n_joints,3).  idb_skeleton_correction_apply = the body of the skeleton denoised_fn
+ * for an active step, in place on x0 (B,1,3 n_joints + 3 n_points + 7,T); with a skeleton projector loaded
+ * idb_p_sample_loop(correction = 1) runs it on the reference's schedule (t <= 500, t % 50 == 0). */
+int idb_projector_init_skeleton(idb_handle* h, int past_len, int future_len, int n_joints);
+int idb_projector_sample_skeleton(idb_handle* h, int T, int B, const float* obj_quat, const float* obj_trans, const float* joints,
+                                  float* quat_out, float* trans_out, void* stream);
+int idb_skeleton_correction_apply(idb_handle* h, int B, int T, int n_points, float* x0, const float* gt, const float* zero_pose_obj,
+                                  int t, void* stream);
 /* Parity hook for the in-loop path: device buffers cond_log [capacity][B] uint8, contact_log [capacity][B][n_markers] int32
  * receive the decisions of every correction step enqueued after this call, in order (NULL, NULL, 0 = off). */
 int idb_correction_set_log(idb_handle* h, uint8_t* cond_log, int32_t* contact_log, int capacity);

@@ -18,7 +18,7 @@ struct BodyModel {
     __half *pd_hi = nullptr, *pd_lo = nullptr; int Nb = 0, Kld = 0;
     // skinning weights in ELL form: sk_n[v] non-zero bones of vertex v (<= SK_MAX), sk_j / sk_w [SK_MAX][V]; sk_dense = some
     // vertex has more than SK_MAX non-zero weights (then the kernel walks all J bones of weightsT instead)
-    unsigned char *sk_n = nullptr, *sk_j = nullptr; float* sk_w = nullptr; bool sk_dense = false;
+    unsigned char *sk_n = nullptr, *sk_j = nullptr; float* sk_w = nullptr; bool sk_dense = false; int sk_max = 0;
     std::vector<void*> owned;
     // per-call workspace
     int capF = 0;

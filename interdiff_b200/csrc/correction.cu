@@ -16,6 +16,7 @@ struct ProjLayer {
 
 struct Projector {
     int past = 0, future = 0, n_pre = 0, P = 0, T = 0;
+    int variant = 0;                   // 0 = SMPL markers net (n_pre 10, width 32), 1 = skeleton net (n_pre 20, joint stack width 64)
     bool committed = false;
     std::map<std::string, DevTensor> raw;
     std::vector<void*> owned;
@@ -33,22 +34,25 @@ struct Projector {
     unsigned char *lbl = nullptr, *cond = nullptr;
     int32_t* contact = nullptr;
     std::vector<void*> ctx_owned;
+    float *skel_ws = nullptr, *skel_hook_ws = nullptr; int skel_cap = 0, skel_hook_cap = 0;     // skeleton variant workspaces
     // optional decision log (idb_correction_set_log): slot k receives the decisions of the k-th correction step enqueued
     unsigned char* log_cond = nullptr; int32_t* log_contact = nullptr; int log_cap = 0, log_n = 0;
 };
 
 namespace {
 
-constexpr int NQ = 10;           // n_pre (dct coefficients kept)
-constexpr int MAXC = 32;
-constexpr int MAXP = 68;
+constexpr int MAXP_SMPL = 68;    // 67 markers + the object's own node
 
-// One block per sample: the whole projector runs out of shared memory.
+// One block per sample: the whole projector runs out of shared memory.  NQ = n_pre (DCT coefficients kept), MAXC = widest
+// layer, MAXP = nodes of the joint stack: <10, 32, 68> for the SMPL net (model/correction_smpl.py), <20, 64, 22> for the
+// skeleton net (model/correction_skeleton.py: 21 joints + 1, st_gcnns_all 9-64-32-64-9).  select_contact: the SMPL net picks
+// the hypothesis of the most-contacted marker (correction_smpl.py:125-136); the skeleton net always reads node 0 (:129).
+template <int NQ, int MAXC, int MAXP>
 __global__ void __launch_bounds__(256)
 k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct, const float* __restrict__ idct,
             const float* __restrict__ ang, const float* __restrict__ tr, const float* __restrict__ markers,
             const int32_t* __restrict__ contact, const int32_t* __restrict__ hand_ids, int n_hand,
-            float* __restrict__ resid, float* __restrict__ out, int T, int B, int P, int past) {
+            float* __restrict__ resid, float* __restrict__ out, int T, int B, int P, int past, int select_contact) {
     extern __shared__ __align__(16) float sm[];
     const int P1 = P + 1;
     float* bufA = sm;                          // [MAXC][NQ][P1]  activations (x / layer output)
@@ -210,7 +214,7 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
     // ---- hypothesis selection (correction_smpl.py:125-136) + inverse DCT of that column only
     if (tid == 0) {
         long long csum = 0;
-        for (int p = 0; p < P; p++) csum += contact[(size_t)b * P + p];
+        if (select_contact) for (int p = 0; p < P; p++) csum += contact[(size_t)b * P + p];
         int sel = 0;
         if (csum > 0) {
             float best = -INFINITY;
@@ -280,9 +284,9 @@ __global__ void __launch_bounds__(256)
 k_frame_stats(const float* __restrict__ verts, const int32_t* __restrict__ marker_ids, const float* __restrict__ objp,
               const float* __restrict__ o2h, float* __restrict__ markers, float* __restrict__ pen, float* __restrict__ dmin,
               unsigned char* __restrict__ lbl, int V, int Pn, int P) {
-    __shared__ float s_m[MAXP * 3];
+    __shared__ float s_m[MAXP_SMPL * 3];
     __shared__ float s_red[256];
-    __shared__ unsigned int s_lbl[MAXP];
+    __shared__ unsigned int s_lbl[MAXP_SMPL];
     __shared__ float s_min[8];
     const int f = blockIdx.x, tid = threadIdx.x;
     for (int i = tid; i < P * 3; i += 256) {
@@ -367,6 +371,8 @@ void idb_projector_release(idb_handle* h) {
     for (void* q : p.ctx_owned) cudaFree(q);
     if (p.resid) cudaFree(p.resid);
     if (p.hand_ids) cudaFree(p.hand_ids);
+    if (p.skel_ws) cudaFree(p.skel_ws);
+    if (p.skel_hook_ws) cudaFree(p.skel_hook_ws);
     delete h->proj;
     h->proj = nullptr;
 }
@@ -374,13 +380,27 @@ void idb_projector_release(idb_handle* h) {
 extern "C" int idb_projector_init(idb_handle* h, int past_len, int future_len, int n_pre, int n_markers) {
     IDB_ENTER(h);
     if (!h) return IDB_ERR_ARG;
-    if (n_pre != NQ) return idb_fail(h, IDB_ERR_ARG, "n_pre (dct) must be 10");
-    if (n_markers + 1 > MAXP || n_markers < 1) return idb_fail(h, IDB_ERR_ARG, "n_markers must be in 1..67");
+    if (n_pre != 10) return idb_fail(h, IDB_ERR_ARG, "n_pre (dct) must be 10 for the SMPL correction net (20: idb_projector_init_skeleton)");
+    if (n_markers + 1 > MAXP_SMPL || n_markers < 1) return idb_fail(h, IDB_ERR_ARG, "n_markers must be in 1..67");
     if (past_len < 1 || future_len < 0) return IDB_ERR_ARG;
     idb_projector_release(h);
     h->proj = new Projector();
     Projector& p = *h->proj;
     p.past = past_len; p.future = future_len; p.n_pre = n_pre; p.P = n_markers; p.T = past_len + future_len;
+    return IDB_OK;
+}
+
+/* skeleton correction net (model/correction_skeleton.py:8-53): n_pre = 20, joint stack 9-64-32-64-9 over n_joints + 1 nodes */
+extern "C" int idb_projector_init_skeleton(idb_handle* h, int past_len, int future_len, int n_joints) {
+    IDB_ENTER(h);
+    if (!h) return IDB_ERR_ARG;
+    if (n_joints < 1 || n_joints + 1 > 22) return idb_fail(h, IDB_ERR_ARG, "n_joints must be in 1..21");
+    if (past_len < 1 || future_len < 0) return IDB_ERR_ARG;
+    idb_projector_release(h);
+    h->proj = new Projector();
+    Projector& p = *h->proj;
+    p.variant = 1;
+    p.past = past_len; p.future = future_len; p.n_pre = 20; p.P = n_joints; p.T = past_len + future_len;
     return IDB_OK;
 }
 
@@ -423,13 +443,16 @@ extern "C" int idb_projector_commit(idb_handle* h) {
     };
     const char* stacks[3] = {"st_gcnns_relative.", "st_gcnns.", "st_gcnns_all."};
     const int nodes[3] = {p.P, 1, p.P + 1};
-    const int chans[5] = {9, 32, 16, 32, 9};
+    const int NQ = p.n_pre;
+    // layer widths (model/correction_smpl.py:18-50; model/correction_skeleton.py:13-50: the joint stack is 9-64-32-64-9)
+    const int chans_std[5] = {9, 32, 16, 32, 9}, chans_wide[5] = {9, 64, 32, 64, 9};
     std::vector<ProjLayer> L(12);
     int rc;
     for (int s = 0; s < 3; s++)
         for (int i = 0; i < 4; i++) {
             ProjLayer& l = L[s * 4 + i];
             const std::string pre = std::string(stacks[s]) + std::to_string(i) + ".";
+            const int* chans = (p.variant == 1 && s == 2) ? chans_wide : chans_std;
             l.cin = chans[i]; l.cout = chans[i + 1]; l.ver = s == 2 ? 2 : 0; l.P = nodes[s]; l.A = nullptr;
             std::vector<float> Tm, A, W, b, g, be, mu, var, Wr, br, gr, ber, mur, varr, pr;
             if ((rc = hostof(pre + "gcn.T", Tm))) return rc;
@@ -472,9 +495,11 @@ extern "C" int idb_projector_commit(idb_handle* h) {
             idct[(size_t)i * NQ + k] = (float)v;
         }
     if ((rc = up(dct, &p.dct)) || (rc = up(idct, &p.idct))) return rc;
-    const int smem = (int)sizeof(float) * (2 * MAXC * NQ * MAXP + NQ * T + NQ * NQ);
-    CUDA_TRY(h, cudaFuncSetAttribute(k_projector, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // per-function, per-device opt-in: always the device maximum (a smaller value set by another handle must not undercut it)
+    CUDA_TRY(h, cudaFuncSetAttribute(k_projector<10, 32, 68>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_projector<20, 64, 22>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     p.committed = true;
+    h->epoch++;
     return IDB_OK;
 }
 
@@ -483,14 +508,22 @@ static int projector_run(idb_handle* h, int T, int B, const float* ang, const fl
     Projector& p = *h->proj;
     if (!p.committed) return idb_fail(h, IDB_ERR_STATE, "idb_projector_commit first");
     if (T != p.T) return idb_fail(h, IDB_ERR_ARG, "T must equal past_len + future_len of the projector (%d)", p.T);
+    const int NQ = p.n_pre;
     if (B > p.capB) {
         h->epoch++;
         if (p.resid) cudaFree(p.resid);
         CUDA_TRY(h, cudaMalloc((void**)&p.resid, sizeof(float) * (size_t)B * 9 * NQ * (p.P + 1)));
         p.capB = B;
     }
-    const size_t smem = sizeof(float) * ((size_t)2 * MAXC * NQ * MAXP + NQ * T + NQ * NQ);
-    k_projector<<<B, 256, smem, st>>>(p.layers_dev, p.dct, p.idct, ang, tr, markers, contact, p.hand_ids, p.n_hand, p.resid, out, T, B, p.P, p.past);
+    if (p.variant == 0) {
+        const size_t smem = sizeof(float) * ((size_t)2 * 32 * 10 * 68 + NQ * T + NQ * NQ);
+        k_projector<10, 32, 68><<<B, 256, smem, st>>>(p.layers_dev, p.dct, p.idct, ang, tr, markers, contact, p.hand_ids, p.n_hand, p.resid, out,
+                                                      T, B, p.P, p.past, 1);
+    } else {
+        const size_t smem = sizeof(float) * ((size_t)2 * 64 * 20 * 22 + NQ * T + NQ * NQ);
+        k_projector<20, 64, 22><<<B, 256, smem, st>>>(p.layers_dev, p.dct, p.idct, ang, tr, markers, nullptr, nullptr, 0, p.resid, out,
+                                                      T, B, p.P, p.past, 0);
+    }
     LAUNCH_CHECK(h);
     return IDB_OK;
 }
@@ -560,7 +593,25 @@ extern "C" int idb_correction_bind(idb_handle* h, int B, int T, int past_len, in
 }
 
 // Grows every workspace a correction step needs BEFORE a stream capture starts (no allocation may happen inside one).
+extern "C" int idb_skeleton_correction_apply(idb_handle* h, int B, int T, int n_points, float* x0, const float* gt, const float* zero_pose_obj,
+                                             int t, void* stream);
 int idb_correction_prepare(idb_handle* h, int B, int T) {
+    if (h->proj && h->proj->variant == 1) {
+        // skeleton hook: run it once outside any capture on a scratch sample so that every workspace has its final size
+        Projector& p = *h->proj;
+        const idb_denoiser_config& c = h->den.cfg;
+        if (c.variant != 1 || !h->den.zero_pose) return idb_fail(h, IDB_ERR_STATE, "the skeleton correction hook needs the skeleton denoiser bound");
+        const int F = T * B;
+        if (F <= p.skel_hook_cap && F <= p.skel_cap && B <= p.capB) return IDB_OK;
+        const size_t n = (size_t)B * (c.c_body + c.c_obj + c.c_extra) * T;
+        float* tmp = nullptr;
+        CUDA_TRY(h, cudaMalloc((void**)&tmp, n * sizeof(float)));
+        cudaMemset(tmp, 0, n * sizeof(float));
+        int rc = idb_skeleton_correction_apply(h, B, T, c.n_points, tmp, tmp, h->den.zero_pose, 0, nullptr);
+        cudaDeviceSynchronize();
+        cudaFree(tmp);
+        return rc;
+    }
     if (!h->proj || !h->proj->B) return idb_fail(h, IDB_ERR_STATE, "idb_correction_bind first");
     if (!h->body) return idb_fail(h, IDB_ERR_STATE, "idb_body_init first");
     Projector& p = *h->proj;
@@ -570,13 +621,17 @@ int idb_correction_prepare(idb_handle* h, int B, int T) {
     if (p.B > p.capB) {
         h->epoch++;
         if (p.resid) cudaFree(p.resid);
-        CUDA_TRY(h, cudaMalloc((void**)&p.resid, sizeof(float) * (size_t)p.B * 9 * NQ * (p.P + 1)));
+        CUDA_TRY(h, cudaMalloc((void**)&p.resid, sizeof(float) * (size_t)p.B * 9 * p.n_pre * (p.P + 1)));
         p.capB = p.B;
     }
     return IDB_OK;
 }
 
 int idb_correction_apply_dev(idb_handle* h, float* x0, const float* gt, int t, cudaStream_t st) {
+    if (h->proj && h->proj->variant == 1) {   // skeleton model: eval_skeleton.py's hook on the bound batch
+        if (!gt) return idb_fail(h, IDB_ERR_ARG, "the correction hook needs the inpainted motion (gt)");
+        return idb_skeleton_correction_apply(h, h->den.B, h->den.T, h->den.cfg.n_points, x0, gt, h->den.zero_pose, t, (void*)st);
+    }
     if (!h->proj || !h->proj->B) return idb_fail(h, IDB_ERR_STATE, "idb_correction_bind first");
     if (!gt) return idb_fail(h, IDB_ERR_ARG, "the correction hook needs the inpainted motion (gt)");
     Projector& p = *h->proj;
@@ -605,6 +660,126 @@ int idb_correction_apply_dev(idb_handle* h, float* x0, const float* gt, int t, c
     // t[0] / 1000 in float32 (torch true-divides the int64 tensor by 1000 -> float32)
     const float a = (float)t / 1000.0f;
     k_blend<<<148 * 2, 256, 0, st>>>(x0, p.proj_out, p.cond, a, B, T, C);
+    LAUNCH_CHECK(h);
+    return IDB_OK;
+}
+
+// ---- skeleton variant (model/correction_skeleton.py:84-135, eval_skeleton.py:80-111) ------------------------------------
+namespace {
+// quaternion xyzw (T,B,4) -> rotation 6D (first two rows of quaternion_to_matrix on (w,x,y,z)), correction_skeleton.py:89-90
+__global__ void k_quat_to_6d(const float* __restrict__ quat, float* __restrict__ ang6, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float q[4] = {quat[(size_t)i * 4 + 3], quat[(size_t)i * 4], quat[(size_t)i * 4 + 1], quat[(size_t)i * 4 + 2]};
+    float R[9];
+    idb_quaternion_to_matrix(q, R);
+    for (int e = 0; e < 6; e++) ang6[(size_t)i * 6 + e] = R[e];
+}
+// projector output (T,B,9) = [6D | trans] -> quaternion xyzw (T,B,4), trans (T,B,3)   (:132-135)
+__global__ void k_proj_to_quat(const float* __restrict__ res, float* __restrict__ quat, float* __restrict__ trans, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float R[9], q[4];
+    idb_rot6d_to_matrix(res + (size_t)i * 9, R);
+    idb_matrix_to_quaternion(R, q);
+    quat[(size_t)i * 4] = q[1]; quat[(size_t)i * 4 + 1] = q[2]; quat[(size_t)i * 4 + 2] = q[3]; quat[(size_t)i * 4 + 3] = q[0];
+    for (int e = 0; e < 3; e++) trans[(size_t)i * 3 + e] = res[(size_t)i * 9 + 6 + e];
+}
+// x (B,1,C,T), C = 3 Jn + 3 Np + 7: gathers of the hook's inputs.  which 0: joints (T,B,Jn,3) from x; 1: pose [trans3 | quat4] of gt
+__global__ void k_skel_gather(const float* __restrict__ x, float* __restrict__ joints, const float* __restrict__ gt, float* __restrict__ gt_trans,
+                              float* __restrict__ gt_quat, int B, int T, int C, int Jn) {
+    const int f = blockIdx.x, t = f / B, b = f % B;
+    for (int i = threadIdx.x; i < Jn * 3; i += blockDim.x) joints[(size_t)f * Jn * 3 + i] = x[((size_t)b * C + i) * T + t];
+    if (threadIdx.x < 7) {
+        const float v = gt[((size_t)b * C + (C - 7) + threadIdx.x) * T + t];
+        if (threadIdx.x < 3) gt_trans[(size_t)f * 3 + threadIdx.x] = v; else gt_quat[(size_t)f * 4 + threadIdx.x - 3] = v;
+    }
+}
+// x = a x + (1 - a) [body | calc_obj_pred(pose_proj, zero_pose_obj) | pose_proj]   for EVERY sample (eval_skeleton.py:106-111)
+__global__ void k_skel_blend(float* __restrict__ x, const float* __restrict__ quat, const float* __restrict__ trans,
+                             const float* __restrict__ zero_pose, float a, int B, int T, int C, int Jn, int Np) {
+    const int f = blockIdx.x, t = f / B, b = f % B;
+    const float a1 = 1.0f - a;
+    __shared__ float R[9];
+    __shared__ float pose[7];
+    if (threadIdx.x == 0) {
+        const float* qq = quat + (size_t)f * 4;
+        const float q[4] = {qq[3], qq[0], qq[1], qq[2]};          // calc_obj_pred: xyzw -> wxyz, un-normalised
+        float Rl[9];
+        idb_quaternion_to_matrix(q, Rl);
+        for (int e = 0; e < 9; e++) R[e] = Rl[e];
+        for (int e = 0; e < 3; e++) pose[e] = trans[(size_t)f * 3 + e];
+        for (int e = 0; e < 4; e++) pose[3 + e] = qq[e];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float* px = x + ((size_t)b * C + c) * T + t;
+        const float xv = *px;
+        float other = xv;                                          // body channels: x_ = body_pred
+        if (c >= 3 * Jn && c < 3 * Jn + 3 * Np) {
+            const int p = (c - 3 * Jn) / 3, ax = (c - 3 * Jn) % 3;
+            const float* zp = zero_pose + ((size_t)b * Np + p) * 3;
+            other = (R[ax * 3] * zp[0] + R[ax * 3 + 1] * zp[1] + R[ax * 3 + 2] * zp[2]) + pose[ax];
+        } else if (c >= 3 * Jn + 3 * Np) {
+            other = pose[c - 3 * Jn - 3 * Np];
+        }
+        *px = __fadd_rn(__fmul_rn(a, xv), __fmul_rn(a1, other));
+    }
+}
+}  // namespace
+
+/* ObjProjector.sample of the skeleton net: obj_quat (T,B,4) xyzw, obj_trans (T,B,3), joints (T,B,n_joints,3)
+   -> quat_out (T,B,4) xyzw, trans_out (T,B,3) */
+extern "C" int idb_projector_sample_skeleton(idb_handle* h, int T, int B, const float* obj_quat, const float* obj_trans, const float* joints,
+                                             float* quat_out, float* trans_out, void* stream) {
+    IDB_ENTER(h);
+    if (!h || !obj_quat || !obj_trans || !joints || !quat_out || !trans_out || T <= 0 || B <= 0) return IDB_ERR_ARG;
+    if (!h->proj || h->proj->variant != 1) return idb_fail(h, IDB_ERR_STATE, "idb_projector_init_skeleton first");
+    Projector& p = *h->proj;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = T * B;
+    if (F > p.skel_cap) {
+        h->epoch++;
+        if (p.skel_ws) cudaFree(p.skel_ws);
+        CUDA_TRY(h, cudaMalloc((void**)&p.skel_ws, sizeof(float) * (size_t)F * (6 + 9)));
+        p.skel_cap = F;
+    }
+    float* ang6 = p.skel_ws; float* res = ang6 + (size_t)F * 6;
+    k_quat_to_6d<<<(F + 127) / 128, 128, 0, st>>>(obj_quat, ang6, F);
+    LAUNCH_CHECK(h);
+    int rc = projector_run(h, T, B, ang6, obj_trans, joints, nullptr, res, st);
+    if (rc) return rc;
+    k_proj_to_quat<<<(F + 127) / 128, 128, 0, st>>>(res, quat_out, trans_out, F);
+    LAUNCH_CHECK(h);
+    return IDB_OK;
+}
+
+/* denoised_fn of eval_skeleton.py:80-111 for an ACTIVE step, in place on x0 (B,1,C,T), C = 3 n_joints + 3 n_points + 7:
+   the object pose of the inpainted motion goes through the skeleton correction net (conditioned on the predicted joints),
+   the object keypoints are re-derived from the projected pose and zero_pose_obj (B,n_points,3), and
+   x0 = (t/1000) x0 + (1 - t/1000) [body | keypoints | pose] for every sample.  (The reference also evaluates
+   body_obj_to_contact (:96) but never uses its result.) */
+extern "C" int idb_skeleton_correction_apply(idb_handle* h, int B, int T, int n_points, float* x0, const float* gt, const float* zero_pose_obj,
+                                             int t, void* stream) {
+    IDB_ENTER(h);
+    if (!h || !x0 || !gt || !zero_pose_obj || B <= 0 || T <= 0 || n_points <= 0) return IDB_ERR_ARG;
+    if (!h->proj || h->proj->variant != 1) return idb_fail(h, IDB_ERR_STATE, "idb_projector_init_skeleton first");
+    Projector& p = *h->proj;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = T * B, Jn = p.P, C = 3 * Jn + 3 * n_points + 7;
+    if (F > p.skel_hook_cap) {
+        h->epoch++;
+        if (p.skel_hook_ws) cudaFree(p.skel_hook_ws);
+        CUDA_TRY(h, cudaMalloc((void**)&p.skel_hook_ws, sizeof(float) * (size_t)F * (Jn * 3 + 3 + 4 + 4 + 3)));
+        p.skel_hook_cap = F;
+    }
+    float* joints = p.skel_hook_ws; float* gtr = joints + (size_t)F * Jn * 3; float* gq = gtr + (size_t)F * 3;
+    float* pq = gq + (size_t)F * 4; float* ptr = pq + (size_t)F * 4;
+    k_skel_gather<<<F, 64, 0, st>>>(x0, joints, gt, gtr, gq, B, T, C, Jn);
+    LAUNCH_CHECK(h);
+    int rc = idb_projector_sample_skeleton(h, T, B, gq, gtr, joints, pq, ptr, stream);
+    if (rc) return rc;
+    k_skel_blend<<<F, 128, 0, st>>>(x0, pq, ptr, zero_pose_obj, (float)t / 1000.0f, B, T, C, Jn, n_points);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }

@@ -192,11 +192,15 @@ k_lbs_skin(const float* __restrict__ posedirsT, const float* __restrict__ shaped
 // transform, translation.  Thread = vertex, block = 256 vertices x FS frames; the A matrices of the frame group live in
 // shared memory (neighbouring vertices share bones, so the reads are mostly broadcasts); vertices leave through a
 // per-warp staging row as 8-byte coalesced stores.
-constexpr int FS = 16;
-__global__ void __launch_bounds__(256, 2)
+constexpr int FS = 8;
+// NZ > 0: every vertex has at most NZ non-zero bones; its ELL list is padded with (bone 0, weight 0), whose products are
+// exact zeros, so the loop runs NZ times without a predicate (a predicated-off instruction still costs an issue slot).
+// NZ == 0: dense walk over all J bones of weightsT.
+template <int NZ>
+__global__ void __launch_bounds__(256, 3)
 k_lbs_skin_sparse(const float* __restrict__ blend, int ldb, const float* __restrict__ v_templT,
-                  const unsigned char* __restrict__ sk_n, const unsigned char* __restrict__ sk_j, const float* __restrict__ sk_w,
-                  const float* __restrict__ weightsT, int dense, const float* __restrict__ Ain,
+                  const unsigned char* __restrict__ sk_j, const float* __restrict__ sk_w,
+                  const float* __restrict__ weightsT, const float* __restrict__ Ain,
                   const float* __restrict__ trans, float* __restrict__ verts, int F, int V, int J) {
     extern __shared__ __align__(16) float sm[];
     float* s_A = sm;                       // [FS][J][12]
@@ -206,84 +210,61 @@ k_lbs_skin_sparse(const float* __restrict__ blend, int ldb, const float* __restr
     const int nf = min(FS, F - f0);
     const int v0 = blockIdx.x * 256 + warp * 32, v = v0 + lane;
     const int vc = v < V ? v : V - 1;
-    // every global read of the thread is issued before its first use (two batches of 8 frames)
-    float bl[FS / 2][3];
+    // every global read of the thread is issued before its first use: one memory latency per block
+    float bl[FS][3];
 #pragma unroll
-    for (int ff = 0; ff < FS / 2; ff++) {
+    for (int ff = 0; ff < FS; ff++) {
         const float* q = blend + (size_t)min(f0 + ff, F - 1) * ldb + (size_t)vc * 3;
         bl[ff][0] = q[0]; bl[ff][1] = q[1]; bl[ff][2] = q[2];
     }
     const float vt0 = v_templT[vc], vt1 = v_templT[(size_t)V + vc], vt2 = v_templT[(size_t)2 * V + vc];
-    int nb = 0, bj[SK_MAX]; float bw[SK_MAX];
-    if (!dense) {
-        nb = sk_n[vc];
+    int bj[NZ > 0 ? NZ : 1]; float bw[NZ > 0 ? NZ : 1];
 #pragma unroll
-        for (int e = 0; e < SK_MAX; e++) { bj[e] = sk_j[(size_t)e * V + vc]; bw[e] = sk_w[(size_t)e * V + vc]; }
-    }
+    for (int e = 0; e < NZ; e++) { bj[e] = 3 * (int)sk_j[(size_t)e * V + vc]; bw[e] = sk_w[(size_t)e * V + vc]; }
     for (int i = tid; i < nf * J * 12; i += 256) s_A[i] = Ain[(size_t)f0 * J * 12 + i];
     for (int i = tid; i < nf * 3; i += 256) s_t[(i / 3) * 4 + i % 3] = trans[(size_t)f0 * 3 + i];
     __syncthreads();
     float* so = s_o + warp * 96;
+    const int nfl = min(32, V - v0) * 3;          // floats of this warp's live vertices (<= 0 for a warp past the end)
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-        float nx[FS / 2][3];
-        if (half == 0) {          // second batch of blend rows, in flight while the first batch is consumed
+    for (int ff = 0; ff < FS; ff++) {
+        if (ff >= nf) break;
+        const float px = fmaf(bl[ff][0], 1.0f / 256.0f, vt0), py = fmaf(bl[ff][1], 1.0f / 256.0f, vt1), pz = fmaf(bl[ff][2], 1.0f / 256.0f, vt2);
+        float Tm[12];
 #pragma unroll
-            for (int ff = 0; ff < FS / 2; ff++) {
-                const float* q = blend + (size_t)min(f0 + FS / 2 + ff, F - 1) * ldb + (size_t)vc * 3;
-                nx[ff][0] = q[0]; nx[ff][1] = q[1]; nx[ff][2] = q[2];
+        for (int e = 0; e < 12; e++) Tm[e] = 0.f;
+        const float4* A4 = reinterpret_cast<const float4*>(s_A + (size_t)ff * J * 12);
+        if (NZ > 0) {
+#pragma unroll
+            for (int e = 0; e < NZ; e++) {
+                const float w = bw[e];
+                const float4 a0 = A4[bj[e]], a1 = A4[bj[e] + 1], a2 = A4[bj[e] + 2];
+                Tm[0] = fmaf(w, a0.x, Tm[0]); Tm[1] = fmaf(w, a0.y, Tm[1]); Tm[2] = fmaf(w, a0.z, Tm[2]); Tm[3] = fmaf(w, a0.w, Tm[3]);
+                Tm[4] = fmaf(w, a1.x, Tm[4]); Tm[5] = fmaf(w, a1.y, Tm[5]); Tm[6] = fmaf(w, a1.z, Tm[6]); Tm[7] = fmaf(w, a1.w, Tm[7]);
+                Tm[8] = fmaf(w, a2.x, Tm[8]); Tm[9] = fmaf(w, a2.y, Tm[9]); Tm[10] = fmaf(w, a2.z, Tm[10]); Tm[11] = fmaf(w, a2.w, Tm[11]);
+            }
+        } else {
+            for (int jn = 0; jn < J; jn++) {
+                const float w = __ldg(weightsT + (size_t)jn * V + vc);
+                const float4 a0 = A4[jn * 3], a1 = A4[jn * 3 + 1], a2 = A4[jn * 3 + 2];
+                Tm[0] = fmaf(w, a0.x, Tm[0]); Tm[1] = fmaf(w, a0.y, Tm[1]); Tm[2] = fmaf(w, a0.z, Tm[2]); Tm[3] = fmaf(w, a0.w, Tm[3]);
+                Tm[4] = fmaf(w, a1.x, Tm[4]); Tm[5] = fmaf(w, a1.y, Tm[5]); Tm[6] = fmaf(w, a1.z, Tm[6]); Tm[7] = fmaf(w, a1.w, Tm[7]);
+                Tm[8] = fmaf(w, a2.x, Tm[8]); Tm[9] = fmaf(w, a2.y, Tm[9]); Tm[10] = fmaf(w, a2.z, Tm[10]); Tm[11] = fmaf(w, a2.w, Tm[11]);
             }
         }
-#pragma unroll
-        for (int fh = 0; fh < FS / 2; fh++) {
-            const int ff = half * (FS / 2) + fh;
-            if (ff < nf) {
-                const float px = fmaf(bl[fh][0], 1.0f / 256.0f, vt0), py = fmaf(bl[fh][1], 1.0f / 256.0f, vt1), pz = fmaf(bl[fh][2], 1.0f / 256.0f, vt2);
-                float Tm[12];
-#pragma unroll
-                for (int e = 0; e < 12; e++) Tm[e] = 0.f;
-                const float4* A4 = reinterpret_cast<const float4*>(s_A + (size_t)ff * J * 12);
-                if (!dense) {
-#pragma unroll
-                    for (int e = 0; e < SK_MAX; e++)
-                        if (e < nb) {
-                            const float w = bw[e];
-                            const float4 a0 = A4[bj[e] * 3], a1 = A4[bj[e] * 3 + 1], a2 = A4[bj[e] * 3 + 2];
-                            Tm[0] = fmaf(w, a0.x, Tm[0]); Tm[1] = fmaf(w, a0.y, Tm[1]); Tm[2] = fmaf(w, a0.z, Tm[2]); Tm[3] = fmaf(w, a0.w, Tm[3]);
-                            Tm[4] = fmaf(w, a1.x, Tm[4]); Tm[5] = fmaf(w, a1.y, Tm[5]); Tm[6] = fmaf(w, a1.z, Tm[6]); Tm[7] = fmaf(w, a1.w, Tm[7]);
-                            Tm[8] = fmaf(w, a2.x, Tm[8]); Tm[9] = fmaf(w, a2.y, Tm[9]); Tm[10] = fmaf(w, a2.z, Tm[10]); Tm[11] = fmaf(w, a2.w, Tm[11]);
-                        }
-                } else {
-                    for (int jn = 0; jn < J; jn++) {
-                        const float w = __ldg(weightsT + (size_t)jn * V + vc);
-                        const float4 a0 = A4[jn * 3], a1 = A4[jn * 3 + 1], a2 = A4[jn * 3 + 2];
-                        Tm[0] = fmaf(w, a0.x, Tm[0]); Tm[1] = fmaf(w, a0.y, Tm[1]); Tm[2] = fmaf(w, a0.z, Tm[2]); Tm[3] = fmaf(w, a0.w, Tm[3]);
-                        Tm[4] = fmaf(w, a1.x, Tm[4]); Tm[5] = fmaf(w, a1.y, Tm[5]); Tm[6] = fmaf(w, a1.z, Tm[6]); Tm[7] = fmaf(w, a1.w, Tm[7]);
-                        Tm[8] = fmaf(w, a2.x, Tm[8]); Tm[9] = fmaf(w, a2.y, Tm[9]); Tm[10] = fmaf(w, a2.z, Tm[10]); Tm[11] = fmaf(w, a2.w, Tm[11]);
-                    }
-                }
-                so[lane * 3 + 0] = (Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3]) + s_t[ff * 4 + 0];
-                so[lane * 3 + 1] = (Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7]) + s_t[ff * 4 + 1];
-                so[lane * 3 + 2] = (Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11]) + s_t[ff * 4 + 2];
-                __syncwarp();
-                // 96 floats of this warp's 32 vertices are contiguous in verts[f][v0 .. v0+31][3]
-                float* dst = verts + ((size_t)(f0 + ff) * V + v0) * 3;
-                const int nfl = min(32, V - v0) * 3;          // floats of live vertices (<= 0 for a warp past the end)
-                if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-                    for (int i = lane * 2; i < nfl; i += 64) {
-                        if (i + 1 < nfl) *reinterpret_cast<float2*>(dst + i) = *reinterpret_cast<const float2*>(so + i);
-                        else dst[i] = so[i];
-                    }
-                } else {
-                    for (int i = lane; i < nfl; i += 32) dst[i] = so[i];
-                }
-                __syncwarp();
-            }
+        so[lane * 3 + 0] = (Tm[0] * px + Tm[1] * py + Tm[2] * pz + Tm[3]) + s_t[ff * 4 + 0];
+        so[lane * 3 + 1] = (Tm[4] * px + Tm[5] * py + Tm[6] * pz + Tm[7]) + s_t[ff * 4 + 1];
+        so[lane * 3 + 2] = (Tm[8] * px + Tm[9] * py + Tm[10] * pz + Tm[11]) + s_t[ff * 4 + 2];
+        __syncwarp();
+        // 96 floats of this warp's 32 vertices are contiguous in verts[f][v0 .. v0+31][3]
+        float* dst = verts + ((size_t)(f0 + ff) * V + v0) * 3;
+        if (nfl == 96 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+            *reinterpret_cast<float2*>(dst + lane * 2) = *reinterpret_cast<const float2*>(so + lane * 2);
+            if (lane < 16) *reinterpret_cast<float2*>(dst + 64 + lane * 2) = *reinterpret_cast<const float2*>(so + 64 + lane * 2);
+        } else {
+            for (int i = lane; i < nfl; i += 32) dst[i] = so[i];
         }
-        if (half == 0) {
-#pragma unroll
-            for (int ff = 0; ff < FS / 2; ff++) { bl[ff][0] = nx[ff][0]; bl[ff][1] = nx[ff][1]; bl[ff][2] = nx[ff][2]; }
-        }
+        __syncwarp();
     }
 }
 
@@ -386,6 +367,7 @@ extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const 
                     skj[(size_t)n * V + v] = (unsigned char)j; skw[(size_t)n * V + v] = w[(size_t)v * J + j]; n++;
                 }
             skn[v] = (unsigned char)n;
+            if (n > m.sk_max) m.sk_max = n;
         }
         CUDA_TRY(h, up(skn.data(), skn.size(), (void**)&m.sk_n)); CUDA_TRY(h, up(skj.data(), skj.size(), (void**)&m.sk_j));
         CUDA_TRY(h, up(skw.data(), skw.size() * 4, (void**)&m.sk_w));
@@ -455,7 +437,9 @@ extern "C" int idb_body_init(idb_handle* h, int V, int J, int NB, int Fc, const 
     const int smem_skin = (int)sizeof(float) * (Kp * FB + FB * J * 12 + NB * FB + FB * 3);
     if (smem_skin > 227 * 1024) return idb_fail(h, IDB_ERR_ARG, "body model too large for the SIMT skinning kernel's shared memory");
     CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin_sparse<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin_sparse<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_lbs_skin_sparse<SK_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     h->epoch++;
     return IDB_OK;
 }
@@ -497,8 +481,12 @@ extern "C" int idb_smplh_lbs(idb_handle* h, int F, const float* pose, const floa
         if ((rc = idb_gemm_ex(h, g, st))) return rc;
         const size_t smem = sizeof(float) * ((size_t)FS * m.J * 12 + FS * 4 + 8 * 96);
         dim3 grid((m.V + 255) / 256, (F + FS - 1) / FS);
-        k_lbs_skin_sparse<<<grid, 256, smem, st>>>(m.blend, m.Nb, m.v_templT, m.sk_n, m.sk_j, m.sk_w, m.weightsT, m.sk_dense ? 1 : 0, m.A,
-                                                    trans, verts, F, m.V, m.J);
+        if (m.sk_dense)
+            k_lbs_skin_sparse<0><<<grid, 256, smem, st>>>(m.blend, m.Nb, m.v_templT, m.sk_j, m.sk_w, m.weightsT, m.A, trans, verts, F, m.V, m.J);
+        else if (m.sk_max <= 4)
+            k_lbs_skin_sparse<4><<<grid, 256, smem, st>>>(m.blend, m.Nb, m.v_templT, m.sk_j, m.sk_w, m.weightsT, m.A, trans, verts, F, m.V, m.J);
+        else
+            k_lbs_skin_sparse<SK_MAX><<<grid, 256, smem, st>>>(m.blend, m.Nb, m.v_templT, m.sk_j, m.sk_w, m.weightsT, m.A, trans, verts, F, m.V, m.J);
         LAUNCH_CHECK(h);
     } else if (verts) {
         const size_t smem_skin = sizeof(float) * ((size_t)m.Kp * FB + (size_t)FB * m.J * 12 + (size_t)m.NB * FB + FB * 3);

@@ -51,3 +51,27 @@ __device__ __forceinline__ void idb_axis_angle_to_matrix(const float* aa, float*
     R[3] = two_s * (i * j + k * r);     R[4] = 1 - two_s * (i * i + k * k); R[5] = two_s * (j * k - i * r);
     R[6] = two_s * (i * k - j * r);     R[7] = two_s * (j * k + i * r);     R[8] = 1 - two_s * (i * i + j * j);
 }
+
+// quaternion_to_matrix (pytorch3d 0.7.2), real part first, NOT normalised (the 2 / |q|^2 factor does it)
+__device__ __forceinline__ void idb_quaternion_to_matrix(const float* q, float* R) {
+    const float r = q[0], i = q[1], j = q[2], k = q[3];
+    const float two_s = 2.0f / (r * r + i * i + j * j + k * k);
+    R[0] = 1 - two_s * (j * j + k * k); R[1] = two_s * (i * j - k * r);     R[2] = two_s * (i * k + j * r);
+    R[3] = two_s * (i * j + k * r);     R[4] = 1 - two_s * (i * i + k * k); R[5] = two_s * (j * k - i * r);
+    R[6] = two_s * (i * k - j * r);     R[7] = two_s * (j * k + i * r);     R[8] = 1 - two_s * (i * i + j * j);
+}
+// matrix_to_quaternion (pytorch3d 0.7.2): 4 candidates, argmax of q_abs (first maximum), no sign standardisation; q = (w,x,y,z)
+__device__ __forceinline__ void idb_matrix_to_quaternion(const float* m, float* q) {
+    const float m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5], m20 = m[6], m21 = m[7], m22 = m[8];
+    float qa[4] = {1.0f + m00 + m11 + m22, 1.0f + m00 - m11 - m22, 1.0f - m00 + m11 - m22, 1.0f - m00 - m11 + m22};
+    int best = 0;
+    for (int i = 0; i < 4; i++) qa[i] = qa[i] > 0.f ? sqrtf(qa[i]) : 0.f;
+    for (int i = 1; i < 4; i++) if (qa[i] > qa[best]) best = i;
+    float c[4];
+    if (best == 0) { c[0] = qa[0] * qa[0]; c[1] = m21 - m12; c[2] = m02 - m20; c[3] = m10 - m01; }
+    else if (best == 1) { c[0] = m21 - m12; c[1] = qa[1] * qa[1]; c[2] = m10 + m01; c[3] = m02 + m20; }
+    else if (best == 2) { c[0] = m02 - m20; c[1] = m10 + m01; c[2] = qa[2] * qa[2]; c[3] = m12 + m21; }
+    else { c[0] = m10 - m01; c[1] = m20 + m02; c[2] = m21 + m12; c[3] = qa[3] * qa[3]; }
+    const float den = 2.0f * fmaxf(qa[best], 0.1f);
+    q[0] = c[0] / den; q[1] = c[1] / den; q[2] = c[2] / den; q[3] = c[3] / den;
+}

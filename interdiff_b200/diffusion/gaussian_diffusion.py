@@ -3,8 +3,8 @@
 
 Same public surface the callers use: get_named_beta_schedule,
 ModelMeanType / ModelVarType / LossType, GaussianDiffusion.{q_sample, q_posterior_mean_variance,
-p_mean_variance, p_sample, p_sample_loop, p_sample_loop_progressive, num_timesteps}.  DDIM / PLMS /
-VB / training_losses are out of scope (never reached by the sampling scripts) and
+p_mean_variance, p_sample, p_sample_loop, p_sample_loop_progressive, training_losses (forward values),
+num_timesteps}.  DDIM / PLMS / VB are out of scope (never reached by the reference's scripts) and
 raise NotImplementedError.
 
 When `model` is an interdiff_b200 MDM the work runs in libinterdiff_b200.so: the whole loop as
@@ -216,7 +216,32 @@ class GaussianDiffusion:
             final = sample
         return dump if dump_steps is not None else final["sample"]
 
-    def training_losses(self, *a, **k):
-        raise NotImplementedError("training is out of scope of the sampling hot path (SURVEY.md 2a #16)")
+    def training_losses(self, model, x_start, t, model_kwargs=None, noise=None, dataset=None):
+        """Reference gaussian_diffusion.py:1233-1368 for the shipped configuration (MSE loss, START_X, FIXED_SMALL): returns
+        (model_output, target) exactly like upstream - x_t = q_sample(x_start, t, noise), the inpainting blend (:1264-1268),
+        one denoiser forward at the per-sample (re-spaced) timesteps, target = x_start.  The forward runs in the library, so
+        the pair carries VALUES only (no autograd graph): it serves the loss terms of validation / evaluation
+        (train_diffusion_smpl.py:66-120 computes them from this pair); optimising the weights is out of scope."""
+        if self.loss_type not in (LossType.MSE, LossType.RESCALED_MSE):
+            raise NotImplementedError(self.loss_type)
+        if model_kwargs is None:
+            model_kwargs = {}
+        if noise is None:
+            noise = th.randn_like(x_start)
+        x_t = self.q_sample(x_start, t, noise=noise)
+        y = model_kwargs["y"]
+        if "inpainting_mask" in y.keys() and "inpainted_motion" in y.keys():
+            m, gt = y["inpainting_mask"], y["inpainted_motion"]
+            assert x_t.shape == m.shape == gt.shape
+            x_t = (x_t * ~m) + (gt * m)
+        ts = th.tensor(self.timestep_map, device=t.device, dtype=t.dtype)[t]       # _WrappedModel (respace.py:118-129)
+        with th.no_grad():
+            model_output = model(x_t, ts, **model_kwargs)
+        target = x_start
+        assert model_output.shape == target.shape == x_start.shape
+        return model_output, target
 
-    ddim_sample = ddim_sample_loop = plms_sample = plms_sample_loop = training_losses
+    def _not_on_the_path(self, *a, **k):
+        raise NotImplementedError("DDIM / PLMS sampling is never called by the reference's scripts (SURVEY.md 2a #1)")
+
+    ddim_sample = ddim_sample_loop = plms_sample = plms_sample_loop = _not_on_the_path

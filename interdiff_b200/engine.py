@@ -400,6 +400,36 @@ class Engine:
         self.past_len, self.future_len = past_len, future_len
         self._projector_owner = None
 
+    def load_projector_skeleton(self, state_dict, past_len, future_len, n_joints=21):
+        """the skeleton correction net (reference model/correction_skeleton.py, checkpoints/obj_skeleton.ckpt)"""
+        self._chk(self.lib.idb_projector_init_skeleton(self._h, past_len, future_len, n_joints))
+        for name, w in state_dict.items():
+            if not torch.is_tensor(w):
+                w = torch.as_tensor(np.asarray(w))
+            if not w.dtype.is_floating_point:
+                continue
+            w = w.detach().to(dtype=torch.float32).contiguous()
+            self._chk(self.lib.idb_projector_load(self._h, name.encode(), C.c_void_p(w.data_ptr()), _shape_arr(w.shape), w.dim()))
+        self._chk(self.lib.idb_projector_commit(self._h))
+        self.past_len, self.future_len = past_len, future_len
+        self._projector_owner = None
+
+    def projector_sample_skeleton(self, obj_quat, obj_trans, joints):
+        """ObjProjector.sample of the skeleton net: (T,B,4) xyzw, (T,B,3), (T,B,J,3) -> (quat (T,B,4), trans (T,B,3))"""
+        q, t, j = self._f32(obj_quat), self._f32(obj_trans), self._f32(joints)
+        T, B, _ = q.shape
+        qo, to = torch.empty(T, B, 4, device=self.device), torch.empty(T, B, 3, device=self.device)
+        self._chk(self.lib.idb_projector_sample_skeleton(self._h, T, B, self._ptr(q), self._ptr(t), self._ptr(j), self._ptr(qo), self._ptr(to), self._stream()))
+        return qo, to
+
+    def skeleton_correction_apply(self, x0, gt, zero_pose_obj, t):
+        """In place on x0 (B,1,106,T): the body of the skeleton denoised_fn (eval_skeleton.py:80-111) for an active step."""
+        assert x0.is_cuda and x0.is_contiguous() and x0.dtype == torch.float32
+        gt, zp = self._f32(gt), self._f32(zero_pose_obj)
+        B, _, _, T = x0.shape
+        self._chk(self.lib.idb_skeleton_correction_apply(self._h, B, T, zp.shape[1], self._ptr(x0), self._ptr(gt), self._ptr(zp), int(t), self._stream()))
+        return x0
+
     def bind_correction(self, hand_pose, betas, obj_points, past_len=None, marker_ids=None, hand_marker_ids=None):
         hand_pose, betas, obj_points = self._f32(hand_pose), self._f32(betas), self._f32(obj_points)
         T, B, _ = hand_pose.shape

@@ -105,6 +105,28 @@ def projector_shapes(P=67, n_pre=10):
     return s
 
 
+def projector_skeleton_shapes(P=21, n_pre=20):
+    """skeleton correction net (reference model/correction_skeleton.py:13-50): joint stack 9-64-32-64-9"""
+    s = {}
+    for stack, nodes, ver, chans in (("st_gcnns_relative", P, 0, [9, 32, 16, 32, 9]), ("st_gcnns", 1, 0, [9, 32, 16, 32, 9]),
+                                     ("st_gcnns_all", P + 1, 2, [9, 64, 32, 64, 9])):
+        for i in range(4):
+            p = "%s.%d." % (stack, i)
+            cin, cout = chans[i], chans[i + 1]
+            if ver == 0:
+                s[p + "gcn.T"] = (n_pre, n_pre)
+            else:
+                s[p + "gcn.A"] = (n_pre, nodes, nodes)
+                s[p + "gcn.T"] = (nodes, n_pre, n_pre)
+            for blk in ("tcn", "residual"):
+                s[p + blk + ".0.weight"] = (cout, cin, 1, 1)
+                s[p + blk + ".0.bias"] = (cout,)
+                for leaf in ("weight", "bias", "running_mean", "running_var"):
+                    s[p + blk + ".1." + leaf] = (cout,)
+            s[p + "prelu.weight"] = (1,)
+    return s
+
+
 def random_state_dict(shapes, seed=233):
     return synthetic.fill_state_dict(shapes, seed)
 
@@ -137,6 +159,8 @@ def bench_weights(name, seed=233):
     if sd is None:
         if name == "correction_smpl":
             shapes = projector_shapes()
+        elif name == "correction_skeleton":
+            shapes = projector_skeleton_shapes()
         elif name == "diffusion_smpl_encoder":
             shapes = {**mdm_encoder_shapes("smpl"), **pointnet_shapes()}
         else:

@@ -18,6 +18,7 @@ def main():
     jobs = (("diffusion", "diffusion_smpl", W.mdm_hot_shapes("smpl", F=1024)),
             ("diffusion_skeleton", "diffusion_skeleton", W.mdm_hot_shapes("skeleton", F=256)),
             ("correction", "correction_smpl", W.projector_shapes()),
+            ("obj_skeleton", "correction_skeleton", W.projector_skeleton_shapes()),
             # conditioning encoder: its own file, only the encoder tests load it
             ("diffusion", "diffusion_smpl_encoder", {**W.mdm_encoder_shapes("smpl", F=1024), **W.pointnet_shapes()}))
     for ck, out, shapes in jobs:

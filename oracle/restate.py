@@ -689,3 +689,23 @@ def rollout_next_window(body, obj, jtr, T, past_len):
                         r6(o[..., :3].reshape(P, B, 1, 3)).reshape(P, B, 6), o[..., 3:6] - centroid], dim=2)
     frames = torch.cat([frames, frames[-1:].repeat(T - P, 1, 1)], dim=0)
     return frames.permute(1, 2, 0).unsqueeze(1).contiguous(), centroid
+
+
+def make_denoised_fn_skeleton(ctx):
+    """denoised_fn of eval_skeleton.py:80-111 restated.  ctx: gt (B,1,106,T), zero_pose_obj (B,12,3), projector (state dict of the
+    skeleton correction net), past_len, future_len.  (body_obj_to_contact (:96) is evaluated upstream but its result is unused.)"""
+    def denoised_fn(x, t, model_kwargs=None):
+        if t[0] > 500 or t[0] % 50 != 0:
+            return x
+        xs = x.squeeze(1).permute(2, 0, 1).contiguous()
+        body_pred = xs[..., :63]
+        gts = ctx["gt"].squeeze(1).permute(2, 0, 1).contiguous()
+        pose_gt = gts[..., 99:106]
+        T, B, _ = body_pred.shape
+        q, tr = obj_projector_skeleton_sample(ctx["projector"], pose_gt[..., 3:7], pose_gt[..., :3], body_pred.reshape(T, B, -1, 3),
+                                              ctx["past_len"], ctx["future_len"])
+        pose_proj = torch.cat([tr, q], dim=2)
+        obj_proj = skeleton_obj_from_pose(pose_proj, ctx["zero_pose_obj"]).reshape(T, B, -1)
+        x_ = torch.cat([body_pred, obj_proj, pose_proj], dim=2).permute(1, 2, 0).unsqueeze(1).contiguous()
+        return t[0] / 1000 * x + (1 - t[0] / 1000) * x_
+    return denoised_fn

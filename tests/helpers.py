@@ -61,6 +61,18 @@ def projector_weights(source="auto", seed=233):
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
 
 
+def projector_skeleton_weights(source="auto", seed=235):
+    sd = None
+    if source in ("ref", "auto"):
+        sd = W.load_ref_weights("correction_skeleton")
+        if sd is None and source == "ref":
+            import pytest
+            pytest.skip("exported reference weights not present")
+    if sd is None:
+        sd = W.random_state_dict(W.projector_skeleton_shapes(), seed)
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+
+
 def smplh_torch(smplh_np):
     return {k: torch.from_numpy(np.asarray(v)) for k, v in smplh_np.items()}
 

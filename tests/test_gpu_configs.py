@@ -614,3 +614,78 @@ def test_rollout_next_window_and_driver(eng, smplh_np):
     assert rel(traj["body"], torch.cat(bodies)) < 1e-5
     # continuity: the inpainted past of window k+1 (frames [P + k F - P .. ) in world coordinates) IS the end of window k
     assert torch.isfinite(traj["pelvis"]).all()
+
+
+@pytest.mark.parametrize("source", ["random", "ref"])
+def test_skeleton_correction(eng, source):
+    """the skeleton correction net on the device (model/correction_skeleton.py:84-135; templated projector
+    kernel, n_pre 20, joint stack 9-64-32-64-9), its hook (eval_skeleton.py:80-111) and the in-loop path of the skeleton
+    sampler, against the oracle (which is pinned to the reference class with checkpoints/obj_skeleton.ckpt)."""
+    from tests.helpers import projector_skeleton_weights
+    psd = projector_skeleton_weights(source)
+    P, Fu = 10, 10
+    T, B = P + Fu, 4
+    eng.load_projector_skeleton(psd, P, Fu, n_joints=21)
+    g = torch.Generator().manual_seed(31)
+    quat = torch.randn(T, B, 4, generator=g)
+    quat[0, 0] = torch.tensor([0.0, 0.0, 0.0, 2.0])                       # un-normalised identity
+    tr, joints = torch.randn(T, B, 3, generator=g), torch.randn(T, B, 21, 3, generator=g)
+    q, t = eng.projector_sample_skeleton(quat, tr, joints)
+    with torch.no_grad():
+        q_ref, t_ref = R.obj_projector_skeleton_sample(psd, quat, tr, joints, P, Fu)
+    assert rel(q, q_ref) < 1e-4 and rel(t, t_ref) < 1e-4
+    # the mirrored module (strict checkpoint names) routes to the same kernel
+    from interdiff_b200.model.correction_skeleton import ObjProjector
+    proj = ObjProjector(Namespace(num_joints=21, dropout=0.0, past_len=P, future_len=Fu, embedding_dim=128))
+    own = proj.state_dict()
+    proj.load_state_dict({k: (psd[k].reshape(own[k].shape) if k in psd else v) for k, v in own.items()}, strict=True)
+    q2, t2 = proj.cuda().eval().sample(quat.cuda(), tr.cuda(), joints.cuda())
+    assert torch.equal(q2, q) and torch.equal(t2, t)
+    # hook body at an active step
+    b = S.make_skeleton_batch(B=B, T=T)
+    gt, zp = torch.from_numpy(b["gt"]), torch.from_numpy(b["zero_pose_obj"])
+    x = gt + 0.05 * torch.randn(gt.shape, generator=g)
+    ctx = dict(gt=gt, zero_pose_obj=zp, projector=psd, past_len=P, future_len=Fu)
+    with torch.no_grad():
+        want = R.make_denoised_fn_skeleton(ctx)(x.clone(), torch.full((B,), 450), None)
+    got = eng.skeleton_correction_apply(x.clone().cuda(), gt, zp, 450)
+    assert rel(got, want) < 1e-4
+    # in the sampling loop of the skeleton denoiser: hook at i = 50 and i = 0 of a 52-step schedule
+    sd = mdm_weights("skeleton", "random")
+    eng.load_denoiser(sd, "skeleton")
+    eng.bind(b["cond"], T, zero_pose_obj=b["zero_pose_obj"])
+    steps = 52
+    betas = R.named_beta_schedule("cosine", steps)
+    eng.init_diffusion(betas)
+    tape = torch.from_numpy(S.noise_tape(b["gt"].shape, steps))
+    mask, cond = torch.from_numpy(b["mask"]), torch.from_numpy(b["cond"])
+    fwd = lambda xx, tt: R.mdm_skeleton_forward(sd, xx, tt, zp, cond)
+    with torch.no_grad():
+        ref = R.p_sample_loop(fwd, R.diffusion_tables(betas), tape, gt, mask, denoised_fn=R.make_denoised_fn_skeleton(ctx))
+        plain = R.p_sample_loop(fwd, R.diffusion_tables(betas), tape, gt, mask)
+    outs = [eng.p_sample_loop(tape.cuda(), gt.cuda(), mask.cuda(), correction=True, use_graph=m).cpu() for m in ("loop", "step", "off")]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert rel(outs[0], ref) < 1e-3 and rel(plain, ref) > 1e-3
+
+
+def test_training_losses_forward_values():
+    """SURVEY 8f rank 4 (second half): diffusion.training_losses(model, x_start, t, model_kwargs, noise) -> (model_output,
+    target) as train_diffusion_smpl.py:61-70 binds it, with per-sample timesteps, against the oracle's forward on the same
+    q_sample."""
+    model, diffusion, msd = _mirror_model(1000)
+    B, T = 4, 30
+    b = S.make_smpl_batch(B=B, T=T)
+    gt, mask, cond = torch.from_numpy(b["gt"]).cuda(), torch.from_numpy(b["mask"]).cuda(), torch.from_numpy(b["cond"]).cuda()
+    t = torch.tensor([999, 500, 37, 0], device="cuda")
+    noise = torch.randn(gt.shape, generator=torch.Generator().manual_seed(2)).cuda()
+    kw = {"y": {"cond": cond, "inpainted_motion": gt, "inpainting_mask": mask}}
+    out, target = diffusion.training_losses(model, gt, t, model_kwargs=kw, noise=noise)
+    assert torch.equal(target, gt) and out.shape == gt.shape
+    tables = R.diffusion_tables(R.named_beta_schedule("cosine", 1000))
+    a = torch.tensor(tables["sqrt_alphas_cumprod"])[t.cpu()].float().view(B, 1, 1, 1)
+    s1 = torch.tensor(tables["sqrt_one_minus_alphas_cumprod"])[t.cpu()].float().view(B, 1, 1, 1)
+    x_t = a * gt.cpu() + s1 * noise.cpu()
+    x_t = (x_t * ~mask.cpu()) + (gt.cpu() * mask.cpu())
+    with torch.no_grad():
+        ref = R.mdm_smpl_forward({k: v.cpu() for k, v in msd.items()}, x_t, t.cpu(), cond.cpu(), faithful=False)
+    assert rel(out, ref) < 3e-4

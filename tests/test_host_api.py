@@ -97,3 +97,16 @@ def test_diffusion_tables_and_spacing():
                                  model_var_type=RL.modules()["diffusion.gaussian_diffusion"].ModelVarType.FIXED_SMALL,
                                  loss_type=RL.modules()["diffusion.gaussian_diffusion"].LossType.MSE)
         assert np.array_equal(rd.betas, d.betas) and rd.timestep_map == d.timestep_map
+
+
+def test_skeleton_projector_mirror_loads_checkpoint_strictly():
+    """interdiff_b200.model.correction_skeleton.ObjProjector carries the reference's state_dict names (obj_skeleton.ckpt)"""
+    if not RL.available():
+        pytest.skip("reference tree not present")
+    from interdiff_b200.model.correction_skeleton import ObjProjector
+    hp, sd = RL.load_ckpt("obj_skeleton")
+    m = ObjProjector(Namespace(**hp))
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    from interdiff_b200 import weights as W2
+    assert set(W2.projector_skeleton_shapes()) == {k for k in sd if "num_batches_tracked" not in k}

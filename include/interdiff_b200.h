@@ -205,6 +205,9 @@ int idb_rollout_next_window(idb_handle* h, int T, int B, int J, int Db, int past
                             const float* jtr, float* gt_out, float* centroid_out, void* stream);
 int idb_add_offset(idb_handle* h, int T, int B, int K, long long ld, int col0, float* x, const float* offset, float sign, void* stream);
 
+/* profiling hook: 8-CTA clusters of the fused decoder-layer kernel that fit on the device at once (-1 on error) */
+int idb_debug_max_layer_clusters(idb_handle* h);
+
 /* ---- kernel-level hook (tests / bench roofline leg) -----------------------------------------
  * C[M,N] = epi(A[M,K] . W[N,K]^T) with the handle's GEMM backend; epi bit 0 bias, 1 GELU(erf),
  * 2 residual add, 3 SiLU (the fused epilogues of the nn.Linear calls of the denoiser). */

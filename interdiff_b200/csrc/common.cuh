@@ -113,7 +113,10 @@ struct idb_handle {
     unsigned attr_mask = 0;   // kernels whose > 48 KB shared-memory opt-in was done on this handle's device (bit 0 GEMM, 1 MLP, 2 NN)
     double last_ms = 0.0;     // mean launch time of the last timed debug hook
     int nn_pruning = 1;       // cluster-pruned nearest-neighbour search for body-mesh targets (identical results)
-    int fused_mlp = 2;        // feed-forward block as ONE cluster kernel (tensor backend, d_model 256, d_ff 1024); 2 = incl. the layer's final norm
+    int fused_mlp = 2;        // feed-forward block as ONE cluster kernel (tensor backend, d_model 256, d_ff 1024); 2 = incl. the layer's final norm;
+                              // 3 = a layer's attention half runs in the same kernel on sample-aligned tiles (one launch per layer):
+                              // measured NOT faster (288.6 vs 282.3 us per step at B=60: programmatic dependent launch already hides the
+                              // boundary) and at B=64 it needs 16 clusters where the device holds 15 (profiles/README.md) - kept as an option
     void* metrics_ws = nullptr; size_t metrics_bytes = 0;        // workspace of idb_metrics (posed object points, normals, signed distances)
     void* scratch = nullptr; size_t scratch_bytes = 0;   // on-the-fly operand splits of idb_gemm
     Denoiser den;

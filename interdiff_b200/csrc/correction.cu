@@ -71,7 +71,7 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
             const ProjLayer L = layers[l0 + li];
             const int cin = L.cin, cout = L.cout, npos = NQ * Pn;
             if (L.ver == 0) {
-                if (tid < NQ * NQ) s_T[tid] = L.Tm[tid];
+                for (int i = tid; i < NQ * NQ; i += 256) s_T[i] = L.Tm[i];
                 __syncthreads();
                 for (int it = tid; it < cin * Pn; it += 256) {
                     const int c = it / Pn, p = it % Pn;
@@ -496,8 +496,12 @@ extern "C" int idb_projector_commit(idb_handle* h) {
         }
     if ((rc = up(dct, &p.dct)) || (rc = up(idct, &p.idct))) return rc;
     // per-function, per-device opt-in: always the device maximum (a smaller value set by another handle must not undercut it)
-    CUDA_TRY(h, cudaFuncSetAttribute(k_projector<10, 32, 68>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_projector<20, 64, 22>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // (the kernels also hold a few bytes of static shared memory: the dynamic limit is the device maximum minus that)
+    cudaFuncAttributes fa;
+    CUDA_TRY(h, cudaFuncGetAttributes(&fa, k_projector<10, 32, 68>));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_projector<10, 32, 68>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
+    CUDA_TRY(h, cudaFuncGetAttributes(&fa, k_projector<20, 64, 22>));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_projector<20, 64, 22>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
     p.committed = true;
     h->epoch++;
     return IDB_OK;

@@ -7,6 +7,7 @@
 // is what the 3-tap QaN filter and the per-sample attention want), features contiguous.
 // All arithmetic fp32 (see gemm.cu header for why).
 #include "common.cuh"
+#include "tc_mlp.cuh"
 
 #include <cstdarg>
 
@@ -270,12 +271,17 @@ __device__ __forceinline__ void load_b_frag_cols(const float* __restrict__ s, in
 //   out[r]  = LN( res[r] + bo + sum_h sum_j softmax_j(q_h[r].k_h[j] / 8) v'_h[j] )
 // Both products run on fp16-pair fragments: logits = 16 (head, 8-key tile) units of 4 k-steps, one
 // per warp; values = [16 x 4T] x [4T x 256], two 8-column tiles per warp.
-__global__ void __launch_bounds__(ANT)
-k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v, int ldv,
-          const float* __restrict__ res, const float* __restrict__ bo, const float* __restrict__ lnw,
-          const float* __restrict__ lnb, float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s,
-          int T, int H) {
-    extern __shared__ __align__(16) float sm[];
+struct AttnArgs {
+    const float* q; int ldq; const float* k; int ldk; const float* v; int ldv; const float *res, *bo, *lnw, *lnb;
+    float* out; __half *out_b, *out_s; int T, H;
+};
+// slab (sample b, rows r0 ..) on caller-provided shared memory (attn_smem() bytes); also phase A1 of the fused standard layer
+__device__ __forceinline__ void attn_body(const AttnArgs& aa, float* sm, const int b, const int r0) {
+    const float* __restrict__ q = aa.q; const float* __restrict__ k = aa.k; const float* __restrict__ v = aa.v;
+    const float* __restrict__ res = aa.res; const float* __restrict__ bo = aa.bo; const float* __restrict__ lnw = aa.lnw;
+    const float* __restrict__ lnb = aa.lnb; float* __restrict__ out = aa.out; __half* __restrict__ out_b = aa.out_b;
+    __half* __restrict__ out_s = aa.out_s;
+    const int ldq = aa.ldq, ldk = aa.ldk, ldv = aa.ldv, T = aa.T, H = aa.H;
     constexpr int LDK = HD + 8;            // key-slice stride (8 mod 32)
     const int Tk = T, HT = H * Tk, HT16 = (HT + 15) & ~15, pld = ((HT16 + 23) / 32) * 32 + 8;   // pld: >= HT16, 8 mod 32
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: parameters, [1]: activations
@@ -285,7 +291,7 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
     float* s_v = s_z + SLAB * LDZ;         // [H*Tk][VLD]   folded values
     float* s_k = s_v + (size_t)HT * VLD;   // [H*Tk][LDK]   key head slices ...
     float* s_p = s_k;                      // [SLAB][pld]   ... then (after a barrier) logits / probabilities
-    const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
+    const int nr = min(SLAB, T - r0), tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
     pdl_trigger();
     if (tid == 0) {
@@ -399,6 +405,12 @@ k_attn_ln(const float* __restrict__ q, int ldq, const float* __restrict__ k, int
         const size_t o = (size_t)(b * T + r0 + r) * D;
         warp_ln_row(s_z + r * LDZ, s_par + D, s_par + 2 * D, out + o, lane, out_b ? out_b + o : nullptr, out_s ? out_s + o : nullptr);
     }
+}
+
+__global__ void __launch_bounds__(ANT)
+k_attn_ln(const AttnArgs aa) {
+    extern __shared__ __align__(16) float sm[];
+    attn_body(aa, sm, blockIdx.x, blockIdx.y * SLAB);
 }
 
 // Step-invariant B operands (folded queries, folded memory keys / values) are split into fp16 (hi, lo) ONCE (at
@@ -554,11 +566,18 @@ __device__ __forceinline__ void stage_memory(const __half* __restrict__ kph, con
 }
 
 // standalone cross-attention block (layers whose first sub-block is the standard self-attention)
-__global__ void __launch_bounds__(ANT)
-k_xattn_ln(const float* __restrict__ x1, const __half* __restrict__ kph, const __half* __restrict__ kpl, const float* __restrict__ kc,
-           const uint32_t* __restrict__ vph, const uint32_t* __restrict__ vpl, const float* __restrict__ bo, const float* __restrict__ lnw, const float* __restrict__ lnb, float* __restrict__ out,
-           __half* __restrict__ out_b, __half* __restrict__ out_s, int T, int B, int Tk, int H) {
-    extern __shared__ __align__(16) float sm[];
+struct XattnArgs {
+    const float* x1; const __half *kph, *kpl; const float* kc; const uint32_t *vph, *vpl; const float *bo, *lnw, *lnb;
+    float* out; __half *out_b, *out_s; int T, B, Tk, H;
+};
+// own_rows: the x1 rows were written by THIS CTA with plain stores just before (fused standard layer): read them back with
+// plain L2 loads instead of bulk copies (which would need a proxy fence)
+__device__ __forceinline__ void xattn_body(const XattnArgs& xa, float* sm, const int b, const int r0, const bool own_rows) {
+    const float* __restrict__ x1 = xa.x1; const __half* __restrict__ kph = xa.kph; const __half* __restrict__ kpl = xa.kpl;
+    const float* __restrict__ kc = xa.kc; const uint32_t* __restrict__ vph = xa.vph; const uint32_t* __restrict__ vpl = xa.vpl;
+    const float* __restrict__ bo = xa.bo; const float* __restrict__ lnw = xa.lnw; const float* __restrict__ lnb = xa.lnb;
+    float* __restrict__ out = xa.out; __half* __restrict__ out_b = xa.out_b; __half* __restrict__ out_s = xa.out_s;
+    const int T = xa.T, B = xa.B, Tk = xa.Tk, H = xa.H;
     const int HT = H * Tk;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: step-invariant tensors, [1]: input rows
     float* s_par = sm + 4;                  // bo, lnw, lnb
@@ -570,7 +589,7 @@ k_xattn_ln(const float* __restrict__ x1, const __half* __restrict__ kph, const _
     float* s_a = reinterpret_cast<float*>(s_vpl + (HT >> 1) * VPW);    // [SLAB][PLD]     probabilities
     float* s_z = s_a + SLAB * PLD;          // [SLAB][LDZ]
     float* s_kc = s_z + SLAB * LDZ;         // [HT]
-    const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
+    const int nr = min(SLAB, T - r0), tid = threadIdx.x;
     pdl_trigger();
     if (tid == 0) {
         mb_init(bar, 1); mb_init(bar + 1, 1);
@@ -584,14 +603,27 @@ k_xattn_ln(const float* __restrict__ x1, const __half* __restrict__ kph, const _
     __syncwarp();
     stage_memory(kph, kpl, kc, vph, vpl, s_kph, s_kpl, s_kc, s_vph, s_vpl, b, B, Tk, H, bar);     // step-invariant: overlaps the previous kernel
     pdl_wait();
-    if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)nr * ROW_BYTES);
-    __syncwarp();
-    if (tid < nr) bulk_g2s(s_x1 + tid * LDX, x1 + (size_t)(b * T + r0 + tid) * D, ROW_BYTES, bar + 1);
+    if (own_rows) {
+        for (int i = tid; i < nr * (D / 4); i += ANT) {
+            const int l = i / (D / 4), c = i % (D / 4);
+            *reinterpret_cast<float4*>(s_x1 + l * LDX + c * 4) = __ldcg(reinterpret_cast<const float4*>(x1 + (size_t)(b * T + r0 + l) * D) + c);
+        }
+    } else {
+        if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)nr * ROW_BYTES);
+        __syncwarp();
+        if (tid < nr) bulk_g2s(s_x1 + tid * LDX, x1 + (size_t)(b * T + r0 + tid) * D, ROW_BYTES, bar + 1);
+    }
     mb_wait(bar, 0);
-    mb_wait(bar + 1, 0);
-    __syncthreads();     // s_kc was written with plain stores
+    if (!own_rows) mb_wait(bar + 1, 0);
+    __syncthreads();     // s_kc (and own rows) were written with plain stores
     cross_attention_tail(s_x1, s_kph, s_kpl, s_kc, s_vph, s_vpl, s_a, s_z, nr, HT, Tk, H, s_par, s_par + D, s_par + 2 * D, out, out_b,
                          out_s, (size_t)b * T + r0);
+}
+
+__global__ void __launch_bounds__(ANT)
+k_xattn_ln(const XattnArgs xa) {
+    extern __shared__ __align__(16) float sm[];
+    xattn_body(xa, sm, blockIdx.x, blockIdx.y * SLAB, false);
 }
 
 // QaN block + residual + LayerNorm1 (model/sublayers.py:343-352 + :332) for a slab of <= 16 rows of
@@ -602,15 +634,22 @@ k_xattn_ln(const float* __restrict__ x1, const __half* __restrict__ kph, const _
 //   a = softmax over the valid slots;  y[t] = sum_s (sum_n wk[n] a[t,n,s]) x[t+s-1];  out = LN1(x + y)
 // ... followed, in the same kernel, by the layer's cross-attention block (cross_attention_tail) on the
 // LN1 rows, which never leave shared memory.
+struct QanArgs {
+    const float *zin, *prew, *preb; const __half *qth, *qtl; const float *wk, *lnw, *lnb; const __half *kph, *kpl; const float* kc;
+    const uint32_t *vph, *vpl; const float *bo2, *ln2w, *ln2b; float* out; __half *out_b, *out_s; int T, N, B, Tk, H;
+};
+// the slab (sample b, rows r0 .. r0 + 15) of the kernel below as a device function on caller-provided shared memory `sm`
+// (16-byte aligned, qan_smem() bytes): also phase A of the fused decoder-layer kernel
 template <bool XATTN>
-__global__ void __launch_bounds__(ANT)
-k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, const float* __restrict__ preb,
-               const __half* __restrict__ qth, const __half* __restrict__ qtl, const float* __restrict__ wk, const float* __restrict__ lnw,
-               const float* __restrict__ lnb, const __half* __restrict__ kph, const __half* __restrict__ kpl, const float* __restrict__ kc,
-               const uint32_t* __restrict__ vph, const uint32_t* __restrict__ vpl, const float* __restrict__ bo2, const float* __restrict__ ln2w,
-               const float* __restrict__ ln2b, float* __restrict__ out, __half* __restrict__ out_b, __half* __restrict__ out_s,
-               int T, int N, int B, int Tk, int H) {
-    extern __shared__ __align__(16) float sm[];
+__device__ __forceinline__ void qan_xattn_body(const QanArgs& qa, float* sm, const int b, const int r0) {
+    const float* __restrict__ zin = qa.zin; const float* __restrict__ prew = qa.prew; const float* __restrict__ preb = qa.preb;
+    const __half* __restrict__ qth = qa.qth; const __half* __restrict__ qtl = qa.qtl; const float* __restrict__ wk = qa.wk;
+    const float* __restrict__ lnw = qa.lnw; const float* __restrict__ lnb = qa.lnb; const __half* __restrict__ kph = qa.kph;
+    const __half* __restrict__ kpl = qa.kpl; const float* __restrict__ kc = qa.kc; const uint32_t* __restrict__ vph = qa.vph;
+    const uint32_t* __restrict__ vpl = qa.vpl; const float* __restrict__ bo2 = qa.bo2; const float* __restrict__ ln2w = qa.ln2w;
+    const float* __restrict__ ln2b = qa.ln2b; float* __restrict__ out = qa.out; __half* __restrict__ out_b = qa.out_b;
+    __half* __restrict__ out_s = qa.out_s;
+    const int T = qa.T, N = qa.N, B = qa.B, Tk = qa.Tk, H = qa.H;
     const int HT = H * Tk, NQ = 3 * N;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: step-invariant tensors, [1]: input rows
     float* s_par = sm + 4;                  // pre w, pre b, ln1 w, ln1 b, bo2, ln2 w, ln2 b
@@ -625,7 +664,7 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     float* s_a = reinterpret_cast<float*>(s_vpl + (HT >> 1) * VPW);      // [SLAB][PLD]     probabilities
     float* s_z = XATTN ? s_a + SLAB * PLD : s_x1;   // [SLAB][LDZ]  (encoder variant: no cross-attention buffers at all)
     float* s_kc = s_z + SLAB * LDZ;         // [HT]
-    const int b = blockIdx.x, r0 = blockIdx.y * SLAB, nr = min(SLAB, T - r0), tid = threadIdx.x;
+    const int nr = min(SLAB, T - r0), tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     // Everything the kernel reads from global memory is requested up front as row-sized bulk copies: first
     // the step-invariant tensors (parameters, folded queries, folded memory keys / values), which overlap
@@ -767,6 +806,98 @@ k_qan_xattn_ln(const float* __restrict__ zin, const float* __restrict__ prew, co
     cross_attention_tail(s_x1, s_kph, s_kpl, s_kc, s_vph, s_vpl, s_a, s_z, nr, HT, Tk, H, s_par + 4 * D, s_par + 5 * D, s_par + 6 * D,
                          out, out_b, out_s, (size_t)b * T + r0, true);
     ATRACE(11);
+}
+
+template <bool XATTN>
+__global__ void __launch_bounds__(ANT)
+k_qan_xattn_ln(const QanArgs qa) {
+    extern __shared__ __align__(16) float sm[];
+    qan_xattn_body<XATTN>(qa, sm, blockIdx.x, blockIdx.y * SLAB);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One QaN decoder layer in ONE launch: QaN block + LN1 + cross-attention + LN2 (phase A, the kernel above as a device
+// function) and the feed-forward block + the layer's final LayerNorm (phase B, tc::mlp_run).  A cluster of 8 CTAs owns G whole
+// samples (G = 8 / ceil(T / 16): 4 samples = 120 rows for T = 30): in phase A CTA c takes slab c % nslabs of the cluster's
+// sample c / nslabs; the LN2 rows (fp32 for the residual, fp16 pairs for the tensor core) go to global memory (L2); after a
+// cluster barrier the same 8 CTAs run the feed-forward block on the cluster's rows as one 128-row tile (rows past G T belong to
+// the next cluster: computed, never reduced or stored).  Tiles aligned to samples mean NO dependency between clusters, so the
+// kernel boundary between the two halves of a layer disappears.  The attention phase uses the operand region of the
+// feed-forward block as its shared memory; the feed-forward barriers and the TMEM allocation sit above it and are set up at entry.
+__global__ void __cluster_dims__(tc::mlp::CLUSTER, 1, 1) __launch_bounds__(ANT, 1)
+k_layer_qan_fused(const QanArgs qa, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+                  const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_w1l,
+                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2l,
+                  const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ res, float* __restrict__ Z,
+                  const float* __restrict__ ln_w, const float* __restrict__ ln_b, __half* __restrict__ Zh, __half* __restrict__ Zl,
+                  int M, int G, int nslabs) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_trigger();
+    const int c = blockIdx.x, cl = blockIdx.y, tid = threadIdx.x;
+    tc::MlpArgs a{&map_x, &map_w1, &map_xl, &map_w1l, &map_w2, &map_w2l, b1, b2, res, D, Z, D, ln_w, ln_b, Zh, Zl, nullptr};
+    const uint32_t tmem_base = tc::mlp_setup(smem_raw, a);
+    // ---- phase A
+    const int sl = c / nslabs, b = cl * G + sl;
+    const bool attend = sl < G && b < qa.B;
+    if (attend) qan_xattn_body<true>(qa, reinterpret_cast<float*>(smem_raw), b, (c % nslabs) * SLAB);
+    else pdl_wait();
+    // this CTA's rows (plain stores) must be visible to the TMA reads and plain loads of the whole cluster
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (tid == 0 && attend) {   // the attention phase's two mbarriers sit in memory the operand ring is about to overwrite
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr(smem_raw)) : "memory");
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr(smem_raw) + 8u) : "memory");
+    }
+    tc::cluster_sync_all();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    // ---- phase B
+    const int m0 = cl * G * qa.T;
+    tc::mlp_run(smem_raw, a, c, m0, min(M, m0 + G * qa.T), tmem_base, false, nullptr);
+    tc::mlp_teardown(tmem_base);
+}
+
+// The same for a standard decoder layer (layers 0 and 7): self-attention + LN1 (phase A1, on the folded-QKV projection a
+// GEMM launch produced), cross-attention + LN2 (phase A2, on the rows phase A1 just wrote), feed-forward + LN3 (phase B).
+__global__ void __cluster_dims__(tc::mlp::CLUSTER, 1, 1) __launch_bounds__(ANT, 1)
+k_layer_std_fused(const AttnArgs aa, const XattnArgs xa, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
+                  const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_w1l,
+                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2l,
+                  const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ res, float* __restrict__ Z,
+                  const float* __restrict__ ln_w, const float* __restrict__ ln_b, __half* __restrict__ Zh, __half* __restrict__ Zl,
+                  int M, int G, int nslabs) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    pdl_trigger();
+    const int c = blockIdx.x, cl = blockIdx.y, tid = threadIdx.x;
+    tc::MlpArgs a{&map_x, &map_w1, &map_xl, &map_w1l, &map_w2, &map_w2l, b1, b2, res, D, Z, D, ln_w, ln_b, Zh, Zl, nullptr};
+    const uint32_t tmem_base = tc::mlp_setup(smem_raw, a);
+    const int sl = c / nslabs, b = cl * G + sl, r0 = (c % nslabs) * SLAB;
+    const bool attend = sl < G && b < xa.B;
+    float* sm = reinterpret_cast<float*>(smem_raw);
+    if (attend) {
+        attn_body(aa, sm, b, r0);
+        __syncthreads();                 // every warp's LN1 rows are in global memory (same CTA reads them back below)
+        if (tid == 0) {
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr(smem_raw)) : "memory");
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr(smem_raw) + 8u) : "memory");
+        }
+        __syncthreads();
+        xattn_body(xa, sm, b, r0, true);
+    } else {
+        pdl_wait();
+    }
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (tid == 0 && attend) {
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr(smem_raw)) : "memory");
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr(smem_raw) + 8u) : "memory");
+    }
+    tc::cluster_sync_all();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    const int m0 = cl * G * xa.T;
+    tc::mlp_run(smem_raw, a, c, m0, min(M, m0 + G * xa.T), tmem_base, false, nullptr);
+    tc::mlp_teardown(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -917,6 +1048,21 @@ __global__ void __launch_bounds__(256) k_step_io(const StepIO a) {
 
 }  // namespace
 
+/* test / profiling hook: how many 8-CTA clusters of the fused decoder-layer kernel the device can hold at once */
+extern "C" int idb_debug_max_layer_clusters(idb_handle* h) {
+    IDB_ENTER(h);
+    if (!h) return -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tc::mlp::CLUSTER, 64); cfg.blockDim = dim3(ANT); cfg.dynamicSmemBytes = tc::mlp::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = tc::mlp::CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = -1;
+    if (cudaOccupancyMaxActiveClusters(&n, k_layer_qan_fused, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
+}
+
 extern "C" int idb_debug_attn_trace(long long* out16) {
     if (!out16) return IDB_ERR_ARG;
     return cudaMemcpyFromSymbol(out16, g_attn_trace, sizeof(long long) * 16) == cudaSuccess ? IDB_OK : IDB_ERR_CUDA;
@@ -927,6 +1073,9 @@ extern "C" int idb_debug_attn_trace(long long* out16) {
 // ------------------------------------------------------------------------------------------
 
 int idb_pointnet_commit(idb_handle* h);
+// six tensor maps of the feed-forward block (x hi/lo rows [M][256], w1 hi/lo [1024][256], w2 hi/lo [256][1024]); gemm_tcgen05.cu
+int idb_mlp_make_maps(idb_handle* h, const __half* x_hi, const __half* x_lo, const __half* w1_hi, const __half* w1_lo, const __half* w2_hi,
+                      const __half* w2_lo, int M, CUtensorMap* out6);
 void idb_pointnet_release(idb_handle* h);
 
 int idb_fail(idb_handle* h, int code, const char* fmt, ...) {
@@ -1360,11 +1509,24 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
     for (auto& L : d.layers) {
         // ---- first sub-block -> x1 = (d.h2, h2_b, h2_s)
         if (L.qan) {
-            const float* in = pending ? d.z : d.h;
+            QanArgs qa = {};
+            qa.zin = pending ? d.z : d.h; qa.prew = pending ? pending->ln3w : nullptr; qa.preb = pending ? pending->ln3b : nullptr;
+            qa.qth = L.qt_b; qa.qtl = L.qt_s; qa.wk = L.wk; qa.lnw = L.ln1w; qa.lnb = L.ln1b; qa.kph = L.kp_hi; qa.kpl = L.kp_lo; qa.kc = L.kc_mem;
+            qa.vph = L.vp_hi; qa.vpl = L.vp_lo; qa.bo2 = L.b_oc; qa.ln2w = L.ln2w; qa.ln2b = L.ln2b; qa.out = d.h2; qa.out_b = d.h2_b; qa.out_s = d.h2_s;
+            qa.T = T; qa.N = N; qa.B = B; qa.Tk = Tm; qa.H = H;
+            if (fused && h->fused_mlp >= 3 && !pending && qan_smem(Tm, H) <= (size_t)(tc::mlp::RING + tc::mlp::S_BYTES)) {
+                // the whole layer in one cluster kernel (attention phase + feed-forward phase on sample-aligned row tiles)
+                const int nslabs = (T + SLAB - 1) / SLAB, G = tc::mlp::CLUSTER / nslabs;
+                CUtensorMap mp[6];
+                if ((rc = idb_mlp_make_maps(h, d.h2_b, d.h2_s, L.w1_b, L.w1_s, L.w2_b, L.w2_s, M, mp))) return rc;
+                idb_launch(pdl, k_layer_qan_fused, dim3(tc::mlp::CLUSTER, (B + G - 1) / G), ANT, (size_t)tc::mlp::SMEM_BYTES, st, qa,
+                           mp[0], mp[1], mp[2], mp[3], mp[4], mp[5], (const float*)L.b1, (const float*)L.b2, (const float*)d.h2, d.h,
+                           (const float*)L.ln3w, (const float*)L.ln3b, d.h_b, d.h_s, M, G, nslabs);
+                LAUNCH_CHECK(h);
+                continue;
+            }
             // QaN block + LN1 + cross-attention + LN2 in one kernel: (z | h) -> (d.h2, pairs)
-            idb_launch(pdl, k_qan_xattn_ln<true>, slab_grid, ANT, qan_smem(Tm, H), st, in, pending ? pending->ln3w : nullptr,
-                       pending ? pending->ln3b : nullptr, L.qt_b, L.qt_s, L.wk, L.ln1w, L.ln1b, L.kp_hi, L.kp_lo, L.kc_mem, L.vp_hi, L.vp_lo, L.b_oc,
-                       L.ln2w, L.ln2b, d.h2, d.h2_b, d.h2_s, T, N, B, Tm, H);
+            idb_launch(pdl, k_qan_xattn_ln<true>, slab_grid, ANT, qan_smem(Tm, H), st, qa);
             LAUNCH_CHECK(h);
         } else {
             if (pending) {
@@ -1374,12 +1536,28 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
             const int NQ = 2 * D + H * D;
             if ((rc = linear(h, d.h_b, d.h_s, D, L.w_qkvf_b, L.w_qkvf_s, D, L.b_qkvf, nullptr, d.qkv, nullptr, nullptr, NQ, M, NQ, D,
                              EPI_BIAS, st))) return rc;
-            idb_launch(pdl, k_attn_ln, slab_grid, ANT, attn_smem(T, H), st, d.qkv, NQ, d.qkv + D, NQ, d.qkv + 2 * D, NQ, d.h,
-                       L.bo_f, L.ln1w, L.ln1b, d.qc, nullptr, nullptr, T, H);
+            AttnArgs aa = {};
+            aa.q = d.qkv; aa.ldq = NQ; aa.k = d.qkv + D; aa.ldk = NQ; aa.v = d.qkv + 2 * D; aa.ldv = NQ; aa.res = d.h; aa.bo = L.bo_f;
+            aa.lnw = L.ln1w; aa.lnb = L.ln1b; aa.out = d.qc; aa.T = T; aa.H = H;
+            XattnArgs xa = {};
+            xa.x1 = d.qc; xa.kph = L.kp_hi; xa.kpl = L.kp_lo; xa.kc = L.kc_mem; xa.vph = L.vp_hi; xa.vpl = L.vp_lo; xa.bo = L.b_oc;
+            xa.lnw = L.ln2w; xa.lnb = L.ln2b; xa.out = d.h2; xa.out_b = d.h2_b; xa.out_s = d.h2_s; xa.T = T; xa.B = B; xa.Tk = Tm; xa.H = H;
+            if (fused && h->fused_mlp >= 3 && attn_smem(T, H) <= (size_t)(tc::mlp::RING + tc::mlp::S_BYTES) &&
+                xattn_smem(Tm, H) <= (size_t)(tc::mlp::RING + tc::mlp::S_BYTES)) {
+                // self-attention + cross-attention + feed-forward of the layer in one cluster kernel
+                const int nslabs = (T + SLAB - 1) / SLAB, G = tc::mlp::CLUSTER / nslabs;
+                CUtensorMap mp[6];
+                if ((rc = idb_mlp_make_maps(h, d.h2_b, d.h2_s, L.w1_b, L.w1_s, L.w2_b, L.w2_s, M, mp))) return rc;
+                idb_launch(pdl, k_layer_std_fused, dim3(tc::mlp::CLUSTER, (B + G - 1) / G), ANT, (size_t)tc::mlp::SMEM_BYTES, st, aa, xa,
+                           mp[0], mp[1], mp[2], mp[3], mp[4], mp[5], (const float*)L.b1, (const float*)L.b2, (const float*)d.h2, d.h,
+                           (const float*)L.ln3w, (const float*)L.ln3b, d.h_b, d.h_s, M, G, nslabs);
+                LAUNCH_CHECK(h);
+                continue;
+            }
+            idb_launch(pdl, k_attn_ln, slab_grid, ANT, attn_smem(T, H), st, aa);
             LAUNCH_CHECK(h);
             // cross attention on the LN1 rows (d.qc) -> (d.h2, pairs)
-            idb_launch(pdl, k_xattn_ln, slab_grid, ANT, xattn_smem(Tm, H), st, d.qc, L.kp_hi, L.kp_lo, L.kc_mem, L.vp_hi, L.vp_lo, L.b_oc,
-                       L.ln2w, L.ln2b, d.h2, d.h2_b, d.h2_s, T, B, Tm, H);
+            idb_launch(pdl, k_xattn_ln, slab_grid, ANT, xattn_smem(Tm, H), st, xa);
             LAUNCH_CHECK(h);
         }
         // ---- feed forward on x2 = d.h2: ff = gelu(x2 W1^T + b1) kept as pairs only; z = ff W2^T + b2 + x2  (pre-norm3)
@@ -1498,6 +1676,8 @@ int idb_denoiser_run(idb_handle* h, const float* x, const long long* tstep, cons
 int idb_denoiser_prepare_kernels(idb_handle* h) {
     // opt in to > 48 KB dynamic shared memory once (T <= 36, Tm <= 16 supported: the self-attention slab kernel keeps all folded values of a sample, 4*T*256 floats, in shared memory)
     CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem(16, 4)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_layer_qan_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::mlp::SMEM_BYTES));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_layer_std_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::mlp::SMEM_BYTES));
     CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_enc_smem()));
     CUDA_TRY(h, cudaFuncSetAttribute(k_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_smem(16, 4)));
     CUDA_TRY(h, cudaFuncSetAttribute(k_attn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(36, 4)));
@@ -1589,11 +1769,11 @@ extern "C" int idb_encode_condition(idb_handle* h, int B, int Tp, const float* p
     const DenoiserLayer* pending = nullptr;      // layer whose final norm (norm2) has not been applied to e_z yet
     for (auto& L : d.enc_layers) {
         if (L.qan) {
-            idb_launch(pdl, k_qan_xattn_ln<false>, slab_grid, ANT, qan_enc_smem(), st, pending ? d.e_z : d.e_h,
-                       pending ? pending->ln3w : nullptr, pending ? pending->ln3b : nullptr, L.qt_b, L.qt_s, L.wk, L.ln1w, L.ln1b,
-                       (const __half*)nullptr, (const __half*)nullptr, (const float*)nullptr, (const uint32_t*)nullptr,
-                       (const uint32_t*)nullptr, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, d.e_h2, d.e_h2_b,
-                       d.e_h2_s, Tp, N, B, 0, H);
+            QanArgs qa = {};
+            qa.zin = pending ? d.e_z : d.e_h; qa.prew = pending ? pending->ln3w : nullptr; qa.preb = pending ? pending->ln3b : nullptr;
+            qa.qth = L.qt_b; qa.qtl = L.qt_s; qa.wk = L.wk; qa.lnw = L.ln1w; qa.lnb = L.ln1b;
+            qa.out = d.e_h2; qa.out_b = d.e_h2_b; qa.out_s = d.e_h2_s; qa.T = Tp; qa.N = N; qa.B = B; qa.Tk = 0; qa.H = H;
+            idb_launch(pdl, k_qan_xattn_ln<false>, slab_grid, ANT, qan_enc_smem(), st, qa);
             LAUNCH_CHECK(h);
         } else {
             if (pending) {
@@ -1603,8 +1783,10 @@ extern "C" int idb_encode_condition(idb_handle* h, int B, int Tp, const float* p
             const int NQ = 2 * D + H * D;
             if ((rc = linear(h, d.e_h_b, d.e_h_s, D, L.w_qkvf_b, L.w_qkvf_s, D, L.b_qkvf, nullptr, d.e_qkv, nullptr, nullptr, NQ, M, NQ, D,
                              EPI_BIAS, st))) return rc;
-            idb_launch(pdl, k_attn_ln, slab_grid, ANT, attn_smem(Tp, H), st, d.e_qkv, NQ, d.e_qkv + D, NQ, d.e_qkv + 2 * D, NQ, d.e_h,
-                       L.bo_f, L.ln1w, L.ln1b, d.e_h2, d.e_h2_b, d.e_h2_s, Tp, H);
+            AttnArgs aa = {};
+            aa.q = d.e_qkv; aa.ldq = NQ; aa.k = d.e_qkv + D; aa.ldk = NQ; aa.v = d.e_qkv + 2 * D; aa.ldv = NQ; aa.res = d.e_h; aa.bo = L.bo_f;
+            aa.lnw = L.ln1w; aa.lnb = L.ln1b; aa.out = d.e_h2; aa.out_b = d.e_h2_b; aa.out_s = d.e_h2_s; aa.T = Tp; aa.H = H;
+            idb_launch(pdl, k_attn_ln, slab_grid, ANT, attn_smem(Tp, H), st, aa);
             LAUNCH_CHECK(h);
         }
         if (fused) {

@@ -25,15 +25,13 @@
 //
 // Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor / InstrDescriptor).
 #include "common.cuh"
+#include "tc_mlp.cuh"
 
 #include <cuda.h>
 
 namespace {
 
-constexpr int BM = 128;
-constexpr int BK = 64;                 // 64 fp16 = one 128-byte swizzle row
-constexpr int UMMA_K = 16;             // kind::f16
-constexpr int NUM_THREADS = 320;
+using namespace tc;
 
 template <int BN> struct Cfg {
     static constexpr int A_BYTES = BM * BK * 2;               // 16 KB
@@ -45,70 +43,6 @@ template <int BN> struct Cfg {
     static constexpr int TMEM_COLS = 512;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// one lane of a fully active warp; the surrounding code stays warp-uniform so that descriptors and
-// addresses live in uniform registers (a divergent `if (lane == 0)` region forces an R2UR per operand)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(pred));
-    return pred != 0;
-}
-
-// K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);     // start address  [0,14)
-    d |= (uint64_t)1 << 16;                       // leading byte offset (16 B, unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset: 8 rows x 128 B
-    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
-    return d;
-}
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -353,51 +287,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #undef TRACE
 }
 
-// ---------------------------------------------------------------------------------------------
-// Fused feed-forward block  Z = gelu(X W1^T + b1) W2^T + b2 + R   for d_model 256, d_ff = 8 x 128.
-//
-// The two GEMMs of a decoder layer are each far below one wave of work (120 / 60 tiles) and their
-// launches, prologues and the 16 MB round trip of the fp16-pair intermediate cost more than the
-// tensor work.  Here a cluster of 8 CTAs owns one 128-row tile: CTA j computes the 128-column chunk j
-// of the hidden layer (GEMM 1, K = 256) into TMEM, its epilogue warps apply bias + GELU, split the
-// result into (hi, lo) fp16 pairs and write them into shared memory directly in the K-major
-// 128B-swizzled layout the tensor core reads, and the same CTA multiplies that chunk with the matching
-// 128 columns of W2 (GEMM 2, N = 256, K = 128).  The 8 partial [128 x 256] products are exchanged
-// through distributed shared memory: CTA j sums rows 16j .. 16j+15 of all 8 partials in rank order
-// (deterministic), adds bias + residual and stores Z.  120 CTAs, one launch, no intermediate in HBM/L2.
-//
-// Shared memory (192 KB): ring = 2 x 64 KB stages (GEMM 1 operands, then the two W2 k-blocks, then
-// - together with the S region - the fp32 partial tile); S = 64 KB (hi | lo, 2 k-blocks of 64).
-// TMEM (512 columns): GEMM 1 main [0,128) + small [128,256); GEMM 2 main [256,512) + small [0,256)
-// (GEMM 1's accumulators are dead once S is written).
-namespace mlp {
-constexpr int FC = 128;                       // hidden columns per CTA
-constexpr int CLUSTER = 8;                    // d_ff / FC
-constexpr int DM = 256;                       // d_model
-constexpr int STAGE1 = 64 * 1024;             // A_hi 16K | W1_hi 16K | A_lo 16K | W1_lo 16K
-constexpr int RING = 2 * STAGE1;
-constexpr int S_BYTES = 64 * 1024;            // S_hi [2][16K] | S_lo [2][16K]
-constexpr int PLD = 260;                      // fp32 partial row stride (floats)
-constexpr int SMEM_BYTES = RING + S_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers, tmem slot, LayerNorm partial sums*/;
-}  // namespace mlp
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&u)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
-          "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
-          "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
+// stand-alone launch of the feed-forward block: grid (8, ceil(M / 128)), one 128-row tile per cluster
 __global__ void __cluster_dims__(mlp::CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_w1l,
@@ -405,304 +295,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                  const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ res, int ldr,
                  float* __restrict__ Z, int ldz, int M, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                  __half* __restrict__ Zh, __half* __restrict__ Zl, long long* __restrict__ trace) {
-    using namespace mlp;
     long long* tr = trace ? trace + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
-#define MTRACE(slot) do { if (tr) tr[slot] = clock64(); } while (0)
-    if (threadIdx.x == 0) MTRACE(0);
+    if (tr && threadIdx.x == 0) tr[0] = clock64();
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t s_base = base + RING;
-    const uint32_t bars = base + RING + S_BYTES;
-    // barriers: full1[2], empty1[2], acc1, full2[2], s_ready, acc2, then the tmem slot
-    auto bar_full1 = [&](int s) { return bars + 8u * s; };
-    auto bar_empty1 = [&](int s) { return bars + 8u * (2 + s); };
-    const uint32_t bar_acc1 = bars + 8u * 4;
-    auto bar_full2 = [&](int s) { return bars + 8u * (5 + s); };
-    const uint32_t bar_sready = bars + 8u * 7, bar_acc2 = bars + 8u * 8, tmem_slot = bars + 8u * 9;
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + RING + S_BYTES + 8 * 9);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int j = blockIdx.x;                 // hidden chunk == rank in the cluster (cluster spans gridDim.x = 8)
-    const int m0 = blockIdx.y * BM;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; s++) { mbar_init(bar_full1(s), 1); mbar_init(bar_empty1(s), 1); mbar_init(bar_full2(s), 1); }
-        mbar_init(bar_acc1, 1); mbar_init(bar_acc2, 1);
-        mbar_init(bar_sready, 256);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_xl) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1l) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2l) : "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_ptr;
-    if (threadIdx.x == 0) MTRACE(1);
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (elect_one()) {
-            for (int kb = 0; kb < 2; kb++) {       // weight tiles do not depend on the previous kernel
-                const uint32_t dst = base + kb * STAGE1;
-                mbar_arrive_expect_tx(bar_full1(kb), STAGE1);
-                tma_load_2d(dst + 16384, &map_w1, bar_full1(kb), kb * BK, j * FC);
-                tma_load_2d(dst + 49152, &map_w1l, bar_full1(kb), kb * BK, j * FC);
-            }
-        }
-        __syncwarp();
-        pdl_wait();
-        if (elect_one()) {
-            for (int kb = 0; kb < 2; kb++) {
-                const uint32_t dst = base + kb * STAGE1;
-                tma_load_2d(dst, &map_x, bar_full1(kb), kb * BK, m0);
-                tma_load_2d(dst + 32768, &map_xl, bar_full1(kb), kb * BK, m0);
-            }
-        }
-        __syncwarp();
-        for (int kb = 2; kb < 4; kb++) {
-            const int s = kb & 1;
-            mbar_wait(bar_empty1(s), 0);
-            const uint32_t dst = base + s * STAGE1;
-            if (elect_one()) {
-                mbar_arrive_expect_tx(bar_full1(s), STAGE1);
-                tma_load_2d(dst, &map_x, bar_full1(s), kb * BK, m0);
-                tma_load_2d(dst + 16384, &map_w1, bar_full1(s), kb * BK, j * FC);
-                tma_load_2d(dst + 32768, &map_xl, bar_full1(s), kb * BK, m0);
-                tma_load_2d(dst + 49152, &map_w1l, bar_full1(s), kb * BK, j * FC);
-            }
-            __syncwarp();
-        }
-        // GEMM 1 finished reading the ring: fetch this chunk's 128 columns of W2 (two k-blocks of 64)
-        // while the epilogue warps turn the accumulators into the S operand
-        mbar_wait(bar_acc1, 0);
-        if (elect_one()) {
-            for (int kb = 0; kb < 2; kb++) {
-                const uint32_t dst = base + kb * STAGE1;
-                mbar_arrive_expect_tx(bar_full2(kb), STAGE1);
-                tma_load_2d(dst, &map_w2, bar_full2(kb), j * FC + kb * BK, 0);
-                tma_load_2d(dst + 32768, &map_w2l, bar_full2(kb), j * FC + kb * BK, 0);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        const uint32_t idesc1 = (1u << 4) | ((uint32_t)(FC >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        const uint32_t idesc2 = (1u << 4) | ((uint32_t)(DM >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        const uint32_t acc1_main = tmem_base, acc1_small = tmem_base + 128u;
-        for (int kb = 0; kb < 4; kb++) {
-            const int s = kb & 1;
-            mbar_wait(bar_full1(s), (kb >> 1) & 1);
-            tc_fence_after();
-            if (kb == 0 && lane == 0) MTRACE(2);
-            const uint32_t st = base + s * STAGE1;
-            const uint64_t dah = make_smem_desc(st), dwh = make_smem_desc(st + 16384);
-            const uint64_t dal = make_smem_desc(st + 32768), dwl = make_smem_desc(st + 49152);
-            if (elect_one()) {
-#pragma unroll
-                for (int kk = 0; kk < BK / UMMA_K; kk++) {
-                    const uint64_t koff = (uint64_t)((kk * UMMA_K * 2) >> 4);
-                    umma_f16(acc1_small, dal + koff, dwh + koff, idesc1, (kb | kk) ? 1u : 0u);
-                    umma_f16(acc1_small, dah + koff, dwl + koff, idesc1, 1u);
-                    umma_f16(acc1_main, dah + koff, dwh + koff, idesc1, (kb | kk) ? 1u : 0u);
-                }
-                umma_commit(bar_empty1(s));
-                if (kb == 3) umma_commit(bar_acc1);
-            }
-            __syncwarp();
-        }
-        if (lane == 0) MTRACE(3);
-        // GEMM 2: A = S (written by the epilogue warps), B = W2 k-blocks in the ring
-        mbar_wait(bar_sready, 0);
-        tc_fence_after();
-        if (lane == 0) MTRACE(6);
-        const uint32_t acc2_main = tmem_base + 256u, acc2_small = tmem_base;
-        for (int kb = 0; kb < 2; kb++) {
-            mbar_wait(bar_full2(kb), 0);
-            tc_fence_after();
-            const uint64_t dah = make_smem_desc(s_base + kb * 16384), dal = make_smem_desc(s_base + 32768 + kb * 16384);
-            const uint64_t dwh = make_smem_desc(base + kb * STAGE1), dwl = make_smem_desc(base + kb * STAGE1 + 32768);
-            if (elect_one()) {
-#pragma unroll
-                for (int kk = 0; kk < BK / UMMA_K; kk++) {
-                    const uint64_t koff = (uint64_t)((kk * UMMA_K * 2) >> 4);
-                    umma_f16(acc2_small, dal + koff, dwh + koff, idesc2, (kb | kk) ? 1u : 0u);
-                    umma_f16(acc2_small, dah + koff, dwl + koff, idesc2, 1u);
-                    umma_f16(acc2_main, dah + koff, dwh + koff, idesc2, (kb | kk) ? 1u : 0u);
-                }
-                if (kb == 1) umma_commit(bar_acc2);
-            }
-            __syncwarp();
-        }
-        if (lane == 0) MTRACE(7);
-    } else {
-        // ===================== epilogue warps 2..9 =====================
-        const int q = warp & 3, ew = warp - 2;       // TMEM lane quarter, 0..7
-        const int r = q * 32 + lane;                 // tile row owned by this thread
-        pdl_wait();
-        mbar_wait(bar_acc1, 0);
-        tc_fence_after();
-        if (threadIdx.x == 64) MTRACE(4);
-        // ---- hidden chunk: bias + GELU -> (hi, lo) fp16 pairs in the swizzled K-major A layout
-#pragma unroll 1
-        for (int c0 = (ew >> 2) * 32; c0 < FC; c0 += 64) {
-            uint32_t um[32], us[32];
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-            tmem_ld32(trow + (uint32_t)c0, um);
-            tmem_ld32(trow + (uint32_t)(128 + c0), us);
-            const int kb = c0 >> 6, ch0 = (c0 & 63) >> 3;
-            uint8_t* srow_hi = base_ptr + RING + kb * 16384 + r * 128;
-            uint8_t* srow_lo = srow_hi + 32768;
-#pragma unroll
-            for (int ch = 0; ch < 4; ch++) {
-                uint32_t hw[4], lw[4];
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int i0 = ch * 8 + e * 2;
-                    const float2 bb = *reinterpret_cast<const float2*>(b1 + j * FC + c0 + i0);
-                    const float v0 = gelu_erf(fmaf(__uint_as_float(us[i0]), 1.0f / 2048.0f, __uint_as_float(um[i0])) + bb.x);
-                    const float v1 = gelu_erf(fmaf(__uint_as_float(us[i0 + 1]), 1.0f / 2048.0f, __uint_as_float(um[i0 + 1])) + bb.y);
-                    __half2 hh, ll;
-                    split_f16x2(v0, v1, hh, ll);
-                    hw[e] = *reinterpret_cast<uint32_t*>(&hh); lw[e] = *reinterpret_cast<uint32_t*>(&ll);
-                }
-                const int pos = ((ch0 + ch) ^ (r & 7)) * 16;
-                *reinterpret_cast<uint4*>(srow_hi + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4*>(srow_lo + pos) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            }
-        }
-        tc_fence_before();                                             // our TMEM reads precede GEMM 2's writes to those columns
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy S writes -> visible to the tensor core
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_sready) : "memory");
-        if (threadIdx.x == 64) MTRACE(5);
-    }
-    // ===================== cross-CTA reduction over distributed shared memory =====================
-    // Every CTA writes its [128 x 256] fp32 partial product into its own (now idle) ring + S region; after a
-    // cluster barrier CTA j PULLS rows 16j .. 16j+15 of all 8 partials with coalesced 16-byte remote loads and sums
-    // them in rank order.  This exchange is bound by the SM-to-SM network (112 KB per CTA, ~13 B/clk/SM with all
-    // 120 CTAs exchanging at once = 8.5 K cycles; measured alternatives: 32 instead of 8 remote loads in flight per
-    // thread 13 K cycles, pushing rows to their owner with remote stores 14 K, staggered peers 8.4 K, exchange
-    // through an L2-resident global buffer 17 K - profiles/README.md).
-    const int q = warp & 3, ew = warp - 2;
-    if (warp >= 2) {
-        mbar_wait(bar_acc2, 0);          // GEMM 2 complete: the operand buffers may be overwritten
-        tc_fence_after();
-        if (threadIdx.x == 64) MTRACE(8);
-        const int r = q * 32 + lane;
-        float* prow = reinterpret_cast<float*>(base_ptr) + (size_t)r * PLD;
-#pragma unroll 1
-        for (int c0 = (ew >> 2) * 128; c0 < (ew >> 2) * 128 + 128; c0 += 32) {
-            uint32_t um[32], us[32];
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-            tmem_ld32(trow + (uint32_t)(256 + c0), um);
-            tmem_ld32(trow + (uint32_t)c0, us);
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(prow + c0 + i) =
-                    make_float4(fmaf(__uint_as_float(us[i]), 1.0f / 2048.0f, __uint_as_float(um[i])),
-                                fmaf(__uint_as_float(us[i + 1]), 1.0f / 2048.0f, __uint_as_float(um[i + 1])),
-                                fmaf(__uint_as_float(us[i + 2]), 1.0f / 2048.0f, __uint_as_float(um[i + 2])),
-                                fmaf(__uint_as_float(us[i + 3]), 1.0f / 2048.0f, __uint_as_float(um[i + 3])));
-        }
-        tc_fence_before();
-        if (threadIdx.x == 64) MTRACE(9);
-    }
-    __syncwarp();
-    cluster_sync_all();                  // every CTA's partial tile is complete and visible cluster-wide
-    if (threadIdx.x == 64) MTRACE(10);
-    if (warp >= 2) {
-        const int ct = threadIdx.x - 64;
-        float4 o[4];
-#pragma unroll 1
-        for (int t = 0; t < 4; t++) {
-            const int idx = ct + t * 256, rr = idx / (DM / 4), c4 = idx % (DM / 4);
-            const int row = m0 + j * 16 + rr;
-            const uint32_t off = base + (uint32_t)(((j * 16 + rr) * PLD + c4 * 4) * 4);   // same offset in every CTA of the cluster
-            float4 p[CLUSTER];
-#pragma unroll
-            for (int i = 0; i < CLUSTER; i++) {
-                uint32_t ra;
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(off), "r"(i));
-                asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(p[i].x), "=f"(p[i].y), "=f"(p[i].z), "=f"(p[i].w) : "r"(ra));
-            }
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < CLUSTER; i++) {          // rank order: deterministic
-                acc.x += p[i].x; acc.y += p[i].y; acc.z += p[i].z; acc.w += p[i].w;
-            }
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < M) {
-                const float4 bb = *reinterpret_cast<const float4*>(b2 + c4 * 4);
-                const float4 r4 = *reinterpret_cast<const float4*>(res + (size_t)row * ldr + c4 * 4);
-                v = make_float4((acc.x + bb.x) + r4.x, (acc.y + bb.y) + r4.y, (acc.z + bb.z) + r4.z, (acc.w + bb.w) + r4.w);
-            }
-            // select by constant index (t is a runtime loop counter of a deliberately rolled loop)
-            if (t == 0) o[0] = v; else if (t == 1) o[1] = v; else if (t == 2) o[2] = v; else o[3] = v;
-        }
-        if (ln_w) {
-            // the layer's final LayerNorm, fused: pass t of a thread belongs to row 4t + (ct >> 6), which lives in 64
-            // consecutive threads (two warps); the warp sums of all four passes meet through shared memory between
-            // two named barriers of the 256 reducing threads (the pulls above stay unsynchronised)
-            float* s_red = reinterpret_cast<float*>(base_ptr + RING + S_BYTES + 128);     // [2][4][8]
-            const int ew2 = warp - 2;
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const float sum = warp_sum((o[t].x + o[t].y) + (o[t].z + o[t].w));
-                if (lane == 0) s_red[t * 8 + ew2] = sum;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            float mean[4];
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                mean[t] = (s_red[t * 8 + (ew2 & ~1)] + s_red[t * 8 + (ew2 | 1)]) * (1.0f / DM);
-                o[t].x -= mean[t]; o[t].y -= mean[t]; o[t].z -= mean[t]; o[t].w -= mean[t];
-                const float sq = warp_sum((o[t].x * o[t].x + o[t].y * o[t].y) + (o[t].z * o[t].z + o[t].w * o[t].w));
-                if (lane == 0) s_red[32 + t * 8 + ew2] = sq;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int c4 = ct % (DM / 4);
-            const float4 w4 = *reinterpret_cast<const float4*>(ln_w + c4 * 4), b4 = *reinterpret_cast<const float4*>(ln_b + c4 * 4);
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const float rstd = 1.0f / sqrtf((s_red[32 + t * 8 + (ew2 & ~1)] + s_red[32 + t * 8 + (ew2 | 1)]) * (1.0f / DM) + 1e-5f);
-                o[t] = make_float4(o[t].x * rstd * w4.x + b4.x, o[t].y * rstd * w4.y + b4.y, o[t].z * rstd * w4.z + b4.z, o[t].w * rstd * w4.w + b4.w);
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int idx = ct + t * 256, rr = idx / (DM / 4), c4 = idx % (DM / 4);
-            const int row = m0 + j * 16 + rr;
-            if (row < M) {
-                *reinterpret_cast<float4*>(Z + (size_t)row * ldz + c4 * 4) = o[t];
-                if (Zh) {
-                    __half2 h01, h23, l01, l23;
-                    split_f16x2(o[t].x, o[t].y, h01, l01);
-                    split_f16x2(o[t].z, o[t].w, h23, l23);
-                    *reinterpret_cast<uint2*>(Zh + (size_t)row * ldz + c4 * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
-                    *reinterpret_cast<uint2*>(Zl + (size_t)row * ldz + c4 * 4) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
-                }
-            }
-        }
-        if (threadIdx.x == 64) MTRACE(11);
-    }
-    __syncwarp();
-    cluster_sync_all();                  // nobody leaves (and frees its shared memory) while peers still read it
-    if (threadIdx.x == 64) MTRACE(12);
-    __syncthreads();
-#undef MTRACE
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
+    MlpArgs a{&map_x, &map_w1, &map_xl, &map_w1l, &map_w2, &map_w2l, b1, b2, res, ldr, Z, ldz, ln_w, ln_b, Zh, Zl, trace};
+    const uint32_t tmem_base = mlp_setup(smem_raw, a);
+    mlp_run(smem_raw, a, blockIdx.x, blockIdx.y * BM, M, tmem_base, true, tr);
+    mlp_teardown(tmem_base);
 }
 
 // ---------------------------------------------------------------- host side
@@ -813,6 +413,19 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
 // x [M][256], w1 [F][256], w2 [256][F];  Z[M][256] = gelu(x w1^T + b1) w2^T + b2 + res, optionally followed by the layer's
 // final LayerNorm (ln_w / ln_b) and an additional fp16 (hi, lo) copy of the output (Z_hi / Z_lo) for the next GEMM.
 bool idb_mlp_tcgen05_supported(int d_model, int d_ff) { return d_model == mlp::DM && d_ff == mlp::FC * mlp::CLUSTER; }
+
+// order: x_hi, w1_hi, x_lo, w1_lo, w2_hi, w2_lo (the kernels' parameter order)
+int idb_mlp_make_maps(idb_handle* h, const __half* x_hi, const __half* x_lo, const __half* w1_hi, const __half* w1_lo, const __half* w2_hi,
+                      const __half* w2_lo, int M, CUtensorMap* out6) {
+    const int F = mlp::FC * mlp::CLUSTER;
+    int rc;
+    if ((rc = make_map(h, &out6[0], x_hi, M, mlp::DM, mlp::DM, BM))) return rc;
+    if ((rc = make_map(h, &out6[1], w1_hi, F, mlp::DM, mlp::DM, mlp::FC))) return rc;
+    if ((rc = make_map(h, &out6[2], x_lo, M, mlp::DM, mlp::DM, BM))) return rc;
+    if ((rc = make_map(h, &out6[3], w1_lo, F, mlp::DM, mlp::DM, mlp::FC))) return rc;
+    if ((rc = make_map(h, &out6[4], w2_hi, mlp::DM, F, F, mlp::DM))) return rc;
+    return make_map(h, &out6[5], w2_lo, mlp::DM, F, F, mlp::DM);
+}
 
 int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const __half* w1_hi, const __half* w1_lo, const float* b1,
                     const __half* w2_hi, const __half* w2_lo, const float* b2, const float* res, int ldr, float* Z, int ldz, int M,

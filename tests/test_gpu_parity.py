@@ -410,7 +410,24 @@ def test_fused_feed_forward_with_final_norm(eng, M):
     t = torch.tensor([900, 400, 50, 0])
     with torch.no_grad():
         ref_out = R.mdm_smpl_forward(sd, xx, t, torch.from_numpy(b["cond"]), faithful=False)
-    for level in (1, 2):       # 1 = feed-forward only (the norm stays with the next kernel), 2 = default
+    outs = {}
+    for level in (1, 2, 3):    # 1 = feed-forward only (the norm stays with the next kernel), 2 = default, 3 = whole layer in one launch
         eng.set_fused_mlp(level)
-        got2 = eng.forward(xx.cuda(), t.cuda()).cpu()
-        assert rel(got2, ref_out) < 2e-4, level
+        outs[level] = eng.forward(xx.cuda(), t.cuda()).cpu()
+        assert rel(outs[level], ref_out) < 2e-4, level
+    eng.set_fused_mlp(2)
+    if M == 1920:
+        # level 3 (attention + feed-forward of a layer in ONE cluster kernel on sample-aligned 4-sample tiles) computes every
+        # row exactly like level 2: bit-identical, also with a partial last cluster (B = 7) and a 3-slab window (T = 35)
+        assert torch.equal(outs[3], outs[2])
+        for B2, T2 in ((7, 30), (3, 35), (9, 16)):
+            b2 = S.make_smpl_batch(B=B2, T=T2)
+            eng.bind(b2["cond"], T2)
+            x2 = torch.from_numpy(S.noise_tape(b2["gt"].shape, 0)[0]).cuda()
+            t2 = torch.randint(0, 1000, (B2,), generator=torch.Generator().manual_seed(B2)).cuda()
+            o = {}
+            for level in (2, 3):
+                eng.set_fused_mlp(level)
+                o[level] = eng.forward(x2, t2).clone()
+            eng.set_fused_mlp(2)
+            assert torch.equal(o[2], o[3]), (B2, T2)

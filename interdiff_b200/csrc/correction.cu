@@ -41,14 +41,15 @@ struct Projector {
 
 namespace {
 
-constexpr int MAXP_SMPL = 68;    // 67 markers + the object's own node
+constexpr int MAXP_SMPL = 68;
+constexpr int PROJ_NT = 512;    // threads per projector block: the net is a chain of small latency-bound phases, more warps hide more of it    // 67 markers + the object's own node
 
 // One block per sample: the whole projector runs out of shared memory.  NQ = n_pre (DCT coefficients kept), MAXC = widest
 // layer, MAXP = nodes of the joint stack: <10, 32, 68> for the SMPL net (model/correction_smpl.py), <20, 64, 22> for the
 // skeleton net (model/correction_skeleton.py: 21 joints + 1, st_gcnns_all 9-64-32-64-9).  select_contact: the SMPL net picks
 // the hypothesis of the most-contacted marker (correction_smpl.py:125-136); the skeleton net always reads node 0 (:129).
-template <int NQ, int MAXC, int MAXP>
-__global__ void __launch_bounds__(256)
+template <int NQ, int MAXC, int MAXP, int NT>
+__global__ void __launch_bounds__(NT)
 k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct, const float* __restrict__ idct,
             const float* __restrict__ ang, const float* __restrict__ tr, const float* __restrict__ markers,
             const int32_t* __restrict__ contact, const int32_t* __restrict__ hand_ids, int n_hand,
@@ -62,7 +63,7 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
     __shared__ int s_sel;
     const int b = blockIdx.x, tid = threadIdx.x;
     float* rs = resid + (size_t)b * 9 * NQ * P1;
-    for (int i = tid; i < NQ * T; i += 256) s_dct[i] = dct[i];
+    for (int i = tid; i < NQ * T; i += NT) s_dct[i] = dct[i];
     __syncthreads();
 
     auto run_stack = [&](int l0, int C0, int Pn) {
@@ -71,9 +72,9 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
             const ProjLayer L = layers[l0 + li];
             const int cin = L.cin, cout = L.cout, npos = NQ * Pn;
             if (L.ver == 0) {
-                for (int i = tid; i < NQ * NQ; i += 256) s_T[i] = L.Tm[i];
+                for (int i = tid; i < NQ * NQ; i += NT) s_T[i] = L.Tm[i];
                 __syncthreads();
-                for (int it = tid; it < cin * Pn; it += 256) {
+                for (int it = tid; it < cin * Pn; it += NT) {
                     const int c = it / Pn, p = it % Pn;
                     float xv[NQ];
 #pragma unroll
@@ -88,7 +89,7 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
                 }
                 __syncthreads();
             } else {
-                for (int it = tid; it < cin * Pn; it += 256) {
+                for (int it = tid; it < cin * Pn; it += NT) {
                     const int c = it / Pn, p = it % Pn;
                     float xv[NQ];
 #pragma unroll
@@ -105,7 +106,7 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
                 __syncthreads();
                 // spatial mix in place, one warp per (c, q) row: g2[w] = sum_v g1[v] A[q][v][w]
                 const int warp = tid >> 5, lane = tid & 31;
-                for (int row = warp; row < cin * NQ; row += 8) {
+                for (int row = warp; row < cin * NQ; row += NT / 32) {
                     const int q = row % NQ;
                     float* g = bufB + row * Pn;
                     float r0 = lane < Pn ? g[lane] : 0.f, r1 = lane + 32 < Pn ? g[lane + 32] : 0.f, r2 = lane + 64 < Pn ? g[lane + 64] : 0.f;
@@ -127,7 +128,7 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
                 __syncthreads();
             }
             // position-wise: out = prelu( W g + b  +  Wr x + br )   (BN folded), written over x
-            for (int pos = tid; pos < npos; pos += 256) {
+            for (int pos = tid; pos < npos; pos += NT) {
                 float xv[MAXC], gv[MAXC];
                 for (int c = 0; c < cin; c++) { xv[c] = bufA[c * npos + pos]; gv[c] = bufB[c * npos + pos]; }
                 for (int co = 0; co < cout; co++) {
@@ -146,7 +147,7 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
     auto src_frame = [&](int t) { return t < past ? t : past - 1; };  // idx_pad (correction_smpl.py:84)
 
     // ---- relative stack: object pose relative to each marker, DCT over the padded past
-    for (int it = tid; it < 9 * P; it += 256) {
+    for (int it = tid; it < 9 * P; it += NT) {
         const int c = it / P, p = it % P;
         float acc[NQ];
 #pragma unroll
@@ -165,7 +166,7 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
     __syncthreads();
     run_stack(0, 9, P);
     // obj_multi = [rel + x][:6] | [rel + x][6:9] + DCT(markers)  -> parked in resid at node slots 1..P
-    for (int it = tid; it < 9 * P; it += 256) {
+    for (int it = tid; it < 9 * P; it += NT) {
         const int c = it / P, p = it % P;
         float ht[NQ];
 #pragma unroll
@@ -183,7 +184,7 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
         }
     }
     __syncthreads();
-    for (int it = tid; it < 9 * NQ * P; it += 256) {
+    for (int it = tid; it < 9 * NQ * P; it += NT) {
         const int cq = it / P, p = it % P;
         rs[cq * P1 + 1 + p] = bufB[cq * P + p];
     }
@@ -208,7 +209,7 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
     if (tid < 9 * NQ) rs[tid * P1] += bufA[tid];
     __syncthreads();
     // ---- joint stack over P+1 nodes
-    for (int it = tid; it < 9 * NQ * P1; it += 256) bufA[it] = rs[it];
+    for (int it = tid; it < 9 * NQ * P1; it += NT) bufA[it] = rs[it];
     __syncthreads();
     run_stack(8, 9, P1);
     // ---- hypothesis selection (correction_smpl.py:125-136) + inverse DCT of that column only
@@ -230,7 +231,7 @@ k_projector(const ProjLayer* __restrict__ layers, const float* __restrict__ dct,
     }
     __syncthreads();
     const int sel = s_sel;
-    for (int it = tid; it < T * 9; it += 256) {
+    for (int it = tid; it < T * 9; it += NT) {
         const int t = it / 9, c = it % 9;
         float a = 0.f;
 #pragma unroll
@@ -498,10 +499,10 @@ extern "C" int idb_projector_commit(idb_handle* h) {
     // per-function, per-device opt-in: always the device maximum (a smaller value set by another handle must not undercut it)
     // (the kernels also hold a few bytes of static shared memory: the dynamic limit is the device maximum minus that)
     cudaFuncAttributes fa;
-    CUDA_TRY(h, cudaFuncGetAttributes(&fa, k_projector<10, 32, 68>));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_projector<10, 32, 68>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
-    CUDA_TRY(h, cudaFuncGetAttributes(&fa, k_projector<20, 64, 22>));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_projector<20, 64, 22>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
+    CUDA_TRY(h, cudaFuncGetAttributes(&fa, k_projector<10, 32, 68, PROJ_NT>));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_projector<10, 32, 68, PROJ_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
+    CUDA_TRY(h, cudaFuncGetAttributes(&fa, k_projector<20, 64, 22, PROJ_NT>));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_projector<20, 64, 22, PROJ_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
     p.committed = true;
     h->epoch++;
     return IDB_OK;
@@ -521,11 +522,11 @@ static int projector_run(idb_handle* h, int T, int B, const float* ang, const fl
     }
     if (p.variant == 0) {
         const size_t smem = sizeof(float) * ((size_t)2 * 32 * 10 * 68 + NQ * T + NQ * NQ);
-        k_projector<10, 32, 68><<<B, 256, smem, st>>>(p.layers_dev, p.dct, p.idct, ang, tr, markers, contact, p.hand_ids, p.n_hand, p.resid, out,
+        k_projector<10, 32, 68, PROJ_NT><<<B, PROJ_NT, smem, st>>>(p.layers_dev, p.dct, p.idct, ang, tr, markers, contact, p.hand_ids, p.n_hand, p.resid, out,
                                                       T, B, p.P, p.past, 1);
     } else {
         const size_t smem = sizeof(float) * ((size_t)2 * 64 * 20 * 22 + NQ * T + NQ * NQ);
-        k_projector<20, 64, 22><<<B, 256, smem, st>>>(p.layers_dev, p.dct, p.idct, ang, tr, markers, nullptr, nullptr, 0, p.resid, out,
+        k_projector<20, 64, 22, PROJ_NT><<<B, PROJ_NT, smem, st>>>(p.layers_dev, p.dct, p.idct, ang, tr, markers, nullptr, nullptr, 0, p.resid, out,
                                                       T, B, p.P, p.past, 0);
     }
     LAUNCH_CHECK(h);

@@ -835,7 +835,7 @@ k_layer_qan_fused(const QanArgs qa, const __grid_constant__ CUtensorMap map_x, c
     pdl_trigger();
     const int c = blockIdx.x, cl = blockIdx.y, tid = threadIdx.x;
     tc::MlpArgs a{&map_x, &map_w1, &map_xl, &map_w1l, &map_w2, &map_w2l, b1, b2, res, D, Z, D, ln_w, ln_b, Zh, Zl, nullptr};
-    const uint32_t tmem_base = tc::mlp_setup(smem_raw, a);
+    const uint32_t tmem_base = tc::mlp_setup<8>(smem_raw, a);
     // ---- phase A
     const int sl = c / nslabs, b = cl * G + sl;
     const bool attend = sl < G && b < qa.B;
@@ -853,7 +853,7 @@ k_layer_qan_fused(const QanArgs qa, const __grid_constant__ CUtensorMap map_x, c
     asm volatile("fence.proxy.async;" ::: "memory");
     // ---- phase B
     const int m0 = cl * G * qa.T;
-    tc::mlp_run(smem_raw, a, c, m0, min(M, m0 + G * qa.T), tmem_base, false, nullptr);
+    tc::mlp_run<8>(smem_raw, a, c, m0, min(M, m0 + G * qa.T), tmem_base, false, nullptr);
     tc::mlp_teardown(tmem_base);
 }
 
@@ -870,7 +870,7 @@ k_layer_std_fused(const AttnArgs aa, const XattnArgs xa, const __grid_constant__
     pdl_trigger();
     const int c = blockIdx.x, cl = blockIdx.y, tid = threadIdx.x;
     tc::MlpArgs a{&map_x, &map_w1, &map_xl, &map_w1l, &map_w2, &map_w2l, b1, b2, res, D, Z, D, ln_w, ln_b, Zh, Zl, nullptr};
-    const uint32_t tmem_base = tc::mlp_setup(smem_raw, a);
+    const uint32_t tmem_base = tc::mlp_setup<8>(smem_raw, a);
     const int sl = c / nslabs, b = cl * G + sl, r0 = (c % nslabs) * SLAB;
     const bool attend = sl < G && b < xa.B;
     float* sm = reinterpret_cast<float*>(smem_raw);
@@ -896,7 +896,7 @@ k_layer_std_fused(const AttnArgs aa, const XattnArgs xa, const __grid_constant__
     tc::cluster_sync_all();
     asm volatile("fence.proxy.async;" ::: "memory");
     const int m0 = cl * G * xa.T;
-    tc::mlp_run(smem_raw, a, c, m0, min(M, m0 + G * xa.T), tmem_base, false, nullptr);
+    tc::mlp_run<8>(smem_raw, a, c, m0, min(M, m0 + G * xa.T), tmem_base, false, nullptr);
     tc::mlp_teardown(tmem_base);
 }
 

@@ -288,7 +288,9 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 }
 
 // stand-alone launch of the feed-forward block: grid (8, ceil(M / 128)), one 128-row tile per cluster
-__global__ void __cluster_dims__(mlp::CLUSTER, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+constexpr int MLP_EW = 16;                          // epilogue warps of the stand-alone kernel (4 per TMEM lane quarter)
+constexpr int MLP_THREADS = (2 + MLP_EW) * 32;      // + TMA producer + MMA issuer
+__global__ void __cluster_dims__(mlp::CLUSTER, 1, 1) __launch_bounds__(MLP_THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_w1l,
                  const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w2l,
@@ -300,8 +302,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     MlpArgs a{&map_x, &map_w1, &map_xl, &map_w1l, &map_w2, &map_w2l, b1, b2, res, ldr, Z, ldz, ln_w, ln_b, Zh, Zl, trace};
-    const uint32_t tmem_base = mlp_setup(smem_raw, a);
-    mlp_run(smem_raw, a, blockIdx.x, blockIdx.y * BM, M, tmem_base, true, tr);
+    const uint32_t tmem_base = mlp_setup<MLP_EW>(smem_raw, a);
+    mlp_run<MLP_EW>(smem_raw, a, blockIdx.x, blockIdx.y * BM, M, tmem_base, true, tr);
     mlp_teardown(tmem_base);
 }
 
@@ -446,7 +448,7 @@ int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const
     if ((rc = make_map(h, &mw2, w2_hi, mlp::DM, F, F, mlp::DM))) return rc;
     if ((rc = make_map(h, &mw2l, w2_lo, mlp::DM, F, F, mlp::DM))) return rc;
     dim3 grid(mlp::CLUSTER, (M + BM - 1) / BM);
-    idb_launch(pdl != 0, mlp_fused_kernel, grid, NUM_THREADS, mlp::SMEM_BYTES, st, mx, mw1, mxl, mw1l, mw2, mw2l, b1, b2, res, ldr, Z, ldz, M, ln_w, ln_b, Z_hi, Z_lo, trace);
+    idb_launch(pdl != 0, mlp_fused_kernel, grid, MLP_THREADS, mlp::SMEM_BYTES, st, mx, mw1, mxl, mw1l, mw2, mw2l, b1, b2, res, ldr, Z, ldz, M, ln_w, ln_b, Z_hi, Z_lo, trace);
     LAUNCH_CHECK(h);
     return IDB_OK;
 }

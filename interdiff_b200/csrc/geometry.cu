@@ -84,10 +84,10 @@ k_signed_nn(const float* __restrict__ query, const float* __restrict__ target, c
 
 // Same result as k_signed_nn, bit for bit, with most of the 6890 candidates pruned.  The target vertices come
 // grouped into NN_CLUSTERS clusters (BodyModel::nn_vid / nn_off).  One block = one frame x a chunk of queries:
-// it stages the frame's vertices cluster-sorted in shared memory and computes a bounding sphere per cluster
-// from the POSED vertices; then one warp per query: (1) squared centre distances for 8 clusters per lane, (2) the
-// cluster with the nearest centre is scanned to seed the minimum d0, (3) only clusters with |q - c| <= sqrt(d0) + r
-// (1e-4 relative slack on the safe side) are scanned.  Candidate
+// it stages the frame's vertices cluster-sorted in shared memory and computes an axis-aligned bounding box per cluster
+// from the POSED vertices; then one warp per query: (1) box distances for 8 clusters per lane, (2) the
+// cluster with the nearest box centre is scanned to seed the minimum d0, (3) only clusters whose box is within d0
+// (2e-4 relative slack on the safe side) are scanned.  Candidate
 // distances use exactly the brute-force expression, candidates compare lexicographically on (distance, vertex
 // id), and a cluster holding a vertex at the final minimum distance can never be skipped (that distance is <= d0),
 // so the FIRST minimum of the brute-force scan is reproduced.
@@ -102,8 +102,9 @@ k_signed_nn_pruned(const float* __restrict__ query, const float* __restrict__ ta
     extern __shared__ __align__(16) float nsm[];
     const int Ptp = (Pt + 3) & ~3;
     float* xs = nsm; float* ys = xs + Ptp; float* zs = ys + Ptp;
-    float4* cen = reinterpret_cast<float4*>(zs + Ptp);                 // centre xyz, radius (< 0: empty cluster)
-    int32_t* off = reinterpret_cast<int32_t*>(cen + NN_CLUSTERS);       // [NN_CLUSTERS + 1] (+3 pad)
+    float4* cen = reinterpret_cast<float4*>(zs + Ptp);                 // box centre xyz, w < 0: empty cluster
+    float4* ext = cen + NN_CLUSTERS;                                    // box half extents (slightly inflated)
+    int32_t* off = reinterpret_cast<int32_t*>(ext + NN_CLUSTERS);       // [NN_CLUSTERS + 1] (+3 pad)
     uint16_t* vid = reinterpret_cast<uint16_t*>(off + NN_CLUSTERS + 4);
     const int f = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* qb = query + (size_t)f * Pq * 3;
@@ -117,33 +118,39 @@ k_signed_nn_pruned(const float* __restrict__ query, const float* __restrict__ ta
     __syncthreads();
     for (int c = tid; c < NN_CLUSTERS; c += 512) {
         const int b = off[c], e = off[c + 1];
-        float4 o = make_float4(0.f, 0.f, 0.f, -1.f);
+        // axis-aligned bounding box of the cluster's POSED vertices (patches of a body surface are flat: a box bounds them
+        // far more tightly than a sphere); half extents inflated so that centre +- extent covers min / max despite rounding
+        float4 o = make_float4(0.f, 0.f, 0.f, -1.f), hx = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e > b) {
-            float sx = 0.f, sy = 0.f, sz = 0.f;
-            for (int i = b; i < e; i++) { sx += xs[i]; sy += ys[i]; sz += zs[i]; }
-            const float inv = 1.0f / (float)(e - b);
-            o.x = sx * inv; o.y = sy * inv; o.z = sz * inv;
-            float r2 = 0.f;
-            for (int i = b; i < e; i++) r2 = fmaxf(r2, nn_dist2(o.x, o.y, o.z, xs[i], ys[i], zs[i]));
-            o.w = sqrtf(r2) * 1.00001f + 1e-7f;
+            float lx = xs[b], ly = ys[b], lz = zs[b], ux = lx, uy = ly, uz = lz;
+            for (int i = b + 1; i < e; i++) {
+                lx = fminf(lx, xs[i]); ly = fminf(ly, ys[i]); lz = fminf(lz, zs[i]);
+                ux = fmaxf(ux, xs[i]); uy = fmaxf(uy, ys[i]); uz = fmaxf(uz, zs[i]);
+            }
+            o = make_float4(0.5f * (lx + ux), 0.5f * (ly + uy), 0.5f * (lz + uz), 1.f);
+            hx = make_float4(0.5f * (ux - lx) * 1.00001f + 1e-6f * (1.0f + fabsf(o.x)), 0.5f * (uy - ly) * 1.00001f + 1e-6f * (1.0f + fabsf(o.y)),
+                             0.5f * (uz - lz) * 1.00001f + 1e-6f * (1.0f + fabsf(o.z)), 0.f);
         }
-        cen[c] = o;
+        cen[c] = o; ext[c] = hx;
     }
     __syncthreads();
     const int q0 = blockIdx.x * qchunk, q1 = min(Pq, q0 + qchunk);
     unsigned* cand = reinterpret_cast<unsigned*>(vid + Ptp) + warp * (NN_CLUSTERS / 32);     // per-warp candidate bit sets
     for (int q = q0 + warp; q < q1; q += 16) {
         const float qx = qb[q * 3], qy = qb[q * 3 + 1], qz = qb[q * 3 + 2];
-        // squared distances to the centres of clusters lane + 32k; the nearest centre seeds the search
-        float dc2[NN_CLUSTERS / 32], rad[NN_CLUSTERS / 32];
+        // clusters lane + 32k: lower bound lb2 of the squared distance to any vertex of the cluster (distance to its box;
+        // < 0 marks an empty cluster); the cluster with the nearest box CENTRE seeds the search
+        float lb2[NN_CLUSTERS / 32];
         float dcmin = INFINITY; int cmin = 0;
 #pragma unroll
         for (int k = 0; k < NN_CLUSTERS / 32; k++) {
             const int c = lane + 32 * k;
-            const float4 cc = cen[c];
-            rad[k] = cc.w;
-            dc2[k] = nn_dist2(qx, qy, qz, cc.x, cc.y, cc.z);
-            if (cc.w >= 0.f && dc2[k] < dcmin) { dcmin = dc2[k]; cmin = c; }
+            const float4 cc = cen[c], hh = ext[c];
+            const float ax = fabsf(qx - cc.x), ay = fabsf(qy - cc.y), az = fabsf(qz - cc.z);
+            const float ex = fmaxf(ax - hh.x, 0.f), ey = fmaxf(ay - hh.y, 0.f), ez = fmaxf(az - hh.z, 0.f);
+            lb2[k] = cc.w >= 0.f ? (ex * ex + ey * ey) + ez * ez : -1.f;
+            const float dc = (ax * ax + ay * ay) + az * az;
+            if (cc.w >= 0.f && dc < dcmin) { dcmin = dc; cmin = c; }
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
@@ -163,15 +170,12 @@ k_signed_nn_pruned(const float* __restrict__ query, const float* __restrict__ ta
         float bound = bd;
 #pragma unroll
         for (int o = 16; o; o >>= 1) bound = fminf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
-        // a cluster can hold a vertex at distance^2 <= bound only if |q - c| <= sqrt(bound) + r; the test is done on
-        // squares with a 1e-4 relative slack on the safe side (the computed quantities are good to ~1e-6)
-        float sb;
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sb) : "f"(bound));
-        sb *= 1.0001f;
+        // a cluster can hold a vertex at distance^2 <= bound only if the distance^2 to its box is <= bound; 2e-4 relative
+        // slack on the safe side (the computed quantities are good to ~1e-6)
+        const float lim2 = bound * 1.0002f;
 #pragma unroll
         for (int k = 0; k < NN_CLUSTERS / 32; k++) {
-            const float lim = sb + rad[k];
-            const unsigned m = __ballot_sync(0xffffffffu, rad[k] >= 0.f && dc2[k] * 0.9999f <= lim * lim && (lane + 32 * k) != cmin);
+            const unsigned m = __ballot_sync(0xffffffffu, lb2[k] >= 0.f && lb2[k] * 0.9999f <= lim2 && (lane + 32 * k) != cmin);
             if (lane == 0) cand[k] = m;
         }
         __syncwarp();
@@ -245,7 +249,7 @@ extern "C" int idb_signed_nn(idb_handle* h, int F, int Pq, int Pt, const float* 
     // body-mesh targets take the cluster-pruned search (identical results, ~8x fewer candidate evaluations)
     if (h->nn_pruning && h->body && h->body->nn_vid && Pt == h->body->V && Pt <= 12000) {
         const int Ptp = (Pt + 3) & ~3;
-        const size_t smem = sizeof(float) * 3 * Ptp + sizeof(float4) * NN_CLUSTERS + sizeof(int32_t) * (NN_CLUSTERS + 4) + sizeof(uint16_t) * Ptp + sizeof(unsigned) * 16 * (NN_CLUSTERS / 32);
+        const size_t smem = sizeof(float) * 3 * Ptp + 2 * sizeof(float4) * NN_CLUSTERS + sizeof(int32_t) * (NN_CLUSTERS + 4) + sizeof(uint16_t) * Ptp + sizeof(unsigned) * 16 * (NN_CLUSTERS / 32);
         if (!(h->attr_mask & 4u)) {
             CUDA_TRY(h, cudaFuncSetAttribute(k_signed_nn_pruned, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             h->attr_mask |= 4u;

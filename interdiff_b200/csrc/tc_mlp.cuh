@@ -132,6 +132,7 @@ struct MlpArgs {
 
 // Barriers, tensor-map prefetch and the TMEM allocation of the feed-forward block; ends with a CTA barrier.  The barrier
 // words live ABOVE the 192 KB operand region, so a caller may use that region for something else until mlp_run starts.
+template <int EW>      // EW = number of epilogue warps of mlp_run<EW>: 8 or 16
 __device__ __forceinline__ uint32_t mlp_setup(uint8_t* smem_raw, const MlpArgs& a) {
     using namespace mlp;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -143,7 +144,7 @@ __device__ __forceinline__ uint32_t mlp_setup(uint8_t* smem_raw, const MlpArgs& 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (2 + s), 1); mbar_init(bars + 8u * (5 + s), 1); }
         mbar_init(bars + 8u * 4, 1); mbar_init(bars + 8u * 8, 1);
-        mbar_init(bars + 8u * 7, 256);
+        mbar_init(bars + 8u * 7, EW * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_w1) : "memory");
@@ -167,9 +168,14 @@ __device__ __forceinline__ uint32_t mlp_setup(uint8_t* smem_raw, const MlpArgs& 
 // fewer than 128 live rows when the caller aligns tiles to samples).  Warps 0 / 1 = TMA producer / MMA issuer, warps 2..9 =
 // epilogue; any further warps of the CTA only take part in the cluster barriers.  wait_dep: execute griddepcontrol.wait
 // before the first dependent access (stand-alone launch); a caller that has already waited passes false.
+template <int EW>
 __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int j, int m0, int row_end, uint32_t tmem_base, bool wait_dep,
                                         long long* tr) {
     using namespace mlp;
+    static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps (2 or 4 per TMEM lane quarter)");
+    constexpr int NEPI = EW * 32;              // epilogue threads
+    constexpr int WPQ = EW / 4;                // warps per TMEM lane quarter
+    constexpr int NPASS = 1024 / NEPI;         // float4 elements of the 16 x 256 reduction slice per thread
 #define MTRACE(slot) do { if (tr) tr[slot] = clock64(); } while (0)
     const CUtensorMap& map_x = *a.map_x; const CUtensorMap& map_w1 = *a.map_w1; const CUtensorMap& map_xl = *a.map_xl;
     const CUtensorMap& map_w1l = *a.map_w1l; const CUtensorMap& map_w2 = *a.map_w2; const CUtensorMap& map_w2l = *a.map_w2l;
@@ -285,7 +291,7 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
             __syncwarp();
         }
         if (lane == 0) MTRACE(7);
-    } else if (warp < 10) {
+    } else if (warp < 2 + EW) {
         // ===================== epilogue warps 2..9 =====================
         const int q = warp & 3, ew = warp - 2;       // TMEM lane quarter, 0..7
         const int r = q * 32 + lane;                 // tile row owned by this thread
@@ -295,7 +301,7 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
         if (threadIdx.x == 64) MTRACE(4);
         // ---- hidden chunk: bias + GELU -> (hi, lo) fp16 pairs in the swizzled K-major A layout
 #pragma unroll 1
-        for (int c0 = (ew >> 2) * 32; c0 < FC; c0 += 64) {
+        for (int c0 = (ew >> 2) * 32; c0 < FC; c0 += 32 * WPQ) {
             uint32_t um[32], us[32];
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
             tmem_ld32(trow + (uint32_t)c0, um);
@@ -334,7 +340,7 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
     // thread 13 K cycles, pushing rows to their owner with remote stores 14 K, staggered peers 8.4 K, exchange
     // through an L2-resident global buffer 17 K - profiles/README.md).
     const int q = warp & 3, ew = warp - 2;
-    const bool epi = warp >= 2 && warp < 10;
+    const bool epi = warp >= 2 && warp < 2 + EW;
     if (epi) {
         mbar_wait(bar_acc2, 0);          // GEMM 2 complete: the operand buffers may be overwritten
         tc_fence_after();
@@ -342,7 +348,7 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
         const int r = q * 32 + lane;
         float* prow = reinterpret_cast<float*>(base_ptr) + (size_t)r * PLD;
 #pragma unroll 1
-        for (int c0 = (ew >> 2) * 128; c0 < (ew >> 2) * 128 + 128; c0 += 32) {
+        for (int c0 = (ew >> 2) * (256 / WPQ); c0 < (ew >> 2) * (256 / WPQ) + 256 / WPQ; c0 += 32) {
             uint32_t um[32], us[32];
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
             tmem_ld32(trow + (uint32_t)(256 + c0), um);
@@ -363,10 +369,10 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
     if (threadIdx.x == 64) MTRACE(10);
     if (epi) {
         const int ct = threadIdx.x - 64;
-        float4 o[4];
+        float4 o[NPASS];
 #pragma unroll 1
-        for (int t = 0; t < 4; t++) {
-            const int idx = ct + t * 256, rr = idx / (DM / 4), c4 = idx % (DM / 4);
+        for (int t = 0; t < NPASS; t++) {
+            const int idx = ct + t * NEPI, rr = idx / (DM / 4), c4 = idx % (DM / 4);
             const int row = m0 + j * 16 + rr;
             const uint32_t off = base + (uint32_t)(((j * 16 + rr) * PLD + c4 * 4) * 4);   // same offset in every CTA of the cluster
             float4 p[CLUSTER];
@@ -389,40 +395,41 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
                 v = make_float4((acc.x + bb.x) + r4.x, (acc.y + bb.y) + r4.y, (acc.z + bb.z) + r4.z, (acc.w + bb.w) + r4.w);
             }
             // select by constant index (t is a runtime loop counter of a deliberately rolled loop)
-            if (t == 0) o[0] = v; else if (t == 1) o[1] = v; else if (t == 2) o[2] = v; else o[3] = v;
+#pragma unroll
+            for (int tt = 0; tt < NPASS; tt++) if (t == tt) o[tt] = v;
         }
         if (ln_w) {
-            // the layer's final LayerNorm, fused: pass t of a thread belongs to row 4t + (ct >> 6), which lives in 64
-            // consecutive threads (two warps); the warp sums of all four passes meet through shared memory between
-            // two named barriers of the 256 reducing threads (the pulls above stay unsynchronised)
-            float* s_red = reinterpret_cast<float*>(base_ptr + RING + S_BYTES + 128);     // [2][4][8]
+            // the layer's final LayerNorm, fused: pass t of a thread belongs to row t NEPI / 64 + (ct >> 6), which lives in 64
+            // consecutive threads (two warps); the warp sums of all passes meet through shared memory between
+            // two named barriers of the NEPI reducing threads (the pulls above stay unsynchronised)
+            float* s_red = reinterpret_cast<float*>(base_ptr + RING + S_BYTES + 128);     // [2][NPASS][EW]
             const int ew2 = warp - 2;
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
+            for (int t = 0; t < NPASS; t++) {
                 const float sum = warp_sum((o[t].x + o[t].y) + (o[t].z + o[t].w));
-                if (lane == 0) s_red[t * 8 + ew2] = sum;
+                if (lane == 0) s_red[t * EW + ew2] = sum;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            float mean[4];
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
+            float mean[NPASS];
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                mean[t] = (s_red[t * 8 + (ew2 & ~1)] + s_red[t * 8 + (ew2 | 1)]) * (1.0f / DM);
+            for (int t = 0; t < NPASS; t++) {
+                mean[t] = (s_red[t * EW + (ew2 & ~1)] + s_red[t * EW + (ew2 | 1)]) * (1.0f / DM);
                 o[t].x -= mean[t]; o[t].y -= mean[t]; o[t].z -= mean[t]; o[t].w -= mean[t];
                 const float sq = warp_sum((o[t].x * o[t].x + o[t].y * o[t].y) + (o[t].z * o[t].z + o[t].w * o[t].w));
-                if (lane == 0) s_red[32 + t * 8 + ew2] = sq;
+                if (lane == 0) s_red[NPASS * EW + t * EW + ew2] = sq;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
             const int c4 = ct % (DM / 4);
             const float4 w4 = *reinterpret_cast<const float4*>(ln_w + c4 * 4), b4 = *reinterpret_cast<const float4*>(ln_b + c4 * 4);
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const float rstd = 1.0f / sqrtf((s_red[32 + t * 8 + (ew2 & ~1)] + s_red[32 + t * 8 + (ew2 | 1)]) * (1.0f / DM) + 1e-5f);
+            for (int t = 0; t < NPASS; t++) {
+                const float rstd = 1.0f / sqrtf((s_red[NPASS * EW + t * EW + (ew2 & ~1)] + s_red[NPASS * EW + t * EW + (ew2 | 1)]) * (1.0f / DM) + 1e-5f);
                 o[t] = make_float4(o[t].x * rstd * w4.x + b4.x, o[t].y * rstd * w4.y + b4.y, o[t].z * rstd * w4.z + b4.z, o[t].w * rstd * w4.w + b4.w);
             }
         }
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int idx = ct + t * 256, rr = idx / (DM / 4), c4 = idx % (DM / 4);
+        for (int t = 0; t < NPASS; t++) {
+            const int idx = ct + t * NEPI, rr = idx / (DM / 4), c4 = idx % (DM / 4);
             const int row = m0 + j * 16 + rr;
             if (row < M) {
                 *reinterpret_cast<float4*>(Z + (size_t)row * ldz + c4 * 4) = o[t];

@@ -205,6 +205,8 @@ int idb_rollout_next_window(idb_handle* h, int T, int B, int J, int Db, int past
                             const float* jtr, float* gt_out, float* centroid_out, void* stream);
 int idb_add_offset(idb_handle* h, int T, int B, int K, long long ld, int col0, float* x, const float* offset, float sign, void* stream);
 
+/* bisecting hook: 0 = the SMPL-H blend GEMM without TMA-multicast row-tile pairs (identical results; default 1) */
+int idb_debug_set_gemm_multicast(idb_handle* h, int on);
 /* profiling hook: 8-CTA clusters of the fused decoder-layer kernel that fit on the device at once (-1 on error) */
 int idb_debug_max_layer_clusters(idb_handle* h);
 

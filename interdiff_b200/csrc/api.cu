@@ -71,6 +71,14 @@ extern "C" int idb_set_nn_pruning(idb_handle* h, int on) {
     idb_sampler_drop_graphs(h);
     return IDB_OK;
 }
+/* test / bisecting hook: 0 = the SMPL-H blend GEMM without the multicast row-tile pairs (identical results) */
+extern "C" int idb_debug_set_gemm_multicast(idb_handle* h, int on) {
+    IDB_ENTER(h);
+    if (!h) return IDB_ERR_ARG;
+    h->gemm_multicast = on ? 1 : 0;
+    idb_sampler_drop_graphs(h);
+    return IDB_OK;
+}
 extern "C" double idb_debug_last_ms(const idb_handle* h) { return h ? h->last_ms : 0.0; }
 extern "C" int idb_set_fused_mlp(idb_handle* h, int on) {
     IDB_ENTER(h);

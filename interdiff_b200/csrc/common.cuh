@@ -112,6 +112,7 @@ struct idb_handle {
     int pdl = 1;              // programmatic dependent launch between the kernels of a sampling step
     unsigned attr_mask = 0;   // kernels whose > 48 KB shared-memory opt-in was done on this handle's device (bit 0 GEMM, 1 MLP, 2 NN)
     double last_ms = 0.0;     // mean launch time of the last timed debug hook
+    int gemm_multicast = 1;   // long wide GEMMs (SMPL-H blend): row-tile pairs share the W tile by TMA multicast (idb_debug_set_gemm_multicast)
     int nn_pruning = 1;       // cluster-pruned nearest-neighbour search for body-mesh targets (identical results)
     int fused_mlp = 2;        // feed-forward block as ONE cluster kernel (tensor backend, d_model 256, d_ff 1024); 2 = incl. the layer's final norm;
                               // 3 = a layer's attention half runs in the same kernel on sample-aligned tiles (one launch per layer):

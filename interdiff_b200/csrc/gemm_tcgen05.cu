@@ -44,7 +44,11 @@ template <int BN> struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// MC (multicast pairs): launched with cluster dimensions (1, 2, 1) - the two CTAs of a cluster own two ROW tiles of the same
+// column tile.  Each loads its own A tile and HALF of the shared W tile, multicast into both CTAs' shared memory
+// (cp.async.bulk.tensor ... .multicast::cluster), which halves the L2 -> SM traffic of the W operand; a stage is refilled only
+// when BOTH CTAs' MMAs have released it (tcgen05.commit ... .multicast::cluster onto the "empty" barrier of both, count 2).
+template <int BN, bool MC = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                       const __grid_constant__ CUtensorMap map_al, const __grid_constant__ CUtensorMap map_wl,
@@ -80,7 +84,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (threadIdx.x == 0) {
         for (int s = 0; s < cfg::STAGES; s++) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_empty(s), 1);
+            mbar_init(bar_empty(s), MC ? 2 : 1);
         }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -98,6 +102,12 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     if (threadIdx.x == 0) TRACE(1);
+    uint32_t crank = 0;
+    if (MC) {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+        cluster_sync_all();      // the peer's barriers exist before anything is multicast into its shared memory
+    }
+    constexpr int WH = cfg::W_BYTES / 2;     // bytes of half a W tile (MC: the part this CTA fetches for both)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -108,8 +118,13 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             for (int kb = 0; kb < npre; kb++) {
                 const uint32_t dst = base + kb * cfg::STAGE_BYTES;
                 mbar_arrive_expect_tx(bar_full(kb), cfg::STAGE_BYTES);
-                tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(kb), (kb0 + kb) * BK, n0);
-                tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(kb), (kb0 + kb) * BK, n0);
+                if (MC) {
+                    tma_load_2d_mc(dst + cfg::A_BYTES + crank * WH, &map_w, bar_full(kb), (kb0 + kb) * BK, n0 + crank * (BN / 2), 3);
+                    tma_load_2d_mc(dst + cfg::HALF_BYTES + cfg::A_BYTES + crank * WH, &map_wl, bar_full(kb), (kb0 + kb) * BK, n0 + crank * (BN / 2), 3);
+                } else {
+                    tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(kb), (kb0 + kb) * BK, n0);
+                    tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(kb), (kb0 + kb) * BK, n0);
+                }
             }
         }
         __syncwarp();
@@ -130,9 +145,14 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full(s), cfg::STAGE_BYTES);
                 tma_load_2d(dst, &map_a, bar_full(s), (kb0 + kb) * BK, m0);
-                tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(s), (kb0 + kb) * BK, n0);
                 tma_load_2d(dst + cfg::HALF_BYTES, &map_al, bar_full(s), (kb0 + kb) * BK, m0);
-                tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(s), (kb0 + kb) * BK, n0);
+                if (MC) {
+                    tma_load_2d_mc(dst + cfg::A_BYTES + crank * WH, &map_w, bar_full(s), (kb0 + kb) * BK, n0 + crank * (BN / 2), 3);
+                    tma_load_2d_mc(dst + cfg::HALF_BYTES + cfg::A_BYTES + crank * WH, &map_wl, bar_full(s), (kb0 + kb) * BK, n0 + crank * (BN / 2), 3);
+                } else {
+                    tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(s), (kb0 + kb) * BK, n0);
+                    tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(s), (kb0 + kb) * BK, n0);
+                }
             }
             __syncwarp();
         }
@@ -162,7 +182,8 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     }
                     umma_f16(acc_main, dah + koff, dwh + koff, idesc, kk ? 1u : first_main);
                 }
-                umma_commit(bar_empty(s));                     // stage reusable once these MMAs have read it
+                if (MC) umma_commit_mc(bar_empty(s), 3);      // ... in BOTH CTAs of the pair (each multicasts into the other's stage)
+                else umma_commit(bar_empty(s));                // stage reusable once these MMAs have read it
                 if (kb == num_kb - 1) umma_commit(bar_acc);    // accumulators complete
             }
             __syncwarp();
@@ -278,6 +299,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (ct == 0) TRACE(10);
     }
     __syncthreads();
+    if (MC) cluster_sync_all();      // the peer may still arrive on this CTA's barriers (multicast commits) until it is done too
     if (threadIdx.x == 0) TRACE(11);
     if (warp == 1) {
         tc_fence_after();
@@ -394,7 +416,25 @@ int idb_gemm_tcgen05(idb_handle* h, const GemmArgs& g, cudaStream_t st) {
     int nacc = one_acc ? 1 : kb_per_cta <= 8 ? 2 : (kb_per_cta + 3) / 4;
     if (nacc > nacc_max) nacc = nacc_max;
     if (g_idb_gemm_nacc > 0) nacc = g_idb_gemm_nacc < nacc_max ? g_idb_gemm_nacc : nacc_max;
-    if (xwide) {
+    if (xwide && g.single_acc && h->gemm_multicast && (M + BM - 1) / BM >= 2) {
+        // long, wide GEMMs (the SMPL-H blend): pairs of row tiles share the W tile by TMA multicast (cluster 1 x 2 x 1)
+        CUtensorMap mwh, mwlh;
+        if ((rc = make_map(h, &mwh, g.W_hi, N, K, g.ldw, 128))) return rc;
+        if ((rc = make_map(h, &mwlh, g.W_lo, N, K, g.ldw, 128))) return rc;
+        if (!(h->attr_mask & 8u)) {
+            CUDA_TRY(h, cudaFuncSetAttribute(gemm_split_f16_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+            h->attr_mask |= 8u;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(N / 256, (((M + BM - 1) / BM) + 1) & ~1, 1);      // an even number of row tiles (a tile past M loads zeros, stores nothing)
+        cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = Cfg<256>::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CUDA_TRY(h, cudaLaunchKernelEx(&cfg, gemm_split_f16_kernel<256, true>, ma, mwh, mal, mwlh, g.bias, g.res, g.ldr, g.C, g.C_hi, g.C_lo, g.ldc,
+                                       M, N, K, g.epi, 1, (float*)nullptr, 0, 0, trace));
+    } else if (xwide) {
         dim3 grid(N / 256, (M + BM - 1) / BM, 1);
         idb_launch(g.pdl != 0, gemm_split_f16_kernel<256>, grid, NUM_THREADS, Cfg<256>::SMEM_BYTES, st, ma, mw, mal, mwl, g.bias, g.res, g.ldr,
                    g.C, g.C_hi, g.C_lo, g.ldc, M, N, K, g.epi, 1, nullptr, 0, 0, trace);

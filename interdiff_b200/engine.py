@@ -89,6 +89,10 @@ class Engine:
         """Cluster-pruned nearest-neighbour search for body-mesh targets (default on; identical results)."""
         self._chk(self.lib.idb_set_nn_pruning(self._h, 1 if on else 0))
 
+    def set_gemm_multicast(self, on):
+        """SMPL-H blend GEMM with / without TMA-multicast row-tile pairs (identical results; bisecting / A-B timing)."""
+        self._chk(self.lib.idb_debug_set_gemm_multicast(self._h, 1 if on else 0))
+
     def set_fused_mlp(self, on):
         """Feed-forward block as one cluster kernel (default on) vs two GEMM launches."""
         self._chk(self.lib.idb_set_fused_mlp(self._h, int(on)))

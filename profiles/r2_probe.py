@@ -58,6 +58,12 @@ for wname, sparse in (("dense tail (every bone non-zero)", False), ("<= 4 non-ze
             F, wname, "fp32 SIMT" if backend == "simt" else "tcgen05 blend + skinning", ms, byt / 1e6, byt / ms / 1e6, byt / ms / 1e6 / 64.861,
             F * 33.2e-3, F * 33.2e6 / ms / 1e9))
 eng.set_gemm_backend("tcgen05")
+eng.load_body(S.make_smplh_model(233, sparse_weights=True))
+for mc in (False, True):
+    eng.set_gemm_multicast(mc)
+    ms = timed(lambda: eng.lbs(pose, betas, trans, want_jtr=False), n=10, warm=3, flush_l2=True)
+    print("LBS F=%d sparse weights, blend GEMM %s multicast row-tile pairs: %.3f ms (%.0f GB/s)" % (F, "with" if mc else "without", ms, byt / ms / 1e6))
+eng.set_gemm_multicast(True)
 
 if "--config3" in sys.argv:
     from interdiff_b200.weights import bench_weights as bw

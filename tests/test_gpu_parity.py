@@ -259,6 +259,12 @@ def test_smplh_lbs_large_blend(eng):
     assert rel(verts, v_ref) < 1e-5 and rel(jtr, j_ref) < 1e-5
     # against float64 the kernel is as close as the fp32 oracle itself (within 3x)
     assert rel(verts, v64) < max(3 * rel(v_ref, v64), 2e-6)
+    # the blend GEMM with TMA-multicast row-tile pairs (3 row tiles here: one pair + one tile paired with an empty one) computes
+    # every element exactly like the unpaired kernel
+    eng.set_gemm_multicast(False)
+    v_plain, _ = eng.lbs(pose, betas, trans)
+    eng.set_gemm_multicast(True)
+    assert torch.equal(v_plain, verts)
 
 
 def test_geometry(eng, smplh_np):

@@ -299,12 +299,14 @@ __device__ __forceinline__ void attn_body(const AttnArgs& aa, float* sm, const i
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // barrier [0]: parameter rows + the folded value rows (120 KB, needed only by the value product: their copy overlaps the
+    // logits and the softmax); barrier [1]: query / residual rows and key slices (needed at once)
     if (tid == 0) {
-        mb_expect_tx(bar, 3 * ROW_BYTES);
+        mb_expect_tx(bar, (uint32_t)(3 + HT) * ROW_BYTES);
         bulk_g2s(s_par, bo, ROW_BYTES, bar); bulk_g2s(s_par + D, lnw, ROW_BYTES, bar); bulk_g2s(s_par + 2 * D, lnb, ROW_BYTES, bar);
     }
     pdl_wait();
-    if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)(2 * nr + (H + 1) * Tk) * ROW_BYTES);
+    if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)(2 * nr + Tk) * ROW_BYTES);
     __syncwarp();
     // one copy per thread and round: query + residual rows, key head slices (256 B), folded value rows
     for (int i = tid; i < 2 * nr + 2 * HT; i += ANT) {
@@ -315,7 +317,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& aa, float* sm, const i
             bulk_g2s(s_k + hj * LDK, k + (size_t)(b * T + j) * ldk + hh * HD, HD * sizeof(float), bar + 1);
         } else {
             const int hj = i - 2 * nr - HT, hh = hj / Tk, j = hj - hh * Tk;
-            bulk_g2s(s_v + (size_t)hj * VLD, v + (size_t)(b * T + j) * ldv + hh * D, ROW_BYTES, bar + 1);
+            bulk_g2s(s_v + (size_t)hj * VLD, v + (size_t)(b * T + j) * ldv + hh * D, ROW_BYTES, bar);
         }
     }
     mb_wait(bar + 1, 0);
@@ -677,8 +679,13 @@ __device__ __forceinline__ void qan_xattn_body(const QanArgs& qa, float* sm, con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // two barriers: [0] parameters + folded queries (needed by the QaN block right away), [1] the sample's folded memory keys /
+    // values (84 KB, needed only by the cross-attention block: their copy overlaps the QaN block)
     const int npar = (prew ? 2 : 0) + 2 + (XATTN ? 3 : 0);
-    if (tid == 0) mb_expect_tx(bar, (uint32_t)(npar + NQ + (XATTN ? 2 * HT : 0)) * ROW_BYTES);
+    if (tid == 0) {
+        mb_expect_tx(bar, (uint32_t)(npar + NQ) * ROW_BYTES);
+        if (XATTN) mb_expect_tx(bar + 1, (uint32_t)(2 * HT) * ROW_BYTES);
+    }
     __syncwarp();
     if (tid < 7) {
         const float* src = tid == 0 ? prew : tid == 1 ? preb : tid == 2 ? lnw : tid == 3 ? lnb : tid == 4 ? bo2 : tid == 5 ? ln2w : ln2b;
@@ -688,7 +695,7 @@ __device__ __forceinline__ void qan_xattn_body(const QanArgs& qa, float* sm, con
         if (r < NQ) bulk_g2s(s_qth + r * KPH, qth + (size_t)r * D, D * sizeof(__half), bar);
         else bulk_g2s(s_qtl + (r - NQ) * KPH, qtl + (size_t)(r - NQ) * D, D * sizeof(__half), bar);
     }
-    if (XATTN) stage_memory(kph, kpl, kc, vph, vpl, s_kph, s_kpl, s_kc, s_vph, s_vpl, b, B, Tk, H, bar);
+    if (XATTN) stage_memory(kph, kpl, kc, vph, vpl, s_kph, s_kpl, s_kc, s_vph, s_vpl, b, B, Tk, H, bar + 1);
     const float wk_n = lane < N ? wk[lane] : 0.f;
     ATRACE(1);
     pdl_wait();
@@ -801,6 +808,7 @@ __device__ __forceinline__ void qan_xattn_body(const QanArgs& qa, float* sm, con
         }
     }
     if (!XATTN) return;
+    mb_wait(bar + 1, 0);     // memory keys / values have landed (copied while the QaN block ran)
     __syncthreads();
     ATRACE(6);
     cross_attention_tail(s_x1, s_kph, s_kpl, s_kc, s_vph, s_vpl, s_a, s_z, nr, HT, Tk, H, s_par + 4 * D, s_par + 5 * D, s_par + 6 * D,

@@ -85,9 +85,8 @@ k_signed_nn(const float* __restrict__ query, const float* __restrict__ target, c
 // Same result as k_signed_nn, bit for bit, with most of the 6890 candidates pruned.  The target vertices come
 // grouped into NN_CLUSTERS clusters (BodyModel::nn_vid / nn_off).  One block = one frame x a chunk of queries:
 // it stages the frame's vertices cluster-sorted in shared memory and computes an axis-aligned bounding box per cluster
-// from the POSED vertices; then one warp per query: (1) box distances for 8 clusters per lane, (2) the
-// cluster with the nearest box centre is scanned to seed the minimum d0, (3) only clusters whose box is within d0
-// (2e-4 relative slack on the safe side) are scanned.  Candidate
+// from the POSED vertices; then one warp per query: box distances for 8 clusters per lane, then a best-first search over
+// the clusters in order of their box distance that stops when no unvisited box can hold a closer (or tying) vertex.  Candidate
 // distances use exactly the brute-force expression, candidates compare lexicographically on (distance, vertex
 // id), and a cluster holding a vertex at the final minimum distance can never be skipped (that distance is <= d0),
 // so the FIRST minimum of the brute-force scan is reproduced.
@@ -135,63 +134,51 @@ k_signed_nn_pruned(const float* __restrict__ query, const float* __restrict__ ta
     }
     __syncthreads();
     const int q0 = blockIdx.x * qchunk, q1 = min(Pq, q0 + qchunk);
-    unsigned* cand = reinterpret_cast<unsigned*>(vid + Ptp) + warp * (NN_CLUSTERS / 32);     // per-warp candidate bit sets
     for (int q = q0 + warp; q < q1; q += 16) {
         const float qx = qb[q * 3], qy = qb[q * 3 + 1], qz = qb[q * 3 + 2];
         // clusters lane + 32k: lower bound lb2 of the squared distance to any vertex of the cluster (distance to its box;
-        // < 0 marks an empty cluster); the cluster with the nearest box CENTRE seeds the search
+        // empty clusters get +inf).  BEST-FIRST search: repeatedly take the unvisited cluster with the smallest lower bound,
+        // scan it, tighten the bound; stop when the smallest remaining lower bound exceeds the best distance found (2e-4
+        // relative slack on the safe side, inclusive: a cluster that could hold a vertex at exactly the best distance - a tie,
+        // resolved towards the lower vertex id - is still visited).  Typically 3-6 clusters are scanned instead of every
+        // cluster whose box intersects the seed sphere.
         float lb2[NN_CLUSTERS / 32];
-        float dcmin = INFINITY; int cmin = 0;
 #pragma unroll
         for (int k = 0; k < NN_CLUSTERS / 32; k++) {
             const int c = lane + 32 * k;
             const float4 cc = cen[c], hh = ext[c];
-            const float ax = fabsf(qx - cc.x), ay = fabsf(qy - cc.y), az = fabsf(qz - cc.z);
-            const float ex = fmaxf(ax - hh.x, 0.f), ey = fmaxf(ay - hh.y, 0.f), ez = fmaxf(az - hh.z, 0.f);
-            lb2[k] = cc.w >= 0.f ? (ex * ex + ey * ey) + ez * ez : -1.f;
-            const float dc = (ax * ax + ay * ay) + az * az;
-            if (cc.w >= 0.f && dc < dcmin) { dcmin = dc; cmin = c; }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            const float od = __shfl_xor_sync(0xffffffffu, dcmin, o);
-            const int oc = __shfl_xor_sync(0xffffffffu, cmin, o);
-            if (od < dcmin || (od == dcmin && oc < cmin)) { dcmin = od; cmin = oc; }
+            const float ex = fmaxf(fabsf(qx - cc.x) - hh.x, 0.f), ey = fmaxf(fabsf(qy - cc.y) - hh.y, 0.f), ez = fmaxf(fabsf(qz - cc.z) - hh.z, 0.f);
+            lb2[k] = cc.w >= 0.f ? (ex * ex + ey * ey) + ez * ez : INFINITY;
         }
         float bd = INFINITY; int bi = 0x7fffffff;
-        {
-            const int b = off[cmin], e = off[cmin + 1];
+        float bound = INFINITY;          // warp-uniform: smallest candidate distance seen so far
+        for (;;) {
+            // lane-local minimum over its 8 clusters, then the warp's (value, cluster) minimum; ties -> lower cluster id
+            float lm = lb2[0]; int lk = 0;
+#pragma unroll
+            for (int k = 1; k < NN_CLUSTERS / 32; k++) if (lb2[k] < lm) { lm = lb2[k]; lk = k; }
+            int lc = lane + 32 * lk;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const float om = __shfl_xor_sync(0xffffffffu, lm, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, lc, o);
+                if (om < lm || (om == lm && oc < lc)) { lm = om; lc = oc; }
+            }
+            if (lm == INFINITY || !(lm * 0.9999f <= bound * 1.0002f)) break;      // every cluster visited, or none left that can matter
+            if ((lc & 31) == lane) {                                // the owner marks the cluster visited
+#pragma unroll
+                for (int k = 0; k < NN_CLUSTERS / 32; k++) if (k == (lc >> 5)) lb2[k] = INFINITY;
+            }
+            const int b = off[lc], e = off[lc + 1];
             for (int i = b + lane; i < e; i += 32) {
                 const float d = nn_dist2(qx, qy, qz, xs[i], ys[i], zs[i]);
                 const int v = vid[i];
                 if (d < bd || (d == bd && v < bi)) { bd = d; bi = v; }
             }
-        }
-        float bound = bd;
+            float nb = bd;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) bound = fminf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
-        // a cluster can hold a vertex at distance^2 <= bound only if the distance^2 to its box is <= bound; 2e-4 relative
-        // slack on the safe side (the computed quantities are good to ~1e-6)
-        const float lim2 = bound * 1.0002f;
-#pragma unroll
-        for (int k = 0; k < NN_CLUSTERS / 32; k++) {
-            const unsigned m = __ballot_sync(0xffffffffu, lb2[k] >= 0.f && lb2[k] * 0.9999f <= lim2 && (lane + 32 * k) != cmin);
-            if (lane == 0) cand[k] = m;
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int k = 0; k < NN_CLUSTERS / 32; k++) {
-            unsigned m = cand[k];
-            while (m) {
-                const int c = __ffs(m) - 1 + 32 * k;
-                m &= m - 1;
-                const int b = off[c], e = off[c + 1];
-                for (int i = b + lane; i < e; i += 32) {
-                    const float d = nn_dist2(qx, qy, qz, xs[i], ys[i], zs[i]);
-                    const int v = vid[i];
-                    if (d < bd || (d == bd && v < bi)) { bd = d; bi = v; }
-                }
-            }
+            for (int o = 16; o; o >>= 1) nb = fminf(nb, __shfl_xor_sync(0xffffffffu, nb, o));
+            bound = nb;
         }
         __syncwarp();
 #pragma unroll

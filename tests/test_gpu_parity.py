@@ -437,3 +437,29 @@ def test_fused_feed_forward_with_final_norm(eng, M):
                 o[level] = eng.forward(x2, t2).clone()
             eng.set_fused_mlp(2)
             assert torch.equal(o[2], o[3]), (B2, T2)
+
+
+def test_rotation_conversions_targeted(eng):
+    """A11: the 6D -> axis-angle chain (rotation_6d_to_matrix -> matrix_to_quaternion's 4-candidate argmax -> axis-angle with the
+    small-angle series) on the cases random inputs do not reach: rotations within 1e-3 .. 1e-6 of pi (where the argmax
+    switches between the x / y / z candidates), exact 180-degree turns about the axes, near-identity rotations on both sides
+    of the 1e-6 series switch, un-normalised and nearly collinear 6D inputs.  Near pi the axis-angle vector itself is
+    ill-conditioned (aa and -aa describe almost the same rotation), so the comparison is made on the rotation matrices the
+    two results describe; away from pi the vectors are compared directly."""
+    from oracle import transforms as tf
+    g = torch.Generator().manual_seed(17)
+    axes = torch.nn.functional.normalize(torch.randn(64, 3, generator=g), dim=1)
+    axes = torch.cat([axes, torch.eye(3), -torch.eye(3), torch.tensor([[0.7071068, 0.7071068, 0.0], [0.0, 0.7071068, -0.7071068]])])
+    angles = torch.tensor([3.14159265, 3.1415, 3.1406, 3.1316, 3.0416, 1e-7, 9e-7, 1.1e-6, 1e-5, 1e-3, 0.0, 1.5707963])
+    aa = (axes[:, None, :] * angles[None, :, None]).reshape(-1, 3)
+    Rm = tf.axis_angle_to_matrix(aa.double()).float()
+    d6 = tf.matrix_to_rotation_6d(Rm)
+    d6 = torch.cat([d6, d6 * torch.tensor([3.0, 3.0, 3.0, 0.2, 0.2, 0.2]),                       # un-normalised rows
+                    torch.cat([d6[:, :3], d6[:, :3] + 0.05 * d6[:, 3:]], dim=1)])                  # second row close to the first (Gram-Schmidt cancels 20x)
+    got = eng.rot6d_to_axis_angle(d6).cpu()
+    want = tf.matrix_to_axis_angle(tf.rotation_6d_to_matrix(d6))
+    R_got, R_want = tf.axis_angle_to_matrix(got), tf.axis_angle_to_matrix(want)
+    assert torch.isfinite(got).all()
+    assert (R_got - R_want).abs().max().item() < 5e-5, (R_got - R_want).abs().max().item()
+    far = (want.norm(dim=1) < 3.0)                 # well away from pi: the vectors themselves agree
+    assert rel(got[far], want[far]) < 5e-5, rel(got[far], want[far])

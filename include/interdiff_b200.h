@@ -230,6 +230,9 @@ int idb_debug_mlp(idb_handle* h, const float* x, const float* w1, const float* b
 double idb_debug_last_ms(const idb_handle* h);
 /* clock64 phase timeline (16 slots, host pointer) of CTA (0,0) of the last fused QaN + cross-attention kernel */
 int idb_debug_attn_trace(long long* out16);
+/* chain timeline probe (profiles/chain_probe.py): device buffer of 64 lanes x (2 + 2 * capacity) uint64, lane[0] = 0, lane[1] = capacity; every
+   kernel of the sampling step then appends (kind | event | grid | block, %globaltimer) records; NULL switches it off */
+int idb_debug_chain_trace(idb_handle* h, unsigned long long* buf);
 /* one launch with a per-CTA clock64 timeline (16 slots per CTA) of the tcgen05 kernel's pipeline */
 int idb_debug_gemm_trace(idb_handle* h, const float* A, const float* W, float* C, int M, int N, int K, long long* trace, void* stream);
 

@@ -149,6 +149,14 @@ extern "C" int idb_debug_gemm_repeat(idb_handle* h, const float* A, const float*
 
 extern long long* g_idb_gemm_trace;
 static int g_idb_trace_epi = 0;
+int idb_chain_set_gemm(unsigned long long* buf);
+int idb_chain_set_denoiser(unsigned long long* buf);
+/* chain timeline probe: buf = 64 lanes x (2 + 2 * capacity) uint64 (lane[0] = 0, lane[1] = capacity), NULL = off */
+extern "C" int idb_debug_chain_trace(idb_handle* h, unsigned long long* buf) {
+    IDB_ENTER(h);
+    if (!h) return IDB_ERR_ARG;
+    return (idb_chain_set_gemm(buf) | idb_chain_set_denoiser(buf)) ? IDB_ERR_CUDA : IDB_OK;
+}
 /* one GEMM launch with a per-CTA clock64 timeline written to trace[ctas][16] (device) */
 extern "C" int idb_debug_gemm_trace(idb_handle* h, const float* A, const float* W, float* C, int M, int N, int K, long long* trace, void* stream) {
     IDB_ENTER(h);
@@ -158,8 +166,10 @@ extern "C" int idb_debug_gemm_trace(idb_handle* h, const float* A, const float* 
 }
 
 extern int g_idb_gemm_nacc;
-/* test hook: number of round-robin TMEM accumulators for the big x big products (0 = default) */
+extern int g_idb_gemm_bn192;
+/* test hook: number of round-robin TMEM accumulators for the big x big products (0 = default); 900 / 901: 192-column tiles off / on */
 extern "C" int idb_debug_set_gemm_accumulators(int n) {
+    if (n == 900 || n == 901) { g_idb_gemm_bn192 = n - 900; return IDB_OK; }
     if (n >= 1000) { g_idb_trace_epi = n - 1000; return IDB_OK; }   // >= 1000: epi flags for idb_debug_gemm_trace
     g_idb_gemm_nacc = n;
     return IDB_OK;

@@ -38,9 +38,8 @@ struct DenoiserLayer {
     // folded self-attention: [Wq; Wk; (Wo_h Wv_h) for h] (1536 x 256), bias [bq; bk; 0], bo' = bo + sum_h Wo_h bv_h
     float *w_qkvf = nullptr, *b_qkvf = nullptr, *bo_f = nullptr;
     // (big, small) splits of the GEMM weights for the tensor-core path
-    __half *qt_b = nullptr, *qt_s = nullptr;                       // folded queries as fp16 (hi, lo)
-    __half *kp_hi = nullptr, *kp_lo = nullptr;                     // bound: folded memory keys, fp16 (hi, lo) [B][H*Tm][D]
-    uint32_t *vp_hi = nullptr, *vp_lo = nullptr;                   // bound: folded memory values, k-pair words [B][H*Tm/2][D]
+    __half* qt_pack = nullptr;                                     // folded queries [2 (hi, lo)][3N][D + 8]: the kernels' staged layout
+    __half* mem_pack = nullptr;                                    // bound: per sample keys hi | lo, value words hi | lo, kc (mem_block_bytes)
     __half *w_qkvf_b = nullptr, *w_qkvf_s = nullptr, *w1_b = nullptr, *w1_s = nullptr,
            *w2_b = nullptr, *w2_s = nullptr;
     // QaN
@@ -204,6 +203,31 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 // chain executes pdl_wait, which makes completion transitive along the stream.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Chain timeline probe (profiles/chain_probe.py): when idb_debug_chain_trace has installed a buffer, a mark appends
+// (kind, event, grid size, block | %globaltimer) to one of 64 lanes of the buffer (lane = block & 63, so that the marks of a
+// launch do not serialise on one counter): lane l = buf + l * (2 + 2 * cap) words: [0] record count, [1] capacity, then records.
+// Events: 0 entry, 1 dependency wait done, 2 exit.  Off (null) in production: one constant load and a branch per mark.  One
+// copy of the pointer per translation unit (CHAIN_SETTER defines the unit's installer).
+static __constant__ unsigned long long* c_chain = nullptr;
+__device__ __forceinline__ void chain_mark(int kind, int ev) {
+    unsigned long long* p = c_chain;
+    if (p) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned long long nb = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
+        const unsigned long long bid = ((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        const unsigned long long cap = p[1];
+        p += (bid & 63) * (2 + 2 * cap);
+        const unsigned long long i = atomicAdd(p, 1ull);
+        if (i < cap) {
+            p[2 + 2 * i] = ((unsigned long long)kind << 56) | ((unsigned long long)ev << 52) | (nb << 26) | bid;
+            p[3 + 2 * i] = t;
+        }
+    }
+}
+#define CHAIN_SETTER(name) \
+    int name(unsigned long long* buf) { return cudaMemcpyToSymbol(c_chain, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1; }
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t idb_launch(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -21,22 +21,33 @@ constexpr int HD = 64;    // head dim
 constexpr int SLAB = 16;  // query rows per block in the per-sample attention kernels
 constexpr int LDZ = D + 4;
 
-// Step-invariant cross-attention operands, split into fp16 (hi, lo) once per bind and laid out per sample in the
-// order the attention kernels stage them: keys [B][H*Tk][D] (row hj = h*Tk + j), values as words of two k-neighbours
-// [B][H*Tk/2][D], word i = (V[2i][n], V[2i+1][n]).   kp / vp rows are (j*B + b) x [H][D].  grid (H*Tk, B), block D.
-__global__ void k_pack_memory(const float* __restrict__ kp, const float* __restrict__ vp, __half* __restrict__ kph,
-                              __half* __restrict__ kpl, uint32_t* __restrict__ vph, uint32_t* __restrict__ vpl, int B, int Tk, int H) {
-    const int hj = blockIdx.x, b = blockIdx.y, n = threadIdx.x, HT = H * Tk;
+// Step-invariant cross-attention operands of one sample, split into fp16 (hi, lo) once per bind and stored as ONE block in
+// exactly the (padded, bank-conflict-free) layout the attention kernels keep in shared memory, so that a CTA stages them with
+// a single bulk copy:  keys hi [HT][KPH] | keys lo [HT][KPH] (row hj = h*Tk + j, fp16) | values hi [HT/2][VPW] | values lo
+// (word i = (V[2i][n], V[2i+1][n])) | kc [HT] fp32 (constant logit term).  kp / vp rows are (j*B + b) x [H][D]; kc [Tk*B][H].
+// The pad columns are never read.  grid (H*Tk, B), block D.
+constexpr int KPH = D + 8;     // halfs per staged row of a pre-split "rows" operand
+constexpr int VPW = D + 8;     // words per staged row of a k-pair-packed K x N operand
+__host__ __device__ constexpr size_t mem_block_bytes(int HT) {
+    return (size_t)2 * HT * KPH * 2 + (size_t)2 * (HT >> 1) * VPW * 4 + (size_t)((HT + 3) & ~3) * 4;
+}
+__global__ void k_pack_memory(const float* __restrict__ kp, const float* __restrict__ vp, const float* __restrict__ kc,
+                              uint8_t* __restrict__ pack, int B, int Tk, int H) {
+    const int hj = blockIdx.x, b = blockIdx.y, n = threadIdx.x, HT = H * Tk, HP = HT >> 1;
+    uint8_t* blk = pack + (size_t)b * mem_block_bytes(HT);
+    __half* kph = reinterpret_cast<__half*>(blk); __half* kpl = kph + (size_t)HT * KPH;
+    uint32_t* vph = reinterpret_cast<uint32_t*>(kpl + (size_t)HT * KPH); uint32_t* vpl = vph + (size_t)HP * VPW;
+    float* kco = reinterpret_cast<float*>(vpl + (size_t)HP * VPW);
     auto src = [&](int q) { return ((size_t)((q % Tk) * B + b) * H + q / Tk) * D + n; };
-    split_f16(kp[src(hj)], kph[((size_t)b * HT + hj) * D + n], kpl[((size_t)b * HT + hj) * D + n]);
-    if ((hj & 1) == 0) {
+    split_f16(kp[src(hj)], kph[(size_t)hj * KPH + n], kpl[(size_t)hj * KPH + n]);
+    if ((hj & 1) == 0 && (hj >> 1) < HP) {
         const float v0 = vp[src(hj)], v1 = hj + 1 < HT ? vp[src(hj + 1)] : 0.f;
         __half2 h2, l2;
         split_f16x2(v0, v1, h2, l2);
-        const size_t o = ((size_t)b * (HT >> 1) + (hj >> 1)) * D + n;
-        vph[o] = *reinterpret_cast<uint32_t*>(&h2);
-        vpl[o] = *reinterpret_cast<uint32_t*>(&l2);
+        vph[(size_t)(hj >> 1) * VPW + n] = *reinterpret_cast<uint32_t*>(&h2);
+        vpl[(size_t)(hj >> 1) * VPW + n] = *reinterpret_cast<uint32_t*>(&l2);
     }
+    if (n == 0) kco[hj] = kc[(size_t)((hj % Tk) * B + b) * H + hj / Tk];
 }
 
 // bind-time: scale the folded keys by 1/sqrt(hd) and compute the constant logit term
@@ -306,6 +317,7 @@ __device__ __forceinline__ void attn_body(const AttnArgs& aa, float* sm, const i
         bulk_g2s(s_par, bo, ROW_BYTES, bar); bulk_g2s(s_par + D, lnw, ROW_BYTES, bar); bulk_g2s(s_par + 2 * D, lnb, ROW_BYTES, bar);
     }
     pdl_wait();
+    if (tid == 0) chain_mark(0, 1);
     if (tid == 0) mb_expect_tx(bar + 1, (uint32_t)(2 * nr + Tk) * ROW_BYTES);
     __syncwarp();
     // one copy per thread and round: query + residual rows, key head slices (256 B), folded value rows
@@ -412,15 +424,15 @@ __device__ __forceinline__ void attn_body(const AttnArgs& aa, float* sm, const i
 __global__ void __launch_bounds__(ANT)
 k_attn_ln(const AttnArgs aa) {
     extern __shared__ __align__(16) float sm[];
+    if (threadIdx.x == 0) chain_mark(4, 0);
     attn_body(aa, sm, blockIdx.x, blockIdx.y * SLAB);
+    if (c_chain) { __syncthreads(); if (threadIdx.x == 0) chain_mark(4, 2); }
 }
 
 // Step-invariant B operands (folded queries, folded memory keys / values) are split into fp16 (hi, lo) ONCE (at
 // commit / bind) so that their fragments are plain 32-bit loads: rows operands as fp16 [rows][KPH] (k contiguous),
 // K x N operands with the two k-neighbours of a column packed in one word, [K/2][VPW].  Strides: KPH/2 = 4 mod 32
 // words, VPW = 8 mod 32 words (conflict-free).
-constexpr int KPH = D + 8;     // halfs per staged row of a pre-split "rows" operand
-constexpr int VPW = D + 8;     // words per staged row of a k-pair-packed K x N operand
 __device__ __forceinline__ void load_b_frag_rows_pk(const __half* __restrict__ sh, const __half* __restrict__ sl, int n0, int nrows,
                                                     int k0, int lane, uint32_t (&hi)[2], uint32_t (&lo)[2]) {
     const int off = min(n0 + (lane >> 2), nrows - 1) * KPH + k0 + 2 * (lane & 3);
@@ -550,61 +562,48 @@ __device__ __forceinline__ void cross_attention_tail(const float* __restrict__ s
     }
 }
 
-// stage the pre-split folded memory tensors of sample b: one bulk copy per row (keys: 512 B fp16 rows hi / lo;
-// values: 1 KB rows of k-pair words hi / lo); kc with plain loads
-__device__ __forceinline__ void stage_memory(const __half* __restrict__ kph, const __half* __restrict__ kpl, const float* __restrict__ kc,
-                                             const uint32_t* __restrict__ vph, const uint32_t* __restrict__ vpl,
-                                             __half* __restrict__ s_kph, __half* __restrict__ s_kpl, float* __restrict__ s_kc,
-                                             uint32_t* __restrict__ s_vph, uint32_t* __restrict__ s_vpl, int b, int B, int Tk, int H,
-                                             uint64_t* bar) {
-    const int HT = H * Tk, HP = HT >> 1, tid = threadIdx.x;
-    for (int i = tid; i < 2 * HT + 2 * HP; i += ANT) {
-        if (i < HT) bulk_g2s(s_kph + i * KPH, kph + ((size_t)b * HT + i) * D, D * sizeof(__half), bar);
-        else if (i < 2 * HT) bulk_g2s(s_kpl + (i - HT) * KPH, kpl + ((size_t)b * HT + i - HT) * D, D * sizeof(__half), bar);
-        else if (i < 2 * HT + HP) bulk_g2s(s_vph + (i - 2 * HT) * VPW, vph + ((size_t)b * HP + i - 2 * HT) * D, ROW_BYTES, bar);
-        else bulk_g2s(s_vpl + (i - 2 * HT - HP) * VPW, vpl + ((size_t)b * HP + i - 2 * HT - HP) * D, ROW_BYTES, bar);
-    }
-    for (int hj = tid; hj < HT; hj += ANT) s_kc[hj] = kc[(size_t)((hj % Tk) * B + b) * H + hj / Tk];
+// stage the packed folded memory tensors of sample b (k_pack_memory's block): ONE bulk copy, issued by the calling thread
+__device__ __forceinline__ void stage_memory(const uint8_t* __restrict__ mpack, __half* __restrict__ s_kph, int b, int HT, uint64_t* bar) {
+    bulk_g2s(s_kph, mpack + (size_t)b * mem_block_bytes(HT), (uint32_t)mem_block_bytes(HT), bar);
 }
 
 // standalone cross-attention block (layers whose first sub-block is the standard self-attention)
 struct XattnArgs {
-    const float* x1; const __half *kph, *kpl; const float* kc; const uint32_t *vph, *vpl; const float *bo, *lnw, *lnb;
+    const float* x1; const uint8_t* mpack; const float *bo, *lnw, *lnb;      // mpack: k_pack_memory's per-sample blocks
     float* out; __half *out_b, *out_s; int T, B, Tk, H;
 };
 // own_rows: the x1 rows were written by THIS CTA with plain stores just before (fused standard layer): read them back with
 // plain L2 loads instead of bulk copies (which would need a proxy fence)
 __device__ __forceinline__ void xattn_body(const XattnArgs& xa, float* sm, const int b, const int r0, const bool own_rows) {
-    const float* __restrict__ x1 = xa.x1; const __half* __restrict__ kph = xa.kph; const __half* __restrict__ kpl = xa.kpl;
-    const float* __restrict__ kc = xa.kc; const uint32_t* __restrict__ vph = xa.vph; const uint32_t* __restrict__ vpl = xa.vpl;
+    const float* __restrict__ x1 = xa.x1;
     const float* __restrict__ bo = xa.bo; const float* __restrict__ lnw = xa.lnw; const float* __restrict__ lnb = xa.lnb;
     float* __restrict__ out = xa.out; __half* __restrict__ out_b = xa.out_b; __half* __restrict__ out_s = xa.out_s;
-    const int T = xa.T, B = xa.B, Tk = xa.Tk, H = xa.H;
+    const int T = xa.T, Tk = xa.Tk, H = xa.H;
     const int HT = H * Tk;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: step-invariant tensors, [1]: input rows
     float* s_par = sm + 4;                  // bo, lnw, lnb
     float* s_x1 = s_par + 3 * D;            // [SLAB][LDX]
-    __half* s_kph = reinterpret_cast<__half*>(s_x1 + SLAB * LDX);      // [HT][KPH] fp16, hi then lo
-    __half* s_kpl = s_kph + HT * KPH;
+    __half* s_kph = reinterpret_cast<__half*>(s_x1 + SLAB * LDX);      // [HT][KPH] fp16, hi then lo     } one block, laid out like
+    __half* s_kpl = s_kph + HT * KPH;                                  //                                 } k_pack_memory's
     uint32_t* s_vph = reinterpret_cast<uint32_t*>(s_kpl + HT * KPH);   // [HT/2][VPW] k-pair words, hi then lo
     uint32_t* s_vpl = s_vph + (HT >> 1) * VPW;
-    float* s_a = reinterpret_cast<float*>(s_vpl + (HT >> 1) * VPW);    // [SLAB][PLD]     probabilities
+    float* s_kc = reinterpret_cast<float*>(s_vpl + (HT >> 1) * VPW);   // [HT] (padded to a multiple of 4)
+    float* s_a = s_kc + ((HT + 3) & ~3);    // [SLAB][PLD]     probabilities
     float* s_z = s_a + SLAB * PLD;          // [SLAB][LDZ]
-    float* s_kc = s_z + SLAB * LDZ;         // [HT]
     const int nr = min(SLAB, T - r0), tid = threadIdx.x;
     pdl_trigger();
     if (tid == 0) {
+        // the initialising thread issues every step-invariant copy itself, at once (they overlap the previous kernel under
+        // programmatic dependent launch, or - when this CTA only got an SM after the previous kernel left it - the row loads)
         mb_init(bar, 1); mb_init(bar + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mb_expect_tx(bar, 3u * ROW_BYTES + (uint32_t)mem_block_bytes(HT));
+        bulk_g2s(s_par, bo, ROW_BYTES, bar); bulk_g2s(s_par + D, lnw, ROW_BYTES, bar); bulk_g2s(s_par + 2 * D, lnb, ROW_BYTES, bar);
+        stage_memory(xa.mpack, s_kph, b, HT, bar);
     }
     __syncthreads();
-    if (tid == 0) {
-        mb_expect_tx(bar, (uint32_t)(3 + 2 * HT) * ROW_BYTES);
-        bulk_g2s(s_par, bo, ROW_BYTES, bar); bulk_g2s(s_par + D, lnw, ROW_BYTES, bar); bulk_g2s(s_par + 2 * D, lnb, ROW_BYTES, bar);
-    }
-    __syncwarp();
-    stage_memory(kph, kpl, kc, vph, vpl, s_kph, s_kpl, s_kc, s_vph, s_vpl, b, B, Tk, H, bar);     // step-invariant: overlaps the previous kernel
     pdl_wait();
+    if (tid == 0) chain_mark(0, 1);
     if (own_rows) {
         for (int i = tid; i < nr * (D / 4); i += ANT) {
             const int l = i / (D / 4), c = i % (D / 4);
@@ -617,7 +616,7 @@ __device__ __forceinline__ void xattn_body(const XattnArgs& xa, float* sm, const
     }
     mb_wait(bar, 0);
     if (!own_rows) mb_wait(bar + 1, 0);
-    __syncthreads();     // s_kc (and own rows) were written with plain stores
+    __syncthreads();     // own rows were written with plain stores
     cross_attention_tail(s_x1, s_kph, s_kpl, s_kc, s_vph, s_vpl, s_a, s_z, nr, HT, Tk, H, s_par, s_par + D, s_par + 2 * D, out, out_b,
                          out_s, (size_t)b * T + r0);
 }
@@ -625,7 +624,9 @@ __device__ __forceinline__ void xattn_body(const XattnArgs& xa, float* sm, const
 __global__ void __launch_bounds__(ANT)
 k_xattn_ln(const XattnArgs xa) {
     extern __shared__ __align__(16) float sm[];
+    if (threadIdx.x == 0) chain_mark(5, 0);
     xattn_body(xa, sm, blockIdx.x, blockIdx.y * SLAB, false);
+    if (c_chain) { __syncthreads(); if (threadIdx.x == 0) chain_mark(5, 2); }
 }
 
 // QaN block + residual + LayerNorm1 (model/sublayers.py:343-352 + :332) for a slab of <= 16 rows of
@@ -637,68 +638,64 @@ k_xattn_ln(const XattnArgs xa) {
 // ... followed, in the same kernel, by the layer's cross-attention block (cross_attention_tail) on the
 // LN1 rows, which never leave shared memory.
 struct QanArgs {
-    const float *zin, *prew, *preb; const __half *qth, *qtl; const float *wk, *lnw, *lnb; const __half *kph, *kpl; const float* kc;
-    const uint32_t *vph, *vpl; const float *bo2, *ln2w, *ln2b; float* out; __half *out_b, *out_s; int T, N, B, Tk, H;
+    const float *zin, *prew, *preb; const __half* qpack; const float *wk, *lnw, *lnb;      // qpack: [2 (hi, lo)][3N][KPH] folded queries
+    const uint8_t* mpack; const float *bo2, *ln2w, *ln2b; float* out; __half *out_b, *out_s; int T, N, B, Tk, H;   // mpack: k_pack_memory's blocks
 };
 // the slab (sample b, rows r0 .. r0 + 15) of the kernel below as a device function on caller-provided shared memory `sm`
 // (16-byte aligned, qan_smem() bytes): also phase A of the fused decoder-layer kernel
 template <bool XATTN>
 __device__ __forceinline__ void qan_xattn_body(const QanArgs& qa, float* sm, const int b, const int r0) {
     const float* __restrict__ zin = qa.zin; const float* __restrict__ prew = qa.prew; const float* __restrict__ preb = qa.preb;
-    const __half* __restrict__ qth = qa.qth; const __half* __restrict__ qtl = qa.qtl; const float* __restrict__ wk = qa.wk;
-    const float* __restrict__ lnw = qa.lnw; const float* __restrict__ lnb = qa.lnb; const __half* __restrict__ kph = qa.kph;
-    const __half* __restrict__ kpl = qa.kpl; const float* __restrict__ kc = qa.kc; const uint32_t* __restrict__ vph = qa.vph;
-    const uint32_t* __restrict__ vpl = qa.vpl; const float* __restrict__ bo2 = qa.bo2; const float* __restrict__ ln2w = qa.ln2w;
+    const float* __restrict__ wk = qa.wk;
+    const float* __restrict__ lnw = qa.lnw; const float* __restrict__ lnb = qa.lnb;
+    const float* __restrict__ bo2 = qa.bo2; const float* __restrict__ ln2w = qa.ln2w;
     const float* __restrict__ ln2b = qa.ln2b; float* __restrict__ out = qa.out; __half* __restrict__ out_b = qa.out_b;
     __half* __restrict__ out_s = qa.out_s;
-    const int T = qa.T, N = qa.N, B = qa.B, Tk = qa.Tk, H = qa.H;
+    const int T = qa.T, N = qa.N, Tk = qa.Tk, H = qa.H;
     const int HT = H * Tk, NQ = 3 * N;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sm);   // [0]: step-invariant tensors, [1]: input rows
     float* s_par = sm + 4;                  // pre w, pre b, ln1 w, ln1 b, bo2, ln2 w, ln2 b
     float* s_x = s_par + 7 * D;             // [SLAB+2][LDX]   rows r0-1 .. r0+nr
-    __half* s_qth = reinterpret_cast<__half*>(s_x + (SLAB + 2) * LDX);   // [30][KPH] fp16 folded queries, hi then lo
-    __half* s_qtl = s_qth + 30 * KPH;
-    float* s_x1 = reinterpret_cast<float*>(s_qtl + 30 * KPH);            // [SLAB][LDX]     LN1 rows (input of the cross-attention block)
-    __half* s_kph = reinterpret_cast<__half*>(s_x1 + SLAB * LDX);        // [HT][KPH]
-    __half* s_kpl = s_kph + HT * KPH;
+    __half* s_qth = reinterpret_cast<__half*>(s_x + (SLAB + 2) * LDX);   // [NQ <= 30][KPH] fp16 folded queries, hi then lo (= qpack)
+    __half* s_qtl = s_qth + NQ * KPH;
+    float* s_x1 = reinterpret_cast<float*>(s_qth + 2 * 30 * KPH);       // [SLAB][LDX]     LN1 rows (input of the cross-attention block)
+    __half* s_kph = reinterpret_cast<__half*>(s_x1 + SLAB * LDX);        // [HT][KPH]       } one block, laid out like
+    __half* s_kpl = s_kph + HT * KPH;                                    //                 } k_pack_memory's
     uint32_t* s_vph = reinterpret_cast<uint32_t*>(s_kpl + HT * KPH);     // [HT/2][VPW]
     uint32_t* s_vpl = s_vph + (HT >> 1) * VPW;
-    float* s_a = reinterpret_cast<float*>(s_vpl + (HT >> 1) * VPW);      // [SLAB][PLD]     probabilities
+    float* s_kc = reinterpret_cast<float*>(s_vpl + (HT >> 1) * VPW);     // [HT] (padded to a multiple of 4)
+    float* s_a = s_kc + ((HT + 3) & ~3);                                 // [SLAB][PLD]     probabilities
     float* s_z = XATTN ? s_a + SLAB * PLD : s_x1;   // [SLAB][LDZ]  (encoder variant: no cross-attention buffers at all)
-    float* s_kc = s_z + SLAB * LDZ;         // [HT]
     const int nr = min(SLAB, T - r0), tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    // Everything the kernel reads from global memory is requested up front as row-sized bulk copies: first
-    // the step-invariant tensors (parameters, folded queries, folded memory keys / values), which overlap
-    // the previous kernel's tail under programmatic dependent launch, then - after the dependency wait -
-    // the input rows r0-1 .. r0+nr (halo of one on each side), local index l = t - (r0 - 1).
+    // Everything step-invariant (parameter rows, the folded queries as ONE block, the sample's folded memory keys / values / kc
+    // as ONE block) is requested by the thread that initialises the barriers, before the CTA-wide barrier: the copies
+    // overlap the previous kernel's tail under programmatic dependent launch, or - when this CTA only got its SM after the
+    // previous kernel left it - the loads of the input rows r0-1 .. r0+nr (halo of one on each side, l = t - (r0 - 1)).
+    // Two barriers: [0] parameters + folded queries (needed by the QaN block right away), [1] the memory block (84 KB, needed
+    // only by the cross-attention block: its copy overlaps the QaN block).
     pdl_trigger();
     ATRACE(0);
     if (tid == 0) {
         mb_init(bar, 1); mb_init(bar + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int npar = (prew ? 2 : 0) + 2 + (XATTN ? 3 : 0);
+        const uint32_t qbytes = (uint32_t)(2 * NQ * KPH * sizeof(__half));
+        mb_expect_tx(bar, (uint32_t)npar * ROW_BYTES + qbytes);
+        bulk_g2s(s_qth, qa.qpack, qbytes, bar);
+        if (prew) { bulk_g2s(s_par, prew, ROW_BYTES, bar); bulk_g2s(s_par + D, preb, ROW_BYTES, bar); }
+        bulk_g2s(s_par + 2 * D, lnw, ROW_BYTES, bar); bulk_g2s(s_par + 3 * D, lnb, ROW_BYTES, bar);
+        if (XATTN) {
+            bulk_g2s(s_par + 4 * D, bo2, ROW_BYTES, bar); bulk_g2s(s_par + 5 * D, ln2w, ROW_BYTES, bar); bulk_g2s(s_par + 6 * D, ln2b, ROW_BYTES, bar);
+            mb_expect_tx(bar + 1, (uint32_t)mem_block_bytes(HT));
+            stage_memory(qa.mpack, s_kph, b, HT, bar + 1);
+        }
     }
     __syncthreads();
-    // two barriers: [0] parameters + folded queries (needed by the QaN block right away), [1] the sample's folded memory keys /
-    // values (84 KB, needed only by the cross-attention block: their copy overlaps the QaN block)
-    const int npar = (prew ? 2 : 0) + 2 + (XATTN ? 3 : 0);
-    if (tid == 0) {
-        mb_expect_tx(bar, (uint32_t)(npar + NQ) * ROW_BYTES);
-        if (XATTN) mb_expect_tx(bar + 1, (uint32_t)(2 * HT) * ROW_BYTES);
-    }
-    __syncwarp();
-    if (tid < 7) {
-        const float* src = tid == 0 ? prew : tid == 1 ? preb : tid == 2 ? lnw : tid == 3 ? lnb : tid == 4 ? bo2 : tid == 5 ? ln2w : ln2b;
-        if (src && (XATTN || tid < 4)) bulk_g2s(s_par + tid * D, src, ROW_BYTES, bar);
-    } else if (tid >= 32 && tid < 32 + 2 * NQ) {
-        const int r = tid - 32;
-        if (r < NQ) bulk_g2s(s_qth + r * KPH, qth + (size_t)r * D, D * sizeof(__half), bar);
-        else bulk_g2s(s_qtl + (r - NQ) * KPH, qtl + (size_t)(r - NQ) * D, D * sizeof(__half), bar);
-    }
-    if (XATTN) stage_memory(kph, kpl, kc, vph, vpl, s_kph, s_kpl, s_kc, s_vph, s_vpl, b, B, Tk, H, bar + 1);
     const float wk_n = lane < N ? wk[lane] : 0.f;
     ATRACE(1);
     pdl_wait();
+    if (tid == 0) chain_mark(0, 1);
     ATRACE(2);
     {
         // the input rows were just written by the previous kernel (L2 resident): plain 16-byte loads straight into the
@@ -710,7 +707,7 @@ __device__ __forceinline__ void qan_xattn_body(const QanArgs& qa, float* sm, con
         }
     }
     mb_wait(bar, 0);
-    __syncthreads();     // s_x rows and s_kc were written with plain stores
+    __syncthreads();     // s_x rows were written with plain stores
     ATRACE(3);
     if (prew) {   // the previous layer's pending LayerNorm3, in place on the staged rows
         for (int l = warp; l < nr + 2; l += ANW) {
@@ -820,7 +817,9 @@ template <bool XATTN>
 __global__ void __launch_bounds__(ANT)
 k_qan_xattn_ln(const QanArgs qa) {
     extern __shared__ __align__(16) float sm[];
+    if (threadIdx.x == 0) chain_mark(3, 0);
     qan_xattn_body<XATTN>(qa, sm, blockIdx.x, blockIdx.y * SLAB);
+    if (c_chain) { __syncthreads(); if (threadIdx.x == 0) chain_mark(3, 2); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -930,6 +929,7 @@ struct StepIO {
     const float* x0_in; const float* xt; const float* noise; float* x_next;
     const StepParams* tbl; int* step_cur; int* ticket;
     int tape_mode, n_steps, emit_next;
+    int i_host;     // >= 0: the step index, known when the launch is enqueued (else read from step_cur after the dependency wait)
     // tokens
     const float* x_in; const long long* tstep;
     __half* xtok_b; __half* xtok_s; const float* tab; const float* pe; float* add;
@@ -945,12 +945,82 @@ __global__ void __launch_bounds__(256) k_step_io(const StepIO a) {
     const int LT = T + 1;
     float* tile = sm;                 // [ncp][T+1]
     float* pose = sm + ncp * LT;      // [T][8]  (skeleton: object translation + quaternion per frame)
+    if (tid == 0) chain_mark(6, 0);
     pdl_trigger();
-    pdl_wait();
+    const int n = nc * T;
+    constexpr int KM = 5, NA = 3;
+    float v_in[KM], v_xt[KM], v_nz[KM], v_gt[KM];
+    unsigned char v_m[KM];
     int i_step = 0;
     StepParams sp = {};
-    if (MODE & 2) { i_step = *a.step_cur; sp = a.tbl[i_step]; }
-    const int n = nc * T;
+    const float* nz = nullptr;
+    // the loads of a batch of KM elements per thread, in two groups: "static" operands exist before the loop's first kernel
+    // (noise tape, inpainting ground truth / mask), "dynamic" ones are written by earlier kernels of the chain
+    auto step_setup = [&]() {
+        sp = a.tbl[i_step];
+        // tape_mode 0: `noise` is this step's eps; 1: `noise` is the tape (n_steps + 1 entries, [0] = x_T); 2: `noise` is a
+        // device slot holding the tape pointer (captured graphs stay valid when the caller passes a new tape tensor)
+        const float* base = a.tape_mode == 2 ? *reinterpret_cast<const float* const*>(a.noise) : a.noise;
+        nz = a.tape_mode ? base + (size_t)(a.n_steps - i_step) * ((size_t)gridDim.x * a.C * T) : base;
+    };
+    auto load_static = [&](int base) {
+#pragma unroll
+        for (int k = 0; k < KM; k++) {
+            const int e = base + tid + k * 256;
+            v_nz[k] = v_gt[k] = 0.f; v_m[k] = 0;
+            if (e < n) {
+                const size_t o = ((size_t)b * a.C + c0) * T + e;        // (B,1,C,T): the block's channels are contiguous
+                if (MODE & 2) v_nz[k] = nz[o];
+                if ((MODE & 1) && a.mask) { v_m[k] = a.mask[o]; v_gt[k] = a.gt[o]; }
+            }
+        }
+    };
+    auto load_dynamic = [&](int base) {
+#pragma unroll
+        for (int k = 0; k < KM; k++) {
+            const int e = base + tid + k * 256;
+            v_in[k] = v_xt[k] = 0.f;
+            if (e < n) {
+                const size_t o = ((size_t)b * a.C + c0) * T + e;
+                if (MODE == 2) v_in[k] = a.x0_in[o];
+                if (MODE == 4) v_in[k] = a.x_in[o];
+                if (MODE & 2) v_xt[k] = a.xt[o];
+            }
+        }
+    };
+    // When the host knows the step index at enqueue time (plain launches, whole-loop graph) nothing "static" depends on an
+    // earlier kernel of the chain: the table entry, the noise / ground truth / mask of the first batch and the rows of the
+    // next step's embedding addend are loaded BEFORE the dependency wait, under the previous kernel's tail (this kernel's
+    // blocks are small enough to be resident next to it).
+    const bool early = (MODE & 2) && a.i_host >= 0;
+    const int nq = T * (D / 4), per = (nq + NP - 1) / NP, q1 = min(nq, (part + 1) * per);
+    float4 add_pre[NA];
+    bool add_early = false;
+    if (early) {
+        i_step = a.i_host;
+        step_setup();
+        load_static(0);
+        if (a.emit_next && i_step > 0 && per <= NA * 256) {
+            long long ti = a.tbl[i_step - 1].t;
+            if (ti < 0) ti = 0;
+            if (ti >= a.pe_rows) ti = a.pe_rows - 1;
+            const float4* trow = reinterpret_cast<const float4*>(a.tab + (size_t)ti * D);
+#pragma unroll
+            for (int k = 0; k < NA; k++) {
+                const int i = part * per + tid + k * 256;
+                add_pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < q1) {
+                    const float4 p4 = reinterpret_cast<const float4*>(a.pe + (size_t)(i / (D / 4)) * D)[i % (D / 4)];
+                    const float4 o4 = trow[i % (D / 4)];
+                    add_pre[k] = make_float4(o4.x + p4.x, o4.y + p4.y, o4.z + p4.z, o4.w + p4.w);
+                }
+            }
+            add_early = true;
+        }
+    }
+    pdl_wait();
+    if (tid == 0) chain_mark(6, 1);
+    if ((MODE & 2) && !early) { i_step = *a.step_cur; step_setup(); }
     if (MODE & 1) {
         // stage the block's linear-head columns, transposed; derived keypoint channels are rebuilt from the pose
         const float* lrow = a.lin + (size_t)b * T * a.Clin;
@@ -962,31 +1032,12 @@ __global__ void __launch_bounds__(256) k_step_io(const StepIO a) {
         }
         if (a.variant != 0)
             for (int j = tid; j < T * 7; j += 256) pose[(j / 7) * 8 + j % 7] = lrow[(size_t)(j / 7) * a.Clin + a.c_body + j % 7];
-        __syncthreads();
     }
-    const float* nz = nullptr;
-    if (MODE & 2) {
-        // tape_mode 0: `noise` is this step's eps; 1: `noise` is the tape (n_steps + 1 entries, [0] = x_T); 2: `noise` is a
-        // device slot holding the tape pointer (captured graphs stay valid when the caller passes a new tape tensor)
-        const float* base = a.tape_mode == 2 ? *reinterpret_cast<const float* const*>(a.noise) : a.noise;
-        nz = a.tape_mode ? base + (size_t)(a.n_steps - i_step) * ((size_t)gridDim.x * a.C * T) : base;
-    }
-    constexpr int KM = 5;
+    load_dynamic(0);
+    if (!early) load_static(0);
+    if (MODE & 1) __syncthreads();
     for (int base = 0; base < n; base += 256 * KM) {
-        float v_in[KM], v_xt[KM], v_nz[KM], v_gt[KM];
-        unsigned char v_m[KM];
-#pragma unroll
-        for (int k = 0; k < KM; k++) {
-            const int e = base + tid + k * 256;
-            v_in[k] = v_xt[k] = v_nz[k] = v_gt[k] = 0.f; v_m[k] = 0;
-            if (e < n) {
-                const size_t o = ((size_t)b * a.C + c0) * T + e;        // (B,1,C,T): the block's channels are contiguous
-                if (MODE == 2) v_in[k] = a.x0_in[o];
-                if (MODE == 4) v_in[k] = a.x_in[o];
-                if (MODE & 2) { v_xt[k] = a.xt[o]; v_nz[k] = nz[o]; }
-                if ((MODE & 1) && a.mask) { v_m[k] = a.mask[o]; v_gt[k] = a.gt[o]; }
-            }
-        }
+        if (base) { load_dynamic(base); load_static(base); }
 #pragma unroll
         for (int k = 0; k < KM; k++) {
             const int e = base + tid + k * 256;
@@ -1031,16 +1082,23 @@ __global__ void __launch_bounds__(256) k_step_io(const StepIO a) {
             const size_t o = ((size_t)b * T + t) * a.Cp + c0 + cc;
             split_f16(cc < nc ? tile[cc * LT + t] : 0.f, a.xtok_b[o], a.xtok_s[o]);     // (hi, lo) fp16 pair; padding columns zero
         }
-        long long ti = MODE == 4 ? (a.tstep ? a.tstep[b] : a.tbl[*a.step_cur].t) : a.tbl[i_step - 1].t;
-        if (ti < 0) ti = 0;
-        if (ti >= a.pe_rows) ti = a.pe_rows - 1;
-        const float4* trow = reinterpret_cast<const float4*>(a.tab + (size_t)ti * D);
-        const int nq = T * (D / 4), per = (nq + NP - 1) / NP, q1 = min(nq, (part + 1) * per);
-        for (int i = part * per + tid; i < q1; i += 256) {
-            const int tt = i / (D / 4), c = i % (D / 4);
-            const float4 p4 = reinterpret_cast<const float4*>(a.pe + (size_t)tt * D)[c];
-            const float4 o4 = trow[c];
-            reinterpret_cast<float4*>(a.add + ((size_t)b * T + tt) * D)[c] = make_float4(o4.x + p4.x, o4.y + p4.y, o4.z + p4.z, o4.w + p4.w);
+        if (add_early) {
+#pragma unroll
+            for (int k = 0; k < NA; k++) {
+                const int i = part * per + tid + k * 256;
+                if (i < q1) reinterpret_cast<float4*>(a.add + ((size_t)b * T + i / (D / 4)) * D)[i % (D / 4)] = add_pre[k];
+            }
+        } else {
+            long long ti = MODE == 4 ? (a.tstep ? a.tstep[b] : a.tbl[*a.step_cur].t) : a.tbl[i_step - 1].t;
+            if (ti < 0) ti = 0;
+            if (ti >= a.pe_rows) ti = a.pe_rows - 1;
+            const float4* trow = reinterpret_cast<const float4*>(a.tab + (size_t)ti * D);
+            for (int i = part * per + tid; i < q1; i += 256) {
+                const int tt = i / (D / 4), c = i % (D / 4);
+                const float4 p4 = reinterpret_cast<const float4*>(a.pe + (size_t)tt * D)[c];
+                const float4 o4 = trow[c];
+                reinterpret_cast<float4*>(a.add + ((size_t)b * T + tt) * D)[c] = make_float4(o4.x + p4.x, o4.y + p4.y, o4.z + p4.z, o4.w + p4.w);
+            }
         }
     }
     if ((MODE & 2) && a.emit_next) {
@@ -1052,9 +1110,12 @@ __global__ void __launch_bounds__(256) k_step_io(const StepIO a) {
             if (done == (int)(gridDim.x * gridDim.y) - 1) { *a.ticket = 0; *a.step_cur = i_step - 1; }
         }
     }
+    if (c_chain) { __syncthreads(); if (tid == 0) chain_mark(6, 2); }
 }
 
 }  // namespace
+
+CHAIN_SETTER(idb_chain_set_denoiser)
 
 /* test / profiling hook: how many 8-CTA clusters of the fused decoder-layer kernel the device can hold at once */
 extern "C" int idb_debug_max_layer_clusters(idb_handle* h) {
@@ -1389,7 +1450,21 @@ extern "C" int idb_denoiser_commit(idb_handle* h) {
         for (auto* stack : {&d.layers, &d.enc_layers})
             for (auto& L : *stack) {
                 if (!rc && !L.qan) rc = split(L.w_qkvf, 2 * D + H * D, D, D, &L.w_qkvf_b, &L.w_qkvf_s);
-                if (!rc && L.qan) rc = split(L.qt, 3 * N, D, D, &L.qt_b, &L.qt_s);
+                if (!rc && L.qan) {
+                    // folded queries as fp16 (hi, lo), rows padded to the stride the kernels keep in shared memory: one block
+                    __half *qb = nullptr, *qs = nullptr;
+                    rc = split(L.qt, 3 * N, D, D, &qb, &qs);
+                    if (!rc) {
+                        CUDA_TRY(h, cudaDeviceSynchronize());      // the split kernels ran on the handle's stream
+                        const size_t half_bytes = (size_t)3 * N * KPH * sizeof(__half);
+                        CUDA_TRY(h, cudaMalloc((void**)&L.qt_pack, 2 * half_bytes));
+                        d.owned.push_back(reinterpret_cast<float*>(L.qt_pack));
+                        CUDA_TRY(h, cudaMemset(L.qt_pack, 0, 2 * half_bytes));
+                        CUDA_TRY(h, cudaMemcpy2D(L.qt_pack, KPH * sizeof(__half), qb, D * sizeof(__half), D * sizeof(__half), 3 * N, cudaMemcpyDeviceToDevice));
+                        CUDA_TRY(h, cudaMemcpy2D(reinterpret_cast<uint8_t*>(L.qt_pack) + half_bytes, KPH * sizeof(__half), qs, D * sizeof(__half),
+                                                 D * sizeof(__half), 3 * N, cudaMemcpyDeviceToDevice));
+                    }
+                }
                 if (!rc) rc = split(L.w1, F, D, D, &L.w1_b, &L.w1_s);
                 if (!rc) rc = split(L.w2, D, F, F, &L.w2_b, &L.w2_s);
             }
@@ -1439,8 +1514,8 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
         for (auto& L : d.layers) {
             rc |= A(&L.kv_mem, (size_t)Tm * B * 2 * D); rc |= A(&L.vp_mem, (size_t)Tm * B * H * D);
             rc |= A(&L.kp_mem, (size_t)Tm * B * H * D); rc |= A(&L.kc_mem, (size_t)Tm * B * H);
-            rc |= AH(&L.kp_hi, (size_t)Tm * B * H * D); rc |= AH(&L.kp_lo, (size_t)Tm * B * H * D);
-            rc |= AH(reinterpret_cast<__half**>(&L.vp_hi), (size_t)Tm * B * H * D); rc |= AH(reinterpret_cast<__half**>(&L.vp_lo), (size_t)Tm * B * H * D);
+            rc |= AH(&L.mem_pack, (size_t)B * mem_block_bytes(H * Tm) / sizeof(__half));
+            if (!rc) cudaMemsetAsync(L.mem_pack, 0, (size_t)B * mem_block_bytes(H * Tm), st);      // pad columns
         }
         if (rc) return rc;
         CUDA_TRY(h, cudaMalloc((void**)&d.step_cur, 2 * sizeof(int)));
@@ -1467,7 +1542,7 @@ extern "C" int idb_denoiser_bind(idb_handle* h, int B, int T, int Tm, const floa
         }
         k_fold_scale<<<(Tm * B * H + 7) / 8, 256, 0, st>>>(L.kp_mem, L.kv_mem, L.b_qc, L.kc_mem, Tm * B, H);
         LAUNCH_CHECK(h);
-        k_pack_memory<<<dim3(H * Tm, B), D, 0, st>>>(L.kp_mem, L.vp_mem, L.kp_hi, L.kp_lo, L.vp_hi, L.vp_lo, B, Tm, H);
+        k_pack_memory<<<dim3(H * Tm, B), D, 0, st>>>(L.kp_mem, L.vp_mem, L.kc_mem, reinterpret_cast<uint8_t*>(L.mem_pack), B, Tm, H);
         LAUNCH_CHECK(h);
     }
     return IDB_OK;
@@ -1519,8 +1594,8 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
         if (L.qan) {
             QanArgs qa = {};
             qa.zin = pending ? d.z : d.h; qa.prew = pending ? pending->ln3w : nullptr; qa.preb = pending ? pending->ln3b : nullptr;
-            qa.qth = L.qt_b; qa.qtl = L.qt_s; qa.wk = L.wk; qa.lnw = L.ln1w; qa.lnb = L.ln1b; qa.kph = L.kp_hi; qa.kpl = L.kp_lo; qa.kc = L.kc_mem;
-            qa.vph = L.vp_hi; qa.vpl = L.vp_lo; qa.bo2 = L.b_oc; qa.ln2w = L.ln2w; qa.ln2b = L.ln2b; qa.out = d.h2; qa.out_b = d.h2_b; qa.out_s = d.h2_s;
+            qa.qpack = L.qt_pack; qa.wk = L.wk; qa.lnw = L.ln1w; qa.lnb = L.ln1b; qa.mpack = reinterpret_cast<const uint8_t*>(L.mem_pack);
+            qa.bo2 = L.b_oc; qa.ln2w = L.ln2w; qa.ln2b = L.ln2b; qa.out = d.h2; qa.out_b = d.h2_b; qa.out_s = d.h2_s;
             qa.T = T; qa.N = N; qa.B = B; qa.Tk = Tm; qa.H = H;
             if (fused && h->fused_mlp >= 3 && !pending && qan_smem(Tm, H) <= (size_t)(tc::mlp::RING + tc::mlp::S_BYTES)) {
                 // the whole layer in one cluster kernel (attention phase + feed-forward phase on sample-aligned row tiles)
@@ -1548,7 +1623,7 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
             aa.q = d.qkv; aa.ldq = NQ; aa.k = d.qkv + D; aa.ldk = NQ; aa.v = d.qkv + 2 * D; aa.ldv = NQ; aa.res = d.h; aa.bo = L.bo_f;
             aa.lnw = L.ln1w; aa.lnb = L.ln1b; aa.out = d.qc; aa.T = T; aa.H = H;
             XattnArgs xa = {};
-            xa.x1 = d.qc; xa.kph = L.kp_hi; xa.kpl = L.kp_lo; xa.kc = L.kc_mem; xa.vph = L.vp_hi; xa.vpl = L.vp_lo; xa.bo = L.b_oc;
+            xa.x1 = d.qc; xa.mpack = reinterpret_cast<const uint8_t*>(L.mem_pack); xa.bo = L.b_oc;
             xa.lnw = L.ln2w; xa.lnb = L.ln2b; xa.out = d.h2; xa.out_b = d.h2_b; xa.out_s = d.h2_s; xa.T = T; xa.B = B; xa.Tk = Tm; xa.H = H;
             if (fused && h->fused_mlp >= 3 && attn_smem(T, H) <= (size_t)(tc::mlp::RING + tc::mlp::S_BYTES) &&
                 xattn_smem(Tm, H) <= (size_t)(tc::mlp::RING + tc::mlp::S_BYTES)) {
@@ -1605,6 +1680,7 @@ static StepIO step_io_base(idb_handle* h) {
     Denoiser& d = h->den;
     const idb_denoiser_config& c = d.cfg;
     StepIO a = {};
+    a.i_host = -1;
     a.lin = d.lin; a.zero_pose = d.zero_pose;
     a.tbl = h->diff.tbl; a.step_cur = d.step_cur; a.ticket = d.ticket; a.n_steps = h->diff.n;
     a.xtok_b = d.xtok_b; a.xtok_s = d.xtok_s; a.tab = d.temb_tab; a.pe = d.pe; a.add = d.addend; a.pe_rows = d.pe_rows;
@@ -1657,16 +1733,18 @@ int idb_denoiser_heads(idb_handle* h, const float* gt, const unsigned char* mask
 
 // posterior sample from a given x0 (after the correction hook, or the stand-alone finish call)
 int idb_step_finish(idb_handle* h, const float* x0, const float* xt, const float* noise, int tape_mode, float* x_next, int emit_next,
-                    cudaStream_t st) {
+                    cudaStream_t st, int i_host) {
     StepIO a = step_io_base(h);
+    a.i_host = i_host;
     a.x0_in = x0; a.xt = xt; a.noise = noise; a.tape_mode = tape_mode; a.x_next = x_next; a.emit_next = emit_next;
     return launch_step_io<2>(h, a, st);
 }
 
 // heads + posterior sample + next step's tokens in one kernel (the tail of a plain sampling step)
 int idb_step_tail(idb_handle* h, const float* gt, const unsigned char* mask, float* x0_out, const float* xt, const float* noise,
-                  int tape_mode, float* x_next, int emit_next, cudaStream_t st) {
+                  int tape_mode, float* x_next, int emit_next, cudaStream_t st, int i_host) {
     StepIO a = step_io_base(h);
+    a.i_host = i_host;
     a.gt = gt; a.mask = mask; a.x0_out = x0_out;
     a.xt = xt; a.noise = noise; a.tape_mode = tape_mode; a.x_next = x_next; a.emit_next = emit_next;
     return launch_step_io<3>(h, a, st);
@@ -1779,7 +1857,7 @@ extern "C" int idb_encode_condition(idb_handle* h, int B, int Tp, const float* p
         if (L.qan) {
             QanArgs qa = {};
             qa.zin = pending ? d.e_z : d.e_h; qa.prew = pending ? pending->ln3w : nullptr; qa.preb = pending ? pending->ln3b : nullptr;
-            qa.qth = L.qt_b; qa.qtl = L.qt_s; qa.wk = L.wk; qa.lnw = L.ln1w; qa.lnb = L.ln1b;
+            qa.qpack = L.qt_pack; qa.wk = L.wk; qa.lnw = L.ln1w; qa.lnb = L.ln1b;
             qa.out = d.e_h2; qa.out_b = d.e_h2_b; qa.out_s = d.e_h2_s; qa.T = Tp; qa.N = N; qa.B = B; qa.Tk = 0; qa.H = H;
             idb_launch(pdl, k_qan_xattn_ln<false>, slab_grid, ANT, qan_enc_smem(), st, qa);
             LAUNCH_CHECK(h);

@@ -12,10 +12,11 @@
 int idb_denoiser_tokens(idb_handle* h, const float* x, const long long* tstep, cudaStream_t st);
 int idb_denoiser_body(idb_handle* h, cudaStream_t st);
 int idb_denoiser_heads(idb_handle* h, const float* gt, const unsigned char* mask, float* out, cudaStream_t st);
+// i_host >= 0: the step index is known when the launch is enqueued (plain launches, whole-loop graph); -1: device counter
 int idb_step_finish(idb_handle* h, const float* x0, const float* xt, const float* noise, int tape_mode, float* x_next, int emit_next,
-                    cudaStream_t st);
+                    cudaStream_t st, int i_host);
 int idb_step_tail(idb_handle* h, const float* gt, const unsigned char* mask, float* x0_out, const float* xt, const float* noise,
-                  int tape_mode, float* x_next, int emit_next, cudaStream_t st);
+                  int tape_mode, float* x_next, int emit_next, cudaStream_t st, int i_host);
 int idb_correction_apply_dev(idb_handle* h, float* x0, const float* gt, int t, cudaStream_t st);
 int idb_correction_prepare(idb_handle* h, int B, int T);
 
@@ -144,7 +145,7 @@ extern "C" int idb_p_sample_finish(idb_handle* h, int i, const float* x0, const 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = set_step(h, i, st);
     if (rc) return rc;
-    return idb_step_finish(h, x0, x_t, noise, 0, x_out, 0, st);
+    return idb_step_finish(h, x0, x_t, noise, 0, x_out, 0, st, -1);
 }
 
 extern "C" int idb_p_sample(idb_handle* h, int i, const float* x_t, const float* noise, const float* gt, const uint8_t* mask,
@@ -158,15 +159,15 @@ extern "C" int idb_p_sample(idb_handle* h, int i, const float* x_t, const float*
     if (rc) return rc;
     if ((rc = idb_denoiser_tokens(h, x_t, nullptr, st))) return rc;
     if ((rc = idb_denoiser_body(h, st))) return rc;
-    return idb_step_tail(h, gt, mask, x0_out, x_t, noise, 0, x_out, 0, st);
+    return idb_step_tail(h, gt, mask, x0_out, x_t, noise, 0, x_out, 0, st, i);
 }
 
 // One plain step / one correction step on the sampler's own buffers (x in place in s.x_a; gt / mask = the
 // graph-stable copies; noise through the tape slot).
-static int plain_step(idb_handle* h, Sampler& s, const float* gt, const unsigned char* mask, cudaStream_t st) {
+static int plain_step(idb_handle* h, Sampler& s, const float* gt, const unsigned char* mask, cudaStream_t st, int i_host) {
     int rc = idb_denoiser_body(h, st);
     if (rc) return rc;
-    return idb_step_tail(h, gt, mask, nullptr, s.x_a, reinterpret_cast<const float*>(s.tape_slot), 2, s.x_a, 1, st);
+    return idb_step_tail(h, gt, mask, nullptr, s.x_a, reinterpret_cast<const float*>(s.tape_slot), 2, s.x_a, 1, st, i_host);
 }
 static int predict_part(idb_handle* h, Sampler& s, const float* gt, const unsigned char* mask, cudaStream_t st) {
     int rc = idb_denoiser_body(h, st);
@@ -178,7 +179,7 @@ static int predict_part(idb_handle* h, Sampler& s, const float* gt, const unsign
 static int correction_tail(idb_handle* h, Sampler& s, const float* gt, int i, cudaStream_t st) {
     int rc = idb_correction_apply_dev(h, s.x0, gt, i, st);
     if (rc) return rc;
-    return idb_step_finish(h, s.x0, s.x_a, reinterpret_cast<const float*>(s.tape_slot), 2, s.x_a, 1, st);
+    return idb_step_finish(h, s.x0, s.x_a, reinterpret_cast<const float*>(s.tape_slot), 2, s.x_a, 1, st, i);
 }
 static inline bool correction_gate(int correction, int i) { return correction && i <= 500 && (i % 50 == 0); }   // eval_smpl_short.py:86-88
 
@@ -239,7 +240,7 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
             rc = capture_graph(h, &s.loop_graph, &s.launches_per_loop, [&](cudaStream_t cs) {
                 int r = idb_denoiser_tokens(h, s.x_a, nullptr, cs);
                 for (int i = n - 1; i >= 0 && !r; i--) {
-                    if (!correction_gate(correction, i)) r = plain_step(h, s, g_gt, g_mask, cs);
+                    if (!correction_gate(correction, i)) r = plain_step(h, s, g_gt, g_mask, cs, i);
                     else { r = predict_part(h, s, g_gt, g_mask, cs); if (!r) r = correction_tail(h, s, g_gt, i, cs); }
                 }
                 return r;
@@ -260,7 +261,7 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
         if (s.step_graph) { cudaGraphExecDestroy(s.step_graph); s.step_graph = nullptr; }
         if (s.predict_graph) { cudaGraphExecDestroy(s.predict_graph); s.predict_graph = nullptr; }
         long long nl = 0;
-        if ((rc = capture_graph(h, &s.step_graph, &nl, [&](cudaStream_t cs) { return plain_step(h, s, g_gt, g_mask, cs); }))) return rc;
+        if ((rc = capture_graph(h, &s.step_graph, &nl, [&](cudaStream_t cs) { return plain_step(h, s, g_gt, g_mask, cs, -1); }))) return rc;
         s.launches_per_step = (int)nl;
         if ((rc = capture_graph(h, &s.predict_graph, &nl, [&](cudaStream_t cs) { return predict_part(h, s, g_gt, g_mask, cs); }))) return rc;
         s.launches_per_predict = (int)nl;
@@ -271,7 +272,7 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
             if (graph_ok) {
                 CUDA_TRY(h, cudaGraphLaunch(s.step_graph, st));
                 h->launches += s.launches_per_step;
-            } else if ((rc = plain_step(h, s, g_gt, g_mask, st))) return rc;
+            } else if ((rc = plain_step(h, s, g_gt, g_mask, st, i))) return rc;
         } else {
             if (graph_ok) {
                 CUDA_TRY(h, cudaGraphLaunch(s.predict_graph, st));

@@ -217,7 +217,7 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
             }
         }
         __syncwarp();
-        if (wait_dep) pdl_wait();
+        if (wait_dep) { pdl_wait(); if (lane == 0) chain_mark(2, 1); }
         if (elect_one()) {
             for (int kb = 0; kb < 2; kb++) {
                 const uint32_t dst = base + kb * STAGE1;

@@ -194,6 +194,48 @@ __device__ __forceinline__ float gelu_erf(float x) {
     const float hx = 0.5f * x;
     return fmaf(hx, erf_fast(x * 0.70710678118654752440f), hx);
 }
+// ---- packed fp32 pairs (fma / mul / add .f32x2, sm_100): the same IEEE operations as the scalar code, two per issue slot
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float a, float b) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// two elements of the feed-forward block's hidden layer: v = gelu_erf(fmaf(small, 2^-11, main) + bias), returned as the fp16
+// (hi, lo) words of split_f16x2(v0, v1).  Operation for operation the scalar gelu_erf / erf_fast / split_f16x2 (bit-identical),
+// with every fp32 multiply / add / fma issued as a packed pair: the phase is bound by the SM's instruction issue rate.
+__device__ __forceinline__ void gelu_split_x2(float m0, float m1, float s0, float s1, float2 bias, uint32_t& hi_w, uint32_t& lo_w) {
+    const f32x2_t x = add2(fma2(pk2(s0, s1), pk2(1.0f / 2048.0f, 1.0f / 2048.0f), pk2(m0, m1)), pk2(bias.x, bias.y));
+    const f32x2_t hx = mul2(x, pk2(0.5f, 0.5f));
+    const f32x2_t y = mul2(x, pk2(0.70710678118654752440f, 0.70710678118654752440f));
+    float y0, y1;
+    upk2(y, y0, y1);
+    const float t0 = fminf(fabsf(y0), 4.0f), t1 = fminf(fabsf(y1), 4.0f);
+    const f32x2_t t = pk2(t0, t1);
+    f32x2_t p = pk2(4.5338660129345953e-05f, 4.5338660129345953e-05f);
+    p = fma2(p, t, pk2(-0.0004454450972843915f, -0.0004454450972843915f));
+    p = fma2(p, t, pk2(0.0014896064531058073f, 0.0014896064531058073f));
+    p = fma2(p, t, pk2(0.0007736838888376951f, 0.0007736838888376951f));
+    p = fma2(p, t, pk2(-0.028252195566892624f, -0.028252195566892624f));
+    p = fma2(p, t, pk2(0.1484806090593338f, 0.1484806090593338f));
+    p = fma2(p, t, pk2(0.9184166789054871f, 0.9184166789054871f));
+    p = fma2(p, t, pk2(1.6279085874557495f, 1.6279085874557495f));
+    float a0, a1, e0, e1;
+    upk2(mul2(t, p), a0, a1);          // erf_fast evaluates (-t) * p: the sign moves into the MUFU operand
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-a1));
+    float r0, r1;
+    upk2(fma2(pk2(e0, e1), pk2(-1.0f, -1.0f), pk2(1.0f, 1.0f)), r0, r1);      // 1 - e (one rounding, like the scalar subtraction)
+    const f32x2_t v = fma2(hx, pk2(copysignf(r0, y0), copysignf(r1, y1)), hx);
+    float v0, v1;
+    upk2(v, v0, v1);
+    const __half2 hh = __floats2half2_rn(v0, v1);
+    const float2 f = __half22float2(hh);
+    float l0, l1;
+    upk2(mul2(fma2(pk2(f.x, f.y), pk2(-1.0f, -1.0f), v), pk2(2048.0f, 2048.0f)), l0, l1);      // (v - hi) * 2^11, v - hi exact
+    const __half2 ll = __floats2half2_rn(l0, l1);
+    hi_w = *reinterpret_cast<const uint32_t*>(&hh); lo_w = *reinterpret_cast<const uint32_t*>(&ll);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
 // Programmatic dependent launch: every kernel of the sampling step releases its successor at once

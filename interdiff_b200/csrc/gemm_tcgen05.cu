@@ -81,6 +81,7 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int kb0 = blockIdx.z * per_kb;
     const int num_kb = min(per_kb, total_kb - kb0);
 
+    const int npre = num_kb < cfg::STAGES ? num_kb : cfg::STAGES;
     if (threadIdx.x == 0) {
         for (int s = 0; s < cfg::STAGES; s++) {
             mbar_init(bar_full(s), 1);
@@ -88,10 +89,30 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
+        if (!MC) {
+            // The first pipeline fill is requested right here, by the thread that initialised the barriers, before the TMEM
+            // allocation and the CTA barrier: the weight tiles (they do not depend on the previous kernel) at once, the
+            // activation tiles after the dependency wait.  A CTA that only got its SM when the previous kernel's CTAs left has
+            // nothing to overlap its prologue with, so the sooner the first bytes are on their way the better.
+            for (int kb = 0; kb < npre; kb++) {
+                const uint32_t dst = base + kb * cfg::STAGE_BYTES;
+                mbar_arrive_expect_tx(bar_full(kb), cfg::STAGE_BYTES);
+                tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(kb), (kb0 + kb) * BK, n0);
+                tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(kb), (kb0 + kb) * BK, n0);
+            }
+            pdl_wait();
+            chain_mark(1, 1);
+            for (int kb = 0; kb < npre; kb++) {
+                const uint32_t dst = base + kb * cfg::STAGE_BYTES;
+                tma_load_2d(dst, &map_a, bar_full(kb), (kb0 + kb) * BK, m0);
+                tma_load_2d(dst + cfg::HALF_BYTES, &map_al, bar_full(kb), (kb0 + kb) * BK, m0);
+            }
+        } else {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)cfg::TMEM_COLS) : "memory");
@@ -111,33 +132,29 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        // The weight tiles of the first pipeline fill do not depend on the previous kernel: they are
-        // requested before the dependency wait (programmatic dependent launch), the activation tiles after.
-        const int npre = num_kb < cfg::STAGES ? num_kb : cfg::STAGES;
-        if (elect_one()) {
-            for (int kb = 0; kb < npre; kb++) {
-                const uint32_t dst = base + kb * cfg::STAGE_BYTES;
-                mbar_arrive_expect_tx(bar_full(kb), cfg::STAGE_BYTES);
-                if (MC) {
+        // (multicast pairs only; otherwise the first fill was requested by thread 0 above)  The weight tiles of the first
+        // pipeline fill do not depend on the previous kernel: requested before the dependency wait, the activation tiles after.
+        if (MC) {
+            if (elect_one()) {
+                for (int kb = 0; kb < npre; kb++) {
+                    const uint32_t dst = base + kb * cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(bar_full(kb), cfg::STAGE_BYTES);
                     tma_load_2d_mc(dst + cfg::A_BYTES + crank * WH, &map_w, bar_full(kb), (kb0 + kb) * BK, n0 + crank * (BN / 2), 3);
                     tma_load_2d_mc(dst + cfg::HALF_BYTES + cfg::A_BYTES + crank * WH, &map_wl, bar_full(kb), (kb0 + kb) * BK, n0 + crank * (BN / 2), 3);
-                } else {
-                    tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(kb), (kb0 + kb) * BK, n0);
-                    tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(kb), (kb0 + kb) * BK, n0);
                 }
             }
-        }
-        __syncwarp();
-        pdl_wait();
-        if (lane == 0) chain_mark(1, 1);
-        if (elect_one()) {
-            for (int kb = 0; kb < npre; kb++) {
-                const uint32_t dst = base + kb * cfg::STAGE_BYTES;
-                tma_load_2d(dst, &map_a, bar_full(kb), (kb0 + kb) * BK, m0);
-                tma_load_2d(dst + cfg::HALF_BYTES, &map_al, bar_full(kb), (kb0 + kb) * BK, m0);
+            __syncwarp();
+            pdl_wait();
+            if (lane == 0) chain_mark(1, 1);
+            if (elect_one()) {
+                for (int kb = 0; kb < npre; kb++) {
+                    const uint32_t dst = base + kb * cfg::STAGE_BYTES;
+                    tma_load_2d(dst, &map_a, bar_full(kb), (kb0 + kb) * BK, m0);
+                    tma_load_2d(dst + cfg::HALF_BYTES, &map_al, bar_full(kb), (kb0 + kb) * BK, m0);
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
         if (lane == 0) TRACE(2);
         for (int kb = npre; kb < num_kb; kb++) {
             const int s = kb % cfg::STAGES, round = kb / cfg::STAGES;
@@ -326,8 +343,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     MlpArgs a{&map_x, &map_w1, &map_xl, &map_w1l, &map_w2, &map_w2l, b1, b2, res, ldr, Z, ldz, ln_w, ln_b, Zh, Zl, trace};
-    const uint32_t tmem_base = mlp_setup<MLP_EW>(smem_raw, a);
-    mlp_run<MLP_EW>(smem_raw, a, blockIdx.x, blockIdx.y * BM, M, tmem_base, true, tr);
+    const uint32_t tmem_base = mlp_setup<MLP_EW, true>(smem_raw, a, blockIdx.x, blockIdx.y * BM);
+    mlp_run<MLP_EW, true>(smem_raw, a, blockIdx.x, blockIdx.y * BM, M, tmem_base, true, tr);
     if (threadIdx.x == 0) chain_mark(2, 2);
     mlp_teardown(tmem_base);
 }

@@ -101,8 +101,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 //
 // Shared memory (192 KB): ring = 2 x 64 KB stages (GEMM 1 operands, then the two W2 k-blocks, then
 // - together with the S region - the fp32 partial tile); S = 64 KB (hi | lo, 2 k-blocks of 64).
-// TMEM (512 columns): GEMM 1 main [0,128) + small [128,256); GEMM 2 main [256,512) + small [0,256)
-// (GEMM 1's accumulators are dead once S is written).
+// TMEM (512 columns): GEMM 1 main [256,384) + small [384,512); GEMM 2 small [0,256) + main [256,512): GEMM 2's small
+// products of the first k-block (they only touch [0,256)) are issued while the epilogue warps still turn GEMM 1's
+// accumulators into the SECOND k-block of S; its main products wait until those accumulators are dead.
 namespace mlp {
 constexpr int FC = 128;                       // hidden columns per CTA
 constexpr int CLUSTER = 8;                    // d_ff / FC
@@ -126,6 +127,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&u)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 16 columns of this warp's 32 TMEM lanes, no wait (pair with tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&u)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -140,26 +151,47 @@ struct MlpArgs {
     long long* trace;
 };
 
-// Barriers, tensor-map prefetch and the TMEM allocation of the feed-forward block; ends with a CTA barrier.  The barrier
+// Barriers and the TMEM allocation of the feed-forward block; ends with a CTA barrier.  The barrier
 // words live ABOVE the 192 KB operand region, so a caller may use that region for something else until mlp_run starts.
-template <int EW>      // EW = number of epilogue warps of mlp_run<EW>: 8 or 16
-__device__ __forceinline__ uint32_t mlp_setup(uint8_t* smem_raw, const MlpArgs& a) {
+// EARLY (stand-alone kernel: the operand region is free from the start): the thread that initialises the barriers also
+// requests the first two k-blocks of operands at once - W1 (step-invariant), then, after the dependency wait, X - instead of
+// leaving that to the producer warp after the TMEM allocation and the CTA barrier.  Most CTAs of a launch only get their SM
+// when the previous kernel's CTAs leave (every kernel of the step fills the SMs' shared memory), so for them nothing overlaps
+// the prologue and these ~700 cycles are on the step's critical path.  mlp_run<EW, true> then skips those requests.
+template <int EW, bool EARLY = false>      // EW = number of epilogue warps of mlp_run<EW>: 8 or 16
+__device__ __forceinline__ uint32_t mlp_setup(uint8_t* smem_raw, const MlpArgs& a, int j = 0, int m0 = 0) {
     using namespace mlp;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bars = base + RING + S_BYTES;
-    const uint32_t tmem_slot = bars + 8u * 9;
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + RING + S_BYTES + 8 * 9);
+    const uint32_t tmem_slot = bars + 8u * 10;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + RING + S_BYTES + 8 * 10);
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (2 + s), 1); mbar_init(bars + 8u * (5 + s), 1); }
         mbar_init(bars + 8u * 4, 1); mbar_init(bars + 8u * 8, 1);
-        mbar_init(bars + 8u * 7, EW * 32);
+        mbar_init(bars + 8u * 7, EW * 32); mbar_init(bars + 8u * 9, EW * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_x) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_w1) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_xl) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_w1l) : "memory");
+        if (EARLY) {
+            for (int kb = 0; kb < 2; kb++) {
+                const uint32_t dst = base + kb * STAGE1;
+                mbar_arrive_expect_tx(bars + 8u * kb, STAGE1);
+                tma_load_2d(dst + 16384, a.map_w1, bars + 8u * kb, kb * BK, j * FC);
+                tma_load_2d(dst + 49152, a.map_w1l, bars + 8u * kb, kb * BK, j * FC);
+            }
+            pdl_wait();
+            chain_mark(2, 1);
+            for (int kb = 0; kb < 2; kb++) {
+                const uint32_t dst = base + kb * STAGE1;
+                tma_load_2d(dst, a.map_x, bars + 8u * kb, kb * BK, m0);
+                tma_load_2d(dst + 32768, a.map_xl, bars + 8u * kb, kb * BK, m0);
+            }
+        } else {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_x) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_w1) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_xl) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_w1l) : "memory");
+        }
         asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_w2) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_w2l) : "memory");
     }
@@ -178,7 +210,7 @@ __device__ __forceinline__ uint32_t mlp_setup(uint8_t* smem_raw, const MlpArgs& 
 // fewer than 128 live rows when the caller aligns tiles to samples).  Warps 0 / 1 = TMA producer / MMA issuer, warps 2..9 =
 // epilogue; any further warps of the CTA only take part in the cluster barriers.  wait_dep: execute griddepcontrol.wait
 // before the first dependent access (stand-alone launch); a caller that has already waited passes false.
-template <int EW>
+template <int EW, bool EARLY = false>
 __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int j, int m0, int row_end, uint32_t tmem_base, bool wait_dep,
                                         long long* tr) {
     using namespace mlp;
@@ -197,35 +229,38 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t s_base = base + RING;
     const uint32_t bars = base + RING + S_BYTES;
-    // barriers: full1[2], empty1[2], acc1, full2[2], s_ready, acc2, then the tmem slot
+    // barriers: full1[2], empty1[2], acc1, full2[2], s_ready[0], acc2, s_ready[1], then the tmem slot
     auto bar_full1 = [&](int s) { return bars + 8u * s; };
     auto bar_empty1 = [&](int s) { return bars + 8u * (2 + s); };
     const uint32_t bar_acc1 = bars + 8u * 4;
     auto bar_full2 = [&](int s) { return bars + 8u * (5 + s); };
-    const uint32_t bar_sready = bars + 8u * 7, bar_acc2 = bars + 8u * 8;
+    auto bar_sready = [&](int kb) { return bars + 8u * (kb ? 9 : 7); };
+    const uint32_t bar_acc2 = bars + 8u * 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) MTRACE(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (elect_one()) {
-            for (int kb = 0; kb < 2; kb++) {       // weight tiles do not depend on the previous kernel
-                const uint32_t dst = base + kb * STAGE1;
-                mbar_arrive_expect_tx(bar_full1(kb), STAGE1);
-                tma_load_2d(dst + 16384, &map_w1, bar_full1(kb), kb * BK, j * FC);
-                tma_load_2d(dst + 49152, &map_w1l, bar_full1(kb), kb * BK, j * FC);
+        if (!EARLY) {      // (EARLY: mlp_setup has already requested the first two k-blocks)
+            if (elect_one()) {
+                for (int kb = 0; kb < 2; kb++) {       // weight tiles do not depend on the previous kernel
+                    const uint32_t dst = base + kb * STAGE1;
+                    mbar_arrive_expect_tx(bar_full1(kb), STAGE1);
+                    tma_load_2d(dst + 16384, &map_w1, bar_full1(kb), kb * BK, j * FC);
+                    tma_load_2d(dst + 49152, &map_w1l, bar_full1(kb), kb * BK, j * FC);
+                }
             }
-        }
-        __syncwarp();
-        if (wait_dep) { pdl_wait(); if (lane == 0) chain_mark(2, 1); }
-        if (elect_one()) {
-            for (int kb = 0; kb < 2; kb++) {
-                const uint32_t dst = base + kb * STAGE1;
-                tma_load_2d(dst, &map_x, bar_full1(kb), kb * BK, m0);
-                tma_load_2d(dst + 32768, &map_xl, bar_full1(kb), kb * BK, m0);
+            __syncwarp();
+            if (wait_dep) { pdl_wait(); if (lane == 0) chain_mark(2, 1); }
+            if (elect_one()) {
+                for (int kb = 0; kb < 2; kb++) {
+                    const uint32_t dst = base + kb * STAGE1;
+                    tma_load_2d(dst, &map_x, bar_full1(kb), kb * BK, m0);
+                    tma_load_2d(dst + 32768, &map_xl, bar_full1(kb), kb * BK, m0);
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
         for (int kb = 2; kb < 4; kb++) {
             const int s = kb & 1;
             mbar_wait(bar_empty1(s), 0);
@@ -255,7 +290,7 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
         // ===================== MMA issuer =====================
         const uint32_t idesc1 = (1u << 4) | ((uint32_t)(FC >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         const uint32_t idesc2 = (1u << 4) | ((uint32_t)(DM >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        const uint32_t acc1_main = tmem_base, acc1_small = tmem_base + 128u;
+        const uint32_t acc1_main = tmem_base + 256u, acc1_small = tmem_base + 384u;
         for (int kb = 0; kb < 4; kb++) {
             const int s = kb & 1;
             mbar_wait(bar_full1(s), (kb >> 1) & 1);
@@ -278,28 +313,50 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
             __syncwarp();
         }
         if (lane == 0) MTRACE(3);
-        // GEMM 2: A = S (written by the epilogue warps), B = W2 k-blocks in the ring
-        mbar_wait(bar_sready, 0);
+        // GEMM 2: A = S (written by the epilogue warps, one k-block of 64 hidden columns at a time), B = W2 k-blocks in the
+        // ring.  Issue order: k-block 0's small products (they accumulate in [0,256), free) as soon as S's first k-block is
+        // ready - the epilogue warps are still reading GEMM 1's accumulators for the second one -, then, once those
+        // accumulators are dead, k-block 0's main products and all of k-block 1.  Per accumulator the order of the
+        // additions is unchanged (k ascending).
+        const uint32_t acc2_main = tmem_base + 256u, acc2_small = tmem_base;
+        uint64_t dah[2], dal[2], dwh[2], dwl[2];
+#pragma unroll
+        for (int kb = 0; kb < 2; kb++) {
+            dah[kb] = make_smem_desc(s_base + kb * 16384); dal[kb] = make_smem_desc(s_base + 32768 + kb * 16384);
+            dwh[kb] = make_smem_desc(base + kb * STAGE1); dwl[kb] = make_smem_desc(base + kb * STAGE1 + 32768);
+        }
+        mbar_wait(bar_sready(0), 0);
+        mbar_wait(bar_full2(0), 0);
         tc_fence_after();
         if (lane == 0) MTRACE(6);
-        const uint32_t acc2_main = tmem_base + 256u, acc2_small = tmem_base;
-        for (int kb = 0; kb < 2; kb++) {
-            mbar_wait(bar_full2(kb), 0);
-            tc_fence_after();
-            const uint64_t dah = make_smem_desc(s_base + kb * 16384), dal = make_smem_desc(s_base + 32768 + kb * 16384);
-            const uint64_t dwh = make_smem_desc(base + kb * STAGE1), dwl = make_smem_desc(base + kb * STAGE1 + 32768);
-            if (elect_one()) {
+        if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < BK / UMMA_K; kk++) {
-                    const uint64_t koff = (uint64_t)((kk * UMMA_K * 2) >> 4);
-                    umma_f16(acc2_small, dal + koff, dwh + koff, idesc2, (kb | kk) ? 1u : 0u);
-                    umma_f16(acc2_small, dah + koff, dwl + koff, idesc2, 1u);
-                    umma_f16(acc2_main, dah + koff, dwh + koff, idesc2, (kb | kk) ? 1u : 0u);
-                }
-                if (kb == 1) umma_commit(bar_acc2);
+            for (int kk = 0; kk < BK / UMMA_K; kk++) {
+                const uint64_t koff = (uint64_t)((kk * UMMA_K * 2) >> 4);
+                umma_f16(acc2_small, dal[0] + koff, dwh[0] + koff, idesc2, kk ? 1u : 0u);
+                umma_f16(acc2_small, dah[0] + koff, dwl[0] + koff, idesc2, 1u);
             }
-            __syncwarp();
         }
+        __syncwarp();
+        mbar_wait(bar_sready(1), 0);
+        mbar_wait(bar_full2(1), 0);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < BK / UMMA_K; kk++) {
+                const uint64_t koff = (uint64_t)((kk * UMMA_K * 2) >> 4);
+                umma_f16(acc2_main, dah[0] + koff, dwh[0] + koff, idesc2, kk ? 1u : 0u);
+            }
+#pragma unroll
+            for (int kk = 0; kk < BK / UMMA_K; kk++) {
+                const uint64_t koff = (uint64_t)((kk * UMMA_K * 2) >> 4);
+                umma_f16(acc2_small, dal[1] + koff, dwh[1] + koff, idesc2, 1u);
+                umma_f16(acc2_small, dah[1] + koff, dwl[1] + koff, idesc2, 1u);
+                umma_f16(acc2_main, dah[1] + koff, dwh[1] + koff, idesc2, 1u);
+            }
+            umma_commit(bar_acc2);
+        }
+        __syncwarp();
         if (lane == 0) MTRACE(7);
     } else if (warp < 2 + EW) {
         // ===================== epilogue warps 2..9 =====================
@@ -309,37 +366,40 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
         mbar_wait(bar_acc1, 0);
         tc_fence_after();
         if (threadIdx.x == 64) MTRACE(4);
-        // ---- hidden chunk: bias + GELU -> (hi, lo) fp16 pairs in the swizzled K-major A layout
+        // ---- hidden chunk: bias + GELU -> (hi, lo) fp16 pairs in the swizzled K-major A layout, one k-block of S (64 hidden
+        // columns) at a time on ALL epilogue warps, so that GEMM 2 can start on the first while the second is produced
+        constexpr int CW = 64 / WPQ;                  // columns per warp and k-block: 16 (16 warps) or 32 (8 warps)
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-        for (int c0 = (ew >> 2) * 32; c0 < FC; c0 += 32 * WPQ) {
-            uint32_t um[32], us[32];
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-            tmem_ld32(trow + (uint32_t)c0, um);
-            tmem_ld32(trow + (uint32_t)(128 + c0), us);
-            const int kb = c0 >> 6, ch0 = (c0 & 63) >> 3;
+        for (int kb = 0; kb < 2; kb++) {
             uint8_t* srow_hi = base_ptr + RING + kb * 16384 + r * 128;
             uint8_t* srow_lo = srow_hi + 32768;
+#pragma unroll 1
+            for (int cc = (ew >> 2) * CW; cc < (ew >> 2) * CW + CW; cc += 16) {
+                const int c0 = kb * 64 + cc;
+                uint32_t um[16], us[16];
+                tmem_ld16_nowait(trow + (uint32_t)(256 + c0), um);
+                tmem_ld16_nowait(trow + (uint32_t)(384 + c0), us);
+                tmem_ld_wait();
 #pragma unroll
-            for (int ch = 0; ch < 4; ch++) {
-                uint32_t hw[4], lw[4];
+                for (int ch = 0; ch < 2; ch++) {
+                    uint32_t hw[4], lw[4];
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int i0 = ch * 8 + e * 2;
-                    const float2 bb = *reinterpret_cast<const float2*>(b1 + j * FC + c0 + i0);
-                    const float v0 = gelu_erf(fmaf(__uint_as_float(us[i0]), 1.0f / 2048.0f, __uint_as_float(um[i0])) + bb.x);
-                    const float v1 = gelu_erf(fmaf(__uint_as_float(us[i0 + 1]), 1.0f / 2048.0f, __uint_as_float(um[i0 + 1])) + bb.y);
-                    __half2 hh, ll;
-                    split_f16x2(v0, v1, hh, ll);
-                    hw[e] = *reinterpret_cast<uint32_t*>(&hh); lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+                    for (int e = 0; e < 4; e++) {
+                        const int i0 = ch * 8 + e * 2;
+                        const float2 bb = *reinterpret_cast<const float2*>(b1 + j * FC + c0 + i0);
+                        gelu_split_x2(__uint_as_float(um[i0]), __uint_as_float(um[i0 + 1]), __uint_as_float(us[i0]), __uint_as_float(us[i0 + 1]),
+                                      bb, hw[e], lw[e]);
+                    }
+                    const int pos = (((cc >> 3) + ch) ^ (r & 7)) * 16;
+                    *reinterpret_cast<uint4*>(srow_hi + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(srow_lo + pos) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
-                const int pos = ((ch0 + ch) ^ (r & 7)) * 16;
-                *reinterpret_cast<uint4*>(srow_hi + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4*>(srow_lo + pos) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
+            tc_fence_before();                                             // our TMEM reads precede GEMM 2's writes to those columns
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy S writes -> visible to the tensor core
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_sready(kb)) : "memory");
         }
-        tc_fence_before();                                             // our TMEM reads precede GEMM 2's writes to those columns
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy S writes -> visible to the tensor core
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_sready) : "memory");
         if (threadIdx.x == 64) MTRACE(5);
     }
     // ===================== cross-CTA reduction over distributed shared memory =====================

@@ -82,7 +82,7 @@ per_step = len(launches) // steps
 print("%d launches, %d per step; globaltimer resolution ~%d ns" % (len(launches), per_step, int(np.min(np.diff(np.unique(t))))))
 # average the middle steps position by position
 use = range(2, steps - 1)
-print("%-3s %-16s %6s | %9s %9s %9s | %9s %9s" % ("#", "kernel", "grid", "chain us", "handoff", "in-kernel", "early us", "exit spr"))
+print("%-3s %-16s %6s | %9s %9s %9s | %9s %9s %9s" % ("#", "kernel", "grid", "chain us", "handoff", "in-kernel", "early us", "last in", "exit spr"))
 tot = 0.0
 agg = {}
 for pos in range(per_step):
@@ -94,10 +94,12 @@ for pos in range(per_step):
         hand = (d["wait_min"] - p["exit_max"]) if d["wait_min"] is not None else float("nan")
         inker = (d["exit_max"] - d["wait_min"]) if d["wait_min"] is not None else float("nan")
         early = p["exit_max"] - d["entry_min"]          # how long before the predecessor's end the first block was resident
-        rows.append((chain, hand, inker, early, d["exit_max"] - d["exit_min"]))
+        # "last in": when the launch's LAST block entered, relative to the predecessor's last exit (blocks that only get an SM
+        # when the predecessor's blocks leave it)
+        rows.append((chain, hand, inker, early, d["entry_max"] - p["exit_max"], d["exit_max"] - d["exit_min"]))
     m = np.nanmean(np.array(rows, dtype=np.float64), axis=0) / 1e3
     d = launches[2 * per_step + pos]
-    print("%-3d %-16s %6d | %9.2f %9.2f %9.2f | %9.2f %9.2f" % (pos, NAMES.get(d["kind"], "?"), d["grid"], m[0], m[1], m[2], m[3], m[4]))
+    print("%-3d %-16s %6d | %9.2f %9.2f %9.2f | %9.2f %9.2f %9.2f" % (pos, NAMES.get(d["kind"], "?"), d["grid"], m[0], m[1], m[2], m[3], m[4], m[5]))
     tot += m[0]
     a = agg.setdefault((NAMES.get(d["kind"], "?"), d["grid"]), [0, 0.0, 0.0, 0.0])
     a[0] += 1; a[1] += m[0]; a[2] += m[1]; a[3] += m[2]

@@ -17,7 +17,7 @@ tr = torch.zeros(256, 16, dtype=torch.int64, device="cuda")
 eng.mlp(x, w1, b1, w2, b2, res, iters=3)
 eng.mlp(x, w1, b1, w2, b2, res, iters=201, trace=tr)
 print("fused feed-forward, M=%d: %.2f us/launch" % (M, eng.last_ms() * 1e3))
-names = ["entry", "setup done", "mma: first operands landed", "mma: GEMM1 issued", "epi: acc1 ready", "epi: S written", "mma: S ready",
+names = ["entry", "setup done", "mma: first operands landed", "mma: GEMM1 issued", "epi: acc1 ready", "epi: S written", "mma: S k-block 0 ready",
          "mma: GEMM2 issued", "epi: acc2 ready", "epi: partial in smem", "cluster sync 1", "reduction stored", "cluster sync 2"]
 t = tr.cpu()[:120]
 for i, n in enumerate(names):

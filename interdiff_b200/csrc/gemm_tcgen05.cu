@@ -494,8 +494,9 @@ int idb_mlp_make_maps(idb_handle* h, const __half* x_hi, const __half* x_lo, con
     if ((rc = make_map(h, &out6[1], w1_hi, F, mlp::DM, mlp::DM, mlp::FC))) return rc;
     if ((rc = make_map(h, &out6[2], x_lo, M, mlp::DM, mlp::DM, BM))) return rc;
     if ((rc = make_map(h, &out6[3], w1_lo, F, mlp::DM, mlp::DM, mlp::FC))) return rc;
-    if ((rc = make_map(h, &out6[4], w2_hi, mlp::DM, F, F, mlp::DM))) return rc;
-    return make_map(h, &out6[5], w2_lo, mlp::DM, F, F, mlp::DM);
+    // W2: boxes of 128 rows (one CTA's half of the output columns) x 64 hidden columns
+    if ((rc = make_map(h, &out6[4], w2_hi, mlp::DM, F, F, mlp::NH))) return rc;
+    return make_map(h, &out6[5], w2_lo, mlp::DM, F, F, mlp::NH);
 }
 
 int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const __half* w1_hi, const __half* w1_lo, const float* b1,
@@ -514,8 +515,8 @@ int idb_mlp_tcgen05(idb_handle* h, const __half* x_hi, const __half* x_lo, const
     if ((rc = make_map(h, &mxl, x_lo, M, mlp::DM, mlp::DM, BM))) return rc;
     if ((rc = make_map(h, &mw1, w1_hi, F, mlp::DM, mlp::DM, mlp::FC))) return rc;
     if ((rc = make_map(h, &mw1l, w1_lo, F, mlp::DM, mlp::DM, mlp::FC))) return rc;
-    if ((rc = make_map(h, &mw2, w2_hi, mlp::DM, F, F, mlp::DM))) return rc;
-    if ((rc = make_map(h, &mw2l, w2_lo, mlp::DM, F, F, mlp::DM))) return rc;
+    if ((rc = make_map(h, &mw2, w2_hi, mlp::DM, F, F, mlp::NH))) return rc;
+    if ((rc = make_map(h, &mw2l, w2_lo, mlp::DM, F, F, mlp::NH))) return rc;
     dim3 grid(mlp::CLUSTER, (M + BM - 1) / BM);
     idb_launch(pdl != 0, mlp_fused_kernel, grid, MLP_THREADS, mlp::SMEM_BYTES, st, mx, mw1, mxl, mw1l, mw2, mw2l, b1, b2, res, ldr, Z, ldz, M, ln_w, ln_b, Z_hi, Z_lo, trace);
     LAUNCH_CHECK(h);

@@ -611,7 +611,9 @@ def test_rollout_next_window_and_driver(eng, smplh_np):
         bodies.append(w[0 if k == 0 else P:])
         offset = offset + c
         cur = nxt.cuda()
-    assert rel(traj["body"], torch.cat(bodies)) < 1e-5
+    # two compositions of the same chain whose window steps differ at rounding level (device vs host get_batch, 1e-6 above);
+    # three windows of a free-running sampler amplify that, hence 1e-4 and not 1e-6
+    assert rel(traj["body"], torch.cat(bodies)) < 1e-4
     # continuity: the inpainted past of window k+1 (frames [P + k F - P .. ) in world coordinates) IS the end of window k
     assert torch.isfinite(traj["pelvis"]).all()
 

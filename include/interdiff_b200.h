@@ -34,7 +34,9 @@ int idb_set_gemm_backend(idb_handle* h, int backend); /* 0 = fp32 SIMT (debug/bi
    either way; 0 serialises the kernels (for bisecting / profiling). */
 int idb_set_dependent_launch(idb_handle* h, int on);
 /* Feed-forward block of a decoder layer as one cluster kernel (tensor backend, d_model 256, d_ff 1024): 2 (default) = incl.
-   the layer's final LayerNorm in its reduction epilogue, 1 = feed-forward only, 0 = the two separate GEMMs (bisecting). */
+   the layer's final LayerNorm in its reduction epilogue, 1 = feed-forward only, 0 = the two separate GEMMs (bisecting);
+   3 = a layer's attention half in the same kernel (option, not faster).  10 / 11: self- and cross-attention of the standard
+   layers as two launches / one launch (default 11; identical results). */
 int idb_set_fused_mlp(idb_handle* h, int on);
 /* Cluster-pruned nearest-neighbour search when the target is the loaded body mesh (default 1; results are identical
    to the brute-force scan, index ties included); 0 = always brute force. */

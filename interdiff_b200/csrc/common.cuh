@@ -113,6 +113,7 @@ struct idb_handle {
     double last_ms = 0.0;     // mean launch time of the last timed debug hook
     int gemm_multicast = 1;   // long wide GEMMs (SMPL-H blend): row-tile pairs share the W tile by TMA multicast (idb_debug_set_gemm_multicast)
     int nn_pruning = 1;       // cluster-pruned nearest-neighbour search for body-mesh targets (identical results)
+    int fuse_attn = 1;        // standard decoder layers: self-attention + cross-attention in one launch (idb_set_fused_mlp(h, 10 / 11) = off / on)
     int fused_mlp = 2;        // feed-forward block as ONE cluster kernel (tensor backend, d_model 256, d_ff 1024); 2 = incl. the layer's final norm;
                               // 3 = a layer's attention half runs in the same kernel on sample-aligned tiles (one launch per layer):
                               // measured NOT faster (288.6 vs 282.3 us per step at B=60: programmatic dependent launch already hides the

@@ -629,6 +629,24 @@ k_xattn_ln(const XattnArgs xa) {
     if (c_chain) { __syncthreads(); if (threadIdx.x == 0) chain_mark(5, 2); }
 }
 
+// Standard decoder layer, attention half in ONE launch: self-attention + LN1 (attn_body) and - on the rows this CTA has just
+// written - cross-attention + LN2 (xattn_body), on the same shared memory one after the other.  Saves the kernel boundary
+// between the two (hand-off, CTA launch, a second prologue: ~3 us of a step's critical path per layer).
+__global__ void __launch_bounds__(ANT)
+k_attn_xattn_ln(const AttnArgs aa, const XattnArgs xa) {
+    extern __shared__ __align__(16) float sm[];
+    if (threadIdx.x == 0) chain_mark(4, 0);
+    attn_body(aa, sm, blockIdx.x, blockIdx.y * SLAB);
+    __syncthreads();                 // every warp's LN1 rows are in global memory (this CTA reads them back below)
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr(sm)) : "memory");
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr(sm) + 8u) : "memory");
+    }
+    __syncthreads();
+    xattn_body(xa, sm, blockIdx.x, blockIdx.y * SLAB, true);
+    if (c_chain) { __syncthreads(); if (threadIdx.x == 0) chain_mark(4, 2); }
+}
+
 // QaN block + residual + LayerNorm1 (model/sublayers.py:343-352 + :332) for a slab of <= 16 rows of
 // one sample, with an optional LayerNorm applied to the input rows first (the previous layer's
 // pending norm3).   grid (B, ceil(T/16)), block 512.
@@ -1637,11 +1655,18 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
                 LAUNCH_CHECK(h);
                 continue;
             }
-            idb_launch(pdl, k_attn_ln, slab_grid, ANT, attn_smem(T, H), st, aa);
-            LAUNCH_CHECK(h);
-            // cross attention on the LN1 rows (d.qc) -> (d.h2, pairs)
-            idb_launch(pdl, k_xattn_ln, slab_grid, ANT, xattn_smem(Tm, H), st, xa);
-            LAUNCH_CHECK(h);
+            if (h->fuse_attn) {
+                // self-attention + LN1 and cross-attention + LN2 in one launch: h -> (d.qc) -> (d.h2, pairs)
+                const size_t smem = attn_smem(T, H) > xattn_smem(Tm, H) ? attn_smem(T, H) : xattn_smem(Tm, H);
+                idb_launch(pdl, k_attn_xattn_ln, slab_grid, ANT, smem, st, aa, xa);
+                LAUNCH_CHECK(h);
+            } else {
+                idb_launch(pdl, k_attn_ln, slab_grid, ANT, attn_smem(T, H), st, aa);
+                LAUNCH_CHECK(h);
+                // cross attention on the LN1 rows (d.qc) -> (d.h2, pairs)
+                idb_launch(pdl, k_xattn_ln, slab_grid, ANT, xattn_smem(Tm, H), st, xa);
+                LAUNCH_CHECK(h);
+            }
         }
         // ---- feed forward on x2 = d.h2: ff = gelu(x2 W1^T + b1) kept as pairs only; z = ff W2^T + b2 + x2  (pre-norm3)
         if (fused) {
@@ -1767,6 +1792,8 @@ int idb_denoiser_prepare_kernels(idb_handle* h) {
     CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_enc_smem()));
     CUDA_TRY(h, cudaFuncSetAttribute(k_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_smem(16, 4)));
     CUDA_TRY(h, cudaFuncSetAttribute(k_attn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(36, 4)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_attn_xattn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(attn_smem(36, 4) > xattn_smem(16, 4) ? attn_smem(36, 4) : xattn_smem(16, 4))));
     return IDB_OK;
 }
 

@@ -439,6 +439,30 @@ def test_fused_feed_forward_with_final_norm(eng, M):
             assert torch.equal(o[2], o[3]), (B2, T2)
 
 
+def test_launch_structure_switches_bit_identical(eng):
+    """The launch-structure options of the step compute every row with the same arithmetic: self- + cross-attention of the
+    standard layers as one launch vs two (idb_set_fused_mlp 11 / 10), 192- vs 256-column tiles of the folded QKV projection
+    (idb_debug_set_gemm_accumulators 901 / 900: same single accumulator and k order per element)."""
+    sd = mdm_weights("smpl", "auto")
+    eng.load_denoiser(sd, "smpl")
+    for B2, T2 in ((64, 30), (5, 35), (9, 16)):
+        b = S.make_smpl_batch(B=B2, T=T2)
+        eng.bind(b["cond"], T2)
+        x = torch.from_numpy(S.noise_tape(b["gt"].shape, 0)[0]).cuda()
+        t = torch.randint(0, 1000, (B2,), generator=torch.Generator().manual_seed(B2)).cuda()
+        base = eng.forward(x, t).clone()
+        eng.set_fused_mlp(10)
+        two = eng.forward(x, t).clone()
+        eng.set_fused_mlp(11)
+        eng.lib.idb_debug_set_gemm_accumulators(900)
+        eng.set_fused_mlp(2)          # (drops the captured graphs)
+        wide = eng.forward(x, t).clone()
+        eng.lib.idb_debug_set_gemm_accumulators(901)
+        eng.set_fused_mlp(2)
+        assert torch.equal(base, two), (B2, T2)
+        assert torch.equal(base, wide), (B2, T2)
+
+
 def test_rotation_conversions_targeted(eng):
     """A11: the 6D -> axis-angle chain (rotation_6d_to_matrix -> matrix_to_quaternion's 4-candidate argmax -> axis-angle with the
     small-angle series) on the cases random inputs do not reach: rotations within 1e-3 .. 1e-6 of pi (where the argmax

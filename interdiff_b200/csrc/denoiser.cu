@@ -1119,9 +1119,10 @@ __global__ void __launch_bounds__(256) k_step_io(const StepIO a) {
             }
         }
     }
-    if ((MODE & 2) && a.emit_next) {
-        // every thread of this block has read step_cur (before the first barrier-free use above it sits in a
-        // register); the last block to get here moves the counter
+    if ((MODE & 2) && a.emit_next && !early) {
+        // (only when the step index comes from the device counter: with a host-known index nobody reads the counter until the
+        // next loop's k_loop_begin sets it)  every thread of this block has read step_cur (before the first barrier-free use
+        // above it sits in a register); the last block to get here moves the counter
         __syncthreads();
         if (tid == 0) {
             const int done = atomicAdd(a.ticket, 1);

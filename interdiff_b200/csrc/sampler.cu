@@ -176,10 +176,12 @@ static int predict_part(idb_handle* h, Sampler& s, const float* gt, const unsign
 }
 // reference order inside p_mean_variance (gaussian_diffusion.py:305-376): model -> inpaint blend -> denoised_fn ->
 // posterior; there is NO re-inpainting after the hook.  The hook receives the UN-mapped step index i (:356).
-static int correction_tail(idb_handle* h, Sampler& s, const float* gt, int i, cudaStream_t st) {
+// i_host: i when every step of the loop is enqueued with its index (plain launches, whole-loop graph), -1 when the other steps
+// replay a captured graph that reads - and therefore needs this step to move - the device counter
+static int correction_tail(idb_handle* h, Sampler& s, const float* gt, int i, cudaStream_t st, int i_host) {
     int rc = idb_correction_apply_dev(h, s.x0, gt, i, st);
     if (rc) return rc;
-    return idb_step_finish(h, s.x0, s.x_a, reinterpret_cast<const float*>(s.tape_slot), 2, s.x_a, 1, st, i);
+    return idb_step_finish(h, s.x0, s.x_a, reinterpret_cast<const float*>(s.tape_slot), 2, s.x_a, 1, st, i_host);
 }
 static inline bool correction_gate(int correction, int i) { return correction && i <= 500 && (i % 50 == 0); }   // eval_smpl_short.py:86-88
 
@@ -241,7 +243,7 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
                 int r = idb_denoiser_tokens(h, s.x_a, nullptr, cs);
                 for (int i = n - 1; i >= 0 && !r; i--) {
                     if (!correction_gate(correction, i)) r = plain_step(h, s, g_gt, g_mask, cs, i);
-                    else { r = predict_part(h, s, g_gt, g_mask, cs); if (!r) r = correction_tail(h, s, g_gt, i, cs); }
+                    else { r = predict_part(h, s, g_gt, g_mask, cs); if (!r) r = correction_tail(h, s, g_gt, i, cs, i); }
                 }
                 return r;
             });
@@ -278,7 +280,7 @@ extern "C" int idb_p_sample_loop(idb_handle* h, const float* tape, const float* 
                 CUDA_TRY(h, cudaGraphLaunch(s.predict_graph, st));
                 h->launches += s.launches_per_predict;
             } else if ((rc = predict_part(h, s, g_gt, g_mask, st))) return rc;
-            if ((rc = correction_tail(h, s, g_gt, i, st))) return rc;
+            if ((rc = correction_tail(h, s, g_gt, i, st, graph_ok ? -1 : i))) return rc;
         }
     }
     CUDA_TRY(h, cudaMemcpyAsync(x_out, s.x_a, numel * sizeof(float), cudaMemcpyDefault, st));

@@ -48,5 +48,17 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_tools():
+    """Stand-alone micro-benchmarks under profiles/ (not part of the library): the cluster-exchange benchmark."""
+    src = os.path.join(HERE, "..", "profiles", "dsmem_bench.cu")
+    out = os.path.join(HERE, "build", "dsmem_bench")
+    if not os.path.exists(src) or (os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src)):
+        return out
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-o", out, src])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))

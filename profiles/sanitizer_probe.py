@@ -13,6 +13,8 @@ from tests.helpers import encoder_weights, metrics_inputs, projector_weights  # 
 
 B, T, steps = 3, 30, 3
 eng = Engine("cuda:0")
+if os.environ.get("IDB_SPLIT_ATTN"):      # standard layers' self- / cross-attention as two launches (racecheck cannot see that the fused
+    eng.set_fused_mlp(10)                 # kernel's two staging phases on the same shared memory are ordered by mbarrier waits)
 eng.load_denoiser(encoder_weights("random"), "smpl")
 smplh = S.make_smplh_model(233)
 eng.load_body(smplh)

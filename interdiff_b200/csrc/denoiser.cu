@@ -661,9 +661,11 @@ struct QanArgs {
 };
 // the slab (sample b, rows r0 .. r0 + 15) of the kernel below as a device function on caller-provided shared memory `sm`
 // (16-byte aligned, qan_smem() bytes): also phase A of the fused decoder-layer kernel
-template <bool XATTN>
+// PRELN = false: instantiated without the pending-LayerNorm code (the fused feed-forward kernel applies the previous layer's
+// norm3 itself, so the hot path never has one pending; a skipped block of ~150 instructions still costs its instruction fetches)
+template <bool XATTN, bool PRELN = true>
 __device__ __forceinline__ void qan_xattn_body(const QanArgs& qa, float* sm, const int b, const int r0) {
-    const float* __restrict__ zin = qa.zin; const float* __restrict__ prew = qa.prew; const float* __restrict__ preb = qa.preb;
+    const float* __restrict__ zin = qa.zin; const float* __restrict__ prew = PRELN ? qa.prew : nullptr; const float* __restrict__ preb = qa.preb;
     const float* __restrict__ wk = qa.wk;
     const float* __restrict__ lnw = qa.lnw; const float* __restrict__ lnb = qa.lnb;
     const float* __restrict__ bo2 = qa.bo2; const float* __restrict__ ln2w = qa.ln2w;
@@ -831,12 +833,12 @@ __device__ __forceinline__ void qan_xattn_body(const QanArgs& qa, float* sm, con
     ATRACE(11);
 }
 
-template <bool XATTN>
+template <bool XATTN, bool PRELN = true>
 __global__ void __launch_bounds__(ANT)
 k_qan_xattn_ln(const QanArgs qa) {
     extern __shared__ __align__(16) float sm[];
     if (threadIdx.x == 0) chain_mark(3, 0);
-    qan_xattn_body<XATTN>(qa, sm, blockIdx.x, blockIdx.y * SLAB);
+    qan_xattn_body<XATTN, PRELN>(qa, sm, blockIdx.x, blockIdx.y * SLAB);
     if (c_chain) { __syncthreads(); if (threadIdx.x == 0) chain_mark(3, 2); }
 }
 
@@ -1628,7 +1630,8 @@ static int denoiser_layers(idb_handle* h, cudaStream_t st) {
                 continue;
             }
             // QaN block + LN1 + cross-attention + LN2 in one kernel: (z | h) -> (d.h2, pairs)
-            idb_launch(pdl, k_qan_xattn_ln<true>, slab_grid, ANT, qan_smem(Tm, H), st, qa);
+            if (pending) idb_launch(pdl, k_qan_xattn_ln<true, true>, slab_grid, ANT, qan_smem(Tm, H), st, qa);
+            else idb_launch(pdl, k_qan_xattn_ln<true, false>, slab_grid, ANT, qan_smem(Tm, H), st, qa);
             LAUNCH_CHECK(h);
         } else {
             if (pending) {
@@ -1787,7 +1790,8 @@ int idb_denoiser_run(idb_handle* h, const float* x, const long long* tstep, cons
 
 int idb_denoiser_prepare_kernels(idb_handle* h) {
     // opt in to > 48 KB dynamic shared memory once (T <= 36, Tm <= 16 supported: the self-attention slab kernel keeps all folded values of a sample, 4*T*256 floats, in shared memory)
-    CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem(16, 4)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem(16, 4)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_smem(16, 4)));
     CUDA_TRY(h, cudaFuncSetAttribute(k_layer_qan_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::mlp::SMEM_BYTES));
     CUDA_TRY(h, cudaFuncSetAttribute(k_layer_std_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::mlp::SMEM_BYTES));
     CUDA_TRY(h, cudaFuncSetAttribute(k_qan_xattn_ln<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qan_enc_smem()));

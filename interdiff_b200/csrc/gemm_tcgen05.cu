@@ -93,23 +93,19 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (!MC) {
-            // The first pipeline fill is requested right here, by the thread that initialised the barriers, before the TMEM
-            // allocation and the CTA barrier: the weight tiles (they do not depend on the previous kernel) at once, the
-            // activation tiles after the dependency wait.  A CTA that only got its SM when the previous kernel's CTAs left has
-            // nothing to overlap its prologue with, so the sooner the first bytes are on their way the better.
-            for (int kb = 0; kb < npre; kb++) {
-                const uint32_t dst = base + kb * cfg::STAGE_BYTES;
-                mbar_arrive_expect_tx(bar_full(kb), cfg::STAGE_BYTES);
-                tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(kb), (kb0 + kb) * BK, n0);
-                tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(kb), (kb0 + kb) * BK, n0);
-            }
+            // The FIRST stage is requested right here, by the thread that initialised the barriers, before the TMEM
+            // allocation and the CTA barrier: its weight tile (it does not depend on the previous kernel) at once, its activation
+            // tile after the dependency wait; the producer warp requests the other stages after the barrier, while the MMA
+            // warp already waits for this one.  A CTA that only got its SM when the previous kernel's CTAs left has nothing to
+            // overlap its prologue with, so the sooner the first bytes are on their way - and the shorter the path to the
+            // barrier - the better (gemm_trace.py: the barrier used to sit behind the requests of all four stages, 1.9 K cycles).
+            mbar_arrive_expect_tx(bar_full(0), cfg::STAGE_BYTES);
+            tma_load_2d(base + cfg::A_BYTES, &map_w, bar_full(0), kb0 * BK, n0);
+            tma_load_2d(base + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(0), kb0 * BK, n0);
             pdl_wait();
             chain_mark(1, 1);
-            for (int kb = 0; kb < npre; kb++) {
-                const uint32_t dst = base + kb * cfg::STAGE_BYTES;
-                tma_load_2d(dst, &map_a, bar_full(kb), (kb0 + kb) * BK, m0);
-                tma_load_2d(dst + cfg::HALF_BYTES, &map_al, bar_full(kb), (kb0 + kb) * BK, m0);
-            }
+            tma_load_2d(base, &map_a, bar_full(0), kb0 * BK, m0);
+            tma_load_2d(base + cfg::HALF_BYTES, &map_al, bar_full(0), kb0 * BK, m0);
         } else {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
@@ -137,6 +133,19 @@ gemm_split_f16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // ===================== TMA producer =====================
         // (multicast pairs only; otherwise the first fill was requested by thread 0 above)  The weight tiles of the first
         // pipeline fill do not depend on the previous kernel: requested before the dependency wait, the activation tiles after.
+        if (!MC) {
+            if (elect_one()) {
+                for (int kb = 1; kb < npre; kb++) {      // the rest of the first pipeline fill (stage 0: thread 0 above)
+                    const uint32_t dst = base + kb * cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(bar_full(kb), cfg::STAGE_BYTES);
+                    tma_load_2d(dst + cfg::A_BYTES, &map_w, bar_full(kb), (kb0 + kb) * BK, n0);
+                    tma_load_2d(dst + cfg::HALF_BYTES + cfg::A_BYTES, &map_wl, bar_full(kb), (kb0 + kb) * BK, n0);
+                    tma_load_2d(dst, &map_a, bar_full(kb), (kb0 + kb) * BK, m0);
+                    tma_load_2d(dst + cfg::HALF_BYTES, &map_al, bar_full(kb), (kb0 + kb) * BK, m0);
+                }
+            }
+            __syncwarp();
+        }
         if (MC) {
             if (elect_one()) {
                 for (int kb = 0; kb < npre; kb++) {

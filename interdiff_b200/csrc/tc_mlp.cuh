@@ -181,15 +181,10 @@ __device__ __forceinline__ uint32_t mlp_setup(uint8_t* smem_raw, const MlpArgs& 
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + RING + S_BYTES + TMEM_SLOT_OFF);
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; s++) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (2 + s), 1); mbar_init(bars + 8u * (5 + s), 1); }
-        mbar_init(bars + 8u * 4, 1); mbar_init(bars + 8u * 8, 1);
-        mbar_init(bars + 8u * 7, EW * 32); mbar_init(bars + 8u * 9, EW * 32);
-        for (int s = 0; s < 2; s++) { mbar_init(bars + 8u * (10 + s), 1); mbar_init(bars + 8u * (13 + s), 1); mbar_init(bars + 8u * (15 + s), 1); }
-        mbar_init(bars + 8u * 12, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // the partner's copies of its S k-blocks complete on these four (16 KB each: hi / lo of a k-block)
-        for (int s = 0; s < 4; s++) mbar_arrive_expect_tx(bars + 8u * (13 + s), 16384u);
         if (EARLY) {
+            // the two "operands landed" barriers of GEMM 1 first, so that the first requests leave before the other 15 barriers exist
+            mbar_init(bars, 1); mbar_init(bars + 8u, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             for (int kb = 0; kb < 2; kb++) {
                 const uint32_t dst = base + kb * STAGE1;
                 mbar_arrive_expect_tx(bars + 8u * kb, STAGE1);
@@ -203,7 +198,16 @@ __device__ __forceinline__ uint32_t mlp_setup(uint8_t* smem_raw, const MlpArgs& 
                 tma_load_2d(dst, a.map_x, bars + 8u * kb, kb * BK, m0);
                 tma_load_2d(dst + 32768, a.map_xl, bars + 8u * kb, kb * BK, m0);
             }
-        } else {
+        }
+        for (int s = 0; s < 2; s++) { if (!EARLY) mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (2 + s), 1); mbar_init(bars + 8u * (5 + s), 1); }
+        mbar_init(bars + 8u * 4, 1); mbar_init(bars + 8u * 8, 1);
+        mbar_init(bars + 8u * 7, EW * 32); mbar_init(bars + 8u * 9, EW * 32);
+        for (int s = 0; s < 2; s++) { mbar_init(bars + 8u * (10 + s), 1); mbar_init(bars + 8u * (13 + s), 1); mbar_init(bars + 8u * (15 + s), 1); }
+        mbar_init(bars + 8u * 12, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the partner's copies of its S k-blocks complete on these four (16 KB each: hi / lo of a k-block)
+        for (int s = 0; s < 4; s++) mbar_arrive_expect_tx(bars + 8u * (13 + s), 16384u);
+        if (!EARLY) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_x) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_w1) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(a.map_xl) : "memory");

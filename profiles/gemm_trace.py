@@ -15,7 +15,10 @@ P = lambda t: C.c_void_p(t.data_ptr())
 names = ["entry", "setup_done", "tma_first_issued", "tma_all_issued", "conv_first_full", "conv_first_done", "mma_first_ready",
          "mma_all_issued", "conv_all_done", "epi_acc_ready", "epi_done", "final_sync", "dealloc"]
 show = ("setup_done", "tma_first_issued", "tma_all_issued", "mma_first_ready", "mma_all_issued", "epi_acc_ready", "epi_done", "dealloc")
-for (M, N, K), flags in itertools.product(((1920, 1024, 256), (1920, 256, 1024), (1920, 256, 256)), (0, 64)):
+shapes = ((1920, 1024, 256), (1920, 256, 1024), (1920, 256, 256), (1920, 1536, 256), (1920, 256, 152), (1920, 144, 256))   # .., QKV', embedding, heads
+for (M, N, K), flags in itertools.product(shapes, (0, 64)):
+    if flags and N != 1024:
+        continue
     eng.lib.idb_debug_set_gemm_accumulators(1000 + flags)
     A = torch.randn(M, K, device="cuda")
     W = torch.randn(N, K, device="cuda") / K ** 0.5

@@ -16,15 +16,16 @@ ncu --set full --clock-control none --import-source on -k regex:k_lbs_skin_spars
 ncu --set full --clock-control none --import-source on -k regex:gemm_split_f16 -c 1 -o gpurun_out/ev2_ncu_lbsgemm python profiles/lbs_only.py > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_signed_nn_pruned -c 1 -o gpurun_out/ev2_ncu_nn python profiles/corr_step_only.py > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_projector -c 1 -o gpurun_out/ev2_ncu_proj python profiles/corr_step_only.py > /dev/null 2>&1
-for k in k_qan_xattn_ln k_attn_xattn_ln; do
-  ncu --set full --clock-control none --import-source on -k regex:^$k -s 4 -c 1 -o gpurun_out/ev2_ncu_$k python profiles/step_probe.py 2 > /dev/null 2>&1
-done
+ncu --set full --clock-control none --import-source on -k regex:^k_qan_xattn_ln -s 4 -c 1 -o gpurun_out/ev2_ncu_k_qan_xattn_ln python profiles/step_probe.py 2 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:^k_attn_xattn_ln -s 1 -c 1 -o gpurun_out/ev2_ncu_k_attn_xattn_ln python profiles/step_probe.py 2 > /dev/null 2>&1
 # the folded QKV projection is the only GEMM on 192-column tiles
 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:gemm_split_f16_kernelILi192 -s 1 -c 1 -o gpurun_out/ev2_ncu_qkvgemm python profiles/step_probe.py 2 > /dev/null 2>&1
 python profiles/mlp_trace.py > gpurun_out/ev2_mlp_trace.txt 2>&1
 python profiles/chain_probe.py 64 12 loop > gpurun_out/ev2_chain_probe.txt 2>&1
 python profiles/chain_probe.py 8 12 loop > gpurun_out/ev2_chain_probe_b8.txt 2>&1
 interdiff_b200/build/dsmem_bench > gpurun_out/ev2_dsmem_bench.txt 2>&1
+python profiles/gemm_trace.py > gpurun_out/ev2_gemm_trace.txt 2>&1
+python profiles/attn_trace.py > gpurun_out/ev2_attn_timeline.txt 2>&1
 python profiles/fused_layer_probe.py > gpurun_out/ev2_fused_layer_probe.txt 2>&1
 python profiles/r2_probe.py --config3 > gpurun_out/ev2_probe.txt 2>&1
 cut -c1-300 gpurun_out/ev2_bench_c2.json; tail -3 gpurun_out/ev2_bench.err; cat gpurun_out/ev2_smoke.txt | tail -2

@@ -122,9 +122,9 @@ constexpr int RING = 2 * STAGE1;
 constexpr int S_BYTES = 64 * 1024;            // S_hi [2][16K] | S_lo [2][16K]
 constexpr int W2SLOT = 32 * 1024;             // W2 k-block: hi [128 rows][128 B] | lo
 constexpr int PLD = NH + 4;                   // fp32 partial row stride (floats)
-constexpr int SMEM_BYTES = RING + S_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers, tmem slot, LayerNorm partial sums*/;
+constexpr int SMEM_BYTES = RING + S_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers, tmem slot*/;
 // barriers (8 B each, above the operand region): full1[2] 0,1 | empty1[2] 2,3 | acc1 4 | w2full[2] 5,6 | s_ready[0] 7 | acc2 8 |
-// s_ready[1] 9 | w2empty[2] 10,11 | peer_free 12 | peer_s hi[2] 13,14 | peer_s lo[2] 15,16 ; tmem slot at 8*17 ; LayerNorm sums from +256
+// s_ready[1] 9 | w2empty[2] 10,11 | peer_free 12 | peer_s hi[2] 13,14 | peer_s lo[2] 15,16 ; tmem slot at 8*17
 constexpr int TMEM_SLOT_OFF = 8 * 17;
 }  // namespace mlp
 
@@ -228,7 +228,7 @@ __device__ __forceinline__ uint32_t mlp_setup(uint8_t* smem_raw, const MlpArgs& 
 
 // The feed-forward block of one 128-row tile on the cluster's 8 CTAs (see the comment above).  j = rank in the cluster =
 // hidden chunk; m0 = first row of the tile; rows >= row_end are neither reduced nor stored (row_end <= M; a tile may hold
-// fewer than 128 live rows when the caller aligns tiles to samples).  Warps 0 / 1 = TMA producer / MMA issuer, warps 2..9 =
+// fewer than 128 live rows when the caller aligns tiles to samples).  Warps 0 / 1 = TMA producer / MMA issuer, warps 2 .. 1 + EW =
 // epilogue; any further warps of the CTA only take part in the cluster barriers.  wait_dep: execute griddepcontrol.wait
 // before the first dependent access (stand-alone launch); a caller that has already waited passes false.
 template <int EW, bool EARLY = false>
@@ -428,7 +428,7 @@ __device__ __forceinline__ void mlp_run(uint8_t* smem_raw, const MlpArgs& a, int
         }
         if (lane == 0) MTRACE(7);
     } else if (warp < 2 + EW) {
-        // ===================== epilogue warps 2..9 =====================
+        // ===================== epilogue warps 2 .. 1 + EW =====================
         const int q = warp & 3, ew = warp - 2;       // TMEM lane quarter, 0..7
         const int r = q * 32 + lane;                 // tile row owned by this thread
         CLUSTER_WAIT();
